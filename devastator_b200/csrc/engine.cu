@@ -1,0 +1,758 @@
+// engine.cu - kernels, window driver and C ABI of the B200 optimistic PDES engine.
+//
+// One engine = one GPU.  The drain loop (deva_b200_drain) replaces pdes::drain's main loop
+// (pdes.cxx:695-1058): instead of "pop the globally earliest LP from a heap, run one event,
+// nurse an asynchronous GVT reduction", every optimistic window is ONE launch of k_pass over all
+// LPs (pdes_core.cuh), whose block+grid min-reduction of everything left pending IS the next GVT
+// (replaces gvt.cxx:53-149 - with a synchronous window there are no messages in flight at the
+// reduction point, so the epoch/credit machinery collapses to a min).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/deva_b200.h"
+#include "pdes_core.cuh"
+#include "window_policy.h"
+
+using namespace deva_b200;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(DEVA_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+constexpr int PASS_THREADS = 128;
+
+template <class M>
+__global__ void __launch_bounds__(PASS_THREADS) k_pass(View v, ModelParams mp, PassArgs pa) {
+  const uint32_t lp = blockIdx.x * PASS_THREADS + threadIdx.x;
+  Acc acc;
+  acc.tmin = ~0ull;
+  acc.executed = acc.committed = acc.rolled = acc.anti = acc.remote = acc.err = acc.nondet = 0;
+  if (lp < v.A) lp_pass<M>(v, mp, pa, lp, acc);
+
+  // block reduction: min for the GVT candidate, sums for the counters, or for the flags
+  unsigned long long tmin = acc.tmin;
+  uint32_t ex = acc.executed, cm = acc.committed, rb = acc.rolled, an = acc.anti, rm = acc.remote;
+  uint32_t fl = acc.err | (acc.nondet << 31);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, tmin, o);
+    tmin = t2 < tmin ? t2 : tmin;
+    ex += __shfl_xor_sync(0xffffffffu, ex, o);
+    cm += __shfl_xor_sync(0xffffffffu, cm, o);
+    rb += __shfl_xor_sync(0xffffffffu, rb, o);
+    an += __shfl_xor_sync(0xffffffffu, an, o);
+    rm += __shfl_xor_sync(0xffffffffu, rm, o);
+    fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+  }
+  __shared__ unsigned long long s_t[PASS_THREADS / 32];
+  __shared__ uint32_t s_c[PASS_THREADS / 32][6];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_t[w] = tmin; s_c[w][0] = ex; s_c[w][1] = cm; s_c[w][2] = rb; s_c[w][3] = an; s_c[w][4] = rm; s_c[w][5] = fl; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < PASS_THREADS / 32; i++) {
+      tmin = s_t[i] < tmin ? s_t[i] : tmin;
+      ex += s_c[i][0]; cm += s_c[i][1]; rb += s_c[i][2]; an += s_c[i][3]; rm += s_c[i][4]; fl |= s_c[i][5];
+    }
+    Ctl *c = v.ctl;
+    if (tmin != ~0ull) atomicMin(&c->gvt_next, tmin);
+    if (ex) atomicAdd(&c->executed, (unsigned long long)ex);
+    if (cm) atomicAdd(&c->committed, (unsigned long long)cm);
+    if (rb) atomicAdd(&c->rolled_back, (unsigned long long)rb);
+    if (an) atomicAdd(&c->anti_sent, (unsigned long long)an);
+    if (rm) atomicAdd(&c->remote_sent, (unsigned long long)rm);
+    if (fl & 0x7fffffffu) atomicOr(&c->err, fl & 0x7fffffffu);
+    if (fl >> 31) atomicOr(&c->nondeterministic, 1u);
+  }
+}
+
+// records -> pending slots (roots, inbox spill, records received from peer GPUs)
+__global__ void k_deliver(View v, const EvRec *recs, const uint32_t *n_ptr, uint32_t n_fixed) {
+  const uint32_t n = n_ptr ? *n_ptr : n_fixed;
+  unsigned long long tmin = ~0ull;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const EvRec r = ld_ev(&recs[i]);
+    deliver_to_pending(v, r, &v.ctl->err);
+    tmin = r.time < tmin ? r.time : tmin;
+  }
+  // delivered records are pending: they bound the GVT (matters for roots; spill / peer records
+  // were already folded in by their sender)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, tmin, o);
+    tmin = t2 < tmin ? t2 : tmin;
+  }
+  if ((threadIdx.x & 31) == 0 && tmin != ~0ull) atomicMin(&v.ctl->gvt_next, tmin);
+}
+
+__global__ void k_min_head(View v) {
+  unsigned long long tmin = ~0ull;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < v.A; i += gridDim.x * blockDim.x) {
+    const unsigned long long h = v.head[i];
+    tmin = h < tmin ? h : tmin;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, tmin, o);
+    tmin = t2 < tmin ? t2 : tmin;
+  }
+  if ((threadIdx.x & 31) == 0 && tmin != ~0ull) atomicMin(&v.ctl->gvt_next, tmin);
+}
+
+template <class M>
+__global__ void k_init(View v, ModelParams mp, int init_state) {
+  const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp >= v.A) return;
+  const uint64_t gid = v.lp_begin + lp;
+  v.head[lp] = ~0ull;
+  v.pcnt[lp] = 0;
+  v.icnt[0][lp] = 0;
+  v.icnt[1][lp] = 0;
+  v.lmeta[lp] = 0;
+  v.seq[lp] = gid;      // pdes.cxx:332: seq_id_bumper = global_cd_begin + i
+  v.lct[lp] = 0;        // pdes.cxx:333
+  v.lcs[lp] = 0;
+  uint64_t s[MAX_STW] = {0, 0, 0};
+  if (init_state) M::init_state(mp, gid, s);
+  for (int w = 0; w < M::STW; w++) v.st[(size_t)w * v.A + lp] = s[w];
+}
+
+// K roots per LP written straight into the LP's pending slots (no atomics: the owner writes).
+template <class M>
+__global__ void k_seed_roots(View v, ModelParams mp, uint32_t k, int rootdiv, uint64_t per_rank) {
+  const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp >= v.A) return;
+  const uint64_t gid = v.lp_begin + lp;
+  uint64_t head = ~0ull;
+  // LPs past the model's actor count exist only as padding of the rank decomposition
+  // (ranks*ceil(actor_n/ranks) > actor_n, test/phold.cxx:46): they get no roots
+  if (gid >= mp.lp_n_model) k = 0;
+  for (uint32_t j = 0; j < k; j++) {
+    EvRec e;
+    uint64_t ray;
+    if (M::MODEL_ID == 2) {          // bench/phold.cxx:154-157
+      ray = gid * k + j;
+      e.time = ray;
+    } else {                         // test/phold.cxx:172-178, PHOLD-T root time
+      ray = gid + (uint64_t)j * mp.lp_n_model;
+      e.time = rootdiv ? j : ray;
+    }
+    e.sub = mp.user_subtime ? ray : gid % per_rank;   // pdes.hxx:907: root subtime = LOCAL cd index
+    e.p0 = (uint32_t)ray; e.p1 = 0; e.dst = (uint32_t)gid; e.flags = 0;
+    st_ev(&v.pq[(size_t)j * v.A + lp], e);
+    head = e.time < head ? e.time : head;
+  }
+  v.pcnt[lp] = k;
+  v.head[lp] = head;
+}
+
+// AoS host layout [count][STW]  <->  SoA device layout [STW][A]
+__global__ void k_state_scatter(View v, const uint64_t *aos, uint32_t first, uint32_t count, int stw, int to_device) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  for (int w = 0; w < stw; w++) {
+    if (to_device) v.st[(size_t)w * v.A + first + i] = aos[(size_t)i * stw + w];
+    else const_cast<uint64_t *>(aos)[(size_t)i * stw + w] = v.st[(size_t)w * v.A + first + i];
+  }
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+  return x;
+}
+__global__ void k_digest(View v, int stw, unsigned long long *out) {
+  unsigned long long x = 0, h = 0, pn = 0, ph = 0;
+  for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < v.A; lp += gridDim.x * blockDim.x) {
+    const uint64_t gid = v.lp_begin + lp;
+    x ^= v.st[(size_t)(stw - 1) * v.A + lp];
+    for (int w = 0; w < stw; w++) h += mix64(v.st[(size_t)w * v.A + lp] ^ mix64(gid * 4 + w + 1));
+    const uint32_t np = v.pcnt[lp];
+    pn += np;
+    for (uint32_t s = 0; s < np; s++) {
+      const EvRec e = ld_ev(&v.pq[(size_t)s * v.A + lp]);
+      ph += mix64(e.time ^ mix64(e.sub ^ mix64(((uint64_t)e.p0 << 32 | e.dst) + e.flags)));
+    }
+  }
+  atomicXor(&out[0], x);
+  atomicAdd(&out[1], h);
+  atomicAdd(&out[2], pn);
+  atomicAdd(&out[3], ph);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily (only multi-GPU jobs need it)
+struct NcclUid { char b[128]; };
+struct Nccl {
+  void *lib = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, NcclUid /*ncclUniqueId by value, 128 B*/, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static Nccl g_nccl;
+static int nccl_load() {
+  if (g_nccl.lib) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return fail(DEVA_B200_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                  \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name);                                    \
+  if (!g_nccl.field) return fail(DEVA_B200_ERR_COMM, "libnccl lacks symbol %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return 0;
+}
+#define NC(call)                                                                                           \
+  do {                                                                                                     \
+    int _r = (call);                                                                                       \
+    if (_r != 0) return fail(DEVA_B200_ERR_COMM, "%s failed: %s", #call, g_nccl.GetErrorString(_r));       \
+  } while (0)
+// nccl.h enums (stable ABI): ncclUint8=1, ncclUint32=3, ncclUint64=5; ncclSum=0, ncclMin=3, ncclMax=2
+enum { NC_U8 = 1, NC_U32 = 3, NC_U64 = 5, NC_SUM = 0, NC_MAX = 2, NC_MIN = 3 };
+
+// ------------------------------------------------------------------------------------------------
+struct deva_b200_engine {
+  deva_b200_config cfg;
+  ModelParams mp;
+  View v;
+  int stw = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
+  std::vector<void *> allocs;
+  Ctl *h_ctl = nullptr;            // pinned mirror
+  unsigned long long *d_digest = nullptr;
+  uint32_t par = 0;
+  uint64_t gvt = 0;
+  WindowPolicy wp;
+  // cumulative statistics (pdes::local_stats since init)
+  uint64_t executed = 0, committed = 0, rolled = 0, anti = 0, remote = 0, passes = 0;
+  bool nondet = false;
+  double drain_ms = 0, exec_ms = 0;
+  // rewind snapshot (pdes.cxx:710-739): LP state, seq counters, last-commit keys, pending set
+  bool has_rewind = false;
+  std::vector<std::pair<void *, void *>> snap_pairs;  // (live, snapshot)
+  std::vector<size_t> snap_bytes;
+  uint64_t snap_gvt = 0;
+  // multi-GPU
+  void *comm = nullptr;
+  EvRec *recvbuf = nullptr;
+  uint32_t *d_counts = nullptr;    // [2][MAX_GPUS]: send counts row, recv counts row
+  uint32_t *h_counts = nullptr;    // pinned
+  unsigned long long *d_red = nullptr;  // allreduce scratch
+  bool profile = true;
+};
+
+template <class T>
+static int dalloc(deva_b200_engine *e, T **p, size_t n) {
+  void *q = nullptr;
+  cudaError_t r = cudaMalloc(&q, n * sizeof(T));
+  if (r != cudaSuccess)
+    return fail(DEVA_B200_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(r));
+  e->allocs.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+
+static const char *err_text(uint32_t err) {
+  static thread_local char buf[256];
+  buf[0] = 0;
+  if (err & ERR_PQ_OVERFLOW) strcat(buf, "pending slots of an LP overflowed (raise pq_cap); ");
+  if (err & ERR_LOG_STALL) strcat(buf, "undo log stalled; ");
+  if (err & ERR_ANTI_UNMATCHED) strcat(buf, "anti-message without matching event; ");
+  if (err & ERR_SELF_CHILD_LOST) strcat(buf, "self-sent child not found on rollback; ");
+  if (err & ERR_SPILL_OVERFLOW) strcat(buf, "inbox spill buffer overflowed (raise inbox_cap); ");
+  if (err & ERR_SEND_OVERFLOW) strcat(buf, "peer staging buffer overflowed; ");
+  if (err & ERR_NOT_OWNER) strcat(buf, "event addressed to an LP this engine does not own; ");
+  if (err & ERR_BELOW_GVT) strcat(buf, "rollback reached below GVT; ");
+  return buf;
+}
+
+template <class F>
+static auto dispatch_model(int model, F &&f) {
+  if (model == DEVA_B200_MODEL_PHOLD_BENCH) return f(PholdBench{});
+  return f(PholdTest{});
+}
+
+extern "C" {
+
+const char *deva_b200_last_error(void) { return g_err; }
+int deva_b200_abi_version(void) { return DEVA_B200_ABI_VERSION; }
+int deva_b200_state_words(const deva_b200_engine *e) { return e ? e->stw : 0; }
+
+int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
+  if (!cfg || !out) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (cfg->abi_version != DEVA_B200_ABI_VERSION) return fail(DEVA_B200_ERR_ARG, "ABI version mismatch");
+  if (cfg->model != DEVA_B200_MODEL_PHOLD_TEST && cfg->model != DEVA_B200_MODEL_PHOLD_BENCH)
+    return fail(DEVA_B200_ERR_ARG, "unknown model %d", cfg->model);
+  if (cfg->lp_count == 0 || cfg->lp_count > 0x7fffffffull || cfg->lp_begin + cfg->lp_count > cfg->lp_n ||
+      cfg->lp_n > 0xffffffffull)
+    return fail(DEVA_B200_ERR_ARG, "bad LP partition");
+  if (cfg->n_gpus < 1 || cfg->n_gpus > MAX_GPUS || cfg->gpu_rank < 0 || cfg->gpu_rank >= cfg->n_gpus)
+    return fail(DEVA_B200_ERR_ARG, "bad n_gpus/gpu_rank");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(DEVA_B200_ERR_CUDA, "no CUDA device: this engine has no CPU path");
+  CU(cudaSetDevice(cfg->device));
+  deva_b200_engine *e = new deva_b200_engine;
+  e->cfg = *cfg;
+  e->stw = cfg->model == DEVA_B200_MODEL_PHOLD_BENCH ? PholdBench::STW : PholdTest::STW;
+  e->mp.lp_n_model = cfg->mp.lp_n_model;
+  e->mp.p_remote_thresh = cfg->mp.p_remote_thresh;
+  e->mp.neg_lambda = -cfg->mp.lambda;
+  e->mp.end_time = cfg->mp.end_time;
+  e->mp.user_subtime = cfg->mp.user_subtime;
+  e->mp.bench_lp_per_rank = cfg->mp.bench_lp_per_rank;
+  e->mp.bench_peer_stddev = cfg->mp.bench_peer_stddev;
+  e->mp.stop = 0;
+  View &v = e->v;
+  memset(&v, 0, sizeof v);
+  v.A = (uint32_t)cfg->lp_count;
+  v.pq_cap = cfg->pq_cap > 0 ? cfg->pq_cap : 64;
+  v.ib_cap = cfg->inbox_cap > 0 ? cfg->inbox_cap : 16;
+  v.log_cap = cfg->log_cap > 0 ? cfg->log_cap : 48;
+  if (v.log_cap > 65535) return fail(DEVA_B200_ERR_ARG, "log_cap must be < 65536");
+  v.lp_begin = cfg->lp_begin;
+  v.lp_n = cfg->lp_n;
+  v.n_gpus = cfg->n_gpus;
+  v.gpu_rank = cfg->gpu_rank;
+  v.lp_per_gpu = (cfg->lp_n + cfg->n_gpus - 1) / cfg->n_gpus;
+  const size_t A = v.A;
+  int rc = 0;
+#define DA(p, n) if ((rc = dalloc(e, &(p), (n)))) { deva_b200_destroy(e); return rc; }
+  DA(v.head, A) DA(v.pcnt, A) DA(v.icnt[0], A) DA(v.icnt[1], A) DA(v.lmeta, A)
+  DA(v.st, A * e->stw) DA(v.seq, A) DA(v.lct, A) DA(v.lcs, A)
+  DA(v.pq, A * v.pq_cap) DA(v.ib[0], A * v.ib_cap) DA(v.ib[1], A * v.ib_cap) DA(v.lg, A * v.log_cap)
+  DA(v.ctl, 1)
+  v.spill_cap = (uint32_t)std::min<size_t>(std::max<size_t>(A * 2, 1u << 16), 1u << 26);
+  DA(v.spill, v.spill_cap)
+  DA(e->d_digest, 4)
+  if (cfg->n_gpus > 1) {
+    // staging sized for one window's worth of cross-GPU records per peer
+    v.send_cap = (uint32_t)std::min<size_t>(std::max<size_t>(A * 4, 1u << 16), 1u << 27);
+    DA(v.sendbuf, (size_t)v.send_cap * cfg->n_gpus)
+    DA(e->recvbuf, (size_t)v.send_cap * cfg->n_gpus)
+    DA(e->d_counts, 2 * MAX_GPUS)
+    DA(e->d_red, 8)
+    CU(cudaHostAlloc((void **)&e->h_counts, 2 * MAX_GPUS * sizeof(uint32_t), cudaHostAllocDefault));
+  }
+#undef DA
+  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&e->ev_a));
+  CU(cudaEventCreate(&e->ev_b));
+  CU(cudaEventCreate(&e->ev_d0));
+  CU(cudaEventCreate(&e->ev_d1));
+  CU(cudaHostAlloc((void **)&e->h_ctl, sizeof(Ctl), cudaHostAllocDefault));
+  CU(cudaMemsetAsync(v.ctl, 0, sizeof(Ctl), e->stream));
+  const int grid = (int)((A + 255) / 256);
+  dispatch_model(cfg->model, [&](auto m) {
+    using M = decltype(m);
+    k_init<M><<<grid, 256, 0, e->stream>>>(v, e->mp, 0);
+    return 0;
+  });
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));
+  e->wp.init(cfg->window);
+  const char *prof = getenv("DEVA_B200_PROFILE");
+  if (prof) e->profile = atoi(prof) != 0;
+  // snapshot list for rewind
+  *out = e;
+  return 0;
+}
+
+void deva_b200_destroy(deva_b200_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  for (auto &p : e->snap_pairs) cudaFree(p.second);
+  for (void *p : e->allocs) cudaFree(p);
+  if (e->h_ctl) cudaFreeHost(e->h_ctl);
+  if (e->h_counts) cudaFreeHost(e->h_counts);
+  if (e->ev_a) cudaEventDestroy(e->ev_a);
+  if (e->ev_b) cudaEventDestroy(e->ev_b);
+  if (e->ev_d0) cudaEventDestroy(e->ev_d0);
+  if (e->ev_d1) cudaEventDestroy(e->ev_d1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int deva_b200_set_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t count, const uint64_t *words) {
+  if (!e || !words) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (lp_first < e->v.lp_begin || lp_first + count > e->v.lp_begin + e->v.A) return fail(DEVA_B200_ERR_ARG, "LP range not owned");
+  if (count == 0) return 0;
+  CU(cudaSetDevice(e->cfg.device));
+  uint64_t *tmp = nullptr;
+  CU(cudaMalloc((void **)&tmp, count * e->stw * 8));
+  CU(cudaMemcpyAsync(tmp, words, count * e->stw * 8, cudaMemcpyHostToDevice, e->stream));
+  k_state_scatter<<<(unsigned)((count + 255) / 256), 256, 0, e->stream>>>(e->v, tmp, (uint32_t)(lp_first - e->v.lp_begin), (uint32_t)count, e->stw, 1);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaFree(tmp));
+  return 0;
+}
+
+int deva_b200_get_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t count, uint64_t *words) {
+  if (!e || !words) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (lp_first < e->v.lp_begin || lp_first + count > e->v.lp_begin + e->v.A) return fail(DEVA_B200_ERR_ARG, "LP range not owned");
+  if (count == 0) return 0;
+  CU(cudaSetDevice(e->cfg.device));
+  uint64_t *tmp = nullptr;
+  CU(cudaMalloc((void **)&tmp, count * e->stw * 8));
+  k_state_scatter<<<(unsigned)((count + 255) / 256), 256, 0, e->stream>>>(e->v, tmp, (uint32_t)(lp_first - e->v.lp_begin), (uint32_t)count, e->stw, 0);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(words, tmp, count * e->stw * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaFree(tmp));
+  return 0;
+}
+
+static int check_ctl_err(deva_b200_engine *e) {
+  const uint32_t err = e->h_ctl->err;
+  if (!err) return 0;
+  const int code = (err & (ERR_PQ_OVERFLOW | ERR_SPILL_OVERFLOW | ERR_SEND_OVERFLOW)) ? DEVA_B200_ERR_CAPACITY : DEVA_B200_ERR_INVARIANT;
+  return fail(code, "engine error 0x%x: %s", err, err_text(err));
+}
+
+static int read_ctl(deva_b200_engine *e) {
+  CU(cudaMemcpyAsync(e->h_ctl, e->v.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time, const uint64_t *subtime,
+                          const uint32_t *lp, const uint32_t *payload) {
+  if (!e || (n && (!time || !subtime || !lp || !payload))) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (n == 0) return 0;
+  if (n > 0xffffffffull) return fail(DEVA_B200_ERR_ARG, "too many roots in one call");
+  CU(cudaSetDevice(e->cfg.device));
+  // pack SoA host columns into records in pinned memory, one H2D copy, one scatter kernel
+  EvRec *h = nullptr, *d = nullptr;
+  CU(cudaHostAlloc((void **)&h, n * sizeof(EvRec), cudaHostAllocDefault));
+  for (uint64_t i = 0; i < n; i++) {
+    h[i].time = time[i]; h[i].sub = subtime[i]; h[i].p0 = payload[i]; h[i].p1 = 0; h[i].dst = lp[i]; h[i].flags = 0;
+  }
+  CU(cudaMalloc((void **)&d, n * sizeof(EvRec)));
+  CU(cudaMemcpyAsync(d, h, n * sizeof(EvRec), cudaMemcpyHostToDevice, e->stream));
+  const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+  k_deliver<<<grid, 256, 0, e->stream>>>(e->v, d, nullptr, (uint32_t)n);
+  CU(cudaGetLastError());
+  int rc = read_ctl(e);
+  cudaFree(d);
+  cudaFreeHost(h);
+  if (rc) return rc;
+  return check_ctl_err(e);
+}
+
+int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k, int32_t rootdiv, int32_t ranks) {
+  if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (k > e->v.pq_cap) return fail(DEVA_B200_ERR_CAPACITY, "k_per_lp exceeds pq_cap");
+  CU(cudaSetDevice(e->cfg.device));
+  const int R = ranks > 0 ? ranks : 1;
+  const uint64_t per = (e->v.lp_n + R - 1) / R;
+  const int grid = (int)((e->v.A + 255) / 256);
+  dispatch_model(e->cfg.model, [&](auto m) {
+    using M = decltype(m);
+    k_init<M><<<grid, 256, 0, e->stream>>>(e->v, e->mp, 1);
+    k_seed_roots<M><<<grid, 256, 0, e->stream>>>(e->v, e->mp, k, rootdiv, per);
+    return 0;
+  });
+  CU(cudaGetLastError());
+  e->par = 0;
+  return 0;
+}
+
+int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) {
+  if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  e->mp.stop = stop;
+  return 0;
+}
+
+// ---- multi-GPU exchange: counts all-to-all, then payload all-to-all (grouped send/recv), then
+//      deliver what arrived into pending slots.  Replaces threads::send / world_gasnet send_remote.
+static int exchange(deva_b200_engine *e) {
+  const int G = e->cfg.n_gpus, me = e->cfg.gpu_rank;
+  View &v = e->v;
+  // 1. counts: every rank sends its send_n[g] to g
+  CU(cudaMemcpyAsync(e->d_counts, v.ctl->send_n, MAX_GPUS * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+  NC(g_nccl.GroupStart());
+  for (int g = 0; g < G; g++) {
+    if (g == me) continue;
+    NC(g_nccl.Send(e->d_counts + g, 1, NC_U32, g, e->comm, e->stream));
+    NC(g_nccl.Recv(e->d_counts + MAX_GPUS + g, 1, NC_U32, g, e->comm, e->stream));
+  }
+  NC(g_nccl.GroupEnd());
+  CU(cudaMemcpyAsync(e->h_counts, e->d_counts, 2 * MAX_GPUS * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  // 2. payload
+  bool any = false;
+  for (int g = 0; g < G; g++) if (g != me && (e->h_counts[g] || e->h_counts[MAX_GPUS + g])) any = true;
+  if (any) {
+    NC(g_nccl.GroupStart());
+    for (int g = 0; g < G; g++) {
+      if (g == me) continue;
+      const uint32_t ns = e->h_counts[g], nr = e->h_counts[MAX_GPUS + g];
+      if (ns > v.send_cap || nr > v.send_cap) return fail(DEVA_B200_ERR_CAPACITY, "peer staging overflow");
+      if (ns) NC(g_nccl.Send(v.sendbuf + (size_t)g * v.send_cap, (size_t)ns * sizeof(EvRec), NC_U8, g, e->comm, e->stream));
+      if (nr) NC(g_nccl.Recv(e->recvbuf + (size_t)g * v.send_cap, (size_t)nr * sizeof(EvRec), NC_U8, g, e->comm, e->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    for (int g = 0; g < G; g++) {
+      if (g == me) continue;
+      const uint32_t nr = e->h_counts[MAX_GPUS + g];
+      if (!nr) continue;
+      const unsigned grid = (unsigned)std::min<uint32_t>((nr + 255) / 256, 148 * 8);
+      k_deliver<<<grid, 256, 0, e->stream>>>(v, e->recvbuf + (size_t)g * v.send_cap, nullptr, nr);
+    }
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemsetAsync(v.ctl->send_n, 0, sizeof(v.ctl->send_n), e->stream));
+  return 0;
+}
+
+// GVT = min over GPUs (ncclMin allreduce; replaces gvt.cxx rdxn_up/rdxn_down); the same call sums
+// the per-window executed / rolled-back counts for the window policy.
+static int allreduce_gvt(deva_b200_engine *e, uint64_t *gvt, uint64_t *exec_sum, uint64_t *rolled_sum, uint32_t *err_or) {
+  unsigned long long h[4] = {*gvt, *exec_sum, *rolled_sum, *err_or};
+  CU(cudaMemcpyAsync(e->d_red, h, sizeof h, cudaMemcpyHostToDevice, e->stream));
+  NC(g_nccl.AllReduce(e->d_red, e->d_red + 4, 1, NC_U64, NC_MIN, e->comm, e->stream));
+  NC(g_nccl.AllReduce(e->d_red + 1, e->d_red + 5, 2, NC_U64, NC_SUM, e->comm, e->stream));
+  NC(g_nccl.AllReduce(e->d_red + 3, e->d_red + 7, 1, NC_U64, NC_MAX, e->comm, e->stream));
+  CU(cudaMemcpyAsync(h, e->d_red + 4, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  *gvt = h[0]; *exec_sum = h[1]; *rolled_sum = h[2]; *err_or = (uint32_t)h[3];
+  return 0;
+}
+
+static int launch_pass(deva_b200_engine *e, const PassArgs &pa) {
+  const int grid = (int)((e->v.A + PASS_THREADS - 1) / PASS_THREADS);
+  if (e->profile) CU(cudaEventRecord(e->ev_a, e->stream));
+  dispatch_model(e->cfg.model, [&](auto m) {
+    using M = decltype(m);
+    k_pass<M><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa);
+    return 0;
+  });
+  CU(cudaGetLastError());
+  if (e->profile) CU(cudaEventRecord(e->ev_b, e->stream));
+  return 0;
+}
+
+// one window: execute kernel, spill delivery, peer exchange, GVT.  Updates e->gvt.
+static int run_window(deva_b200_engine *e, uint64_t ub, uint32_t sweep, uint64_t *win_exec, uint64_t *win_rolled) {
+  View &v = e->v;
+  // reset the GVT accumulator (0xff.. == ~0ull)
+  CU(cudaMemsetAsync(&v.ctl->gvt_next, 0xff, sizeof(unsigned long long), e->stream));
+  PassArgs pa;
+  pa.gvt = e->gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep;
+  int rc = launch_pass(e, pa);
+  if (rc) return rc;
+  const Ctl before = *e->h_ctl;
+  if ((rc = read_ctl(e))) return rc;
+  if (e->profile) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->exec_ms += ms; }
+  e->passes++;
+  if (e->h_ctl->spill_n) {   // rare: some LP's inbox overflowed this window
+    if (e->h_ctl->spill_n > v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "inbox spill buffer overflowed (raise inbox_cap)");
+    const unsigned grid = (unsigned)std::min<uint32_t>((e->h_ctl->spill_n + 255) / 256, 148 * 8);
+    k_deliver<<<grid, 256, 0, e->stream>>>(v, v.spill, nullptr, e->h_ctl->spill_n);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(&v.ctl->spill_n, 0, sizeof(uint32_t), e->stream));
+    if ((rc = read_ctl(e))) return rc;
+  }
+  uint64_t gvt = e->h_ctl->gvt_next;
+  uint64_t wx = e->h_ctl->executed - before.executed, wr = e->h_ctl->rolled_back - before.rolled_back;
+  uint32_t err = e->h_ctl->err;
+  if (e->cfg.n_gpus > 1) {
+    if ((rc = exchange(e))) return rc;
+    if ((rc = read_ctl(e))) return rc;       // k_deliver may have raised a capacity error
+    err = e->h_ctl->err;
+    if ((rc = allreduce_gvt(e, &gvt, &wx, &wr, &err))) return rc;
+    e->h_ctl->err = err;
+  }
+  if ((rc = check_ctl_err(e))) return rc;
+  e->gvt = gvt;
+  e->par ^= 1u;
+  *win_exec = wx; *win_rolled = wr;
+  return 0;
+}
+
+int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out) {
+  if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->has_rewind) return fail(DEVA_B200_ERR_STATE, "lingering rewind state: call deva_b200_rewind first (pdes.cxx:705-708)");
+  if (e->cfg.n_gpus > 1 && !e->comm) return fail(DEVA_B200_ERR_STATE, "n_gpus > 1 but deva_b200_comm_init was not called");
+  CU(cudaSetDevice(e->cfg.device));
+  View &v = e->v;
+  int rc;
+  CU(cudaEventRecord(e->ev_d0, e->stream));
+  if (rewindable) {
+    // snapshot = what pdes.cxx:710-739 saves: seq counters, last-commit keys, user state (fridge),
+    // and the pending set ("anything in future upon entry to drain is a root")
+    if (e->snap_pairs.empty()) {
+      const size_t A = v.A;
+      struct { void *p; size_t b; } live[] = {
+          {v.head, A * 8}, {v.pcnt, A * 4}, {v.st, A * e->stw * 8}, {v.seq, A * 8}, {v.lct, A * 8}, {v.lcs, A * 8},
+          {v.pq, A * v.pq_cap * sizeof(EvRec)}};
+      for (auto &l : live) {
+        void *s = nullptr;
+        CU(cudaMalloc(&s, l.b));
+        e->snap_pairs.push_back({l.p, s});
+        e->snap_bytes.push_back(l.b);
+      }
+    }
+    for (size_t i = 0; i < e->snap_pairs.size(); i++)
+      CU(cudaMemcpyAsync(e->snap_pairs[i].second, e->snap_pairs[i].first, e->snap_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
+    e->has_rewind = true;
+  }
+  // initial GVT = min over LP heads (pdes.cxx:755-759: reduce_min(lvt))
+  CU(cudaMemsetAsync(&v.ctl->gvt_next, 0xff, sizeof(unsigned long long), e->stream));
+  k_min_head<<<148 * 4, 256, 0, e->stream>>>(v);
+  CU(cudaGetLastError());
+  if ((rc = read_ctl(e))) return rc;
+  if ((rc = check_ctl_err(e))) return rc;
+  uint64_t gvt = e->h_ctl->gvt_next;
+  if (e->cfg.n_gpus > 1) {
+    uint64_t a = 0, b = 0; uint32_t er = 0;
+    if ((rc = allreduce_gvt(e, &gvt, &a, &b, &er))) return rc;
+  }
+  e->gvt = gvt;
+  if (rewindable) e->snap_gvt = gvt;
+  e->wp.begin_drain();
+  uint64_t stall = 0;
+  while (e->gvt < t_end) {
+    const uint64_t ub = e->wp.upper_bound(e->gvt, t_end);
+    const uint64_t gvt_before = e->gvt;
+    uint64_t wx = 0, wr = 0;
+    if ((rc = run_window(e, ub, 0, &wx, &wr))) return rc;
+    e->wp.update(wx, wr);
+    // progress guard: GVT frozen and nothing executed for many windows == the undo log cannot
+    // drain (more same-time events at one LP than log_cap)
+    if (e->gvt == gvt_before && wx == 0) { if (++stall > 64) return fail(DEVA_B200_ERR_CAPACITY, "no progress: raise log_cap"); }
+    else stall = 0;
+  }
+  // final sweep: every LP fossil-collects below GVT (>= t_end) and folds its inbox, so that no
+  // processed-uncommitted event and no in-flight arrival is left (pdes.cxx:1020-1023 asserts)
+  {
+    uint64_t wx = 0, wr = 0;
+    if ((rc = run_window(e, t_end, 1, &wx, &wr))) return rc;
+    if (wx != 0) return fail(DEVA_B200_ERR_INVARIANT, "events executed during the final sweep");
+    // (the other inbox parity is already empty: every LP that had arrivals there was active in
+    //  the last regular window and zeroed its counter)
+  }
+  CU(cudaEventRecord(e->ev_d1, e->stream));
+  CU(cudaEventSynchronize(e->ev_d1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e->ev_d0, e->ev_d1));
+  e->drain_ms += ms;
+  // fold counters into the cumulative statistics (pdes::local_stats)
+  e->executed = e->h_ctl->executed; e->committed = e->h_ctl->committed; e->rolled = e->h_ctl->rolled_back;
+  e->anti = e->h_ctl->anti_sent; e->remote = e->h_ctl->remote_sent;
+  e->nondet = e->h_ctl->nondeterministic != 0;
+  if (gvt_out) *gvt_out = e->gvt;
+  return 0;
+}
+
+int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind) {
+  if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (!e->has_rewind) return fail(DEVA_B200_ERR_STATE, "rewind without a rewindable drain (pdes.cxx:1138)");
+  CU(cudaSetDevice(e->cfg.device));
+  e->has_rewind = false;
+  if (do_rewind) {
+    // restore state, seq counters, last-commit keys and the exact pending set (pdes.cxx:1145-1200);
+    // statistics are NOT rewound
+    for (size_t i = 0; i < e->snap_pairs.size(); i++)
+      CU(cudaMemcpyAsync(e->snap_pairs[i].first, e->snap_pairs[i].second, e->snap_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemsetAsync(e->v.icnt[0], 0, e->v.A * 4, e->stream));
+    CU(cudaMemsetAsync(e->v.icnt[1], 0, e->v.A * 4, e->stream));
+    CU(cudaMemsetAsync(e->v.lmeta, 0, e->v.A * 4, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->gvt = e->snap_gvt;
+  }
+  return 0;
+}
+
+int deva_b200_get_stats(deva_b200_engine *e, deva_b200_stats *out) {
+  if (!e || !out) return fail(DEVA_B200_ERR_ARG, "null argument");
+  memset(out, 0, sizeof *out);
+  out->executed_n = e->executed;
+  out->committed_n = e->committed;
+  out->deterministic = e->nondet ? 0 : 1;
+  out->rolled_back_n = e->rolled;
+  out->anti_sent_n = e->anti;
+  out->remote_sent_n = e->remote;
+  out->passes = e->passes;
+  out->window_last = e->wp.window();
+  out->drain_ms = e->drain_ms;
+  out->exec_kernel_ms = e->exec_ms;
+  return 0;
+}
+
+int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]) {
+  if (!e || !out) return fail(DEVA_B200_ERR_ARG, "null argument");
+  CU(cudaSetDevice(e->cfg.device));
+  CU(cudaMemsetAsync(e->d_digest, 0, 4 * sizeof(unsigned long long), e->stream));
+  k_digest<<<148 * 4, 256, 0, e->stream>>>(e->v, e->stw, e->d_digest);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, e->d_digest, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int deva_b200_comm_unique_id(void *uid128) {
+  if (!uid128) return fail(DEVA_B200_ERR_ARG, "null argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  NC(g_nccl.GetUniqueId(uid128));
+  return 0;
+}
+
+int deva_b200_comm_init(deva_b200_engine *e, const void *uid128) {
+  if (!e || !uid128) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->cfg.n_gpus == 1) return 0;
+  int rc = nccl_load();
+  if (rc) return rc;
+  CU(cudaSetDevice(e->cfg.device));
+  NcclUid uid;
+  memcpy(uid.b, uid128, 128);
+  NC(g_nccl.CommInitRank(&e->comm, e->cfg.n_gpus, uid, e->cfg.gpu_rank));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// pdes_types.cuh - record formats and the device-memory view of one engine (one GPU).
+//
+// HBM layout (A = LPs owned by this GPU).  Everything is structure-of-arrays over LPs, slot-major,
+// so that thread-per-LP accesses of one slot are a contiguous 32 B x 32 = 1 KB per warp, moved
+// with 128-bit loads/stores:
+//
+//   head [A]            u64   min time over the LP's pending slots (~0 = none)   } per-LP heads,
+//   pcnt [A]            u32   pending slots in use                               } the only thing
+//   icnt [2][A]         u32   arrivals this / next window (double-buffered)      } read for an
+//   lmeta[A]            u32   undo-log ring: count | tail<<16                    } idle LP (20 B)
+//   st   [STW][A]       u64   model state words
+//   seq  [A]            u64   next default subtime (sequence id), pdes.cxx:221-225
+//   lct,lcs [A]         u64   last committed (time+1, subtime), pdes.cxx:828-831
+//   pq   [pq_cap][A]    EvRec 32 B   pending events (replaces cd_state::future_events heap)
+//   ib   [2][ib_cap][A] EvRec 32 B   arrivals written by OTHER LPs' threads in the previous window
+//   lg   [log_cap][A]   LogRec 64 B  processed-uncommitted events + saved state
+//                                    (replaces cd_state::past_events + event::exec_ret)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+  #define DEVA_ALIGN(n) __align__(n)
+#else
+  #define DEVA_ALIGN(n) __attribute__((aligned(n)))
+#endif
+
+namespace deva_b200 {
+
+enum : uint32_t {
+  EV_ANTI = 1u,   // anti-message (cancels the positive record with identical time/sub/payload)
+  EV_SENT = 2u    // log only: the event sent a child when it ran
+};
+
+// One event record: (time, tiebreak, payload, destination LP).  == the logical content of the
+// reference's 128-byte detail::event (pdes.hxx:359-438) for a POD payload.
+struct DEVA_ALIGN(16) EvRec {
+  uint64_t time;
+  uint64_t sub;
+  uint32_t p0, p1;   // payload words (PHOLD: ray)
+  uint32_t dst;      // destination LP, GLOBAL id
+  uint32_t flags;
+};
+static_assert(sizeof(EvRec) == 32, "EvRec must be 32 bytes");
+
+constexpr int MAX_STW = 3;
+struct DEVA_ALIGN(16) LogRec {
+  EvRec ev;
+  uint64_t st[MAX_STW];  // LP state before the event ran (== the reference's `reverse` object)
+  uint64_t spare;
+};
+static_assert(sizeof(LogRec) == 64, "LogRec must be 64 bytes");
+
+enum : uint32_t {
+  ERR_PQ_OVERFLOW = 1u, ERR_LOG_STALL = 2u, ERR_ANTI_UNMATCHED = 4u, ERR_SELF_CHILD_LOST = 8u,
+  ERR_SPILL_OVERFLOW = 16u, ERR_SEND_OVERFLOW = 32u, ERR_NOT_OWNER = 64u, ERR_BELOW_GVT = 128u
+};
+
+constexpr int MAX_GPUS = 8;
+
+// Device-resident control block (one per engine).
+struct Ctl {
+  unsigned long long gvt_next;    // atomicMin accumulator: min time over everything still pending
+  unsigned long long executed, committed, rolled_back, anti_sent, remote_sent;
+  uint32_t err;
+  uint32_t nondeterministic;
+  uint32_t spill_n;               // records in the spill buffer (inbox overflow)
+  uint32_t send_n[MAX_GPUS];      // records staged for each peer GPU
+  uint32_t _pad;
+};
+
+struct View {
+  uint32_t A;            // LPs owned here
+  uint32_t pq_cap, ib_cap, log_cap;
+  uint64_t lp_begin;     // first global LP owned here
+  uint64_t lp_n;         // global LP count N (sequence-id stride)
+  uint64_t *head;
+  uint32_t *pcnt;
+  uint32_t *icnt[2];
+  uint32_t *lmeta;
+  uint64_t *st;          // [STW][A]
+  uint64_t *seq, *lct, *lcs;
+  EvRec *pq;
+  EvRec *ib[2];
+  LogRec *lg;
+  Ctl *ctl;
+  EvRec *spill;          // inbox-overflow records, delivered into pq between windows
+  uint32_t spill_cap;
+  // multi-GPU staging: send[g] region = sendbuf + g*send_cap
+  EvRec *sendbuf;
+  uint32_t send_cap;
+  int32_t n_gpus, gpu_rank;
+  uint64_t lp_per_gpu;   // block partition: owner(lp) = lp / lp_per_gpu
+};
+
+struct PassArgs {
+  uint64_t gvt;      // GVT known at the start of this window (fossil-collect below it)
+  uint64_t ub;       // execute events with time < ub  (= min(gvt + window, t_end))
+  uint32_t par;      // inbox parity read this window (arrivals are written to par^1)
+  uint32_t sweep;    // final pass of a drain: every LP fossil-collects and folds its inbox
+};
+
+}  // namespace deva_b200

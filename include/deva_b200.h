@@ -1,0 +1,142 @@
+/* deva_b200.h - C ABI of the B200-native optimistic PDES engine (libdeva_b200.so).
+ *
+ * Drop-in boundary.  The reference (cychan-lbnl/devastator) has no FFI layer: its "operator API"
+ * is the C++ template surface of src/devastator/pdes.hxx and its natural cut is the type-erasure
+ * point `event_vtable` (pdes.hxx:350-357) plus the per-rank scheduler entry points of pdes.cxx.
+ * Each entry point below names the reference interface it replaces.  The C++ mirror of the
+ * reference's header surface (include/devastator/*.hxx) is a thin veneer over exactly these calls,
+ * and so is the Python binding (devastator_b200/engine.py).
+ *
+ * Plain C types only: pointers, sizes, integers.  No exceptions cross it; every call returns 0 on
+ * success or a negative code, with text in deva_b200_last_error().  There is NO CPU fallback: if
+ * no CUDA device is usable, deva_b200_create fails.
+ *
+ * Threading: an engine is driven by one host thread at a time (the reference runs every pdes::
+ * function collectively on all rank threads, pdes.cxx:212; the C++ mirror elects one driver).
+ * One engine = one GPU.  Multi-GPU = one engine per GPU (one process per GPU, or one thread per
+ * GPU in one process) joined by deva_b200_comm_init.
+ */
+#ifndef DEVA_B200_H
+#define DEVA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEVA_B200_ABI_VERSION 1
+
+/* Device-resident models (the handler runs inside the execute kernel). */
+enum {
+  DEVA_B200_MODEL_PHOLD_TEST = 1,  /* test/phold.cxx:19-38,95-135 (state: rng.a, rng.b, check) */
+  DEVA_B200_MODEL_PHOLD_BENCH = 2  /* bench/phold.cxx:22-58,87-128 (state: rng.a, rng.b) */
+};
+
+enum {
+  DEVA_B200_OK = 0,
+  DEVA_B200_ERR_ARG = -1,
+  DEVA_B200_ERR_CUDA = -2,      /* CUDA runtime error / no device */
+  DEVA_B200_ERR_CAPACITY = -3,  /* a per-LP pool overflowed (raise pq_cap / inbox_cap / log_cap) */
+  DEVA_B200_ERR_INVARIANT = -4, /* engine invariant violated (== DEVA_ASSERT in the reference) */
+  DEVA_B200_ERR_STATE = -5,     /* call sequence error (e.g. rewind without rewindable drain) */
+  DEVA_B200_ERR_COMM = -6       /* NCCL error */
+};
+
+/* Model parameters.  PHOLD_TEST uses lp_n_model/p_remote_thresh/lambda/end_time/user_subtime;
+ * PHOLD_BENCH uses lp_n_model/lambda/bench_lp_per_rank/bench_peer_stddev/end_time. */
+typedef struct {
+  uint64_t lp_n_model;        /* actor_n (test/phold.cxx:40) / lp_n (bench/phold.cxx:89) */
+  uint64_t p_remote_thresh;   /* uint64_t(percent_remote*double(-1ull)), test/phold.cxx:119 */
+  double lambda;              /* test/phold.cxx:43, bench/phold.cxx:106 */
+  uint64_t end_time;          /* test/phold.cxx:44; ~0 = never stop re-sending */
+  int32_t user_subtime;       /* 1: E::subtime() = ray (test/phold.cxx:75); 0: sequence ids */
+  int32_t bench_lp_per_rank;  /* bench/phold.cxx:60 */
+  double bench_peer_stddev;   /* bench/phold.cxx:62 */
+} deva_b200_model_params;
+
+typedef struct {
+  int32_t abi_version;   /* DEVA_B200_ABI_VERSION */
+  int32_t model;         /* DEVA_B200_MODEL_* */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t n_gpus;        /* engines in the job (1 = no communicator needed) */
+  int32_t gpu_rank;      /* this engine's index in [0, n_gpus) */
+  int32_t pq_cap;        /* pending-event slots per LP (0 = default) */
+  int32_t inbox_cap;     /* arrival slots per LP per window (0 = default) */
+  int32_t log_cap;       /* processed-uncommitted (undo log) slots per LP (0 = default) */
+  uint64_t lp_n;         /* global LP count N = pdes::init's scan_reduce_sum total (pdes.cxx:319-321) */
+  uint64_t lp_begin;     /* first global LP owned by this engine (block partition) */
+  uint64_t lp_count;     /* LPs owned by this engine */
+  uint64_t window;       /* optimism window width in sim-time units; 0 = adaptive
+                          * (replaces deva_static_look_dt / global_status_state, pdes.cxx:36,227-310) */
+  deva_b200_model_params mp;
+} deva_b200_config;
+
+/* pdes::statistics (pdes.hxx:117-128) + engine counters. */
+typedef struct {
+  uint64_t executed_n;      /* statistics::executed_n (includes re-executions) */
+  uint64_t committed_n;     /* statistics::committed_n */
+  int32_t deterministic;    /* statistics::deterministic (pdes.cxx:828-831) */
+  int32_t _pad;
+  uint64_t rolled_back_n;   /* events undone */
+  uint64_t anti_sent_n;     /* anti-messages emitted to other LPs */
+  uint64_t remote_sent_n;   /* event records that crossed GPUs */
+  uint64_t passes;          /* optimistic windows executed (execute-kernel launches) */
+  uint64_t window_last;     /* window width used by the last pass */
+  double drain_ms;          /* device time of all drain() calls (CUDA events) */
+  double exec_kernel_ms;    /* device time inside the execute kernel only */
+} deva_b200_stats;
+
+typedef struct deva_b200_engine deva_b200_engine;
+
+/* replaces pdes::init (pdes.cxx:313-343) */
+int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out);
+/* replaces pdes::finalize's teardown (pdes.cxx:1060-1135) */
+void deva_b200_destroy(deva_b200_engine *e);
+const char *deva_b200_last_error(void);
+int deva_b200_abi_version(void);
+
+/* LP state words, host side: words[count][state_words] (u64).  Replaces the user-state half of
+ * pdes::register_state (pdes.hxx:894-897): the C++ mirror gathers the registered objects into
+ * this layout before drain and scatters them back after. */
+int deva_b200_state_words(const deva_b200_engine *e);
+int deva_b200_set_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t count, const uint64_t *words);
+int deva_b200_get_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t count, uint64_t *words);
+
+/* replaces pdes::root_event (pdes.hxx:901-909, pdes.cxx:376-387): n events, structure-of-arrays.
+ * lp = GLOBAL LP id (must be owned by this engine); subtime = E::subtime() or the LOCAL cd index
+ * (pdes.hxx:907); payload = model payload word (ray). */
+int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time, const uint64_t *subtime,
+                          const uint32_t *lp, const uint32_t *payload);
+
+/* Device-side seeding of a whole PHOLD instance (LP states + k roots per LP) straight in HBM, for
+ * the "inputs already resident" measurement: state = rng_state{lp}, check = lp
+ * (test/phold.cxx:161-162, bench/phold.cxx:150); roots as the apps create them
+ * (test/phold.cxx:172-178 with root time ray or ray/A; bench/phold.cxx:152-158).
+ * ranks = app-visible rank count (root subtime = lp % ceil(lp_n/ranks) when !user_subtime). */
+int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k_per_lp, int32_t rootdiv, int32_t ranks);
+
+/* replaces pdes::drain (pdes.cxx:695-1058): executes every event with time < t_end, returns the
+ * GVT (min pending time; ~0 when no event is left) in *gvt_out.  Collective over all engines. */
+int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out);
+/* replaces pdes::rewind (pdes.cxx:1137-1229) */
+int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind);
+/* replaces pdes::local_stats (pdes.cxx:345-347) */
+int deva_b200_get_stats(deva_b200_engine *e, deva_b200_stats *out);
+/* bench PHOLD's wall-clock cut-off (bench/phold.cxx:95-104): once set, events stop re-sending */
+int deva_b200_set_stop(deva_b200_engine *e, int32_t stop);
+
+/* Digest of this engine's LPs, computed on the device: out[0] = XOR of state word (state_words-1)
+ * (== test/phold.cxx:138-148 checksum()), out[1] = order-sensitive 64-bit hash of all state words,
+ * out[2] = pending-event count, out[3] = XOR-hash of the pending-event records. */
+int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]);
+
+/* Multi-GPU (replaces world_gasnet / threads transports and gvt.cxx's credit-counted reduction
+ * with a per-window NCCL exchange + min-allreduce).  uid = 128-byte ncclUniqueId made by rank 0. */
+int deva_b200_comm_unique_id(void *uid128);
+int deva_b200_comm_init(deva_b200_engine *e, const void *uid128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,332 @@
+// tests/emu/emu_engine.cpp - HOST emulation harness for the engine's window logic.
+//
+// TEST INFRASTRUCTURE ONLY (built into tests/emu/_build/libdeva_b200_emu.so, never shipped, never
+// loaded by the product: devastator_b200/engine.py refuses anything but libdeva_b200.so).
+// It compiles the SAME per-LP window code the execute kernel runs (devastator_b200/csrc/
+// pdes_core.cuh, models.cuh, window_policy.h) for the host and drives it one LP at a time - in a
+// seeded random LP order, to shake out any dependence on thread scheduling - so that the
+// `-m "not gpu"` suite can check the straggler / rollback / anti-message / fossil-collection
+// logic and the multi-GPU partition+exchange protocol against the oracle without a GPU.
+// It exports the same deva_b200_* C ABI (include/deva_b200.h) plus emu_* helpers.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/deva_b200.h"
+#include "../../devastator_b200/csrc/pdes_core.cuh"
+#include "../../devastator_b200/csrc/window_policy.h"
+
+using namespace deva_b200;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct deva_b200_engine {
+  deva_b200_config cfg;
+  ModelParams mp;
+  View v;
+  int stw;
+  Ctl ctl;
+  std::vector<void *> allocs;
+  uint32_t par = 0;
+  uint64_t gvt = 0;
+  WindowPolicy wp;
+  uint64_t passes = 0;
+  bool has_rewind = false;
+  std::vector<std::vector<char>> snap;
+  uint64_t snap_gvt = 0;
+  uint64_t shuffle = 1;   // LP visiting order seed
+  std::vector<EvRec> recv;
+};
+
+template <class T>
+static void halloc(deva_b200_engine *e, T **p, size_t n) {
+  *p = (T *)calloc(n ? n : 1, sizeof(T));
+  e->allocs.push_back(*p);
+}
+
+template <class F>
+static auto dispatch_model(int model, F &&f) {
+  if (model == DEVA_B200_MODEL_PHOLD_BENCH) return f(PholdBench{});
+  return f(PholdTest{});
+}
+
+static void init_lps(deva_b200_engine *e, int init_state) {
+  View &v = e->v;
+  dispatch_model(e->cfg.model, [&](auto m) {
+    using M = decltype(m);
+    for (uint32_t lp = 0; lp < v.A; lp++) {
+      const uint64_t gid = v.lp_begin + lp;
+      v.head[lp] = ~0ull; v.pcnt[lp] = 0; v.icnt[0][lp] = 0; v.icnt[1][lp] = 0; v.lmeta[lp] = 0;
+      v.seq[lp] = gid; v.lct[lp] = 0; v.lcs[lp] = 0;
+      uint64_t s[MAX_STW] = {0, 0, 0};
+      if (init_state) M::init_state(e->mp, gid, s);
+      for (int w = 0; w < M::STW; w++) v.st[(size_t)w * v.A + lp] = s[w];
+    }
+    return 0;
+  });
+}
+
+extern "C" {
+
+const char *deva_b200_last_error(void) { return g_err; }
+int deva_b200_abi_version(void) { return DEVA_B200_ABI_VERSION; }
+int deva_b200_state_words(const deva_b200_engine *e) { return e ? e->stw : 0; }
+
+int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
+  if (!cfg || !out) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (cfg->lp_count == 0 || cfg->lp_begin + cfg->lp_count > cfg->lp_n) return fail(DEVA_B200_ERR_ARG, "bad LP partition");
+  deva_b200_engine *e = new deva_b200_engine;
+  e->cfg = *cfg;
+  e->stw = cfg->model == DEVA_B200_MODEL_PHOLD_BENCH ? PholdBench::STW : PholdTest::STW;
+  e->mp.lp_n_model = cfg->mp.lp_n_model;
+  e->mp.p_remote_thresh = cfg->mp.p_remote_thresh;
+  e->mp.neg_lambda = -cfg->mp.lambda;
+  e->mp.end_time = cfg->mp.end_time;
+  e->mp.user_subtime = cfg->mp.user_subtime;
+  e->mp.bench_lp_per_rank = cfg->mp.bench_lp_per_rank;
+  e->mp.bench_peer_stddev = cfg->mp.bench_peer_stddev;
+  e->mp.stop = 0;
+  View &v = e->v;
+  memset(&v, 0, sizeof v);
+  memset(&e->ctl, 0, sizeof e->ctl);
+  v.A = (uint32_t)cfg->lp_count;
+  v.pq_cap = cfg->pq_cap > 0 ? cfg->pq_cap : 64;
+  v.ib_cap = cfg->inbox_cap > 0 ? cfg->inbox_cap : 16;
+  v.log_cap = cfg->log_cap > 0 ? cfg->log_cap : 48;
+  v.lp_begin = cfg->lp_begin;
+  v.lp_n = cfg->lp_n;
+  v.n_gpus = cfg->n_gpus;
+  v.gpu_rank = cfg->gpu_rank;
+  v.lp_per_gpu = (cfg->lp_n + cfg->n_gpus - 1) / cfg->n_gpus;
+  const size_t A = v.A;
+  halloc(e, &v.head, A); halloc(e, &v.pcnt, A); halloc(e, &v.icnt[0], A); halloc(e, &v.icnt[1], A);
+  halloc(e, &v.lmeta, A); halloc(e, &v.st, A * e->stw); halloc(e, &v.seq, A); halloc(e, &v.lct, A); halloc(e, &v.lcs, A);
+  halloc(e, &v.pq, A * v.pq_cap); halloc(e, &v.ib[0], A * v.ib_cap); halloc(e, &v.ib[1], A * v.ib_cap);
+  halloc(e, &v.lg, A * v.log_cap);
+  v.ctl = &e->ctl;
+  v.spill_cap = (uint32_t)std::max<size_t>(A * 2, 1u << 12);
+  halloc(e, &v.spill, v.spill_cap);
+  if (cfg->n_gpus > 1) {
+    v.send_cap = (uint32_t)std::max<size_t>(A * 4, 1u << 12);
+    halloc(e, &v.sendbuf, (size_t)v.send_cap * cfg->n_gpus);
+  }
+  init_lps(e, 0);
+  e->wp.init(cfg->window);
+  *out = e;
+  return 0;
+}
+
+void deva_b200_destroy(deva_b200_engine *e) {
+  if (!e) return;
+  for (void *p : e->allocs) free(p);
+  delete e;
+}
+
+int deva_b200_set_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t count, const uint64_t *words) {
+  for (uint64_t i = 0; i < count; i++)
+    for (int w = 0; w < e->stw; w++) e->v.st[(size_t)w * e->v.A + (lp_first - e->v.lp_begin) + i] = words[i * e->stw + w];
+  return 0;
+}
+int deva_b200_get_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t count, uint64_t *words) {
+  for (uint64_t i = 0; i < count; i++)
+    for (int w = 0; w < e->stw; w++) words[i * e->stw + w] = e->v.st[(size_t)w * e->v.A + (lp_first - e->v.lp_begin) + i];
+  return 0;
+}
+
+static int check_err(deva_b200_engine *e) {
+  if (!e->ctl.err) return 0;
+  return fail((e->ctl.err & (ERR_PQ_OVERFLOW | ERR_SPILL_OVERFLOW | ERR_SEND_OVERFLOW)) ? DEVA_B200_ERR_CAPACITY : DEVA_B200_ERR_INVARIANT,
+              "engine error 0x%x", e->ctl.err);
+}
+
+int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time, const uint64_t *subtime,
+                          const uint32_t *lp, const uint32_t *payload) {
+  for (uint64_t i = 0; i < n; i++) {
+    EvRec r; r.time = time[i]; r.sub = subtime[i]; r.p0 = payload[i]; r.p1 = 0; r.dst = lp[i]; r.flags = 0;
+    deliver_to_pending(e->v, r, &e->ctl.err);
+  }
+  return check_err(e);
+}
+
+int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k, int32_t rootdiv, int32_t ranks) {
+  View &v = e->v;
+  if (k > v.pq_cap) return fail(DEVA_B200_ERR_CAPACITY, "k_per_lp exceeds pq_cap");
+  const int R = ranks > 0 ? ranks : 1;
+  const uint64_t per = (v.lp_n + R - 1) / R;
+  init_lps(e, 1);
+  for (uint32_t lp = 0; lp < v.A; lp++) {
+    const uint64_t gid = v.lp_begin + lp;
+    uint64_t head = ~0ull;
+    const uint32_t kk = gid < e->mp.lp_n_model ? k : 0;   // padding LPs of the rank decomposition get no roots
+    for (uint32_t j = 0; j < kk; j++) {
+      EvRec r;
+      uint64_t ray;
+      if (e->cfg.model == DEVA_B200_MODEL_PHOLD_BENCH) { ray = gid * k + j; r.time = ray; }
+      else { ray = gid + (uint64_t)j * e->mp.lp_n_model; r.time = rootdiv ? j : ray; }
+      r.sub = e->mp.user_subtime ? ray : gid % per;
+      r.p0 = (uint32_t)ray; r.p1 = 0; r.dst = (uint32_t)gid; r.flags = 0;
+      v.pq[(size_t)j * v.A + lp] = r;
+      head = std::min(head, r.time);
+    }
+    v.pcnt[lp] = kk; v.head[lp] = head;
+  }
+  e->par = 0;
+  return 0;
+}
+
+int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) { e->mp.stop = stop; return 0; }
+
+// ---- lockstep multi-engine driver (stands in for one process per GPU + NCCL) ---------------------
+static void pass_one(deva_b200_engine *e, const PassArgs &pa, uint64_t *wx, uint64_t *wr) {
+  View &v = e->v;
+  std::vector<uint32_t> order(v.A);
+  for (uint32_t i = 0; i < v.A; i++) order[i] = i;
+  if (e->shuffle) {   // xorshift Fisher-Yates
+    uint64_t s = e->shuffle * 0x9E3779B97F4A7C15ull + e->passes + 1;
+    for (uint32_t i = v.A; i > 1; i--) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; std::swap(order[i - 1], order[s % i]); }
+  }
+  Acc acc; memset(&acc, 0, sizeof acc); acc.tmin = ~0ull;
+  dispatch_model(e->cfg.model, [&](auto m) {
+    using M = decltype(m);
+    for (uint32_t i = 0; i < v.A; i++) lp_pass<M>(v, e->mp, pa, order[i], acc);
+    return 0;
+  });
+  e->ctl.gvt_next = std::min<unsigned long long>(e->ctl.gvt_next, acc.tmin);
+  e->ctl.executed += acc.executed; e->ctl.committed += acc.committed; e->ctl.rolled_back += acc.rolled;
+  e->ctl.anti_sent += acc.anti; e->ctl.remote_sent += acc.remote; e->ctl.err |= acc.err;
+  e->ctl.nondeterministic |= acc.nondet;
+  *wx = acc.executed; *wr = acc.rolled;
+  e->passes++;
+}
+
+static int window_all(deva_b200_engine **es, int G, uint64_t ub, uint32_t sweep, uint64_t *wx_sum, uint64_t *wr_sum) {
+  *wx_sum = *wr_sum = 0;
+  for (int g = 0; g < G; g++) {
+    deva_b200_engine *e = es[g];
+    e->ctl.gvt_next = ~0ull;
+    PassArgs pa; pa.gvt = e->gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep;
+    uint64_t wx, wr;
+    pass_one(e, pa, &wx, &wr);
+    *wx_sum += wx; *wr_sum += wr;
+    if (e->ctl.spill_n > e->v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "spill overflow");
+    for (uint32_t i = 0; i < e->ctl.spill_n; i++) deliver_to_pending(e->v, e->v.spill[i], &e->ctl.err);
+    e->ctl.spill_n = 0;
+  }
+  // exchange: what NCCL grouped send/recv does on the GPU box
+  for (int g = 0; g < G; g++)
+    for (int d = 0; d < G; d++) {
+      if (d == g) continue;
+      deva_b200_engine *s = es[g], *r = es[d];
+      const uint32_t n = s->ctl.send_n[d];
+      if (n > s->v.send_cap) return fail(DEVA_B200_ERR_CAPACITY, "send overflow");
+      for (uint32_t i = 0; i < n; i++) deliver_to_pending(r->v, s->v.sendbuf[(size_t)d * s->v.send_cap + i], &r->ctl.err);
+      s->ctl.send_n[d] = 0;
+    }
+  uint64_t gvt = ~0ull;
+  for (int g = 0; g < G; g++) { gvt = std::min<uint64_t>(gvt, es[g]->ctl.gvt_next); int rc = check_err(es[g]); if (rc) return rc; }
+  for (int g = 0; g < G; g++) { es[g]->gvt = gvt; es[g]->par ^= 1u; }
+  return 0;
+}
+
+int emu_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out) {
+  for (int g = 0; g < G; g++) if (es[g]->has_rewind) return fail(DEVA_B200_ERR_STATE, "lingering rewind state");
+  uint64_t gvt = ~0ull;
+  for (int g = 0; g < G; g++) {
+    deva_b200_engine *e = es[g];
+    View &v = e->v;
+    if (rewindable) {
+      const size_t A = v.A;
+      struct { void *p; size_t b; } live[] = {{v.head, A * 8}, {v.pcnt, A * 4}, {v.st, A * e->stw * 8}, {v.seq, A * 8},
+                                              {v.lct, A * 8}, {v.lcs, A * 8}, {v.pq, A * v.pq_cap * sizeof(EvRec)}};
+      e->snap.clear();
+      for (auto &l : live) e->snap.emplace_back((char *)l.p, (char *)l.p + l.b);
+      e->has_rewind = true;
+    }
+    for (uint32_t lp = 0; lp < v.A; lp++) gvt = std::min<uint64_t>(gvt, v.head[lp]);
+  }
+  for (int g = 0; g < G; g++) { es[g]->gvt = gvt; es[g]->snap_gvt = gvt; }
+  uint64_t stall = 0;
+  while (es[0]->gvt < t_end) {
+    const uint64_t ub = es[0]->wp.upper_bound(es[0]->gvt, t_end);
+    const uint64_t before = es[0]->gvt;
+    uint64_t wx, wr;
+    int rc = window_all(es, G, ub, 0, &wx, &wr);
+    if (rc) return rc;
+    for (int g = 0; g < G; g++) es[g]->wp.update(wx, wr);
+    if (es[0]->gvt == before && wx == 0) { if (++stall > 64) return fail(DEVA_B200_ERR_CAPACITY, "no progress: raise log_cap"); }
+    else stall = 0;
+  }
+  uint64_t wx, wr;
+  int rc = window_all(es, G, t_end, 1, &wx, &wr);
+  if (rc) return rc;
+  if (wx) return fail(DEVA_B200_ERR_INVARIANT, "events executed during the final sweep");
+  // post-conditions the reference asserts at drain exit (pdes.cxx:1020-1035)
+  for (int g = 0; g < G; g++)
+    for (uint32_t lp = 0; lp < es[g]->v.A; lp++) {
+      if (es[g]->v.lmeta[lp] & 0xffffu) return fail(DEVA_B200_ERR_INVARIANT, "uncommitted event left at drain exit");
+      if (es[g]->v.icnt[0][lp] || es[g]->v.icnt[1][lp]) return fail(DEVA_B200_ERR_INVARIANT, "arrival left in an inbox at drain exit");
+    }
+  if (gvt_out) *gvt_out = es[0]->gvt;
+  return 0;
+}
+
+int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out) {
+  if (e->cfg.n_gpus != 1) return fail(DEVA_B200_ERR_STATE, "emu: use emu_drain_multi for n_gpus > 1");
+  return emu_drain_multi(&e, 1, t_end, rewindable, gvt_out);
+}
+
+int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind) {
+  if (!e->has_rewind) return fail(DEVA_B200_ERR_STATE, "rewind without a rewindable drain");
+  e->has_rewind = false;
+  if (do_rewind) {
+    View &v = e->v;
+    void *live[] = {v.head, v.pcnt, v.st, v.seq, v.lct, v.lcs, v.pq};
+    for (size_t i = 0; i < e->snap.size(); i++) memcpy(live[i], e->snap[i].data(), e->snap[i].size());
+    memset(v.icnt[0], 0, v.A * 4); memset(v.icnt[1], 0, v.A * 4); memset(v.lmeta, 0, v.A * 4);
+    e->gvt = e->snap_gvt;
+  }
+  return 0;
+}
+
+int deva_b200_get_stats(deva_b200_engine *e, deva_b200_stats *out) {
+  memset(out, 0, sizeof *out);
+  out->executed_n = e->ctl.executed; out->committed_n = e->ctl.committed;
+  out->deterministic = e->ctl.nondeterministic ? 0 : 1;
+  out->rolled_back_n = e->ctl.rolled_back; out->anti_sent_n = e->ctl.anti_sent; out->remote_sent_n = e->ctl.remote_sent;
+  out->passes = e->passes; out->window_last = e->wp.window();
+  return 0;
+}
+
+static uint64_t mix64(uint64_t x) { x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31; return x; }
+int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]) {
+  View &v = e->v;
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (uint32_t lp = 0; lp < v.A; lp++) {
+    const uint64_t gid = v.lp_begin + lp;
+    out[0] ^= v.st[(size_t)(e->stw - 1) * v.A + lp];
+    for (int w = 0; w < e->stw; w++) out[1] += mix64(v.st[(size_t)w * v.A + lp] ^ mix64(gid * 4 + w + 1));
+    out[2] += v.pcnt[lp];
+    for (uint32_t s = 0; s < v.pcnt[lp]; s++) {
+      const EvRec r = v.pq[(size_t)s * v.A + lp];
+      out[3] += mix64(r.time ^ mix64(r.sub ^ mix64(((uint64_t)r.p0 << 32 | r.dst) + r.flags)));
+    }
+  }
+  return 0;
+}
+
+int deva_b200_comm_unique_id(void *uid128) { memset(uid128, 0, 128); return 0; }
+int deva_b200_comm_init(deva_b200_engine *, const void *) { return 0; }
+void emu_set_shuffle(deva_b200_engine *e, uint64_t seed) { e->shuffle = seed; }
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+"""Engine parity through the C ABI (include/deva_b200.h).
+
+backend "emu"  : tests/emu host emulation of the SAME window code (CPU suite, logic only)
+backend "cuda" : libdeva_b200.so on cuda:0 (the product; -m gpu)
+
+Mirrors the reference's own test strategy: test/phold.cxx compares checksums
+across plain drains and drain/rewind thirds; here every run is additionally compared word for word
+with the oracle, for several optimism-window widths (the window must never change committed
+results)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import scenarios as S
+from devastator_b200 import engine as E
+
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=BACKENDS)
+def api(request):
+    return request.getfixturevalue("emu_api" if request.param == "emu" else "cuda_api")
+
+
+# ---- window width never changes results ----------------------------------------------------------
+@pytest.mark.parametrize("window", [1, 3, 20, 100, 0])
+@pytest.mark.parametrize("cfg", [
+    dict(A=64, K=4, P=0.5, LAM=10.0, END=400),        # tiny, heavy cross-LP traffic
+    dict(A=1000, K=16, P=0.10, LAM=100.0, END=300),   # "small"
+    dict(A=1000, K=16, P=0.50, LAM=100.0, END=300),   # "smallq"
+], ids=["tiny", "small", "smallq"])
+def test_phold_t_matches_oracle(api, cfg, window):
+    s, o = S.run_phold_t(api, cfg["A"], cfg["K"], cfg["P"], cfg["LAM"], cfg["END"], window=window)
+    if window == 1:   # dt >= 1: a 1-tick window is conservative, nothing may roll back
+        assert s["rolled_back_n"] == 0 and s["executed_n"] == o["commits"]
+
+
+# ---- default tiebreak = per-LP sequence ids, root subtime = local cd index (test/phold.cxx) ------
+@pytest.mark.parametrize("ranks", [2, 3, 8])
+@pytest.mark.parametrize("window", [1, 50, 0])
+def test_reference_phold_test_config(api, ranks, window):
+    """Config 1': unchanged test/phold.cxx model. 180 812 commits, checksum 15341107330209340805
+    (tests/golden/ref_goldens.json)."""
+    s, o = S.run_phold_t(api, 1000, 2, 0.5, 100.0, 10000, window=window, sub=0, rootdiv=0, ranks=ranks)
+    assert o["commits"] == 180812 and o["checksum"] == 15341107330209340805
+    gold = [g for g in S.goldens()["phold_t"] if g["tag"] == "seqid"][0]
+    assert s["committed_n"] == gold["commits"]
+
+
+# ---- golden fixtures straight from the reference binaries ---------------------------------------
+@pytest.mark.parametrize("tag", ["tiny", "small", "smallq"])
+def test_against_reference_state_fixture(api, tag):
+    g = [x for x in S.goldens()["phold_t"] if x["tag"] == tag and x["drain_end"] == 2**64 - 1][0]
+    c = g["cfg"]
+    want = np.load(os.path.join(S.GOLDEN, f"phold_t_{tag}_state.npy"))
+    eng = S.make(api, c["A"], P=c["P"], LAM=c["LAMBDA"], END=c["END"])
+    eng.seed_phold(c["K"], c["rootdiv"], 1)
+    gvt = eng.drain()
+    np.testing.assert_array_equal(eng.get_state(), want)
+    assert eng.stats()["committed_n"] == g["commits"] and eng.digest()["checksum"] == g["checksum"] and gvt == g["gvt"]
+
+
+# ---- drain(t_end): pause points, returned GVT, resume -------------------------------------------
+def test_drain_t_end_segments(api):
+    A, K, P, LAM, END = 1000, 16, 0.1, 100.0, 300
+    eng = S.make(api, A, P=P, LAM=LAM, END=END, window=20)
+    eng.seed_phold(K, 1, 1)
+    for t_end in (50, 150, E.T_INF):
+        gvt = eng.drain(t_end)
+        o, ost = O.run(A, K, P, LAM, END, drain_end=t_end)
+        S.check_against_oracle(eng, o, ost, gvt)
+    # the two pause points are also pinned by the reference itself (goldens with drain_end 50/150)
+    for g in S.goldens()["phold_t"]:
+        if g["tag"] == "small" and g["drain_end"] in (50, 150):
+            o, _ = O.run(A, K, P, LAM, END, drain_end=g["drain_end"])
+            assert (o["commits"], o["gvt"]) == (g["commits"], g["gvt"])
+
+
+# ---- pause / rewind / resume, as test/phold.cxx:180-198 drives it -------------------------------
+@pytest.mark.parametrize("window", [7, 0])
+def test_rewind_thirds_like_reference_test(api, window):
+    A, K, P, LAM, END = 1000, 2, 0.5, 100.0, 10000
+    ranks = 2
+    eng = S.make(api, A, P=P, LAM=LAM, END=END, sub=0, window=window, lp_n_model=A)
+    eng.seed_phold(K, 0, ranks)
+    t0, dt = 0, END // 3
+    while True:
+        t1 = t0 + dt
+        eng.drain(t1, rewindable=True)
+        eng.rewind(True)
+        gvt = eng.drain(t1, rewindable=True)
+        eng.rewind(False)
+        if gvt == E.T_INF:
+            break
+        t0 = t1
+    s, d = eng.stats(), eng.digest()
+    assert s["committed_n"] == 361624          # stats are not rewound: 2 x 180 812 (Appendix A.7)
+    assert d["checksum"] == 15341107330209340805
+    o, ost = O.run(A, K, P, LAM, END, ranks=ranks, user_subtime=0, rootdiv=0)
+    np.testing.assert_array_equal(eng.get_state(), ost)
+
+
+def test_rewind_requires_rewindable_drain(api):
+    eng = S.make(api, 64, P=0.5, LAM=10.0, END=100)
+    eng.seed_phold(2, 1, 1)
+    eng.drain(50)
+    with pytest.raises(E.EngineError):
+        eng.rewind(True)
+
+
+# ---- host-buffer path: set_lp_state + root_events (what pdes::register_state/root_event feed) ---
+def test_host_roots_and_state_equal_device_seeding(api):
+    A, K, P, LAM, END = 1000, 16, 0.1, 100.0, 300
+    o, ost = O.run(A, K, P, LAM, END)
+    eng = S.make(api, A, P=P, LAM=LAM, END=END, window=30)
+    eng.set_state(E.phold_initial_state_np(E.MODEL_PHOLD_TEST, 0, A))
+    eng.root_events(*E.phold_roots(E.MODEL_PHOLD_TEST, A, K, 0, A))
+    gvt = eng.drain()
+    S.check_against_oracle(eng, o, ost, gvt)
+    np.testing.assert_array_equal(E.phold_initial_state_np(E.MODEL_PHOLD_TEST, 5, 40), E.phold_initial_state(E.MODEL_PHOLD_TEST, 5, 40))
+
+
+# ---- edge cases --------------------------------------------------------------------------------
+def test_empty_simulation(api):
+    eng = S.make(api, 16, P=0.5, LAM=10.0, END=100)
+    assert eng.drain() == E.T_INF                      # no events at all: GVT = ~0 (pdes.cxx:878-886)
+    assert eng.stats()["committed_n"] == 0
+
+
+def test_single_lp_and_ragged_sizes(api):
+    for A in (1, 33, 129):
+        S.run_phold_t(api, A, 3, 0.5, 10.0, 200, window=25)
+
+
+def test_events_beyond_t_end_stay_pending(api):
+    A, K, P, LAM, END = 64, 4, 0.5, 10.0, 400
+    eng = S.make(api, A, P=P, LAM=LAM, END=END, window=10)
+    eng.seed_phold(K, 1, 1)
+    gvt = eng.drain(0)          # nothing below t_end = 0
+    assert gvt == 0 and eng.stats()["committed_n"] == 0 and eng.digest()["pending"] == A * K
+
+
+def test_capacity_overflow_fails_loudly(api):
+    eng = S.make(api, 64, P=0.5, LAM=10.0, END=400, pq_cap=4, inbox_cap=2, log_cap=8)
+    eng.seed_phold(4, 1, 1)
+    with pytest.raises(E.EngineError):
+        eng.drain()
+
+
+def test_small_capacities_still_exact(api):
+    """Inbox spill, working-set eviction and a full undo log are slow paths, not wrong paths."""
+    S.run_phold_t(api, 64, 4, 0.5, 10.0, 400, window=40, pq_cap=64, inbox_cap=1, log_cap=6)
+
+
+# ---- bench/phold.cxx model (rng + Box-Muller destination), made reproducible by an end_time -----
+@pytest.mark.parametrize("window", [1, 2000, 0])
+def test_bench_model_matches_oracle(api, window):
+    lp_per_rank, R, K, END = 128, 4, 2, 60000
+    A = lp_per_rank * R
+    o, ost = O.run(A, K, 0.0, 10000.0, END, model=O.MODEL_BENCH, ranks=R, user_subtime=0, rootdiv=0,
+                   bench_lp_per_rank=lp_per_rank, bench_peer_stddev=2.0)
+    eng = E.Engine(E.MODEL_PHOLD_BENCH, A, window=window, lam=10000.0, end_time=END, user_subtime=0,
+                   bench_lp_per_rank=lp_per_rank, bench_peer_stddev=2.0, api=api)
+    eng.seed_phold(K, 0, R)
+    gvt = eng.drain()
+    st, s = eng.get_state(), eng.stats()
+    assert s["committed_n"] == o["commits"] and gvt == o["gvt"]
+    np.testing.assert_array_equal(st, ost[:, :2])
+
+
+def test_bench_model_stop_flag(api):
+    """bench/phold.cxx:95-104: after the wall-clock cut-off events stop re-sending and the drain ends."""
+    lp_per_rank, R, K = 64, 2, 2
+    A = lp_per_rank * R
+    eng = E.Engine(E.MODEL_PHOLD_BENCH, A, window=5000, lam=10000.0, user_subtime=0,
+                   bench_lp_per_rank=lp_per_rank, bench_peer_stddev=2.0, api=api)
+    eng.seed_phold(K, 0, R)
+    eng.drain(200000)
+    before = eng.stats()["committed_n"]
+    assert before > A * K
+    eng.set_stop(True)
+    assert eng.drain() == E.T_INF
+    s = eng.stats()
+    assert s["committed_n"] - before == eng_pending_before(A, K)  # every pending event runs once, sends nothing
+
+
+def eng_pending_before(A, K):
+    return A * K   # PHOLD keeps the live-event population constant until the cut-off
