@@ -109,6 +109,16 @@ __global__ void k_deliver(View v, const EvRec *recs, const uint32_t *n_ptr, uint
   if ((threadIdx.x & 31) == 0 && tmin != ~0ull) atomicMin(&v.ctl->gvt_next, tmin);
 }
 
+// root events given as structure-of-arrays columns (deva_b200_root_events): pack + deliver on the device
+__global__ void k_deliver_soa(View v, const uint64_t *time, const uint64_t *sub, const uint32_t *lp,
+                              const uint32_t *payload, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    EvRec r;
+    r.time = time[i]; r.sub = sub[i]; r.p0 = payload[i]; r.p1 = 0; r.dst = lp[i]; r.flags = 0;
+    deliver_to_pending(v, r, &v.ctl->err);
+  }
+}
+
 __global__ void k_min_head(View v) {
   unsigned long long tmin = ~0ull;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < v.A; i += gridDim.x * blockDim.x) {
@@ -265,7 +275,7 @@ struct deva_b200_engine {
   uint64_t gvt = 0;
   WindowPolicy wp;
   // cumulative statistics (pdes::local_stats since init)
-  uint64_t executed = 0, committed = 0, rolled = 0, anti = 0, remote = 0, passes = 0;
+  uint64_t executed = 0, committed = 0, rolled = 0, anti = 0, remote = 0, passes = 0, launches = 0;
   bool nondet = false;
   double drain_ms = 0, exec_ms = 0;
   // rewind snapshot (pdes.cxx:710-739): LP state, seq counters, last-commit keys, pending set
@@ -318,6 +328,7 @@ extern "C" {
 const char *deva_b200_last_error(void) { return g_err; }
 int deva_b200_abi_version(void) { return DEVA_B200_ABI_VERSION; }
 int deva_b200_state_words(const deva_b200_engine *e) { return e ? e->stw : 0; }
+void *deva_b200_stream(deva_b200_engine *e) { return e ? (void *)e->stream : nullptr; }
 
 int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   if (!cfg || !out) return fail(DEVA_B200_ERR_ARG, "null argument");
@@ -465,20 +476,22 @@ int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time,
   if (n == 0) return 0;
   if (n > 0xffffffffull) return fail(DEVA_B200_ERR_ARG, "too many roots in one call");
   CU(cudaSetDevice(e->cfg.device));
-  // pack SoA host columns into records in pinned memory, one H2D copy, one scatter kernel
-  EvRec *h = nullptr, *d = nullptr;
-  CU(cudaHostAlloc((void **)&h, n * sizeof(EvRec), cudaHostAllocDefault));
-  for (uint64_t i = 0; i < n; i++) {
-    h[i].time = time[i]; h[i].sub = subtime[i]; h[i].p0 = payload[i]; h[i].p1 = 0; h[i].dst = lp[i]; h[i].flags = 0;
-  }
-  CU(cudaMalloc((void **)&d, n * sizeof(EvRec)));
-  CU(cudaMemcpyAsync(d, h, n * sizeof(EvRec), cudaMemcpyHostToDevice, e->stream));
-  const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
-  k_deliver<<<grid, 256, 0, e->stream>>>(e->v, d, nullptr, (uint32_t)n);
+  // four column copies (DMA straight from the caller's buffers; pinned buffers go at link speed),
+  // then one kernel packs the records and scatters them into the owners' pending slots
+  char *d = nullptr;
+  CU(cudaMalloc((void **)&d, n * 24));
+  uint64_t *d_t = (uint64_t *)d, *d_s = d_t + n;
+  uint32_t *d_l = (uint32_t *)(d_s + n), *d_p = d_l + n;
+  CU(cudaMemcpyAsync(d_t, time, n * 8, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(d_s, subtime, n * 8, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(d_l, lp, n * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(d_p, payload, n * 4, cudaMemcpyHostToDevice, e->stream));
+  const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+  k_deliver_soa<<<grid, 256, 0, e->stream>>>(e->v, d_t, d_s, d_l, d_p, (uint32_t)n);
+  e->launches++;
   CU(cudaGetLastError());
   int rc = read_ctl(e);
   cudaFree(d);
-  cudaFreeHost(h);
   if (rc) return rc;
   return check_ctl_err(e);
 }
@@ -496,8 +509,27 @@ int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k, int32_t rootdiv, int32
     k_seed_roots<M><<<grid, 256, 0, e->stream>>>(e->v, e->mp, k, rootdiv, per);
     return 0;
   });
+  e->launches += 2;
   CU(cudaGetLastError());
   e->par = 0;
+  return 0;
+}
+
+// pdes::finalize + pdes::init again on the same allocation: empties every queue, log and inbox,
+// zeroes the LP state words, restarts the sequence counters (statistics keep accumulating).
+int deva_b200_reset(deva_b200_engine *e) {
+  if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  CU(cudaSetDevice(e->cfg.device));
+  const int grid = (int)((e->v.A + 255) / 256);
+  dispatch_model(e->cfg.model, [&](auto m) {
+    using M = decltype(m);
+    k_init<M><<<grid, 256, 0, e->stream>>>(e->v, e->mp, 0);
+    return 0;
+  });
+  e->launches++;
+  CU(cudaGetLastError());
+  e->par = 0;
+  e->has_rewind = false;
   return 0;
 }
 
@@ -542,6 +574,7 @@ static int exchange(deva_b200_engine *e) {
       if (!nr) continue;
       const unsigned grid = (unsigned)std::min<uint32_t>((nr + 255) / 256, 148 * 8);
       k_deliver<<<grid, 256, 0, e->stream>>>(v, e->recvbuf + (size_t)g * v.send_cap, nullptr, nr);
+      e->launches++;
     }
     CU(cudaGetLastError());
   }
@@ -571,6 +604,7 @@ static int launch_pass(deva_b200_engine *e, const PassArgs &pa) {
     k_pass<M><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa);
     return 0;
   });
+  e->launches++;
   CU(cudaGetLastError());
   if (e->profile) CU(cudaEventRecord(e->ev_b, e->stream));
   return 0;
@@ -593,6 +627,7 @@ static int run_window(deva_b200_engine *e, uint64_t ub, uint32_t sweep, uint64_t
     if (e->h_ctl->spill_n > v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "inbox spill buffer overflowed (raise inbox_cap)");
     const unsigned grid = (unsigned)std::min<uint32_t>((e->h_ctl->spill_n + 255) / 256, 148 * 8);
     k_deliver<<<grid, 256, 0, e->stream>>>(v, v.spill, nullptr, e->h_ctl->spill_n);
+    e->launches++;
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(&v.ctl->spill_n, 0, sizeof(uint32_t), e->stream));
     if ((rc = read_ctl(e))) return rc;
@@ -644,6 +679,7 @@ int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uin
   // initial GVT = min over LP heads (pdes.cxx:755-759: reduce_min(lvt))
   CU(cudaMemsetAsync(&v.ctl->gvt_next, 0xff, sizeof(unsigned long long), e->stream));
   k_min_head<<<148 * 4, 256, 0, e->stream>>>(v);
+  e->launches++;
   CU(cudaGetLastError());
   if ((rc = read_ctl(e))) return rc;
   if ((rc = check_ctl_err(e))) return rc;
@@ -721,6 +757,7 @@ int deva_b200_get_stats(deva_b200_engine *e, deva_b200_stats *out) {
   out->window_last = e->wp.window();
   out->drain_ms = e->drain_ms;
   out->exec_kernel_ms = e->exec_ms;
+  out->kernel_launches = e->launches;
   return 0;
 }
 

@@ -1,10 +1,9 @@
 // window_policy.h - optimism window width W: events with time < min(GVT + W, t_end) may run.
 //
-// Replaces global_status_state::{update,calc_look_t_ub} (pdes.cxx:227-310).  Same shape as the
-// reference's controller - a 16-round history of executed vs. useful work, quarter / halve the
-// window when efficiency drops under .33 / .66, double it above .95 - but "useful" is measured as
-// executed minus rolled-back per window (exact on the device), because fossil collection here is
-// lazy and per-window commit counts lag.  Like the reference's look_dt it never changes committed
+// Replaces global_status_state::{update,calc_look_t_ub} (pdes.cxx:227-310).  Same idea as the
+// reference's controller - shrink the window when too much executed work is wasted, grow it when
+// nearly all of it survives - but "useful" is measured as executed minus rolled-back (exact on the
+// device), because fossil collection here is lazy and per-window commit counts lag.  Like the reference's look_dt it never changes committed
 // results, only how much work is wasted.  `fixed` != 0 pins W
 // (the reference's deva_static_look_dt, pdes.cxx:36,247-250).
 #pragma once
@@ -13,18 +12,18 @@
 namespace deva_b200 {
 
 struct WindowPolicy {
-  static constexpr int HIST = 16;
+  static constexpr int PERIOD = 4;   // windows per decision: a rollback is charged to a LATER window
+                                     // than the execution it undoes, so single windows are noisy
   uint64_t fixed = 0;
   uint64_t w = 1;
-  uint64_t hist_exec[HIST] = {0}, hist_useful[HIST] = {0};
-  uint64_t sum_exec = 0, sum_useful = 0;
+  uint64_t acc_exec = 0, acc_rolled = 0;
   unsigned round = 0;
 
   void init(uint64_t window) {
     fixed = window;
     w = window ? window : 16;
   }
-  void begin_drain() {}
+  void begin_drain() { acc_exec = acc_rolled = 0; round = 0; }
   uint64_t window() const { return w; }
   // calc_look_t_ub, pdes.cxx:303-309
   uint64_t upper_bound(uint64_t gvt, uint64_t t_end) const {
@@ -32,17 +31,22 @@ struct WindowPolicy {
     if (ub < gvt) ub = ~uint64_t(0);
     return ub > t_end ? t_end : ub;
   }
+  // global_status_state::update, pdes.cxx:233-280: efficiency bands decide the window.  On the GPU
+  // a window costs one kernel launch whatever its width, and measured throughput is flat over a
+  // wide range of widths as long as ~95 % or more of the executed events survive, so the policy
+  // holds efficiency in [0.95, 0.985]: quarter / halve-ish below, grow by 25 % above.
   void update(uint64_t exec_n, uint64_t rolled_n) {
-    const uint64_t useful = exec_n > rolled_n ? exec_n - rolled_n : 0;
-    const unsigned r = round++ % HIST;
-    sum_exec -= hist_exec[r]; sum_useful -= hist_useful[r];
-    hist_exec[r] = exec_n; hist_useful[r] = useful;
-    sum_exec += exec_n; sum_useful += useful;
     if (fixed) { w = fixed; return; }
-    if (sum_exec == 0) return;
-    const double num = (double)sum_useful, den = (double)sum_exec;
-    if (num < .66 * den) w = num < .33 * den ? w / 4 : w / 2;
-    else if (num > .95 * den) w *= 2;
+    acc_exec += exec_n;
+    acc_rolled += rolled_n;
+    if (++round % PERIOD) return;
+    if (acc_exec) {
+      const double eff = 1.0 - (double)acc_rolled / (double)acc_exec;
+      if (eff < 0.80) w /= 2;
+      else if (eff < 0.95) w = w - w / 4;
+      else if (eff > 0.985) w = w + w / 4 + 1;
+    }
+    acc_exec = acc_rolled = 0;
     if (w > (uint64_t(1) << 58)) w = uint64_t(1) << 58;
     if (w < 1) w = 1;
   }

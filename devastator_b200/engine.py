@@ -42,7 +42,7 @@ class Stats(C.Structure):
     _fields_ = [("executed_n", C.c_uint64), ("committed_n", C.c_uint64), ("deterministic", C.c_int32),
                 ("_pad", C.c_int32), ("rolled_back_n", C.c_uint64), ("anti_sent_n", C.c_uint64),
                 ("remote_sent_n", C.c_uint64), ("passes", C.c_uint64), ("window_last", C.c_uint64),
-                ("drain_ms", C.c_double), ("exec_kernel_ms", C.c_double)]
+                ("drain_ms", C.c_double), ("exec_kernel_ms", C.c_double), ("kernel_launches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "_pad"}
@@ -53,7 +53,8 @@ ABI_SYMBOLS = [
     "deva_b200_create", "deva_b200_destroy", "deva_b200_last_error", "deva_b200_abi_version",
     "deva_b200_state_words", "deva_b200_set_lp_state", "deva_b200_get_lp_state", "deva_b200_root_events",
     "deva_b200_seed_phold", "deva_b200_drain", "deva_b200_rewind", "deva_b200_get_stats", "deva_b200_set_stop",
-    "deva_b200_digest", "deva_b200_comm_unique_id", "deva_b200_comm_init",
+    "deva_b200_digest", "deva_b200_comm_unique_id", "deva_b200_comm_init", "deva_b200_stream",
+    "deva_b200_reset",
 ]
 
 
@@ -86,6 +87,9 @@ class Api:
         L.deva_b200_digest.argtypes = [P, P]
         L.deva_b200_comm_unique_id.argtypes = [P]
         L.deva_b200_comm_init.argtypes = [P, P]
+        L.deva_b200_stream.argtypes = [P]
+        L.deva_b200_reset.argtypes = [P]
+        L.deva_b200_stream.restype = P
 
     def check(self, rc):
         if rc != 0:
@@ -181,6 +185,9 @@ class Engine:
         self.api.check(self.api.lib.deva_b200_root_events(self.h, t.size, t.ctypes.data, s.ctypes.data,
                                                           l.ctypes.data, p.ctypes.data))
 
+    def reset(self):
+        self.api.check(self.api.lib.deva_b200_reset(self.h))
+
     def seed_phold(self, k_per_lp, rootdiv=1, ranks=1):
         self.api.check(self.api.lib.deva_b200_seed_phold(self.h, k_per_lp, rootdiv, ranks))
 
@@ -205,6 +212,10 @@ class Engine:
         out = (C.c_uint64 * 4)()
         self.api.check(self.api.lib.deva_b200_digest(self.h, out))
         return dict(checksum=out[0], state_hash=out[1], pending=out[2], pending_hash=out[3])
+
+    def stream_ptr(self):
+        """cudaStream_t the engine launches on (wrap with torch.cuda.ExternalStream to time it)."""
+        return self.api.lib.deva_b200_stream(self.h)
 
     def comm_init(self, uid_bytes):
         buf = C.create_string_buffer(bytes(uid_bytes), 128)

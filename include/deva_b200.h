@@ -85,6 +85,7 @@ typedef struct {
   uint64_t window_last;     /* window width used by the last pass */
   double drain_ms;          /* device time of all drain() calls (CUDA events) */
   double exec_kernel_ms;    /* device time inside the execute kernel only */
+  uint64_t kernel_launches; /* kernels this engine has launched since create */
 } deva_b200_stats;
 
 typedef struct deva_b200_engine deva_b200_engine;
@@ -116,6 +117,10 @@ int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time,
  * ranks = app-visible rank count (root subtime = lp % ceil(lp_n/ranks) when !user_subtime). */
 int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k_per_lp, int32_t rootdiv, int32_t ranks);
 
+/* pdes::finalize followed by pdes::init on the same allocation (pdes.cxx:313-343,1060-1135):
+ * empties queues, logs and inboxes, zeroes LP state, restarts sequence ids. */
+int deva_b200_reset(deva_b200_engine *e);
+
 /* replaces pdes::drain (pdes.cxx:695-1058): executes every event with time < t_end, returns the
  * GVT (min pending time; ~0 when no event is left) in *gvt_out.  Collective over all engines. */
 int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out);
@@ -130,6 +135,10 @@ int deva_b200_set_stop(deva_b200_engine *e, int32_t stop);
  * (== test/phold.cxx:138-148 checksum()), out[1] = order-sensitive 64-bit hash of all state words,
  * out[2] = pending-event count, out[3] = XOR-hash of the pending-event records. */
 int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]);
+
+/* The cudaStream_t every kernel and copy of this engine is issued on (for CUDA-event timing by the
+ * caller: events must be recorded on the launching stream). */
+void *deva_b200_stream(deva_b200_engine *e);
 
 /* Multi-GPU (replaces world_gasnet / threads transports and gvt.cxx's credit-counted reduction
  * with a per-window NCCL exchange + min-allreduce).  uid = 128-byte ncclUniqueId made by rank 0. */

@@ -81,6 +81,12 @@ int main() {
   const char *drain_end_s = std::getenv("PHOLD_T_DRAIN_END");
   uint64_t drain_end = drain_end_s ? std::strtoull(drain_end_s, nullptr, 10) : ~uint64_t(0);
   g_dump = (uint64_t*)std::calloc(size_t(actor_n)*3, sizeof(uint64_t));
+  int seg_n = 0; uint64_t seg_dt = 0;
+  if(const char *sg = std::getenv("PHOLD_T_SEGMENTS")) {   // "n:dt"
+    seg_n = std::atoi(sg);
+    const char *c = std::strchr(sg, ':');
+    seg_dt = c ? std::strtoull(c+1, nullptr, 10) : 1;
+  }
   auto doit = [&]() {
     pdes::chitter_secs = -1;
     pdes::init(actor_per_rank);
@@ -99,10 +105,35 @@ int main() {
         pdes::root_event(actor - actor_lb, PHOLD_ROOT_TIME(ray), event{int(ray), actor});
     }
     deva::barrier();
-    auto t0 = std::chrono::steady_clock::now();
-    uint64_t gvt = pdes::drain(drain_end, false);
-    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    secs = deva::reduce_max(secs);
+    uint64_t gvt = 0;
+    double secs = 0;
+    if(seg_n > 0) {
+      // segment mode (bench.py reference arm): setup once, then seg_n timed drain(t_end) slices of
+      // seg_dt simulated-time units each; one JSON line per slice
+      uint64_t commits_prev = 0;
+      for(int sgi=0; sgi < seg_n; sgi++) {
+        uint64_t t_end_i = uint64_t(sgi+1)*seg_dt;
+        deva::barrier();
+        auto t0 = std::chrono::steady_clock::now();
+        gvt = pdes::drain(t_end_i, false);
+        double s1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        s1 = deva::reduce_max(s1);
+        pdes::statistics st1 = deva::reduce_sum(pdes::local_stats());
+        if(deva::rank_me() == 0) {
+          std::printf("{\"segment\": %d, \"t_end\": %llu, \"commits\": %llu, \"drain_secs\": %.6f, \"ranks\": %d}\n",
+                      sgi, (unsigned long long)t_end_i, (unsigned long long)(st1.committed_n - commits_prev), s1, rank_n);
+          std::fflush(stdout);
+        }
+        commits_prev = st1.committed_n;
+        secs += s1;
+      }
+    }
+    else {
+      auto t0 = std::chrono::steady_clock::now();
+      gvt = pdes::drain(drain_end, false);
+      secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      secs = deva::reduce_max(secs);
+    }
     pdes::finalize();
     pdes::statistics stats = deva::reduce_sum(pdes::local_stats());
     uint64_t chk = checksum();
@@ -223,6 +254,7 @@ def main():
     ap.add_argument("--ranks", type=int, nargs="*", default=[2, 8])
     ap.add_argument("--only", default="phold_test,phold_bench,phold_t")
     ap.add_argument("--tags", default=",".join(PHOLD_T_CONFIGS))
+    ap.add_argument("--baseline-ranks", type=int, nargs="*", default=[4, 16, 32, 64])
     ap.add_argument("--force", action="store_true")
     a = ap.parse_args()
     if not os.path.isdir(REF):
@@ -246,6 +278,15 @@ def main():
                 jobs.append((gen, exe_name("phold_t", R, tag), tuple(phold_t_flags(PHOLD_T_CONFIGS[tag]))))
         with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
             built += list(ex.map(lambda j: link_app(R, objs, j[0], j[1], j[2], a.force), jobs))
+    # the CPU-baseline binary (BASELINE config 2) for the host core counts a GPU box may have
+    if "phold_t" in only and "cfg2" in tags:
+        gen = gen_phold_t()
+        for R in a.baseline_ranks:
+            if R in a.ranks:
+                continue
+            objs = build_runtime(R, a.force)
+            built.append(link_app(R, objs, gen, exe_name("phold_t", R, "cfg2"),
+                                  tuple(phold_t_flags(PHOLD_T_CONFIGS["cfg2"])), a.force))
     for b in built:
         print("built", os.path.relpath(b, os.path.dirname(HERE)))
     return 0

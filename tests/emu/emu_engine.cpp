@@ -82,6 +82,7 @@ extern "C" {
 const char *deva_b200_last_error(void) { return g_err; }
 int deva_b200_abi_version(void) { return DEVA_B200_ABI_VERSION; }
 int deva_b200_state_words(const deva_b200_engine *e) { return e ? e->stw : 0; }
+void *deva_b200_stream(deva_b200_engine *) { return nullptr; }
 
 int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   if (!cfg || !out) return fail(DEVA_B200_ERR_ARG, "null argument");
@@ -186,6 +187,7 @@ int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k, int32_t rootdiv, int32
 }
 
 int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) { e->mp.stop = stop; return 0; }
+int deva_b200_reset(deva_b200_engine *e) { init_lps(e, 0); e->par = 0; e->has_rewind = false; return 0; }
 
 // ---- lockstep multi-engine driver (stands in for one process per GPU + NCCL) ---------------------
 static void pass_one(deva_b200_engine *e, const PassArgs &pa, uint64_t *wx, uint64_t *wr) {
