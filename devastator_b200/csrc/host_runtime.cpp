@@ -1,0 +1,443 @@
+// host_runtime.cpp - libdeva_host.so: the C++ host side behind include/devastator/*.hxx.
+//
+// Provides (1) the rank-thread world (deva::run, barrier, mailbox send, reductions' shared slots),
+// (2) datarow / diagnostic, and (3) the deva::pdes veneer over the engine's C ABI
+// (include/deva_b200.h).  It is the thread-per-rank shim of SURVEY.md section 8b: app state is
+// thread_local per rank, so every app-visible rank is an OS thread; rank 0 is the elected driver
+// of the GPU.  No event ever executes here: handlers of device-resident models run in k_pass.
+#include <devastator/world.hxx>
+#include <devastator/diagnostic.hxx>
+#include <devastator/os_env.hxx>
+#include <devastator/pdes.hxx>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <csignal>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <sched.h>
+
+#ifndef DEVA_GIT_VERSION
+  #define DEVA_GIT_VERSION "devastator-b200"
+#endif
+
+// ================================================================================================
+// world: persistent rank threads
+namespace {
+  struct World {
+    int n = 0;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::uint64_t job_gen = 0;
+    void (*tramp)(void*) = nullptr;
+    void *ctx = nullptr;
+    int done = 0;
+    bool quit = false;
+    // sense-reversing barrier
+    std::atomic<int> bar_count{0};
+    std::atomic<std::uint64_t> bar_gen{0};
+    std::vector<void*> slots;
+    // mailboxes
+    std::vector<std::deque<std::function<void()>>> mail;
+    std::vector<std::mutex*> mail_mu;
+    ~World() {
+      { std::lock_guard<std::mutex> l(mu); quit = true; }
+      cv.notify_all();
+      for(auto &t: workers) if(t.joinable()) t.join();
+      for(auto *m: mail_mu) delete m;
+    }
+  };
+  World g_world;
+  thread_local int t_rank = 0;
+
+  void worker_main(int rank) {
+    t_rank = rank;
+    std::uint64_t seen = 0;
+    while(true) {
+      void (*tramp)(void*); void *ctx;
+      {
+        std::unique_lock<std::mutex> l(g_world.mu);
+        g_world.cv.wait(l, [&] { return g_world.quit || g_world.job_gen != seen; });
+        if(g_world.quit) return;
+        seen = g_world.job_gen;
+        tramp = g_world.tramp; ctx = g_world.ctx;
+      }
+      tramp(ctx);
+      {
+        std::lock_guard<std::mutex> l(g_world.mu);
+        g_world.done++;
+      }
+      g_world.cv.notify_all();
+    }
+  }
+}
+
+namespace deva { namespace detail {
+  void world_run(int n, void (*tramp)(void*), void *ctx) {   // threads::run, threads.cxx:210-256
+    World &w = g_world;
+    if(w.n == 0) {
+      w.n = n;
+      w.slots.assign(n, nullptr);
+      w.mail.resize(n);
+      for(int i = 0; i < n; i++) w.mail_mu.push_back(new std::mutex);
+      for(int r = 1; r < n; r++) w.workers.emplace_back(worker_main, r);
+    }
+    if(w.n != n) { std::cerr << "deva::run: rank_n changed between calls\n"; std::abort(); }
+    t_rank = 0;
+    {
+      std::lock_guard<std::mutex> l(w.mu);
+      w.tramp = tramp; w.ctx = ctx; w.done = 0; w.job_gen++;
+    }
+    w.cv.notify_all();
+    tramp(ctx);                       // the calling thread is rank 0
+    std::unique_lock<std::mutex> l(w.mu);
+    w.cv.wait(l, [&] { return w.done == n - 1; });
+  }
+  int world_rank_me() { return t_rank; }
+  void world_progress() {
+    World &w = g_world;
+    if(w.n == 0) return;
+    std::deque<std::function<void()>> mine;
+    { std::lock_guard<std::mutex> l(*w.mail_mu[t_rank]); mine.swap(w.mail[t_rank]); }
+    for(auto &f: mine) f();
+  }
+  void world_barrier() {
+    World &w = g_world;
+    if(w.n <= 1) { world_progress(); return; }
+    const std::uint64_t gen = w.bar_gen.load(std::memory_order_acquire);
+    if(w.bar_count.fetch_add(1, std::memory_order_acq_rel) + 1 == w.n) {
+      w.bar_count.store(0, std::memory_order_relaxed);
+      w.bar_gen.store(gen + 1, std::memory_order_release);
+    }
+    else {
+      int spins = 0;
+      while(w.bar_gen.load(std::memory_order_acquire) == gen) {
+        if(++spins > 64) { sched_yield(); }
+      }
+    }
+    world_progress();
+  }
+  void **world_slots() { return g_world.slots.data(); }
+  void world_post(int rank, std::function<void()> fn) {
+    World &w = g_world;
+    std::lock_guard<std::mutex> l(*w.mail_mu[rank]);
+    w.mail[rank].push_back(std::move(fn));
+  }
+}}
+
+// ================================================================================================
+// diagnostic + datarow
+namespace { std::mutex g_io_mu; }
+const char *const deva::git_version = DEVA_GIT_VERSION;
+
+void deva::dbgbrk(bool*) { std::raise(SIGINT); }
+
+void deva::assert_failed(const char *file, int line, const char *msg) {
+  std::stringstream ss;
+  ss << std::string(50, '/') << '\n' << "ASSERT FAILED rank=" << deva::rank_me() << " at=" << file << ':' << line << '\n';
+  if(msg && msg[0]) ss << '\n' << msg << '\n';
+  ss << std::string(50, '/') << '\n';
+  { std::lock_guard<std::mutex> l(g_io_mu); std::cerr << ss.str(); }
+  std::abort();
+}
+deva::say::say() { ss << "[" << deva::rank_me() << "] "; }
+deva::say::~say() { ss << "\n"; std::lock_guard<std::mutex> l(g_io_mu); std::cerr << ss.str(); }
+
+deva::datarow deva::describe() {
+  datarow ans;
+  ans &= datarow::x("git", DEVA_GIT_VERSION);
+  ans &= datarow::x("world", "threads+b200");
+  ans &= datarow::x("ranks", g_world.n);
+  ans &= datarow::x("engine", "deva_b200");
+  return ans;
+}
+
+void deva::datarow::cell::to_python(std::ostream &o) const {
+  if(is_num) { o << num; return; }
+  o << '"';
+  for(char c: str) { if(c == '"' || c == '\\') o << '\\'; o << c; }
+  o << '"';
+}
+void deva::datarow::to_python_kwargs(bool x_not_y, std::ostream &o, bool leading_comma) {
+  for(auto const &kv: m_) {
+    if(x_not_y == kv.second.is_y) continue;
+    if(leading_comma) o << ", ";
+    leading_comma = true;
+    o << kv.first << '=';
+    kv.second.to_python(o);
+  }
+}
+deva::datarow deva::datarow::from_python_kwargs(std::istream &in) {
+  // name=value[, name=value ...]; values are numbers, bare words or quoted strings
+  auto skip = [&](const char *set) { while(in.peek() != EOF && std::strchr(set, in.peek())) in.get(); };
+  auto token = [&](bool &is_num, double &num) -> std::string {
+    is_num = false;
+    int c = in.peek();
+    if((c >= '0' && c <= '9') || c == '.' || c == '-') { in >> num; is_num = true; return std::string(); }
+    std::string s;
+    if(c == '"' || c == '\'') {
+      const char q = char(in.get());
+      while(in.peek() != EOF && in.peek() != q) { if(in.peek() == '\\') in.get(); s.push_back(char(in.get())); }
+      in.get();
+    }
+    else while(in.peek() != EOF && !std::strchr("=:, \t\n", in.peek())) { if(in.peek() == '\\') in.get(); s.push_back(char(in.get())); }
+    return s;
+  };
+  datarow ans;
+  skip(" \t\n");
+  while(in.peek() != EOF) {
+    bool is_num; double num = 0;
+    std::string name = token(is_num, num);
+    skip(" \t\n");
+    const int sep = in.get();
+    DEVA_ASSERT_ALWAYS(sep == '=' || sep == ':');
+    skip(" \t\n");
+    std::string sval = token(is_num, num);
+    if(is_num) ans.m_.emplace(std::move(name), cell(num, false));
+    else ans.m_.emplace(std::move(name), cell(std::move(sval), false));
+    skip(", \t\n");
+  }
+  return ans;
+}
+deva::datarow deva::datarow::prefix_all(std::string prefix) {
+  datarow ans;
+  for(auto const &kv: m_) ans.m_.emplace(prefix + kv.first, kv.second);
+  return ans;
+}
+deva::datarow& deva::operator&=(datarow &a, datarow b) {
+  for(auto &kv: b.m_) a.m_.emplace(kv.first, std::move(kv.second));   // first assignment wins
+  return a;
+}
+deva::datarow deva::operator&(datarow a, datarow b) { a &= std::move(b); return a; }
+std::size_t std::hash<deva::datarow>::operator()(deva::datarow const &row) const {
+  std::size_t h = 1469598103934665603ull;
+  for(auto const &kv: row.m_) {
+    h = (h ^ std::hash<std::string>()(kv.first)) * 1099511628211ull;
+    h = (h ^ (kv.second.is_num ? std::hash<double>()(kv.second.num) : std::hash<std::string>()(kv.second.str))) * 1099511628211ull;
+    h ^= std::size_t(kv.second.is_y) << 7;
+  }
+  return h;
+}
+
+// ================================================================================================
+// pdes veneer over the C ABI
+namespace pdes = deva::pdes;
+int pdes::chitter_secs = 3;
+std::ostream *pdes::chitter_io = &std::cout;
+
+namespace {
+  struct Reg { std::int32_t cd; void *addr; std::size_t bytes; };
+  struct Root { std::uint64_t time, sub; std::uint32_t lp, payload; };
+  struct RankSide {            // what one rank thread has told pdes since init
+    std::int32_t cds = -1;
+    std::uint64_t lp_begin = 0;
+    std::vector<Reg> regs;
+    std::vector<Root> roots;
+  };
+  struct Sim {
+    std::vector<RankSide> ranks;
+    std::uint64_t lp_n = 0;
+    const pdes::model_binding *model = nullptr;
+    bool user_subtime = false;
+    deva_b200_engine *eng = nullptr;
+    bool has_rewind = false;
+    pdes::statistics stats;      // cumulative since init; read after finalize (test/phold.cxx:201-204)
+    std::uint64_t gvt = 0;
+    std::mutex mu;
+  };
+  Sim g_sim;
+
+  [[noreturn]] void die(const char *what) {
+    std::stringstream ss;
+    ss << what << ": " << deva_b200_last_error();
+    deva::assert_failed(__FILE__, __LINE__, ss.str().c_str());
+    std::abort();
+  }
+  void ck(int rc, const char *what) { if(rc != 0) die(what); }
+
+  // registered objects of one LP, concatenated in registration order == the model's state words
+  void gather_state(std::vector<std::uint64_t> &words, int stw) {
+    words.assign(std::size_t(g_sim.lp_n)*stw, 0);
+    for(auto &rs: g_sim.ranks) {
+      std::vector<std::size_t> off(std::size_t(rs.cds), 0);
+      for(auto &r: rs.regs) {
+        char *dst = reinterpret_cast<char*>(&words[(rs.lp_begin + r.cd)*stw]) + off[r.cd];
+        DEVA_ASSERT_ALWAYS(off[r.cd] + r.bytes <= std::size_t(stw)*8, "registered state of a cd exceeds the device model's state words");
+        std::memcpy(dst, r.addr, r.bytes);
+        off[r.cd] += r.bytes;
+      }
+    }
+  }
+  void scatter_state(const std::vector<std::uint64_t> &words, int stw) {
+    for(auto &rs: g_sim.ranks) {
+      std::vector<std::size_t> off(std::size_t(rs.cds), 0);
+      for(auto &r: rs.regs) {
+        const char *src = reinterpret_cast<const char*>(&words[(rs.lp_begin + r.cd)*stw]) + off[r.cd];
+        std::memcpy(r.addr, src, r.bytes);
+        off[r.cd] += r.bytes;
+      }
+    }
+  }
+  void download_state() {
+    const int stw = deva_b200_state_words(g_sim.eng);
+    std::vector<std::uint64_t> words(std::size_t(g_sim.lp_n)*stw);
+    ck(deva_b200_get_lp_state(g_sim.eng, 0, g_sim.lp_n, words.data()), "deva_b200_get_lp_state");
+    scatter_state(words, stw);
+  }
+}
+
+void pdes::detail::no_device_model(const char *what) {
+  std::stringstream ss;
+  ss << what << ": this event type has no device-resident model (deva::pdes::device_model<E>). "
+        "Host-handler execution is not built; there is no CPU path. Force-include a model header "
+        "(include/devastator_b200/models/*.hxx) on the build line.";
+  deva::assert_failed(__FILE__, __LINE__, ss.str().c_str());
+  std::abort();
+}
+
+void pdes::init(std::int32_t cds_this_rank) {       // pdes.cxx:313-343
+  const int me = deva::rank_me();
+  deva::barrier();
+  if(me == 0) {
+    DEVA_ASSERT_ALWAYS(g_sim.eng == nullptr, "pdes::init called twice without pdes::finalize");
+    g_sim.ranks.assign(deva::rank_n, RankSide());
+    g_sim.model = nullptr;
+    g_sim.stats = pdes::statistics();
+    g_sim.has_rewind = false;
+  }
+  deva::barrier();
+  std::uint64_t begin, total;
+  std::tie(begin, total) = deva::scan_reduce_sum<std::uint64_t>(std::uint64_t(cds_this_rank));   // pdes.cxx:319
+  RankSide &rs = g_sim.ranks[me];
+  rs.cds = cds_this_rank;
+  rs.lp_begin = begin;
+  if(me == 0) g_sim.lp_n = total;
+  deva::barrier();
+}
+
+void pdes::detail::register_state_raw(std::int32_t cd, void *addr, std::size_t bytes) {
+  RankSide &rs = g_sim.ranks[deva::rank_me()];
+  DEVA_ASSERT_ALWAYS(0 <= cd && cd < rs.cds);
+  rs.regs.push_back({cd, addr, bytes});
+}
+
+void pdes::register_checksum_if_debug(std::int32_t, std::function<std::uint64_t()>&&) {
+  // DEBUG-only hook in the reference (pdes.cxx:369-374); device models are checked against the
+  // oracle instead (tests/)
+}
+
+void pdes::detail::root_event_raw(std::int32_t cd, std::uint64_t time, std::uint64_t subtime, bool user_subtime,
+                                  std::uint32_t payload, const model_binding *model) {
+  RankSide &rs = g_sim.ranks[deva::rank_me()];
+  DEVA_ASSERT_ALWAYS(0 <= cd && cd < rs.cds);
+  {
+    std::lock_guard<std::mutex> l(g_sim.mu);
+    if(!g_sim.model) { g_sim.model = model; g_sim.user_subtime = user_subtime; }
+    DEVA_ASSERT_ALWAYS(g_sim.model->model_id == model->model_id, "one device model per simulation");
+  }
+  rs.roots.push_back({time, subtime, std::uint32_t(rs.lp_begin + cd), payload});
+}
+
+std::uint64_t pdes::drain(std::uint64_t t_end, bool rewindable) {   // pdes.cxx:695-1058
+  deva::barrier();
+  if(deva::rank_me() == 0) {
+    DEVA_ASSERT_ALWAYS(!g_sim.has_rewind, "Lingering rewind state must be rewound via pdes::rewind(true|false) before calling pdes::drain().");
+    if(!g_sim.eng) {
+      if(!g_sim.model) pdes::detail::no_device_model("pdes::drain (no root event was ever inserted through a device model)");
+      deva_b200_config cfg;
+      std::memset(&cfg, 0, sizeof cfg);
+      cfg.abi_version = DEVA_B200_ABI_VERSION;
+      cfg.model = g_sim.model->model_id;
+      cfg.device = deva::os_env<int>("DEVA_B200_DEVICE", 0);
+      cfg.n_gpus = 1; cfg.gpu_rank = 0;
+      cfg.pq_cap = deva::os_env<int>("DEVA_B200_PQ_CAP", 0);
+      cfg.inbox_cap = deva::os_env<int>("DEVA_B200_INBOX_CAP", 0);
+      cfg.log_cap = deva::os_env<int>("DEVA_B200_LOG_CAP", 0);
+      cfg.lp_n = g_sim.lp_n; cfg.lp_begin = 0; cfg.lp_count = g_sim.lp_n;
+      const long long look = deva::os_env<long long>("deva_static_look_dt", -1);   // pdes.cxx:36
+      cfg.window = look > 0 ? std::uint64_t(look) : 0;
+      g_sim.model->fill(&cfg.mp, deva::rank_n, g_sim.lp_n);
+      cfg.mp.user_subtime = g_sim.user_subtime ? 1 : 0;
+      ck(deva_b200_create(&cfg, &g_sim.eng), "deva_b200_create");
+    }
+    const int stw = deva_b200_state_words(g_sim.eng);
+    DEVA_ASSERT_ALWAYS(stw == g_sim.model->state_words);
+    std::vector<std::uint64_t> words;
+    gather_state(words, stw);
+    ck(deva_b200_set_lp_state(g_sim.eng, 0, g_sim.lp_n, words.data()), "deva_b200_set_lp_state");
+    std::vector<std::uint64_t> t, s; std::vector<std::uint32_t> lp, pay;
+    for(auto &rs: g_sim.ranks) {
+      for(auto &r: rs.roots) { t.push_back(r.time); s.push_back(r.sub); lp.push_back(r.lp); pay.push_back(r.payload); }
+      rs.roots.clear();
+    }
+    if(!t.empty()) ck(deva_b200_root_events(g_sim.eng, t.size(), t.data(), s.data(), lp.data(), pay.data()), "deva_b200_root_events");
+
+    // bench PHOLD's wall-clock cut-off (bench/phold.cxx:95-104): a watchdog flips the stop flag
+    std::atomic<bool> finished{false};
+    std::thread watchdog;
+    const double cutoff = g_sim.model->stop_after_secs();
+    if(cutoff >= 0) {
+      deva_b200_set_stop(g_sim.eng, 0);
+      watchdog = std::thread([&finished, cutoff] {
+        const auto t0 = std::chrono::steady_clock::now();
+        while(!finished.load()) {
+          if(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= cutoff) { deva_b200_set_stop(g_sim.eng, 1); break; }
+          std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        }
+      });
+    }
+    std::uint64_t gvt = 0;
+    const int rc = deva_b200_drain(g_sim.eng, t_end, rewindable ? 1 : 0, &gvt);
+    finished.store(true);
+    if(watchdog.joinable()) watchdog.join();
+    ck(rc, "deva_b200_drain");
+    g_sim.gvt = gvt;
+    g_sim.has_rewind = rewindable;
+    download_state();
+    deva_b200_stats st;
+    ck(deva_b200_get_stats(g_sim.eng, &st), "deva_b200_get_stats");
+    g_sim.stats.executed_n = st.executed_n;
+    g_sim.stats.committed_n = st.committed_n;
+    g_sim.stats.deterministic = st.deterministic != 0;
+  }
+  deva::barrier();
+  return g_sim.gvt;
+}
+
+void pdes::rewind(bool do_rewind) {                   // pdes.cxx:1137-1229
+  deva::barrier();
+  if(deva::rank_me() == 0) {
+    DEVA_ASSERT_ALWAYS(g_sim.has_rewind, "pdes::rewind without a rewindable drain");
+    g_sim.has_rewind = false;
+    ck(deva_b200_rewind(g_sim.eng, do_rewind ? 1 : 0), "deva_b200_rewind");
+    if(do_rewind) download_state();       // fridge::restore: the host copies go back too
+  }
+  deva::barrier();
+}
+
+void pdes::finalize() {                               // pdes.cxx:1060-1135
+  deva::barrier();
+  if(deva::rank_me() == 0) {
+    if(g_sim.eng) { deva_b200_destroy(g_sim.eng); g_sim.eng = nullptr; }
+    g_sim.has_rewind = false;
+    for(auto &rs: g_sim.ranks) { rs.regs.clear(); rs.roots.clear(); }
+  }
+  deva::barrier();
+}
+
+pdes::statistics pdes::local_stats() {
+  // the engine keeps one set of counters; rank 0 reports them so that reduce_sum(local_stats())
+  // (bench/phold.cxx:169, test/phold.cxx:147) yields the totals
+  return deva::rank_me() == 0 ? g_sim.stats : pdes::statistics();
+}
+
+std::pair<size_t, size_t> pdes::get_total_event_counts() {
+  pdes::statistics s = deva::reduce_sum(pdes::local_stats());
+  return {s.executed_n, s.committed_n};
+}

@@ -21,11 +21,12 @@ def main():
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        uid.copy_(torch.frombuffer(bytearray(E.comm_unique_id()), dtype=torch.uint8))
-    dist.broadcast(uid, 0)
-    uid_b = uid.cpu().numpy().tobytes()
+    def fresh_uid():   # an ncclUniqueId makes exactly one communicator
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(E.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        return uid.cpu().numpy().tobytes()
     ok_all = True
     cases = [dict(A=1000, K=16, P=0.5, LAM=100.0, END=300, window=20), dict(A=1000, K=16, P=0.1, LAM=100.0, END=300, window=0),
              dict(A=100000, K=16, P=0.5, LAM=100.0, END=300, window=0), dict(A=100000, K=16, P=0.10, LAM=100.0, END=300, window=32)]
@@ -35,7 +36,7 @@ def main():
         cnt = min(per, A - rank * per)
         eng = E.Engine(E.MODEL_PHOLD_TEST, A, lp_begin=rank * per, lp_count=cnt, device=local, n_gpus=world, gpu_rank=rank,
                        window=c["window"], p_remote=c["P"], lam=c["LAM"], end_time=c["END"])
-        eng.comm_init(uid_b)
+        eng.comm_init(fresh_uid())
         eng.seed_phold(c["K"], 1, 1)
         gvt = eng.drain()
         st = torch.from_numpy(eng.get_state().astype(np.int64)).cuda()

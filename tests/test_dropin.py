@@ -1,0 +1,75 @@
+"""The drop-in boundary in C++: the reference's OWN app sources, unchanged, compiled against
+include/devastator/*.hxx (dropin/build_dropin.py).
+
+ - CPU suite: when /root/reference is present (build container) test/phold.cxx is compiled against
+   the header mirror and linked with the host EMULATION of the engine ABI, which checks the C++
+   veneer (rank threads, collectives, state gather/scatter, root staging, rewind) without a GPU.
+ - GPU suite: the prebuilt product binaries (linked with libdeva_b200.so) run on the B200."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("DEVA_REFERENCE_ROOT", "/root/reference")
+BIN = os.path.join(ROOT, "dropin", "_bin")
+
+
+def parse_iterations(text):
+    its = []
+    for m in re.finditer(r"rewind enabled = (\d)\s+events = (\d+)\s+commits = (\d+)\s+deterministic = (\d)\s+checksum = (\d+)", text):
+        its.append(dict(rewind=int(m.group(1)), commits=int(m.group(3)), deterministic=int(m.group(4)), checksum=int(m.group(5))))
+    return its
+
+
+def check_phold_test_output(text):
+    assert "Looks good!" in text
+    its = parse_iterations(text)
+    assert len(its) == 4
+    for it in its:   # SURVEY.md Appendix B / tests/golden/ref_goldens.json
+        assert it["checksum"] == 15341107330209340805
+        assert it["commits"] == (361624 if it["rewind"] else 180812)
+        assert it["deterministic"] == 1
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+@pytest.mark.parametrize("R", [2, 3, 8])
+def test_reference_phold_test_source_through_cpp_mirror_emu(emu_api, tmp_path, R):
+    exe = str(tmp_path / f"phold_test_R{R}")
+    emu_dir = os.path.join(ROOT, "tests", "emu", "_build")
+    subprocess.check_call([
+        "g++", "-std=c++14", "-O2", "-pthread", "-w", f"-DDEVA_THREAD_N={R}", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1",
+        "-DDEBUG=0", f"-I{ROOT}/include", "-include", f"{ROOT}/include/devastator_b200/models/phold_test_model.hxx",
+        f"{REF}/test/phold.cxx", f"{ROOT}/devastator_b200/csrc/host_runtime.cpp", f"-L{emu_dir}", "-ldeva_b200_emu",
+        f"-Wl,-rpath,{emu_dir}", "-o", exe])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout
+    check_phold_test_output(out.stdout)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R", [2, 8])
+def test_reference_phold_test_source_on_gpu(R):
+    exe = os.path.join(BIN, f"phold_test_R{R}")
+    assert os.path.exists(exe), "dropin/_bin missing: run __graft_entry__.build() where /root/reference exists"
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout
+    check_phold_test_output(out.stdout)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R", [1, 4])
+def test_reference_phold_bench_source_on_gpu(R):
+    """bench/phold.cxx, unchanged: wall-clock terminated, so only plumbing is checked (config 1 of
+    SURVEY.md 8d): it runs, prints a report row, deterministic = 1."""
+    exe = os.path.join(BIN, f"phold_bench_R{R}")
+    assert os.path.exists(exe)
+    env = dict(os.environ, lp_per_rank=str(1024 // R), ray_per_lp="1", peer_stddev="2", wall_secs="1", report_file="-")
+    out = subprocess.run([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout
+    m = re.search(r"row\(xs=dict\((.*?)\),\s*ys=dict\((.*?)\)\)", out.stdout, re.S)
+    assert m, out.stdout
+    ys = dict(kv.split("=") for kv in m.group(2).replace(" ", "").split(","))
+    assert float(ys["deterministic"]) == 1
+    assert float(ys["commit_per_rank_per_sec"]) > 0
