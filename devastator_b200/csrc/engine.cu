@@ -44,15 +44,17 @@ static int fail(int code, const char *fmt, ...) {
 // kernels
 constexpr int PASS_THREADS = 128;
 
-template <class M>
-__global__ void __launch_bounds__(PASS_THREADS) k_pass(View v, ModelParams mp, PassArgs pa) {
+// MINB = minimum resident blocks per SM the register allocator must allow (occupancy knob)
+template <class M, int MINB>
+__global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(View v, ModelParams mp, PassArgs pa) {
   const uint32_t lp = blockIdx.x * PASS_THREADS + threadIdx.x;
   Acc acc;
   acc.tmin = ~0ull;
   acc.executed = acc.committed = acc.rolled = acc.anti = acc.remote = acc.err = acc.nondet = 0;
   if (lp < v.A) lp_pass<M>(v, mp, pa, lp, acc);
 
-  // block reduction: min for the GVT candidate, sums for the counters, or for the flags
+  // warp reduction (no block barrier: a finished warp leaves at once), then one RED per quantity
+  // into a counter slot picked by the block index
   unsigned long long tmin = acc.tmin;
   uint32_t ex = acc.executed, cm = acc.committed, rb = acc.rolled, an = acc.anti, rm = acc.remote;
   uint32_t fl = acc.err | (acc.nondet << 31);
@@ -67,26 +69,16 @@ __global__ void __launch_bounds__(PASS_THREADS) k_pass(View v, ModelParams mp, P
     rm += __shfl_xor_sync(0xffffffffu, rm, o);
     fl |= __shfl_xor_sync(0xffffffffu, fl, o);
   }
-  __shared__ unsigned long long s_t[PASS_THREADS / 32];
-  __shared__ uint32_t s_c[PASS_THREADS / 32][6];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { s_t[w] = tmin; s_c[w][0] = ex; s_c[w][1] = cm; s_c[w][2] = rb; s_c[w][3] = an; s_c[w][4] = rm; s_c[w][5] = fl; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 1; i < PASS_THREADS / 32; i++) {
-      tmin = s_t[i] < tmin ? s_t[i] : tmin;
-      ex += s_c[i][0]; cm += s_c[i][1]; rb += s_c[i][2]; an += s_c[i][3]; rm += s_c[i][4]; fl |= s_c[i][5];
-    }
+  if ((threadIdx.x & 31) == 0) {
     Ctl *c = v.ctl;
-    if (tmin != ~0ull) atomicMin(&c->gvt_next, tmin);
-    if (ex) atomicAdd(&c->executed, (unsigned long long)ex);
-    if (cm) atomicAdd(&c->committed, (unsigned long long)cm);
-    if (rb) atomicAdd(&c->rolled_back, (unsigned long long)rb);
-    if (an) atomicAdd(&c->anti_sent, (unsigned long long)an);
-    if (rm) atomicAdd(&c->remote_sent, (unsigned long long)rm);
-    if (fl & 0x7fffffffu) atomicOr(&c->err, fl & 0x7fffffffu);
-    if (fl >> 31) atomicOr(&c->nondeterministic, 1u);
+    const int slot = (int)((blockIdx.x * (PASS_THREADS / 32) + (threadIdx.x >> 5)) % CTL_SLOTS);
+    if (tmin != ~0ull) atomicMin(&c->gvt_slot[slot][0], tmin);
+    if (ex) atomicAdd(&c->cnt[slot][CNT_EXEC], (unsigned long long)ex);
+    if (cm) atomicAdd(&c->cnt[slot][CNT_COMMIT], (unsigned long long)cm);
+    if (rb) atomicAdd(&c->cnt[slot][CNT_ROLLED], (unsigned long long)rb);
+    if (an) atomicAdd(&c->cnt[slot][CNT_ANTI], (unsigned long long)an);
+    if (rm) atomicAdd(&c->cnt[slot][CNT_REMOTE], (unsigned long long)rm);
+    if (fl) atomicOr(&c->cnt[slot][CNT_FLAGS], (unsigned long long)fl);
   }
 }
 
@@ -106,7 +98,7 @@ __global__ void k_deliver(View v, const EvRec *recs, const uint32_t *n_ptr, uint
     const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, tmin, o);
     tmin = t2 < tmin ? t2 : tmin;
   }
-  if ((threadIdx.x & 31) == 0 && tmin != ~0ull) atomicMin(&v.ctl->gvt_next, tmin);
+  if ((threadIdx.x & 31) == 0 && tmin != ~0ull) atomicMin(&v.ctl->gvt_slot[blockIdx.x % CTL_SLOTS][0], tmin);
 }
 
 // root events given as structure-of-arrays columns (deva_b200_root_events): pack + deliver on the device
@@ -130,54 +122,20 @@ __global__ void k_min_head(View v) {
     const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, tmin, o);
     tmin = t2 < tmin ? t2 : tmin;
   }
-  if ((threadIdx.x & 31) == 0 && tmin != ~0ull) atomicMin(&v.ctl->gvt_next, tmin);
+  if ((threadIdx.x & 31) == 0 && tmin != ~0ull) atomicMin(&v.ctl->gvt_slot[blockIdx.x % CTL_SLOTS][0], tmin);
 }
 
 template <class M>
 __global__ void k_init(View v, ModelParams mp, int init_state) {
   const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lp >= v.A) return;
-  const uint64_t gid = v.lp_begin + lp;
-  v.head[lp] = ~0ull;
-  v.pcnt[lp] = 0;
-  v.icnt[0][lp] = 0;
-  v.icnt[1][lp] = 0;
-  v.lmeta[lp] = 0;
-  v.seq[lp] = gid;      // pdes.cxx:332: seq_id_bumper = global_cd_begin + i
-  v.lct[lp] = 0;        // pdes.cxx:333
-  v.lcs[lp] = 0;
-  uint64_t s[MAX_STW] = {0, 0, 0};
-  if (init_state) M::init_state(mp, gid, s);
-  for (int w = 0; w < M::STW; w++) v.st[(size_t)w * v.A + lp] = s[w];
+  if (lp < v.A) init_lp<M>(v, mp, lp, init_state);
 }
 
 // K roots per LP written straight into the LP's pending slots (no atomics: the owner writes).
 template <class M>
 __global__ void k_seed_roots(View v, ModelParams mp, uint32_t k, int rootdiv, uint64_t per_rank) {
   const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lp >= v.A) return;
-  const uint64_t gid = v.lp_begin + lp;
-  uint64_t head = ~0ull;
-  // LPs past the model's actor count exist only as padding of the rank decomposition
-  // (ranks*ceil(actor_n/ranks) > actor_n, test/phold.cxx:46): they get no roots
-  if (gid >= mp.lp_n_model) k = 0;
-  for (uint32_t j = 0; j < k; j++) {
-    EvRec e;
-    uint64_t ray;
-    if (M::MODEL_ID == 2) {          // bench/phold.cxx:154-157
-      ray = gid * k + j;
-      e.time = ray;
-    } else {                         // test/phold.cxx:172-178, PHOLD-T root time
-      ray = gid + (uint64_t)j * mp.lp_n_model;
-      e.time = rootdiv ? j : ray;
-    }
-    e.sub = mp.user_subtime ? ray : gid % per_rank;   // pdes.hxx:907: root subtime = LOCAL cd index
-    e.p0 = (uint32_t)ray; e.p1 = 0; e.dst = (uint32_t)gid; e.flags = 0;
-    st_ev(&v.pq[(size_t)j * v.A + lp], e);
-    head = e.time < head ? e.time : head;
-  }
-  v.pcnt[lp] = k;
-  v.head[lp] = head;
+  if (lp < v.A) seed_lp_roots<M>(v, mp, lp, k, rootdiv, per_rank);
 }
 
 // AoS host layout [count][STW]  <->  SoA device layout [STW][A]
@@ -190,27 +148,13 @@ __global__ void k_state_scatter(View v, const uint64_t *aos, uint32_t first, uin
   }
 }
 
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
-  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
-  return x;
-}
 __global__ void k_digest(View v, int stw, unsigned long long *out) {
-  unsigned long long x = 0, h = 0, pn = 0, ph = 0;
-  for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < v.A; lp += gridDim.x * blockDim.x) {
-    const uint64_t gid = v.lp_begin + lp;
-    x ^= v.st[(size_t)(stw - 1) * v.A + lp];
-    for (int w = 0; w < stw; w++) h += mix64(v.st[(size_t)w * v.A + lp] ^ mix64(gid * 4 + w + 1));
-    const uint32_t np = v.pcnt[lp];
-    pn += np;
-    for (uint32_t s = 0; s < np; s++) {
-      const EvRec e = ld_ev(&v.pq[(size_t)s * v.A + lp]);
-      ph += mix64(e.time ^ mix64(e.sub ^ mix64(((uint64_t)e.p0 << 32 | e.dst) + e.flags)));
-    }
-  }
-  atomicXor(&out[0], x);
-  atomicAdd(&out[1], h);
-  atomicAdd(&out[2], pn);
-  atomicAdd(&out[3], ph);
+  uint64_t acc[4] = {0, 0, 0, 0};
+  for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < v.A; lp += gridDim.x * blockDim.x) digest_lp(v, stw, lp, acc);
+  atomicXor(&out[0], (unsigned long long)acc[0]);
+  atomicAdd(&out[1], (unsigned long long)acc[1]);
+  atomicAdd(&out[2], (unsigned long long)acc[2]);
+  atomicAdd(&out[3], (unsigned long long)acc[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -260,6 +204,9 @@ static int nccl_load() {
 // nccl.h enums (stable ABI): ncclUint8=1, ncclUint32=3, ncclUint64=5; ncclSum=0, ncclMin=3, ncclMax=2
 enum { NC_U8 = 1, NC_U32 = 3, NC_U64 = 5, NC_SUM = 0, NC_MAX = 2, NC_MIN = 3 };
 
+// folded view of the spread reduction slots of Ctl
+struct CtlSum { uint64_t gvt_next, executed, committed, rolled_back, anti_sent, remote_sent; uint32_t err, nondet; };
+
 // ------------------------------------------------------------------------------------------------
 struct deva_b200_engine {
   deva_b200_config cfg;
@@ -270,6 +217,7 @@ struct deva_b200_engine {
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
   std::vector<void *> allocs;
   Ctl *h_ctl = nullptr;            // pinned mirror
+  CtlSum sum;                      // folded view of the last read
   unsigned long long *d_digest = nullptr;
   uint32_t par = 0;
   uint64_t gvt = 0;
@@ -290,6 +238,7 @@ struct deva_b200_engine {
   uint32_t *h_counts = nullptr;    // pinned
   unsigned long long *d_red = nullptr;  // allreduce scratch
   bool profile = true;
+  int pass_variant = 6;   // k_pass<M, MINB> instantiation (DEVA_B200_PASS_MINB = 4 | 6 | 8)
 };
 
 template <class T>
@@ -362,6 +311,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   v.ib_cap = cfg->inbox_cap > 0 ? cfg->inbox_cap : 16;
   v.log_cap = cfg->log_cap > 0 ? cfg->log_cap : 48;
   if (v.log_cap > 65535) return fail(DEVA_B200_ERR_ARG, "log_cap must be < 65536");
+  if (v.pq_cap > MAX_PQ_CAP) return fail(DEVA_B200_ERR_ARG, "pq_cap must be <= %d", MAX_PQ_CAP);
   v.lp_begin = cfg->lp_begin;
   v.lp_n = cfg->lp_n;
   v.n_gpus = cfg->n_gpus;
@@ -372,7 +322,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n)))) { deva_b200_destroy(e); return rc; }
   DA(v.head, A) DA(v.pcnt, A) DA(v.icnt[0], A) DA(v.icnt[1], A) DA(v.lmeta, A)
   DA(v.st, A * e->stw) DA(v.seq, A) DA(v.lct, A) DA(v.lcs, A)
-  DA(v.pq, A * v.pq_cap) DA(v.ib[0], A * v.ib_cap) DA(v.ib[1], A * v.ib_cap) DA(v.lg, A * v.log_cap)
+  DA(v.pq_t, A * v.pq_cap) DA(v.pq_r, A * v.pq_cap) DA(v.ib[0], A * v.ib_cap) DA(v.ib[1], A * v.ib_cap) DA(v.lg, A * v.log_cap)
   DA(v.ctl, 1)
   v.spill_cap = (uint32_t)std::min<size_t>(std::max<size_t>(A * 2, 1u << 16), 1u << 26);
   DA(v.spill, v.spill_cap)
@@ -405,6 +355,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   e->wp.init(cfg->window);
   const char *prof = getenv("DEVA_B200_PROFILE");
   if (prof) e->profile = atoi(prof) != 0;
+  if (const char *pv = getenv("DEVA_B200_PASS_MINB")) e->pass_variant = atoi(pv);
   // snapshot list for rewind
   *out = e;
   return 0;
@@ -458,15 +409,27 @@ int deva_b200_get_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t coun
 }
 
 static int check_ctl_err(deva_b200_engine *e) {
-  const uint32_t err = e->h_ctl->err;
+  const uint32_t err = e->sum.err;
   if (!err) return 0;
   const int code = (err & (ERR_PQ_OVERFLOW | ERR_SPILL_OVERFLOW | ERR_SEND_OVERFLOW)) ? DEVA_B200_ERR_CAPACITY : DEVA_B200_ERR_INVARIANT;
   return fail(code, "engine error 0x%x: %s", err, err_text(err));
 }
 
+// host-side fold of the spread reduction slots
+static CtlSum fold_ctl(const Ctl *c) {
+  CtlSum s; memset(&s, 0, sizeof s); s.gvt_next = ~0ull; s.err = c->err;
+  for (int i = 0; i < CTL_SLOTS; i++) {
+    s.gvt_next = std::min<uint64_t>(s.gvt_next, c->gvt_slot[i][0]);
+    s.executed += c->cnt[i][CNT_EXEC]; s.committed += c->cnt[i][CNT_COMMIT]; s.rolled_back += c->cnt[i][CNT_ROLLED];
+    s.anti_sent += c->cnt[i][CNT_ANTI]; s.remote_sent += c->cnt[i][CNT_REMOTE];
+    s.err |= (uint32_t)(c->cnt[i][CNT_FLAGS] & 0x7fffffffu); s.nondet |= (uint32_t)((c->cnt[i][CNT_FLAGS] >> 31) & 1u);
+  }
+  return s;
+}
 static int read_ctl(deva_b200_engine *e) {
   CU(cudaMemcpyAsync(e->h_ctl, e->v.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
+  e->sum = fold_ctl(e->h_ctl);
   return 0;
 }
 
@@ -601,7 +564,11 @@ static int launch_pass(deva_b200_engine *e, const PassArgs &pa) {
   if (e->profile) CU(cudaEventRecord(e->ev_a, e->stream));
   dispatch_model(e->cfg.model, [&](auto m) {
     using M = decltype(m);
-    k_pass<M><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa);
+    switch (e->pass_variant) {
+      case 4: k_pass<M, 4><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa); break;
+      case 8: k_pass<M, 8><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa); break;
+      default: k_pass<M, 6><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa); break;
+    }
     return 0;
   });
   e->launches++;
@@ -614,12 +581,12 @@ static int launch_pass(deva_b200_engine *e, const PassArgs &pa) {
 static int run_window(deva_b200_engine *e, uint64_t ub, uint32_t sweep, uint64_t *win_exec, uint64_t *win_rolled) {
   View &v = e->v;
   // reset the GVT accumulator (0xff.. == ~0ull)
-  CU(cudaMemsetAsync(&v.ctl->gvt_next, 0xff, sizeof(unsigned long long), e->stream));
+  CU(cudaMemsetAsync(v.ctl->gvt_slot, 0xff, sizeof(v.ctl->gvt_slot), e->stream));
   PassArgs pa;
   pa.gvt = e->gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep;
   int rc = launch_pass(e, pa);
   if (rc) return rc;
-  const Ctl before = *e->h_ctl;
+  const CtlSum before = e->sum;
   if ((rc = read_ctl(e))) return rc;
   if (e->profile) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->exec_ms += ms; }
   e->passes++;
@@ -632,15 +599,15 @@ static int run_window(deva_b200_engine *e, uint64_t ub, uint32_t sweep, uint64_t
     CU(cudaMemsetAsync(&v.ctl->spill_n, 0, sizeof(uint32_t), e->stream));
     if ((rc = read_ctl(e))) return rc;
   }
-  uint64_t gvt = e->h_ctl->gvt_next;
-  uint64_t wx = e->h_ctl->executed - before.executed, wr = e->h_ctl->rolled_back - before.rolled_back;
-  uint32_t err = e->h_ctl->err;
+  uint64_t gvt = e->sum.gvt_next;
+  uint64_t wx = e->sum.executed - before.executed, wr = e->sum.rolled_back - before.rolled_back;
+  uint32_t err = e->sum.err;
   if (e->cfg.n_gpus > 1) {
     if ((rc = exchange(e))) return rc;
     if ((rc = read_ctl(e))) return rc;       // k_deliver may have raised a capacity error
-    err = e->h_ctl->err;
+    err = e->sum.err;
     if ((rc = allreduce_gvt(e, &gvt, &wx, &wr, &err))) return rc;
-    e->h_ctl->err = err;
+    e->sum.err = err;
   }
   if ((rc = check_ctl_err(e))) return rc;
   e->gvt = gvt;
@@ -664,7 +631,7 @@ int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uin
       const size_t A = v.A;
       struct { void *p; size_t b; } live[] = {
           {v.head, A * 8}, {v.pcnt, A * 4}, {v.st, A * e->stw * 8}, {v.seq, A * 8}, {v.lct, A * 8}, {v.lcs, A * 8},
-          {v.pq, A * v.pq_cap * sizeof(EvRec)}};
+          {v.pq_t, A * v.pq_cap * sizeof(uint64_t)}, {v.pq_r, A * v.pq_cap * sizeof(PqRest)}};
       for (auto &l : live) {
         void *s = nullptr;
         CU(cudaMalloc(&s, l.b));
@@ -677,13 +644,13 @@ int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uin
     e->has_rewind = true;
   }
   // initial GVT = min over LP heads (pdes.cxx:755-759: reduce_min(lvt))
-  CU(cudaMemsetAsync(&v.ctl->gvt_next, 0xff, sizeof(unsigned long long), e->stream));
+  CU(cudaMemsetAsync(v.ctl->gvt_slot, 0xff, sizeof(v.ctl->gvt_slot), e->stream));
   k_min_head<<<148 * 4, 256, 0, e->stream>>>(v);
   e->launches++;
   CU(cudaGetLastError());
   if ((rc = read_ctl(e))) return rc;
   if ((rc = check_ctl_err(e))) return rc;
-  uint64_t gvt = e->h_ctl->gvt_next;
+  uint64_t gvt = e->sum.gvt_next;
   if (e->cfg.n_gpus > 1) {
     uint64_t a = 0, b = 0; uint32_t er = 0;
     if ((rc = allreduce_gvt(e, &gvt, &a, &b, &er))) return rc;
@@ -718,9 +685,9 @@ int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uin
   CU(cudaEventElapsedTime(&ms, e->ev_d0, e->ev_d1));
   e->drain_ms += ms;
   // fold counters into the cumulative statistics (pdes::local_stats)
-  e->executed = e->h_ctl->executed; e->committed = e->h_ctl->committed; e->rolled = e->h_ctl->rolled_back;
-  e->anti = e->h_ctl->anti_sent; e->remote = e->h_ctl->remote_sent;
-  e->nondet = e->h_ctl->nondeterministic != 0;
+  e->executed = e->sum.executed; e->committed = e->sum.committed; e->rolled = e->sum.rolled_back;
+  e->anti = e->sum.anti_sent; e->remote = e->sum.remote_sent;
+  e->nondet = e->sum.nondet != 0;
   if (gvt_out) *gvt_out = e->gvt;
   return 0;
 }

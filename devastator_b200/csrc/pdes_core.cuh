@@ -30,7 +30,7 @@
 namespace deva_b200 {
 
 #ifndef DEVA_WK_CAP
-#define DEVA_WK_CAP 32   // in-window working set per LP (events sorted in thread-local memory)
+#define DEVA_WK_CAP 24   // in-window working set per LP (events sorted in thread-local memory)
 #endif
 #ifndef DEVA_AN_CAP
 #define DEVA_AN_CAP 8    // anti-messages handled per LP per window (extra ones wait in pending)
@@ -53,6 +53,27 @@ DEVA_HD void st_ev(EvRec *p, const EvRec &e) {
   reinterpret_cast<uint4 *>(p)[0] = make_uint4((uint32_t)e.time, (uint32_t)(e.time >> 32), (uint32_t)e.sub, (uint32_t)(e.sub >> 32));
   reinterpret_cast<uint4 *>(p)[1] = make_uint4(e.p0, e.p1, e.dst, e.flags);
 }
+DEVA_HD PqRest ld_rest(const PqRest *p) {
+  const uint4 a = *reinterpret_cast<const uint4 *>(p);
+  PqRest r; r.sub = ((uint64_t)a.y << 32) | a.x; r.p0 = a.z; r.p1f = a.w; return r;
+}
+DEVA_HD void st_rest(PqRest *p, const PqRest &r) {
+  *reinterpret_cast<uint4 *>(p) = make_uint4((uint32_t)r.sub, (uint32_t)(r.sub >> 32), r.p0, r.p1f);
+}
+DEVA_HD LogRec ld_log(const LogRec *p) {
+  const uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1], c = reinterpret_cast<const uint4 *>(p)[2];
+  LogRec l;
+  l.time = ((uint64_t)a.y << 32) | a.x; l.sub = ((uint64_t)a.w << 32) | a.z;
+  l.p0 = b.x; l.fl = b.y; l.st[0] = ((uint64_t)b.w << 32) | b.z;
+  l.st[1] = ((uint64_t)c.y << 32) | c.x; l.st[2] = ((uint64_t)c.w << 32) | c.z;
+  return l;
+}
+DEVA_HD void st_log(LogRec *p, const LogRec &l) {
+  reinterpret_cast<uint4 *>(p)[0] = make_uint4((uint32_t)l.time, (uint32_t)(l.time >> 32), (uint32_t)l.sub, (uint32_t)(l.sub >> 32));
+  reinterpret_cast<uint4 *>(p)[1] = make_uint4(l.p0, l.fl, (uint32_t)l.st[0], (uint32_t)(l.st[0] >> 32));
+  reinterpret_cast<uint4 *>(p)[2] = make_uint4((uint32_t)l.st[1], (uint32_t)(l.st[1] >> 32), (uint32_t)l.st[2], (uint32_t)(l.st[2] >> 32));
+}
+DEVA_HD int ffs64(uint64_t x) { return __ffsll((long long)x); }
 // warp-aggregated slot claim on a hot counter (peer-GPU staging): lanes that are converged here and
 // target the same counter elect one atomicAdd.
 __device__ __forceinline__ uint32_t agg_claim(uint32_t *ctr, uint32_t key) {
@@ -71,6 +92,11 @@ DEVA_HD void atom_or_u32(uint32_t *p, uint32_t v) { *p |= v; }
 DEVA_HD void atom_min_u64(uint64_t *p, uint64_t v) { if (v < *p) *p = v; }
 DEVA_HD EvRec ld_ev(const EvRec *p) { return *p; }
 DEVA_HD void st_ev(EvRec *p, const EvRec &e) { *p = e; }
+DEVA_HD PqRest ld_rest(const PqRest *p) { return *p; }
+DEVA_HD void st_rest(PqRest *p, const PqRest &r) { *p = r; }
+DEVA_HD LogRec ld_log(const LogRec *p) { return *p; }
+DEVA_HD void st_log(LogRec *p, const LogRec &l) { *p = l; }
+DEVA_HD int ffs64(uint64_t x) { return __builtin_ffsll((long long)x); }
 DEVA_HD uint32_t agg_claim(uint32_t *ctr, uint32_t) { return atom_add_u32(ctr, 1); }
 #endif
 
@@ -80,6 +106,8 @@ DEVA_HD bool key_less(uint64_t t1, uint64_t s1, uint64_t t2, uint64_t s2) {  // 
 DEVA_HD bool same_event(const EvRec &a, const EvRec &b) {
   return a.time == b.time && a.sub == b.sub && a.p0 == b.p0 && a.p1 == b.p1;
 }
+constexpr uint32_t P1_ANTI = 0x80000000u;   // PqRest::p1f anti-message bit
+constexpr uint32_t FL_SENT = 0x80000000u;   // LogRec::fl "sent a child" bit
 
 // per-thread accumulators, block-reduced by the kernel wrapper
 struct Acc {
@@ -107,9 +135,8 @@ struct WorkSet {
       n--;
       evicted = 1;
     }
-    int i = n;   // shift smaller-keyed entries (at the end) right until the slot for e is found
+    int i = n;   // entries not larger than e sit at the end and move one place right
     while (i > 0 && !key_less(e.time, e.sub, t[i - 1], s[i - 1])) {
-      // e >= entry i-1  -> entry i-1 (smaller or equal) must stay AFTER e: move it right
       t[i] = t[i - 1]; s[i] = s[i - 1]; p0[i] = p0[i - 1]; p1[i] = p1[i - 1];
       i--;
     }
@@ -152,6 +179,18 @@ DEVA_HD void deliver(const View &v, uint32_t par_next, const EvRec &rec, Acc &ac
   }
 }
 
+DEVA_HD void pq_store(const View &v, uint32_t lp, uint32_t slot, const EvRec &e) {
+  v.pq_t[(size_t)slot * v.A + lp] = e.time;
+  PqRest r; r.sub = e.sub; r.p0 = e.p0; r.p1f = (e.p1 & ~P1_ANTI) | ((e.flags & EV_ANTI) ? P1_ANTI : 0u);
+  st_rest(&v.pq_r[(size_t)slot * v.A + lp], r);
+}
+DEVA_HD EvRec pq_load(const View &v, uint32_t lp, uint32_t slot, uint64_t t, uint32_t dst) {
+  const PqRest r = ld_rest(&v.pq_r[(size_t)slot * v.A + lp]);
+  EvRec e; e.time = t; e.sub = r.sub; e.p0 = r.p0; e.p1 = r.p1f & ~P1_ANTI; e.dst = dst;
+  e.flags = (r.p1f & P1_ANTI) ? EV_ANTI : 0u;
+  return e;
+}
+
 template <class M>
 DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, uint32_t lp, Acc &acc) {
   const size_t A = v.A;
@@ -166,19 +205,40 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     return;
   }
   const uint64_t gid = v.lp_begin + lp;
+  const uint32_t gid32 = (uint32_t)gid;
   const uint32_t par_next = pa.par ^ 1u;
 
   // ---- phase 0: fossil collection - commit log entries with time < GVT (pdes.cxx:816-871) -------
+  // The first PF tail entries are fetched together (independent loads in flight), the rare rest
+  // one by one.
   if (ln > 0) {
+    constexpr int PF = 4;
+    uint64_t pt[PF], ps[PF];
+#pragma unroll
+    for (int i = 0; i < PF; i++) {
+      uint32_t idx = lt + i; if (idx >= v.log_cap) idx -= v.log_cap;
+      const bool ok = (uint32_t)i < ln;
+      const LogRec *lr = &v.lg[(size_t)(ok ? idx : lt) * A + lp];
+      pt[i] = ok ? lr->time : ~0ull;
+      ps[i] = ok ? lr->sub : 0ull;
+    }
     uint64_t lct = v.lct[lp], lcs = v.lcs[lp];
     bool any = false;
+    int k = 0;
     while (ln > 0) {
-      const EvRec *le = &v.lg[(size_t)lt * A + lp].ev;
-      const uint64_t t = le->time;
+      uint64_t t, sb;
+      if (k < PF) {
+        t = pt[0]; sb = ps[0];
+#pragma unroll
+        for (int i = 0; i + 1 < PF; i++) { pt[i] = pt[i + 1]; ps[i] = ps[i + 1]; }
+      } else {
+        const LogRec *lr = &v.lg[(size_t)lt * A + lp];
+        t = lr->time; sb = lr->sub;
+      }
+      k++;
       if (t >= pa.gvt) break;       // strict <, pdes.cxx:825
-      const uint64_t s = le->sub;
-      if (!key_less(lct, lcs, t + 1, s)) acc.nondet = 1;   // pdes.cxx:828-831
-      lct = t + 1; lcs = s;
+      if (!key_less(lct, lcs, t + 1, sb)) acc.nondet = 1;   // pdes.cxx:828-831
+      lct = t + 1; lcs = sb;
       lt = (lt + 1 == v.log_cap) ? 0 : lt + 1;
       ln--;
       acc.committed++;
@@ -197,88 +257,133 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   for (int w = 0; w < M::STW; w++) st[w] = v.st[(size_t)w * A + lp];
   uint64_t seq = v.seq[lp];
 
-  // ---- phase 1: fold pending slots + this window's arrivals into {working set, antis, kept} -----
+  // ---- phase 1: fold pending slots + this window's arrivals -------------------------------------
+  // The pending pool is NOT compacted: slots whose event is taken become holes (bitmask `hole`),
+  // new pending records fill holes first, and only what is left of the holes is closed at the end
+  // by moving tail records down.  Records that stay are never rewritten.
   WorkSet wk; wk.n = 0;
   EvRec an[DEVA_AN_CAP]; int na = 0;
-  uint32_t nk = 0;           // kept pending records, compacted in place into pq[0..nk)
-  uint64_t khead = ~0ull;    // min time over kept
+  uint64_t hole = 0;            // bit s: slot s (< top) is free
+  uint32_t top = np;            // slots in use: [0, top) minus holes
+  uint64_t khead = ~0ull;       // min time over pending records (valid unless khead_dirty)
   bool khead_dirty = false;
-  bool anti_overflow = false;   // more than DEVA_AN_CAP anti-messages this window (rare)
+  bool anti_overflow = false;   // an in-window anti-message stayed in the pool (an[] was full)
 
-  auto keep = [&](const EvRec &e) {
-    if (nk >= v.pq_cap) { acc.err |= ERR_PQ_OVERFLOW; return; }
-    st_ev(&v.pq[(size_t)nk * A + lp], e);
-    nk++;
+  auto put_pending = [&](const EvRec &e) {
+    uint32_t s;
+    if (hole) { s = (uint32_t)ffs64(hole) - 1u; hole &= hole - 1; }
+    else {
+      if (top >= v.pq_cap) { acc.err |= ERR_PQ_OVERFLOW; return; }
+      s = top++;
+    }
+    pq_store(v, lp, s, e);
     if (e.time < khead) khead = e.time;
   };
-  auto consider = [&](const EvRec &e) {
+  auto take_slot = [&](uint32_t s) { hole |= 1ull << s; };
+
+  // Stage A: every pending time of this LP in flight at once (8 B per slot, coalesced across the
+  // warp), reduced to a bitmask of the slots below the window bound.
+  uint64_t inwin = 0;
+  {
+    constexpr int CH = 16;
+    for (uint32_t base = 0; base < np; base += CH) {
+      uint64_t tt[CH];
+#pragma unroll
+      for (int i = 0; i < CH; i++) tt[i] = (base + i < np) ? v.pq_t[(size_t)(base + i) * A + lp] : ~0ull;
+#pragma unroll
+      for (int i = 0; i < CH; i++) {
+        if (tt[i] < pa.ub) inwin |= 1ull << (base + i);      // (~0 for absent slots is never < ub)
+        else if (tt[i] < khead) khead = tt[i];
+      }
+    }
+  }
+  // Stage B: the records of the in-window slots, fetched four at a time (loads issued together).
+  auto fold_pool_record = [&](const EvRec &e, uint32_t s) {
     if (e.flags & EV_ANTI) {
-      if (na < DEVA_AN_CAP) an[na++] = e; else { keep(e); anti_overflow = true; }
-    } else if (e.time < pa.ub) {
+      if (na < DEVA_AN_CAP) { an[na++] = e; take_slot(s); }
+      else { anti_overflow = true; if (e.time < khead) khead = e.time; }
+    } else {
       EvRec out;
-      const int r = wk.insert(e, out, (uint32_t)gid);
-      if (r == 1) keep(out); else if (r == 2) keep(e);
-    } else keep(e);
+      const int r = wk.insert(e, out, gid32);
+      if (r == 0) take_slot(s);
+      else if (r == 1) { pq_store(v, lp, s, out); if (out.time < khead) khead = out.time; }   // evicted one takes the slot
+      else if (e.time < khead) khead = e.time;                                                // rejected: stays
+    }
   };
-  for (uint32_t s = 0; s < np; s++) consider(ld_ev(&v.pq[(size_t)s * A + lp]));   // nk <= s: in-place safe
+  while (inwin) {
+    constexpr int RB = 4;
+    uint32_t ss[RB];
+    EvRec ee[RB];
+#pragma unroll
+    for (int i = 0; i < RB; i++) {
+      ss[i] = inwin ? (uint32_t)ffs64(inwin) - 1u : 0xffffffffu;
+      inwin &= inwin - 1;
+    }
+#pragma unroll
+    for (int i = 0; i < RB; i++)
+      if (ss[i] != 0xffffffffu) ee[i] = pq_load(v, lp, ss[i], v.pq_t[(size_t)ss[i] * A + lp], gid32);
+#pragma unroll
+    for (int i = 0; i < RB; i++)
+      if (ss[i] != 0xffffffffu) fold_pool_record(ee[i], ss[i]);
+  }
   if (ni > 0) {
     if (ni > v.ib_cap) ni = v.ib_cap;
-    for (uint32_t s = 0; s < ni; s++) consider(ld_ev(&v.ib[pa.par][(size_t)s * A + lp]));
+    auto fold_arrival = [&](const EvRec &e) {
+      if (e.flags & EV_ANTI) {
+        if (na < DEVA_AN_CAP) an[na++] = e; else { put_pending(e); anti_overflow |= e.time < pa.ub; }
+      } else if (e.time < pa.ub) {
+        EvRec out;
+        const int r = wk.insert(e, out, gid32);
+        if (r == 1) put_pending(out); else if (r == 2) put_pending(e);
+      } else put_pending(e);
+    };
+    for (uint32_t base = 0; base < ni; base += 4) {
+      EvRec ee[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) if (base + i < ni) ee[i] = ld_ev(&v.ib[pa.par][(size_t)(base + i) * A + lp]);
+#pragma unroll
+      for (int i = 0; i < 4; i++) if (base + i < ni) fold_arrival(ee[i]);
+    }
     v.icnt[pa.par][lp] = 0;
   }
 
-  // kept-slot helpers (rare paths: anti-message for an event beyond the window, surplus antis)
-  auto find_kept = [&](const EvRec &a, uint32_t want_flags) -> int {
-    for (uint32_t s = 0; s < nk; s++) {
-      const EvRec e = ld_ev(&v.pq[(size_t)s * A + lp]);
-      if ((e.flags & EV_ANTI) == want_flags && same_event(e, a)) return (int)s;
+  // pool helpers for the rare paths (slot indices are stable: removal only sets a hole bit)
+  auto find_pending = [&](const EvRec &a, uint32_t want_anti) -> int {
+    for (uint32_t s = 0; s < top; s++) {
+      if ((hole >> s) & 1ull) continue;
+      if (v.pq_t[(size_t)s * A + lp] != a.time) continue;
+      const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
+      if (r.sub == a.sub && r.p0 == a.p0 && (r.p1f & ~P1_ANTI) == a.p1 && ((r.p1f & P1_ANTI) ? 1u : 0u) == want_anti) return (int)s;
     }
     return -1;
   };
-  auto remove_kept_at = [&](uint32_t s) {
-    nk--;
-    if (s != nk) st_ev(&v.pq[(size_t)s * A + lp], ld_ev(&v.pq[(size_t)nk * A + lp]));
-    khead_dirty = true;
-  };
-  auto remove_kept = [&](const EvRec &a) -> bool {   // remove one POSITIVE identical to a
-    const int s = find_kept(a, 0u);
+  auto remove_pending = [&](const EvRec &a) -> bool {   // remove one POSITIVE identical to a
+    const int s = find_pending(a, 0u);
     if (s < 0) return false;
-    remove_kept_at((uint32_t)s);
+    take_slot((uint32_t)s);
+    khead_dirty = true;
     return true;
   };
 
   // ---- phase 2: annihilate anti-messages against not-yet-executed positives ----------------------
-  // (arrive_near<-1> with future_not_past, pdes.cxx:480-487).  Every anti-message is resolved in
-  // the window it arrives in: an[] is the fast path, the surplus (n_kept_anti) sits in kept slots.
+  // (arrive_near<-1> with future_not_past, pdes.cxx:480-487)
   uint64_t anti_t = ~0ull, anti_s = ~0ull;   // min key over antis whose positive already ran
   int na_log = 0;
   for (int i = 0; i < na; i++) {
-    if (wk.remove_match(an[i]) || remove_kept(an[i])) continue;
+    if (wk.remove_match(an[i]) || remove_pending(an[i])) continue;
     an[na_log++] = an[i];                    // positive is in the undo log: roll back through it
     if (key_less(an[i].time, an[i].sub, anti_t, anti_s)) { anti_t = an[i].time; anti_s = an[i].sub; }
   }
-  uint32_t n_kept_anti = 0;                  // surplus antis whose positive already ran
+  uint32_t n_pool_anti = 0;                  // in-window antis still in the pool whose positive already ran
   if (anti_overflow) {
-    uint32_t s = 0;
-    while (s < nk) {
-      const EvRec a = ld_ev(&v.pq[(size_t)s * A + lp]);
-      if (!(a.flags & EV_ANTI)) { s++; continue; }
-      if (wk.remove_match(a)) { remove_kept_at(s); continue; }   // slot s now holds another record
-      const int q = find_kept(a, 0u);
-      if (q >= 0) {   // remove the pair; take the higher index out first so the lower stays valid
-        const uint32_t hi = (uint32_t)q > s ? (uint32_t)q : s, lo = (uint32_t)q > s ? s : (uint32_t)q;
-        remove_kept_at(hi);
-        remove_kept_at(lo);
-        s = lo;       // re-examine what was swapped into the lower slot
-        continue;
-      }
-      s++;   // positive already ran: stays here until phase 3 undoes it
-    }
-    // survivors are counted after the sweep (pair removal above may move an examined record)
-    for (uint32_t q = 0; q < nk; q++) {
-      const EvRec a = ld_ev(&v.pq[(size_t)q * A + lp]);
+    for (uint32_t s = 0; s < top; s++) {
+      if ((hole >> s) & 1ull) continue;
+      const uint64_t t = v.pq_t[(size_t)s * A + lp];
+      if (t >= pa.ub) continue;
+      const EvRec a = pq_load(v, lp, s, t, gid32);
       if (!(a.flags & EV_ANTI)) continue;
-      n_kept_anti++;
+      if (wk.remove_match(a) || remove_pending(a)) { take_slot(s); khead_dirty = true; continue; }
+      n_pool_anti++;
       if (key_less(a.time, a.sub, anti_t, anti_s)) { anti_t = a.time; anti_s = a.sub; }
     }
   }
@@ -286,31 +391,35 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     anti_t = ~0ull; anti_s = ~0ull;
     for (int i = 0; i < na_log; i++)
       if (key_less(an[i].time, an[i].sub, anti_t, anti_s)) { anti_t = an[i].time; anti_s = an[i].sub; }
-    if (n_kept_anti)
-      for (uint32_t s = 0; s < nk; s++) {
-        const EvRec a = ld_ev(&v.pq[(size_t)s * A + lp]);
-        if ((a.flags & EV_ANTI) && key_less(a.time, a.sub, anti_t, anti_s)) { anti_t = a.time; anti_s = a.sub; }
+    if (n_pool_anti)
+      for (uint32_t s = 0; s < top; s++) {
+        if ((hole >> s) & 1ull) continue;
+        const uint64_t t = v.pq_t[(size_t)s * A + lp];
+        if (t >= pa.ub) continue;
+        const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
+        if ((r.p1f & P1_ANTI) && key_less(t, r.sub, anti_t, anti_s)) { anti_t = t; anti_s = r.sub; }
       }
   };
 
   // ---- phase 3: straggler / anti-message rollback (insert_past, remove_past, rollback) -----------
-  const bool have_log_anti = na_log > 0 || n_kept_anti > 0;
-  if (ln > 0 && (wk.n > 0 || have_log_anti)) {
+  if (ln > 0 && (wk.n > 0 || na_log > 0 || n_pool_anti > 0)) {
     const uint64_t sg_t = wk.n > 0 ? wk.t[wk.n - 1] : ~0ull;   // smallest in-window key = straggler
     const uint64_t sg_s = wk.n > 0 ? wk.s[wk.n - 1] : ~0ull;
     while (ln > 0) {
       uint32_t li = lt + ln - 1; if (li >= v.log_cap) li -= v.log_cap;
-      const LogRec *lr = &v.lg[(size_t)li * A + lp];
-      const EvRec le = ld_ev(&lr->ev);
+      const LogRec *lrp = &v.lg[(size_t)li * A + lp];
+      const uint64_t lt_time = lrp->time, lt_sub = lrp->sub;
       // undo while the newest processed event is later than the straggler, or not earlier than
       // an anti-message's target (the target itself must be undone)
-      const bool undo = key_less(sg_t, sg_s, le.time, le.sub) ||
-                        ((na_log > 0 || n_kept_anti > 0) && !key_less(le.time, le.sub, anti_t, anti_s));
+      const bool undo = key_less(sg_t, sg_s, lt_time, lt_sub) ||
+                        ((na_log > 0 || n_pool_anti > 0) && !key_less(lt_time, lt_sub, anti_t, anti_s));
       if (!undo) break;
-      if (le.time < pa.gvt) acc.err |= ERR_BELOW_GVT;         // would undo a committable event
+      if (lt_time < pa.gvt) acc.err |= ERR_BELOW_GVT;          // would undo a committable event
+      const LogRec lr = ld_log(lrp);
+      EvRec le; le.time = lr.time; le.sub = lr.sub; le.p0 = lr.p0; le.p1 = lr.fl & ~FL_SENT; le.dst = gid32; le.flags = 0;
 #pragma unroll
-      for (int w = 0; w < M::STW; w++) st[w] = lr->st[w];      // == reverse::unexecute
-      if (le.flags & EV_SENT) {
+      for (int w = 0; w < M::STW; w++) st[w] = lr.st[w];       // == reverse::unexecute
+      if (lr.fl & FL_SENT) {
         // regenerate the child from the restored pre-state and cancel it
         uint64_t tmp[MAX_STW];
 #pragma unroll
@@ -320,7 +429,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
         seq -= v.lp_n;                                         // pdes.cxx:566,574
         if (!mp.user_subtime) c.sub = seq;
         if ((uint64_t)c.dst == gid) {
-          if (!(wk.remove_match(c) || remove_kept(c))) acc.err |= ERR_SELF_CHILD_LOST;
+          if (!(wk.remove_match(c) || remove_pending(c))) acc.err |= ERR_SELF_CHILD_LOST;
         } else {
           c.flags = EV_ANTI;
           deliver(v, par_next, c, acc);
@@ -331,53 +440,41 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
       bool dead = false;
       for (int i = 0; i < na_log; i++)
         if (same_event(an[i], le)) { an[i] = an[na_log - 1]; na_log--; dead = true; break; }
-      if (!dead && n_kept_anti) {
-        const int q = find_kept(le, EV_ANTI);
-        if (q >= 0) { remove_kept_at((uint32_t)q); n_kept_anti--; dead = true; }
+      if (!dead && n_pool_anti) {
+        const int q = find_pending(le, 1u);
+        if (q >= 0) { take_slot((uint32_t)q); khead_dirty = true; n_pool_anti--; dead = true; }
       }
       if (dead) {
         recompute_anti_min();
       } else {
-        EvRec e = le; e.flags = 0; e.dst = (uint32_t)gid;
         EvRec out;
-        const int r = (e.time < pa.ub) ? wk.insert(e, out, (uint32_t)gid) : 2;
-        if (r == 1) keep(out); else if (r == 2) keep(e);
+        const int r = (le.time < pa.ub) ? wk.insert(le, out, gid32) : 2;
+        if (r == 1) put_pending(out); else if (r == 2) put_pending(le);
       }
       ln--;
       acc.rolled++;
     }
-    if (na_log > 0 || n_kept_anti > 0) {
-      acc.err |= ERR_ANTI_UNMATCHED;
-#if defined(DEVA_EMU_DEBUG)
-      fprintf(stderr, "ANTI_UNMATCHED(a) lp=%llu na_log=%d nka=%u anti0(t=%llu,s=%llu) ub=%llu gvt=%llu ln=%u wk.n=%d nk=%u sweep=%u\n", (unsigned long long)gid, na_log, n_kept_anti,
-              (unsigned long long)(na_log ? an[0].time : 0), (unsigned long long)(na_log ? an[0].sub : 0), (unsigned long long)pa.ub, (unsigned long long)pa.gvt, ln, wk.n, nk, pa.sweep);
-#endif
-    }
-  } else if (have_log_anti) {
-    acc.err |= ERR_ANTI_UNMATCHED;
-#if defined(DEVA_EMU_DEBUG)
-    fprintf(stderr, "ANTI_UNMATCHED(b) lp=%llu na_log=%d nka=%u anti0(t=%llu,s=%llu) ub=%llu gvt=%llu ln=%u wk.n=%d nk=%u sweep=%u\n", (unsigned long long)gid, na_log, n_kept_anti,
-            (unsigned long long)(na_log ? an[0].time : 0), (unsigned long long)(na_log ? an[0].sub : 0), (unsigned long long)pa.ub, (unsigned long long)pa.gvt, ln, wk.n, nk, pa.sweep);
-#endif
-  }
+    if (na_log > 0 || n_pool_anti > 0) acc.err |= ERR_ANTI_UNMATCHED;
+  } else if (na_log > 0 || n_pool_anti > 0) acc.err |= ERR_ANTI_UNMATCHED;
 
   // ---- phase 4: execute the working set in (time, subtime) order --------------------------------
   while (wk.n > 0) {
     if (ln == v.log_cap) {   // undo log full: leave the rest pending (they stay below GVT's reach)
-      for (int i = 0; i < wk.n; i++) keep(wk.get(i, (uint32_t)gid));
+      for (int i = 0; i < wk.n; i++) put_pending(wk.get(i, gid32));
       wk.n = 0;
       break;
     }
-    EvRec e = wk.get(wk.n - 1, (uint32_t)gid);
+    const EvRec e = wk.get(wk.n - 1, gid32);
     wk.n--;
     uint32_t li = lt + ln; if (li >= v.log_cap) li -= v.log_cap;
-    LogRec *lr = &v.lg[(size_t)li * A + lp];
+    LogRec lr;
+    lr.time = e.time; lr.sub = e.sub; lr.p0 = e.p0;
 #pragma unroll
-    for (int w = 0; w < M::STW; w++) lr->st[w] = st[w];
+    for (int w = 0; w < MAX_STW; w++) lr.st[w] = w < M::STW ? st[w] : 0;
     EvRec c;
     const bool sent = M::execute(mp, st, e, gid, c, false);
-    e.flags = sent ? EV_SENT : 0u;
-    st_ev(&lr->ev, e);
+    lr.fl = (e.p1 & ~FL_SENT) | (sent ? FL_SENT : 0u);
+    st_log(&v.lg[(size_t)li * A + lp], lr);
     ln++;
     acc.executed++;
     if (sent) {
@@ -385,23 +482,33 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
       seq += v.lp_n;
       if ((uint64_t)c.dst == gid) {
         EvRec out;
-        const int r = (c.time < pa.ub) ? wk.insert(c, out, (uint32_t)gid) : 2;
-        if (r == 1) keep(out); else if (r == 2) keep(c);
+        const int r = (c.time < pa.ub) ? wk.insert(c, out, gid32) : 2;
+        if (r == 1) put_pending(out); else if (r == 2) put_pending(c);
       } else {
         deliver(v, par_next, c, acc);
       }
     }
   }
 
-  // ---- phase 5: write back ----------------------------------------------------------------------
+  // ---- phase 5: close the remaining holes, write back --------------------------------------------
+  while (hole) {
+    while (top > 0 && ((hole >> (top - 1)) & 1ull)) { top--; hole &= ~(1ull << top); }   // free tail slots
+    if (!hole) break;
+    const uint32_t s = (uint32_t)ffs64(hole) - 1u;   // lowest hole, below top-1 which is in use
+    const uint32_t j = top - 1;
+    v.pq_t[(size_t)s * A + lp] = v.pq_t[(size_t)j * A + lp];
+    st_rest(&v.pq_r[(size_t)s * A + lp], ld_rest(&v.pq_r[(size_t)j * A + lp]));
+    hole &= ~(1ull << s);
+    top--;
+  }
   if (khead_dirty) {
     khead = ~0ull;
-    for (uint32_t s = 0; s < nk; s++) { const uint64_t t = v.pq[(size_t)s * A + lp].time; if (t < khead) khead = t; }
+    for (uint32_t s = 0; s < top; s++) { const uint64_t t = v.pq_t[(size_t)s * A + lp]; if (t < khead) khead = t; }
   }
 #pragma unroll
   for (int w = 0; w < M::STW; w++) v.st[(size_t)w * A + lp] = st[w];
   v.seq[lp] = seq;
-  v.pcnt[lp] = nk;
+  v.pcnt[lp] = top;
   v.head[lp] = khead;
   v.lmeta[lp] = ln | (lt << 16);
   if (khead < acc.tmin) acc.tmin = khead;
@@ -415,8 +522,69 @@ DEVA_HD void deliver_to_pending(const View &v, const EvRec &rec, uint32_t *err) 
   const uint32_t dl = (uint32_t)dl64;
   const uint32_t slot = atom_add_u32(&v.pcnt[dl], 1u);
   if (slot >= v.pq_cap) { atom_or_u32(err, ERR_PQ_OVERFLOW); return; }
-  st_ev(&v.pq[(size_t)slot * v.A + dl], rec);
+  pq_store(v, dl, slot, rec);
   atom_min_u64(&v.head[dl], rec.time);
+}
+
+// ---- setup / digest helpers shared by the kernels and the host emulation -------------------------
+template <class M>
+DEVA_HD void init_lp(const View &v, const ModelParams &mp, uint32_t lp, int init_state) {
+  const uint64_t gid = v.lp_begin + lp;
+  v.head[lp] = ~0ull;
+  v.pcnt[lp] = 0;
+  v.icnt[0][lp] = 0;
+  v.icnt[1][lp] = 0;
+  v.lmeta[lp] = 0;
+  v.seq[lp] = gid;      // pdes.cxx:332: seq_id_bumper = global_cd_begin + i
+  v.lct[lp] = 0;        // pdes.cxx:333
+  v.lcs[lp] = 0;
+  uint64_t s[MAX_STW] = {0, 0, 0};
+  if (init_state) M::init_state(mp, gid, s);
+  for (int w = 0; w < M::STW; w++) v.st[(size_t)w * v.A + lp] = s[w];
+}
+
+// K roots of one LP written straight into its pending slots (the owner writes: no atomics).
+template <class M>
+DEVA_HD void seed_lp_roots(const View &v, const ModelParams &mp, uint32_t lp, uint32_t k, int rootdiv, uint64_t per_rank) {
+  const uint64_t gid = v.lp_begin + lp;
+  uint64_t head = ~0ull;
+  // LPs past the model's actor count exist only as padding of the rank decomposition
+  // (ranks*ceil(actor_n/ranks) > actor_n, test/phold.cxx:46): they get no roots
+  if (gid >= mp.lp_n_model) k = 0;
+  for (uint32_t j = 0; j < k; j++) {
+    EvRec e;
+    uint64_t ray;
+    if (M::MODEL_ID == 2) {          // bench/phold.cxx:154-157
+      ray = gid * k + j;
+      e.time = ray;
+    } else {                         // test/phold.cxx:172-178, PHOLD-T root time
+      ray = gid + (uint64_t)j * mp.lp_n_model;
+      e.time = rootdiv ? j : ray;
+    }
+    e.sub = mp.user_subtime ? ray : gid % per_rank;   // pdes.hxx:907: root subtime = LOCAL cd index
+    e.p0 = (uint32_t)ray; e.p1 = 0; e.dst = (uint32_t)gid; e.flags = 0;
+    pq_store(v, lp, j, e);
+    head = e.time < head ? e.time : head;
+  }
+  v.pcnt[lp] = k;
+  v.head[lp] = head;
+}
+
+DEVA_HD uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+  return x;
+}
+// out[0] ^= last state word, out[1] += hash(state words), out[2] += pending count, out[3] += hash(pending)
+DEVA_HD void digest_lp(const View &v, int stw, uint32_t lp, uint64_t out[4]) {
+  const uint64_t gid = v.lp_begin + lp;
+  out[0] ^= v.st[(size_t)(stw - 1) * v.A + lp];
+  for (int w = 0; w < stw; w++) out[1] += mix64(v.st[(size_t)w * v.A + lp] ^ mix64(gid * 4 + w + 1));
+  const uint32_t np = v.pcnt[lp];
+  out[2] += np;
+  for (uint32_t s = 0; s < np; s++) {
+    const EvRec e = pq_load(v, lp, s, v.pq_t[(size_t)s * v.A + lp], (uint32_t)gid);
+    out[3] += mix64(e.time ^ mix64(e.sub ^ mix64(((uint64_t)e.p0 << 32 | e.dst) + e.flags)));
+  }
 }
 
 }  // namespace deva_b200

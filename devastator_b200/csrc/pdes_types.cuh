@@ -11,10 +11,13 @@
 //   st   [STW][A]       u64   model state words
 //   seq  [A]            u64   next default subtime (sequence id), pdes.cxx:221-225
 //   lct,lcs [A]         u64   last committed (time+1, subtime), pdes.cxx:828-831
-//   pq   [pq_cap][A]    EvRec 32 B   pending events (replaces cd_state::future_events heap)
+//   pq_t [pq_cap][A]    u64          pending events, time column   } replaces the per-LP
+//   pq_r [pq_cap][A]    PqRest 16 B  pending events, the rest      } cd_state::future_events heap
 //   ib   [2][ib_cap][A] EvRec 32 B   arrivals written by OTHER LPs' threads in the previous window
-//   lg   [log_cap][A]   LogRec 64 B  processed-uncommitted events + saved state
+//   lg   [log_cap][A]   LogRec 48 B  processed-uncommitted events + saved state
 //                                    (replaces cd_state::past_events + event::exec_ret)
+// The pending pool is split so that the per-window scan - "which of my events are below the window
+// bound?" - reads 8 bytes per slot; the 16-byte rest is fetched only for events that will run.
 #pragma once
 #include <stdint.h>
 
@@ -42,13 +45,21 @@ struct DEVA_ALIGN(16) EvRec {
 };
 static_assert(sizeof(EvRec) == 32, "EvRec must be 32 bytes");
 
+// pending record minus its time: 16 bytes.  p1f = payload word 1 (31 bits) | anti flag << 31
+struct DEVA_ALIGN(16) PqRest {
+  uint64_t sub;
+  uint32_t p0, p1f;
+};
+static_assert(sizeof(PqRest) == 16, "PqRest must be 16 bytes");
+constexpr int MAX_PQ_CAP = 64;   // free-slot bitmask of an LP's pending pool is one u64
+
 constexpr int MAX_STW = 3;
 struct DEVA_ALIGN(16) LogRec {
-  EvRec ev;
+  uint64_t time, sub;
+  uint32_t p0, fl;       // fl = p1 (31 bits) | EV_SENT-as-bit-31
   uint64_t st[MAX_STW];  // LP state before the event ran (== the reference's `reverse` object)
-  uint64_t spare;
 };
-static_assert(sizeof(LogRec) == 64, "LogRec must be 64 bytes");
+static_assert(sizeof(LogRec) == 48, "LogRec must be 48 bytes");
 
 enum : uint32_t {
   ERR_PQ_OVERFLOW = 1u, ERR_LOG_STALL = 2u, ERR_ANTI_UNMATCHED = 4u, ERR_SELF_CHILD_LOST = 8u,
@@ -57,15 +68,18 @@ enum : uint32_t {
 
 constexpr int MAX_GPUS = 8;
 
-// Device-resident control block (one per engine).
+// Device-resident control block (one per engine).  The per-window reduction targets are spread over
+// CTL_SLOTS cache lines so that the per-warp REDs of the execute kernel do not serialise on one
+// L2 address; the host folds the slots when it reads the block.
+constexpr int CTL_SLOTS = 32;
+enum { CNT_EXEC = 0, CNT_COMMIT, CNT_ROLLED, CNT_ANTI, CNT_REMOTE, CNT_FLAGS /* err | nondet<<31 */ };
 struct Ctl {
-  unsigned long long gvt_next;    // atomicMin accumulator: min time over everything still pending
-  unsigned long long executed, committed, rolled_back, anti_sent, remote_sent;
-  uint32_t err;
-  uint32_t nondeterministic;
+  unsigned long long gvt_slot[CTL_SLOTS][16];   // [i][0]: atomicMin accumulator (min time still pending)
+  unsigned long long cnt[CTL_SLOTS][16];        // [i][CNT_*]: cumulative counters / OR-ed flags
+  uint32_t err;                   // errors raised by the between-window kernels
   uint32_t spill_n;               // records in the spill buffer (inbox overflow)
   uint32_t send_n[MAX_GPUS];      // records staged for each peer GPU
-  uint32_t _pad;
+  uint32_t _pad[2];
 };
 
 struct View {
@@ -79,7 +93,8 @@ struct View {
   uint32_t *lmeta;
   uint64_t *st;          // [STW][A]
   uint64_t *seq, *lct, *lcs;
-  EvRec *pq;
+  uint64_t *pq_t;
+  PqRest *pq_r;
   EvRec *ib[2];
   LogRec *lg;
   Ctl *ctl;

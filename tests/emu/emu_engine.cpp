@@ -62,17 +62,9 @@ static auto dispatch_model(int model, F &&f) {
 }
 
 static void init_lps(deva_b200_engine *e, int init_state) {
-  View &v = e->v;
   dispatch_model(e->cfg.model, [&](auto m) {
     using M = decltype(m);
-    for (uint32_t lp = 0; lp < v.A; lp++) {
-      const uint64_t gid = v.lp_begin + lp;
-      v.head[lp] = ~0ull; v.pcnt[lp] = 0; v.icnt[0][lp] = 0; v.icnt[1][lp] = 0; v.lmeta[lp] = 0;
-      v.seq[lp] = gid; v.lct[lp] = 0; v.lcs[lp] = 0;
-      uint64_t s[MAX_STW] = {0, 0, 0};
-      if (init_state) M::init_state(e->mp, gid, s);
-      for (int w = 0; w < M::STW; w++) v.st[(size_t)w * v.A + lp] = s[w];
-    }
+    for (uint32_t lp = 0; lp < e->v.A; lp++) init_lp<M>(e->v, e->mp, lp, init_state);
     return 0;
   });
 }
@@ -105,6 +97,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   v.pq_cap = cfg->pq_cap > 0 ? cfg->pq_cap : 64;
   v.ib_cap = cfg->inbox_cap > 0 ? cfg->inbox_cap : 16;
   v.log_cap = cfg->log_cap > 0 ? cfg->log_cap : 48;
+  if (v.pq_cap > MAX_PQ_CAP) return fail(DEVA_B200_ERR_ARG, "pq_cap must be <= %d", MAX_PQ_CAP);
   v.lp_begin = cfg->lp_begin;
   v.lp_n = cfg->lp_n;
   v.n_gpus = cfg->n_gpus;
@@ -113,7 +106,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   const size_t A = v.A;
   halloc(e, &v.head, A); halloc(e, &v.pcnt, A); halloc(e, &v.icnt[0], A); halloc(e, &v.icnt[1], A);
   halloc(e, &v.lmeta, A); halloc(e, &v.st, A * e->stw); halloc(e, &v.seq, A); halloc(e, &v.lct, A); halloc(e, &v.lcs, A);
-  halloc(e, &v.pq, A * v.pq_cap); halloc(e, &v.ib[0], A * v.ib_cap); halloc(e, &v.ib[1], A * v.ib_cap);
+  halloc(e, &v.pq_t, A * v.pq_cap); halloc(e, &v.pq_r, A * v.pq_cap); halloc(e, &v.ib[0], A * v.ib_cap); halloc(e, &v.ib[1], A * v.ib_cap);
   halloc(e, &v.lg, A * v.log_cap);
   v.ctl = &e->ctl;
   v.spill_cap = (uint32_t)std::max<size_t>(A * 2, 1u << 12);
@@ -166,22 +159,11 @@ int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k, int32_t rootdiv, int32
   const int R = ranks > 0 ? ranks : 1;
   const uint64_t per = (v.lp_n + R - 1) / R;
   init_lps(e, 1);
-  for (uint32_t lp = 0; lp < v.A; lp++) {
-    const uint64_t gid = v.lp_begin + lp;
-    uint64_t head = ~0ull;
-    const uint32_t kk = gid < e->mp.lp_n_model ? k : 0;   // padding LPs of the rank decomposition get no roots
-    for (uint32_t j = 0; j < kk; j++) {
-      EvRec r;
-      uint64_t ray;
-      if (e->cfg.model == DEVA_B200_MODEL_PHOLD_BENCH) { ray = gid * k + j; r.time = ray; }
-      else { ray = gid + (uint64_t)j * e->mp.lp_n_model; r.time = rootdiv ? j : ray; }
-      r.sub = e->mp.user_subtime ? ray : gid % per;
-      r.p0 = (uint32_t)ray; r.p1 = 0; r.dst = (uint32_t)gid; r.flags = 0;
-      v.pq[(size_t)j * v.A + lp] = r;
-      head = std::min(head, r.time);
-    }
-    v.pcnt[lp] = kk; v.head[lp] = head;
-  }
+  dispatch_model(e->cfg.model, [&](auto m) {
+    using M = decltype(m);
+    for (uint32_t lp = 0; lp < v.A; lp++) seed_lp_roots<M>(v, e->mp, lp, k, rootdiv, per);
+    return 0;
+  });
   e->par = 0;
   return 0;
 }
@@ -204,10 +186,10 @@ static void pass_one(deva_b200_engine *e, const PassArgs &pa, uint64_t *wx, uint
     for (uint32_t i = 0; i < v.A; i++) lp_pass<M>(v, e->mp, pa, order[i], acc);
     return 0;
   });
-  e->ctl.gvt_next = std::min<unsigned long long>(e->ctl.gvt_next, acc.tmin);
-  e->ctl.executed += acc.executed; e->ctl.committed += acc.committed; e->ctl.rolled_back += acc.rolled;
-  e->ctl.anti_sent += acc.anti; e->ctl.remote_sent += acc.remote; e->ctl.err |= acc.err;
-  e->ctl.nondeterministic |= acc.nondet;
+  e->ctl.gvt_slot[0][0] = std::min<unsigned long long>(e->ctl.gvt_slot[0][0], acc.tmin);
+  e->ctl.cnt[0][CNT_EXEC] += acc.executed; e->ctl.cnt[0][CNT_COMMIT] += acc.committed; e->ctl.cnt[0][CNT_ROLLED] += acc.rolled;
+  e->ctl.cnt[0][CNT_ANTI] += acc.anti; e->ctl.cnt[0][CNT_REMOTE] += acc.remote; e->ctl.err |= acc.err;
+  e->ctl.cnt[0][CNT_FLAGS] |= (unsigned long long)acc.nondet << 31;
   *wx = acc.executed; *wr = acc.rolled;
   e->passes++;
 }
@@ -216,7 +198,7 @@ static int window_all(deva_b200_engine **es, int G, uint64_t ub, uint32_t sweep,
   *wx_sum = *wr_sum = 0;
   for (int g = 0; g < G; g++) {
     deva_b200_engine *e = es[g];
-    e->ctl.gvt_next = ~0ull;
+    e->ctl.gvt_slot[0][0] = ~0ull;
     PassArgs pa; pa.gvt = e->gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep;
     uint64_t wx, wr;
     pass_one(e, pa, &wx, &wr);
@@ -236,7 +218,7 @@ static int window_all(deva_b200_engine **es, int G, uint64_t ub, uint32_t sweep,
       s->ctl.send_n[d] = 0;
     }
   uint64_t gvt = ~0ull;
-  for (int g = 0; g < G; g++) { gvt = std::min<uint64_t>(gvt, es[g]->ctl.gvt_next); int rc = check_err(es[g]); if (rc) return rc; }
+  for (int g = 0; g < G; g++) { gvt = std::min<uint64_t>(gvt, es[g]->ctl.gvt_slot[0][0]); int rc = check_err(es[g]); if (rc) return rc; }
   for (int g = 0; g < G; g++) { es[g]->gvt = gvt; es[g]->par ^= 1u; }
   return 0;
 }
@@ -250,7 +232,7 @@ int emu_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewind
     if (rewindable) {
       const size_t A = v.A;
       struct { void *p; size_t b; } live[] = {{v.head, A * 8}, {v.pcnt, A * 4}, {v.st, A * e->stw * 8}, {v.seq, A * 8},
-                                              {v.lct, A * 8}, {v.lcs, A * 8}, {v.pq, A * v.pq_cap * sizeof(EvRec)}};
+                                              {v.lct, A * 8}, {v.lcs, A * 8}, {v.pq_t, A * v.pq_cap * 8}, {v.pq_r, A * v.pq_cap * sizeof(PqRest)}};
       e->snap.clear();
       for (auto &l : live) e->snap.emplace_back((char *)l.p, (char *)l.p + l.b);
       e->has_rewind = true;
@@ -293,7 +275,7 @@ int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind) {
   e->has_rewind = false;
   if (do_rewind) {
     View &v = e->v;
-    void *live[] = {v.head, v.pcnt, v.st, v.seq, v.lct, v.lcs, v.pq};
+    void *live[] = {v.head, v.pcnt, v.st, v.seq, v.lct, v.lcs, v.pq_t, v.pq_r};
     for (size_t i = 0; i < e->snap.size(); i++) memcpy(live[i], e->snap[i].data(), e->snap[i].size());
     memset(v.icnt[0], 0, v.A * 4); memset(v.icnt[1], 0, v.A * 4); memset(v.lmeta, 0, v.A * 4);
     e->gvt = e->snap_gvt;
@@ -303,27 +285,16 @@ int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind) {
 
 int deva_b200_get_stats(deva_b200_engine *e, deva_b200_stats *out) {
   memset(out, 0, sizeof *out);
-  out->executed_n = e->ctl.executed; out->committed_n = e->ctl.committed;
-  out->deterministic = e->ctl.nondeterministic ? 0 : 1;
-  out->rolled_back_n = e->ctl.rolled_back; out->anti_sent_n = e->ctl.anti_sent; out->remote_sent_n = e->ctl.remote_sent;
+  out->executed_n = e->ctl.cnt[0][CNT_EXEC]; out->committed_n = e->ctl.cnt[0][CNT_COMMIT];
+  out->deterministic = (e->ctl.cnt[0][CNT_FLAGS] >> 31) ? 0 : 1;
+  out->rolled_back_n = e->ctl.cnt[0][CNT_ROLLED]; out->anti_sent_n = e->ctl.cnt[0][CNT_ANTI]; out->remote_sent_n = e->ctl.cnt[0][CNT_REMOTE];
   out->passes = e->passes; out->window_last = e->wp.window();
   return 0;
 }
 
-static uint64_t mix64(uint64_t x) { x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31; return x; }
 int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]) {
-  View &v = e->v;
   out[0] = out[1] = out[2] = out[3] = 0;
-  for (uint32_t lp = 0; lp < v.A; lp++) {
-    const uint64_t gid = v.lp_begin + lp;
-    out[0] ^= v.st[(size_t)(e->stw - 1) * v.A + lp];
-    for (int w = 0; w < e->stw; w++) out[1] += mix64(v.st[(size_t)w * v.A + lp] ^ mix64(gid * 4 + w + 1));
-    out[2] += v.pcnt[lp];
-    for (uint32_t s = 0; s < v.pcnt[lp]; s++) {
-      const EvRec r = v.pq[(size_t)s * v.A + lp];
-      out[3] += mix64(r.time ^ mix64(r.sub ^ mix64(((uint64_t)r.p0 << 32 | r.dst) + r.flags)));
-    }
-  }
+  for (uint32_t lp = 0; lp < e->v.A; lp++) digest_lp(e->v, e->stw, lp, out);
   return 0;
 }
 
