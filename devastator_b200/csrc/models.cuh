@@ -47,8 +47,8 @@ struct PholdTest {
     s[2] = lp;                      // test/phold.cxx:162
   }
   // event::execute, test/phold.cxx:95-135.  Returns true when a child is sent.
-  DEVA_HD_NOINLINE static bool execute(const ModelParams &p, uint64_t *s, const EvRec &e, uint64_t lp, EvRec &c,
-                                       bool /*resend*/) {
+  DEVA_HD static bool execute(const ModelParams &p, uint64_t *s, const EvRec &e, uint64_t lp, EvRec &c,
+                              bool /*resend*/) {
     const uint32_t ray = e.p0;
     uint64_t chk = s[2];
     chk ^= chk >> 31;
@@ -95,8 +95,8 @@ struct PholdBench {
   }
   // bounce::execute, bench/phold.cxx:87-128.  `resend`: regenerate the child of an event that did
   // send when it ran (rollback), regardless of the cut-off flag.
-  DEVA_HD_NOINLINE static bool execute(const ModelParams &p, uint64_t *s, const EvRec &e, uint64_t lp, EvRec &c,
-                                       bool resend) {
+  DEVA_HD static bool execute(const ModelParams &p, uint64_t *s, const EvRec &e, uint64_t lp, EvRec &c,
+                              bool resend) {
     if (p.stop && !resend) return false;  // after the cut-off: no rng use, no send (:95-104)
     const uint64_t dt = phold_dt(rng_next(s[0], s[1]), p.neg_lambda);
     const int lp_n = (int)p.lp_n_model;

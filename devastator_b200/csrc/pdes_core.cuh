@@ -126,7 +126,7 @@ struct WorkSet {
   DEVA_HD void put(int i, const EvRec &e) { t[i] = e.time; s[i] = e.sub; p0[i] = e.p0; p1[i] = e.p1; }
   // Insert keeping order.  Returns 0 = inserted; 1 = inserted and `out` (the largest) evicted;
   // 2 = rejected (full and e is not smaller than the largest).
-  DEVA_HD_NOINLINE int insert(const EvRec &e, EvRec &out, uint32_t dst) {
+  DEVA_HD int insert(const EvRec &e, EvRec &out, uint32_t dst) {
     int evicted = 0;
     if (n == DEVA_WK_CAP) {
       if (!key_less(e.time, e.sub, t[0], s[0])) return 2;
@@ -144,7 +144,7 @@ struct WorkSet {
     n++;
     return evicted;
   }
-  DEVA_HD_NOINLINE bool remove_match(const EvRec &a) {
+  DEVA_HD bool remove_match(const EvRec &a) {
     for (int i = 0; i < n; i++)
       if (t[i] == a.time && s[i] == a.sub && p0[i] == a.p0 && p1[i] == a.p1) {
         for (int j = i; j + 1 < n; j++) { t[j] = t[j + 1]; s[j] = s[j + 1]; p0[j] = p0[j + 1]; p1[j] = p1[j + 1]; }
@@ -158,7 +158,7 @@ struct WorkSet {
 // Deliver a record (child or anti-message) to the LP that owns rec.dst.  Same GPU: straight into
 // that LP's next-window inbox.  Other GPU: into the staging buffer for that peer (exchanged after
 // the kernel).  Replaces execute_context::send's near/far split (pdes.hxx:691-731).
-DEVA_HD_NOINLINE void deliver(const View &v, uint32_t par_next, const EvRec &rec, Acc &acc) {
+DEVA_HD void deliver(const View &v, uint32_t par_next, const EvRec &rec, Acc &acc) {
   if (rec.time < acc.tmin) acc.tmin = rec.time;
   uint32_t g = (uint32_t)v.gpu_rank;
   if (v.n_gpus > 1) g = (uint32_t)(rec.dst / v.lp_per_gpu);
@@ -191,165 +191,6 @@ DEVA_HD EvRec pq_load(const View &v, uint32_t lp, uint32_t slot, uint64_t t, uin
   return e;
 }
 
-// ---- the LP's pending pool during a window ------------------------------------------------------
-// Slots [0, top) minus the `hole` bitmask are in use.  The pool is NOT compacted: a taken slot
-// becomes a hole, new records fill holes first, and only the holes left at the end are closed by
-// moving tail records down.  Records that stay are never rewritten.
-struct Pool {
-  uint64_t hole;     // bit s: slot s (< top) is free
-  uint64_t khead;    // min time over the records in the pool (valid unless dirty)
-  uint32_t top;
-  uint32_t err;
-  uint32_t dirty;    // a record was removed: khead must be recomputed
-};
-
-DEVA_HD_NOINLINE void pool_put(const View &v, uint32_t lp, Pool &pl, const EvRec &e) {
-  uint32_t s;
-  if (pl.hole) { s = (uint32_t)ffs64(pl.hole) - 1u; pl.hole &= pl.hole - 1; }
-  else {
-    if (pl.top >= v.pq_cap) { pl.err |= ERR_PQ_OVERFLOW; return; }
-    s = pl.top++;
-  }
-  pq_store(v, lp, s, e);
-  if (e.time < pl.khead) pl.khead = e.time;
-}
-
-// search the pool for a record identical to `a` (rare paths only)
-DEVA_HD_NOINLINE int pool_find(const View &v, uint32_t lp, const Pool &pl, const EvRec &a, uint32_t want_anti) {
-#pragma unroll 1
-  for (uint32_t s = 0; s < pl.top; s++) {
-    if ((pl.hole >> s) & 1ull) continue;
-    if (v.pq_t[(size_t)s * v.A + lp] != a.time) continue;
-    const PqRest r = ld_rest(&v.pq_r[(size_t)s * v.A + lp]);
-    if (r.sub == a.sub && r.p0 == a.p0 && (r.p1f & ~P1_ANTI) == a.p1 && ((r.p1f & P1_ANTI) ? 1u : 0u) == want_anti) return (int)s;
-  }
-  return -1;
-}
-DEVA_HD bool pool_remove_positive(const View &v, uint32_t lp, Pool &pl, const EvRec &a) {
-  const int s = pool_find(v, lp, pl, a, 0u);
-  if (s < 0) return false;
-  pl.hole |= 1ull << s;
-  pl.dirty = 1;
-  return true;
-}
-
-// wk.insert with the overflow going to the pool
-DEVA_HD void wk_or_pool(const View &v, uint32_t lp, WorkSet &wk, Pool &pl, const EvRec &e, bool in_window, uint32_t gid32) {
-  EvRec out;
-  const int r = in_window ? wk.insert(e, out, gid32) : 2;
-  if (r == 1) pool_put(v, lp, pl, out); else if (r == 2) pool_put(v, lp, pl, e);
-}
-
-// ---- phases 2-3, out of line: anti-message annihilation and rollback -----------------------------
-// (arrive_near<-1>, arrive_far_anti, insert_past, remove_past, rollback: pdes.cxx:393-693)
-// Only LPs that received an anti-message or a straggler this window come here.
-template <class M>
-DEVA_HD_NOINLINE void rollback_path(const View &v, const ModelParams &mp, const PassArgs &pa, uint32_t lp, Acc &acc,
-                                    WorkSet &wk, Pool &pl, EvRec *an, int na, bool anti_overflow,
-                                    uint32_t &ln_io, uint32_t lt, uint64_t *st, uint64_t &seq_io) {
-  const size_t A = v.A;
-  const uint64_t gid = v.lp_begin + lp;
-  const uint32_t gid32 = (uint32_t)gid;
-  const uint32_t par_next = pa.par ^ 1u;
-  uint32_t ln = ln_io;
-  uint64_t seq = seq_io;
-
-  // phase 2: annihilate anti-messages against not-yet-executed positives (pdes.cxx:480-487)
-  uint64_t anti_t = ~0ull, anti_s = ~0ull;   // min key over antis whose positive already ran
-  int na_log = 0;
-#pragma unroll 1
-  for (int i = 0; i < na; i++) {
-    if (wk.remove_match(an[i]) || pool_remove_positive(v, lp, pl, an[i])) continue;
-    an[na_log++] = an[i];                    // positive is in the undo log: roll back through it
-    if (key_less(an[i].time, an[i].sub, anti_t, anti_s)) { anti_t = an[i].time; anti_s = an[i].sub; }
-  }
-  uint32_t n_pool_anti = 0;                  // in-window antis still in the pool whose positive already ran
-  if (anti_overflow) {
-#pragma unroll 1
-    for (uint32_t s = 0; s < pl.top; s++) {
-      if ((pl.hole >> s) & 1ull) continue;
-      const uint64_t t = v.pq_t[(size_t)s * A + lp];
-      if (t >= pa.ub) continue;
-      const EvRec a = pq_load(v, lp, s, t, gid32);
-      if (!(a.flags & EV_ANTI)) continue;
-      if (wk.remove_match(a) || pool_remove_positive(v, lp, pl, a)) { pl.hole |= 1ull << s; pl.dirty = 1; continue; }
-      n_pool_anti++;
-      if (key_less(a.time, a.sub, anti_t, anti_s)) { anti_t = a.time; anti_s = a.sub; }
-    }
-  }
-
-  // phase 3: straggler / anti-message rollback
-  if (ln > 0 && (wk.n > 0 || na_log > 0 || n_pool_anti > 0)) {
-    const uint64_t sg_t = wk.n > 0 ? wk.t[wk.n - 1] : ~0ull;   // smallest in-window key = straggler
-    const uint64_t sg_s = wk.n > 0 ? wk.s[wk.n - 1] : ~0ull;
-#pragma unroll 1
-    while (ln > 0) {
-      uint32_t li = lt + ln - 1; if (li >= v.log_cap) li -= v.log_cap;
-      const LogRec *lrp = &v.lg[(size_t)li * A + lp];
-      const uint64_t lt_time = lrp->time, lt_sub = lrp->sub;
-      // undo while the newest processed event is later than the straggler, or not earlier than
-      // an anti-message's target (the target itself must be undone)
-      const bool undo = key_less(sg_t, sg_s, lt_time, lt_sub) ||
-                        ((na_log > 0 || n_pool_anti > 0) && !key_less(lt_time, lt_sub, anti_t, anti_s));
-      if (!undo) break;
-      if (lt_time < pa.gvt) acc.err |= ERR_BELOW_GVT;          // would undo a committable event
-      const LogRec lr = ld_log(lrp);
-      EvRec le; le.time = lr.time; le.sub = lr.sub; le.p0 = lr.p0; le.p1 = lr.fl & ~FL_SENT; le.dst = gid32; le.flags = 0;
-#pragma unroll
-      for (int w = 0; w < M::STW; w++) st[w] = lr.st[w];       // == reverse::unexecute
-      if (lr.fl & FL_SENT) {
-        // regenerate the child from the restored pre-state and cancel it
-        uint64_t tmp[MAX_STW];
-#pragma unroll
-        for (int w = 0; w < M::STW; w++) tmp[w] = st[w];
-        EvRec c;
-        M::execute(mp, tmp, le, gid, c, true);
-        seq -= v.lp_n;                                         // pdes.cxx:566,574
-        if (!mp.user_subtime) c.sub = seq;
-        if ((uint64_t)c.dst == gid) {
-          if (!(wk.remove_match(c) || pool_remove_positive(v, lp, pl, c))) acc.err |= ERR_SELF_CHILD_LOST;
-        } else {
-          c.flags = EV_ANTI;
-          deliver(v, par_next, c, acc);
-          acc.anti++;
-        }
-      }
-      // the undone event: annihilated if an anti-message names it, else back to pending
-      bool dead = false;
-#pragma unroll 1
-      for (int i = 0; i < na_log; i++)
-        if (same_event(an[i], le)) { an[i] = an[na_log - 1]; na_log--; dead = true; break; }
-      if (!dead && n_pool_anti) {
-        const int q = pool_find(v, lp, pl, le, 1u);
-        if (q >= 0) { pl.hole |= 1ull << q; pl.dirty = 1; n_pool_anti--; dead = true; }
-      }
-      if (dead) {   // recompute the min key over the antis still waiting for their target
-        anti_t = ~0ull; anti_s = ~0ull;
-#pragma unroll 1
-        for (int i = 0; i < na_log; i++)
-          if (key_less(an[i].time, an[i].sub, anti_t, anti_s)) { anti_t = an[i].time; anti_s = an[i].sub; }
-        if (n_pool_anti) {
-#pragma unroll 1
-          for (uint32_t s = 0; s < pl.top; s++) {
-            if ((pl.hole >> s) & 1ull) continue;
-            const uint64_t t = v.pq_t[(size_t)s * A + lp];
-            if (t >= pa.ub) continue;
-            const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
-            if ((r.p1f & P1_ANTI) && key_less(t, r.sub, anti_t, anti_s)) { anti_t = t; anti_s = r.sub; }
-          }
-        }
-      } else {
-        wk_or_pool(v, lp, wk, pl, le, le.time < pa.ub, gid32);
-      }
-      ln--;
-      acc.rolled++;
-    }
-    if (na_log > 0 || n_pool_anti > 0) acc.err |= ERR_ANTI_UNMATCHED;
-  } else if (na_log > 0 || n_pool_anti > 0) acc.err |= ERR_ANTI_UNMATCHED;
-  ln_io = ln;
-  seq_io = seq;
-}
-
 template <class M>
 DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, uint32_t lp, Acc &acc) {
   const size_t A = v.A;
@@ -369,9 +210,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
 
   // ---- phase 0: fossil collection - commit log entries with time < GVT (pdes.cxx:816-871) -------
   // The first PF tail entries are fetched together (independent loads in flight), the rare rest
-  // one by one.  The newest entry's key is fetched alongside: it decides whether this LP has a
-  // straggler (phase 3) without another exposed round trip.
-  uint64_t new_t = 0, new_s = 0;   // key of the newest log entry (valid when ln > 0)
+  // one by one.
   if (ln > 0) {
     constexpr int PF = 4;
     uint64_t pt[PF], ps[PF];
@@ -383,15 +222,9 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
       pt[i] = ok ? lr->time : ~0ull;
       ps[i] = ok ? lr->sub : 0ull;
     }
-    {
-      uint32_t li = lt + ln - 1; if (li >= v.log_cap) li -= v.log_cap;
-      const LogRec *lr = &v.lg[(size_t)li * A + lp];
-      new_t = lr->time; new_s = lr->sub;
-    }
     uint64_t lct = v.lct[lp], lcs = v.lcs[lp];
     bool any = false;
     int k = 0;
-#pragma unroll 1
     while (ln > 0) {
       uint64_t t, sb;
       if (k < PF) {
@@ -425,17 +258,34 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   uint64_t seq = v.seq[lp];
 
   // ---- phase 1: fold pending slots + this window's arrivals -------------------------------------
+  // The pending pool is NOT compacted: slots whose event is taken become holes (bitmask `hole`),
+  // new pending records fill holes first, and only what is left of the holes is closed at the end
+  // by moving tail records down.  Records that stay are never rewritten.
   WorkSet wk; wk.n = 0;
   EvRec an[DEVA_AN_CAP]; int na = 0;
-  Pool pl; pl.hole = 0; pl.khead = ~0ull; pl.top = np; pl.err = 0; pl.dirty = 0;
+  uint64_t hole = 0;            // bit s: slot s (< top) is free
+  uint32_t top = np;            // slots in use: [0, top) minus holes
+  uint64_t khead = ~0ull;       // min time over pending records (valid unless khead_dirty)
+  bool khead_dirty = false;
   bool anti_overflow = false;   // an in-window anti-message stayed in the pool (an[] was full)
+
+  auto put_pending = [&](const EvRec &e) {
+    uint32_t s;
+    if (hole) { s = (uint32_t)ffs64(hole) - 1u; hole &= hole - 1; }
+    else {
+      if (top >= v.pq_cap) { acc.err |= ERR_PQ_OVERFLOW; return; }
+      s = top++;
+    }
+    pq_store(v, lp, s, e);
+    if (e.time < khead) khead = e.time;
+  };
+  auto take_slot = [&](uint32_t s) { hole |= 1ull << s; };
 
   // Stage A: every pending time of this LP in flight at once (8 B per slot, coalesced across the
   // warp), reduced to a bitmask of the slots below the window bound.
   uint64_t inwin = 0;
   {
     constexpr int CH = 16;
-#pragma unroll 1
     for (uint32_t base = 0; base < np; base += CH) {
       uint64_t tt[CH];
 #pragma unroll
@@ -443,12 +293,23 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
 #pragma unroll
       for (int i = 0; i < CH; i++) {
         if (tt[i] < pa.ub) inwin |= 1ull << (base + i);      // (~0 for absent slots is never < ub)
-        else if (tt[i] < pl.khead) pl.khead = tt[i];
+        else if (tt[i] < khead) khead = tt[i];
       }
     }
   }
   // Stage B: the records of the in-window slots, fetched four at a time (loads issued together).
-#pragma unroll 1
+  auto fold_pool_record = [&](const EvRec &e, uint32_t s) {
+    if (e.flags & EV_ANTI) {
+      if (na < DEVA_AN_CAP) { an[na++] = e; take_slot(s); }
+      else { anti_overflow = true; if (e.time < khead) khead = e.time; }
+    } else {
+      EvRec out;
+      const int r = wk.insert(e, out, gid32);
+      if (r == 0) take_slot(s);
+      else if (r == 1) { pq_store(v, lp, s, out); if (out.time < khead) khead = out.time; }   // evicted one takes the slot
+      else if (e.time < khead) khead = e.time;                                                // rejected: stays
+    }
+  };
   while (inwin) {
     constexpr int RB = 4;
     uint32_t ss[RB];
@@ -461,53 +322,145 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
 #pragma unroll
     for (int i = 0; i < RB; i++)
       if (ss[i] != 0xffffffffu) ee[i] = pq_load(v, lp, ss[i], v.pq_t[(size_t)ss[i] * A + lp], gid32);
-#pragma unroll 1
-    for (int i = 0; i < RB; i++) {
-      if (ss[i] == 0xffffffffu) break;
-      const EvRec &e = ee[i];
-      const uint32_t s = ss[i];
-      if (e.flags & EV_ANTI) {
-        if (na < DEVA_AN_CAP) { an[na++] = e; pl.hole |= 1ull << s; }
-        else { anti_overflow = true; if (e.time < pl.khead) pl.khead = e.time; }
-      } else {
-        EvRec out;
-        const int r = wk.insert(e, out, gid32);
-        if (r == 0) pl.hole |= 1ull << s;
-        else if (r == 1) { pq_store(v, lp, s, out); if (out.time < pl.khead) pl.khead = out.time; }   // evicted one takes the slot
-        else if (e.time < pl.khead) pl.khead = e.time;                                                // rejected: stays
-      }
-    }
+#pragma unroll
+    for (int i = 0; i < RB; i++)
+      if (ss[i] != 0xffffffffu) fold_pool_record(ee[i], ss[i]);
   }
   if (ni > 0) {
     if (ni > v.ib_cap) ni = v.ib_cap;
-#pragma unroll 1
+    auto fold_arrival = [&](const EvRec &e) {
+      if (e.flags & EV_ANTI) {
+        if (na < DEVA_AN_CAP) an[na++] = e; else { put_pending(e); anti_overflow |= e.time < pa.ub; }
+      } else if (e.time < pa.ub) {
+        EvRec out;
+        const int r = wk.insert(e, out, gid32);
+        if (r == 1) put_pending(out); else if (r == 2) put_pending(e);
+      } else put_pending(e);
+    };
     for (uint32_t base = 0; base < ni; base += 4) {
       EvRec ee[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) if (base + i < ni) ee[i] = ld_ev(&v.ib[pa.par][(size_t)(base + i) * A + lp]);
-#pragma unroll 1
-      for (int i = 0; i < 4; i++) {
-        if (base + i >= ni) break;
-        const EvRec &e = ee[i];
-        if (e.flags & EV_ANTI) {
-          if (na < DEVA_AN_CAP) an[na++] = e; else { pool_put(v, lp, pl, e); anti_overflow |= e.time < pa.ub; }
-        } else wk_or_pool(v, lp, wk, pl, e, e.time < pa.ub, gid32);
-      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) if (base + i < ni) fold_arrival(ee[i]);
     }
     v.icnt[pa.par][lp] = 0;
   }
 
-  // ---- phases 2-3 (rare): anti-messages, stragglers -> rollback_path -----------------------------
-  if (na > 0 || anti_overflow ||
-      (ln > 0 && wk.n > 0 && key_less(wk.t[wk.n - 1], wk.s[wk.n - 1], new_t, new_s)))
-    rollback_path<M>(v, mp, pa, lp, acc, wk, pl, an, na, anti_overflow, ln, lt, st, seq);
+  // pool helpers for the rare paths (slot indices are stable: removal only sets a hole bit)
+  auto find_pending = [&](const EvRec &a, uint32_t want_anti) -> int {
+    for (uint32_t s = 0; s < top; s++) {
+      if ((hole >> s) & 1ull) continue;
+      if (v.pq_t[(size_t)s * A + lp] != a.time) continue;
+      const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
+      if (r.sub == a.sub && r.p0 == a.p0 && (r.p1f & ~P1_ANTI) == a.p1 && ((r.p1f & P1_ANTI) ? 1u : 0u) == want_anti) return (int)s;
+    }
+    return -1;
+  };
+  auto remove_pending = [&](const EvRec &a) -> bool {   // remove one POSITIVE identical to a
+    const int s = find_pending(a, 0u);
+    if (s < 0) return false;
+    take_slot((uint32_t)s);
+    khead_dirty = true;
+    return true;
+  };
+
+  // ---- phase 2: annihilate anti-messages against not-yet-executed positives ----------------------
+  // (arrive_near<-1> with future_not_past, pdes.cxx:480-487)
+  uint64_t anti_t = ~0ull, anti_s = ~0ull;   // min key over antis whose positive already ran
+  int na_log = 0;
+  for (int i = 0; i < na; i++) {
+    if (wk.remove_match(an[i]) || remove_pending(an[i])) continue;
+    an[na_log++] = an[i];                    // positive is in the undo log: roll back through it
+    if (key_less(an[i].time, an[i].sub, anti_t, anti_s)) { anti_t = an[i].time; anti_s = an[i].sub; }
+  }
+  uint32_t n_pool_anti = 0;                  // in-window antis still in the pool whose positive already ran
+  if (anti_overflow) {
+    for (uint32_t s = 0; s < top; s++) {
+      if ((hole >> s) & 1ull) continue;
+      const uint64_t t = v.pq_t[(size_t)s * A + lp];
+      if (t >= pa.ub) continue;
+      const EvRec a = pq_load(v, lp, s, t, gid32);
+      if (!(a.flags & EV_ANTI)) continue;
+      if (wk.remove_match(a) || remove_pending(a)) { take_slot(s); khead_dirty = true; continue; }
+      n_pool_anti++;
+      if (key_less(a.time, a.sub, anti_t, anti_s)) { anti_t = a.time; anti_s = a.sub; }
+    }
+  }
+  auto recompute_anti_min = [&]() {
+    anti_t = ~0ull; anti_s = ~0ull;
+    for (int i = 0; i < na_log; i++)
+      if (key_less(an[i].time, an[i].sub, anti_t, anti_s)) { anti_t = an[i].time; anti_s = an[i].sub; }
+    if (n_pool_anti)
+      for (uint32_t s = 0; s < top; s++) {
+        if ((hole >> s) & 1ull) continue;
+        const uint64_t t = v.pq_t[(size_t)s * A + lp];
+        if (t >= pa.ub) continue;
+        const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
+        if ((r.p1f & P1_ANTI) && key_less(t, r.sub, anti_t, anti_s)) { anti_t = t; anti_s = r.sub; }
+      }
+  };
+
+  // ---- phase 3: straggler / anti-message rollback (insert_past, remove_past, rollback) -----------
+  if (ln > 0 && (wk.n > 0 || na_log > 0 || n_pool_anti > 0)) {
+    const uint64_t sg_t = wk.n > 0 ? wk.t[wk.n - 1] : ~0ull;   // smallest in-window key = straggler
+    const uint64_t sg_s = wk.n > 0 ? wk.s[wk.n - 1] : ~0ull;
+    while (ln > 0) {
+      uint32_t li = lt + ln - 1; if (li >= v.log_cap) li -= v.log_cap;
+      const LogRec *lrp = &v.lg[(size_t)li * A + lp];
+      const uint64_t lt_time = lrp->time, lt_sub = lrp->sub;
+      // undo while the newest processed event is later than the straggler, or not earlier than
+      // an anti-message's target (the target itself must be undone)
+      const bool undo = key_less(sg_t, sg_s, lt_time, lt_sub) ||
+                        ((na_log > 0 || n_pool_anti > 0) && !key_less(lt_time, lt_sub, anti_t, anti_s));
+      if (!undo) break;
+      if (lt_time < pa.gvt) acc.err |= ERR_BELOW_GVT;          // would undo a committable event
+      const LogRec lr = ld_log(lrp);
+      EvRec le; le.time = lr.time; le.sub = lr.sub; le.p0 = lr.p0; le.p1 = lr.fl & ~FL_SENT; le.dst = gid32; le.flags = 0;
+#pragma unroll
+      for (int w = 0; w < M::STW; w++) st[w] = lr.st[w];       // == reverse::unexecute
+      if (lr.fl & FL_SENT) {
+        // regenerate the child from the restored pre-state and cancel it
+        uint64_t tmp[MAX_STW];
+#pragma unroll
+        for (int w = 0; w < M::STW; w++) tmp[w] = st[w];
+        EvRec c;
+        M::execute(mp, tmp, le, gid, c, true);
+        seq -= v.lp_n;                                         // pdes.cxx:566,574
+        if (!mp.user_subtime) c.sub = seq;
+        if ((uint64_t)c.dst == gid) {
+          if (!(wk.remove_match(c) || remove_pending(c))) acc.err |= ERR_SELF_CHILD_LOST;
+        } else {
+          c.flags = EV_ANTI;
+          deliver(v, par_next, c, acc);
+          acc.anti++;
+        }
+      }
+      // the undone event: annihilated if an anti-message names it, else back to pending
+      bool dead = false;
+      for (int i = 0; i < na_log; i++)
+        if (same_event(an[i], le)) { an[i] = an[na_log - 1]; na_log--; dead = true; break; }
+      if (!dead && n_pool_anti) {
+        const int q = find_pending(le, 1u);
+        if (q >= 0) { take_slot((uint32_t)q); khead_dirty = true; n_pool_anti--; dead = true; }
+      }
+      if (dead) {
+        recompute_anti_min();
+      } else {
+        EvRec out;
+        const int r = (le.time < pa.ub) ? wk.insert(le, out, gid32) : 2;
+        if (r == 1) put_pending(out); else if (r == 2) put_pending(le);
+      }
+      ln--;
+      acc.rolled++;
+    }
+    if (na_log > 0 || n_pool_anti > 0) acc.err |= ERR_ANTI_UNMATCHED;
+  } else if (na_log > 0 || n_pool_anti > 0) acc.err |= ERR_ANTI_UNMATCHED;
 
   // ---- phase 4: execute the working set in (time, subtime) order --------------------------------
-#pragma unroll 1
   while (wk.n > 0) {
     if (ln == v.log_cap) {   // undo log full: leave the rest pending (they stay below GVT's reach)
-#pragma unroll 1
-      for (int i = 0; i < wk.n; i++) pool_put(v, lp, pl, wk.get(i, gid32));
+      for (int i = 0; i < wk.n; i++) put_pending(wk.get(i, gid32));
       wk.n = 0;
       break;
     }
@@ -527,15 +480,17 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     if (sent) {
       if (!mp.user_subtime) c.sub = seq;   // event_subtime / next_seq_id, pdes.hxx:513-526,676
       seq += v.lp_n;
-      if ((uint64_t)c.dst == gid) wk_or_pool(v, lp, wk, pl, c, c.time < pa.ub, gid32);
-      else deliver(v, par_next, c, acc);
+      if ((uint64_t)c.dst == gid) {
+        EvRec out;
+        const int r = (c.time < pa.ub) ? wk.insert(c, out, gid32) : 2;
+        if (r == 1) put_pending(out); else if (r == 2) put_pending(c);
+      } else {
+        deliver(v, par_next, c, acc);
+      }
     }
   }
 
   // ---- phase 5: close the remaining holes, write back --------------------------------------------
-  uint64_t hole = pl.hole;
-  uint32_t top = pl.top;
-#pragma unroll 1
   while (hole) {
     while (top > 0 && ((hole >> (top - 1)) & 1ull)) { top--; hole &= ~(1ull << top); }   // free tail slots
     if (!hole) break;
@@ -546,13 +501,10 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     hole &= ~(1ull << s);
     top--;
   }
-  uint64_t khead = pl.khead;
-  if (pl.dirty) {
+  if (khead_dirty) {
     khead = ~0ull;
-#pragma unroll 1
     for (uint32_t s = 0; s < top; s++) { const uint64_t t = v.pq_t[(size_t)s * A + lp]; if (t < khead) khead = t; }
   }
-  acc.err |= pl.err;
 #pragma unroll
   for (int w = 0; w < M::STW; w++) v.st[(size_t)w * A + lp] = st[w];
   v.seq[lp] = seq;

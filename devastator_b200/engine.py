@@ -103,14 +103,10 @@ def load():
     """Loads libdeva_b200.so (built in-tree by __graft_entry__.build()).  No fallback."""
     global _api
     if _api is None:
-        path = LIB_PATH
-        alt = os.environ.get("DEVA_B200_LIB_VARIANT")   # tuning builds: devastator_b200/libdeva_b200_<variant>.so
-        if alt:
-            path = os.path.join(PKG_DIR, f"libdeva_b200_{alt}.so")
-        if not os.path.exists(path):
-            raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
                                "There is no CPU path.")
-        _api = Api(C.CDLL(path))
+        _api = Api(C.CDLL(LIB_PATH))
         if _api.lib.deva_b200_abi_version() != ABI_VERSION:
             raise RuntimeError("libdeva_b200.so ABI version mismatch")
     return _api
