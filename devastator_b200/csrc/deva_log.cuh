@@ -18,8 +18,11 @@
 
 #if defined(__CUDACC__)
   #define DEVA_HD __host__ __device__ __forceinline__
+  // out-of-line on the device: keeps rarely executed code out of the hot instruction stream
+  #define DEVA_HD_NOINLINE __host__ __device__ __noinline__
 #else
   #define DEVA_HD inline
+  #define DEVA_HD_NOINLINE inline
 #endif
 
 #if defined(__CUDA_ARCH__)
