@@ -161,19 +161,36 @@ DEVA_HD void pool_remove(const View &v, uint32_t lp, uint32_t &top, uint32_t s) 
     st_rest(&v.pq_r[(size_t)s * v.A + lp], ld_rest(&v.pq_r[(size_t)top * v.A + lp]));
   }
 }
+// like pool_remove, but keeps `keep` pointing at the same record if that record is the one moved
+DEVA_HD void pool_remove_keep(const View &v, uint32_t lp, uint32_t &top, uint32_t s, uint32_t &keep) {
+  pool_remove(v, lp, top, s);
+  if (keep == top) keep = s;   // the last record (old index top) now lives in slot s
+}
 DEVA_HD bool pool_append(const View &v, uint32_t lp, uint32_t &top, const EvRec &e, Acc &acc) {
   if (top >= v.pq_cap) { acc.err |= ERR_PQ_OVERFLOW; return false; }
   pq_store(v, lp, top, e);
   top++;
   return true;
 }
-// slot of a record identical to `a` with the given anti flag, skipping slot `skip`; -1 if none
+// slot of a record identical to `a` with the given anti flag, skipping slot `skip`; -1 if none.
+// The pool's times are fetched 16 at a time (independent loads), the 16-byte rest only on a time match.
 DEVA_HD_NOINLINE int pool_find(const View &v, uint32_t lp, uint32_t top, const EvRec &a, uint32_t want_anti, uint32_t skip) {
+  constexpr int CH = 16;
 #pragma unroll 1
-  for (uint32_t s = 0; s < top; s++) {
-    if (s == skip || v.pq_t[(size_t)s * v.A + lp] != a.time) continue;
-    const PqRest r = ld_rest(&v.pq_r[(size_t)s * v.A + lp]);
-    if (r.sub == a.sub && r.p0 == a.p0 && (r.p1f & ~P1_ANTI) == a.p1 && ((r.p1f & P1_ANTI) ? 1u : 0u) == want_anti) return (int)s;
+  for (uint32_t base = 0; base < top; base += CH) {
+    uint64_t tt[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++) tt[i] = (base + i < top) ? v.pq_t[(size_t)(base + i) * v.A + lp] : ~0ull;
+    uint32_t hit = 0;
+#pragma unroll
+    for (int i = 0; i < CH; i++) hit |= (tt[i] == a.time && base + i < top && base + i != skip) ? (1u << i) : 0u;
+#pragma unroll 1
+    while (hit) {
+      const uint32_t s = base + (uint32_t)ffs64(hit) - 1u;
+      hit &= hit - 1;
+      const PqRest r = ld_rest(&v.pq_r[(size_t)s * v.A + lp]);
+      if (r.sub == a.sub && r.p0 == a.p0 && (r.p1f & ~P1_ANTI) == a.p1 && ((r.p1f & P1_ANTI) ? 1u : 0u) == want_anti) return (int)s;
+    }
   }
   return -1;
 }
@@ -187,7 +204,7 @@ DEVA_HD_NOINLINE int pool_find(const View &v, uint32_t lp, uint32_t top, const E
 template <class M>
 DEVA_HD_NOINLINE bool rollback(const View &v, const ModelParams &mp, const PassArgs &pa, uint32_t lp, Acc &acc,
                                uint32_t &top, uint32_t &ln, uint32_t lt, uint64_t *st, uint64_t &seq,
-                               uint64_t kt, uint64_t ks, const EvRec *kill) {
+                               uint64_t kt, uint64_t ks, const EvRec *kill, uint64_t &requeued_min, uint32_t &keep_slot) {
   const size_t A = v.A;
   const uint64_t gid = v.lp_begin + lp;
   const uint32_t gid32 = (uint32_t)gid;
@@ -214,7 +231,8 @@ DEVA_HD_NOINLINE bool rollback(const View &v, const ModelParams &mp, const PassA
       if (!mp.user_subtime) c.sub = seq;
       if ((uint64_t)c.dst == gid) {
         const int q = pool_find(v, lp, top, c, 0u, 0xffffffffu);
-        if (q >= 0) pool_remove(v, lp, top, (uint32_t)q); else acc.err |= ERR_SELF_CHILD_LOST;
+        // (never the straggler's own slot: the child is later than its parent, which is later than the straggler)
+      if (q >= 0) pool_remove_keep(v, lp, top, (uint32_t)q, keep_slot); else acc.err |= ERR_SELF_CHILD_LOST;
       } else {
         c.flags = EV_ANTI;
         deliver(v, pa.par ^ 1u, c, acc);
@@ -222,7 +240,7 @@ DEVA_HD_NOINLINE bool rollback(const View &v, const ModelParams &mp, const PassA
       }
     }
     if (kill && !killed && same_event(*kill, le)) killed = true;   // annihilated
-    else pool_append(v, lp, top, le, acc);                          // back to pending
+    else { pool_append(v, lp, top, le, acc); if (le.time < requeued_min) requeued_min = le.time; }   // back to pending
     ln--;
     acc.rolled++;
   }
@@ -260,19 +278,29 @@ DEVA_HD_NOINLINE bool slow_select(const View &v, const ModelParams &mp, const Pa
   const uint32_t gid32 = (uint32_t)(v.lp_begin + lp);
 #pragma unroll 1
   for (int guard = 0; guard < 65536; guard++) {
-    // minimum key over the pool: time, then anti-messages first, then subtime
+    // minimum key over the pool: time, then anti-messages first, then subtime.  Times are fetched
+    // 16 at a time; a record's rest only when its time ties or beats the best so far.
     uint64_t bt = ~0ull, bs = ~0ull, t2 = ~0ull;
     uint32_t bslot = 0xffffffffu, bp1f = 0, bp0 = 0;
+    constexpr int CH = 16;
 #pragma unroll 1
-    for (uint32_t s = 0; s < top; s++) {
-      const uint64_t t = v.pq_t[(size_t)s * A + lp];
-      if (t > bt) { if (t < t2) t2 = t; continue; }
-      const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
-      const uint32_t anti = r.p1f & P1_ANTI;
-      bool better = true;
-      if (t == bt) better = (anti && !(bp1f & P1_ANTI)) || (anti == (bp1f & P1_ANTI) && r.sub < bs);
-      t2 = bt;                      // the displaced best, or the tied record, is the runner-up
-      if (better) { bt = t; bs = r.sub; bp0 = r.p0; bp1f = r.p1f; bslot = s; }
+    for (uint32_t base = 0; base < top; base += CH) {
+      uint64_t tt[CH];
+#pragma unroll
+      for (int i = 0; i < CH; i++) tt[i] = (base + i < top) ? v.pq_t[(size_t)(base + i) * A + lp] : ~0ull;
+#pragma unroll 1
+      for (int i = 0; i < CH; i++) {
+        const uint32_t s = base + i;
+        if (s >= top) break;
+        const uint64_t t = tt[i];
+        if (t > bt) { if (t < t2) t2 = t; continue; }
+        const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
+        const uint32_t anti = r.p1f & P1_ANTI;
+        bool better = true;
+        if (t == bt) better = (anti && !(bp1f & P1_ANTI)) || (anti == (bp1f & P1_ANTI) && r.sub < bs);
+        t2 = bt;                      // the displaced best, or the tied record, is the runner-up
+        if (better) { bt = t; bs = r.sub; bp0 = r.p0; bp1f = r.p1f; bslot = s; }
+      }
     }
     if (bslot == 0xffffffffu || bt >= pa.ub) { head_rest = bt; return false; }
     EvRec cand; cand.time = bt; cand.sub = bs; cand.p0 = bp0; cand.p1 = bp1f & ~P1_ANTI; cand.dst = gid32; cand.flags = 0;
@@ -285,7 +313,8 @@ DEVA_HD_NOINLINE bool slow_select(const View &v, const ModelParams &mp, const Pa
         pool_remove(v, lp, top, lo);
       } else {                // already executed: roll back through it (remove_past, pdes.cxx:517-525)
         pool_remove(v, lp, top, bslot);
-        if (!rollback<M>(v, mp, pa, lp, acc, top, ln, lt, st, seq, bt, bs, &cand)) acc.err |= ERR_ANTI_UNMATCHED;
+        uint64_t rq = ~0ull; uint32_t keep = 0xffffffffu;
+        if (!rollback<M>(v, mp, pa, lp, acc, top, ln, lt, st, seq, bt, bs, &cand, rq, keep)) acc.err |= ERR_ANTI_UNMATCHED;
       }
       continue;
     }
@@ -293,7 +322,8 @@ DEVA_HD_NOINLINE bool slow_select(const View &v, const ModelParams &mp, const Pa
       uint32_t li = lt + ln - 1; if (li >= v.log_cap) li -= v.log_cap;
       const LogRec *lrp = &v.lg[(size_t)li * A + lp];
       if (key_less(bt, bs, lrp->time, lrp->sub)) {
-        rollback<M>(v, mp, pa, lp, acc, top, ln, lt, st, seq, bt, bs, nullptr);
+        uint64_t rq = ~0ull; uint32_t keep = bslot;
+        rollback<M>(v, mp, pa, lp, acc, top, ln, lt, st, seq, bt, bs, nullptr, rq, keep);
         continue;             // undone events went back to the pool: select again
       }
     }
@@ -420,8 +450,9 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     EvRec e; e.time = t1; e.sub = 0; e.p0 = 0; e.p1 = 0; e.dst = gid32; e.flags = 0;
     uint32_t s_sel = s1;
     uint64_t head_rest = t2;
-    bool ok;
-    if (ties > 1) ok = slow_select<M>(v, mp, pa, lp, acc, top, ln, lt, st, seq, e, s_sel, head_rest);
+    bool ok = true;
+    int slow = 0;   // 1 = straggler (rollback only), 2 = full re-selection (anti-message at the head, 3-way tie)
+    if (ties > 1) slow = 2;
     else {
       PqRest r = ld_rest(&v.pq_r[(size_t)s1 * A + lp]);
       uint32_t antis = r.p1f & P1_ANTI;
@@ -431,10 +462,28 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
         if (rb.sub < r.sub) { r = rb; s_sel = s1b; }
       }
       e.sub = r.sub; e.p0 = r.p0; e.p1 = r.p1f & ~P1_ANTI;
-      // anti-message at the head, or a straggler (earlier than the newest processed event): slow path
-      if (antis || (ln > 0 && key_less(e.time, e.sub, new_t, new_s)))
-        ok = slow_select<M>(v, mp, pa, lp, acc, top, ln, lt, st, seq, e, s_sel, head_rest);
-      else ok = true;
+      if (antis) slow = 2;
+      else if (ln > 0 && key_less(e.time, e.sub, new_t, new_s)) slow = 1;   // lazy straggler detection, pdes.cxx:496-515
+    }
+    if (slow) {
+      // Out-of-line calls get COPIES of the hot variables (an address-taken variable would live in
+      // local memory for the whole kernel).
+      uint32_t top2 = top, ln2 = ln, s2 = s_sel;
+      uint64_t seq2 = seq, hr2 = head_rest, st2[MAX_STW];
+#pragma unroll
+      for (int w = 0; w < MAX_STW; w++) st2[w] = st[w];
+      Acc a2; a2.tmin = ~0ull; a2.executed = a2.committed = a2.rolled = a2.anti = a2.remote = a2.err = a2.nondet = 0;
+      EvRec e2 = e;
+      if (slow == 1) {   // undo everything later than the straggler; it stays the earliest record
+        uint64_t rq = ~0ull;
+        rollback<M>(v, mp, pa, lp, a2, top2, ln2, lt, st2, seq2, e.time, e.sub, nullptr, rq, s2);
+        if (rq < hr2) hr2 = rq;
+      } else ok = slow_select<M>(v, mp, pa, lp, a2, top2, ln2, lt, st2, seq2, e2, s2, hr2);
+      top = top2; ln = ln2; s_sel = s2; seq = seq2; head_rest = hr2; e = e2;
+#pragma unroll
+      for (int w = 0; w < MAX_STW; w++) st[w] = st2[w];
+      if (a2.tmin < acc.tmin) acc.tmin = a2.tmin;
+      acc.rolled += a2.rolled; acc.anti += a2.anti; acc.remote += a2.remote; acc.err |= a2.err;
     }
     head = ok ? (e.time < head_rest ? e.time : head_rest) : head_rest;
     if (ok && ln < v.log_cap) {   // (undo log full: the event waits; GVT cannot pass it)
