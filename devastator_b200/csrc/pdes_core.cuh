@@ -403,26 +403,35 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   for (int w = 0; w < M::STW; w++) st[w] = v.st[(size_t)w * A + lp];
   uint64_t seq = v.seq[lp];
 
-  // ---- phase 1: earliest record of the pool ------------------------------------------------------
-  // t1 = min time (slot s1), s1b = another slot with the same time (tie), t2 = min over the rest.
-  uint64_t t1 = ~0ull, t2 = ~0ull;
-  uint32_t s1 = 0, s1b = 0, ties = 0;
-  auto consider = [&](uint64_t t, uint32_t s) {
-    if (t < t1) { t2 = t1; t1 = t; s1 = s; ties = 0; }
-    else {
-      if (t == t1 && t != ~0ull) { ties++; s1b = s; }
-      if (t < t2) t2 = t;
-    }
+  // ---- phase 1: earliest records of the pool -----------------------------------------------------
+  // Every pending time is >= GVT, so a slot is summarised by one 32-bit key
+  //     key = min(time - GVT, KEY_FAR) << 6 | slot
+  // and the three smallest keys (minimum, runner-up for the new head / two-way tie, third for
+  // three-way-tie detection) come out of a branch-free min/max network: ~5 instructions per slot.
+  // Times are loaded unconditionally (all pq_cap rows exist), 16 loads in flight per chunk.
+  constexpr uint32_t KEY_NONE = 0xffffffffu;          // empty slot
+  constexpr uint32_t KEY_FAR = (1u << 26) - 2u;       // saturated distance (exact value re-read when needed)
+  uint32_t m1 = KEY_NONE, m2 = KEY_NONE, m3 = KEY_NONE;
+  auto consider_key = [&](uint32_t k) {
+    const uint32_t a1 = k < m1 ? k : m1, b1 = k < m1 ? m1 : k;
+    const uint32_t a2 = b1 < m2 ? b1 : m2, b2 = b1 < m2 ? m2 : b1;
+    m1 = a1; m2 = a2; m3 = b2 < m3 ? b2 : m3;
+  };
+  auto make_key = [&](uint64_t t, uint32_t s) -> uint32_t {
+    const uint64_t d = t - pa.gvt;
+    const uint32_t d32 = d >= (uint64_t)KEY_FAR ? KEY_FAR : (uint32_t)d;
+    return (d32 << 6) | s;
   };
   {
-    constexpr int CH = 16;   // every pending time in flight at once: 8 B per slot, coalesced
+    constexpr int CH = 16;
 #pragma unroll 1
     for (uint32_t base = 0; base < np; base += CH) {
       uint64_t tt[CH];
+      const uint64_t *row = v.pq_t + (size_t)base * A + lp;
 #pragma unroll
-      for (int i = 0; i < CH; i++) tt[i] = (base + i < np) ? v.pq_t[(size_t)(base + i) * A + lp] : ~0ull;
+      for (int i = 0; i < CH; i++) tt[i] = (base + i < v.pq_cap) ? row[(size_t)i * A] : 0;
 #pragma unroll
-      for (int i = 0; i < CH; i++) consider(tt[i], base + i);
+      for (int i = 0; i < CH; i++) consider_key(base + i < np ? make_key(tt[i], base + i) : KEY_NONE);
     }
   }
   uint32_t top = np;
@@ -438,15 +447,24 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
         if (base + i < ni) {
           const uint32_t s = top;
           if (ee[i].flags & EV_ANTI) has_anti = PC_ANTI;
-          if (pool_append(v, lp, top, ee[i], acc)) consider(ee[i].time, s);
+          if (pool_append(v, lp, top, ee[i], acc)) consider_key(make_key(ee[i].time, s));
         }
     }
     v.icnt[pa.par][lp] = 0;
   }
+  // decode: t1 = min time at slot s1; a second record with the same time sits at s1b when ties >= 1
+  const uint32_t d1 = m1 >> 6, d2 = m2 >> 6;
+  const uint32_t s1 = m1 & 63u, s1b = m2 & 63u;
+  const uint32_t ties = (m1 != KEY_NONE && d2 == d1 ? 1u : 0u) + (m1 != KEY_NONE && (m3 >> 6) == d1 ? 1u : 0u);
+  bool inexact = (m1 != KEY_NONE && d1 == KEY_FAR) || (m2 != KEY_NONE && d2 == KEY_FAR);   // a saturated key matters
+  const uint64_t t1 = m1 == KEY_NONE ? ~0ull : pa.gvt + d1;
+  const uint64_t t2 = m2 == KEY_NONE ? ~0ull : pa.gvt + d2;
+  const uint64_t ubr = pa.ub > pa.gvt ? pa.ub - pa.gvt : 0;   // (the final sweep runs with ub = t_end <= GVT)
+  const bool in_window = m1 != KEY_NONE && d1 != KEY_FAR && (uint64_t)d1 < ubr;
 
   // ---- phase 2: execute the earliest record if it lies in the window -----------------------------
   uint64_t head = t1;
-  if (t1 < pa.ub) {
+  if (in_window) {
     EvRec e; e.time = t1; e.sub = 0; e.p0 = 0; e.p1 = 0; e.dst = gid32; e.flags = 0;
     uint32_t s_sel = s1;
     uint64_t head_rest = t2;
@@ -516,6 +534,12 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   if (pa.sweep && has_anti) {   // final pass of a drain: no anti-message may linger (rare, out of line)
     sweep_annihilate(v, lp, top, acc);
     has_anti = 0;
+    head = ~0ull;
+#pragma unroll 1
+    for (uint32_t s = 0; s < top; s++) { const uint64_t t = v.pq_t[(size_t)s * A + lp]; if (t < head) head = t; }
+  }
+
+  if (inexact) {   // a saturated key took part: re-read the exact minimum (rare)
     head = ~0ull;
 #pragma unroll 1
     for (uint32_t s = 0; s < top; s++) { const uint64_t t = v.pq_t[(size_t)s * A + lp]; if (t < head) head = t; }
