@@ -338,12 +338,26 @@ DEVA_HD_NOINLINE bool slow_select(const View &v, const ModelParams &mp, const Pa
 template <class M>
 DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, uint32_t lp, Acc &acc) {
   const size_t A = v.A;
+  // Round trip 1: everything whose address depends only on the LP index goes out together - the
+  // header words, the first 16 pending times and the model state - so that the fast path has two
+  // dependent memory round trips (this one; then the chosen record + the undo-log tail).
+  constexpr int CH = 16;
   const uint64_t head0 = v.head[lp];
   const uint32_t np_raw = v.pcnt[lp];
-  const uint32_t np = np_raw & ~PC_ANTI;
-  uint32_t has_anti = np_raw & PC_ANTI;
   uint32_t ni = v.icnt[pa.par][lp];
   const uint32_t lm = v.lmeta[lp];
+  uint64_t tt0[CH];
+  {
+    const uint64_t *row = v.pq_t + lp;
+#pragma unroll
+    for (int i = 0; i < CH; i++) tt0[i] = ((uint32_t)i < v.pq_cap) ? row[(size_t)i * A] : 0;
+  }
+  uint64_t st[MAX_STW];
+#pragma unroll
+  for (int w = 0; w < M::STW; w++) st[w] = v.st[(size_t)w * A + lp];
+  uint64_t seq = v.seq[lp];
+  const uint32_t np = np_raw & ~PC_ANTI;
+  uint32_t has_anti = np_raw & PC_ANTI;
   uint32_t ln = lm & 0xffffu, lt = lm >> 16;
   const bool active = head0 < pa.ub || ni > 0 || (pa.sweep && has_anti);
   if (!active && !(pa.sweep && ln > 0)) {
@@ -398,11 +412,6 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     return;
   }
 
-  uint64_t st[MAX_STW];
-#pragma unroll
-  for (int w = 0; w < M::STW; w++) st[w] = v.st[(size_t)w * A + lp];
-  uint64_t seq = v.seq[lp];
-
   // ---- phase 1: earliest records of the pool -----------------------------------------------------
   // Every pending time is >= GVT, so a slot is summarised by one 32-bit key
   //     key = min(time - GVT, KEY_FAR) << 6 | slot
@@ -422,17 +431,16 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     const uint32_t d32 = d >= (uint64_t)KEY_FAR ? KEY_FAR : (uint32_t)d;
     return (d32 << 6) | s;
   };
-  {
-    constexpr int CH = 16;
+#pragma unroll
+  for (int i = 0; i < CH; i++) consider_key((uint32_t)i < np ? make_key(tt0[i], (uint32_t)i) : KEY_NONE);
 #pragma unroll 1
-    for (uint32_t base = 0; base < np; base += CH) {
-      uint64_t tt[CH];
-      const uint64_t *row = v.pq_t + (size_t)base * A + lp;
+  for (uint32_t base = CH; base < np; base += CH) {   // pools deeper than 16 records (rare)
+    uint64_t tt[CH];
+    const uint64_t *row = v.pq_t + (size_t)base * A + lp;
 #pragma unroll
-      for (int i = 0; i < CH; i++) tt[i] = (base + i < v.pq_cap) ? row[(size_t)i * A] : 0;
+    for (int i = 0; i < CH; i++) tt[i] = (base + i < v.pq_cap) ? row[(size_t)i * A] : 0;
 #pragma unroll
-      for (int i = 0; i < CH; i++) consider_key(base + i < np ? make_key(tt[i], base + i) : KEY_NONE);
-    }
+    for (int i = 0; i < CH; i++) consider_key(base + i < np ? make_key(tt[i], base + i) : KEY_NONE);
   }
   uint32_t top = np;
   if (ni > 0) {   // this window's arrivals (children and anti-messages from other LPs) join the pool
