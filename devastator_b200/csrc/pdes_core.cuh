@@ -415,16 +415,20 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   // ---- phase 1: earliest records of the pool -----------------------------------------------------
   // Every pending time is >= GVT, so a slot is summarised by one 32-bit key
   //     key = min(time - GVT, KEY_FAR) << 6 | slot
-  // and the three smallest keys (minimum, runner-up for the new head / two-way tie, third for
-  // three-way-tie detection) come out of a branch-free min/max network: ~5 instructions per slot.
-  // Times are loaded unconditionally (all pq_cap rows exist), 16 loads in flight per chunk.
-  constexpr uint32_t KEY_NONE = 0xffffffffu;          // empty slot
+  // and the FOUR smallest keys come out of a branch-free min/max network (7 instructions per slot).
+  // m1..m4 stay in registers and feed up to DEVA_EV_PER_PASS executions in this launch.
+  // Times are loaded unconditionally (all pq_cap rows exist), 16 loads in flight.
+  constexpr uint32_t KEY_NONE = 0xffffffffu;          // empty / unknown
   constexpr uint32_t KEY_FAR = (1u << 26) - 2u;       // saturated distance (exact value re-read when needed)
-  uint32_t m1 = KEY_NONE, m2 = KEY_NONE, m3 = KEY_NONE;
+  uint32_t m1 = KEY_NONE, m2 = KEY_NONE, m3 = KEY_NONE, m4 = KEY_NONE;
+  uint32_t dropped = KEY_NONE;   // smallest key that fell off the 4-entry list (lower bound of the unknown rest)
   auto consider_key = [&](uint32_t k) {
     const uint32_t a1 = k < m1 ? k : m1, b1 = k < m1 ? m1 : k;
     const uint32_t a2 = b1 < m2 ? b1 : m2, b2 = b1 < m2 ? m2 : b1;
-    m1 = a1; m2 = a2; m3 = b2 < m3 ? b2 : m3;
+    const uint32_t a3 = b2 < m3 ? b2 : m3, b3 = b2 < m3 ? m3 : b2;
+    const uint32_t a4 = b3 < m4 ? b3 : m4, b4 = b3 < m4 ? m4 : b3;
+    m1 = a1; m2 = a2; m3 = a3; m4 = a4;
+    dropped = b4 < dropped ? b4 : dropped;
   };
   auto make_key = [&](uint64_t t, uint32_t s) -> uint32_t {
     const uint64_t d = t - pa.gvt;
@@ -460,84 +464,115 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     }
     v.icnt[pa.par][lp] = 0;
   }
-  // decode: t1 = min time at slot s1; a second record with the same time sits at s1b when ties >= 1
-  const uint32_t d1 = m1 >> 6, d2 = m2 >> 6;
-  const uint32_t s1 = m1 & 63u, s1b = m2 & 63u;
-  const uint32_t ties = (m1 != KEY_NONE && d2 == d1 ? 1u : 0u) + (m1 != KEY_NONE && (m3 >> 6) == d1 ? 1u : 0u);
-  bool inexact = (m1 != KEY_NONE && d1 == KEY_FAR) || (m2 != KEY_NONE && d2 == KEY_FAR);   // a saturated key matters
-  const uint64_t t1 = m1 == KEY_NONE ? ~0ull : pa.gvt + d1;
-  const uint64_t t2 = m2 == KEY_NONE ? ~0ull : pa.gvt + d2;
   const uint64_t ubr = pa.ub > pa.gvt ? pa.ub - pa.gvt : 0;   // (the final sweep runs with ub = t_end <= GVT)
-  const bool in_window = m1 != KEY_NONE && d1 != KEY_FAR && (uint64_t)d1 < ubr;
 
-  // ---- phase 2: execute the earliest record if it lies in the window -----------------------------
-  uint64_t head = t1;
-  if (in_window) {
-    EvRec e; e.time = t1; e.sub = 0; e.p0 = 0; e.p1 = 0; e.dst = gid32; e.flags = 0;
-    uint32_t s_sel = s1;
-    uint64_t head_rest = t2;
+  // ---- phase 2: execute the earliest records that lie in the window ------------------------------
+  // The list m1 <= m2 <= m3 <= m4 holds the true smallest keys of the pool (everything else is
+  // >= `dropped`), so while it is non-empty m1 IS the LP's next event.  The first event gets the
+  // full treatment (ties, anti-message at the head, straggler -> out-of-line slow paths); follow-up
+  // events run only in the plain case and otherwise wait for the next launch.
+  uint64_t head = ~0ull;
+  bool head_known = false;      // head was set by a slow path (the key list is stale)
+#ifndef DEVA_EV_PER_PASS
+#define DEVA_EV_PER_PASS 3
+#endif
+#pragma unroll 1
+  for (int it = 0; it < DEVA_EV_PER_PASS; it++) {
+    const uint32_t k1 = m1, d1 = k1 >> 6;
+    if (k1 == KEY_NONE || d1 == KEY_FAR || (uint64_t)d1 >= ubr) break;
+    const bool tie2 = (m2 >> 6) == d1, tie3 = (m3 >> 6) == d1 || (dropped >> 6) == d1;
+    if (it > 0 && (tie2 || tie3)) break;
+    EvRec e; e.time = pa.gvt + d1; e.sub = 0; e.p0 = 0; e.p1 = 0; e.dst = gid32; e.flags = 0;
+    uint32_t s_sel = k1 & 63u;
+    bool second_of_tie = false;   // the record at m2 (not m1) was chosen
     bool ok = true;
     int slow = 0;   // 1 = straggler (rollback only), 2 = full re-selection (anti-message at the head, 3-way tie)
-    if (ties > 1) slow = 2;
+    if (tie3) slow = 2;
     else {
-      PqRest r = ld_rest(&v.pq_r[(size_t)s1 * A + lp]);
+      PqRest r = ld_rest(&v.pq_r[(size_t)s_sel * A + lp]);
       uint32_t antis = r.p1f & P1_ANTI;
-      if (ties == 1) {   // two records share the minimum time: the smaller subtime runs
-        const PqRest rb = ld_rest(&v.pq_r[(size_t)s1b * A + lp]);
+      if (tie2) {   // two records share the minimum time: the smaller subtime runs
+        const PqRest rb = ld_rest(&v.pq_r[(size_t)(m2 & 63u) * A + lp]);
         antis |= rb.p1f & P1_ANTI;
-        if (rb.sub < r.sub) { r = rb; s_sel = s1b; }
+        if (rb.sub < r.sub) { r = rb; s_sel = m2 & 63u; second_of_tie = true; }
       }
       e.sub = r.sub; e.p0 = r.p0; e.p1 = r.p1f & ~P1_ANTI;
       if (antis) slow = 2;
-      else if (ln > 0 && key_less(e.time, e.sub, new_t, new_s)) slow = 1;   // lazy straggler detection, pdes.cxx:496-515
+      else if (it == 0 && ln > 0 && key_less(e.time, e.sub, new_t, new_s)) slow = 1;   // lazy straggler detection, pdes.cxx:496-515
     }
+    if (slow && it > 0) break;
+    uint64_t head_rest = ~0ull;
     if (slow) {
       // Out-of-line calls get COPIES of the hot variables (an address-taken variable would live in
       // local memory for the whole kernel).
       uint32_t top2 = top, ln2 = ln, s2 = s_sel;
-      uint64_t seq2 = seq, hr2 = head_rest, st2[MAX_STW];
+      uint64_t seq2 = seq, hr2 = ~0ull, st2[MAX_STW];
 #pragma unroll
       for (int w = 0; w < MAX_STW; w++) st2[w] = st[w];
       Acc a2; a2.tmin = ~0ull; a2.executed = a2.committed = a2.rolled = a2.anti = a2.remote = a2.err = a2.nondet = 0;
       EvRec e2 = e;
       if (slow == 1) {   // undo everything later than the straggler; it stays the earliest record
+        // runner-up of the pool before the rollback: the other key of the pair (m1, m2)
+        const uint32_t kr = second_of_tie ? m1 : m2;
+        hr2 = kr == KEY_NONE ? ~0ull : pa.gvt + (kr >> 6);
+        bool sat = kr != KEY_NONE && (kr >> 6) == KEY_FAR;
         uint64_t rq = ~0ull;
         rollback<M>(v, mp, pa, lp, a2, top2, ln2, lt, st2, seq2, e.time, e.sub, nullptr, rq, s2);
         if (rq < hr2) hr2 = rq;
+        if (sat) hr2 = 0;   // (saturated runner-up: exact head is re-read below)
       } else ok = slow_select<M>(v, mp, pa, lp, a2, top2, ln2, lt, st2, seq2, e2, s2, hr2);
       top = top2; ln = ln2; s_sel = s2; seq = seq2; head_rest = hr2; e = e2;
 #pragma unroll
       for (int w = 0; w < MAX_STW; w++) st[w] = st2[w];
       if (a2.tmin < acc.tmin) acc.tmin = a2.tmin;
       acc.rolled += a2.rolled; acc.anti += a2.anti; acc.remote += a2.remote; acc.err |= a2.err;
+      head_known = true;
+      head = ok ? (e.time < head_rest ? e.time : head_rest) : head_rest;
+      if (!ok) break;
     }
-    head = ok ? (e.time < head_rest ? e.time : head_rest) : head_rest;
-    if (ok && ln < v.log_cap) {   // (undo log full: the event waits; GVT cannot pass it)
-      uint32_t li = lt + ln; if (li >= v.log_cap) li -= v.log_cap;
-      LogRec lr;
-      lr.time = e.time; lr.sub = e.sub; lr.p0 = e.p0;
+    if (ln == v.log_cap) break;   // undo log full: the event waits; GVT cannot pass it
+    uint32_t li = lt + ln; if (li >= v.log_cap) li -= v.log_cap;
+    LogRec lr;
+    lr.time = e.time; lr.sub = e.sub; lr.p0 = e.p0;
 #pragma unroll
-      for (int w = 0; w < MAX_STW; w++) lr.st[w] = w < M::STW ? st[w] : 0;
-      EvRec c;
-      const bool sent = M::execute(mp, st, e, gid, c, false);
-      lr.fl = (e.p1 & ~FL_SENT) | (sent ? FL_SENT : 0u);
-      st_log(&v.lg[(size_t)li * A + lp], lr);
-      ln++;
-      acc.executed++;
-      head = head_rest;
-      if (sent) {
-        if (!mp.user_subtime) c.sub = seq;   // event_subtime / next_seq_id, pdes.hxx:513-526,676
-        seq += v.lp_n;
-      }
-      if (sent && (uint64_t)c.dst == gid) {  // self-sent child takes the slot of its parent, in place
-        pq_store(v, lp, s_sel, c);
-        if (c.time < head) head = c.time;
-      } else {
-        pool_remove(v, lp, top, s_sel);
-        if (sent) deliver(v, pa.par ^ 1u, c, acc);
-      }
+    for (int w = 0; w < MAX_STW; w++) lr.st[w] = w < M::STW ? st[w] : 0;
+    EvRec c;
+    const bool sent = M::execute(mp, st, e, gid, c, false);
+    lr.fl = (e.p1 & ~FL_SENT) | (sent ? FL_SENT : 0u);
+    st_log(&v.lg[(size_t)li * A + lp], lr);
+    ln++;
+    acc.executed++;
+    if (sent) {
+      if (!mp.user_subtime) c.sub = seq;   // event_subtime / next_seq_id, pdes.hxx:513-526,676
+      seq += v.lp_n;
     }
+    const bool self_child = sent && (uint64_t)c.dst == gid;
+    // the executed record leaves the key list
+    if (second_of_tie) { m2 = m3; m3 = m4; m4 = KEY_NONE; }
+    else { m1 = m2; m2 = m3; m3 = m4; m4 = KEY_NONE; }
+    if (self_child) {            // self-sent child takes the slot of its parent, in place
+      pq_store(v, lp, s_sel, c);
+      if (!slow) consider_key(make_key(c.time, s_sel));
+      if (slow && c.time < head_rest) head_rest = c.time;
+    } else {
+      const uint32_t last = top - 1;
+      pool_remove(v, lp, top, s_sel);
+      if (!slow && s_sel != last) {   // the record that lived in slot `last` now lives in slot s_sel
+        if (m1 != KEY_NONE && (m1 & 63u) == last) m1 = (m1 & ~63u) | s_sel;
+        if (m2 != KEY_NONE && (m2 & 63u) == last) m2 = (m2 & ~63u) | s_sel;
+        if (m3 != KEY_NONE && (m3 & 63u) == last) m3 = (m3 & ~63u) | s_sel;
+        // (a changed slot field can leave two equal-time keys out of order; equal times are
+        //  resolved by reading both subtimes, so order between them does not matter)
+      }
+      if (sent) deliver(v, pa.par ^ 1u, c, acc);
+    }
+    if (slow) { head = head_rest; break; }   // the pool was reshuffled: the key list is stale
   }
+  bool inexact = false;
+  if (!head_known) {
+    if (m1 != KEY_NONE) { head = pa.gvt + (m1 >> 6); inexact = (m1 >> 6) == KEY_FAR; }
+    else { head = ~0ull; inexact = dropped != KEY_NONE; }   // list exhausted but the pool holds more
+  } else inexact = head == 0;
 
   if (pa.sweep && has_anti) {   // final pass of a drain: no anti-message may linger (rare, out of line)
     sweep_annihilate(v, lp, top, acc);
