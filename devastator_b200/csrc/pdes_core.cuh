@@ -466,6 +466,27 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   }
   const uint64_t ubr = pa.ub > pa.gvt ? pa.ub - pa.gvt : 0;   // (the final sweep runs with ub = t_end <= GVT)
 
+  // Round trip 2: the records behind the three earliest keys, fetched together (one exposed
+  // latency for up to three executions instead of one each).
+  PqRest pr[3];
+  uint32_t pslot[3];
+  {
+    const uint32_t mk[3] = {m1, m2, m3};
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const bool want = mk[j] != KEY_NONE && (uint64_t)(mk[j] >> 6) < ubr;
+      pslot[j] = want ? (mk[j] & 63u) : 0xffffffffu;
+      if (want) pr[j] = ld_rest(&v.pq_r[(size_t)pslot[j] * A + lp]);
+      else { pr[j].sub = 0; pr[j].p0 = 0; pr[j].p1f = 0; }
+    }
+  }
+  auto rest_of = [&](uint32_t slot) -> PqRest {   // prefetched copy if there is one, else memory
+    if (slot == pslot[0]) return pr[0];
+    if (slot == pslot[1]) return pr[1];
+    if (slot == pslot[2]) return pr[2];
+    return ld_rest(&v.pq_r[(size_t)slot * A + lp]);
+  };
+
   // ---- phase 2: execute the earliest records that lie in the window ------------------------------
   // The list m1 <= m2 <= m3 <= m4 holds the true smallest keys of the pool (everything else is
   // >= `dropped`), so while it is non-empty m1 IS the LP's next event.  The first event gets the
@@ -489,10 +510,10 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     int slow = 0;   // 1 = straggler (rollback only), 2 = full re-selection (anti-message at the head, 3-way tie)
     if (tie3) slow = 2;
     else {
-      PqRest r = ld_rest(&v.pq_r[(size_t)s_sel * A + lp]);
+      PqRest r = rest_of(s_sel);
       uint32_t antis = r.p1f & P1_ANTI;
       if (tie2) {   // two records share the minimum time: the smaller subtime runs
-        const PqRest rb = ld_rest(&v.pq_r[(size_t)(m2 & 63u) * A + lp]);
+        const PqRest rb = rest_of(m2 & 63u);
         antis |= rb.p1f & P1_ANTI;
         if (rb.sub < r.sub) { r = rb; s_sel = m2 & 63u; second_of_tie = true; }
       }
@@ -550,6 +571,8 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     // the executed record leaves the key list
     if (second_of_tie) { m2 = m3; m3 = m4; m4 = KEY_NONE; }
     else { m1 = m2; m2 = m3; m3 = m4; m4 = KEY_NONE; }
+#pragma unroll
+    for (int j = 0; j < 3; j++) if (pslot[j] == s_sel || pslot[j] == top - 1) pslot[j] = 0xffffffffu;   // these slots change below
     if (self_child) {            // self-sent child takes the slot of its parent, in place
       pq_store(v, lp, s_sel, c);
       if (!slow) consider_key(make_key(c.time, s_sel));
