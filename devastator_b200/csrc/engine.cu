@@ -46,8 +46,6 @@ constexpr int PASS_THREADS = 128;
 
 // MINB = minimum resident blocks per SM the register allocator must allow (occupancy knob)
 template <class M, int MINB>
-// __grid_constant__: out-of-line callees take the parameters' addresses in place (without it every
-// thread copies the ~400 bytes of parameters to its local stack: measured 14 M store sectors/pass)
 __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const __grid_constant__ View v, const __grid_constant__ ModelParams mp,
                                                              const __grid_constant__ PassArgs pa) {
   const uint32_t lp = blockIdx.x * PASS_THREADS + threadIdx.x;

@@ -1,34 +1,26 @@
 // pdes_core.cuh - one optimistic window for ONE LP: the body of the execute kernel.
 //
 // Replaces, for a device-resident model, the reference's per-event scheduler loop:
-//   drain "execute one event"          pdes.cxx:900-999   -> fast path of lp_pass
-//   insert_past (lazy straggler check) pdes.cxx:496-515   -> straggler test + slow_select/rollback
-//   remove_past / rollback             pdes.cxx:517-693   -> rollback()
-//   arrive_near<+-1>, arrive_far[_anti] pdes.cxx:393-493  -> inbox fold + slow_select
+//   drain "execute one event"          pdes.cxx:900-999   -> phase 4
+//   insert_past (lazy straggler check) pdes.cxx:496-515   -> phase 3
+//   remove_past / rollback             pdes.cxx:517-693   -> phases 2-3
+//   arrive_near<+-1>, arrive_far[_anti] pdes.cxx:393-493  -> phase 1 (inbox fold) + phase 2
 //   fossil collection / commit sweep   pdes.cxx:816-871   -> phase 0
 //   execute_context::send              pdes.hxx:666-732   -> deliver()
 //   cd_state::next_seq_id              pdes.cxx:221-225   -> seq += N / seq -= N
 //
-// One launch = one pass over all LPs, one thread per LP.  In a pass every LP executes AT MOST ITS
-// EARLIEST pending event, if that event lies below the window bound ub = min(GVT + W, t_end).
-// That keeps the hot path straight-line and the lanes of a warp in step (measured on B200: a
-// per-thread loop over a variable number of events ran at 9 of 32 lanes and was instruction-fetch
-// bound).  The common case touches: the LP's header (20 B), its pending times (8 B per slot, all
-// loads in flight together), the chosen record (16 B), the model state, one undo-log record
-// (48 B) and the child (24 B in place when self-sent, else 32 B into the destination's inbox).
-// Everything unusual - a tie on the minimum time beyond two records, an anti-message at the head of
-// the pool, a straggler - goes to slow_select(), out of line, which rescans the pool from memory.
+// One thread owns one LP for the whole window, so everything of that LP (pending slots, undo-log
+// ring, state words, sequence counter) is touched by exactly one thread: no locks.  The only
+// cross-thread traffic is delivery of a child / anti-message into ANOTHER LP's inbox (next-window
+// parity), claimed with one atomicAdd on that LP's arrival counter.
 //
-// Anti-messages are ordinary records in the destination's pool: they "run" as cancellations when
-// they become the LP's earliest record (ties go to the anti-message first), annihilating the
-// identical positive in the pool or, if it already ran, rolling the LP back through it.  Models
-// are pure (models.cuh), so the child of an undone event is regenerated from the saved pre-state
-// instead of being logged.  A positive is always delivered at least one window before its
-// anti-message, so the anti-before-positive case of pdes.cxx:400-457 cannot arise.
-//
-// One thread owns one LP for the whole pass: no locks.  The only cross-thread traffic is delivery
-// of a child / anti-message into ANOTHER LP's inbox (next-window parity), claimed with one
-// atomicAdd on that LP's arrival counter.
+// Rollback does not log children.  Models are pure (models.cuh), so the child of an undone event
+// is regenerated from the saved pre-state; the log keeps one bit (EV_SENT).  Anti-messages carry
+// the full record and cancel the positive with identical (time, subtime, payload): two records
+// that agree on all of these are interchangeable, so no event ids are needed.  A positive is
+// always delivered at least one window before its anti-message (an event can only be undone in a
+// later window than the one it ran in), so the anti-before-positive case of
+// arrive_far/arrive_far_anti (pdes.cxx:400-457) cannot arise here.
 //
 // Compiles for the device (engine.cu) and for the host (tests/emu: CPU logic tests only).
 #pragma once
@@ -36,6 +28,13 @@
 #include "models.cuh"
 
 namespace deva_b200 {
+
+#ifndef DEVA_WK_CAP
+#define DEVA_WK_CAP 24   // in-window working set per LP (events sorted in thread-local memory)
+#endif
+#ifndef DEVA_AN_CAP
+#define DEVA_AN_CAP 8    // anti-messages handled per LP per window (extra ones wait in pending)
+#endif
 
 // ---- atomics / vector moves: CUDA on the device, plain on the host emulation --------------------
 #if defined(__CUDA_ARCH__)
@@ -109,12 +108,51 @@ DEVA_HD bool same_event(const EvRec &a, const EvRec &b) {
 }
 constexpr uint32_t P1_ANTI = 0x80000000u;   // PqRest::p1f anti-message bit
 constexpr uint32_t FL_SENT = 0x80000000u;   // LogRec::fl "sent a child" bit
-constexpr uint32_t PC_ANTI = 0x80000000u;   // pcnt[lp] bit: the pool may hold anti-messages
 
-// per-thread accumulators, warp-reduced by the kernel wrapper
+// per-thread accumulators, block-reduced by the kernel wrapper
 struct Acc {
   uint64_t tmin;     // min time over everything this thread leaves pending or emits (-> next GVT)
   uint32_t executed, committed, rolled, anti, remote, err, nondet;
+};
+
+// In-window events of one LP, sorted DESCENDING by (time, sub): the next event to run is e[n-1].
+struct WorkSet {
+  uint64_t t[DEVA_WK_CAP], s[DEVA_WK_CAP];
+  uint32_t p0[DEVA_WK_CAP], p1[DEVA_WK_CAP];
+  int n;
+  DEVA_HD EvRec get(int i, uint32_t dst) const {
+    EvRec e; e.time = t[i]; e.sub = s[i]; e.p0 = p0[i]; e.p1 = p1[i]; e.dst = dst; e.flags = 0; return e;
+  }
+  DEVA_HD void put(int i, const EvRec &e) { t[i] = e.time; s[i] = e.sub; p0[i] = e.p0; p1[i] = e.p1; }
+  // Insert keeping order.  Returns 0 = inserted; 1 = inserted and `out` (the largest) evicted;
+  // 2 = rejected (full and e is not smaller than the largest).
+  DEVA_HD int insert(const EvRec &e, EvRec &out, uint32_t dst) {
+    int evicted = 0;
+    if (n == DEVA_WK_CAP) {
+      if (!key_less(e.time, e.sub, t[0], s[0])) return 2;
+      out = get(0, dst);
+      for (int i = 0; i + 1 < n; i++) { t[i] = t[i + 1]; s[i] = s[i + 1]; p0[i] = p0[i + 1]; p1[i] = p1[i + 1]; }
+      n--;
+      evicted = 1;
+    }
+    int i = n;   // entries not larger than e sit at the end and move one place right
+    while (i > 0 && !key_less(e.time, e.sub, t[i - 1], s[i - 1])) {
+      t[i] = t[i - 1]; s[i] = s[i - 1]; p0[i] = p0[i - 1]; p1[i] = p1[i - 1];
+      i--;
+    }
+    put(i, e);
+    n++;
+    return evicted;
+  }
+  DEVA_HD bool remove_match(const EvRec &a) {
+    for (int i = 0; i < n; i++)
+      if (t[i] == a.time && s[i] == a.sub && p0[i] == a.p0 && p1[i] == a.p1) {
+        for (int j = i; j + 1 < n; j++) { t[j] = t[j + 1]; s[j] = s[j + 1]; p0[j] = p0[j + 1]; p1[j] = p1[j + 1]; }
+        n--;
+        return true;
+      }
+    return false;
+  }
 };
 
 // Deliver a record (child or anti-message) to the LP that owns rec.dst.  Same GPU: straight into
@@ -153,226 +191,28 @@ DEVA_HD EvRec pq_load(const View &v, uint32_t lp, uint32_t slot, uint64_t t, uin
   return e;
 }
 
-// ---- pool helpers (slots [0, top) are in use, always compact) ------------------------------------
-DEVA_HD void pool_remove(const View &v, uint32_t lp, uint32_t &top, uint32_t s) {   // move the last record into s
-  top--;
-  if (s != top) {
-    v.pq_t[(size_t)s * v.A + lp] = v.pq_t[(size_t)top * v.A + lp];
-    st_rest(&v.pq_r[(size_t)s * v.A + lp], ld_rest(&v.pq_r[(size_t)top * v.A + lp]));
-  }
-}
-// like pool_remove, but keeps `keep` pointing at the same record if that record is the one moved
-DEVA_HD void pool_remove_keep(const View &v, uint32_t lp, uint32_t &top, uint32_t s, uint32_t &keep) {
-  pool_remove(v, lp, top, s);
-  if (keep == top) keep = s;   // the last record (old index top) now lives in slot s
-}
-DEVA_HD bool pool_append(const View &v, uint32_t lp, uint32_t &top, const EvRec &e, Acc &acc) {
-  if (top >= v.pq_cap) { acc.err |= ERR_PQ_OVERFLOW; return false; }
-  pq_store(v, lp, top, e);
-  top++;
-  return true;
-}
-// slot of a record identical to `a` with the given anti flag, skipping slot `skip`; -1 if none.
-// The pool's times are fetched 16 at a time (independent loads), the 16-byte rest only on a time match.
-DEVA_HD_NOINLINE int pool_find(const View &v, uint32_t lp, uint32_t top, const EvRec &a, uint32_t want_anti, uint32_t skip) {
-  constexpr int CH = 16;
-#pragma unroll 1
-  for (uint32_t base = 0; base < top; base += CH) {
-    uint64_t tt[CH];
-#pragma unroll
-    for (int i = 0; i < CH; i++) tt[i] = (base + i < top) ? v.pq_t[(size_t)(base + i) * v.A + lp] : ~0ull;
-    uint32_t hit = 0;
-#pragma unroll
-    for (int i = 0; i < CH; i++) hit |= (tt[i] == a.time && base + i < top && base + i != skip) ? (1u << i) : 0u;
-#pragma unroll 1
-    while (hit) {
-      const uint32_t s = base + (uint32_t)ffs64(hit) - 1u;
-      hit &= hit - 1;
-      const PqRest r = ld_rest(&v.pq_r[(size_t)s * v.A + lp]);
-      if (r.sub == a.sub && r.p0 == a.p0 && (r.p1f & ~P1_ANTI) == a.p1 && ((r.p1f & P1_ANTI) ? 1u : 0u) == want_anti) return (int)s;
-    }
-  }
-  return -1;
-}
-
-// ---- rollback (pdes.cxx:527-693), out of line -----------------------------------------------------
-// Undo the newest log entries while their key is > (kt,ks) [straggler] or >= (kt,ks) [anti-message
-// target, `kill` != null].  Every undone event restores the saved state, steps the sequence
-// counter back, regenerates its child and cancels it (self-sent: removed from this pool, else an
-// anti-message is delivered), and goes back to the pool - except the entry identical to *kill,
-// which is annihilated.  Returns whether *kill was found.
-template <class M>
-DEVA_HD_NOINLINE bool rollback(const View &v, const ModelParams &mp, const PassArgs &pa, uint32_t lp, Acc &acc,
-                               uint32_t &top, uint32_t &ln, uint32_t lt, uint64_t *st, uint64_t &seq,
-                               uint64_t kt, uint64_t ks, const EvRec *kill, uint64_t &requeued_min, uint32_t &keep_slot) {
-  const size_t A = v.A;
-  const uint64_t gid = v.lp_begin + lp;
-  const uint32_t gid32 = (uint32_t)gid;
-  bool killed = false;
-#pragma unroll 1
-  while (ln > 0) {
-    uint32_t li = lt + ln - 1; if (li >= v.log_cap) li -= v.log_cap;
-    const LogRec *lrp = &v.lg[(size_t)li * A + lp];
-    const uint64_t et = lrp->time, es = lrp->sub;
-    const bool undo = kill ? !key_less(et, es, kt, ks) : key_less(kt, ks, et, es);
-    if (!undo) break;
-    if (et < pa.gvt) acc.err |= ERR_BELOW_GVT;            // would undo a committable event
-    const LogRec lr = ld_log(lrp);
-    EvRec le; le.time = lr.time; le.sub = lr.sub; le.p0 = lr.p0; le.p1 = lr.fl & ~FL_SENT; le.dst = gid32; le.flags = 0;
-#pragma unroll
-    for (int w = 0; w < M::STW; w++) st[w] = lr.st[w];     // == reverse::unexecute
-    if (lr.fl & FL_SENT) {
-      uint64_t tmp[MAX_STW];
-#pragma unroll
-      for (int w = 0; w < M::STW; w++) tmp[w] = st[w];
-      EvRec c;
-      M::execute(mp, tmp, le, gid, c, true);               // regenerate the child from the pre-state
-      seq -= v.lp_n;                                       // pdes.cxx:566,574
-      if (!mp.user_subtime) c.sub = seq;
-      if ((uint64_t)c.dst == gid) {
-        const int q = pool_find(v, lp, top, c, 0u, 0xffffffffu);
-        // (never the straggler's own slot: the child is later than its parent, which is later than the straggler)
-      if (q >= 0) pool_remove_keep(v, lp, top, (uint32_t)q, keep_slot); else acc.err |= ERR_SELF_CHILD_LOST;
-      } else {
-        c.flags = EV_ANTI;
-        deliver(v, pa.par ^ 1u, c, acc);
-        acc.anti++;
-      }
-    }
-    if (kill && !killed && same_event(*kill, le)) killed = true;   // annihilated
-    else { pool_append(v, lp, top, le, acc); if (le.time < requeued_min) requeued_min = le.time; }   // back to pending
-    ln--;
-    acc.rolled++;
-  }
-  return killed;
-}
-
-// End of a drain: every anti-message still in the pool lies at or beyond t_end, so its positive
-// never ran and sits in the same pool.  Annihilate all such pairs (the reference asserts that no
-// anti-message lingers when drain returns, pdes.cxx:1025-1035).
-DEVA_HD_NOINLINE void sweep_annihilate(const View &v, uint32_t lp, uint32_t &top, Acc &acc) {
-  const uint32_t gid32 = (uint32_t)(v.lp_begin + lp);
-  uint32_t s = 0;
-#pragma unroll 1
-  while (s < top) {
-    const EvRec a = pq_load(v, lp, s, v.pq_t[(size_t)s * v.A + lp], gid32);
-    if (!(a.flags & EV_ANTI)) { s++; continue; }
-    const int q = pool_find(v, lp, top, a, 0u, s);
-    if (q < 0) { acc.err |= ERR_ANTI_UNMATCHED; s++; continue; }
-    const uint32_t hi = (uint32_t)q > s ? (uint32_t)q : s, lo = (uint32_t)q > s ? s : (uint32_t)q;
-    pool_remove(v, lp, top, hi);
-    pool_remove(v, lp, top, lo);
-    s = lo;   // whatever was moved into the lower slot has not been examined yet
-  }
-}
-
-// ---- slow path: full re-selection from memory (ties, anti-messages, stragglers) -------------------
-// Returns true when `e` (pool slot s_sel) is the LP's next event to execute: below the window
-// bound, positive, and no longer a straggler.  head_rest = min time over the other pool records.
-// Returns false when nothing is executable; head_rest = min time over the whole pool.
-template <class M>
-DEVA_HD_NOINLINE bool slow_select(const View &v, const ModelParams &mp, const PassArgs &pa, uint32_t lp, Acc &acc,
-                                  uint32_t &top, uint32_t &ln, uint32_t lt, uint64_t *st, uint64_t &seq,
-                                  EvRec &e, uint32_t &s_sel, uint64_t &head_rest) {
-  const size_t A = v.A;
-  const uint32_t gid32 = (uint32_t)(v.lp_begin + lp);
-#pragma unroll 1
-  for (int guard = 0; guard < 65536; guard++) {
-    // minimum key over the pool: time, then anti-messages first, then subtime.  Times are fetched
-    // 16 at a time; a record's rest only when its time ties or beats the best so far.
-    uint64_t bt = ~0ull, bs = ~0ull, t2 = ~0ull;
-    uint32_t bslot = 0xffffffffu, bp1f = 0, bp0 = 0;
-    constexpr int CH = 16;
-#pragma unroll 1
-    for (uint32_t base = 0; base < top; base += CH) {
-      uint64_t tt[CH];
-#pragma unroll
-      for (int i = 0; i < CH; i++) tt[i] = (base + i < top) ? v.pq_t[(size_t)(base + i) * A + lp] : ~0ull;
-#pragma unroll 1
-      for (int i = 0; i < CH; i++) {
-        const uint32_t s = base + i;
-        if (s >= top) break;
-        const uint64_t t = tt[i];
-        if (t > bt) { if (t < t2) t2 = t; continue; }
-        const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
-        const uint32_t anti = r.p1f & P1_ANTI;
-        bool better = true;
-        if (t == bt) better = (anti && !(bp1f & P1_ANTI)) || (anti == (bp1f & P1_ANTI) && r.sub < bs);
-        t2 = bt;                      // the displaced best, or the tied record, is the runner-up
-        if (better) { bt = t; bs = r.sub; bp0 = r.p0; bp1f = r.p1f; bslot = s; }
-      }
-    }
-    if (bslot == 0xffffffffu || bt >= pa.ub) { head_rest = bt; return false; }
-    EvRec cand; cand.time = bt; cand.sub = bs; cand.p0 = bp0; cand.p1 = bp1f & ~P1_ANTI; cand.dst = gid32; cand.flags = 0;
-    if (bp1f & P1_ANTI) {
-      // anti-message at the head of the pool: annihilate its positive (arrive_near<-1>, pdes.cxx:480-489)
-      const int q = pool_find(v, lp, top, cand, 0u, bslot);
-      if (q >= 0) {           // not yet executed: drop both (higher slot first keeps the lower valid)
-        const uint32_t hi = (uint32_t)q > bslot ? (uint32_t)q : bslot, lo = (uint32_t)q > bslot ? bslot : (uint32_t)q;
-        pool_remove(v, lp, top, hi);
-        pool_remove(v, lp, top, lo);
-      } else {                // already executed: roll back through it (remove_past, pdes.cxx:517-525)
-        pool_remove(v, lp, top, bslot);
-        uint64_t rq = ~0ull; uint32_t keep = 0xffffffffu;
-        if (!rollback<M>(v, mp, pa, lp, acc, top, ln, lt, st, seq, bt, bs, &cand, rq, keep)) acc.err |= ERR_ANTI_UNMATCHED;
-      }
-      continue;
-    }
-    if (ln > 0) {             // lazy straggler detection (insert_past, pdes.cxx:496-515)
-      uint32_t li = lt + ln - 1; if (li >= v.log_cap) li -= v.log_cap;
-      const LogRec *lrp = &v.lg[(size_t)li * A + lp];
-      if (key_less(bt, bs, lrp->time, lrp->sub)) {
-        uint64_t rq = ~0ull; uint32_t keep = bslot;
-        rollback<M>(v, mp, pa, lp, acc, top, ln, lt, st, seq, bt, bs, nullptr, rq, keep);
-        continue;             // undone events went back to the pool: select again
-      }
-    }
-    e = cand; s_sel = bslot; head_rest = t2;
-    return true;
-  }
-  acc.err |= ERR_LOG_STALL;
-  head_rest = 0;
-  return false;
-}
-
 template <class M>
 DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, uint32_t lp, Acc &acc) {
   const size_t A = v.A;
-  // Round trip 1: everything whose address depends only on the LP index goes out together - the
-  // header words, the first 16 pending times and the model state - so that the fast path has two
-  // dependent memory round trips (this one; then the chosen record + the undo-log tail).
-  constexpr int CH = 16;
   const uint64_t head0 = v.head[lp];
-  const uint32_t np_raw = v.pcnt[lp];
+  const uint32_t np = v.pcnt[lp];
   uint32_t ni = v.icnt[pa.par][lp];
   const uint32_t lm = v.lmeta[lp];
-  uint64_t tt0[CH];
-  {
-    const uint64_t *row = v.pq_t + lp;
-#pragma unroll
-    for (int i = 0; i < CH; i++) tt0[i] = ((uint32_t)i < v.pq_cap) ? row[(size_t)i * A] : 0;
-  }
-  uint64_t st[MAX_STW];
-#pragma unroll
-  for (int w = 0; w < M::STW; w++) st[w] = v.st[(size_t)w * A + lp];
-  uint64_t seq = v.seq[lp];
-  const uint32_t np = np_raw & ~PC_ANTI;
-  uint32_t has_anti = np_raw & PC_ANTI;
   uint32_t ln = lm & 0xffffu, lt = lm >> 16;
-  const bool active = head0 < pa.ub || ni > 0 || (pa.sweep && has_anti);
+  const bool active = head0 < pa.ub || ni > 0;
   if (!active && !(pa.sweep && ln > 0)) {
     if (head0 < acc.tmin) acc.tmin = head0;
     return;
   }
   const uint64_t gid = v.lp_begin + lp;
   const uint32_t gid32 = (uint32_t)gid;
+  const uint32_t par_next = pa.par ^ 1u;
 
   // ---- phase 0: fossil collection - commit log entries with time < GVT (pdes.cxx:816-871) -------
-  // The first PF tail entries and the newest entry's key are fetched together (independent loads
-  // in flight); the newest key decides the straggler test without another exposed round trip.
-  uint64_t new_t = 0, new_s = 0;
+  // The first PF tail entries are fetched together (independent loads in flight), the rare rest
+  // one by one.
   if (ln > 0) {
-    constexpr int PF = 2;
+    constexpr int PF = 4;
     uint64_t pt[PF], ps[PF];
 #pragma unroll
     for (int i = 0; i < PF; i++) {
@@ -382,29 +222,29 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
       pt[i] = ok ? lr->time : ~0ull;
       ps[i] = ok ? lr->sub : 0ull;
     }
-    {
-      uint32_t li = lt + ln - 1; if (li >= v.log_cap) li -= v.log_cap;
-      const LogRec *lr = &v.lg[(size_t)li * A + lp];
-      new_t = lr->time; new_s = lr->sub;
-    }
-    if (pt[0] < pa.gvt) {
-      uint64_t lct = v.lct[lp], lcs = v.lcs[lp];
-      int k = 0;
-#pragma unroll 1
-      while (ln > 0) {
-        uint64_t t, sb;
-        if (k < PF) { t = pt[0]; sb = ps[0]; pt[0] = pt[1]; ps[0] = ps[1]; }
-        else { const LogRec *lr = &v.lg[(size_t)lt * A + lp]; t = lr->time; sb = lr->sub; }
-        k++;
-        if (t >= pa.gvt) break;       // strict <, pdes.cxx:825
-        if (!key_less(lct, lcs, t + 1, sb)) acc.nondet = 1;   // pdes.cxx:828-831
-        lct = t + 1; lcs = sb;
-        lt = (lt + 1 == v.log_cap) ? 0 : lt + 1;
-        ln--;
-        acc.committed++;
+    uint64_t lct = v.lct[lp], lcs = v.lcs[lp];
+    bool any = false;
+    int k = 0;
+    while (ln > 0) {
+      uint64_t t, sb;
+      if (k < PF) {
+        t = pt[0]; sb = ps[0];
+#pragma unroll
+        for (int i = 0; i + 1 < PF; i++) { pt[i] = pt[i + 1]; ps[i] = ps[i + 1]; }
+      } else {
+        const LogRec *lr = &v.lg[(size_t)lt * A + lp];
+        t = lr->time; sb = lr->sub;
       }
-      v.lct[lp] = lct; v.lcs[lp] = lcs;
+      k++;
+      if (t >= pa.gvt) break;       // strict <, pdes.cxx:825
+      if (!key_less(lct, lcs, t + 1, sb)) acc.nondet = 1;   // pdes.cxx:828-831
+      lct = t + 1; lcs = sb;
+      lt = (lt + 1 == v.log_cap) ? 0 : lt + 1;
+      ln--;
+      acc.committed++;
+      any = true;
     }
+    if (any) { v.lct[lp] = lct; v.lcs[lp] = lcs; }
   }
   if (!active) {
     v.lmeta[lp] = ln | (lt << 16);
@@ -412,146 +252,220 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     return;
   }
 
-  // ---- phase 1: earliest records of the pool -----------------------------------------------------
-  // Every pending time is >= GVT, so a slot is summarised by one 32-bit key
-  //     key = min(time - GVT, KEY_FAR) << 6 | slot
-  // and the FOUR smallest keys come out of a branch-free min/max network (7 instructions per slot).
-  // m1..m4 stay in registers and feed up to DEVA_EV_PER_PASS executions in this launch.
-  // Times are loaded unconditionally (all pq_cap rows exist), 16 loads in flight.
-  constexpr uint32_t KEY_NONE = 0xffffffffu;          // empty / unknown
-  constexpr uint32_t KEY_FAR = (1u << 26) - 2u;       // saturated distance (exact value re-read when needed)
-  uint32_t m1 = KEY_NONE, m2 = KEY_NONE, m3 = KEY_NONE, m4 = KEY_NONE;
-  uint32_t dropped = KEY_NONE;   // smallest key that fell off the 4-entry list (lower bound of the unknown rest)
-  auto consider_key = [&](uint32_t k) {
-    const uint32_t a1 = k < m1 ? k : m1, b1 = k < m1 ? m1 : k;
-    const uint32_t a2 = b1 < m2 ? b1 : m2, b2 = b1 < m2 ? m2 : b1;
-    const uint32_t a3 = b2 < m3 ? b2 : m3, b3 = b2 < m3 ? m3 : b2;
-    const uint32_t a4 = b3 < m4 ? b3 : m4, b4 = b3 < m4 ? m4 : b3;
-    m1 = a1; m2 = a2; m3 = a3; m4 = a4;
-    dropped = b4 < dropped ? b4 : dropped;
+  uint64_t st[MAX_STW];
+#pragma unroll
+  for (int w = 0; w < M::STW; w++) st[w] = v.st[(size_t)w * A + lp];
+  uint64_t seq = v.seq[lp];
+
+  // ---- phase 1: fold pending slots + this window's arrivals -------------------------------------
+  // The pending pool is NOT compacted: slots whose event is taken become holes (bitmask `hole`),
+  // new pending records fill holes first, and only what is left of the holes is closed at the end
+  // by moving tail records down.  Records that stay are never rewritten.
+  WorkSet wk; wk.n = 0;
+  EvRec an[DEVA_AN_CAP]; int na = 0;
+  uint64_t hole = 0;            // bit s: slot s (< top) is free
+  uint32_t top = np;            // slots in use: [0, top) minus holes
+  uint64_t khead = ~0ull;       // min time over pending records (valid unless khead_dirty)
+  bool khead_dirty = false;
+  bool anti_overflow = false;   // an in-window anti-message stayed in the pool (an[] was full)
+
+  auto put_pending = [&](const EvRec &e) {
+    uint32_t s;
+    if (hole) { s = (uint32_t)ffs64(hole) - 1u; hole &= hole - 1; }
+    else {
+      if (top >= v.pq_cap) { acc.err |= ERR_PQ_OVERFLOW; return; }
+      s = top++;
+    }
+    pq_store(v, lp, s, e);
+    if (e.time < khead) khead = e.time;
   };
-  auto make_key = [&](uint64_t t, uint32_t s) -> uint32_t {
-    const uint64_t d = t - pa.gvt;
-    const uint32_t d32 = d >= (uint64_t)KEY_FAR ? KEY_FAR : (uint32_t)d;
-    return (d32 << 6) | s;
-  };
+  auto take_slot = [&](uint32_t s) { hole |= 1ull << s; };
+
+  // Stage A: every pending time of this LP in flight at once (8 B per slot, coalesced across the
+  // warp), reduced to a bitmask of the slots below the window bound.
+  uint64_t inwin = 0;
+  {
+    constexpr int CH = 16;
+    for (uint32_t base = 0; base < np; base += CH) {
+      uint64_t tt[CH];
 #pragma unroll
-  for (int i = 0; i < CH; i++) consider_key((uint32_t)i < np ? make_key(tt0[i], (uint32_t)i) : KEY_NONE);
-#pragma unroll 1
-  for (uint32_t base = CH; base < np; base += CH) {   // pools deeper than 16 records (rare)
-    uint64_t tt[CH];
-    const uint64_t *row = v.pq_t + (size_t)base * A + lp;
+      for (int i = 0; i < CH; i++) tt[i] = (base + i < np) ? v.pq_t[(size_t)(base + i) * A + lp] : ~0ull;
 #pragma unroll
-    for (int i = 0; i < CH; i++) tt[i] = (base + i < v.pq_cap) ? row[(size_t)i * A] : 0;
-#pragma unroll
-    for (int i = 0; i < CH; i++) consider_key(base + i < np ? make_key(tt[i], base + i) : KEY_NONE);
+      for (int i = 0; i < CH; i++) {
+        if (tt[i] < pa.ub) inwin |= 1ull << (base + i);      // (~0 for absent slots is never < ub)
+        else if (tt[i] < khead) khead = tt[i];
+      }
+    }
   }
-  uint32_t top = np;
-  if (ni > 0) {   // this window's arrivals (children and anti-messages from other LPs) join the pool
+  // Stage B: the records of the in-window slots, fetched four at a time (loads issued together).
+  auto fold_pool_record = [&](const EvRec &e, uint32_t s) {
+    if (e.flags & EV_ANTI) {
+      if (na < DEVA_AN_CAP) { an[na++] = e; take_slot(s); }
+      else { anti_overflow = true; if (e.time < khead) khead = e.time; }
+    } else {
+      EvRec out;
+      const int r = wk.insert(e, out, gid32);
+      if (r == 0) take_slot(s);
+      else if (r == 1) { pq_store(v, lp, s, out); if (out.time < khead) khead = out.time; }   // evicted one takes the slot
+      else if (e.time < khead) khead = e.time;                                                // rejected: stays
+    }
+  };
+  while (inwin) {
+    constexpr int RB = 4;
+    uint32_t ss[RB];
+    EvRec ee[RB];
+#pragma unroll
+    for (int i = 0; i < RB; i++) {
+      ss[i] = inwin ? (uint32_t)ffs64(inwin) - 1u : 0xffffffffu;
+      inwin &= inwin - 1;
+    }
+#pragma unroll
+    for (int i = 0; i < RB; i++)
+      if (ss[i] != 0xffffffffu) ee[i] = pq_load(v, lp, ss[i], v.pq_t[(size_t)ss[i] * A + lp], gid32);
+#pragma unroll
+    for (int i = 0; i < RB; i++)
+      if (ss[i] != 0xffffffffu) fold_pool_record(ee[i], ss[i]);
+  }
+  if (ni > 0) {
     if (ni > v.ib_cap) ni = v.ib_cap;
-#pragma unroll 1
+    auto fold_arrival = [&](const EvRec &e) {
+      if (e.flags & EV_ANTI) {
+        if (na < DEVA_AN_CAP) an[na++] = e; else { put_pending(e); anti_overflow |= e.time < pa.ub; }
+      } else if (e.time < pa.ub) {
+        EvRec out;
+        const int r = wk.insert(e, out, gid32);
+        if (r == 1) put_pending(out); else if (r == 2) put_pending(e);
+      } else put_pending(e);
+    };
     for (uint32_t base = 0; base < ni; base += 4) {
       EvRec ee[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) if (base + i < ni) ee[i] = ld_ev(&v.ib[pa.par][(size_t)(base + i) * A + lp]);
 #pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (base + i < ni) {
-          const uint32_t s = top;
-          if (ee[i].flags & EV_ANTI) has_anti = PC_ANTI;
-          if (pool_append(v, lp, top, ee[i], acc)) consider_key(make_key(ee[i].time, s));
-        }
+      for (int i = 0; i < 4; i++) if (base + i < ni) fold_arrival(ee[i]);
     }
     v.icnt[pa.par][lp] = 0;
   }
-  const uint64_t ubr = pa.ub > pa.gvt ? pa.ub - pa.gvt : 0;   // (the final sweep runs with ub = t_end <= GVT)
 
-  // Round trip 2: the records behind the three earliest keys, fetched together (one exposed
-  // latency for up to three executions instead of one each).
-  PqRest pr[3];
-  uint32_t pslot[3];
-  {
-    const uint32_t mk[3] = {m1, m2, m3};
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const bool want = mk[j] != KEY_NONE && (uint64_t)(mk[j] >> 6) < ubr;
-      pslot[j] = want ? (mk[j] & 63u) : 0xffffffffu;
-      if (want) pr[j] = ld_rest(&v.pq_r[(size_t)pslot[j] * A + lp]);
-      else { pr[j].sub = 0; pr[j].p0 = 0; pr[j].p1f = 0; }
+  // pool helpers for the rare paths (slot indices are stable: removal only sets a hole bit)
+  auto find_pending = [&](const EvRec &a, uint32_t want_anti) -> int {
+    for (uint32_t s = 0; s < top; s++) {
+      if ((hole >> s) & 1ull) continue;
+      if (v.pq_t[(size_t)s * A + lp] != a.time) continue;
+      const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
+      if (r.sub == a.sub && r.p0 == a.p0 && (r.p1f & ~P1_ANTI) == a.p1 && ((r.p1f & P1_ANTI) ? 1u : 0u) == want_anti) return (int)s;
     }
-  }
-  auto rest_of = [&](uint32_t slot) -> PqRest {   // prefetched copy if there is one, else memory
-    if (slot == pslot[0]) return pr[0];
-    if (slot == pslot[1]) return pr[1];
-    if (slot == pslot[2]) return pr[2];
-    return ld_rest(&v.pq_r[(size_t)slot * A + lp]);
+    return -1;
+  };
+  auto remove_pending = [&](const EvRec &a) -> bool {   // remove one POSITIVE identical to a
+    const int s = find_pending(a, 0u);
+    if (s < 0) return false;
+    take_slot((uint32_t)s);
+    khead_dirty = true;
+    return true;
   };
 
-  // ---- phase 2: execute the earliest records that lie in the window ------------------------------
-  // The list m1 <= m2 <= m3 <= m4 holds the true smallest keys of the pool (everything else is
-  // >= `dropped`), so while it is non-empty m1 IS the LP's next event.  The first event gets the
-  // full treatment (ties, anti-message at the head, straggler -> out-of-line slow paths); follow-up
-  // events run only in the plain case and otherwise wait for the next launch.
-  uint64_t head = ~0ull;
-  bool head_known = false;      // head was set by a slow path (the key list is stale)
-#ifndef DEVA_EV_PER_PASS
-#define DEVA_EV_PER_PASS 3
-#endif
-#pragma unroll 1
-  for (int it = 0; it < DEVA_EV_PER_PASS; it++) {
-    const uint32_t k1 = m1, d1 = k1 >> 6;
-    if (k1 == KEY_NONE || d1 == KEY_FAR || (uint64_t)d1 >= ubr) break;
-    const bool tie2 = (m2 >> 6) == d1, tie3 = (m3 >> 6) == d1 || (dropped >> 6) == d1;
-    if (it > 0 && (tie2 || tie3)) break;
-    EvRec e; e.time = pa.gvt + d1; e.sub = 0; e.p0 = 0; e.p1 = 0; e.dst = gid32; e.flags = 0;
-    uint32_t s_sel = k1 & 63u;
-    bool second_of_tie = false;   // the record at m2 (not m1) was chosen
-    bool ok = true;
-    int slow = 0;   // 1 = straggler (rollback only), 2 = full re-selection (anti-message at the head, 3-way tie)
-    if (tie3) slow = 2;
-    else {
-      PqRest r = rest_of(s_sel);
-      uint32_t antis = r.p1f & P1_ANTI;
-      if (tie2) {   // two records share the minimum time: the smaller subtime runs
-        const PqRest rb = rest_of(m2 & 63u);
-        antis |= rb.p1f & P1_ANTI;
-        if (rb.sub < r.sub) { r = rb; s_sel = m2 & 63u; second_of_tie = true; }
+  // ---- phase 2: annihilate anti-messages against not-yet-executed positives ----------------------
+  // (arrive_near<-1> with future_not_past, pdes.cxx:480-487)
+  uint64_t anti_t = ~0ull, anti_s = ~0ull;   // min key over antis whose positive already ran
+  int na_log = 0;
+  for (int i = 0; i < na; i++) {
+    if (wk.remove_match(an[i]) || remove_pending(an[i])) continue;
+    an[na_log++] = an[i];                    // positive is in the undo log: roll back through it
+    if (key_less(an[i].time, an[i].sub, anti_t, anti_s)) { anti_t = an[i].time; anti_s = an[i].sub; }
+  }
+  uint32_t n_pool_anti = 0;                  // in-window antis still in the pool whose positive already ran
+  if (anti_overflow) {
+    for (uint32_t s = 0; s < top; s++) {
+      if ((hole >> s) & 1ull) continue;
+      const uint64_t t = v.pq_t[(size_t)s * A + lp];
+      if (t >= pa.ub) continue;
+      const EvRec a = pq_load(v, lp, s, t, gid32);
+      if (!(a.flags & EV_ANTI)) continue;
+      if (wk.remove_match(a) || remove_pending(a)) { take_slot(s); khead_dirty = true; continue; }
+      n_pool_anti++;
+      if (key_less(a.time, a.sub, anti_t, anti_s)) { anti_t = a.time; anti_s = a.sub; }
+    }
+  }
+  auto recompute_anti_min = [&]() {
+    anti_t = ~0ull; anti_s = ~0ull;
+    for (int i = 0; i < na_log; i++)
+      if (key_less(an[i].time, an[i].sub, anti_t, anti_s)) { anti_t = an[i].time; anti_s = an[i].sub; }
+    if (n_pool_anti)
+      for (uint32_t s = 0; s < top; s++) {
+        if ((hole >> s) & 1ull) continue;
+        const uint64_t t = v.pq_t[(size_t)s * A + lp];
+        if (t >= pa.ub) continue;
+        const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
+        if ((r.p1f & P1_ANTI) && key_less(t, r.sub, anti_t, anti_s)) { anti_t = t; anti_s = r.sub; }
       }
-      e.sub = r.sub; e.p0 = r.p0; e.p1 = r.p1f & ~P1_ANTI;
-      if (antis) slow = 2;
-      else if (it == 0 && ln > 0 && key_less(e.time, e.sub, new_t, new_s)) slow = 1;   // lazy straggler detection, pdes.cxx:496-515
-    }
-    if (slow && it > 0) break;
-    uint64_t head_rest = ~0ull;
-    if (slow) {
-      // Out-of-line calls get COPIES of the hot variables (an address-taken variable would live in
-      // local memory for the whole kernel).
-      uint32_t top2 = top, ln2 = ln, s2 = s_sel;
-      uint64_t seq2 = seq, hr2 = ~0ull, st2[MAX_STW];
+  };
+
+  // ---- phase 3: straggler / anti-message rollback (insert_past, remove_past, rollback) -----------
+  if (ln > 0 && (wk.n > 0 || na_log > 0 || n_pool_anti > 0)) {
+    const uint64_t sg_t = wk.n > 0 ? wk.t[wk.n - 1] : ~0ull;   // smallest in-window key = straggler
+    const uint64_t sg_s = wk.n > 0 ? wk.s[wk.n - 1] : ~0ull;
+    while (ln > 0) {
+      uint32_t li = lt + ln - 1; if (li >= v.log_cap) li -= v.log_cap;
+      const LogRec *lrp = &v.lg[(size_t)li * A + lp];
+      const uint64_t lt_time = lrp->time, lt_sub = lrp->sub;
+      // undo while the newest processed event is later than the straggler, or not earlier than
+      // an anti-message's target (the target itself must be undone)
+      const bool undo = key_less(sg_t, sg_s, lt_time, lt_sub) ||
+                        ((na_log > 0 || n_pool_anti > 0) && !key_less(lt_time, lt_sub, anti_t, anti_s));
+      if (!undo) break;
+      if (lt_time < pa.gvt) acc.err |= ERR_BELOW_GVT;          // would undo a committable event
+      const LogRec lr = ld_log(lrp);
+      EvRec le; le.time = lr.time; le.sub = lr.sub; le.p0 = lr.p0; le.p1 = lr.fl & ~FL_SENT; le.dst = gid32; le.flags = 0;
 #pragma unroll
-      for (int w = 0; w < MAX_STW; w++) st2[w] = st[w];
-      Acc a2; a2.tmin = ~0ull; a2.executed = a2.committed = a2.rolled = a2.anti = a2.remote = a2.err = a2.nondet = 0;
-      EvRec e2 = e;
-      if (slow == 1) {   // undo everything later than the straggler; it stays the earliest record
-        // runner-up of the pool before the rollback: the other key of the pair (m1, m2)
-        const uint32_t kr = second_of_tie ? m1 : m2;
-        hr2 = kr == KEY_NONE ? ~0ull : pa.gvt + (kr >> 6);
-        bool sat = kr != KEY_NONE && (kr >> 6) == KEY_FAR;
-        uint64_t rq = ~0ull;
-        rollback<M>(v, mp, pa, lp, a2, top2, ln2, lt, st2, seq2, e.time, e.sub, nullptr, rq, s2);
-        if (rq < hr2) hr2 = rq;
-        if (sat) hr2 = 0;   // (saturated runner-up: exact head is re-read below)
-      } else ok = slow_select<M>(v, mp, pa, lp, a2, top2, ln2, lt, st2, seq2, e2, s2, hr2);
-      top = top2; ln = ln2; s_sel = s2; seq = seq2; head_rest = hr2; e = e2;
+      for (int w = 0; w < M::STW; w++) st[w] = lr.st[w];       // == reverse::unexecute
+      if (lr.fl & FL_SENT) {
+        // regenerate the child from the restored pre-state and cancel it
+        uint64_t tmp[MAX_STW];
 #pragma unroll
-      for (int w = 0; w < MAX_STW; w++) st[w] = st2[w];
-      if (a2.tmin < acc.tmin) acc.tmin = a2.tmin;
-      acc.rolled += a2.rolled; acc.anti += a2.anti; acc.remote += a2.remote; acc.err |= a2.err;
-      head_known = true;
-      head = ok ? (e.time < head_rest ? e.time : head_rest) : head_rest;
-      if (!ok) break;
+        for (int w = 0; w < M::STW; w++) tmp[w] = st[w];
+        EvRec c;
+        M::execute(mp, tmp, le, gid, c, true);
+        seq -= v.lp_n;                                         // pdes.cxx:566,574
+        if (!mp.user_subtime) c.sub = seq;
+        if ((uint64_t)c.dst == gid) {
+          if (!(wk.remove_match(c) || remove_pending(c))) acc.err |= ERR_SELF_CHILD_LOST;
+        } else {
+          c.flags = EV_ANTI;
+          deliver(v, par_next, c, acc);
+          acc.anti++;
+        }
+      }
+      // the undone event: annihilated if an anti-message names it, else back to pending
+      bool dead = false;
+      for (int i = 0; i < na_log; i++)
+        if (same_event(an[i], le)) { an[i] = an[na_log - 1]; na_log--; dead = true; break; }
+      if (!dead && n_pool_anti) {
+        const int q = find_pending(le, 1u);
+        if (q >= 0) { take_slot((uint32_t)q); khead_dirty = true; n_pool_anti--; dead = true; }
+      }
+      if (dead) {
+        recompute_anti_min();
+      } else {
+        EvRec out;
+        const int r = (le.time < pa.ub) ? wk.insert(le, out, gid32) : 2;
+        if (r == 1) put_pending(out); else if (r == 2) put_pending(le);
+      }
+      ln--;
+      acc.rolled++;
     }
-    if (ln == v.log_cap) break;   // undo log full: the event waits; GVT cannot pass it
+    if (na_log > 0 || n_pool_anti > 0) acc.err |= ERR_ANTI_UNMATCHED;
+  } else if (na_log > 0 || n_pool_anti > 0) acc.err |= ERR_ANTI_UNMATCHED;
+
+  // ---- phase 4: execute the working set in (time, subtime) order --------------------------------
+  while (wk.n > 0) {
+    if (ln == v.log_cap) {   // undo log full: leave the rest pending (they stay below GVT's reach)
+      for (int i = 0; i < wk.n; i++) put_pending(wk.get(i, gid32));
+      wk.n = 0;
+      break;
+    }
+    const EvRec e = wk.get(wk.n - 1, gid32);
+    wk.n--;
     uint32_t li = lt + ln; if (li >= v.log_cap) li -= v.log_cap;
     LogRec lr;
     lr.time = e.time; lr.sub = e.sub; lr.p0 = e.p0;
@@ -566,59 +480,38 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     if (sent) {
       if (!mp.user_subtime) c.sub = seq;   // event_subtime / next_seq_id, pdes.hxx:513-526,676
       seq += v.lp_n;
-    }
-    const bool self_child = sent && (uint64_t)c.dst == gid;
-    // the executed record leaves the key list
-    if (second_of_tie) { m2 = m3; m3 = m4; m4 = KEY_NONE; }
-    else { m1 = m2; m2 = m3; m3 = m4; m4 = KEY_NONE; }
-#pragma unroll
-    for (int j = 0; j < 3; j++) if (pslot[j] == s_sel || pslot[j] == top - 1) pslot[j] = 0xffffffffu;   // these slots change below
-    if (self_child) {            // self-sent child takes the slot of its parent, in place
-      pq_store(v, lp, s_sel, c);
-      if (!slow) consider_key(make_key(c.time, s_sel));
-      if (slow && c.time < head_rest) head_rest = c.time;
-    } else {
-      const uint32_t last = top - 1;
-      pool_remove(v, lp, top, s_sel);
-      if (!slow && s_sel != last) {   // the record that lived in slot `last` now lives in slot s_sel
-        if (m1 != KEY_NONE && (m1 & 63u) == last) m1 = (m1 & ~63u) | s_sel;
-        if (m2 != KEY_NONE && (m2 & 63u) == last) m2 = (m2 & ~63u) | s_sel;
-        if (m3 != KEY_NONE && (m3 & 63u) == last) m3 = (m3 & ~63u) | s_sel;
-        // (a changed slot field can leave two equal-time keys out of order; equal times are
-        //  resolved by reading both subtimes, so order between them does not matter)
+      if ((uint64_t)c.dst == gid) {
+        EvRec out;
+        const int r = (c.time < pa.ub) ? wk.insert(c, out, gid32) : 2;
+        if (r == 1) put_pending(out); else if (r == 2) put_pending(c);
+      } else {
+        deliver(v, par_next, c, acc);
       }
-      if (sent) deliver(v, pa.par ^ 1u, c, acc);
     }
-    if (slow) { head = head_rest; break; }   // the pool was reshuffled: the key list is stale
-  }
-  bool inexact = false;
-  if (!head_known) {
-    if (m1 != KEY_NONE) { head = pa.gvt + (m1 >> 6); inexact = (m1 >> 6) == KEY_FAR; }
-    else { head = ~0ull; inexact = dropped != KEY_NONE; }   // list exhausted but the pool holds more
-  } else inexact = head == 0;
-
-  if (pa.sweep && has_anti) {   // final pass of a drain: no anti-message may linger (rare, out of line)
-    sweep_annihilate(v, lp, top, acc);
-    has_anti = 0;
-    head = ~0ull;
-#pragma unroll 1
-    for (uint32_t s = 0; s < top; s++) { const uint64_t t = v.pq_t[(size_t)s * A + lp]; if (t < head) head = t; }
   }
 
-  if (inexact) {   // a saturated key took part: re-read the exact minimum (rare)
-    head = ~0ull;
-#pragma unroll 1
-    for (uint32_t s = 0; s < top; s++) { const uint64_t t = v.pq_t[(size_t)s * A + lp]; if (t < head) head = t; }
+  // ---- phase 5: close the remaining holes, write back --------------------------------------------
+  while (hole) {
+    while (top > 0 && ((hole >> (top - 1)) & 1ull)) { top--; hole &= ~(1ull << top); }   // free tail slots
+    if (!hole) break;
+    const uint32_t s = (uint32_t)ffs64(hole) - 1u;   // lowest hole, below top-1 which is in use
+    const uint32_t j = top - 1;
+    v.pq_t[(size_t)s * A + lp] = v.pq_t[(size_t)j * A + lp];
+    st_rest(&v.pq_r[(size_t)s * A + lp], ld_rest(&v.pq_r[(size_t)j * A + lp]));
+    hole &= ~(1ull << s);
+    top--;
   }
-
-  // ---- phase 3: write back -----------------------------------------------------------------------
+  if (khead_dirty) {
+    khead = ~0ull;
+    for (uint32_t s = 0; s < top; s++) { const uint64_t t = v.pq_t[(size_t)s * A + lp]; if (t < khead) khead = t; }
+  }
 #pragma unroll
   for (int w = 0; w < M::STW; w++) v.st[(size_t)w * A + lp] = st[w];
   v.seq[lp] = seq;
-  v.pcnt[lp] = top | has_anti;
-  v.head[lp] = head;
+  v.pcnt[lp] = top;
+  v.head[lp] = khead;
   v.lmeta[lp] = ln | (lt << 16);
-  if (head < acc.tmin) acc.tmin = head;
+  if (khead < acc.tmin) acc.tmin = khead;
 }
 
 // Between windows: put records (roots, inbox spill, records received from peer GPUs) into the
@@ -627,9 +520,8 @@ DEVA_HD void deliver_to_pending(const View &v, const EvRec &rec, uint32_t *err) 
   const uint64_t dl64 = (uint64_t)rec.dst - v.lp_begin;
   if (dl64 >= v.A) { atom_or_u32(err, ERR_NOT_OWNER); return; }
   const uint32_t dl = (uint32_t)dl64;
-  const uint32_t slot = atom_add_u32(&v.pcnt[dl], 1u) & ~PC_ANTI;
+  const uint32_t slot = atom_add_u32(&v.pcnt[dl], 1u);
   if (slot >= v.pq_cap) { atom_or_u32(err, ERR_PQ_OVERFLOW); return; }
-  if (rec.flags & EV_ANTI) atom_or_u32(&v.pcnt[dl], PC_ANTI);
   pq_store(v, dl, slot, rec);
   atom_min_u64(&v.head[dl], rec.time);
 }
@@ -687,7 +579,7 @@ DEVA_HD void digest_lp(const View &v, int stw, uint32_t lp, uint64_t out[4]) {
   const uint64_t gid = v.lp_begin + lp;
   out[0] ^= v.st[(size_t)(stw - 1) * v.A + lp];
   for (int w = 0; w < stw; w++) out[1] += mix64(v.st[(size_t)w * v.A + lp] ^ mix64(gid * 4 + w + 1));
-  const uint32_t np = v.pcnt[lp] & ~PC_ANTI;
+  const uint32_t np = v.pcnt[lp];
   out[2] += np;
   for (uint32_t s = 0; s < np; s++) {
     const EvRec e = pq_load(v, lp, s, v.pq_t[(size_t)s * v.A + lp], (uint32_t)gid);

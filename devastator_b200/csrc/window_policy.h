@@ -34,7 +34,7 @@ struct WindowPolicy {
   // global_status_state::update, pdes.cxx:233-280: efficiency bands decide the window.  On the GPU
   // a window costs one kernel launch whatever its width, and measured throughput is flat over a
   // wide range of widths as long as ~95 % or more of the executed events survive, so the policy
-  // holds efficiency in [0.95, 0.985]: quarter / halve-ish below, grow by 25 % above.
+  // holds efficiency in [0.965, 0.985]: quarter / halve-ish below, grow by 25 % above.
   void update(uint64_t exec_n, uint64_t rolled_n) {
     if (fixed) { w = fixed; return; }
     acc_exec += exec_n;
@@ -43,7 +43,7 @@ struct WindowPolicy {
     if (acc_exec) {
       const double eff = 1.0 - (double)acc_rolled / (double)acc_exec;
       if (eff < 0.80) w /= 2;
-      else if (eff < 0.95) w = w - w / 4;
+      else if (eff < 0.965) w = w - w / 4;
       else if (eff > 0.985) w = w + w / 4 + 1;
     }
     acc_exec = acc_rolled = 0;
