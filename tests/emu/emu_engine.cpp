@@ -302,4 +302,37 @@ int deva_b200_comm_unique_id(void *uid128) { memset(uid128, 0, 128); return 0; }
 int deva_b200_comm_init(deva_b200_engine *, const void *) { return 0; }
 void emu_set_shuffle(deva_b200_engine *e, uint64_t seed) { e->shuffle = seed; }
 
+// ---- stepping interface: one engine per PROCESS, exchange done by the caller (gloo test) ----------
+// Mirrors run_window()/drain() of engine.cu piece by piece so that a multi-process driver can put a
+// real transport between the pieces.
+uint64_t emu_local_min_head(deva_b200_engine *e) {
+  uint64_t m = ~0ull;
+  for (uint32_t lp = 0; lp < e->v.A; lp++) m = std::min<uint64_t>(m, e->v.head[lp]);
+  return m;
+}
+int emu_window_begin(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t sweep, uint64_t *wx, uint64_t *wr) {
+  e->gvt = gvt;
+  e->ctl.gvt_slot[0][0] = ~0ull;
+  PassArgs pa; pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep;
+  pass_one(e, pa, wx, wr);
+  if (e->ctl.spill_n > e->v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "spill overflow");
+  for (uint32_t i = 0; i < e->ctl.spill_n; i++) deliver_to_pending(e->v, e->v.spill[i], &e->ctl.err);
+  e->ctl.spill_n = 0;
+  return check_err(e);
+}
+uint32_t emu_send_count(deva_b200_engine *e, int g) { return e->ctl.send_n[g]; }
+void emu_copy_send(deva_b200_engine *e, int g, void *out) {   // records staged for peer g (32 B each)
+  memcpy(out, e->v.sendbuf + (size_t)g * e->v.send_cap, (size_t)e->ctl.send_n[g] * sizeof(EvRec));
+  e->ctl.send_n[g] = 0;
+}
+int emu_deliver(deva_b200_engine *e, const void *recs, uint32_t n) {
+  const EvRec *r = (const EvRec *)recs;
+  for (uint32_t i = 0; i < n; i++) deliver_to_pending(e->v, r[i], &e->ctl.err);
+  return check_err(e);
+}
+uint64_t emu_gvt_candidate(deva_b200_engine *e) { return e->ctl.gvt_slot[0][0]; }
+void emu_window_end(deva_b200_engine *e, uint64_t gvt) { e->gvt = gvt; e->par ^= 1u; }
+uint64_t emu_upper_bound(deva_b200_engine *e, uint64_t gvt, uint64_t t_end) { return e->wp.upper_bound(gvt, t_end); }
+void emu_policy_update(deva_b200_engine *e, uint64_t wx, uint64_t wr) { e->wp.update(wx, wr); }
+
 }  // extern "C"

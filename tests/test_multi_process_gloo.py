@@ -1,0 +1,132 @@
+"""World-size-2 test of the multi-GPU protocol with REAL processes and a real transport (gloo):
+each process owns one block of LPs in an emulated engine (tests/emu), and the per-window sequence of
+engine.cu's run_window() - execute pass, exchange the per-peer counts, exchange the staged records,
+deliver them, min-allreduce the GVT candidate, sum-allreduce the window statistics, lockstep window
+policy - is driven from Python with torch.distributed in place of NCCL.  Result must equal the oracle."""
+import ctypes as C
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+T_INF = 2**64 - 1
+
+
+def _bind(api):
+    L = api.lib
+    P = C.c_void_p
+    L.emu_local_min_head.argtypes = [P]; L.emu_local_min_head.restype = C.c_uint64
+    L.emu_window_begin.argtypes = [P, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.emu_send_count.argtypes = [P, C.c_int]; L.emu_send_count.restype = C.c_uint32
+    L.emu_copy_send.argtypes = [P, C.c_int, P]; L.emu_copy_send.restype = None
+    L.emu_deliver.argtypes = [P, P, C.c_uint32]
+    L.emu_gvt_candidate.argtypes = [P]; L.emu_gvt_candidate.restype = C.c_uint64
+    L.emu_window_end.argtypes = [P, C.c_uint64]; L.emu_window_end.restype = None
+    L.emu_upper_bound.argtypes = [P, C.c_uint64, C.c_uint64]; L.emu_upper_bound.restype = C.c_uint64
+    L.emu_policy_update.argtypes = [P, C.c_uint64, C.c_uint64]; L.emu_policy_update.restype = None
+
+
+def _u64_min(x):
+    # gloo has no uint64: order-preserving map to int64 by flipping the sign bit
+    t = torch.tensor([np.uint64(x ^ (1 << 63)).astype(np.int64)], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(np.int64(t.item()).astype(np.uint64)) ^ (1 << 63)
+
+
+def _sum(*xs):
+    t = torch.tensor(list(xs), dtype=torch.int64)
+    dist.all_reduce(t)
+    return [int(v) for v in t]
+
+
+def _window(api, eng, rank, world, gvt, ub, sweep):
+    wx, wr = C.c_uint64(), C.c_uint64()
+    api.check(api.lib.emu_window_begin(eng.h, gvt, ub, sweep, C.byref(wx), C.byref(wr)))
+    # 1. counts all-to-all
+    counts = torch.tensor([api.lib.emu_send_count(eng.h, g) for g in range(world)], dtype=torch.int64)
+    allc = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allc, counts)
+    # 2. payload exchange (pairwise send/recv), 3. deliver
+    for peer in range(world):
+        if peer == rank:
+            continue
+        ns, nr = int(counts[peer]), int(allc[peer][rank])
+        sbuf = torch.zeros(max(ns, 1) * 32, dtype=torch.uint8)
+        if ns:
+            api.lib.emu_copy_send(eng.h, peer, sbuf.data_ptr())
+        rbuf = torch.zeros(max(nr, 1) * 32, dtype=torch.uint8)
+        reqs = []
+        if rank < peer:
+            if ns: dist.send(sbuf[:ns * 32], peer)
+            if nr: dist.recv(rbuf[:nr * 32], peer)
+        else:
+            if nr: dist.recv(rbuf[:nr * 32], peer)
+            if ns: dist.send(sbuf[:ns * 32], peer)
+        if nr:
+            api.check(api.lib.emu_deliver(eng.h, rbuf.data_ptr(), nr))
+    # 4. GVT = min over ranks; window statistics summed (same window policy on every rank)
+    gvt_new = _u64_min(api.lib.emu_gvt_candidate(eng.h))
+    wxs, wrs = _sum(wx.value, wr.value)
+    api.lib.emu_window_end(eng.h, gvt_new)
+    return gvt_new, wxs, wrs
+
+
+def _worker(rank, world, port, cfg, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from devastator_b200 import engine as E
+    api = E.Api(C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libdeva_b200_emu.so")))
+    _bind(api)
+    A = cfg["A"]
+    per = (A + world - 1) // world
+    cnt = min(per, A - rank * per)
+    eng = E.Engine(E.MODEL_PHOLD_TEST, A, lp_begin=rank * per, lp_count=cnt, n_gpus=world, gpu_rank=rank, window=cfg["window"],
+                   p_remote=cfg["P"], lam=cfg["LAM"], end_time=cfg["END"], api=api)
+    eng.seed_phold(cfg["K"], 1, 1)
+    t_end = T_INF
+    gvt = _u64_min(api.lib.emu_local_min_head(eng.h))
+    windows = 0
+    while gvt < t_end:
+        ub = api.lib.emu_upper_bound(eng.h, gvt, t_end)
+        gvt, wx, wr = _window(api, eng, rank, world, gvt, ub, 0)
+        api.lib.emu_policy_update(eng.h, wx, wr)
+        windows += 1
+        assert windows < 100000
+    gvt, wx, _ = _window(api, eng, rank, world, gvt, t_end, 1)     # final sweep
+    assert wx == 0
+    st = torch.from_numpy(eng.get_state().astype(np.int64))
+    pad = torch.zeros((per, 3), dtype=torch.int64); pad[:cnt] = st
+    gathered = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(gathered, pad)
+    s = eng.stats()
+    tot = _sum(s["committed_n"], s["remote_sent_n"])
+    if rank == 0:
+        full = torch.cat(gathered)[:A].numpy().astype(np.uint64)
+        ret["state"] = full
+        ret["commits"], ret["crossed"], ret["gvt"], ret["windows"] = tot[0], tot[1], gvt, windows
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cfg", [dict(A=1000, K=16, P=0.5, LAM=100.0, END=300, window=20),
+                                 dict(A=1000, K=16, P=0.1, LAM=100.0, END=300, window=0)], ids=["p50-w20", "p10-adaptive"])
+def test_two_processes_gloo_equal_oracle(emu_api, cfg):
+    import oracle_lib as O
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, cfg, ret), nprocs=2, join=True)
+    o, ost = O.run(cfg["A"], cfg["K"], cfg["P"], cfg["LAM"], cfg["END"])
+    np.testing.assert_array_equal(ret["state"], ost)
+    assert ret["commits"] == o["commits"] and ret["gvt"] == o["gvt"]
+    assert ret["crossed"] > 0
