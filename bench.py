@@ -111,11 +111,14 @@ def ref_binary(threads=None):
     return None, 0
 
 
+REF_LEAD_IN = 200   # untimed lead-in [0, 200): the start-up transient (16 roots/LP inside [0,16)) is not steady state
+
+
 def run_reference_segments(n_seg, dt, timeout=900):
     exe, R = ref_binary()
     if not exe:
         return None
-    env = dict(os.environ, pdes_heartbeat="0", PHOLD_T_SEGMENTS=f"{n_seg}:{dt}", PHOLD_T_END=str(10**9))
+    env = dict(os.environ, pdes_heartbeat="0", PHOLD_T_SEGMENTS=f"{n_seg}:{dt}:{REF_LEAD_IN}", PHOLD_T_END=str(10**9))
     out = subprocess.run([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
     segs = []
     for line in out.stdout.splitlines():
@@ -135,7 +138,7 @@ def reference_arm(args):
     if rank != 0:
         return 0
     K, W = args.steps, args.warmup
-    per_step_s = min(20.0, max(1.0, 150.0 / (K + W)))
+    per_step_s = min(15.0, max(1.0, 120.0 / (K + W)))
     dt = max(2, int(round(per_step_s * 1.0e6 / (LP_PER_GPU * K_ROOTS / LAMBDA))))
     res = run_reference_segments(K + W, dt)
     if not res or len(res["segments"]) < K + W:
@@ -145,7 +148,7 @@ def reference_arm(args):
     commits = sum(s["commits"] for s in timed)
     secs = sum(s["drain_secs"] for s in timed)
     val = commits / secs
-    sample = (f"{K} timed drain(t_end) slices of {dt} sim-time units after {W} warm-up slices, 1M-LP PHOLD-T "
+    sample = (f"{K} timed drain(t_end) slices of {dt} sim-time units after an untimed lead-in [0,{REF_LEAD_IN}) and {W} warm-up slices, 1M-LP PHOLD-T "
               f"(single-GPU geometry; also used for N>1, where the larger LP count would only slow the CPU run)")
     line = {
         "impl": "reference", "metric": "committed events/sec (PHOLD-T)", "value": val, "unit": "events/s",
@@ -320,7 +323,7 @@ def measured_traffic():
 
 def cpu_baseline():
     """Bounded sample (about 10-30 s) of the same workload on the reference itself, host cores."""
-    dt = 12
+    dt = 40
     res = run_reference_segments(3, dt, timeout=600)
     if not res or len(res["segments"]) < 3:
         return {"value": None, "unit": "events/s", "cores": 0, "kind": "reference", "sample": "unavailable: oracle/_ref binary missing"}
@@ -329,7 +332,8 @@ def cpu_baseline():
     secs = sum(s["drain_secs"] for s in timed)
     return {"value": commits / secs, "unit": "events/s", "cores": res["ranks"], "kind": "reference",
             "sample": f"reference binary (oracle/_ref, {res['ranks']} rank threads of {os.cpu_count()} host CPUs): 2 timed drain(t_end) "
-                      f"slices of {dt} sim-time units ({commits} commits in {secs:.1f} s) after 1 warm-up slice, 1M-LP PHOLD-T"}
+                      f"slices of {dt} sim-time units ({commits} commits in {secs:.1f} s) after an untimed lead-in [0,{REF_LEAD_IN}) and "
+                      f"1 warm-up slice, 1M-LP PHOLD-T"}
 
 
 def main():

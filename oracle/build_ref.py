@@ -81,11 +81,13 @@ int main() {
   const char *drain_end_s = std::getenv("PHOLD_T_DRAIN_END");
   uint64_t drain_end = drain_end_s ? std::strtoull(drain_end_s, nullptr, 10) : ~uint64_t(0);
   g_dump = (uint64_t*)std::calloc(size_t(actor_n)*3, sizeof(uint64_t));
-  int seg_n = 0; uint64_t seg_dt = 0;
-  if(const char *sg = std::getenv("PHOLD_T_SEGMENTS")) {   // "n:dt"
+  int seg_n = 0; uint64_t seg_dt = 0, seg_t0 = 0;
+  if(const char *sg = std::getenv("PHOLD_T_SEGMENTS")) {   // "n:dt[:t0]"  n slices of dt after an untimed lead-in [0,t0)
     seg_n = std::atoi(sg);
     const char *c = std::strchr(sg, ':');
     seg_dt = c ? std::strtoull(c+1, nullptr, 10) : 1;
+    const char *c2 = c ? std::strchr(c+1, ':') : nullptr;
+    seg_t0 = c2 ? std::strtoull(c2+1, nullptr, 10) : 0;
   }
   auto doit = [&]() {
     pdes::chitter_secs = -1;
@@ -111,8 +113,12 @@ int main() {
       // segment mode (bench.py reference arm): setup once, then seg_n timed drain(t_end) slices of
       // seg_dt simulated-time units each; one JSON line per slice
       uint64_t commits_prev = 0;
+      if(seg_t0 > 0) {   // untimed lead-in: skips the start-up transient (all roots sit in [0,K))
+        pdes::drain(seg_t0, false);
+        commits_prev = deva::reduce_sum(pdes::local_stats()).committed_n;
+      }
       for(int sgi=0; sgi < seg_n; sgi++) {
-        uint64_t t_end_i = uint64_t(sgi+1)*seg_dt;
+        uint64_t t_end_i = seg_t0 + uint64_t(sgi+1)*seg_dt;
         deva::barrier();
         auto t0 = std::chrono::steady_clock::now();
         gvt = pdes::drain(t_end_i, false);
