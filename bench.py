@@ -257,12 +257,18 @@ def ours(args):
     h2d = st_host.numel() * 8 + sum(c.numel() * c.element_size() for c in cols)
     d2h = st_out.numel() * 8
 
+    st_np, st_out_np, cols_np = st_host.numpy(), st_out.numpy(), [c.numpy() for c in cols]
+    dbg = os.environ.get("DEVA_BENCH_DEBUG")
+
     def step_host():
-        eng.reset()
-        eng.set_state(st_host.numpy())
-        eng.root_events(*[c.numpy() for c in cols])
-        g = eng.drain()
-        eng.get_state(out=st_out.numpy())
+        t = [time.perf_counter()]
+        eng.reset(); t.append(time.perf_counter())
+        eng.set_state(st_np); t.append(time.perf_counter())
+        eng.root_events(*cols_np); t.append(time.perf_counter())
+        g = eng.drain(); t.append(time.perf_counter())
+        eng.get_state(out=st_out_np); t.append(time.perf_counter())
+        if dbg and rank == 0:
+            sys.stderr.write("e2e step ms reset/set_state/roots/drain/get_state: %s\n" % [round((b - a) * 1e3, 2) for a, b in zip(t, t[1:])])
         return g, eng.stats()
 
     e2e_steps = max(1, min(args.steps, 3))
