@@ -47,12 +47,15 @@ constexpr int PASS_THREADS = 128;
 // MINB = minimum resident blocks per SM the register allocator must allow (occupancy knob)
 template <class M, int MINB>
 __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const __grid_constant__ View v, const __grid_constant__ ModelParams mp,
-                                                             const __grid_constant__ PassArgs pa) {
-  const uint32_t lp = blockIdx.x * PASS_THREADS + threadIdx.x;
+                                                             const __grid_constant__ PassArgs pa, const uint32_t list_n) {
+  // list_n == 0: one thread per LP (the epoch's full pass).  list_n > 0: one thread per entry of the
+  // wake list written by the previous pass (follow-up pass: only LPs that received records).
+  const uint32_t i = blockIdx.x * PASS_THREADS + threadIdx.x;
   Acc acc;
-  acc.tmin = ~0ull;
+  acc.tmin = ~0ull; acc.stall = ~0ull;
   acc.executed = acc.committed = acc.rolled = acc.anti = acc.remote = acc.err = acc.nondet = 0;
-  if (lp < v.A) lp_pass<M>(v, mp, pa, lp, acc);
+  if (list_n == 0) { if (i < v.A) lp_pass<M>(v, mp, pa, i, acc); }
+  else if (i < list_n) lp_pass<M>(v, mp, pa, v.wake[pa.par][i], acc);
 
   // warp reduction (no block barrier: a finished warp leaves at once), then one RED per quantity
   // into a counter slot picked by the block index
@@ -84,12 +87,12 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const __grid_consta
 }
 
 // records -> pending slots (roots, inbox spill, records received from peer GPUs)
-__global__ void k_deliver(View v, const EvRec *recs, const uint32_t *n_ptr, uint32_t n_fixed) {
+__global__ void k_deliver(View v, const EvRec *recs, const uint32_t *n_ptr, uint32_t n_fixed, PassArgs pa) {
   const uint32_t n = n_ptr ? *n_ptr : n_fixed;
   unsigned long long tmin = ~0ull;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const EvRec r = ld_ev(&recs[i]);
-    deliver_to_pending(v, r, &v.ctl->err);
+    deliver_between_passes(v, r, pa, &v.ctl->err);
     tmin = r.time < tmin ? r.time : tmin;
   }
   // delivered records are pending: they bound the GVT (matters for roots; spill / peer records
@@ -240,6 +243,7 @@ struct deva_b200_engine {
   unsigned long long *d_red = nullptr;  // allreduce scratch
   bool profile = true;
   int pass_variant = 6;   // k_pass<M, MINB> instantiation (DEVA_B200_PASS_MINB = 4 | 6 | 8)
+  uint32_t pass_tag = 0;  // serial number of the last pass (wake-list dedup tag)
 };
 
 template <class T>
@@ -325,6 +329,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   DA(v.st, A * e->stw) DA(v.seq, A) DA(v.lct, A) DA(v.lcs, A)
   DA(v.pq_t, A * v.pq_cap) DA(v.pq_r, A * v.pq_cap) DA(v.ib[0], A * v.ib_cap) DA(v.ib[1], A * v.ib_cap) DA(v.lg, A * v.log_cap)
   DA(v.ctl, 1)
+  DA(v.wake[0], A) DA(v.wake[1], A) DA(v.wmark, A)
   v.spill_cap = (uint32_t)std::min<size_t>(std::max<size_t>(A * 2, 1u << 16), 1u << 26);
   DA(v.spill, v.spill_cap)
   DA(e->d_digest, 4)
@@ -334,7 +339,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
     DA(v.sendbuf, (size_t)v.send_cap * cfg->n_gpus)
     DA(e->recvbuf, (size_t)v.send_cap * cfg->n_gpus)
     DA(e->d_counts, 2 * MAX_GPUS)
-    DA(e->d_red, 8)
+    DA(e->d_red, 16)
     CU(cudaHostAlloc((void **)&e->h_counts, 2 * MAX_GPUS * sizeof(uint32_t), cudaHostAllocDefault));
   }
 #undef DA
@@ -345,6 +350,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   CU(cudaEventCreate(&e->ev_d1));
   CU(cudaHostAlloc((void **)&e->h_ctl, sizeof(Ctl), cudaHostAllocDefault));
   CU(cudaMemsetAsync(v.ctl, 0, sizeof(Ctl), e->stream));
+  CU(cudaMemsetAsync(v.wmark, 0, A * sizeof(uint32_t), e->stream));
   const int grid = (int)((A + 255) / 256);
   dispatch_model(cfg->model, [&](auto m) {
     using M = decltype(m);
@@ -505,7 +511,7 @@ int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) {
 
 // ---- multi-GPU exchange: counts all-to-all, then payload all-to-all (grouped send/recv), then
 //      deliver what arrived into pending slots.  Replaces threads::send / world_gasnet send_remote.
-static int exchange(deva_b200_engine *e) {
+static int exchange(deva_b200_engine *e, const PassArgs &pa) {
   const int G = e->cfg.n_gpus, me = e->cfg.gpu_rank;
   View &v = e->v;
   // 1. counts: every rank sends its send_n[g] to g
@@ -537,7 +543,7 @@ static int exchange(deva_b200_engine *e) {
       const uint32_t nr = e->h_counts[MAX_GPUS + g];
       if (!nr) continue;
       const unsigned grid = (unsigned)std::min<uint32_t>((nr + 255) / 256, 148 * 8);
-      k_deliver<<<grid, 256, 0, e->stream>>>(v, e->recvbuf + (size_t)g * v.send_cap, nullptr, nr);
+      k_deliver<<<grid, 256, 0, e->stream>>>(v, e->recvbuf + (size_t)g * v.send_cap, nullptr, nr, pa);
       e->launches++;
     }
     CU(cudaGetLastError());
@@ -546,29 +552,29 @@ static int exchange(deva_b200_engine *e) {
   return 0;
 }
 
-// GVT = min over GPUs (ncclMin allreduce; replaces gvt.cxx rdxn_up/rdxn_down); the same call sums
-// the per-window executed / rolled-back counts for the window policy.
-static int allreduce_gvt(deva_b200_engine *e, uint64_t *gvt, uint64_t *exec_sum, uint64_t *rolled_sum, uint32_t *err_or) {
-  unsigned long long h[4] = {*gvt, *exec_sum, *rolled_sum, *err_or};
+// One small allreduce set per pass (replaces gvt.cxx rdxn_up/rdxn_down): min of the GVT candidate,
+// sums of executed / rolled-back / woken-LP counts (window policy, epoch completion), max of errors.
+static int allreduce_pass(deva_b200_engine *e, uint64_t *gvt, uint64_t *exec_sum, uint64_t *rolled_sum, uint64_t *woken_sum, uint32_t *err_or) {
+  unsigned long long h[5] = {*gvt, *exec_sum, *rolled_sum, *woken_sum, *err_or};
   CU(cudaMemcpyAsync(e->d_red, h, sizeof h, cudaMemcpyHostToDevice, e->stream));
-  NC(g_nccl.AllReduce(e->d_red, e->d_red + 4, 1, NC_U64, NC_MIN, e->comm, e->stream));
-  NC(g_nccl.AllReduce(e->d_red + 1, e->d_red + 5, 2, NC_U64, NC_SUM, e->comm, e->stream));
-  NC(g_nccl.AllReduce(e->d_red + 3, e->d_red + 7, 1, NC_U64, NC_MAX, e->comm, e->stream));
-  CU(cudaMemcpyAsync(h, e->d_red + 4, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+  NC(g_nccl.AllReduce(e->d_red, e->d_red + 8, 1, NC_U64, NC_MIN, e->comm, e->stream));
+  NC(g_nccl.AllReduce(e->d_red + 1, e->d_red + 9, 3, NC_U64, NC_SUM, e->comm, e->stream));
+  NC(g_nccl.AllReduce(e->d_red + 4, e->d_red + 12, 1, NC_U64, NC_MAX, e->comm, e->stream));
+  CU(cudaMemcpyAsync(h, e->d_red + 8, sizeof h, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
-  *gvt = h[0]; *exec_sum = h[1]; *rolled_sum = h[2]; *err_or = (uint32_t)h[3];
+  *gvt = h[0]; *exec_sum = h[1]; *rolled_sum = h[2]; *woken_sum = h[3]; *err_or = (uint32_t)h[4];
   return 0;
 }
 
-static int launch_pass(deva_b200_engine *e, const PassArgs &pa) {
-  const int grid = (int)((e->v.A + PASS_THREADS - 1) / PASS_THREADS);
+static int launch_pass(deva_b200_engine *e, const PassArgs &pa, uint32_t list_n) {
+  const int grid = (int)(((list_n ? list_n : e->v.A) + PASS_THREADS - 1) / PASS_THREADS);
   if (e->profile) CU(cudaEventRecord(e->ev_a, e->stream));
   dispatch_model(e->cfg.model, [&](auto m) {
     using M = decltype(m);
     switch (e->pass_variant) {
-      case 4: k_pass<M, 4><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa); break;
-      case 8: k_pass<M, 8><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa); break;
-      default: k_pass<M, 6><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa); break;
+      case 4: k_pass<M, 4><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa, list_n); break;
+      case 8: k_pass<M, 8><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa, list_n); break;
+      default: k_pass<M, 6><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa, list_n); break;
     }
     return 0;
   });
@@ -578,42 +584,66 @@ static int launch_pass(deva_b200_engine *e, const PassArgs &pa) {
   return 0;
 }
 
-// one window: execute kernel, spill delivery, peer exchange, GVT.  Updates e->gvt.
-static int run_window(deva_b200_engine *e, uint64_t ub, uint32_t sweep, uint64_t *win_exec, uint64_t *win_rolled) {
+// One pass of an epoch: the execute kernel over all LPs (full = true) or over the wake list the
+// previous pass wrote, then spill delivery and the peer exchange.  Returns the number of LPs woken
+// for the next follow-up pass (summed over GPUs).
+static int run_pass(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t sweep, bool full,
+                    uint64_t *p_exec, uint64_t *p_rolled, uint64_t *p_woken) {
   View &v = e->v;
-  // reset the GVT accumulator (0xff.. == ~0ull)
-  CU(cudaMemsetAsync(v.ctl->gvt_slot, 0xff, sizeof(v.ctl->gvt_slot), e->stream));
   PassArgs pa;
-  pa.gvt = e->gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep;
-  int rc = launch_pass(e, pa);
-  if (rc) return rc;
+  pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa._pad = 0;
+  const uint32_t list_n = full ? 0u : e->h_ctl->wake_n[e->par];
+  CU(cudaMemsetAsync(v.ctl->gvt_slot, 0xff, sizeof(v.ctl->gvt_slot), e->stream));
+  CU(cudaMemsetAsync(&v.ctl->wake_n[e->par ^ 1u], 0, sizeof(uint32_t), e->stream));   // the list this pass writes
+  int rc = 0;
   const CtlSum before = e->sum;
-  if ((rc = read_ctl(e))) return rc;
-  if (e->profile) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->exec_ms += ms; }
-  e->passes++;
-  if (e->h_ctl->spill_n) {   // rare: some LP's inbox overflowed this window
+  if (full || list_n > 0) {
+    if ((rc = launch_pass(e, pa, list_n))) return rc;
+    if ((rc = read_ctl(e))) return rc;
+    if (e->profile) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->exec_ms += ms; }
+    e->passes++;
+  } else if ((rc = read_ctl(e))) return rc;
+  if (e->h_ctl->spill_n) {   // rare: some LP's inbox overflowed this pass
     if (e->h_ctl->spill_n > v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "inbox spill buffer overflowed (raise inbox_cap)");
     const unsigned grid = (unsigned)std::min<uint32_t>((e->h_ctl->spill_n + 255) / 256, 148 * 8);
-    k_deliver<<<grid, 256, 0, e->stream>>>(v, v.spill, nullptr, e->h_ctl->spill_n);
+    k_deliver<<<grid, 256, 0, e->stream>>>(v, v.spill, nullptr, e->h_ctl->spill_n, pa);
     e->launches++;
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(&v.ctl->spill_n, 0, sizeof(uint32_t), e->stream));
     if ((rc = read_ctl(e))) return rc;
   }
-  uint64_t gvt = e->sum.gvt_next;
   uint64_t wx = e->sum.executed - before.executed, wr = e->sum.rolled_back - before.rolled_back;
-  uint32_t err = e->sum.err;
+  uint64_t woken = e->h_ctl->wake_n[e->par ^ 1u];
   if (e->cfg.n_gpus > 1) {
-    if ((rc = exchange(e))) return rc;
-    if ((rc = read_ctl(e))) return rc;       // k_deliver may have raised a capacity error
-    err = e->sum.err;
-    if ((rc = allreduce_gvt(e, &gvt, &wx, &wr, &err))) return rc;
+    if ((rc = exchange(e, pa))) return rc;
+    if ((rc = read_ctl(e))) return rc;       // records from peers may have woken LPs / raised a capacity error
+    woken = e->h_ctl->wake_n[e->par ^ 1u];
+    uint32_t err = e->sum.err;
+    uint64_t g = ~0ull;
+    if ((rc = allreduce_pass(e, &g, &wx, &wr, &woken, &err))) return rc;
     e->sum.err = err;
   }
   if ((rc = check_ctl_err(e))) return rc;
-  e->gvt = gvt;
   e->par ^= 1u;
-  *win_exec = wx; *win_rolled = wr;
+  *p_exec = wx; *p_rolled = wr; *p_woken = woken;
+  return 0;
+}
+
+// exact GVT: min over the LP heads (all inboxes are empty between epochs), min over GPUs
+static int exact_gvt(deva_b200_engine *e, uint64_t *out) {
+  int rc;
+  CU(cudaMemsetAsync(e->v.ctl->gvt_slot, 0xff, sizeof(e->v.ctl->gvt_slot), e->stream));
+  k_min_head<<<148 * 4, 256, 0, e->stream>>>(e->v);
+  e->launches++;
+  CU(cudaGetLastError());
+  if ((rc = read_ctl(e))) return rc;
+  if ((rc = check_ctl_err(e))) return rc;
+  uint64_t gvt = e->sum.gvt_next;
+  if (e->cfg.n_gpus > 1) {
+    uint64_t a = 0, b = 0, c = 0; uint32_t er = 0;
+    if ((rc = allreduce_pass(e, &gvt, &a, &b, &c, &er))) return rc;
+  }
+  *out = gvt;
   return 0;
 }
 
@@ -645,40 +675,43 @@ int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uin
     e->has_rewind = true;
   }
   // initial GVT = min over LP heads (pdes.cxx:755-759: reduce_min(lvt))
-  CU(cudaMemsetAsync(v.ctl->gvt_slot, 0xff, sizeof(v.ctl->gvt_slot), e->stream));
-  k_min_head<<<148 * 4, 256, 0, e->stream>>>(v);
-  e->launches++;
-  CU(cudaGetLastError());
-  if ((rc = read_ctl(e))) return rc;
-  if ((rc = check_ctl_err(e))) return rc;
-  uint64_t gvt = e->sum.gvt_next;
-  if (e->cfg.n_gpus > 1) {
-    uint64_t a = 0, b = 0; uint32_t er = 0;
-    if ((rc = allreduce_gvt(e, &gvt, &a, &b, &er))) return rc;
-  }
+  uint64_t gvt = 0;
+  if ((rc = exact_gvt(e, &gvt))) return rc;
   e->gvt = gvt;
   if (rewindable) e->snap_gvt = gvt;
   e->wp.begin_drain();
   uint64_t stall = 0;
+  // Epochs.  Window [GVT, ub): one full pass over all LPs, then follow-up passes over only the LPs
+  // that received records in the previous pass (stragglers, anti-messages, children that landed
+  // inside the window), until no LP is woken.  Then nothing below ub is left unprocessed, the exact
+  // GVT is one min-reduction over the LP heads, and the next epoch starts at a fresh window: every
+  // stretch of simulated time is scanned by ONE full pass instead of ~3 overlapping ones.
   while (e->gvt < t_end) {
     const uint64_t ub = e->wp.upper_bound(e->gvt, t_end);
     const uint64_t gvt_before = e->gvt;
-    uint64_t wx = 0, wr = 0;
-    if ((rc = run_window(e, ub, 0, &wx, &wr))) return rc;
-    e->wp.update(wx, wr);
-    // progress guard: GVT frozen and nothing executed for many windows == the undo log cannot
+    uint64_t ex = 0, rb = 0, woken = 0, px = 0, pr = 0;
+    if ((rc = run_pass(e, e->gvt, ub, 0, true, &px, &pr, &woken))) return rc;
+    ex += px; rb += pr;
+    int guard = 0;
+    while (woken > 0) {
+      if ((rc = run_pass(e, e->gvt, ub, 0, false, &px, &pr, &woken))) return rc;
+      ex += px; rb += pr;
+      if (++guard > 100000) return fail(DEVA_B200_ERR_INVARIANT, "epoch does not converge");
+    }
+    if ((rc = exact_gvt(e, &gvt))) return rc;
+    e->gvt = gvt;
+    e->wp.update(ex, rb);
+    // progress guard: GVT frozen and nothing executed for many epochs == the undo log cannot
     // drain (more same-time events at one LP than log_cap)
-    if (e->gvt == gvt_before && wx == 0) { if (++stall > 64) return fail(DEVA_B200_ERR_CAPACITY, "no progress: raise log_cap"); }
+    if (e->gvt == gvt_before && ex == 0) { if (++stall > 64) return fail(DEVA_B200_ERR_CAPACITY, "no progress: raise log_cap"); }
     else stall = 0;
   }
-  // final sweep: every LP fossil-collects below GVT (>= t_end) and folds its inbox, so that no
-  // processed-uncommitted event and no in-flight arrival is left (pdes.cxx:1020-1023 asserts)
+  // final sweep: every LP fossil-collects below GVT (>= t_end), so that no processed-uncommitted
+  // event is left (pdes.cxx:1020-1023 asserts); inboxes are already empty (last epoch converged)
   {
-    uint64_t wx = 0, wr = 0;
-    if ((rc = run_window(e, t_end, 1, &wx, &wr))) return rc;
-    if (wx != 0) return fail(DEVA_B200_ERR_INVARIANT, "events executed during the final sweep");
-    // (the other inbox parity is already empty: every LP that had arrivals there was active in
-    //  the last regular window and zeroed its counter)
+    uint64_t wx = 0, wr = 0, woken = 0;
+    if ((rc = run_pass(e, e->gvt, t_end, 1, true, &wx, &wr, &woken))) return rc;
+    if (wx != 0 || woken != 0) return fail(DEVA_B200_ERR_INVARIANT, "events executed during the final sweep");
   }
   CU(cudaEventRecord(e->ev_d1, e->stream));
   CU(cudaEventSynchronize(e->ev_d1));

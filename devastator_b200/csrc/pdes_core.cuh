@@ -41,6 +41,7 @@ namespace deva_b200 {
 DEVA_HD uint32_t atom_add_u32(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 DEVA_HD void atom_or_u32(uint32_t *p, uint32_t v) { atomicOr(p, v); }
 DEVA_HD void atom_min_u64(uint64_t *p, uint64_t v) { atomicMin((unsigned long long *)p, (unsigned long long)v); }
+DEVA_HD uint32_t atom_exch_u32(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
 DEVA_HD EvRec ld_ev(const EvRec *p) {
   const uint4 a = reinterpret_cast<const uint4 *>(p)[0];
   const uint4 b = reinterpret_cast<const uint4 *>(p)[1];
@@ -90,6 +91,7 @@ __device__ __forceinline__ uint32_t agg_claim(uint32_t *ctr, uint32_t key) {
 DEVA_HD uint32_t atom_add_u32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 DEVA_HD void atom_or_u32(uint32_t *p, uint32_t v) { *p |= v; }
 DEVA_HD void atom_min_u64(uint64_t *p, uint64_t v) { if (v < *p) *p = v; }
+DEVA_HD uint32_t atom_exch_u32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
 DEVA_HD EvRec ld_ev(const EvRec *p) { return *p; }
 DEVA_HD void st_ev(EvRec *p, const EvRec &e) { *p = e; }
 DEVA_HD PqRest ld_rest(const PqRest *p) { return *p; }
@@ -112,6 +114,7 @@ constexpr uint32_t FL_SENT = 0x80000000u;   // LogRec::fl "sent a child" bit
 // per-thread accumulators, block-reduced by the kernel wrapper
 struct Acc {
   uint64_t tmin;     // min time over everything this thread leaves pending or emits (-> next GVT)
+  uint64_t stall;    // min time of an in-window event this thread could not run (working set / undo log full)
   uint32_t executed, committed, rolled, anti, remote, err, nondet;
 };
 
@@ -166,6 +169,10 @@ DEVA_HD void deliver(const View &v, uint32_t par_next, const EvRec &rec, Acc &ac
     const uint32_t dl = (uint32_t)(rec.dst - v.lp_begin);
     if (dl >= v.A) { acc.err |= ERR_NOT_OWNER; return; }
     const uint32_t slot = atom_add_u32(&v.icnt[par_next][dl], 1u);
+    if (slot == 0) {   // first arrival of this pass: the LP joins the follow-up pass's wake list (once)
+      const uint32_t k = agg_claim(&v.ctl->wake_n[par_next], 0xffu);
+      v.wake[par_next][k] = dl;
+    }
     if (slot < v.ib_cap) {
       st_ev(&v.ib[par_next][(size_t)slot * v.A + dl], rec);
     } else {  // inbox full: spill; delivered into the LP's pending slots between windows
@@ -207,6 +214,31 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   const uint64_t gid = v.lp_begin + lp;
   const uint32_t gid32 = (uint32_t)gid;
   const uint32_t par_next = pa.par ^ 1u;
+
+  // ---- fold-only path: the LP was woken by arrivals that all lie beyond the window (the common
+  // case in a follow-up pass): move them to the pool, lower the head, touch nothing else.
+  if (ni > v.ib_cap) ni = v.ib_cap;   // (arrivals beyond the inbox capacity went to the spill buffer)
+  if (head0 >= pa.ub && ni > 0 && ni <= 4 && !pa.sweep && np + ni <= v.pq_cap) {
+    EvRec ee[4];
+    bool plain = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if ((uint32_t)i < ni) {
+        ee[i] = ld_ev(&v.ib[pa.par][(size_t)i * A + lp]);
+        plain &= ee[i].time >= pa.ub && !(ee[i].flags & EV_ANTI);
+      }
+    if (plain) {
+      uint64_t h = head0;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if ((uint32_t)i < ni) { pq_store(v, lp, np + i, ee[i]); if (ee[i].time < h) h = ee[i].time; }
+      v.icnt[pa.par][lp] = 0;
+      v.pcnt[lp] = np + ni;
+      v.head[lp] = h;
+      if (h < acc.tmin) acc.tmin = h;
+      return;
+    }
+  }
 
   // ---- phase 0: fossil collection - commit log entries with time < GVT (pdes.cxx:816-871) -------
   // The first PF tail entries are fetched together (independent loads in flight), the rare rest
@@ -512,6 +544,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   v.head[lp] = khead;
   v.lmeta[lp] = ln | (lt << 16);
   if (khead < acc.tmin) acc.tmin = khead;
+  if (khead < pa.ub && khead < acc.stall) acc.stall = khead;   // an in-window record could not run (capacity)
 }
 
 // Between windows: put records (roots, inbox spill, records received from peer GPUs) into the
@@ -524,6 +557,22 @@ DEVA_HD void deliver_to_pending(const View &v, const EvRec &rec, uint32_t *err) 
   if (slot >= v.pq_cap) { atom_or_u32(err, ERR_PQ_OVERFLOW); return; }
   pq_store(v, dl, slot, rec);
   atom_min_u64(&v.head[dl], rec.time);
+}
+
+// deliver_to_pending + wake: a record that lands below the window bound between passes (inbox spill,
+// record from a peer GPU) must be looked at in this epoch, so its LP joins the follow-up pass's wake
+// list - unless an inbox arrival already put it there (icnt > 0) or another record of this batch did.
+DEVA_HD void deliver_between_passes(const View &v, const EvRec &rec, const PassArgs &pa, uint32_t *err) {
+  deliver_to_pending(v, rec, err);
+  if (rec.time < pa.ub) {
+    const uint32_t par_next = pa.par ^ 1u;
+    const uint64_t dl64 = (uint64_t)rec.dst - v.lp_begin;
+    if (dl64 < v.A) {
+      const uint32_t dl = (uint32_t)dl64;
+      if (v.icnt[par_next][dl] == 0 && atom_exch_u32(&v.wmark[dl], pa.tag) != pa.tag)
+        v.wake[par_next][atom_add_u32(&v.ctl->wake_n[par_next], 1u)] = dl;
+    }
+  }
 }
 
 // ---- setup / digest helpers shared by the kernels and the host emulation -------------------------

@@ -79,7 +79,8 @@ struct Ctl {
   uint32_t err;                   // errors raised by the between-window kernels
   uint32_t spill_n;               // records in the spill buffer (inbox overflow)
   uint32_t send_n[MAX_GPUS];      // records staged for each peer GPU
-  uint32_t _pad[2];
+  uint32_t wake_n[2];             // LPs woken for the next / current follow-up pass (double-buffered)
+  unsigned long long stall_min;   // min time of an in-window event that could not run (capacity): bounds the next epoch
 };
 
 struct View {
@@ -105,6 +106,9 @@ struct View {
   uint32_t send_cap;
   int32_t n_gpus, gpu_rank;
   uint64_t lp_per_gpu;   // block partition: owner(lp) = lp / lp_per_gpu
+  // wake lists: LPs that received a record during a pass are the only ones the follow-up pass visits
+  uint32_t *wake[2];
+  uint32_t *wmark;       // per-LP tag of the last pass that woke it (dedup for records delivered between passes)
 };
 
 struct PassArgs {
@@ -112,6 +116,8 @@ struct PassArgs {
   uint64_t ub;       // execute events with time < ub  (= min(gvt + window, t_end))
   uint32_t par;      // inbox parity read this window (arrivals are written to par^1)
   uint32_t sweep;    // final pass of a drain: every LP fossil-collects and folds its inbox
+  uint32_t tag;      // pass serial number (wake-list dedup)
+  uint32_t _pad;
 };
 
 }  // namespace deva_b200

@@ -12,8 +12,7 @@
 namespace deva_b200 {
 
 struct WindowPolicy {
-  static constexpr int PERIOD = 4;   // windows per decision: a rollback is charged to a LATER window
-                                     // than the execution it undoes, so single windows are noisy
+  static constexpr int PERIOD = 2;   // epochs per decision (update() is called once per epoch with its sums)
   uint64_t fixed = 0;
   uint64_t w = 1;
   uint64_t acc_exec = 0, acc_rolled = 0;

@@ -46,6 +46,7 @@ struct deva_b200_engine {
   std::vector<std::vector<char>> snap;
   uint64_t snap_gvt = 0;
   uint64_t shuffle = 1;   // LP visiting order seed
+  uint32_t pass_tag = 0;
   std::vector<EvRec> recv;
 };
 
@@ -108,6 +109,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   halloc(e, &v.lmeta, A); halloc(e, &v.st, A * e->stw); halloc(e, &v.seq, A); halloc(e, &v.lct, A); halloc(e, &v.lcs, A);
   halloc(e, &v.pq_t, A * v.pq_cap); halloc(e, &v.pq_r, A * v.pq_cap); halloc(e, &v.ib[0], A * v.ib_cap); halloc(e, &v.ib[1], A * v.ib_cap);
   halloc(e, &v.lg, A * v.log_cap);
+  halloc(e, &v.wake[0], A); halloc(e, &v.wake[1], A); halloc(e, &v.wmark, A);
   v.ctl = &e->ctl;
   v.spill_cap = (uint32_t)std::max<size_t>(A * 2, 1u << 12);
   halloc(e, &v.spill, v.spill_cap);
@@ -172,18 +174,21 @@ int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) { e->mp.stop = stop; r
 int deva_b200_reset(deva_b200_engine *e) { init_lps(e, 0); e->par = 0; e->has_rewind = false; return 0; }
 
 // ---- lockstep multi-engine driver (stands in for one process per GPU + NCCL) ---------------------
-static void pass_one(deva_b200_engine *e, const PassArgs &pa, uint64_t *wx, uint64_t *wr) {
+static void pass_one(deva_b200_engine *e, const PassArgs &pa, bool full, uint64_t *wx, uint64_t *wr) {
   View &v = e->v;
-  std::vector<uint32_t> order(v.A);
-  for (uint32_t i = 0; i < v.A; i++) order[i] = i;
-  if (e->shuffle) {   // xorshift Fisher-Yates
+  // visiting order: all LPs, or the wake list the previous pass wrote - shuffled either way
+  std::vector<uint32_t> order;
+  if (full) { order.resize(v.A); for (uint32_t i = 0; i < v.A; i++) order[i] = i; }
+  else order.assign(v.wake[pa.par], v.wake[pa.par] + e->ctl.wake_n[pa.par]);
+  if (e->shuffle && order.size() > 1) {   // xorshift Fisher-Yates
     uint64_t s = e->shuffle * 0x9E3779B97F4A7C15ull + e->passes + 1;
-    for (uint32_t i = v.A; i > 1; i--) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; std::swap(order[i - 1], order[s % i]); }
+    for (size_t i = order.size(); i > 1; i--) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; std::swap(order[i - 1], order[s % i]); }
   }
-  Acc acc; memset(&acc, 0, sizeof acc); acc.tmin = ~0ull;
+  e->ctl.wake_n[pa.par ^ 1u] = 0;
+  Acc acc; memset(&acc, 0, sizeof acc); acc.tmin = ~0ull; acc.stall = ~0ull;
   dispatch_model(e->cfg.model, [&](auto m) {
     using M = decltype(m);
-    for (uint32_t i = 0; i < v.A; i++) lp_pass<M>(v, e->mp, pa, order[i], acc);
+    for (uint32_t lp : order) lp_pass<M>(v, e->mp, pa, lp, acc);
     return 0;
   });
   e->ctl.gvt_slot[0][0] = std::min<unsigned long long>(e->ctl.gvt_slot[0][0], acc.tmin);
@@ -194,38 +199,51 @@ static void pass_one(deva_b200_engine *e, const PassArgs &pa, uint64_t *wx, uint
   e->passes++;
 }
 
-static int window_all(deva_b200_engine **es, int G, uint64_t ub, uint32_t sweep, uint64_t *wx_sum, uint64_t *wr_sum) {
-  *wx_sum = *wr_sum = 0;
+// one pass on every engine + spill delivery + the exchange NCCL does on the GPU box; returns the
+// number of LPs woken for the next follow-up pass
+static int pass_all(deva_b200_engine **es, int G, uint64_t gvt, uint64_t ub, uint32_t sweep, bool full,
+                    uint64_t *wx_sum, uint64_t *wr_sum, uint64_t *woken) {
+  std::vector<PassArgs> pas(G);
   for (int g = 0; g < G; g++) {
     deva_b200_engine *e = es[g];
     e->ctl.gvt_slot[0][0] = ~0ull;
-    PassArgs pa; pa.gvt = e->gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep;
+    PassArgs &pa = pas[g];
+    pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa._pad = 0;
     uint64_t wx, wr;
-    pass_one(e, pa, &wx, &wr);
+    pass_one(e, pa, full, &wx, &wr);
     *wx_sum += wx; *wr_sum += wr;
     if (e->ctl.spill_n > e->v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "spill overflow");
-    for (uint32_t i = 0; i < e->ctl.spill_n; i++) deliver_to_pending(e->v, e->v.spill[i], &e->ctl.err);
+    for (uint32_t i = 0; i < e->ctl.spill_n; i++) deliver_between_passes(e->v, e->v.spill[i], pa, &e->ctl.err);
     e->ctl.spill_n = 0;
   }
-  // exchange: what NCCL grouped send/recv does on the GPU box
   for (int g = 0; g < G; g++)
     for (int d = 0; d < G; d++) {
       if (d == g) continue;
       deva_b200_engine *s = es[g], *r = es[d];
       const uint32_t n = s->ctl.send_n[d];
       if (n > s->v.send_cap) return fail(DEVA_B200_ERR_CAPACITY, "send overflow");
-      for (uint32_t i = 0; i < n; i++) deliver_to_pending(r->v, s->v.sendbuf[(size_t)d * s->v.send_cap + i], &r->ctl.err);
+      for (uint32_t i = 0; i < n; i++) deliver_between_passes(r->v, s->v.sendbuf[(size_t)d * s->v.send_cap + i], pas[d], &r->ctl.err);
       s->ctl.send_n[d] = 0;
     }
-  uint64_t gvt = ~0ull;
-  for (int g = 0; g < G; g++) { gvt = std::min<uint64_t>(gvt, es[g]->ctl.gvt_slot[0][0]); int rc = check_err(es[g]); if (rc) return rc; }
-  for (int g = 0; g < G; g++) { es[g]->gvt = gvt; es[g]->par ^= 1u; }
+  *woken = 0;
+  for (int g = 0; g < G; g++) {
+    int rc = check_err(es[g]);
+    if (rc) return rc;
+    *woken += es[g]->ctl.wake_n[es[g]->par ^ 1u];
+    es[g]->par ^= 1u;
+  }
   return 0;
+}
+
+static uint64_t exact_gvt_all(deva_b200_engine **es, int G) {
+  uint64_t gvt = ~0ull;
+  for (int g = 0; g < G; g++)
+    for (uint32_t lp = 0; lp < es[g]->v.A; lp++) gvt = std::min<uint64_t>(gvt, es[g]->v.head[lp]);
+  return gvt;
 }
 
 int emu_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out) {
   for (int g = 0; g < G; g++) if (es[g]->has_rewind) return fail(DEVA_B200_ERR_STATE, "lingering rewind state");
-  uint64_t gvt = ~0ull;
   for (int g = 0; g < G; g++) {
     deva_b200_engine *e = es[g];
     View &v = e->v;
@@ -237,31 +255,37 @@ int emu_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewind
       for (auto &l : live) e->snap.emplace_back((char *)l.p, (char *)l.p + l.b);
       e->has_rewind = true;
     }
-    for (uint32_t lp = 0; lp < v.A; lp++) gvt = std::min<uint64_t>(gvt, v.head[lp]);
   }
+  uint64_t gvt = exact_gvt_all(es, G);
   for (int g = 0; g < G; g++) { es[g]->gvt = gvt; es[g]->snap_gvt = gvt; }
   uint64_t stall = 0;
-  while (es[0]->gvt < t_end) {
-    const uint64_t ub = es[0]->wp.upper_bound(es[0]->gvt, t_end);
-    const uint64_t before = es[0]->gvt;
-    uint64_t wx, wr;
-    int rc = window_all(es, G, ub, 0, &wx, &wr);
+  while (gvt < t_end) {   // epochs: see deva_b200_drain in engine.cu
+    const uint64_t ub = es[0]->wp.upper_bound(gvt, t_end);
+    const uint64_t before = gvt;
+    uint64_t ex = 0, rb = 0, woken = 0;
+    int rc = pass_all(es, G, gvt, ub, 0, true, &ex, &rb, &woken);
     if (rc) return rc;
-    for (int g = 0; g < G; g++) es[g]->wp.update(wx, wr);
-    if (es[0]->gvt == before && wx == 0) { if (++stall > 64) return fail(DEVA_B200_ERR_CAPACITY, "no progress: raise log_cap"); }
+    int guard = 0;
+    while (woken > 0) {
+      if ((rc = pass_all(es, G, gvt, ub, 0, false, &ex, &rb, &woken))) return rc;
+      if (++guard > 100000) return fail(DEVA_B200_ERR_INVARIANT, "epoch does not converge");
+    }
+    gvt = exact_gvt_all(es, G);
+    for (int g = 0; g < G; g++) { es[g]->gvt = gvt; es[g]->wp.update(ex, rb); }
+    if (gvt == before && ex == 0) { if (++stall > 64) return fail(DEVA_B200_ERR_CAPACITY, "no progress: raise log_cap"); }
     else stall = 0;
   }
-  uint64_t wx, wr;
-  int rc = window_all(es, G, t_end, 1, &wx, &wr);
+  uint64_t wx = 0, wr = 0, woken = 0;
+  int rc = pass_all(es, G, gvt, t_end, 1, true, &wx, &wr, &woken);
   if (rc) return rc;
-  if (wx) return fail(DEVA_B200_ERR_INVARIANT, "events executed during the final sweep");
+  if (wx || woken) return fail(DEVA_B200_ERR_INVARIANT, "events executed during the final sweep");
   // post-conditions the reference asserts at drain exit (pdes.cxx:1020-1035)
   for (int g = 0; g < G; g++)
     for (uint32_t lp = 0; lp < es[g]->v.A; lp++) {
       if (es[g]->v.lmeta[lp] & 0xffffu) return fail(DEVA_B200_ERR_INVARIANT, "uncommitted event left at drain exit");
       if (es[g]->v.icnt[0][lp] || es[g]->v.icnt[1][lp]) return fail(DEVA_B200_ERR_INVARIANT, "arrival left in an inbox at drain exit");
     }
-  if (gvt_out) *gvt_out = es[0]->gvt;
+  if (gvt_out) *gvt_out = gvt;
   return 0;
 }
 
@@ -310,13 +334,15 @@ uint64_t emu_local_min_head(deva_b200_engine *e) {
   for (uint32_t lp = 0; lp < e->v.A; lp++) m = std::min<uint64_t>(m, e->v.head[lp]);
   return m;
 }
-int emu_window_begin(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t sweep, uint64_t *wx, uint64_t *wr) {
+static PassArgs g_step_pa;   // args of the pass in progress (one engine per process in the gloo test)
+int emu_pass_begin(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t sweep, int full, uint64_t *wx, uint64_t *wr) {
   e->gvt = gvt;
   e->ctl.gvt_slot[0][0] = ~0ull;
-  PassArgs pa; pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep;
-  pass_one(e, pa, wx, wr);
+  PassArgs &pa = g_step_pa;
+  pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa._pad = 0;
+  pass_one(e, pa, full != 0, wx, wr);
   if (e->ctl.spill_n > e->v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "spill overflow");
-  for (uint32_t i = 0; i < e->ctl.spill_n; i++) deliver_to_pending(e->v, e->v.spill[i], &e->ctl.err);
+  for (uint32_t i = 0; i < e->ctl.spill_n; i++) deliver_between_passes(e->v, e->v.spill[i], pa, &e->ctl.err);
   e->ctl.spill_n = 0;
   return check_err(e);
 }
@@ -327,11 +353,14 @@ void emu_copy_send(deva_b200_engine *e, int g, void *out) {   // records staged 
 }
 int emu_deliver(deva_b200_engine *e, const void *recs, uint32_t n) {
   const EvRec *r = (const EvRec *)recs;
-  for (uint32_t i = 0; i < n; i++) deliver_to_pending(e->v, r[i], &e->ctl.err);
+  for (uint32_t i = 0; i < n; i++) deliver_between_passes(e->v, r[i], g_step_pa, &e->ctl.err);
   return check_err(e);
 }
-uint64_t emu_gvt_candidate(deva_b200_engine *e) { return e->ctl.gvt_slot[0][0]; }
-void emu_window_end(deva_b200_engine *e, uint64_t gvt) { e->gvt = gvt; e->par ^= 1u; }
+uint32_t emu_pass_end(deva_b200_engine *e) {   // LPs woken for the next follow-up pass on this engine
+  const uint32_t woken = e->ctl.wake_n[e->par ^ 1u];
+  e->par ^= 1u;
+  return woken;
+}
 uint64_t emu_upper_bound(deva_b200_engine *e, uint64_t gvt, uint64_t t_end) { return e->wp.upper_bound(gvt, t_end); }
 void emu_policy_update(deva_b200_engine *e, uint64_t wx, uint64_t wr) { e->wp.update(wx, wr); }
 

@@ -22,12 +22,11 @@ def _bind(api):
     L = api.lib
     P = C.c_void_p
     L.emu_local_min_head.argtypes = [P]; L.emu_local_min_head.restype = C.c_uint64
-    L.emu_window_begin.argtypes = [P, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.emu_pass_begin.argtypes = [P, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.emu_send_count.argtypes = [P, C.c_int]; L.emu_send_count.restype = C.c_uint32
     L.emu_copy_send.argtypes = [P, C.c_int, P]; L.emu_copy_send.restype = None
     L.emu_deliver.argtypes = [P, P, C.c_uint32]
-    L.emu_gvt_candidate.argtypes = [P]; L.emu_gvt_candidate.restype = C.c_uint64
-    L.emu_window_end.argtypes = [P, C.c_uint64]; L.emu_window_end.restype = None
+    L.emu_pass_end.argtypes = [P]; L.emu_pass_end.restype = C.c_uint32
     L.emu_upper_bound.argtypes = [P, C.c_uint64, C.c_uint64]; L.emu_upper_bound.restype = C.c_uint64
     L.emu_policy_update.argtypes = [P, C.c_uint64, C.c_uint64]; L.emu_policy_update.restype = None
 
@@ -45,14 +44,15 @@ def _sum(*xs):
     return [int(v) for v in t]
 
 
-def _window(api, eng, rank, world, gvt, ub, sweep):
+def _pass(api, eng, rank, world, gvt, ub, sweep, full):
+    """One pass of an epoch on this rank + the exchange (engine.cu run_pass)."""
     wx, wr = C.c_uint64(), C.c_uint64()
-    api.check(api.lib.emu_window_begin(eng.h, gvt, ub, sweep, C.byref(wx), C.byref(wr)))
+    api.check(api.lib.emu_pass_begin(eng.h, gvt, ub, sweep, int(full), C.byref(wx), C.byref(wr)))
     # 1. counts all-to-all
     counts = torch.tensor([api.lib.emu_send_count(eng.h, g) for g in range(world)], dtype=torch.int64)
     allc = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(allc, counts)
-    # 2. payload exchange (pairwise send/recv), 3. deliver
+    # 2. payload exchange (pairwise send/recv), 3. deliver (+ wake LPs hit inside the window)
     for peer in range(world):
         if peer == rank:
             continue
@@ -61,7 +61,6 @@ def _window(api, eng, rank, world, gvt, ub, sweep):
         if ns:
             api.lib.emu_copy_send(eng.h, peer, sbuf.data_ptr())
         rbuf = torch.zeros(max(nr, 1) * 32, dtype=torch.uint8)
-        reqs = []
         if rank < peer:
             if ns: dist.send(sbuf[:ns * 32], peer)
             if nr: dist.recv(rbuf[:nr * 32], peer)
@@ -70,11 +69,10 @@ def _window(api, eng, rank, world, gvt, ub, sweep):
             if ns: dist.send(sbuf[:ns * 32], peer)
         if nr:
             api.check(api.lib.emu_deliver(eng.h, rbuf.data_ptr(), nr))
-    # 4. GVT = min over ranks; window statistics summed (same window policy on every rank)
-    gvt_new = _u64_min(api.lib.emu_gvt_candidate(eng.h))
-    wxs, wrs = _sum(wx.value, wr.value)
-    api.lib.emu_window_end(eng.h, gvt_new)
-    return gvt_new, wxs, wrs
+    # 4. statistics and woken-LP counts summed over ranks (same decisions on every rank)
+    woken = api.lib.emu_pass_end(eng.h)
+    wxs, wrs, wk = _sum(wx.value, wr.value, woken)
+    return wxs, wrs, wk
 
 
 def _worker(rank, world, port, cfg, ret):
@@ -94,14 +92,18 @@ def _worker(rank, world, port, cfg, ret):
     t_end = T_INF
     gvt = _u64_min(api.lib.emu_local_min_head(eng.h))
     windows = 0
-    while gvt < t_end:
+    while gvt < t_end:                      # epochs, as deva_b200_drain drives them
         ub = api.lib.emu_upper_bound(eng.h, gvt, t_end)
-        gvt, wx, wr = _window(api, eng, rank, world, gvt, ub, 0)
-        api.lib.emu_policy_update(eng.h, wx, wr)
+        ex, rb, woken = _pass(api, eng, rank, world, gvt, ub, 0, True)
+        while woken > 0:
+            x, r, woken = _pass(api, eng, rank, world, gvt, ub, 0, False)
+            ex += x; rb += r
+        gvt = _u64_min(api.lib.emu_local_min_head(eng.h))
+        api.lib.emu_policy_update(eng.h, ex, rb)
         windows += 1
         assert windows < 100000
-    gvt, wx, _ = _window(api, eng, rank, world, gvt, t_end, 1)     # final sweep
-    assert wx == 0
+    wx, _, woken = _pass(api, eng, rank, world, gvt, t_end, 1, True)     # final sweep
+    assert wx == 0 and woken == 0
     st = torch.from_numpy(eng.get_state().astype(np.int64))
     pad = torch.zeros((per, 3), dtype=torch.int64); pad[:cnt] = st
     gathered = [torch.zeros_like(pad) for _ in range(world)]
