@@ -244,6 +244,7 @@ struct deva_b200_engine {
   bool profile = true;
   int pass_variant = 6;   // k_pass<M, MINB> instantiation (DEVA_B200_PASS_MINB = 4 | 6 | 8)
   uint32_t pass_tag = 0;  // serial number of the last pass (wake-list dedup tag)
+  uint64_t wake_min = 0;  // stop an epoch's follow-up passes when no more than this many LPs (job-wide) are woken
 };
 
 template <class T>
@@ -363,6 +364,8 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   const char *prof = getenv("DEVA_B200_PROFILE");
   if (prof) e->profile = atoi(prof) != 0;
   if (const char *pv = getenv("DEVA_B200_PASS_MINB")) e->pass_variant = atoi(pv);
+  e->wake_min = cfg->lp_n / 512;
+  if (const char *wm = getenv("DEVA_B200_WAKE_MIN")) e->wake_min = strtoull(wm, nullptr, 10);
   // snapshot list for rewind
   *out = e;
   return 0;
@@ -588,7 +591,7 @@ static int launch_pass(deva_b200_engine *e, const PassArgs &pa, uint32_t list_n)
 // previous pass wrote, then spill delivery and the peer exchange.  Returns the number of LPs woken
 // for the next follow-up pass (summed over GPUs).
 static int run_pass(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t sweep, bool full,
-                    uint64_t *p_exec, uint64_t *p_rolled, uint64_t *p_woken) {
+                    uint64_t *p_exec, uint64_t *p_rolled, uint64_t *p_woken, uint64_t *p_emit_min) {
   View &v = e->v;
   PassArgs pa;
   pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa._pad = 0;
@@ -614,18 +617,21 @@ static int run_pass(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t swe
   }
   uint64_t wx = e->sum.executed - before.executed, wr = e->sum.rolled_back - before.rolled_back;
   uint64_t woken = e->h_ctl->wake_n[e->par ^ 1u];
+  // min time over what the LPs visited in this pass left pending or emitted: with the LP heads it
+  // bounds the GVT even when the epoch is cut short (records still sitting in inboxes were emitted
+  // in this very pass; older ones have been folded by the follow-up passes in between)
+  uint64_t emit_min = (full || list_n > 0) ? e->sum.gvt_next : ~0ull;
   if (e->cfg.n_gpus > 1) {
     if ((rc = exchange(e, pa))) return rc;
     if ((rc = read_ctl(e))) return rc;       // records from peers may have woken LPs / raised a capacity error
     woken = e->h_ctl->wake_n[e->par ^ 1u];
     uint32_t err = e->sum.err;
-    uint64_t g = ~0ull;
-    if ((rc = allreduce_pass(e, &g, &wx, &wr, &woken, &err))) return rc;
+    if ((rc = allreduce_pass(e, &emit_min, &wx, &wr, &woken, &err))) return rc;
     e->sum.err = err;
   }
   if ((rc = check_ctl_err(e))) return rc;
   e->par ^= 1u;
-  *p_exec = wx; *p_rolled = wr; *p_woken = woken;
+  *p_exec = wx; *p_rolled = wr; *p_woken = woken; *p_emit_min = emit_min;
   return 0;
 }
 
@@ -689,28 +695,31 @@ int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uin
   while (e->gvt < t_end) {
     const uint64_t ub = e->wp.upper_bound(e->gvt, t_end);
     const uint64_t gvt_before = e->gvt;
-    uint64_t ex = 0, rb = 0, woken = 0, px = 0, pr = 0;
-    if ((rc = run_pass(e, e->gvt, ub, 0, true, &px, &pr, &woken))) return rc;
+    uint64_t ex = 0, rb = 0, woken = 0, px = 0, pr = 0, emit_min = ~0ull;
+    if ((rc = run_pass(e, e->gvt, ub, 0, true, &px, &pr, &woken, &emit_min))) return rc;
     ex += px; rb += pr;
     int guard = 0;
-    while (woken > 0) {
-      if ((rc = run_pass(e, e->gvt, ub, 0, false, &px, &pr, &woken))) return rc;
+    // follow-up passes while enough LPs are woken to be worth a launch (and a peer exchange); the
+    // few left over are simply visited by the next epoch's full pass
+    while (woken > e->wake_min) {
+      if ((rc = run_pass(e, e->gvt, ub, 0, false, &px, &pr, &woken, &emit_min))) return rc;
       ex += px; rb += pr;
       if (++guard > 100000) return fail(DEVA_B200_ERR_INVARIANT, "epoch does not converge");
     }
     if ((rc = exact_gvt(e, &gvt))) return rc;
-    e->gvt = gvt;
+    e->gvt = woken > 0 && emit_min < gvt ? emit_min : gvt;
     e->wp.update(ex, rb);
     // progress guard: GVT frozen and nothing executed for many epochs == the undo log cannot
     // drain (more same-time events at one LP than log_cap)
     if (e->gvt == gvt_before && ex == 0) { if (++stall > 64) return fail(DEVA_B200_ERR_CAPACITY, "no progress: raise log_cap"); }
     else stall = 0;
   }
-  // final sweep: every LP fossil-collects below GVT (>= t_end), so that no processed-uncommitted
-  // event is left (pdes.cxx:1020-1023 asserts); inboxes are already empty (last epoch converged)
+  // final sweep: every LP fossil-collects below GVT (>= t_end) and folds what is left in its inbox
+  // (all of it >= t_end), so that no processed-uncommitted event and no arrival is left behind
+  // (pdes.cxx:1020-1023 asserts)
   {
-    uint64_t wx = 0, wr = 0, woken = 0;
-    if ((rc = run_pass(e, e->gvt, t_end, 1, true, &wx, &wr, &woken))) return rc;
+    uint64_t wx = 0, wr = 0, woken = 0, em = 0;
+    if ((rc = run_pass(e, e->gvt, t_end, 1, true, &wx, &wr, &woken, &em))) return rc;
     if (wx != 0 || woken != 0) return fail(DEVA_B200_ERR_INVARIANT, "events executed during the final sweep");
   }
   CU(cudaEventRecord(e->ev_d1, e->stream));

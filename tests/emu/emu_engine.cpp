@@ -47,6 +47,7 @@ struct deva_b200_engine {
   uint64_t snap_gvt = 0;
   uint64_t shuffle = 1;   // LP visiting order seed
   uint32_t pass_tag = 0;
+  uint64_t wake_min = 0;
   std::vector<EvRec> recv;
 };
 
@@ -119,6 +120,8 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   }
   init_lps(e, 0);
   e->wp.init(cfg->window);
+  e->wake_min = cfg->lp_n / 512;
+  if (const char *wm = getenv("DEVA_B200_WAKE_MIN")) e->wake_min = strtoull(wm, nullptr, 10);
   *out = e;
   return 0;
 }
@@ -202,8 +205,9 @@ static void pass_one(deva_b200_engine *e, const PassArgs &pa, bool full, uint64_
 // one pass on every engine + spill delivery + the exchange NCCL does on the GPU box; returns the
 // number of LPs woken for the next follow-up pass
 static int pass_all(deva_b200_engine **es, int G, uint64_t gvt, uint64_t ub, uint32_t sweep, bool full,
-                    uint64_t *wx_sum, uint64_t *wr_sum, uint64_t *woken) {
+                    uint64_t *wx_sum, uint64_t *wr_sum, uint64_t *woken, uint64_t *emit_min) {
   std::vector<PassArgs> pas(G);
+  *emit_min = ~0ull;
   for (int g = 0; g < G; g++) {
     deva_b200_engine *e = es[g];
     e->ctl.gvt_slot[0][0] = ~0ull;
@@ -212,6 +216,7 @@ static int pass_all(deva_b200_engine **es, int G, uint64_t gvt, uint64_t ub, uin
     uint64_t wx, wr;
     pass_one(e, pa, full, &wx, &wr);
     *wx_sum += wx; *wr_sum += wr;
+    *emit_min = std::min<uint64_t>(*emit_min, e->ctl.gvt_slot[0][0]);
     if (e->ctl.spill_n > e->v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "spill overflow");
     for (uint32_t i = 0; i < e->ctl.spill_n; i++) deliver_between_passes(e->v, e->v.spill[i], pa, &e->ctl.err);
     e->ctl.spill_n = 0;
@@ -262,21 +267,22 @@ int emu_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewind
   while (gvt < t_end) {   // epochs: see deva_b200_drain in engine.cu
     const uint64_t ub = es[0]->wp.upper_bound(gvt, t_end);
     const uint64_t before = gvt;
-    uint64_t ex = 0, rb = 0, woken = 0;
-    int rc = pass_all(es, G, gvt, ub, 0, true, &ex, &rb, &woken);
+    uint64_t ex = 0, rb = 0, woken = 0, emit_min = ~0ull;
+    int rc = pass_all(es, G, gvt, ub, 0, true, &ex, &rb, &woken, &emit_min);
     if (rc) return rc;
     int guard = 0;
-    while (woken > 0) {
-      if ((rc = pass_all(es, G, gvt, ub, 0, false, &ex, &rb, &woken))) return rc;
+    while (woken > es[0]->wake_min) {
+      if ((rc = pass_all(es, G, gvt, ub, 0, false, &ex, &rb, &woken, &emit_min))) return rc;
       if (++guard > 100000) return fail(DEVA_B200_ERR_INVARIANT, "epoch does not converge");
     }
     gvt = exact_gvt_all(es, G);
+    if (woken > 0 && emit_min < gvt) gvt = emit_min;   // epoch cut short: unread arrivals bound the GVT
     for (int g = 0; g < G; g++) { es[g]->gvt = gvt; es[g]->wp.update(ex, rb); }
     if (gvt == before && ex == 0) { if (++stall > 64) return fail(DEVA_B200_ERR_CAPACITY, "no progress: raise log_cap"); }
     else stall = 0;
   }
-  uint64_t wx = 0, wr = 0, woken = 0;
-  int rc = pass_all(es, G, gvt, t_end, 1, true, &wx, &wr, &woken);
+  uint64_t wx = 0, wr = 0, woken = 0, em = 0;
+  int rc = pass_all(es, G, gvt, t_end, 1, true, &wx, &wr, &woken, &em);
   if (rc) return rc;
   if (wx || woken) return fail(DEVA_B200_ERR_INVARIANT, "events executed during the final sweep");
   // post-conditions the reference asserts at drain exit (pdes.cxx:1020-1035)
@@ -356,6 +362,8 @@ int emu_deliver(deva_b200_engine *e, const void *recs, uint32_t n) {
   for (uint32_t i = 0; i < n; i++) deliver_between_passes(e->v, r[i], g_step_pa, &e->ctl.err);
   return check_err(e);
 }
+uint64_t emu_emit_min(deva_b200_engine *e) { return e->ctl.gvt_slot[0][0]; }
+uint64_t emu_wake_min(deva_b200_engine *e) { return e->wake_min; }
 uint32_t emu_pass_end(deva_b200_engine *e) {   // LPs woken for the next follow-up pass on this engine
   const uint32_t woken = e->ctl.wake_n[e->par ^ 1u];
   e->par ^= 1u;

@@ -38,6 +38,14 @@ def test_phold_t_matches_oracle(api, cfg, window):
         assert s["rolled_back_n"] == 0 and s["executed_n"] == o["commits"]
 
 
+# ---- how early an epoch's follow-up passes stop never changes results either ----------------------
+@pytest.mark.parametrize("wake_min", ["0", "3", "50", "100000"])
+def test_epoch_cut_threshold_never_changes_results(api, monkeypatch, wake_min):
+    monkeypatch.setenv("DEVA_B200_WAKE_MIN", wake_min)
+    S.run_phold_t(api, 1000, 16, 0.5, 100.0, 300, window=25)
+    S.run_phold_t(api, 64, 4, 0.5, 10.0, 400, window=40)
+
+
 # ---- default tiebreak = per-LP sequence ids, root subtime = local cd index (test/phold.cxx) ------
 @pytest.mark.parametrize("ranks", [2, 3, 8])
 @pytest.mark.parametrize("window", [1, 50, 0])

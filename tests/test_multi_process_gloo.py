@@ -27,6 +27,8 @@ def _bind(api):
     L.emu_copy_send.argtypes = [P, C.c_int, P]; L.emu_copy_send.restype = None
     L.emu_deliver.argtypes = [P, P, C.c_uint32]
     L.emu_pass_end.argtypes = [P]; L.emu_pass_end.restype = C.c_uint32
+    L.emu_emit_min.argtypes = [P]; L.emu_emit_min.restype = C.c_uint64
+    L.emu_wake_min.argtypes = [P]; L.emu_wake_min.restype = C.c_uint64
     L.emu_upper_bound.argtypes = [P, C.c_uint64, C.c_uint64]; L.emu_upper_bound.restype = C.c_uint64
     L.emu_policy_update.argtypes = [P, C.c_uint64, C.c_uint64]; L.emu_policy_update.restype = None
 
@@ -70,9 +72,10 @@ def _pass(api, eng, rank, world, gvt, ub, sweep, full):
         if nr:
             api.check(api.lib.emu_deliver(eng.h, rbuf.data_ptr(), nr))
     # 4. statistics and woken-LP counts summed over ranks (same decisions on every rank)
+    emit_min = _u64_min(api.lib.emu_emit_min(eng.h))
     woken = api.lib.emu_pass_end(eng.h)
     wxs, wrs, wk = _sum(wx.value, wr.value, woken)
-    return wxs, wrs, wk
+    return wxs, wrs, wk, emit_min
 
 
 def _worker(rank, world, port, cfg, ret):
@@ -94,15 +97,17 @@ def _worker(rank, world, port, cfg, ret):
     windows = 0
     while gvt < t_end:                      # epochs, as deva_b200_drain drives them
         ub = api.lib.emu_upper_bound(eng.h, gvt, t_end)
-        ex, rb, woken = _pass(api, eng, rank, world, gvt, ub, 0, True)
-        while woken > 0:
-            x, r, woken = _pass(api, eng, rank, world, gvt, ub, 0, False)
+        ex, rb, woken, emit_min = _pass(api, eng, rank, world, gvt, ub, 0, True)
+        while woken > api.lib.emu_wake_min(eng.h):
+            x, r, woken, emit_min = _pass(api, eng, rank, world, gvt, ub, 0, False)
             ex += x; rb += r
         gvt = _u64_min(api.lib.emu_local_min_head(eng.h))
+        if woken > 0 and emit_min < gvt:
+            gvt = emit_min
         api.lib.emu_policy_update(eng.h, ex, rb)
         windows += 1
         assert windows < 100000
-    wx, _, woken = _pass(api, eng, rank, world, gvt, t_end, 1, True)     # final sweep
+    wx, _, woken, _ = _pass(api, eng, rank, world, gvt, t_end, 1, True)     # final sweep
     assert wx == 0 and woken == 0
     st = torch.from_numpy(eng.get_state().astype(np.int64))
     pad = torch.zeros((per, 3), dtype=torch.int64); pad[:cnt] = st
