@@ -244,6 +244,8 @@ struct deva_b200_engine {
   bool profile = true;
   int pass_variant = 6;   // k_pass<M, MINB> instantiation (DEVA_B200_PASS_MINB = 4 | 6 | 8)
   uint32_t pass_tag = 0;  // serial number of the last pass (wake-list dedup tag)
+  char *stage = nullptr;  // grow-only device staging for host-buffer calls (no cudaMalloc/cudaFree per call)
+  size_t stage_bytes = 0;
   uint64_t wake_min = 0;  // stop an epoch's follow-up passes when no more than this many LPs (job-wide) are woken
 };
 
@@ -255,6 +257,16 @@ static int dalloc(deva_b200_engine *e, T **p, size_t n) {
     return fail(DEVA_B200_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(r));
   e->allocs.push_back(q);
   *p = (T *)q;
+  return 0;
+}
+
+static int stage_reserve(deva_b200_engine *e, size_t bytes) {
+  if (bytes <= e->stage_bytes) return 0;
+  if (e->stage) cudaFree(e->stage);
+  e->stage = nullptr; e->stage_bytes = 0;
+  cudaError_t r = cudaMalloc((void **)&e->stage, bytes);
+  if (r != cudaSuccess) return fail(DEVA_B200_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(r));
+  e->stage_bytes = bytes;
   return 0;
 }
 
@@ -364,7 +376,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   const char *prof = getenv("DEVA_B200_PROFILE");
   if (prof) e->profile = atoi(prof) != 0;
   if (const char *pv = getenv("DEVA_B200_PASS_MINB")) e->pass_variant = atoi(pv);
-  e->wake_min = cfg->lp_n / 512;
+  e->wake_min = cfg->lp_n / 32;   // measured: flat on one GPU, fewer peer exchanges on several
   if (const char *wm = getenv("DEVA_B200_WAKE_MIN")) e->wake_min = strtoull(wm, nullptr, 10);
   // snapshot list for rewind
   *out = e;
@@ -378,6 +390,7 @@ void deva_b200_destroy(deva_b200_engine *e) {
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto &p : e->snap_pairs) cudaFree(p.second);
   for (void *p : e->allocs) cudaFree(p);
+  if (e->stage) cudaFree(e->stage);
   if (e->h_ctl) cudaFreeHost(e->h_ctl);
   if (e->h_counts) cudaFreeHost(e->h_counts);
   if (e->ev_a) cudaEventDestroy(e->ev_a);
@@ -393,13 +406,13 @@ int deva_b200_set_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t coun
   if (lp_first < e->v.lp_begin || lp_first + count > e->v.lp_begin + e->v.A) return fail(DEVA_B200_ERR_ARG, "LP range not owned");
   if (count == 0) return 0;
   CU(cudaSetDevice(e->cfg.device));
-  uint64_t *tmp = nullptr;
-  CU(cudaMalloc((void **)&tmp, count * e->stw * 8));
+  int rc = stage_reserve(e, count * e->stw * 8);
+  if (rc) return rc;
+  uint64_t *tmp = (uint64_t *)e->stage;
   CU(cudaMemcpyAsync(tmp, words, count * e->stw * 8, cudaMemcpyHostToDevice, e->stream));
   k_state_scatter<<<(unsigned)((count + 255) / 256), 256, 0, e->stream>>>(e->v, tmp, (uint32_t)(lp_first - e->v.lp_begin), (uint32_t)count, e->stw, 1);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(e->stream));
-  CU(cudaFree(tmp));
   return 0;
 }
 
@@ -408,13 +421,13 @@ int deva_b200_get_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t coun
   if (lp_first < e->v.lp_begin || lp_first + count > e->v.lp_begin + e->v.A) return fail(DEVA_B200_ERR_ARG, "LP range not owned");
   if (count == 0) return 0;
   CU(cudaSetDevice(e->cfg.device));
-  uint64_t *tmp = nullptr;
-  CU(cudaMalloc((void **)&tmp, count * e->stw * 8));
+  int rc = stage_reserve(e, count * e->stw * 8);
+  if (rc) return rc;
+  uint64_t *tmp = (uint64_t *)e->stage;
   k_state_scatter<<<(unsigned)((count + 255) / 256), 256, 0, e->stream>>>(e->v, tmp, (uint32_t)(lp_first - e->v.lp_begin), (uint32_t)count, e->stw, 0);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(words, tmp, count * e->stw * 8, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
-  CU(cudaFree(tmp));
   return 0;
 }
 
@@ -451,8 +464,9 @@ int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time,
   CU(cudaSetDevice(e->cfg.device));
   // four column copies (DMA straight from the caller's buffers; pinned buffers go at link speed),
   // then one kernel packs the records and scatters them into the owners' pending slots
-  char *d = nullptr;
-  CU(cudaMalloc((void **)&d, n * 24));
+  int rc = stage_reserve(e, n * 24);
+  if (rc) return rc;
+  char *d = e->stage;
   uint64_t *d_t = (uint64_t *)d, *d_s = d_t + n;
   uint32_t *d_l = (uint32_t *)(d_s + n), *d_p = d_l + n;
   CU(cudaMemcpyAsync(d_t, time, n * 8, cudaMemcpyHostToDevice, e->stream));
@@ -463,9 +477,7 @@ int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time,
   k_deliver_soa<<<grid, 256, 0, e->stream>>>(e->v, d_t, d_s, d_l, d_p, (uint32_t)n);
   e->launches++;
   CU(cudaGetLastError());
-  int rc = read_ctl(e);
-  cudaFree(d);
-  if (rc) return rc;
+  if ((rc = read_ctl(e))) return rc;
   return check_ctl_err(e);
 }
 

@@ -120,7 +120,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   }
   init_lps(e, 0);
   e->wp.init(cfg->window);
-  e->wake_min = cfg->lp_n / 512;
+  e->wake_min = cfg->lp_n / 32;
   if (const char *wm = getenv("DEVA_B200_WAKE_MIN")) e->wake_min = strtoull(wm, nullptr, 10);
   *out = e;
   return 0;
