@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const __grid_consta
 
 // records -> pending slots (roots, inbox spill, records received from peer GPUs)
 __global__ void k_deliver(View v, const EvRec *recs, const uint32_t *n_ptr, uint32_t n_fixed, PassArgs pa) {
-  const uint32_t n = n_ptr ? *n_ptr : n_fixed;
+  // n_ptr != null: count read on the device (clamped to n_fixed = capacity; overflow was flagged by the writer)
+  const uint32_t n = n_ptr ? (*n_ptr < n_fixed ? *n_ptr : n_fixed) : n_fixed;
   unsigned long long tmin = ~0ull;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const EvRec r = ld_ev(&recs[i]);
@@ -113,6 +114,27 @@ __global__ void k_deliver_soa(View v, const uint64_t *time, const uint64_t *sub,
     r.time = time[i]; r.sub = sub[i]; r.p0 = payload[i]; r.p1 = 0; r.dst = lp[i]; r.flags = 0;
     deliver_to_pending(v, r, &v.ctl->err);
   }
+}
+
+// folds the spread reduction slots of Ctl into the five allreduce inputs, on the device:
+// out = {GVT candidate, ~error flags, executed (cumulative), rolled back (cumulative), LPs woken}
+__global__ void k_pack_red(View v, uint32_t par_next, unsigned long long *out) {
+  const Ctl *c = v.ctl;
+  unsigned long long g = ~0ull, ex = 0, rb = 0, fl = c->err;
+  for (int i = threadIdx.x; i < CTL_SLOTS; i += 32) {
+    const unsigned long long t = c->gvt_slot[i][0];
+    g = t < g ? t : g;
+    ex += c->cnt[i][CNT_EXEC]; rb += c->cnt[i][CNT_ROLLED]; fl |= c->cnt[i][CNT_FLAGS] & 0x7fffffffull;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, g, o);
+    g = t2 < g ? t2 : g;
+    ex += __shfl_xor_sync(0xffffffffu, ex, o);
+    rb += __shfl_xor_sync(0xffffffffu, rb, o);
+    fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+  }
+  if (threadIdx.x == 0) { out[0] = g; out[1] = ~fl; out[2] = ex; out[3] = rb; out[4] = c->wake_n[par_next]; }
 }
 
 __global__ void k_min_head(View v) {
@@ -170,6 +192,7 @@ struct Nccl {
   int (*CommInitRank)(void **, int, NcclUid /*ncclUniqueId by value, 128 B*/, int) = nullptr;
   int (*CommDestroy)(void *) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
   int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -192,6 +215,7 @@ static int nccl_load() {
   SYM(CommInitRank, "ncclCommInitRank")
   SYM(CommDestroy, "ncclCommDestroy")
   SYM(AllReduce, "ncclAllReduce")
+  SYM(AllGather, "ncclAllGather")
   SYM(Send, "ncclSend")
   SYM(Recv, "ncclRecv")
   SYM(GroupStart, "ncclGroupStart")
@@ -240,6 +264,8 @@ struct deva_b200_engine {
   EvRec *recvbuf = nullptr;
   uint32_t *d_counts = nullptr;    // [2][MAX_GPUS]: send counts row, recv counts row
   uint32_t *h_counts = nullptr;    // pinned
+  unsigned long long *h_red = nullptr;  // pinned: allreduce results
+  uint64_t g_exec = 0, g_rolled = 0;    // job-wide cumulative counters at the previous pass (multi-GPU)
   unsigned long long *d_red = nullptr;  // allreduce scratch
   bool profile = true;
   int pass_variant = 6;   // k_pass<M, MINB> instantiation (DEVA_B200_PASS_MINB = 4 | 6 | 8)
@@ -351,9 +377,10 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
     v.send_cap = (uint32_t)std::min<size_t>(std::max<size_t>(A * 4, 1u << 16), 1u << 27);
     DA(v.sendbuf, (size_t)v.send_cap * cfg->n_gpus)
     DA(e->recvbuf, (size_t)v.send_cap * cfg->n_gpus)
-    DA(e->d_counts, 2 * MAX_GPUS)
+    DA(e->d_counts, MAX_GPUS * MAX_GPUS)
     DA(e->d_red, 16)
-    CU(cudaHostAlloc((void **)&e->h_counts, 2 * MAX_GPUS * sizeof(uint32_t), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void **)&e->h_counts, MAX_GPUS * MAX_GPUS * sizeof(uint32_t), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void **)&e->h_red, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
   }
 #undef DA
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -393,6 +420,7 @@ void deva_b200_destroy(deva_b200_engine *e) {
   if (e->stage) cudaFree(e->stage);
   if (e->h_ctl) cudaFreeHost(e->h_ctl);
   if (e->h_counts) cudaFreeHost(e->h_counts);
+  if (e->h_red) cudaFreeHost(e->h_red);
   if (e->ev_a) cudaEventDestroy(e->ev_a);
   if (e->ev_b) cudaEventDestroy(e->ev_b);
   if (e->ev_d0) cudaEventDestroy(e->ev_d0);
@@ -529,25 +557,20 @@ int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) {
 static int exchange(deva_b200_engine *e, const PassArgs &pa) {
   const int G = e->cfg.n_gpus, me = e->cfg.gpu_rank;
   View &v = e->v;
-  // 1. counts: every rank sends its send_n[g] to g
-  CU(cudaMemcpyAsync(e->d_counts, v.ctl->send_n, MAX_GPUS * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
-  NC(g_nccl.GroupStart());
-  for (int g = 0; g < G; g++) {
-    if (g == me) continue;
-    NC(g_nccl.Send(e->d_counts + g, 1, NC_U32, g, e->comm, e->stream));
-    NC(g_nccl.Recv(e->d_counts + MAX_GPUS + g, 1, NC_U32, g, e->comm, e->stream));
-  }
-  NC(g_nccl.GroupEnd());
-  CU(cudaMemcpyAsync(e->h_counts, e->d_counts, 2 * MAX_GPUS * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  // 1. counts: one all-gather of every rank's send_n row -> the G x G count matrix on every rank
+  NC(g_nccl.AllGather(v.ctl->send_n, e->d_counts, MAX_GPUS, NC_U32, e->comm, e->stream));
+  CU(cudaMemcpyAsync(e->h_counts, e->d_counts, (size_t)G * MAX_GPUS * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
+  auto n_send = [&](int g) { return e->h_counts[(size_t)me * MAX_GPUS + g]; };   // me -> g
+  auto n_recv = [&](int g) { return e->h_counts[(size_t)g * MAX_GPUS + me]; };   // g -> me
   // 2. payload
   bool any = false;
-  for (int g = 0; g < G; g++) if (g != me && (e->h_counts[g] || e->h_counts[MAX_GPUS + g])) any = true;
+  for (int g = 0; g < G; g++) if (g != me && (n_send(g) || n_recv(g))) any = true;
   if (any) {
     NC(g_nccl.GroupStart());
     for (int g = 0; g < G; g++) {
       if (g == me) continue;
-      const uint32_t ns = e->h_counts[g], nr = e->h_counts[MAX_GPUS + g];
+      const uint32_t ns = n_send(g), nr = n_recv(g);
       if (ns > v.send_cap || nr > v.send_cap) return fail(DEVA_B200_ERR_CAPACITY, "peer staging overflow");
       if (ns) NC(g_nccl.Send(v.sendbuf + (size_t)g * v.send_cap, (size_t)ns * sizeof(EvRec), NC_U8, g, e->comm, e->stream));
       if (nr) NC(g_nccl.Recv(e->recvbuf + (size_t)g * v.send_cap, (size_t)nr * sizeof(EvRec), NC_U8, g, e->comm, e->stream));
@@ -555,7 +578,7 @@ static int exchange(deva_b200_engine *e, const PassArgs &pa) {
     NC(g_nccl.GroupEnd());
     for (int g = 0; g < G; g++) {
       if (g == me) continue;
-      const uint32_t nr = e->h_counts[MAX_GPUS + g];
+      const uint32_t nr = n_recv(g);
       if (!nr) continue;
       const unsigned grid = (unsigned)std::min<uint32_t>((nr + 255) / 256, 148 * 8);
       k_deliver<<<grid, 256, 0, e->stream>>>(v, e->recvbuf + (size_t)g * v.send_cap, nullptr, nr, pa);
@@ -569,15 +592,19 @@ static int exchange(deva_b200_engine *e, const PassArgs &pa) {
 
 // One small allreduce set per pass (replaces gvt.cxx rdxn_up/rdxn_down): min of the GVT candidate,
 // sums of executed / rolled-back / woken-LP counts (window policy, epoch completion), max of errors.
-static int allreduce_pass(deva_b200_engine *e, uint64_t *gvt, uint64_t *exec_sum, uint64_t *rolled_sum, uint64_t *woken_sum, uint32_t *err_or) {
-  unsigned long long h[5] = {*gvt, *exec_sum, *rolled_sum, *woken_sum, *err_or};
-  CU(cudaMemcpyAsync(e->d_red, h, sizeof h, cudaMemcpyHostToDevice, e->stream));
-  NC(g_nccl.AllReduce(e->d_red, e->d_red + 8, 1, NC_U64, NC_MIN, e->comm, e->stream));
-  NC(g_nccl.AllReduce(e->d_red + 1, e->d_red + 9, 3, NC_U64, NC_SUM, e->comm, e->stream));
-  NC(g_nccl.AllReduce(e->d_red + 4, e->d_red + 12, 1, NC_U64, NC_MAX, e->comm, e->stream));
-  CU(cudaMemcpyAsync(h, e->d_red + 8, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+static int allreduce_pass(deva_b200_engine *e, bool pack_on_device, uint32_t par_next,
+                          uint64_t *gvt, uint64_t *exec_sum, uint64_t *rolled_sum, uint64_t *woken_sum, uint32_t *err_or) {
+  // {gvt, ~err} under MIN (max of the error flags == ~min of their complements); {exec, rolled, woken} under SUM
+  unsigned long long h[5] = {*gvt, ~(unsigned long long)*err_or, *exec_sum, *rolled_sum, *woken_sum};
+  if (pack_on_device) { k_pack_red<<<1, 32, 0, e->stream>>>(e->v, par_next, e->d_red); e->launches++; CU(cudaGetLastError()); }
+  else CU(cudaMemcpyAsync(e->d_red, h, sizeof h, cudaMemcpyHostToDevice, e->stream));
+  NC(g_nccl.AllReduce(e->d_red, e->d_red + 8, 2, NC_U64, NC_MIN, e->comm, e->stream));
+  NC(g_nccl.AllReduce(e->d_red + 2, e->d_red + 10, 3, NC_U64, NC_SUM, e->comm, e->stream));
+  CU(cudaMemcpyAsync(e->h_red, e->d_red + 8, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaMemcpyAsync(e->h_ctl, e->v.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
-  *gvt = h[0]; *exec_sum = h[1]; *rolled_sum = h[2]; *woken_sum = h[3]; *err_or = (uint32_t)h[4];
+  e->sum = fold_ctl(e->h_ctl);
+  *gvt = e->h_red[0]; *err_or = (uint32_t)~e->h_red[1]; *exec_sum = e->h_red[2]; *rolled_sum = e->h_red[3]; *woken_sum = e->h_red[4];
   return 0;
 }
 
@@ -608,39 +635,50 @@ static int run_pass(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t swe
   PassArgs pa;
   pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa._pad = 0;
   const uint32_t list_n = full ? 0u : e->h_ctl->wake_n[e->par];
+  const bool ran = full || list_n > 0;
   CU(cudaMemsetAsync(v.ctl->gvt_slot, 0xff, sizeof(v.ctl->gvt_slot), e->stream));
   CU(cudaMemsetAsync(&v.ctl->wake_n[e->par ^ 1u], 0, sizeof(uint32_t), e->stream));   // the list this pass writes
   int rc = 0;
-  const CtlSum before = e->sum;
-  if (full || list_n > 0) {
+  if (ran) {
     if ((rc = launch_pass(e, pa, list_n))) return rc;
-    if ((rc = read_ctl(e))) return rc;
-    if (e->profile) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->exec_ms += ms; }
     e->passes++;
-  } else if ((rc = read_ctl(e))) return rc;
-  if (e->h_ctl->spill_n) {   // rare: some LP's inbox overflowed this pass
-    if (e->h_ctl->spill_n > v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "inbox spill buffer overflowed (raise inbox_cap)");
-    const unsigned grid = (unsigned)std::min<uint32_t>((e->h_ctl->spill_n + 255) / 256, 148 * 8);
-    k_deliver<<<grid, 256, 0, e->stream>>>(v, v.spill, nullptr, e->h_ctl->spill_n, pa);
+  }
+  uint64_t wx, wr, woken, emit_min;
+  if (e->cfg.n_gpus == 1) {
+    const CtlSum before = e->sum;
+    if ((rc = read_ctl(e))) return rc;
+    if (e->h_ctl->spill_n) {   // rare: some LP's inbox overflowed this pass
+      if (e->h_ctl->spill_n > v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "inbox spill buffer overflowed (raise inbox_cap)");
+      const unsigned grid = (unsigned)std::min<uint32_t>((e->h_ctl->spill_n + 255) / 256, 148 * 8);
+      k_deliver<<<grid, 256, 0, e->stream>>>(v, v.spill, nullptr, e->h_ctl->spill_n, pa);
+      e->launches++;
+      CU(cudaGetLastError());
+      CU(cudaMemsetAsync(&v.ctl->spill_n, 0, sizeof(uint32_t), e->stream));
+      if ((rc = read_ctl(e))) return rc;
+    }
+    wx = e->sum.executed - before.executed; wr = e->sum.rolled_back - before.rolled_back;
+    woken = e->h_ctl->wake_n[e->par ^ 1u];
+    // min time over what the LPs visited in this pass left pending or emitted: with the LP heads
+    // it bounds the GVT even when the epoch is cut short (records still sitting in inboxes were
+    // emitted in this very pass; older ones have been folded by the follow-up passes in between)
+    emit_min = ran ? e->sum.gvt_next : ~0ull;
+  } else {
+    // several GPUs: no host round trip until the peer counts are needed - the spill is delivered
+    // from a device-side count, the allreduce inputs are packed on the device
+    k_deliver<<<148, 256, 0, e->stream>>>(v, v.spill, &v.ctl->spill_n, v.spill_cap, pa);
     e->launches++;
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(&v.ctl->spill_n, 0, sizeof(uint32_t), e->stream));
-    if ((rc = read_ctl(e))) return rc;
-  }
-  uint64_t wx = e->sum.executed - before.executed, wr = e->sum.rolled_back - before.rolled_back;
-  uint64_t woken = e->h_ctl->wake_n[e->par ^ 1u];
-  // min time over what the LPs visited in this pass left pending or emitted: with the LP heads it
-  // bounds the GVT even when the epoch is cut short (records still sitting in inboxes were emitted
-  // in this very pass; older ones have been folded by the follow-up passes in between)
-  uint64_t emit_min = (full || list_n > 0) ? e->sum.gvt_next : ~0ull;
-  if (e->cfg.n_gpus > 1) {
     if ((rc = exchange(e, pa))) return rc;
-    if ((rc = read_ctl(e))) return rc;       // records from peers may have woken LPs / raised a capacity error
-    woken = e->h_ctl->wake_n[e->par ^ 1u];
-    uint32_t err = e->sum.err;
-    if ((rc = allreduce_pass(e, &emit_min, &wx, &wr, &woken, &err))) return rc;
-    e->sum.err = err;
+    uint32_t err = 0;
+    uint64_t cx = 0, cr = 0;
+    emit_min = ~0ull; woken = 0;
+    if ((rc = allreduce_pass(e, true, e->par ^ 1u, &emit_min, &cx, &cr, &woken, &err))) return rc;
+    wx = cx - e->g_exec; wr = cr - e->g_rolled;   // cumulative job-wide counters -> this pass
+    e->g_exec = cx; e->g_rolled = cr;
+    e->sum.err |= err;
   }
+  if (e->profile && ran) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->exec_ms += ms; }
   if ((rc = check_ctl_err(e))) return rc;
   e->par ^= 1u;
   *p_exec = wx; *p_rolled = wr; *p_woken = woken; *p_emit_min = emit_min;
@@ -659,7 +697,7 @@ static int exact_gvt(deva_b200_engine *e, uint64_t *out) {
   uint64_t gvt = e->sum.gvt_next;
   if (e->cfg.n_gpus > 1) {
     uint64_t a = 0, b = 0, c = 0; uint32_t er = 0;
-    if ((rc = allreduce_pass(e, &gvt, &a, &b, &c, &er))) return rc;
+    if ((rc = allreduce_pass(e, false, 0, &gvt, &a, &b, &c, &er))) return rc;
   }
   *out = gvt;
   return 0;
