@@ -54,8 +54,10 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const __grid_consta
   Acc acc;
   acc.tmin = ~0ull; acc.stall = ~0ull;
   acc.executed = acc.committed = acc.rolled = acc.anti = acc.remote = acc.err = acc.nondet = 0;
-  if (list_n == 0) { if (i < v.A) lp_pass<M>(v, mp, pa, i, acc); }
-  else if (i < list_n) lp_pass<M>(v, mp, pa, v.wake[pa.par][i], acc);
+  uint32_t lp = 0xffffffffu;
+  if (list_n == 0) { if (i < v.A) lp = i; }
+  else if (i < list_n) lp = v.wake[pa.par][i];
+  if (lp != 0xffffffffu) lp_pass<M>(v, mp, pa, lp, acc);
 
   // warp reduction (no block barrier: a finished warp leaves at once), then one RED per quantity
   // into a counter slot picked by the block index

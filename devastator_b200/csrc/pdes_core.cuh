@@ -108,6 +108,22 @@ DEVA_HD bool key_less(uint64_t t1, uint64_t s1, uint64_t t2, uint64_t s2) {  // 
 DEVA_HD bool same_event(const EvRec &a, const EvRec &b) {
   return a.time == b.time && a.sub == b.sub && a.p0 == b.p0 && a.p1 == b.p1;
 }
+// ee[i] for a run-time i with ee held in registers (a select chain, no local-memory indexing):
+// lets a loop body exist ONCE in the instruction stream instead of once per unrolled iteration.
+DEVA_HD EvRec sel4(const EvRec (&ee)[4], int i) {
+  EvRec r = ee[0];
+  if (i == 1) r = ee[1];
+  if (i == 2) r = ee[2];
+  if (i == 3) r = ee[3];
+  return r;
+}
+DEVA_HD uint32_t sel4(const uint32_t (&x)[4], int i) {
+  uint32_t r = x[0];
+  if (i == 1) r = x[1];
+  if (i == 2) r = x[2];
+  if (i == 3) r = x[3];
+  return r;
+}
 constexpr uint32_t P1_ANTI = 0x80000000u;   // PqRest::p1f anti-message bit
 constexpr uint32_t FL_SENT = 0x80000000u;   // LogRec::fl "sent a child" bit
 
@@ -312,6 +328,18 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     if (e.time < khead) khead = e.time;
   };
   auto take_slot = [&](uint32_t s) { hole |= 1ull << s; };
+  // a positive record that is not in the pool: into the working set if it lies in the window (the
+  // record it pushes out, or the record itself when it does not fit, goes to the pool), else the pool
+  auto place = [&](const EvRec &e) {
+    EvRec q = e;
+    bool to_pool = true;
+    if (e.time < pa.ub) {
+      EvRec out;
+      const int r = wk.insert(e, out, gid32);
+      if (r == 0) to_pool = false; else if (r == 1) q = out;
+    }
+    if (to_pool) put_pending(q);
+  };
 
   // Stage A: every pending time of this LP in flight at once (8 B per slot, coalesced across the
   // warp), reduced to a bitmask of the slots below the window bound.
@@ -354,33 +382,33 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
 #pragma unroll
     for (int i = 0; i < RB; i++)
       if (ss[i] != 0xffffffffu) ee[i] = pq_load(v, lp, ss[i], v.pq_t[(size_t)ss[i] * A + lp], gid32);
-#pragma unroll
-    for (int i = 0; i < RB; i++)
-      if (ss[i] != 0xffffffffu) fold_pool_record(ee[i], ss[i]);
+#pragma unroll 1
+    for (int i = 0; i < RB; i++) {
+      const uint32_t si = sel4(ss, i);
+      if (si == 0xffffffffu) break;
+      fold_pool_record(sel4(ee, i), si);
+    }
   }
   if (ni > 0) {
     if (ni > v.ib_cap) ni = v.ib_cap;
     auto fold_arrival = [&](const EvRec &e) {
       if (e.flags & EV_ANTI) {
         if (na < DEVA_AN_CAP) an[na++] = e; else { put_pending(e); anti_overflow |= e.time < pa.ub; }
-      } else if (e.time < pa.ub) {
-        EvRec out;
-        const int r = wk.insert(e, out, gid32);
-        if (r == 1) put_pending(out); else if (r == 2) put_pending(e);
-      } else put_pending(e);
+      } else place(e);
     };
     for (uint32_t base = 0; base < ni; base += 4) {
       EvRec ee[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) if (base + i < ni) ee[i] = ld_ev(&v.ib[pa.par][(size_t)(base + i) * A + lp]);
-#pragma unroll
-      for (int i = 0; i < 4; i++) if (base + i < ni) fold_arrival(ee[i]);
+#pragma unroll 1
+      for (int i = 0; i < 4 && base + i < ni; i++) fold_arrival(sel4(ee, i));
     }
     v.icnt[pa.par][lp] = 0;
   }
 
   // pool helpers for the rare paths (slot indices are stable: removal only sets a hole bit)
   auto find_pending = [&](const EvRec &a, uint32_t want_anti) -> int {
+#pragma unroll 1
     for (uint32_t s = 0; s < top; s++) {
       if ((hole >> s) & 1ull) continue;
       if (v.pq_t[(size_t)s * A + lp] != a.time) continue;
@@ -408,6 +436,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   }
   uint32_t n_pool_anti = 0;                  // in-window antis still in the pool whose positive already ran
   if (anti_overflow) {
+#pragma unroll 1
     for (uint32_t s = 0; s < top; s++) {
       if ((hole >> s) & 1ull) continue;
       const uint64_t t = v.pq_t[(size_t)s * A + lp];
@@ -424,6 +453,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     for (int i = 0; i < na_log; i++)
       if (key_less(an[i].time, an[i].sub, anti_t, anti_s)) { anti_t = an[i].time; anti_s = an[i].sub; }
     if (n_pool_anti)
+#pragma unroll 1
       for (uint32_t s = 0; s < top; s++) {
         if ((hole >> s) & 1ull) continue;
         const uint64_t t = v.pq_t[(size_t)s * A + lp];
@@ -478,11 +508,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
       }
       if (dead) {
         recompute_anti_min();
-      } else {
-        EvRec out;
-        const int r = (le.time < pa.ub) ? wk.insert(le, out, gid32) : 2;
-        if (r == 1) put_pending(out); else if (r == 2) put_pending(le);
-      }
+      } else place(le);
       ln--;
       acc.rolled++;
     }
@@ -492,6 +518,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   // ---- phase 4: execute the working set in (time, subtime) order --------------------------------
   while (wk.n > 0) {
     if (ln == v.log_cap) {   // undo log full: leave the rest pending (they stay below GVT's reach)
+#pragma unroll 1
       for (int i = 0; i < wk.n; i++) put_pending(wk.get(i, gid32));
       wk.n = 0;
       break;
@@ -512,13 +539,8 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     if (sent) {
       if (!mp.user_subtime) c.sub = seq;   // event_subtime / next_seq_id, pdes.hxx:513-526,676
       seq += v.lp_n;
-      if ((uint64_t)c.dst == gid) {
-        EvRec out;
-        const int r = (c.time < pa.ub) ? wk.insert(c, out, gid32) : 2;
-        if (r == 1) put_pending(out); else if (r == 2) put_pending(c);
-      } else {
-        deliver(v, par_next, c, acc);
-      }
+      if ((uint64_t)c.dst == gid) place(c);
+      else deliver(v, par_next, c, acc);
     }
   }
 
@@ -535,6 +557,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   }
   if (khead_dirty) {
     khead = ~0ull;
+#pragma unroll 1
     for (uint32_t s = 0; s < top; s++) { const uint64_t t = v.pq_t[(size_t)s * A + lp]; if (t < khead) khead = t; }
   }
 #pragma unroll
