@@ -60,21 +60,15 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const __grid_consta
   if (lp != 0xffffffffu) lp_pass<M>(v, mp, pa, lp, acc);
 
   // warp reduction (no block barrier: a finished warp leaves at once), then one RED per quantity
-  // into a counter slot picked by the block index
-  unsigned long long tmin = acc.tmin;
-  uint32_t ex = acc.executed, cm = acc.committed, rb = acc.rolled, an = acc.anti, rm = acc.remote;
-  uint32_t fl = acc.err | (acc.nondet << 31);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, tmin, o);
-    tmin = t2 < tmin ? t2 : tmin;
-    ex += __shfl_xor_sync(0xffffffffu, ex, o);
-    cm += __shfl_xor_sync(0xffffffffu, cm, o);
-    rb += __shfl_xor_sync(0xffffffffu, rb, o);
-    an += __shfl_xor_sync(0xffffffffu, an, o);
-    rm += __shfl_xor_sync(0xffffffffu, rm, o);
-    fl |= __shfl_xor_sync(0xffffffffu, fl, o);
-  }
+  // into a counter slot picked by the block index.  32-bit quantities reduce in one REDUX each;
+  // the 64-bit minimum as high word first, then the low word among the lanes that hold that high word.
+  const uint32_t thi = __reduce_min_sync(0xffffffffu, (uint32_t)(acc.tmin >> 32));
+  const uint32_t tlo = __reduce_min_sync(0xffffffffu, (uint32_t)(acc.tmin >> 32) == thi ? (uint32_t)acc.tmin : 0xffffffffu);
+  const unsigned long long tmin = ((unsigned long long)thi << 32) | tlo;
+  const uint32_t ex = __reduce_add_sync(0xffffffffu, acc.executed), cm = __reduce_add_sync(0xffffffffu, acc.committed);
+  const uint32_t rb = __reduce_add_sync(0xffffffffu, acc.rolled), an = __reduce_add_sync(0xffffffffu, acc.anti);
+  const uint32_t rm = __reduce_add_sync(0xffffffffu, acc.remote);
+  const uint32_t fl = __reduce_or_sync(0xffffffffu, acc.err | (acc.nondet << 31));
   if ((threadIdx.x & 31) == 0) {
     Ctl *c = v.ctl;
     const int slot = (int)((blockIdx.x * (PASS_THREADS / 32) + (threadIdx.x >> 5)) % CTL_SLOTS);

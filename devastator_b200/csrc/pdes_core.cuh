@@ -42,9 +42,10 @@ DEVA_HD uint32_t atom_add_u32(uint32_t *p, uint32_t v) { return atomicAdd(p, v);
 DEVA_HD void atom_or_u32(uint32_t *p, uint32_t v) { atomicOr(p, v); }
 DEVA_HD void atom_min_u64(uint64_t *p, uint64_t v) { atomicMin((unsigned long long *)p, (unsigned long long)v); }
 DEVA_HD uint32_t atom_exch_u32(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
+#define DEVA_LD(p) (*(p))   // (streaming __ldcs loads were measured: no gain, slightly slower at 10 % remote)
 DEVA_HD EvRec ld_ev(const EvRec *p) {
-  const uint4 a = reinterpret_cast<const uint4 *>(p)[0];
-  const uint4 b = reinterpret_cast<const uint4 *>(p)[1];
+  const uint4 a = DEVA_LD(reinterpret_cast<const uint4 *>(p));
+  const uint4 b = DEVA_LD(reinterpret_cast<const uint4 *>(p) + 1);
   EvRec e;
   e.time = ((uint64_t)a.y << 32) | a.x; e.sub = ((uint64_t)a.w << 32) | a.z;
   e.p0 = b.x; e.p1 = b.y; e.dst = b.z; e.flags = b.w;
@@ -55,26 +56,32 @@ DEVA_HD void st_ev(EvRec *p, const EvRec &e) {
   reinterpret_cast<uint4 *>(p)[1] = make_uint4(e.p0, e.p1, e.dst, e.flags);
 }
 DEVA_HD PqRest ld_rest(const PqRest *p) {
-  const uint4 a = *reinterpret_cast<const uint4 *>(p);
+  const uint4 a = DEVA_LD(reinterpret_cast<const uint4 *>(p));
   PqRest r; r.sub = ((uint64_t)a.y << 32) | a.x; r.p0 = a.z; r.p1f = a.w; return r;
 }
 DEVA_HD void st_rest(PqRest *p, const PqRest &r) {
   *reinterpret_cast<uint4 *>(p) = make_uint4((uint32_t)r.sub, (uint32_t)(r.sub >> 32), r.p0, r.p1f);
 }
 DEVA_HD LogRec ld_log(const LogRec *p) {
-  const uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1], c = reinterpret_cast<const uint4 *>(p)[2];
+  const uint4 a = DEVA_LD(reinterpret_cast<const uint4 *>(p)), b = DEVA_LD(reinterpret_cast<const uint4 *>(p) + 1), c = DEVA_LD(reinterpret_cast<const uint4 *>(p) + 2);
   LogRec l;
   l.time = ((uint64_t)a.y << 32) | a.x; l.sub = ((uint64_t)a.w << 32) | a.z;
   l.p0 = b.x; l.fl = b.y; l.st[0] = ((uint64_t)b.w << 32) | b.z;
   l.st[1] = ((uint64_t)c.y << 32) | c.x; l.st[2] = ((uint64_t)c.w << 32) | c.z;
   return l;
 }
+DEVA_HD void ld_key(const LogRec *p, uint64_t &t, uint64_t &s) {   // (time, sub) of a log entry: one 16-byte load
+  const uint4 a = DEVA_LD(reinterpret_cast<const uint4 *>(p));
+  t = ((uint64_t)a.y << 32) | a.x; s = ((uint64_t)a.w << 32) | a.z;
+}
 DEVA_HD void st_log(LogRec *p, const LogRec &l) {
   reinterpret_cast<uint4 *>(p)[0] = make_uint4((uint32_t)l.time, (uint32_t)(l.time >> 32), (uint32_t)l.sub, (uint32_t)(l.sub >> 32));
   reinterpret_cast<uint4 *>(p)[1] = make_uint4(l.p0, l.fl, (uint32_t)l.st[0], (uint32_t)(l.st[0] >> 32));
   reinterpret_cast<uint4 *>(p)[2] = make_uint4((uint32_t)l.st[1], (uint32_t)(l.st[1] >> 32), (uint32_t)l.st[2], (uint32_t)(l.st[2] >> 32));
 }
+DEVA_HD uint64_t ld_u64(const uint64_t *p) { return DEVA_LD(reinterpret_cast<const unsigned long long *>(p)); }
 DEVA_HD int ffs64(uint64_t x) { return __ffsll((long long)x); }
+DEVA_HD int ffs32(uint32_t x) { return __ffs((int)x); }
 // warp-aggregated slot claim on a hot counter (peer-GPU staging): lanes that are converged here and
 // target the same counter elect one atomicAdd.
 __device__ __forceinline__ uint32_t agg_claim(uint32_t *ctr, uint32_t key) {
@@ -98,7 +105,10 @@ DEVA_HD PqRest ld_rest(const PqRest *p) { return *p; }
 DEVA_HD void st_rest(PqRest *p, const PqRest &r) { *p = r; }
 DEVA_HD LogRec ld_log(const LogRec *p) { return *p; }
 DEVA_HD void st_log(LogRec *p, const LogRec &l) { *p = l; }
+DEVA_HD void ld_key(const LogRec *p, uint64_t &t, uint64_t &s) { t = p->time; s = p->sub; }
+DEVA_HD uint64_t ld_u64(const uint64_t *p) { return *p; }
 DEVA_HD int ffs64(uint64_t x) { return __builtin_ffsll((long long)x); }
+DEVA_HD int ffs32(uint32_t x) { return __builtin_ffs((int)x); }
 DEVA_HD uint32_t agg_claim(uint32_t *ctr, uint32_t) { return atom_add_u32(ctr, 1); }
 #endif
 
@@ -134,42 +144,57 @@ struct Acc {
   uint32_t executed, committed, rolled, anti, remote, err, nondet;
 };
 
-// In-window events of one LP, sorted DESCENDING by (time, sub): the next event to run is e[n-1].
+// In-window events of one LP, UNSORTED in thread-local memory with a bitmask of the entries in use.
+// Entries never move: an insert writes one entry, taking the next event is a scan for the minimum
+// key over the live entries (loads only, L1 hits) and clearing its bit.  (Thread-local stores are
+// written through to L2, so a sorted array that shifts entries on every insert costs far more
+// memory traffic than the events themselves.)
 struct WorkSet {
   uint64_t t[DEVA_WK_CAP], s[DEVA_WK_CAP];
   uint32_t p0[DEVA_WK_CAP], p1[DEVA_WK_CAP];
-  int n;
+  uint32_t live;   // bit i: entry i holds an event
+  static_assert(DEVA_WK_CAP <= 32, "live mask is 32 bits");
+  static constexpr uint32_t ALL = DEVA_WK_CAP == 32 ? 0xffffffffu : ((1u << DEVA_WK_CAP) - 1u);
+  DEVA_HD bool empty() const { return live == 0; }
   DEVA_HD EvRec get(int i, uint32_t dst) const {
     EvRec e; e.time = t[i]; e.sub = s[i]; e.p0 = p0[i]; e.p1 = p1[i]; e.dst = dst; e.flags = 0; return e;
   }
   DEVA_HD void put(int i, const EvRec &e) { t[i] = e.time; s[i] = e.sub; p0[i] = e.p0; p1[i] = e.p1; }
-  // Insert keeping order.  Returns 0 = inserted; 1 = inserted and `out` (the largest) evicted;
-  // 2 = rejected (full and e is not smaller than the largest).
+  DEVA_HD void drop(int i) { live &= ~(1u << i); }
+  // index of the live entry with the smallest (largest) key, -1 if none
+  DEVA_HD int extreme(bool want_max) const {
+    int best = -1;
+    uint64_t bt = 0, bs = 0;
+#pragma unroll 1
+    for (uint32_t m = live; m; m &= m - 1) {
+      const int i = ffs32(m) - 1;
+      const uint64_t ti = t[i], si = s[i];
+      if (best < 0 || (want_max ? key_less(bt, bs, ti, si) : key_less(ti, si, bt, bs))) { best = i; bt = ti; bs = si; }
+    }
+    return best;
+  }
+  // Returns 0 = inserted; 1 = inserted and `out` (the largest) evicted; 2 = rejected (full and e is
+  // not smaller than the largest).
   DEVA_HD int insert(const EvRec &e, EvRec &out, uint32_t dst) {
-    int evicted = 0;
-    if (n == DEVA_WK_CAP) {
-      if (!key_less(e.time, e.sub, t[0], s[0])) return 2;
-      out = get(0, dst);
-      for (int i = 0; i + 1 < n; i++) { t[i] = t[i + 1]; s[i] = s[i + 1]; p0[i] = p0[i + 1]; p1[i] = p1[i + 1]; }
-      n--;
-      evicted = 1;
+    const uint32_t free_m = ~live & ALL;
+    if (free_m) {
+      const int i = ffs32(free_m) - 1;
+      put(i, e);
+      live |= 1u << i;
+      return 0;
     }
-    int i = n;   // entries not larger than e sit at the end and move one place right
-    while (i > 0 && !key_less(e.time, e.sub, t[i - 1], s[i - 1])) {
-      t[i] = t[i - 1]; s[i] = s[i - 1]; p0[i] = p0[i - 1]; p1[i] = p1[i - 1];
-      i--;
-    }
-    put(i, e);
-    n++;
-    return evicted;
+    const int mx = extreme(true);
+    if (!key_less(e.time, e.sub, t[mx], s[mx])) return 2;
+    out = get(mx, dst);
+    put(mx, e);
+    return 1;
   }
   DEVA_HD bool remove_match(const EvRec &a) {
-    for (int i = 0; i < n; i++)
-      if (t[i] == a.time && s[i] == a.sub && p0[i] == a.p0 && p1[i] == a.p1) {
-        for (int j = i; j + 1 < n; j++) { t[j] = t[j + 1]; s[j] = s[j + 1]; p0[j] = p0[j + 1]; p1[j] = p1[j + 1]; }
-        n--;
-        return true;
-      }
+#pragma unroll 1
+    for (uint32_t m = live; m; m &= m - 1) {
+      const int i = ffs32(m) - 1;
+      if (t[i] == a.time && s[i] == a.sub && p0[i] == a.p0 && p1[i] == a.p1) { drop(i); return true; }
+    }
     return false;
   }
 };
@@ -260,37 +285,36 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   // The first PF tail entries are fetched together (independent loads in flight), the rare rest
   // one by one.
   if (ln > 0) {
-    constexpr int PF = 4;
-    uint64_t pt[PF], ps[PF];
-#pragma unroll
-    for (int i = 0; i < PF; i++) {
-      uint32_t idx = lt + i; if (idx >= v.log_cap) idx -= v.log_cap;
-      const bool ok = (uint32_t)i < ln;
-      const LogRec *lr = &v.lg[(size_t)(ok ? idx : lt) * A + lp];
-      pt[i] = ok ? lr->time : ~0ull;
-      ps[i] = ok ? lr->sub : 0ull;
-    }
+    // Entries are fetched PF at a time (independent 16-byte loads of (time, sub), all in flight
+    // together): with epochs nearly everything an LP ran in the previous window commits here.
+    constexpr int PF = 8;
     uint64_t lct = v.lct[lp], lcs = v.lcs[lp];
     bool any = false;
-    int k = 0;
     while (ln > 0) {
-      uint64_t t, sb;
-      if (k < PF) {
-        t = pt[0]; sb = ps[0];
+      uint64_t pt[PF], ps[PF];
 #pragma unroll
-        for (int i = 0; i + 1 < PF; i++) { pt[i] = pt[i + 1]; ps[i] = ps[i + 1]; }
-      } else {
-        const LogRec *lr = &v.lg[(size_t)lt * A + lp];
-        t = lr->time; sb = lr->sub;
+      for (int i = 0; i < PF; i++) {
+        uint32_t idx = lt + i; if (idx >= v.log_cap) idx -= v.log_cap;
+        const bool ok = (uint32_t)i < ln;
+        ld_key(&v.lg[(size_t)(ok ? idx : lt) * A + lp], pt[i], ps[i]);
+        if (!ok) pt[i] = ~0ull;
       }
-      k++;
-      if (t >= pa.gvt) break;       // strict <, pdes.cxx:825
-      if (!key_less(lct, lcs, t + 1, sb)) acc.nondet = 1;   // pdes.cxx:828-831
-      lct = t + 1; lcs = sb;
-      lt = (lt + 1 == v.log_cap) ? 0 : lt + 1;
-      ln--;
-      acc.committed++;
-      any = true;
+      uint32_t c = 0;
+      bool stop = false;
+#pragma unroll
+      for (int i = 0; i < PF; i++) {
+        stop |= pt[i] >= pa.gvt;                                   // strict <, pdes.cxx:825
+        if (!stop) {
+          if (!key_less(lct, lcs, pt[i] + 1, ps[i])) acc.nondet = 1;   // pdes.cxx:828-831
+          lct = pt[i] + 1; lcs = ps[i];
+          c++;
+        }
+      }
+      lt += c; if (lt >= v.log_cap) lt -= v.log_cap;
+      ln -= c;
+      acc.committed += c;
+      any |= c > 0;
+      if (stop) break;
     }
     if (any) { v.lct[lp] = lct; v.lcs[lp] = lcs; }
   }
@@ -309,7 +333,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   // The pending pool is NOT compacted: slots whose event is taken become holes (bitmask `hole`),
   // new pending records fill holes first, and only what is left of the holes is closed at the end
   // by moving tail records down.  Records that stay are never rewritten.
-  WorkSet wk; wk.n = 0;
+  WorkSet wk; wk.live = 0;
   EvRec an[DEVA_AN_CAP]; int na = 0;
   uint64_t hole = 0;            // bit s: slot s (< top) is free
   uint32_t top = np;            // slots in use: [0, top) minus holes
@@ -349,7 +373,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     for (uint32_t base = 0; base < np; base += CH) {
       uint64_t tt[CH];
 #pragma unroll
-      for (int i = 0; i < CH; i++) tt[i] = (base + i < np) ? v.pq_t[(size_t)(base + i) * A + lp] : ~0ull;
+      for (int i = 0; i < CH; i++) tt[i] = (base + i < np) ? ld_u64(&v.pq_t[(size_t)(base + i) * A + lp]) : ~0ull;
 #pragma unroll
       for (int i = 0; i < CH; i++) {
         if (tt[i] < pa.ub) inwin |= 1ull << (base + i);      // (~0 for absent slots is never < ub)
@@ -381,7 +405,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     }
 #pragma unroll
     for (int i = 0; i < RB; i++)
-      if (ss[i] != 0xffffffffu) ee[i] = pq_load(v, lp, ss[i], v.pq_t[(size_t)ss[i] * A + lp], gid32);
+      if (ss[i] != 0xffffffffu) ee[i] = pq_load(v, lp, ss[i], ld_u64(&v.pq_t[(size_t)ss[i] * A + lp]), gid32);
 #pragma unroll 1
     for (int i = 0; i < RB; i++) {
       const uint32_t si = sel4(ss, i);
@@ -464,9 +488,10 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   };
 
   // ---- phase 3: straggler / anti-message rollback (insert_past, remove_past, rollback) -----------
-  if (ln > 0 && (wk.n > 0 || na_log > 0 || n_pool_anti > 0)) {
-    const uint64_t sg_t = wk.n > 0 ? wk.t[wk.n - 1] : ~0ull;   // smallest in-window key = straggler
-    const uint64_t sg_s = wk.n > 0 ? wk.s[wk.n - 1] : ~0ull;
+  if (ln > 0 && (!wk.empty() || na_log > 0 || n_pool_anti > 0)) {
+    const int sg = wk.extreme(false);                          // smallest in-window key = straggler
+    const uint64_t sg_t = sg >= 0 ? wk.t[sg] : ~0ull;
+    const uint64_t sg_s = sg >= 0 ? wk.s[sg] : ~0ull;
     while (ln > 0) {
       uint32_t li = lt + ln - 1; if (li >= v.log_cap) li -= v.log_cap;
       const LogRec *lrp = &v.lg[(size_t)li * A + lp];
@@ -516,15 +541,16 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   } else if (na_log > 0 || n_pool_anti > 0) acc.err |= ERR_ANTI_UNMATCHED;
 
   // ---- phase 4: execute the working set in (time, subtime) order --------------------------------
-  while (wk.n > 0) {
+  while (!wk.empty()) {
     if (ln == v.log_cap) {   // undo log full: leave the rest pending (they stay below GVT's reach)
 #pragma unroll 1
-      for (int i = 0; i < wk.n; i++) put_pending(wk.get(i, gid32));
-      wk.n = 0;
+      for (uint32_t m = wk.live; m; m &= m - 1) put_pending(wk.get(ffs32(m) - 1, gid32));
+      wk.live = 0;
       break;
     }
-    const EvRec e = wk.get(wk.n - 1, gid32);
-    wk.n--;
+    const int mi = wk.extreme(false);
+    const EvRec e = wk.get(mi, gid32);
+    wk.drop(mi);
     uint32_t li = lt + ln; if (li >= v.log_cap) li -= v.log_cap;
     LogRec lr;
     lr.time = e.time; lr.sub = e.sub; lr.p0 = e.p0;
