@@ -30,7 +30,7 @@
 namespace deva_b200 {
 
 #ifndef DEVA_WK_CAP
-#define DEVA_WK_CAP 24   // in-window working set per LP (events sorted in thread-local memory)
+#define DEVA_WK_CAP 24   // in-window working set per LP (unsorted records in thread-local memory)
 #endif
 #ifndef DEVA_AN_CAP
 #define DEVA_AN_CAP 8    // anti-messages handled per LP per window (extra ones wait in pending)
@@ -202,29 +202,53 @@ struct WorkSet {
 // Deliver a record (child or anti-message) to the LP that owns rec.dst.  Same GPU: straight into
 // that LP's next-window inbox.  Other GPU: into the staging buffer for that peer (exchanged after
 // the kernel).  Replaces execute_context::send's near/far split (pdes.hxx:691-731).
-DEVA_HD void deliver(const View &v, uint32_t par_next, const EvRec &rec, Acc &acc) {
+// Two halves, so that the round trip of the slot-claiming atomic overlaps the caller's next event:
+// send_begin issues the atomic, send_end (called one event later) uses its result.
+struct Send {
+  EvRec rec;
+  uint32_t slot;
+  uint32_t route;   // 0 = nothing in flight, 1 = same-GPU inbox, 2 = peer staging buffer
+  uint32_t g;       // peer GPU (route 2)
+};
+DEVA_HD void send_begin(const View &v, uint32_t par_next, const EvRec &rec, Acc &acc, Send &sd) {
   if (rec.time < acc.tmin) acc.tmin = rec.time;
   uint32_t g = (uint32_t)v.gpu_rank;
   if (v.n_gpus > 1) g = (uint32_t)(rec.dst / v.lp_per_gpu);
+  sd.rec = rec;
+  sd.g = g;
   if (g == (uint32_t)v.gpu_rank) {
     const uint32_t dl = (uint32_t)(rec.dst - v.lp_begin);
-    if (dl >= v.A) { acc.err |= ERR_NOT_OWNER; return; }
-    const uint32_t slot = atom_add_u32(&v.icnt[par_next][dl], 1u);
-    if (slot == 0) {   // first arrival of this pass: the LP joins the follow-up pass's wake list (once)
+    if (dl >= v.A) { acc.err |= ERR_NOT_OWNER; sd.route = 0; return; }
+    sd.slot = atom_add_u32(&v.icnt[par_next][dl], 1u);
+    sd.route = 1;
+  } else {
+    sd.slot = agg_claim(&v.ctl->send_n[g], g);
+    sd.route = 2;
+    acc.remote++;
+  }
+}
+DEVA_HD void send_end(const View &v, uint32_t par_next, Acc &acc, Send &sd) {
+  if (sd.route == 1) {
+    const uint32_t dl = (uint32_t)(sd.rec.dst - v.lp_begin);
+    if (sd.slot == 0) {   // first arrival of this pass: the LP joins the follow-up pass's wake list (once)
       const uint32_t k = agg_claim(&v.ctl->wake_n[par_next], 0xffu);
       v.wake[par_next][k] = dl;
     }
-    if (slot < v.ib_cap) {
-      st_ev(&v.ib[par_next][(size_t)slot * v.A + dl], rec);
+    if (sd.slot < v.ib_cap) {
+      st_ev(&v.ib[par_next][(size_t)sd.slot * v.A + dl], sd.rec);
     } else {  // inbox full: spill; delivered into the LP's pending slots between windows
       const uint32_t k = atom_add_u32(&v.ctl->spill_n, 1u);
-      if (k < v.spill_cap) st_ev(&v.spill[k], rec); else acc.err |= ERR_SPILL_OVERFLOW;
+      if (k < v.spill_cap) st_ev(&v.spill[k], sd.rec); else acc.err |= ERR_SPILL_OVERFLOW;
     }
-  } else {
-    const uint32_t k = agg_claim(&v.ctl->send_n[g], g);
-    if (k < v.send_cap) st_ev(&v.sendbuf[(size_t)g * v.send_cap + k], rec); else acc.err |= ERR_SEND_OVERFLOW;
-    acc.remote++;
+  } else if (sd.route == 2) {
+    if (sd.slot < v.send_cap) st_ev(&v.sendbuf[(size_t)sd.g * v.send_cap + sd.slot], sd.rec); else acc.err |= ERR_SEND_OVERFLOW;
   }
+  sd.route = 0;
+}
+DEVA_HD void deliver(const View &v, uint32_t par_next, const EvRec &rec, Acc &acc) {
+  Send sd;
+  send_begin(v, par_next, rec, acc, sd);
+  send_end(v, par_next, acc, sd);
 }
 
 DEVA_HD void pq_store(const View &v, uint32_t lp, uint32_t slot, const EvRec &e) {
@@ -541,6 +565,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   } else if (na_log > 0 || n_pool_anti > 0) acc.err |= ERR_ANTI_UNMATCHED;
 
   // ---- phase 4: execute the working set in (time, subtime) order --------------------------------
+  Send sd; sd.route = 0;   // the previous event's child, its inbox-slot claim still in flight
   while (!wk.empty()) {
     if (ln == v.log_cap) {   // undo log full: leave the rest pending (they stay below GVT's reach)
 #pragma unroll 1
@@ -566,9 +591,11 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
       if (!mp.user_subtime) c.sub = seq;   // event_subtime / next_seq_id, pdes.hxx:513-526,676
       seq += v.lp_n;
       if ((uint64_t)c.dst == gid) place(c);
-      else deliver(v, par_next, c, acc);
+      else { send_end(v, par_next, acc, sd); send_begin(v, par_next, c, acc, sd); }
     }
   }
+
+  send_end(v, par_next, acc, sd);
 
   // ---- phase 5: close the remaining holes, write back --------------------------------------------
   while (hole) {
