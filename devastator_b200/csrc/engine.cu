@@ -611,6 +611,7 @@ static int launch_pass(deva_b200_engine *e, const PassArgs &pa, uint32_t list_n)
     using M = decltype(m);
     switch (e->pass_variant) {
       case 4: k_pass<M, 4><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa, list_n); break;
+      case 5: k_pass<M, 5><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa, list_n); break;
       case 8: k_pass<M, 8><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa, list_n); break;
       default: k_pass<M, 6><<<grid, PASS_THREADS, 0, e->stream>>>(e->v, e->mp, pa, list_n); break;
     }

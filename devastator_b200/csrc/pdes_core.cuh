@@ -78,6 +78,7 @@ DEVA_HD void st_log(LogRec *p, const LogRec &l) {
   reinterpret_cast<uint4 *>(p)[0] = make_uint4((uint32_t)l.time, (uint32_t)(l.time >> 32), (uint32_t)l.sub, (uint32_t)(l.sub >> 32));
   reinterpret_cast<uint4 *>(p)[1] = make_uint4(l.p0, l.fl, (uint32_t)l.st[0], (uint32_t)(l.st[0] >> 32));
   reinterpret_cast<uint4 *>(p)[2] = make_uint4((uint32_t)l.st[1], (uint32_t)(l.st[1] >> 32), (uint32_t)l.st[2], (uint32_t)(l.st[2] >> 32));
+  reinterpret_cast<uint4 *>(p)[3] = make_uint4(0u, 0u, 0u, 0u);   // padding: completes the second 32-byte sector
 }
 DEVA_HD uint64_t ld_u64(const uint64_t *p) { return DEVA_LD(reinterpret_cast<const unsigned long long *>(p)); }
 DEVA_HD int ffs64(uint64_t x) { return __ffsll((long long)x); }
@@ -311,7 +312,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   if (ln > 0) {
     // Entries are fetched PF at a time (independent 16-byte loads of (time, sub), all in flight
     // together): with epochs nearly everything an LP ran in the previous window commits here.
-    constexpr int PF = 8;
+    constexpr int PF = 4;
     uint64_t lct = v.lct[lp], lcs = v.lcs[lp];
     bool any = false;
     while (ln > 0) {
@@ -393,7 +394,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   // warp), reduced to a bitmask of the slots below the window bound.
   uint64_t inwin = 0;
   {
-    constexpr int CH = 16;
+    constexpr int CH = 8;
     for (uint32_t base = 0; base < np; base += CH) {
       uint64_t tt[CH];
 #pragma unroll
@@ -420,8 +421,8 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   };
   while (inwin) {
     constexpr int RB = 4;
-    uint32_t ss[RB];
-    EvRec ee[RB];
+    uint32_t ss[4];
+    EvRec ee[4];
 #pragma unroll
     for (int i = 0; i < RB; i++) {
       ss[i] = inwin ? (uint32_t)ffs64(inwin) - 1u : 0xffffffffu;
@@ -444,12 +445,13 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
         if (na < DEVA_AN_CAP) an[na++] = e; else { put_pending(e); anti_overflow |= e.time < pa.ub; }
       } else place(e);
     };
-    for (uint32_t base = 0; base < ni; base += 4) {
+    constexpr int IB = 4;
+    for (uint32_t base = 0; base < ni; base += IB) {
       EvRec ee[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) if (base + i < ni) ee[i] = ld_ev(&v.ib[pa.par][(size_t)(base + i) * A + lp]);
+      for (int i = 0; i < IB; i++) if (base + i < ni) ee[i] = ld_ev(&v.ib[pa.par][(size_t)(base + i) * A + lp]);
 #pragma unroll 1
-      for (int i = 0; i < 4 && base + i < ni; i++) fold_arrival(sel4(ee, i));
+      for (int i = 0; i < IB && base + i < ni; i++) fold_arrival(sel4(ee, i));
     }
     v.icnt[pa.par][lp] = 0;
   }
@@ -579,6 +581,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     uint32_t li = lt + ln; if (li >= v.log_cap) li -= v.log_cap;
     LogRec lr;
     lr.time = e.time; lr.sub = e.sub; lr.p0 = e.p0;
+    lr._pad[0] = lr._pad[1] = 0;
 #pragma unroll
     for (int w = 0; w < MAX_STW; w++) lr.st[w] = w < M::STW ? st[w] : 0;
     EvRec c;
