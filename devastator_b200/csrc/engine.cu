@@ -630,7 +630,7 @@ static int run_pass(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t swe
                     uint64_t *p_exec, uint64_t *p_rolled, uint64_t *p_woken, uint64_t *p_emit_min) {
   View &v = e->v;
   PassArgs pa;
-  pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa._pad = 0;
+  pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa.full = full ? 1u : 0u;
   const uint32_t list_n = full ? 0u : e->h_ctl->wake_n[e->par];
   const bool ran = full || list_n > 0;
   CU(cudaMemsetAsync(v.ctl->gvt_slot, 0xff, sizeof(v.ctl->gvt_slot), e->stream));

@@ -273,7 +273,8 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   const uint32_t lm = v.lmeta[lp];
   uint32_t ln = lm & 0xffffu, lt = lm >> 16;
   const bool active = head0 < pa.ub || ni > 0;
-  if (!active && !(pa.sweep && ln > 0)) {
+  const bool collect = pa.full && ln > 0;   // full pass: every LP with a log commits what lies below GVT
+  if (!active && !collect) {
     if (head0 < acc.tmin) acc.tmin = head0;
     return;
   }
@@ -284,7 +285,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   // ---- fold-only path: the LP was woken by arrivals that all lie beyond the window (the common
   // case in a follow-up pass): move them to the pool, lower the head, touch nothing else.
   if (ni > v.ib_cap) ni = v.ib_cap;   // (arrivals beyond the inbox capacity went to the spill buffer)
-  if (head0 >= pa.ub && ni > 0 && ni <= 4 && !pa.sweep && np + ni <= v.pq_cap) {
+  if (head0 >= pa.ub && ni > 0 && ni <= 4 && !collect && np + ni <= v.pq_cap) {
     EvRec ee[4];
     bool plain = true;
 #pragma unroll
@@ -309,7 +310,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   // ---- phase 0: fossil collection - commit log entries with time < GVT (pdes.cxx:816-871) -------
   // The first PF tail entries are fetched together (independent loads in flight), the rare rest
   // one by one.
-  if (ln > 0) {
+  if (collect) {
     // Entries are fetched PF at a time (independent 16-byte loads of (time, sub), all in flight
     // together): with epochs nearly everything an LP ran in the previous window commits here.
     constexpr int PF = 4;

@@ -122,7 +122,8 @@ struct PassArgs {
   uint32_t par;      // inbox parity read this window (arrivals are written to par^1)
   uint32_t sweep;    // final pass of a drain: every LP fossil-collects and folds its inbox
   uint32_t tag;      // pass serial number (wake-list dedup)
-  uint32_t _pad;
+  uint32_t full;     // the epoch's full pass (visits every LP): the only pass that fossil-collects - GVT does not
+                     // move between the passes of one epoch, so a follow-up pass would find nothing new to commit
 };
 
 }  // namespace deva_b200

@@ -212,7 +212,7 @@ static int pass_all(deva_b200_engine **es, int G, uint64_t gvt, uint64_t ub, uin
     deva_b200_engine *e = es[g];
     e->ctl.gvt_slot[0][0] = ~0ull;
     PassArgs &pa = pas[g];
-    pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa._pad = 0;
+    pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa.full = full ? 1u : 0u;
     uint64_t wx, wr;
     pass_one(e, pa, full, &wx, &wr);
     *wx_sum += wx; *wr_sum += wr;
@@ -345,7 +345,7 @@ int emu_pass_begin(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t swee
   e->gvt = gvt;
   e->ctl.gvt_slot[0][0] = ~0ull;
   PassArgs &pa = g_step_pa;
-  pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa._pad = 0;
+  pa.gvt = gvt; pa.ub = ub; pa.par = e->par; pa.sweep = sweep; pa.tag = ++e->pass_tag; pa.full = full ? 1u : 0u;
   pass_one(e, pa, full != 0, wx, wr);
   if (e->ctl.spill_n > e->v.spill_cap) return fail(DEVA_B200_ERR_CAPACITY, "spill overflow");
   for (uint32_t i = 0; i < e->ctl.spill_n; i++) deliver_between_passes(e->v, e->v.spill[i], pa, &e->ctl.err);
