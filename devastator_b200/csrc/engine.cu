@@ -258,6 +258,9 @@ struct deva_b200_engine {
   // multi-GPU
   void *comm = nullptr;
   EvRec *recvbuf = nullptr;
+  EvRec *p2p_buf = nullptr;        // this GPU's receive buffer for peer delivery (peers store into it over NVLink)
+  uint32_t *p2p_cnt = nullptr;     // its slot-claim counter
+  std::vector<void *> ipc_open;    // peer mappings to close
   uint32_t *d_counts = nullptr;    // [2][MAX_GPUS]: send counts row, recv counts row
   uint32_t *h_counts = nullptr;    // pinned
   unsigned long long *h_red = nullptr;  // pinned: allreduce results
@@ -370,13 +373,21 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   DA(e->d_digest, 4)
   if (cfg->n_gpus > 1) {
     // staging sized for one window's worth of cross-GPU records per peer
-    v.send_cap = (uint32_t)std::min<size_t>(std::max<size_t>(A * 4, 1u << 16), 1u << 27);
+    // records one pass may send to one peer (staged) / receive from all peers (peer delivery): 8 per
+    // owned LP by default - a start-up window that runs all 16 roots of every LP at 50 % remote on 2
+    // GPUs needs ~4.5; overflow is reported (DEVA_B200_ERR_CAPACITY), never dropped
+    size_t per_lp = 8;
+    if (const char *sc = getenv("DEVA_B200_SEND_CAP_PER_LP")) per_lp = std::max<size_t>(1, strtoull(sc, nullptr, 10));
+    v.send_cap = (uint32_t)std::min<size_t>(std::max<size_t>(A * per_lp, 1u << 16), 1u << 27);
     DA(v.sendbuf, (size_t)v.send_cap * cfg->n_gpus)
     DA(e->recvbuf, (size_t)v.send_cap * cfg->n_gpus)
+    DA(e->p2p_buf, (size_t)v.send_cap)
+    DA(e->p2p_cnt, 64)
+    CU(cudaMemset(e->p2p_cnt, 0, 64 * sizeof(uint32_t)));
     DA(e->d_counts, MAX_GPUS * MAX_GPUS)
-    DA(e->d_red, 16)
+    DA(e->d_red, 32 + 8 * MAX_GPUS)
     CU(cudaHostAlloc((void **)&e->h_counts, MAX_GPUS * MAX_GPUS * sizeof(uint32_t), cudaHostAllocDefault));
-    CU(cudaHostAlloc((void **)&e->h_red, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void **)&e->h_red, 8 * MAX_GPUS * sizeof(unsigned long long), cudaHostAllocDefault));
   }
 #undef DA
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -410,6 +421,7 @@ void deva_b200_destroy(deva_b200_engine *e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void *p : e->ipc_open) cudaIpcCloseMemHandle(p);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto &p : e->snap_pairs) cudaFree(p.second);
   for (void *p : e->allocs) cudaFree(p);
@@ -586,7 +598,7 @@ static int exchange(deva_b200_engine *e, const PassArgs &pa) {
   return 0;
 }
 
-// One small allreduce set per pass (replaces gvt.cxx rdxn_up/rdxn_down): min of the GVT candidate,
+// One small reduction per pass (replaces gvt.cxx rdxn_up/rdxn_down): min of the GVT candidate,
 // sums of executed / rolled-back / woken-LP counts (window policy, epoch completion), max of errors.
 static int allreduce_pass(deva_b200_engine *e, bool pack_on_device, uint32_t par_next,
                           uint64_t *gvt, uint64_t *exec_sum, uint64_t *rolled_sum, uint64_t *woken_sum, uint32_t *err_or) {
@@ -594,13 +606,21 @@ static int allreduce_pass(deva_b200_engine *e, bool pack_on_device, uint32_t par
   unsigned long long h[5] = {*gvt, ~(unsigned long long)*err_or, *exec_sum, *rolled_sum, *woken_sum};
   if (pack_on_device) { k_pack_red<<<1, 32, 0, e->stream>>>(e->v, par_next, e->d_red); e->launches++; CU(cudaGetLastError()); }
   else CU(cudaMemcpyAsync(e->d_red, h, sizeof h, cudaMemcpyHostToDevice, e->stream));
-  NC(g_nccl.AllReduce(e->d_red, e->d_red + 8, 2, NC_U64, NC_MIN, e->comm, e->stream));
-  NC(g_nccl.AllReduce(e->d_red + 2, e->d_red + 10, 3, NC_U64, NC_SUM, e->comm, e->stream));
-  CU(cudaMemcpyAsync(e->h_red, e->d_red + 8, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+  // ONE collective: every rank's five values to every rank (8 u64 per rank), folded on the host -
+  // a min and a sum in the same round instead of two allreduces
+  const int G = e->cfg.n_gpus;
+  NC(g_nccl.AllGather(e->d_red, e->d_red + 32, 8, NC_U64, e->comm, e->stream));
+  CU(cudaMemcpyAsync(e->h_red, e->d_red + 32, (size_t)G * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaMemcpyAsync(e->h_ctl, e->v.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   e->sum = fold_ctl(e->h_ctl);
-  *gvt = e->h_red[0]; *err_or = (uint32_t)~e->h_red[1]; *exec_sum = e->h_red[2]; *rolled_sum = e->h_red[3]; *woken_sum = e->h_red[4];
+  unsigned long long r[5] = {~0ull, ~0ull, 0, 0, 0};
+  for (int g = 0; g < G; g++) {
+    const unsigned long long *row = e->h_red + (size_t)g * 8;
+    r[0] = std::min(r[0], row[0]); r[1] = std::min(r[1], row[1]);
+    r[2] += row[2]; r[3] += row[3]; r[4] += row[4];
+  }
+  *gvt = r[0]; *err_or = (uint32_t)~r[1]; *exec_sum = r[2]; *rolled_sum = r[3]; *woken_sum = r[4];
   return 0;
 }
 
@@ -666,7 +686,17 @@ static int run_pass(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t swe
     e->launches++;
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(&v.ctl->spill_n, 0, sizeof(uint32_t), e->stream));
-    if ((rc = exchange(e, pa))) return rc;
+    if (v.peer_cap) {
+      // peer delivery: the records are already in the destination GPUs' receive buffers.  One tiny
+      // allreduce orders "every GPU's kernel has finished" before anybody reads its buffer; the
+      // counter is cleared before this GPU joins the pass's closing allreduces, i.e. before any peer
+      // can start the next pass.
+      NC(g_nccl.AllReduce(e->d_red + 16, e->d_red + 17, 1, NC_U64, NC_SUM, e->comm, e->stream));
+      k_deliver<<<148, 256, 0, e->stream>>>(v, e->p2p_buf, e->p2p_cnt, v.peer_cap, pa);
+      e->launches++;
+      CU(cudaGetLastError());
+      CU(cudaMemsetAsync(e->p2p_cnt, 0, sizeof(uint32_t), e->stream));
+    } else if ((rc = exchange(e, pa))) return rc;
     uint32_t err = 0;
     uint64_t cx = 0, cr = 0;
     emit_min = ~0ull; woken = 0;
@@ -846,6 +876,44 @@ int deva_b200_comm_init(deva_b200_engine *e, const void *uid128) {
   NcclUid uid;
   memcpy(uid.b, uid128, 128);
   NC(g_nccl.CommInitRank(&e->comm, e->cfg.n_gpus, uid, e->cfg.gpu_rank));
+  // Peer delivery: map every peer's receive buffer + counter with CUDA IPC (one process per GPU).
+  // DEVA_B200_XCHG=nccl keeps the staged exchange (sendbuf + NCCL send/recv); so does a box where
+  // the mapping fails on any rank (agreed by an allreduce), with a note on stderr.
+  const char *x = getenv("DEVA_B200_XCHG");
+  if (x && !strcmp(x, "nccl")) return 0;
+  const int G = e->cfg.n_gpus, me = e->cfg.gpu_rank;
+  struct Handles { cudaIpcMemHandle_t buf, cnt; };
+  static_assert(sizeof(Handles) == 128, "two 64-byte IPC handles");
+  Handles mine;
+  unsigned long long ok = 1;
+  if (cudaIpcGetMemHandle(&mine.buf, e->p2p_buf) != cudaSuccess || cudaIpcGetMemHandle(&mine.cnt, e->p2p_cnt) != cudaSuccess) {
+    ok = 0; memset(&mine, 0, sizeof mine); cudaGetLastError();
+  }
+  Handles *d_all = nullptr;
+  CU(cudaMalloc((void **)&d_all, sizeof(Handles) * (G + 1)));
+  CU(cudaMemcpyAsync(d_all + G, &mine, sizeof mine, cudaMemcpyHostToDevice, e->stream));
+  NC(g_nccl.AllGather(d_all + G, d_all, sizeof(Handles), NC_U8, e->comm, e->stream));
+  std::vector<Handles> all(G);
+  CU(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * G, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  cudaFree(d_all);
+  View &v = e->v;
+  for (int g = 0; g < G && ok; g++) {
+    if (g == me) { v.peer_buf[g] = e->p2p_buf; v.peer_cnt[g] = e->p2p_cnt; continue; }
+    void *pb = nullptr, *pc = nullptr;
+    if (cudaIpcOpenMemHandle(&pb, all[g].buf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    e->ipc_open.push_back(pb);
+    if (cudaIpcOpenMemHandle(&pc, all[g].cnt, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    e->ipc_open.push_back(pc);
+    v.peer_buf[g] = (EvRec *)pb; v.peer_cnt[g] = (uint32_t *)pc;
+  }
+  unsigned long long h[2] = {ok, 0};
+  CU(cudaMemcpyAsync(e->d_red + 16, h, sizeof h, cudaMemcpyHostToDevice, e->stream));
+  NC(g_nccl.AllReduce(e->d_red + 16, e->d_red + 17, 1, NC_U64, NC_MIN, e->comm, e->stream));
+  CU(cudaMemcpyAsync(h, e->d_red + 17, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  if (h[0]) v.peer_cap = v.send_cap;
+  else if (me == 0) fprintf(stderr, "deva_b200: CUDA IPC peer mapping unavailable, using the staged NCCL exchange\n");
   return 0;
 }
 

@@ -111,6 +111,13 @@ struct View {
   uint32_t send_cap;
   int32_t n_gpus, gpu_rank;
   uint64_t lp_per_gpu;   // block partition: owner(lp) = lp / lp_per_gpu
+  // peer delivery (one process per GPU, buffers mapped with CUDA IPC over NVLink): a record for an
+  // LP of GPU g is stored straight into g's receive buffer from inside the execute kernel, its slot
+  // claimed with an atomic on a counter that lives on g.  peer_cap == 0: staged exchange instead
+  // (sendbuf + NCCL send/recv after the kernel).
+  EvRec *peer_buf[MAX_GPUS];
+  uint32_t *peer_cnt[MAX_GPUS];
+  uint32_t peer_cap;
   // wake lists: LPs that received a record during a pass are the only ones the follow-up pass visits
   uint32_t *wake[2];
   uint32_t *wmark;       // per-LP tag of the last pass that woke it (dedup for records delivered between passes)
