@@ -102,6 +102,18 @@ __global__ void k_deliver(View v, const EvRec *recs, const uint32_t *n_ptr, uint
   if ((threadIdx.x & 31) == 0 && tmin != ~0ull) atomicMin(&v.ctl->gvt_slot[blockIdx.x % CTL_SLOTS][0], tmin);
 }
 
+// peer delivery: what the other GPUs stored into this GPU's receive buffer (region y = source GPU y,
+// its record count read from the gathered count matrix on the device) -> pending slots
+__global__ void k_deliver_regions(View v, const EvRec *recvbuf, const uint32_t *counts, PassArgs pa) {
+  const uint32_t src = blockIdx.y;
+  if ((int)src == v.gpu_rank) return;
+  const uint32_t c = counts[src * MAX_GPUS + v.gpu_rank];
+  const uint32_t n = c < v.send_cap ? c : v.send_cap;   // (overflow was flagged by the sender)
+  const EvRec *recs = recvbuf + (size_t)src * v.send_cap;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    deliver_between_passes(v, ld_ev(&recs[i]), pa, &v.ctl->err);
+}
+
 // root events given as structure-of-arrays columns (deva_b200_root_events): pack + deliver on the device
 __global__ void k_deliver_soa(View v, const uint64_t *time, const uint64_t *sub, const uint32_t *lp,
                               const uint32_t *payload, uint32_t n) {
@@ -258,8 +270,6 @@ struct deva_b200_engine {
   // multi-GPU
   void *comm = nullptr;
   EvRec *recvbuf = nullptr;
-  EvRec *p2p_buf = nullptr;        // this GPU's receive buffer for peer delivery (peers store into it over NVLink)
-  uint32_t *p2p_cnt = nullptr;     // its slot-claim counter
   std::vector<void *> ipc_open;    // peer mappings to close
   uint32_t *d_counts = nullptr;    // [2][MAX_GPUS]: send counts row, recv counts row
   uint32_t *h_counts = nullptr;    // pinned
@@ -381,9 +391,6 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
     v.send_cap = (uint32_t)std::min<size_t>(std::max<size_t>(A * per_lp, 1u << 16), 1u << 27);
     DA(v.sendbuf, (size_t)v.send_cap * cfg->n_gpus)
     DA(e->recvbuf, (size_t)v.send_cap * cfg->n_gpus)
-    DA(e->p2p_buf, (size_t)v.send_cap)
-    DA(e->p2p_cnt, 64)
-    CU(cudaMemset(e->p2p_cnt, 0, 64 * sizeof(uint32_t)));
     DA(e->d_counts, MAX_GPUS * MAX_GPUS)
     DA(e->d_red, 32 + 8 * MAX_GPUS)
     CU(cudaHostAlloc((void **)&e->h_counts, MAX_GPUS * MAX_GPUS * sizeof(uint32_t), cudaHostAllocDefault));
@@ -687,15 +694,16 @@ static int run_pass(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t swe
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(&v.ctl->spill_n, 0, sizeof(uint32_t), e->stream));
     if (v.peer_cap) {
-      // peer delivery: the records are already in the destination GPUs' receive buffers.  One tiny
-      // allreduce orders "every GPU's kernel has finished" before anybody reads its buffer; the
-      // counter is cleared before this GPU joins the pass's closing allreduces, i.e. before any peer
-      // can start the next pass.
-      NC(g_nccl.AllReduce(e->d_red + 16, e->d_red + 17, 1, NC_U64, NC_SUM, e->comm, e->stream));
-      k_deliver<<<148, 256, 0, e->stream>>>(v, e->p2p_buf, e->p2p_cnt, v.peer_cap, pa);
+      // peer delivery: the records are already in the destination GPUs' receive buffers.  The
+      // all-gather of the send counts tells every GPU how many records each peer stored for it and
+      // orders "every GPU's kernel has finished" before anybody reads its buffer - no host round
+      // trip.  This GPU joins the pass's closing collective only after its delivery kernel, so no
+      // peer can start the next pass (and overwrite the regions) before they are consumed.
+      NC(g_nccl.AllGather(v.ctl->send_n, e->d_counts, MAX_GPUS, NC_U32, e->comm, e->stream));
+      k_deliver_regions<<<dim3(64, (unsigned)e->cfg.n_gpus), 256, 0, e->stream>>>(v, e->recvbuf, e->d_counts, pa);
       e->launches++;
       CU(cudaGetLastError());
-      CU(cudaMemsetAsync(e->p2p_cnt, 0, sizeof(uint32_t), e->stream));
+      CU(cudaMemsetAsync(v.ctl->send_n, 0, sizeof(v.ctl->send_n), e->stream));
     } else if ((rc = exchange(e, pa))) return rc;
     uint32_t err = 0;
     uint64_t cx = 0, cr = 0;
@@ -876,36 +884,30 @@ int deva_b200_comm_init(deva_b200_engine *e, const void *uid128) {
   NcclUid uid;
   memcpy(uid.b, uid128, 128);
   NC(g_nccl.CommInitRank(&e->comm, e->cfg.n_gpus, uid, e->cfg.gpu_rank));
-  // Peer delivery: map every peer's receive buffer + counter with CUDA IPC (one process per GPU).
+  // Peer delivery: map every peer's receive buffer with CUDA IPC (one process per GPU).
   // DEVA_B200_XCHG=nccl keeps the staged exchange (sendbuf + NCCL send/recv); so does a box where
   // the mapping fails on any rank (agreed by an allreduce), with a note on stderr.
   const char *x = getenv("DEVA_B200_XCHG");
   if (x && !strcmp(x, "nccl")) return 0;
   const int G = e->cfg.n_gpus, me = e->cfg.gpu_rank;
-  struct Handles { cudaIpcMemHandle_t buf, cnt; };
-  static_assert(sizeof(Handles) == 128, "two 64-byte IPC handles");
-  Handles mine;
+  cudaIpcMemHandle_t mine;
   unsigned long long ok = 1;
-  if (cudaIpcGetMemHandle(&mine.buf, e->p2p_buf) != cudaSuccess || cudaIpcGetMemHandle(&mine.cnt, e->p2p_cnt) != cudaSuccess) {
-    ok = 0; memset(&mine, 0, sizeof mine); cudaGetLastError();
-  }
-  Handles *d_all = nullptr;
-  CU(cudaMalloc((void **)&d_all, sizeof(Handles) * (G + 1)));
+  if (cudaIpcGetMemHandle(&mine, e->recvbuf) != cudaSuccess) { ok = 0; memset(&mine, 0, sizeof mine); cudaGetLastError(); }
+  cudaIpcMemHandle_t *d_all = nullptr;
+  CU(cudaMalloc((void **)&d_all, sizeof(mine) * (G + 1)));
   CU(cudaMemcpyAsync(d_all + G, &mine, sizeof mine, cudaMemcpyHostToDevice, e->stream));
-  NC(g_nccl.AllGather(d_all + G, d_all, sizeof(Handles), NC_U8, e->comm, e->stream));
-  std::vector<Handles> all(G);
-  CU(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * G, cudaMemcpyDeviceToHost, e->stream));
+  NC(g_nccl.AllGather(d_all + G, d_all, sizeof(mine), NC_U8, e->comm, e->stream));
+  std::vector<cudaIpcMemHandle_t> all(G);
+  CU(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * G, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   cudaFree(d_all);
   View &v = e->v;
   for (int g = 0; g < G && ok; g++) {
-    if (g == me) { v.peer_buf[g] = e->p2p_buf; v.peer_cnt[g] = e->p2p_cnt; continue; }
-    void *pb = nullptr, *pc = nullptr;
-    if (cudaIpcOpenMemHandle(&pb, all[g].buf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    if (g == me) { v.peer_buf[g] = nullptr; continue; }
+    void *pb = nullptr;
+    if (cudaIpcOpenMemHandle(&pb, all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
     e->ipc_open.push_back(pb);
-    if (cudaIpcOpenMemHandle(&pc, all[g].cnt, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
-    e->ipc_open.push_back(pc);
-    v.peer_buf[g] = (EvRec *)pb; v.peer_cnt[g] = (uint32_t *)pc;
+    v.peer_buf[g] = (EvRec *)pb + (size_t)me * v.send_cap;   // this GPU's region in g's receive buffer
   }
   unsigned long long h[2] = {ok, 0};
   CU(cudaMemcpyAsync(e->d_red + 16, h, sizeof h, cudaMemcpyHostToDevice, e->stream));

@@ -95,17 +95,6 @@ __device__ __forceinline__ uint32_t agg_claim(uint32_t *ctr, uint32_t key) {
   base = __shfl_sync(peers, base, leader);
   return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 }
-// the same on a counter that lives in ANOTHER GPU's memory (system-scope atomic over NVLink)
-__device__ __forceinline__ uint32_t agg_claim_sys(uint32_t *ctr, uint32_t key) {
-  const unsigned act = __activemask();
-  const unsigned peers = __match_any_sync(act, key);
-  const int leader = __ffs(peers) - 1;
-  const int lane = threadIdx.x & 31;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd_system(ctr, (uint32_t)__popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-}
 #else
 DEVA_HD uint32_t atom_add_u32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 DEVA_HD void atom_or_u32(uint32_t *p, uint32_t v) { *p |= v; }
@@ -122,7 +111,6 @@ DEVA_HD uint64_t ld_u64(const uint64_t *p) { return *p; }
 DEVA_HD int ffs64(uint64_t x) { return __builtin_ffsll((long long)x); }
 DEVA_HD int ffs32(uint32_t x) { return __builtin_ffs((int)x); }
 DEVA_HD uint32_t agg_claim(uint32_t *ctr, uint32_t) { return atom_add_u32(ctr, 1); }
-DEVA_HD uint32_t agg_claim_sys(uint32_t *ctr, uint32_t) { return atom_add_u32(ctr, 1); }
 #endif
 
 DEVA_HD bool key_less(uint64_t t1, uint64_t s1, uint64_t t2, uint64_t s2) {  // stamped_event::operator<, pdes.hxx:936-941
@@ -234,13 +222,9 @@ DEVA_HD void send_begin(const View &v, uint32_t par_next, const EvRec &rec, Acc 
     if (dl >= v.A) { acc.err |= ERR_NOT_OWNER; sd.route = 0; return; }
     sd.slot = atom_add_u32(&v.icnt[par_next][dl], 1u);
     sd.route = 1;
-  } else if (v.peer_cap) {
-    sd.slot = agg_claim_sys(v.peer_cnt[g], g);
-    sd.route = 3;
-    acc.remote++;
   } else {
     sd.slot = agg_claim(&v.ctl->send_n[g], g);
-    sd.route = 2;
+    sd.route = v.peer_cap ? 3u : 2u;
     acc.remote++;
   }
 }

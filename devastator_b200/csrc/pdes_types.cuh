@@ -112,11 +112,11 @@ struct View {
   int32_t n_gpus, gpu_rank;
   uint64_t lp_per_gpu;   // block partition: owner(lp) = lp / lp_per_gpu
   // peer delivery (one process per GPU, buffers mapped with CUDA IPC over NVLink): a record for an
-  // LP of GPU g is stored straight into g's receive buffer from inside the execute kernel, its slot
-  // claimed with an atomic on a counter that lives on g.  peer_cap == 0: staged exchange instead
-  // (sendbuf + NCCL send/recv after the kernel).
-  EvRec *peer_buf[MAX_GPUS];
-  uint32_t *peer_cnt[MAX_GPUS];
+  // LP of GPU g is stored straight into THIS GPU's region of g's receive buffer from inside the
+  // execute kernel (posted 32-byte stores; the slot is claimed on the local counter send_n[g], so
+  // no atomic crosses the link).  peer_cap == 0: staged exchange instead (sendbuf + NCCL send/recv
+  // after the kernel).
+  EvRec *peer_buf[MAX_GPUS];   // peer_buf[g] = &recvbuf_of_g[gpu_rank * send_cap]
   uint32_t peer_cap;
   // wake lists: LPs that received a record during a pass are the only ones the follow-up pass visits
   uint32_t *wake[2];
