@@ -140,8 +140,12 @@ int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]);
  * caller: events must be recorded on the launching stream). */
 void *deva_b200_stream(deva_b200_engine *e);
 
-/* Multi-GPU (replaces world_gasnet / threads transports and gvt.cxx's credit-counted reduction
- * with a per-window NCCL exchange + min-allreduce).  uid = 128-byte ncclUniqueId made by rank 0. */
+/* Multi-GPU (replaces world_gasnet / threads transports and gvt.cxx's credit-counted reduction).
+ * uid = 128-byte ncclUniqueId made by rank 0.  With one process per GPU the engines map each other's
+ * receive buffers (CUDA IPC) and the execute kernel stores cross-GPU records straight into the
+ * destination GPU's memory over NVLink; NCCL then carries only two small all-gathers per pass
+ * (record counts; GVT candidate + counters).  Environment DEVA_B200_XCHG=nccl, or engines that share
+ * a process, select the staged transport instead (per-peer buffers + grouped ncclSend/ncclRecv). */
 int deva_b200_comm_unique_id(void *uid128);
 int deva_b200_comm_init(deva_b200_engine *e, const void *uid128);
 
