@@ -377,7 +377,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   DA(v.st, A * e->stw) DA(v.seq, A) DA(v.lct, A) DA(v.lcs, A)
   DA(v.pq_t, A * v.pq_cap) DA(v.pq_r, A * v.pq_cap) DA(v.ib[0], A * v.ib_cap) DA(v.ib[1], A * v.ib_cap) DA(v.lg, A * v.log_cap)
   DA(v.ctl, 1)
-  DA(v.wake[0], A) DA(v.wake[1], A) DA(v.wmark, A)
+  DA(v.wake[0], A) DA(v.wake[1], A) DA(v.wmark, A) DA(v.panti, A)
   v.spill_cap = (uint32_t)std::min<size_t>(std::max<size_t>(A * 2, 1u << 16), 1u << 26);
   DA(v.spill, v.spill_cap)
   DA(e->d_digest, 4)
@@ -806,6 +806,10 @@ int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uin
     uint64_t wx = 0, wr = 0, woken = 0, em = 0;
     if ((rc = run_pass(e, e->gvt, t_end, 1, true, &wx, &wr, &woken, &em))) return rc;
     if (wx != 0 || woken != 0) return fail(DEVA_B200_ERR_INVARIANT, "events executed during the final sweep");
+    // the sweep may have annihilated positive / anti pairs that were still pending beyond t_end (and
+    // bounded the GVT from below until now): the value returned is the exact minimum (pdes.cxx:878-886)
+    if ((rc = exact_gvt(e, &gvt))) return rc;
+    e->gvt = gvt;
   }
   CU(cudaEventRecord(e->ev_d1, e->stream));
   CU(cudaEventSynchronize(e->ev_d1));
@@ -832,6 +836,7 @@ int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind) {
       CU(cudaMemcpyAsync(e->snap_pairs[i].first, e->snap_pairs[i].second, e->snap_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaMemsetAsync(e->v.icnt[0], 0, e->v.A * 4, e->stream));
     CU(cudaMemsetAsync(e->v.icnt[1], 0, e->v.A * 4, e->stream));
+    CU(cudaMemsetAsync(e->v.panti, 0, e->v.A * 4, e->stream));
     CU(cudaMemsetAsync(e->v.lmeta, 0, e->v.A * 4, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->gvt = e->snap_gvt;

@@ -276,7 +276,10 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   uint32_t ln = lm & 0xffffu, lt = lm >> 16;
   const bool active = head0 < pa.ub || ni > 0;
   const bool collect = pa.full && ln > 0;   // full pass: every LP with a log commits what lies below GVT
-  if (!active && !collect) {
+  // final sweep of a drain: anti-messages that were put straight into the pool and still lie beyond
+  // every window so far are matched now, so that no positive / anti pair is left pending at the pause
+  const uint32_t pool_antis = pa.sweep ? v.panti[lp] : 0u;
+  if (!active && !collect && !pool_antis) {
     if (head0 < acc.tmin) acc.tmin = head0;
     return;
   }
@@ -287,7 +290,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   // ---- fold-only path: the LP was woken by arrivals that all lie beyond the window (the common
   // case in a follow-up pass): move them to the pool, lower the head, touch nothing else.
   if (ni > v.ib_cap) ni = v.ib_cap;   // (arrivals beyond the inbox capacity went to the spill buffer)
-  if (head0 >= pa.ub && ni > 0 && ni <= 4 && !collect && np + ni <= v.pq_cap) {
+  if (head0 >= pa.ub && ni > 0 && ni <= 4 && !collect && !pool_antis && np + ni <= v.pq_cap) {
     EvRec ee[4];
     bool plain = true;
 #pragma unroll
@@ -346,7 +349,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     }
     if (any) { v.lct[lp] = lct; v.lcs[lp] = lcs; }
   }
-  if (!active) {
+  if (!active && !pool_antis) {
     v.lmeta[lp] = ln | (lt << 16);
     if (head0 < acc.tmin) acc.tmin = head0;
     return;
@@ -409,11 +412,21 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
       }
     }
   }
+  if (pool_antis) {   // (sweep only) every anti-message in the pool, whatever its time, joins this pass's list
+#pragma unroll 1
+    for (uint32_t s = 0; s < np; s++) {
+      if ((inwin >> s) & 1ull) continue;   // in-window slots are fetched below anyway
+      const PqRest r = ld_rest(&v.pq_r[(size_t)s * A + lp]);
+      if (r.p1f & P1_ANTI) inwin |= 1ull << s;
+    }
+    v.panti[lp] = 0;
+    khead_dirty = true;   // khead was computed over slots that may now leave the pool
+  }
   // Stage B: the records of the in-window slots, fetched four at a time (loads issued together).
   auto fold_pool_record = [&](const EvRec &e, uint32_t s) {
     if (e.flags & EV_ANTI) {
       if (na < DEVA_AN_CAP) { an[na++] = e; take_slot(s); }
-      else { anti_overflow = true; if (e.time < khead) khead = e.time; }
+      else { anti_overflow = true; if (e.time < khead) khead = e.time; if (e.time >= pa.ub) v.panti[lp] = 1; }
     } else {
       EvRec out;
       const int r = wk.insert(e, out, gid32);
@@ -445,7 +458,8 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     if (ni > v.ib_cap) ni = v.ib_cap;
     auto fold_arrival = [&](const EvRec &e) {
       if (e.flags & EV_ANTI) {
-        if (na < DEVA_AN_CAP) an[na++] = e; else { put_pending(e); anti_overflow |= e.time < pa.ub; }
+        if (na < DEVA_AN_CAP) an[na++] = e;
+        else { put_pending(e); anti_overflow |= e.time < pa.ub || pool_antis; if (e.time >= pa.ub) v.panti[lp] = 1; }
       } else place(e);
     };
     constexpr int IB = 4;
@@ -493,7 +507,7 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
     for (uint32_t s = 0; s < top; s++) {
       if ((hole >> s) & 1ull) continue;
       const uint64_t t = v.pq_t[(size_t)s * A + lp];
-      if (t >= pa.ub) continue;
+      if (t >= pa.ub && !pool_antis) continue;   // (the final sweep matches anti-messages of any time)
       const EvRec a = pq_load(v, lp, s, t, gid32);
       if (!(a.flags & EV_ANTI)) continue;
       if (wk.remove_match(a) || remove_pending(a)) { take_slot(s); khead_dirty = true; continue; }
@@ -639,6 +653,7 @@ DEVA_HD void deliver_to_pending(const View &v, const EvRec &rec, uint32_t *err) 
   if (slot >= v.pq_cap) { atom_or_u32(err, ERR_PQ_OVERFLOW); return; }
   pq_store(v, dl, slot, rec);
   atom_min_u64(&v.head[dl], rec.time);
+  if (rec.flags & EV_ANTI) atom_add_u32(&v.panti[dl], 1u);
 }
 
 // deliver_to_pending + wake: a record that lands below the window bound between passes (inbox spill,
@@ -665,6 +680,7 @@ DEVA_HD void init_lp(const View &v, const ModelParams &mp, uint32_t lp, int init
   v.pcnt[lp] = 0;
   v.icnt[0][lp] = 0;
   v.icnt[1][lp] = 0;
+  v.panti[lp] = 0;
   v.lmeta[lp] = 0;
   v.seq[lp] = gid;      // pdes.cxx:332: seq_id_bumper = global_cd_begin + i
   v.lct[lp] = 0;        // pdes.cxx:333

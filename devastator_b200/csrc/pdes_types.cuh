@@ -121,6 +121,9 @@ struct View {
   // wake lists: LPs that received a record during a pass are the only ones the follow-up pass visits
   uint32_t *wake[2];
   uint32_t *wmark;       // per-LP tag of the last pass that woke it (dedup for records delivered between passes)
+  uint32_t *panti;       // per-LP count of anti-messages put straight into the pending pool between passes (inbox
+                         // spill, records from peer GPUs): beyond the window they meet their positive only when
+                         // their time comes - or in the drain's final sweep, which looks for them if this is set
 };
 
 struct PassArgs {

@@ -36,6 +36,8 @@ def emu_api():
     api = E.Api(ctypes.CDLL(so))
     api.lib.emu_set_shuffle.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
     api.lib.emu_set_shuffle.restype = None
+    api.lib.emu_enable_peer_delivery.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
+    api.lib.emu_enable_peer_delivery.restype = None
     api.lib.emu_drain_multi.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_uint64, ctypes.c_int32,
                                         ctypes.POINTER(ctypes.c_uint64)]
     return api

@@ -46,6 +46,7 @@ struct deva_b200_engine {
   std::vector<std::vector<char>> snap;
   uint64_t snap_gvt = 0;
   uint64_t shuffle = 1;   // LP visiting order seed
+  EvRec *recvbuf = nullptr;   // peer delivery: region g = records stored by engine g (as comm_init maps them in engine.cu)
   uint32_t pass_tag = 0;
   uint64_t wake_min = 0;
   std::vector<EvRec> recv;
@@ -110,13 +111,14 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   halloc(e, &v.lmeta, A); halloc(e, &v.st, A * e->stw); halloc(e, &v.seq, A); halloc(e, &v.lct, A); halloc(e, &v.lcs, A);
   halloc(e, &v.pq_t, A * v.pq_cap); halloc(e, &v.pq_r, A * v.pq_cap); halloc(e, &v.ib[0], A * v.ib_cap); halloc(e, &v.ib[1], A * v.ib_cap);
   halloc(e, &v.lg, A * v.log_cap);
-  halloc(e, &v.wake[0], A); halloc(e, &v.wake[1], A); halloc(e, &v.wmark, A);
+  halloc(e, &v.wake[0], A); halloc(e, &v.wake[1], A); halloc(e, &v.wmark, A); halloc(e, &v.panti, A);
   v.ctl = &e->ctl;
   v.spill_cap = (uint32_t)std::max<size_t>(A * 2, 1u << 12);
   halloc(e, &v.spill, v.spill_cap);
   if (cfg->n_gpus > 1) {
     v.send_cap = (uint32_t)std::max<size_t>(A * 4, 1u << 12);
     halloc(e, &v.sendbuf, (size_t)v.send_cap * cfg->n_gpus);
+    halloc(e, &e->recvbuf, (size_t)v.send_cap * cfg->n_gpus);
   }
   init_lps(e, 0);
   e->wp.init(cfg->window);
@@ -227,7 +229,10 @@ static int pass_all(deva_b200_engine **es, int G, uint64_t gvt, uint64_t ub, uin
       deva_b200_engine *s = es[g], *r = es[d];
       const uint32_t n = s->ctl.send_n[d];
       if (n > s->v.send_cap) return fail(DEVA_B200_ERR_CAPACITY, "send overflow");
-      for (uint32_t i = 0; i < n; i++) deliver_between_passes(r->v, s->v.sendbuf[(size_t)d * s->v.send_cap + i], pas[d], &r->ctl.err);
+      // staged: the sender's buffer for peer d; peer delivery: region g of the receiver's buffer, where
+      // the sender's lp_pass stored the records itself (k_deliver_regions in engine.cu)
+      const EvRec *recs = s->v.peer_cap ? r->recvbuf + (size_t)g * r->v.send_cap : s->v.sendbuf + (size_t)d * s->v.send_cap;
+      for (uint32_t i = 0; i < n; i++) deliver_between_passes(r->v, recs[i], pas[d], &r->ctl.err);
       s->ctl.send_n[d] = 0;
     }
   *woken = 0;
@@ -285,6 +290,8 @@ int emu_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewind
   int rc = pass_all(es, G, gvt, t_end, 1, true, &wx, &wr, &woken, &em);
   if (rc) return rc;
   if (wx || woken) return fail(DEVA_B200_ERR_INVARIANT, "events executed during the final sweep");
+  gvt = exact_gvt_all(es, G);   // pairs annihilated by the sweep no longer bound it (see deva_b200_drain)
+  for (int g = 0; g < G; g++) es[g]->gvt = gvt;
   // post-conditions the reference asserts at drain exit (pdes.cxx:1020-1035)
   for (int g = 0; g < G; g++)
     for (uint32_t lp = 0; lp < es[g]->v.A; lp++) {
@@ -307,7 +314,7 @@ int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind) {
     View &v = e->v;
     void *live[] = {v.head, v.pcnt, v.st, v.seq, v.lct, v.lcs, v.pq_t, v.pq_r};
     for (size_t i = 0; i < e->snap.size(); i++) memcpy(live[i], e->snap[i].data(), e->snap[i].size());
-    memset(v.icnt[0], 0, v.A * 4); memset(v.icnt[1], 0, v.A * 4); memset(v.lmeta, 0, v.A * 4);
+    memset(v.icnt[0], 0, v.A * 4); memset(v.icnt[1], 0, v.A * 4); memset(v.lmeta, 0, v.A * 4); memset(v.panti, 0, v.A * 4);
     e->gvt = e->snap_gvt;
   }
   return 0;
@@ -331,6 +338,14 @@ int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]) {
 int deva_b200_comm_unique_id(void *uid128) { memset(uid128, 0, 128); return 0; }
 int deva_b200_comm_init(deva_b200_engine *, const void *) { return 0; }
 void emu_set_shuffle(deva_b200_engine *e, uint64_t seed) { e->shuffle = seed; }
+// what deva_b200_comm_init does with CUDA IPC: every engine gets a pointer to ITS region of every
+// peer's receive buffer, and lp_pass stores cross-GPU records there directly
+void emu_enable_peer_delivery(deva_b200_engine **es, int G) {
+  for (int g = 0; g < G; g++) {
+    for (int d = 0; d < G; d++) es[g]->v.peer_buf[d] = d == g ? nullptr : es[d]->recvbuf + (size_t)g * es[d]->v.send_cap;
+    es[g]->v.peer_cap = es[g]->v.send_cap;
+  }
+}
 
 // ---- stepping interface: one engine per PROCESS, exchange done by the caller (gloo test) ----------
 // Mirrors run_window()/drain() of engine.cu piece by piece so that a multi-process driver can put a

@@ -18,19 +18,24 @@ def drain_multi(api, engs, t_end=E.T_INF, rewindable=False):
     return gvt.value
 
 
-def make_group(api, G, A, **kw):
+def make_group(api, G, A, peer=False, **kw):
     per = (A + G - 1) // G
-    return [E.Engine(E.MODEL_PHOLD_TEST, A, lp_begin=g * per, lp_count=min(per, A - g * per), n_gpus=G, gpu_rank=g,
+    engs = [E.Engine(E.MODEL_PHOLD_TEST, A, lp_begin=g * per, lp_count=min(per, A - g * per), n_gpus=G, gpu_rank=g,
                      api=api, **kw) for g in range(G)]
+    if peer:   # records stored straight into the destination engine's receive buffer (deva_b200_comm_init's IPC mapping)
+        arr = (C.c_void_p * G)(*[e.h for e in engs])
+        api.lib.emu_enable_peer_delivery(arr, G)
+    return engs
 
 
+@pytest.mark.parametrize("peer", [False, True], ids=["staged", "peer"])
 @pytest.mark.parametrize("G", [2, 4, 8])
 @pytest.mark.parametrize("window", [1, 20, 0])
 @pytest.mark.parametrize("P", [0.1, 0.5])
-def test_partitioned_equals_oracle(emu_api, G, window, P):
+def test_partitioned_equals_oracle(emu_api, G, window, P, peer):
     A, K, LAM, END = 1000, 16, 100.0, 300
     o, ost = O.run(A, K, P, LAM, END)
-    engs = make_group(emu_api, G, A, window=window, p_remote=P, lam=LAM, end_time=END)
+    engs = make_group(emu_api, G, A, peer=peer, window=window, p_remote=P, lam=LAM, end_time=END)
     for e in engs:
         e.seed_phold(K, 1, 1)
     gvt = drain_multi(emu_api, engs)
@@ -49,7 +54,7 @@ def test_partitioned_equals_oracle(emu_api, G, window, P):
 def test_partitioned_default_subtime_and_rewind(emu_api):
     """test/phold.cxx on 2 GPUs x (virtual ranks = 4): sequence-id tiebreak, drain/rewind thirds."""
     A, K, P, LAM, END, ranks, G = 1000, 2, 0.5, 100.0, 10000, 4, 2
-    engs = make_group(emu_api, G, A, window=0, p_remote=P, lam=LAM, end_time=END, user_subtime=0)
+    engs = make_group(emu_api, G, A, peer=True, window=0, p_remote=P, lam=LAM, end_time=END, user_subtime=0)
     for e in engs:
         e.seed_phold(K, 0, ranks)
     t0, dt = 0, END // 3

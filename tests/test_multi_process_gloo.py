@@ -109,6 +109,7 @@ def _worker(rank, world, port, cfg, ret):
         assert windows < 100000
     wx, _, woken, _ = _pass(api, eng, rank, world, gvt, t_end, 1, True)     # final sweep
     assert wx == 0 and woken == 0
+    gvt = _u64_min(api.lib.emu_local_min_head(eng.h))   # exact: the sweep may have annihilated pending pairs
     st = torch.from_numpy(eng.get_state().astype(np.int64))
     pad = torch.zeros((per, 3), dtype=torch.int64); pad[:cnt] = st
     gathered = [torch.zeros_like(pad) for _ in range(world)]
