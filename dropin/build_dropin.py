@@ -4,6 +4,7 @@
 
     /root/reference/test/phold.cxx   -> dropin/_bin/phold_test_R<R>     (self-checking: "Looks good!")
     /root/reference/bench/phold.cxx  -> dropin/_bin/phold_bench_R<R>    (prints a report row)
+    /root/reference/test/gvt-test.cxx -> dropin/_bin/gvt_test_R<R>      (host-rank GVT service, asserts on: "SUCCESS")
 
 The sources are compiled where they lie under /root/reference (never copied).  The only additions
 on the build line are -I include and the force-included model binding header.  Outputs are
@@ -26,6 +27,9 @@ APPS = [
     # (name, source under the reference, model header, extra reference sources, rank counts)
     ("phold_test", "test/phold.cxx", "devastator_b200/models/phold_test_model.hxx", [], [2, 8]),
     ("phold_bench", "bench/phold.cxx", "devastator_b200/models/phold_bench_model.hxx", ["bench/util/report.cxx"], [1, 4, 8]),
+    # no device model: drives deva::gvt (include/devastator/gvt.hxx) directly; built with the asserts of the
+    # test enabled (DEBUG=1), they are what checks that the GVT never overtakes a message
+    ("gvt_test", "test/gvt-test.cxx", None, [], [2, 3, 8]),
 ]
 
 
@@ -49,8 +53,10 @@ def main():
             srcs = [os.path.join(REF, src)] + [os.path.join(REF, e) for e in extra]
             if not (force or newer(exe, srcs + hdrs + [RUNTIME, os.path.join(LIBDIR, "libdeva_b200.so"), __file__])):
                 continue
+            dbg = ["-DDEBUG=1"] if model is None else ["-DDEBUG=0", "-DNDEBUG=1"]
+            inc_model = [] if model is None else ["-include", os.path.join(INC, model)]
             cmd = ["g++", "-std=c++14", "-O2", "-pthread", "-w", f"-DDEVA_THREAD_N={R}", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1",
-                   "-DDEBUG=0", "-DNDEBUG=1", f"-I{INC}", f"-I{os.path.join(REF, 'bench')}", "-include", os.path.join(INC, model),
+                   *dbg, f"-I{INC}", f"-I{os.path.join(REF, 'bench')}", *inc_model,
                    *srcs, RUNTIME, f"-L{LIBDIR}", "-ldeva_b200", "-Wl,-rpath,$ORIGIN/../../devastator_b200", "-o", exe]
             r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             if r.returncode != 0:

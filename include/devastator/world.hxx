@@ -41,8 +41,13 @@ namespace upcxx { namespace detail {
     Ret (*call_)(void*, Arg...) = nullptr;
   public:
     function_ref() = default;
+    // a plain function (deva::run_and_die(tmain), test/gvt-test.cxx:91)
+    function_ref(Ret (&fn)(Arg...)):
+      obj_(reinterpret_cast<void*>(&fn)),
+      call_([](void *o, Arg ...a)->Ret { return reinterpret_cast<Ret(*)(Arg...)>(o)(static_cast<Arg>(a)...); }) {}
     template<typename Fn, typename = typename std::enable_if<
-               !std::is_same<typename std::decay<Fn>::type, function_ref>::value>::type>
+               !std::is_same<typename std::decay<Fn>::type, function_ref>::value &&
+               !std::is_function<typename std::remove_reference<Fn>::type>::value>::type>
     function_ref(Fn &&fn):
       obj_(const_cast<void*>(static_cast<const void*>(&fn))),
       call_([](void *o, Arg ...a)->Ret { return (*static_cast<typename std::remove_reference<Fn>::type*>(o))(static_cast<Arg>(a)...); }) {}

@@ -73,3 +73,18 @@ def test_reference_phold_bench_source_on_gpu(R):
     ys = dict(kv.split("=") for kv in m.group(2).replace(" ", "").split(","))
     assert float(ys["deterministic"]) == 1
     assert float(ys["commit_per_rank_per_sec"]) > 0
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+@pytest.mark.parametrize("R", [2, 3, 8])
+def test_reference_gvt_test_source_through_gvt_mirror(tmp_path, R):
+    """test/gvt-test.cxx, unchanged, against include/devastator/gvt.hxx (host-rank GVT service; no
+    engine, no GPU).  Built with the test's own asserts on (`epoch_gvt() <= t` at every send and
+    arrival): it ends only if the GVT reaches ~0 and every one of rank_n*100*t_end orbits landed."""
+    exe = str(tmp_path / f"gvt_test_R{R}")
+    subprocess.check_call([
+        "g++", "-std=c++14", "-O2", "-pthread", "-w", f"-DDEVA_THREAD_N={R}", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1",
+        "-DDEBUG=1", f"-I{ROOT}/include", f"{REF}/test/gvt-test.cxx", f"{ROOT}/devastator_b200/csrc/host_runtime.cpp",
+        f"-L{ROOT}/devastator_b200", "-ldeva_b200", f"-Wl,-rpath,{ROOT}/devastator_b200", "-o", exe])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "SUCCESS", out.stdout
