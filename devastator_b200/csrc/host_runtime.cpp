@@ -107,7 +107,10 @@ namespace deva { namespace detail {
     { std::lock_guard<std::mutex> l(*w.mail_mu[t_rank]); mine.swap(w.mail[t_rank]); }
     for(auto &f: mine) f();
   }
-  void world_barrier() {
+  // barrier(deaf = false) keeps running incoming active messages while it waits, as the reference's
+  // does (world_threads.hxx:102-125, threads.hxx barrier): a rank that is already waiting must still
+  // serve the ranks that are not (test/send_vlen.cxx relies on it for its acks)
+  void world_barrier(bool deaf) {
     World &w = g_world;
     if(w.n <= 1) { world_progress(); return; }
     const std::uint64_t gen = w.bar_gen.load(std::memory_order_acquire);
@@ -118,11 +121,13 @@ namespace deva { namespace detail {
     else {
       int spins = 0;
       while(w.bar_gen.load(std::memory_order_acquire) == gen) {
+        if(!deaf) world_progress();
         if(++spins > 64) { sched_yield(); }
       }
     }
     world_progress();
   }
+  void world_barrier() { world_barrier(false); }
   void **world_slots() { return g_world.slots.data(); }
   void world_post(int rank, std::function<void()> fn) {
     World &w = g_world;

@@ -68,6 +68,7 @@ namespace deva {
     void world_run(int n, void (*tramp)(void*), void *ctx);
     int world_rank_me();
     void world_barrier();
+    void world_barrier(bool deaf);
     void **world_slots();                       // one pointer per rank, for reductions
     void world_post(int rank, std::function<void()> fn);
     void world_progress();
@@ -86,12 +87,12 @@ namespace deva {
   constexpr int process_rank_hi(int = 0) { return rank_n; }
 
   inline void progress(bool /*spinning*/ = false) { detail::world_progress(); }
-  inline void barrier(bool /*deaf*/ = false) { detail::world_barrier(); }
+  inline void barrier(bool deaf = false) { detail::world_barrier(deaf); }
 
   // bind(fn, b...) -> callable applying fn(b..., args...)  (world_threads.hxx:60-99)
   template<typename Fn, typename ...B>
   struct bound {
-    Fn fn_;
+    mutable Fn fn_;
     mutable std::tuple<B...> b_;
     template<std::size_t ...i, typename ...Arg>
     auto apply_(std::index_sequence<i...>, Arg &&...a) const

@@ -88,3 +88,19 @@ def test_reference_gvt_test_source_through_gvt_mirror(tmp_path, R):
         f"-L{ROOT}/devastator_b200", "-ldeva_b200", f"-Wl,-rpath,{ROOT}/devastator_b200", "-o", exe])
     out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == "SUCCESS", out.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+@pytest.mark.parametrize("app,expect", [("barrier", "quitting"), ("bcast", "done"), ("send_ring", "SUCCESS"),
+                                        ("send_vlen", "send/recv n = 3000 3000")])
+def test_reference_world_tests_through_world_mirror(tmp_path, app, expect):
+    """The reference's own tests of the SPMD world surface (run, barrier, send, bcast_procs, progress,
+    reductions), unchanged, against include/devastator/world.hxx + host_runtime.cpp at 3 ranks.
+    Their asserts are built in (DEBUG=1); send_vlen checks payload bytes, epochs and counts itself."""
+    exe = str(tmp_path / app)
+    subprocess.check_call([
+        "g++", "-std=c++14", "-O2", "-pthread", "-w", "-DDEVA_THREAD_N=3", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1",
+        "-DDEBUG=1", f"-I{ROOT}/include", f"{REF}/test/{app}.cxx", f"{ROOT}/devastator_b200/csrc/host_runtime.cpp",
+        f"-L{ROOT}/devastator_b200", "-ldeva_b200", f"-Wl,-rpath,{ROOT}/devastator_b200", "-o", exe])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert out.returncode == 0 and expect in out.stdout, out.stdout[-2000:]
