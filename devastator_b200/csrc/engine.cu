@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -282,7 +283,34 @@ struct deva_b200_engine {
   char *stage = nullptr;  // grow-only device staging for host-buffer calls (no cudaMalloc/cudaFree per call)
   size_t stage_bytes = 0;
   uint64_t wake_min = 0;  // stop an epoch's follow-up passes when no more than this many LPs (job-wide) are woken
+  // drain timer (the counterpart of the reference's DrainTimer, pdes.hxx:139-308): one row per epoch,
+  // i.e. per stretch of simulated time, written as CSV when DEVA_B200_DRAIN_TIMER=<path prefix> is set
+  struct TimerRow { uint64_t gvt, ub, executed, rolled_back, woken_left; uint32_t window, passes; double full_ms, followup_ms, gvt_ms, wall_ms; };
+  std::string timer_path;
+  std::vector<TimerRow> timer_rows;
+  float last_pass_ms = 0;
 };
+
+static double wall_ms_since(std::chrono::steady_clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// drain_timer.<rank>.csv next to the reference's drain_timer.{wall,sim}.<rank>.csv: time spent per
+// category, binned by simulated time (one bin = one epoch).  "execute" splits into the full pass and
+// the follow-up passes; rolled_back / executed is the share of it that was wasted (the reference's
+// execute_rb); exchange + host = wall - full - followup - gvt.
+static void dump_drain_timer(deva_b200_engine *e) {
+  if (e->timer_path.empty() || e->timer_rows.empty()) return;
+  const std::string path = e->timer_path + "." + std::to_string(e->cfg.gpu_rank) + ".csv";
+  FILE *f = fopen(path.c_str(), "a");
+  if (!f) return;
+  if (ftell(f) == 0) fprintf(f, "sim_time,window_end,window,passes,executed,rolled_back,woken_left,execute_full_ms,execute_followup_ms,gvt_ms,wall_ms\n");
+  for (const auto &r : e->timer_rows)
+    fprintf(f, "%llu,%llu,%u,%u,%llu,%llu,%llu,%.4f,%.4f,%.4f,%.4f\n", (unsigned long long)r.gvt, (unsigned long long)r.ub, r.window, r.passes,
+            (unsigned long long)r.executed, (unsigned long long)r.rolled_back, (unsigned long long)r.woken_left, r.full_ms, r.followup_ms, r.gvt_ms, r.wall_ms);
+  fclose(f);
+  e->timer_rows.clear();
+}
 
 template <class T>
 static int dalloc(deva_b200_engine *e, T **p, size_t n) {
@@ -417,6 +445,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   const char *prof = getenv("DEVA_B200_PROFILE");
   if (prof) e->profile = atoi(prof) != 0;
   if (const char *pv = getenv("DEVA_B200_PASS_MINB")) e->pass_variant = atoi(pv);
+  if (const char *tp = getenv("DEVA_B200_DRAIN_TIMER")) { e->timer_path = tp; e->profile = true; }
   e->wake_min = cfg->lp_n / 32;   // measured: flat on one GPU, fewer peer exchanges on several
   if (const char *wm = getenv("DEVA_B200_WAKE_MIN")) e->wake_min = strtoull(wm, nullptr, 10);
   // snapshot list for rewind
@@ -713,7 +742,8 @@ static int run_pass(deva_b200_engine *e, uint64_t gvt, uint64_t ub, uint32_t swe
     e->g_exec = cx; e->g_rolled = cr;
     e->sum.err |= err;
   }
-  if (e->profile && ran) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->exec_ms += ms; }
+  e->last_pass_ms = 0;
+  if (e->profile && ran) { float ms = 0; CU(cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->exec_ms += ms; e->last_pass_ms = ms; }
   if ((rc = check_ctl_err(e))) return rc;
   e->par ^= 1u;
   *p_exec = wx; *p_rolled = wr; *p_woken = woken; *p_emit_min = emit_min;
@@ -780,19 +810,31 @@ int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uin
   while (e->gvt < t_end) {
     const uint64_t ub = e->wp.upper_bound(e->gvt, t_end);
     const uint64_t gvt_before = e->gvt;
+    const bool timing = !e->timer_path.empty();
+    const auto t_epoch = std::chrono::steady_clock::now();
+    deva_b200_engine::TimerRow row{};
     uint64_t ex = 0, rb = 0, woken = 0, px = 0, pr = 0, emit_min = ~0ull;
     if ((rc = run_pass(e, e->gvt, ub, 0, true, &px, &pr, &woken, &emit_min))) return rc;
     ex += px; rb += pr;
+    row.full_ms = e->last_pass_ms; row.passes = 1;
     int guard = 0;
     // follow-up passes while enough LPs are woken to be worth a launch (and a peer exchange); the
     // few left over are simply visited by the next epoch's full pass
     while (woken > e->wake_min) {
       if ((rc = run_pass(e, e->gvt, ub, 0, false, &px, &pr, &woken, &emit_min))) return rc;
       ex += px; rb += pr;
+      row.followup_ms += e->last_pass_ms; row.passes++;
       if (++guard > 100000) return fail(DEVA_B200_ERR_INVARIANT, "epoch does not converge");
     }
+    const auto t_gvt = std::chrono::steady_clock::now();
     if ((rc = exact_gvt(e, &gvt))) return rc;
     e->gvt = woken > 0 && emit_min < gvt ? emit_min : gvt;
+    if (timing) {
+      row.gvt = gvt_before; row.ub = ub; row.window = (uint32_t)std::min<uint64_t>(ub - gvt_before, 0xffffffffu);
+      row.executed = ex; row.rolled_back = rb; row.woken_left = woken;
+      row.gvt_ms = wall_ms_since(t_gvt); row.wall_ms = wall_ms_since(t_epoch);
+      e->timer_rows.push_back(row);
+    }
     e->wp.update(ex, rb);
     // progress guard: GVT frozen and nothing executed for many epochs == the undo log cannot
     // drain (more same-time events at one LP than log_cap)
@@ -816,6 +858,7 @@ int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uin
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, e->ev_d0, e->ev_d1));
   e->drain_ms += ms;
+  dump_drain_timer(e);
   // fold counters into the cumulative statistics (pdes::local_stats)
   e->executed = e->sum.executed; e->committed = e->sum.committed; e->rolled = e->sum.rolled_back;
   e->anti = e->sum.anti_sent; e->remote = e->sum.remote_sent;
