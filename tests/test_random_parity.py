@@ -91,3 +91,81 @@ def test_random_partitioned_config_matches_oracle(emu_api, G, A, K, P, LAM, END,
         assert chk == o["checksum"]
     finally:
         os.environ.pop("DEVA_B200_WAKE_MIN", None)
+
+
+@settings(max_examples=int(os.environ.get("DEVA_TEST_EXAMPLES", 100)), deadline=None,
+          derandomize="DEVA_TEST_EXAMPLES" not in os.environ,
+          suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(lp_per_rank=st.integers(1, 96), R=st.sampled_from([1, 2, 4]), K=st.integers(1, 4), END=st.integers(0, 60000),
+       window=st.sampled_from([0, 1, 500, 5000, 100000]), stddev=st.sampled_from([0.5, 2.0, 8.0]),
+       inbox_cap=st.sampled_from([16, 2]), wake_min=st.sampled_from(["0", "100000"]), drain_frac=st.sampled_from([None, 0.4]))
+def test_random_bench_model_matches_oracle(emu_api, lp_per_rank, R, K, END, window, stddev, inbox_cap, wake_min, drain_frac):
+    """bench/phold.cxx's model (xorshift rng, Box-Muller destination, lambda = 10000), made reproducible by
+    an end time: default tiebreak = per-LP sequence ids, root subtime = local LP index."""
+    import numpy as np
+    os.environ["DEVA_B200_WAKE_MIN"] = wake_min
+    try:
+        A = lp_per_rank * R
+        drain_end = S.E.T_INF if drain_frac is None else int(END * drain_frac)
+        o, ost = O.run(A, K, 0.0, 10000.0, END, model=O.MODEL_BENCH, ranks=R, user_subtime=0, rootdiv=0,
+                       bench_lp_per_rank=lp_per_rank, bench_peer_stddev=stddev, drain_end=drain_end)
+        eng = S.E.Engine(S.E.MODEL_PHOLD_BENCH, A, window=window, lam=10000.0, end_time=END, user_subtime=0,
+                         bench_lp_per_rank=lp_per_rank, bench_peer_stddev=stddev, inbox_cap=inbox_cap, api=emu_api)
+        eng.seed_phold(K, 0, R)
+        gvt = eng.drain(drain_end)
+        s = eng.stats()
+        if o["deterministic"]:
+            assert s["committed_n"] == o["commits"] and gvt == o["gvt"] and s["deterministic"] == 1
+            np.testing.assert_array_equal(eng.get_state(), ost[:, :2])
+            assert eng.digest()["pending"] == o["pending"]
+        else:
+            assert s["deterministic"] == 0
+        eng.close()
+    except S.E.EngineError as ex:
+        if ex.code == -3 and inbox_cap != 16:
+            assume(False)
+        raise
+    finally:
+        os.environ.pop("DEVA_B200_WAKE_MIN", None)
+
+
+@settings(max_examples=int(os.environ.get("DEVA_TEST_EXAMPLES", 80)), deadline=None,
+          derandomize="DEVA_TEST_EXAMPLES" not in os.environ,
+          suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(A=st.integers(2, 150), K=st.integers(1, 6), P=st.sampled_from([0.1, 0.5]), LAM=st.sampled_from([10.0, 100.0]),
+       END=st.integers(50, 400), window=st.sampled_from([0, 3, 40, 1000]),
+       cuts=st.lists(st.floats(0.05, 0.95), min_size=1, max_size=3), replays=st.lists(st.integers(0, 2), min_size=4, max_size=4),
+       inbox_cap=st.sampled_from([16, 1]))
+def test_random_pause_rewind_resume_matches_oracle(emu_api, A, K, P, LAM, END, window, cuts, replays, inbox_cap):
+    """drain(t, rewindable) / rewind(true) / drain again / rewind(false) at random pause points
+    (test/phold.cxx:180-198 does it at thirds): after every segment the engine must stand exactly where the
+    oracle stands after one uninterrupted run to that point; statistics are NOT rewound (Appendix A.7)."""
+    import numpy as np
+    points = sorted({int(END * c) for c in cuts}) + [S.E.T_INF]
+    if not O.run(A, K, P, LAM, END)[0]["deterministic"]:
+        return
+    eng = S.make(emu_api, A, P=P, LAM=LAM, END=END, window=window, inbox_cap=inbox_cap)
+    eng.seed_phold(K, 1, 1)
+    expect_commits, prev = 0, 0
+    try:
+        for i, t in enumerate(points):
+            o, ost = O.run(A, K, P, LAM, END, drain_end=t)
+            seg = o["commits"] - prev
+            for _ in range(replays[i % 4]):      # run the segment, throw it away
+                eng.drain(t, rewindable=True)
+                eng.rewind(True)
+                expect_commits += seg
+            gvt = eng.drain(t, rewindable=True)
+            eng.rewind(False)
+            expect_commits += seg
+            prev = o["commits"]
+            np.testing.assert_array_equal(eng.get_state(), ost)
+            d = eng.digest()
+            assert gvt == o["gvt"] and d["pending"] == o["pending"] and d["checksum"] == o["checksum"]
+            assert eng.stats()["committed_n"] == expect_commits
+    except S.E.EngineError as ex:   # see test_random_config_matches_oracle
+        if ex.code == -3 and (inbox_cap != 16 or (window or 16) / LAM > 8):
+            assume(False)
+        raise
+    finally:
+        eng.close()
