@@ -6,7 +6,7 @@
 //   remove_past / rollback             pdes.cxx:517-693   -> phases 2-3
 //   arrive_near<+-1>, arrive_far[_anti] pdes.cxx:393-493  -> phase 1 (inbox fold) + phase 2
 //   fossil collection / commit sweep   pdes.cxx:816-871   -> phase 0
-//   execute_context::send              pdes.hxx:666-732   -> deliver()
+//   execute_context::send              pdes.hxx:666-732   -> send_begin() / send_end()
 //   cd_state::next_seq_id              pdes.cxx:221-225   -> seq += N / seq -= N
 //
 // One thread owns one LP for the whole window, so everything of that LP (pending slots, undo-log

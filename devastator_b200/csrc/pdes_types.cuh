@@ -54,8 +54,6 @@ static_assert(sizeof(PqRest) == 16, "PqRest must be 16 bytes");
 constexpr int MAX_PQ_CAP = 64;   // free-slot bitmask of an LP's pending pool is one u64
 
 constexpr int MAX_STW = 3;
-// 48 B of content padded to 64 B = two whole 32-byte DRAM sectors per record: an append then
-// overwrites whole sectors, and L2 never has to fetch the old contents of a ring slot to merge.
 // 48 B of content padded to 64 B = two whole 32-byte DRAM sectors per record: an append overwrites
 // whole sectors, so L2 never has to fetch the old contents of a ring slot to merge (measured +4 %).
 struct DEVA_ALIGN(16) LogRec {
