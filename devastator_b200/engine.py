@@ -113,10 +113,14 @@ def load():
 
 
 def remote_thresh(p_remote):
-    """uint64_t(percent_remote*double(-1ull)) as x86-64 g++ evaluates it (test/phold.cxx:119)."""
+    """uint64_t(percent_remote*double(-1ull)) as g++ evaluates it in the reference (test/phold.cxx:119).
+    percent_remote is a compile-time constant there, so the conversion is constant-folded: for
+    p = 1.0 the product is 2^64, out of range, and GCC folds it to the saturated 2^64-1 (the
+    run-time cvttsd2si sequence would give 0; checked with g++ 13.3 and pinned by the reference
+    binary's golden `allrem`, tests/golden/ref_goldens.json)."""
     x = float(p_remote) * 18446744073709551616.0
     if x >= 18446744073709551616.0:
-        return 0  # cvttsd2si overflow path, matches the reference binary for p = 1.0
+        return 2**64 - 1
     return int(x)
 
 

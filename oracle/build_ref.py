@@ -62,6 +62,13 @@ PHOLD_T_CONFIGS = {
     "small":  dict(A=1000,    K=16, P=0.10, LAMBDA=100, END=300,  sub=1, rootdiv=1),
     "smallq": dict(A=1000,    K=16, P=0.50, LAMBDA=100, END=300,  sub=1, rootdiv=1),
     "seqid":  dict(A=1000,    K=2,  P=0.5,  LAMBDA=100, END=10000, sub=0, rootdiv=0),  # == test/phold.cxx
+    # more parameter regimes, only to pin the oracle against the reference (tests/test_oracle.py)
+    "allrem": dict(A=257,     K=3,  P=1.0,  LAMBDA=50,  END=500,  sub=1, rootdiv=1),   # every child leaves its LP, odd A
+    "norem":  dict(A=300,     K=5,  P=0.0,  LAMBDA=20,  END=400,  sub=1, rootdiv=1),   # no child ever does
+    "dense":  dict(A=500,     K=8,  P=0.3,  LAMBDA=5,   END=150,  sub=1, rootdiv=1),   # short delays: many same-time events
+    "seq3":   dict(A=777,     K=3,  P=0.25, LAMBDA=100, END=3000, sub=0, rootdiv=0),   # sequence-id tiebreak, A % ranks != 0
+    "rayt":   dict(A=2000,    K=1,  P=0.5,  LAMBDA=200, END=2000, sub=1, rootdiv=0),   # root time = ray id
+    "wide":   dict(A=20000,   K=8,  P=0.5,  LAMBDA=100, END=200,  sub=1, rootdiv=1),
     # SURVEY Appendix B golden: commits 6 241 953, checksum 3349230152040954854
     "mid":    dict(A=100000,  K=16, P=0.10, LAMBDA=100, END=300,  sub=1, rootdiv=1),
     # BASELINE config 2 (1M LPs, 16 ev/LP, 10% remote); END is a run-time env knob (PHOLD_T_END)

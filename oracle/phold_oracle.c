@@ -114,7 +114,11 @@ int phold_oracle_run(const phold_oracle_cfg *c, phold_oracle_out *out, uint64_t 
   const uint64_t per = (A + (uint64_t)R - 1) / (uint64_t)R; /* test/phold.cxx:46 */
   const uint64_t N = per * (uint64_t)R;                     /* pdes.cxx:319-321 */
   const int bench = c->model == PHOLD_ORACLE_MODEL_BENCH;
-  const uint64_t thresh = (uint64_t)(c->p_remote * (double)(-1ull)); /* test/phold.cxx:119 */
+  /* test/phold.cxx:119: uint64_t(percent_remote*double(-1ull)) with a constexpr percent_remote, i.e.
+     folded by the compiler: for p = 1.0 the product is 2^64 and GCC folds the out-of-range conversion
+     to 2^64-1 (a run-time conversion would give 0).  Pinned by the reference golden "allrem". */
+  const double thr_d = c->p_remote * (double)(-1ull);
+  const uint64_t thresh = thr_d >= 18446744073709551616.0 ? ~(uint64_t)0 : (uint64_t)thr_d;
 
   rng_t *rng = (rng_t *)malloc(A * sizeof(rng_t));
   uint64_t *check = (uint64_t *)malloc(A * sizeof(uint64_t));

@@ -59,7 +59,7 @@ def test_reference_phold_test_config(api, ranks, window):
 
 
 # ---- golden fixtures straight from the reference binaries ---------------------------------------
-@pytest.mark.parametrize("tag", ["tiny", "small", "smallq"])
+@pytest.mark.parametrize("tag", ["tiny", "small", "smallq", "allrem", "norem", "dense"])
 def test_against_reference_state_fixture(api, tag):
     g = [x for x in S.goldens()["phold_t"] if x["tag"] == tag and x["drain_end"] == 2**64 - 1][0]
     c = g["cfg"]

@@ -28,7 +28,7 @@ def test_oracle_matches_reference_binary(g):
     assert hashlib.sha256(st.tobytes()).hexdigest() == g["state_sha256"]
 
 
-@pytest.mark.parametrize("tag", ["tiny", "small", "smallq", "seqid"])
+@pytest.mark.parametrize("tag", ["tiny", "small", "smallq", "seqid", "allrem", "norem", "dense", "seq3"])
 def test_oracle_per_lp_state_fixture(tag):
     g = [x for x in S.goldens()["phold_t"] if x["tag"] == tag and x["ranks"] == 2 and x["drain_end"] == 2**64 - 1][0]
     c = g["cfg"]
