@@ -249,6 +249,90 @@ def gen_phold_t():
     return path
 
 
+PHOLD_B_MAIN = r'''
+// ---- driver appended by oracle/build_ref.py (not reference text) --------------------------------
+// PHOLD-B: bench/phold.cxx's model made reproducible - the wall-clock cut-off is replaced by an end
+// time (an event sends its child iff time + dt < PHOLD_B_END; the rng is consumed either way), the
+// report by a JSON line + a dump of every LP's rng state.  Setup as in the reference's main().
+#include <cstdio>
+#include <cstdlib>
+int main() {
+  const char *dump_path = std::getenv("PHOLD_B_DUMP");
+  const char *drain_end_s = std::getenv("PHOLD_B_DRAIN_END");
+  const uint64_t drain_end = drain_end_s ? std::strtoull(drain_end_s, nullptr, 10) : ~uint64_t(0);
+  g_phold_b_end = std::getenv("PHOLD_B_END") ? std::strtoull(std::getenv("PHOLD_B_END"), nullptr, 10) : ~uint64_t(0);
+  static uint64_t *dump = nullptr;
+  auto doit = [&]() {
+    if(deva::rank_me_local() == 0) {
+      lp_per_rank = deva::os_env<int>("lp_per_rank", 1000);
+      ray_per_lp = deva::os_env<int>("ray_per_lp", 2);
+      peer_stddev = deva::os_env<double>("peer_stddev", 2.0);
+      dump = (uint64_t*)std::calloc(size_t(lp_per_rank)*rank_n*2, sizeof(uint64_t));
+    }
+    deva::barrier();
+    pdes::chitter_secs = -1;
+    pdes::init(lp_per_rank);
+    state_cur.reset(new rng_state[lp_per_rank]);
+    for(int cd=0; cd < lp_per_rank; cd++) {
+      int lp = rank_me()*lp_per_rank + cd;
+      state_cur[cd] = rng_state{lp};
+      pdes::register_state(cd, &state_cur[cd]);
+      for(int lp_ray=0; lp_ray < ray_per_lp; lp_ray++) {
+        int ray = lp*ray_per_lp + lp_ray;
+        pdes::root_event(cd, ray, bounce{ray, lp});
+      }
+    }
+    deva::barrier();
+    uint64_t gvt = pdes::drain(drain_end, false);
+    pdes::finalize();
+    pdes::statistics stats = deva::reduce_sum(pdes::local_stats());
+    for(int cd=0; cd < lp_per_rank; cd++) {
+      size_t lp = size_t(rank_me())*lp_per_rank + cd;
+      dump[2*lp+0] = state_cur[cd].a;
+      dump[2*lp+1] = state_cur[cd].b;
+    }
+    deva::barrier();
+    if(deva::rank_me() == 0) {
+      std::printf("{\"ranks\": %d, \"lp_per_rank\": %d, \"ray_per_lp\": %d, \"peer_stddev\": %.17g, "
+                  "\"end_time\": %llu, \"drain_end\": %llu, \"commits\": %llu, \"deterministic\": %d, \"gvt\": %llu}\n",
+                  rank_n, lp_per_rank, ray_per_lp, peer_stddev, (unsigned long long)g_phold_b_end,
+                  (unsigned long long)drain_end, (unsigned long long)stats.committed_n, int(stats.deterministic),
+                  (unsigned long long)gvt);
+      if(dump_path) {
+        FILE *f = std::fopen(dump_path, "wb");
+        std::fwrite(dump, sizeof(uint64_t), size_t(lp_per_rank)*rank_n*2, f);
+        std::fclose(f);
+      }
+    }
+  };
+  deva::run(doit);
+  return 0;
+}
+'''
+
+
+def gen_phold_b():
+    """bench/phold.cxx's model with an end time instead of the wall-clock cut-off (never committed)."""
+    text = open(os.path.join(REF, "bench/phold.cxx")).read()
+    model = text[:text.index("int main()")]
+
+    def sub1(pat, rep, s, flags=re.M):
+        s2, n = re.subn(pat, rep, s, count=1, flags=flags)
+        if n != 1:
+            raise SystemExit(f"oracle/build_ref.py: pattern not found in reference bench/phold.cxx: {pat}")
+        return s2
+    # the cut-off block (bench/phold.cxx:95-104) goes; the send becomes conditional on the end time
+    model = sub1(r"static __thread int skips = 0;.*?\n      \}\n    \}\n", "", model, flags=re.S)
+    model = sub1(r"^(\s*)cxt\.send\(", r"\1if(cxt.time + dt < g_phold_b_end) cxt.send(", model)
+    model = sub1(r"^struct bounce \{", "static uint64_t g_phold_b_end = ~uint64_t(0);\nstruct bounce {", model)
+    os.makedirs(os.path.join(OUT, "gen"), exist_ok=True)
+    path = os.path.join(OUT, "gen", "phold_b.cxx")
+    body = model + PHOLD_B_MAIN
+    if not os.path.exists(path) or open(path).read() != body:
+        open(path, "w").write(body)
+    return path
+
+
 def phold_t_flags(cfg):
     root = "((uint64_t)((ray)/actor_n))" if cfg["rootdiv"] else "((uint64_t)(ray))"
     return [f"-DPHOLD_A={cfg['A']}", f"-DPHOLD_K={cfg['K']}", f"-DPHOLD_P={cfg['P']}",
@@ -259,13 +343,15 @@ def phold_t_flags(cfg):
 def exe_name(kind, R, tag=None):
     if kind == "phold_t":
         return os.path.join(OUT, f"ref_phold_t_{tag}_R{R}")
+    if kind == "phold_b":
+        return os.path.join(OUT, f"ref_phold_b_R{R}")
     return os.path.join(OUT, f"ref_{kind}_R{R}")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ranks", type=int, nargs="*", default=[2, 8])
-    ap.add_argument("--only", default="phold_test,phold_bench,phold_t")
+    ap.add_argument("--only", default="phold_test,phold_bench,phold_t,phold_b")
     ap.add_argument("--tags", default=",".join(PHOLD_T_CONFIGS))
     ap.add_argument("--baseline-ranks", type=int, nargs="*", default=[4, 16, 32, 64])
     ap.add_argument("--force", action="store_true")
@@ -285,6 +371,8 @@ def main():
         if "phold_bench" in only:
             jobs.append((os.path.join(REF, "bench/phold.cxx"), exe_name("phold_bench", R),
                          (os.path.join(REF, "bench/util/report.cxx"),)))
+        if "phold_b" in only:
+            jobs.append((gen_phold_b(), exe_name("phold_b", R), (os.path.join(REF, "bench/util/report.cxx"),)))
         if "phold_t" in only:
             gen = gen_phold_t()
             for tag in tags:

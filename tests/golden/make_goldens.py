@@ -39,6 +39,30 @@ def run_phold_t(tag, R, drain_end=None, end=None):
     return out, st
 
 
+# PHOLD-B: bench/phold.cxx's model with an end time instead of the wall-clock cut-off (build_ref.py gen_phold_b)
+PHOLD_B_CASES = [
+    # (tag, ranks, lp_per_rank, ray_per_lp, peer_stddev, end_time, drain_end)
+    ("b_small", 2, 64, 2, 2.0, 60000, None),
+    ("b_pause", 2, 64, 2, 2.0, 60000, 25000),
+    ("b_narrow", 8, 125, 2, 0.5, 40000, None),
+    ("b_wide", 2, 500, 1, 8.0, 100000, None),
+    ("b_big", 8, 4096, 2, 2.0, 30000, None),
+]
+
+
+def run_phold_b(R, lp_per_rank, ray_per_lp, stddev, end, drain_end):
+    dump = f"/tmp/_golden_dump_b_{os.getpid()}.bin"
+    env = dict(env0, PHOLD_B_DUMP=dump, PHOLD_B_END=str(end), lp_per_rank=str(lp_per_rank), ray_per_lp=str(ray_per_lp),
+               peer_stddev=repr(stddev))
+    if drain_end is not None:
+        env["PHOLD_B_DRAIN_END"] = str(drain_end)
+    out = json.loads(subprocess.check_output([os.path.join(REFDIR, f"ref_phold_b_R{R}")], env=env))
+    st = np.fromfile(dump, dtype=np.uint64).reshape(-1, 2)
+    os.unlink(dump)
+    out["state_sha256"] = hashlib.sha256(st.tobytes()).hexdigest()
+    return out, st
+
+
 def parse_phold_test(text):
     iters = []
     cur = None
@@ -56,7 +80,13 @@ def parse_phold_test(text):
 
 def main():
     gold = {"_about": "printed by the reference's own binaries (oracle/_ref); see make_goldens.py",
-            "phold_t": [], "phold_test": []}
+            "phold_t": [], "phold_test": [], "phold_b": []}
+    for tag, R, per, k, sd, end, de in PHOLD_B_CASES:
+        out, st = run_phold_b(R, per, k, sd, end, de)
+        out["tag"] = tag
+        gold["phold_b"].append(out)
+        if per * R <= 1000 and de is None:
+            np.save(os.path.join(HERE, f"phold_b_{tag}_state.npy"), st)
     for tag, cfg in PHOLD_T_CONFIGS.items():
         if tag == "cfg2":
             continue

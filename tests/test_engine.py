@@ -197,3 +197,18 @@ def test_bench_model_stop_flag(api):
 
 def eng_pending_before(A, K):
     return A * K   # PHOLD keeps the live-event population constant until the cut-off
+
+
+# ---- bench model against fixtures from the reference's own handler code (PHOLD-B, build_ref.py) ----
+@pytest.mark.parametrize("tag", ["b_small", "b_narrow", "b_wide"])
+def test_bench_model_against_reference_state_fixture(api, tag):
+    g = [x for x in S.goldens()["phold_b"] if x["tag"] == tag][0]
+    want = np.load(os.path.join(S.GOLDEN, f"phold_b_{tag}_state.npy"))
+    A = g["lp_per_rank"] * g["ranks"]
+    eng = E.Engine(E.MODEL_PHOLD_BENCH, A, window=0, lam=10000.0, end_time=g["end_time"], user_subtime=0,
+                   bench_lp_per_rank=g["lp_per_rank"], bench_peer_stddev=g["peer_stddev"], api=api)
+    eng.seed_phold(g["ray_per_lp"], 0, g["ranks"])
+    gvt = eng.drain()
+    np.testing.assert_array_equal(eng.get_state(), want)
+    s = eng.stats()
+    assert (s["committed_n"], gvt, s["deterministic"]) == (g["commits"], g["gvt"], 1)

@@ -46,3 +46,15 @@ def test_reference_phold_test_golden():
             assert it["commits"] == (361624 if it["rewind"] else 180812)
     o, _ = O.run(1000, 2, 0.5, 100.0, 10000, ranks=2, user_subtime=0, rootdiv=0)
     assert (o["commits"], o["checksum"], o["deterministic"]) == (180812, 15341107330209340805, 1)
+
+
+@pytest.mark.parametrize("g", S.goldens().get("phold_b", []), ids=lambda g: g["tag"])
+def test_oracle_bench_model_matches_reference_binary(g):
+    """bench/phold.cxx's model (xorshift rng, exponential delay, Box-Muller destination, sequence-id
+    tiebreak) against PHOLD-B: the reference's own handler code compiled with an end time in place of
+    the wall-clock cut-off (oracle/build_ref.py gen_phold_b)."""
+    A = g["lp_per_rank"] * g["ranks"]
+    o, st = O.run(A, g["ray_per_lp"], 0.0, 10000.0, g["end_time"], model=O.MODEL_BENCH, ranks=g["ranks"], user_subtime=0,
+                  rootdiv=0, bench_lp_per_rank=g["lp_per_rank"], bench_peer_stddev=g["peer_stddev"], drain_end=g["drain_end"])
+    assert (o["commits"], o["gvt"], o["deterministic"]) == (g["commits"], g["gvt"], g["deterministic"])
+    assert hashlib.sha256(np.ascontiguousarray(st[:, :2]).tobytes()).hexdigest() == g["state_sha256"]
