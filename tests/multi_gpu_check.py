@@ -28,7 +28,9 @@ def main():
         dist.broadcast(uid, 0)
         return uid.cpu().numpy().tobytes()
     ok_all = True
-    cases = [dict(A=1000, K=16, P=0.5, LAM=100.0, END=300, window=20), dict(A=1000, K=16, P=0.1, LAM=100.0, END=300, window=0),
+    # `pause`: drain(t) first and compare the GVT returned and the pending count at the pause as well (cross-GPU
+    # anti-messages beyond t are matched by the final sweep, so no positive / anti pair may be left to bound the GVT)
+    cases = [dict(A=1000, K=16, P=0.5, LAM=100.0, END=300, window=20, pause=150), dict(A=1000, K=16, P=0.1, LAM=100.0, END=300, window=0),
              dict(A=100000, K=16, P=0.5, LAM=100.0, END=300, window=0), dict(A=100000, K=16, P=0.10, LAM=100.0, END=300, window=32)]
     for c in cases:
         A = c["A"]
@@ -38,6 +40,15 @@ def main():
                        window=c["window"], p_remote=c["P"], lam=c["LAM"], end_time=c["END"])
         eng.comm_init(fresh_uid())
         eng.seed_phold(c["K"], 1, 1)
+        pause_ok = None
+        if c.get("pause"):
+            gvt_p = eng.drain(c["pause"])
+            pend = torch.tensor([eng.digest()["pending"]], dtype=torch.int64, device="cuda")
+            dist.all_reduce(pend)
+            if rank == 0:
+                import oracle_lib as O
+                op, _ = O.run(A, c["K"], c["P"], c["LAM"], c["END"], drain_end=c["pause"])
+                pause_ok = gvt_p == op["gvt"] and int(pend[0]) == op["pending"]
         gvt = eng.drain()
         st = torch.from_numpy(eng.get_state().astype(np.int64)).cuda()
         s = eng.stats()
@@ -51,7 +62,7 @@ def main():
             import oracle_lib as O   # the checker
             o, ost = O.run(A, c["K"], c["P"], c["LAM"], c["END"])
             full = torch.cat(gathered)[:A].cpu().numpy().astype(np.uint64)
-            ok = bool((full == ost).all()) and int(tot[0]) == o["commits"] and gvt == o["gvt"]
+            ok = bool((full == ost).all()) and int(tot[0]) == o["commits"] and gvt == o["gvt"] and pause_ok is not False
             ok_all &= ok
             gold = None
             if A == 100000 and c["P"] == 0.10:   # SURVEY Appendix B golden from the reference binary
