@@ -304,6 +304,7 @@ static void dump_drain_timer(deva_b200_engine *e) {
   const std::string path = e->timer_path + "." + std::to_string(e->cfg.gpu_rank) + ".csv";
   FILE *f = fopen(path.c_str(), "a");
   if (!f) return;
+  fseek(f, 0, SEEK_END);   // (append mode: make the reported position the file size on every libc)
   if (ftell(f) == 0) fprintf(f, "sim_time,window_end,window,passes,executed,rolled_back,woken_left,execute_full_ms,execute_followup_ms,gvt_ms,wall_ms\n");
   for (const auto &r : e->timer_rows)
     fprintf(f, "%llu,%llu,%u,%u,%llu,%llu,%llu,%.4f,%.4f,%.4f,%.4f\n", (unsigned long long)r.gvt, (unsigned long long)r.ub, r.window, r.passes,
