@@ -4,7 +4,7 @@
  * is the C++ template surface of src/devastator/pdes.hxx and its natural cut is the type-erasure
  * point `event_vtable` (pdes.hxx:350-357) plus the per-rank scheduler entry points of pdes.cxx.
  * Each entry point below names the reference interface it replaces.  The C++ mirror of the
- * reference's header surface (include/devastator/*.hxx) is a thin veneer over exactly these calls,
+ * reference's header surface (the .hxx files under include/devastator/) is a thin veneer over these calls,
  * and so is the Python binding (devastator_b200/engine.py).
  *
  * Plain C types only: pointers, sizes, integers.  No exceptions cross it; every call returns 0 on

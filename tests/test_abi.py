@@ -54,3 +54,24 @@ def test_create_fails_loudly_without_gpu():
         assert ex.code == -2 and "no CPU path" in str(ex)
     else:
         raise AssertionError("engine creation must fail without a CUDA device")
+
+
+def test_header_is_plain_c99_and_agrees_with_the_python_binding(tmp_path):
+    """include/deva_b200.h must compile as C (the boundary a cgo / JNI / ctypes binding sees), link against the
+    library, and lay its structs out exactly as devastator_b200/engine.py declares them."""
+    import ctypes
+    import subprocess
+    from devastator_b200 import engine as E
+    src = tmp_path / "abi_c.c"
+    src.write_text('#include "deva_b200.h"\n#include <stddef.h>\n#include <stdio.h>\nint main(void) {\n'
+                   '  printf("%d %zu %zu %zu %zu %zu %zu\\n", deva_b200_abi_version(), sizeof(deva_b200_config),\n'
+                   '         sizeof(deva_b200_model_params), sizeof(deva_b200_stats), offsetof(deva_b200_config, mp),\n'
+                   '         offsetof(deva_b200_config, window), offsetof(deva_b200_stats, kernel_launches));\n  return 0;\n}\n')
+    exe = tmp_path / "abi_c"
+    libdir = os.path.dirname(E.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", f"-I{ROOT}/include", str(src),
+                           f"-L{libdir}", "-ldeva_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    want = [E.ABI_VERSION, ctypes.sizeof(E.Config), ctypes.sizeof(E.ModelParams), ctypes.sizeof(E.Stats),
+            E.Config.mp.offset, E.Config.window.offset, E.Stats.kernel_launches.offset]
+    assert got == want
