@@ -10,6 +10,15 @@ import oracle_lib as O
 import scenarios as S
 
 
+def _extreme_optimism(K, window, LAM):
+    """True where a loud capacity refusal is tolerated: the window (16 ticks at start-up when adaptive)
+    spans more than 8 mean delays, or holds more than ~16 events per LP (K * W / lambda) - a quarter of the
+    64-slot pending pool, and under rollback every one of them can be in flight as a positive plus its
+    anti-message."""
+    w = window or 16
+    return w / LAM > 8 or K * w / LAM > 16
+
+
 @settings(max_examples=int(os.environ.get("DEVA_TEST_EXAMPLES", 400)), deadline=None,
           derandomize="DEVA_TEST_EXAMPLES" not in os.environ,
           suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
@@ -44,9 +53,9 @@ def test_random_config_matches_oracle(emu_api, A, K, P, LAM, END, window, sub, r
         # A per-LP pool may overflow with the deliberately tiny capacities, or when the window is so wide
         # against the mean delay (lambda) that one pass speculates through 8+ generations of events and
         # the rollback cascades pile positive / anti records up at single LPs (a fixed 1000-tick window at
-        # lambda = 5; the 16-tick start-up window at lambda = 1).  The engine then refuses loudly
+        # lambda = 5; the 16-tick start-up window at lambda = 1; see _extreme_optimism).  The engine then refuses loudly
         # (DEVA_B200_ERR_CAPACITY = -3) - it never drops a record.  Otherwise it may not refuse.
-        if ex.code == -3 and (caps != (64, 16, 48) or (window or 16) / LAM > 8):
+        if ex.code == -3 and (caps != (64, 16, 48) or _extreme_optimism(K, window, LAM)):
             event("capacity refusal (tiny caps or window > 8 lambda)")
             assume(False)
         raise
@@ -78,7 +87,7 @@ def test_random_partitioned_config_matches_oracle(emu_api, G, A, K, P, LAM, END,
         try:
             gvt = M.drain_multi(emu_api, engs, drain_end)
         except S.E.EngineError as ex:   # see test_random_config_matches_oracle
-            if ex.code == -3 and (inbox_cap != 16 or (window or 16) / LAM > 8):
+            if ex.code == -3 and (inbox_cap != 16 or _extreme_optimism(K, window, LAM)):
                 assume(False)
             raise
         np.testing.assert_array_equal(np.concatenate([e.get_state() for e in engs]), ost)
@@ -164,7 +173,7 @@ def test_random_pause_rewind_resume_matches_oracle(emu_api, A, K, P, LAM, END, w
             assert gvt == o["gvt"] and d["pending"] == o["pending"] and d["checksum"] == o["checksum"]
             assert eng.stats()["committed_n"] == expect_commits
     except S.E.EngineError as ex:   # see test_random_config_matches_oracle
-        if ex.code == -3 and (inbox_cap != 16 or (window or 16) / LAM > 8):
+        if ex.code == -3 and (inbox_cap != 16 or _extreme_optimism(K, window, LAM)):
             assume(False)
         raise
     finally:
