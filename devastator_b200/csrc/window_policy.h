@@ -8,6 +8,7 @@
 // (the reference's deva_static_look_dt, pdes.cxx:36,247-250).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace deva_b200 {
 
@@ -15,12 +16,23 @@ struct WindowPolicy {
   static constexpr int PERIOD = 2;   // epochs per decision (update() is called once per epoch with its sums)
   uint64_t fixed = 0;
   uint64_t w = 1;
+  bool ramp = false;   // DEVA_B200_WINDOW_START given: start there and DOUBLE while efficiency is above the band and w < 16
   uint64_t acc_exec = 0, acc_rolled = 0;
   unsigned round = 0;
 
+  // The adaptive window starts at 16 ticks (tuned on BASELINE's lambda = 100).  For models whose mean
+  // delay is a few ticks that first window spans many generations of events and can overflow the
+  // per-LP pools before the policy has seen a single efficiency figure; DEVA_B200_WINDOW_START=1
+  // starts like the reference (look_dt = 1, pdes.cxx:68) and doubles up (pdes.cxx:264-265) until 16.
   void init(uint64_t window) {
     fixed = window;
     w = window ? window : 16;
+    if (!window) {
+      if (const char *ws = getenv("DEVA_B200_WINDOW_START")) {
+        const uint64_t w0 = strtoull(ws, nullptr, 10);
+        if (w0 >= 1) { w = w0; ramp = true; }
+      }
+    }
   }
   void begin_drain() { acc_exec = acc_rolled = 0; round = 0; }
   uint64_t window() const { return w; }
@@ -43,7 +55,7 @@ struct WindowPolicy {
       const double eff = 1.0 - (double)acc_rolled / (double)acc_exec;
       if (eff < 0.80) w /= 2;
       else if (eff < 0.965) w = w - w / 4;
-      else if (eff > 0.985) w = w + w / 4 + 1;
+      else if (eff > 0.985) w = (ramp && w < 16) ? w * 2 : w + w / 4 + 1;
     }
     acc_exec = acc_rolled = 0;
     if (w > (uint64_t(1) << 58)) w = uint64_t(1) << 58;

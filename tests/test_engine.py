@@ -212,3 +212,22 @@ def test_bench_model_against_reference_state_fixture(api, tag):
     np.testing.assert_array_equal(eng.get_state(), want)
     s = eng.stats()
     assert (s["committed_n"], gvt, s["deterministic"]) == (g["commits"], g["gvt"], 1)
+
+
+# ---- DEVA_B200_WINDOW_START: reference-like start-up (window 1, doubling) for dense models -----------
+def test_window_start_knob_keeps_dense_models_within_capacity(api, monkeypatch):
+    """lambda = 1 with every child leaving its LP: the default 16-tick start-up window spans ~16 generations of
+    events and overflows the pools (a loud refusal, see the next test); started at 1 the run completes and
+    equals the oracle."""
+    monkeypatch.setenv("DEVA_B200_WAKE_MIN", "0")
+    monkeypatch.setenv("DEVA_B200_WINDOW_START", "1")
+    S.run_phold_t(api, 47, 7, 1.0, 1.0, 15, window=0)
+    S.run_phold_t(api, 181, 8, 1.0, 5.0, 40, window=0)
+    S.run_phold_t(api, 1000, 16, 0.5, 100.0, 300, window=0)   # and an ordinary one
+
+
+def test_default_start_window_refuses_loudly_when_far_too_optimistic(emu_api, monkeypatch):
+    monkeypatch.setenv("DEVA_B200_WAKE_MIN", "0")
+    with pytest.raises(E.EngineError) as ei:
+        S.run_phold_t(emu_api, 47, 7, 1.0, 1.0, 15, window=0)
+    assert ei.value.code == -3   # DEVA_B200_ERR_CAPACITY: never a silent drop
