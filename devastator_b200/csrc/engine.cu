@@ -21,6 +21,7 @@
 #include "../../include/deva_b200.h"
 #include "pdes_core.cuh"
 #include "window_policy.h"
+#include "tile_engine.cuh"
 
 using namespace deva_b200;
 
@@ -34,6 +35,21 @@ static int fail(int code, const char *fmt, ...) {
   va_end(ap);
   return code;
 }
+namespace deva_b200 { namespace tl {
+int tile_fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+} }
+typedef deva_b200::tl::TileEngine<deva_b200::tl::CudaBE> CudaTile;
+// Two engines behind one ABI.  Default: the TILE engine (tile_core.cuh: calendar of per-tile event lists,
+// bulk-copied into shared memory, epochs closed on the device).  DEVA_B200_ENGINE=lp selects the first
+// engine (one thread per LP over per-LP pools, pdes_core.cuh), kept as the measured baseline.
+static bool want_tile() { const char *k = getenv("DEVA_B200_ENGINE"); return !(k && !strcmp(k, "lp")); }
+
 #define CU(call)                                                                                   \
   do {                                                                                             \
     cudaError_t _e = (call);                                                                       \
@@ -246,6 +262,7 @@ struct CtlSum { uint64_t gvt_next, executed, committed, rolled_back, anti_sent, 
 
 // ------------------------------------------------------------------------------------------------
 struct deva_b200_engine {
+  CudaTile *tile = nullptr;
   deva_b200_config cfg;
   ModelParams mp;
   View v;
@@ -359,7 +376,7 @@ extern "C" {
 const char *deva_b200_last_error(void) { return g_err; }
 int deva_b200_abi_version(void) { return DEVA_B200_ABI_VERSION; }
 int deva_b200_state_words(const deva_b200_engine *e) { return e ? e->stw : 0; }
-void *deva_b200_stream(deva_b200_engine *e) { return e ? (void *)e->stream : nullptr; }
+void *deva_b200_stream(deva_b200_engine *e) { return e ? (e->tile ? (void *)e->tile->be.stream : (void *)e->stream) : nullptr; }
 
 int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   if (!cfg || !out) return fail(DEVA_B200_ERR_ARG, "null argument");
@@ -378,6 +395,13 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   deva_b200_engine *e = new deva_b200_engine;
   e->cfg = *cfg;
   e->stw = cfg->model == DEVA_B200_MODEL_PHOLD_BENCH ? PholdBench::STW : PholdTest::STW;
+  if (want_tile()) {
+    e->tile = new CudaTile;
+    const int trc = e->tile->create(cfg);
+    if (trc) { e->tile->destroy(); delete e->tile; delete e; return trc; }
+    *out = e;
+    return 0;
+  }
   e->mp.lp_n_model = cfg->mp.lp_n_model;
   e->mp.p_remote_thresh = cfg->mp.p_remote_thresh;
   e->mp.neg_lambda = -cfg->mp.lambda;
@@ -456,6 +480,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
 
 void deva_b200_destroy(deva_b200_engine *e) {
   if (!e) return;
+  if (e->tile) { e->tile->destroy(); delete e->tile; delete e; return; }
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void *p : e->ipc_open) cudaIpcCloseMemHandle(p);
@@ -476,6 +501,10 @@ void deva_b200_destroy(deva_b200_engine *e) {
 
 int deva_b200_set_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t count, const uint64_t *words) {
   if (!e || !words) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->tile) {
+    if (lp_first < e->cfg.lp_begin || lp_first + count > e->cfg.lp_begin + e->cfg.lp_count) return fail(DEVA_B200_ERR_ARG, "LP range not owned");
+    return e->tile->set_state(lp_first, count, words);
+  }
   if (lp_first < e->v.lp_begin || lp_first + count > e->v.lp_begin + e->v.A) return fail(DEVA_B200_ERR_ARG, "LP range not owned");
   if (count == 0) return 0;
   CU(cudaSetDevice(e->cfg.device));
@@ -491,6 +520,10 @@ int deva_b200_set_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t coun
 
 int deva_b200_get_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t count, uint64_t *words) {
   if (!e || !words) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->tile) {
+    if (lp_first < e->cfg.lp_begin || lp_first + count > e->cfg.lp_begin + e->cfg.lp_count) return fail(DEVA_B200_ERR_ARG, "LP range not owned");
+    return e->tile->get_state(lp_first, count, words);
+  }
   if (lp_first < e->v.lp_begin || lp_first + count > e->v.lp_begin + e->v.A) return fail(DEVA_B200_ERR_ARG, "LP range not owned");
   if (count == 0) return 0;
   CU(cudaSetDevice(e->cfg.device));
@@ -533,6 +566,7 @@ int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time,
                           const uint32_t *lp, const uint32_t *payload) {
   if (!e || (n && (!time || !subtime || !lp || !payload))) return fail(DEVA_B200_ERR_ARG, "null argument");
   if (n == 0) return 0;
+  if (e->tile) return e->tile->roots(n, time, subtime, lp, payload);
   if (n > 0xffffffffull) return fail(DEVA_B200_ERR_ARG, "too many roots in one call");
   CU(cudaSetDevice(e->cfg.device));
   // four column copies (DMA straight from the caller's buffers; pinned buffers go at link speed),
@@ -556,6 +590,7 @@ int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time,
 
 int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k, int32_t rootdiv, int32_t ranks) {
   if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->tile) return e->tile->seed(k, rootdiv, ranks);
   if (k > e->v.pq_cap) return fail(DEVA_B200_ERR_CAPACITY, "k_per_lp exceeds pq_cap");
   CU(cudaSetDevice(e->cfg.device));
   const int R = ranks > 0 ? ranks : 1;
@@ -577,6 +612,7 @@ int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k, int32_t rootdiv, int32
 // zeroes the LP state words, restarts the sequence counters (statistics keep accumulating).
 int deva_b200_reset(deva_b200_engine *e) {
   if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->tile) return e->tile->reset();
   CU(cudaSetDevice(e->cfg.device));
   const int grid = (int)((e->v.A + 255) / 256);
   dispatch_model(e->cfg.model, [&](auto m) {
@@ -593,6 +629,7 @@ int deva_b200_reset(deva_b200_engine *e) {
 
 int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) {
   if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->tile) { e->tile->stop_req.store(stop); return 0; }
   e->mp.stop = stop;
   return 0;
 }
@@ -771,6 +808,10 @@ static int exact_gvt(deva_b200_engine *e, uint64_t *out) {
 
 int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out) {
   if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->tile) {
+    CU(cudaSetDevice(e->cfg.device));
+    return e->tile->drain(t_end, rewindable, gvt_out);
+  }
   if (e->has_rewind) return fail(DEVA_B200_ERR_STATE, "lingering rewind state: call deva_b200_rewind first (pdes.cxx:705-708)");
   if (e->cfg.n_gpus > 1 && !e->comm) return fail(DEVA_B200_ERR_STATE, "n_gpus > 1 but deva_b200_comm_init was not called");
   CU(cudaSetDevice(e->cfg.device));
@@ -870,6 +911,7 @@ int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uin
 
 int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind) {
   if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->tile) { CU(cudaSetDevice(e->cfg.device)); return e->tile->rewind(do_rewind); }
   if (!e->has_rewind) return fail(DEVA_B200_ERR_STATE, "rewind without a rewindable drain (pdes.cxx:1138)");
   CU(cudaSetDevice(e->cfg.device));
   e->has_rewind = false;
@@ -890,6 +932,7 @@ int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind) {
 
 int deva_b200_get_stats(deva_b200_engine *e, deva_b200_stats *out) {
   if (!e || !out) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->tile) { CU(cudaSetDevice(e->cfg.device)); return e->tile->get_stats(out); }
   memset(out, 0, sizeof *out);
   out->executed_n = e->executed;
   out->committed_n = e->committed;
@@ -907,6 +950,7 @@ int deva_b200_get_stats(deva_b200_engine *e, deva_b200_stats *out) {
 
 int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]) {
   if (!e || !out) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->tile) return e->tile->digest(out);
   CU(cudaSetDevice(e->cfg.device));
   CU(cudaMemsetAsync(e->d_digest, 0, 4 * sizeof(unsigned long long), e->stream));
   k_digest<<<148 * 4, 256, 0, e->stream>>>(e->v, e->stw, e->d_digest);

@@ -31,7 +31,8 @@ namespace deva_b200 {
 
 enum : uint32_t {
   EV_ANTI = 1u,   // anti-message (cancels the positive record with identical time/sub/payload)
-  EV_SENT = 2u    // log only: the event sent a child when it ran
+  EV_SENT = 2u,   // log only: the event sent a child when it ran
+  EV_DEAD = 4u    // tile engine: record annihilated in place (a positive / anti pair matched at a drain's exit)
 };
 
 // One event record: (time, tiebreak, payload, destination LP).  == the logical content of the

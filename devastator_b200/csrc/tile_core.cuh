@@ -1,0 +1,989 @@
+// tile_core.cuh - the TILE engine's algorithm: one optimistic epoch for one tile of 256 LPs, the
+// epoch state machine, the calendar maintenance.  Compiles for the device (tile_engine.cuh: the
+// kernels) and for the host (tests/emu: block phases become loops over the thread index).
+//
+// What it replaces in the reference (for a device-resident model):
+//   drain "execute one event"            pdes.cxx:900-999  -> eval_tile: bulk-load the tile's open bucket
+//                                                             into shared memory, counting-sort by LP, every
+//                                                             LP's thread runs its events in (time, subtime) order
+//   insert_past / remove_past / rollback pdes.cxx:496-693  -> re-evaluation from the epoch checkpoint:
+//                                                             an LP that receives a straggler or an
+//                                                             anti-message inside the open window re-runs its
+//                                                             window from the state saved at the epoch start
+//                                                             (the other half of the double-buffered LpState),
+//                                                             walks the OLD and the NEW event sequence from
+//                                                             the point where they part, cancels the old
+//                                                             children with anti-messages and sends the new ones
+//   arrive_near/far(+anti)               pdes.cxx:393-493  -> route_append + the per-LP netting of
+//                                                             anti-messages against identical positives
+//   gvt.cxx epochs / fossil collection   gvt.cxx:53-149, pdes.cxx:816-871
+//                                                          -> an epoch ends when no tile received an in-window
+//                                                             arrival; everything below the window bound is then
+//                                                             committed at once and the bucket's lists are dropped
+//                                                             (no per-event log survives an epoch)
+//   global_status_state::update          pdes.cxx:233-280  -> policy_update (device side)
+//
+// State saving is per epoch, not per event: the checkpoint IS the LP-state array the epoch started
+// from, so the common path writes no undo record at all; an LP that must roll back re-executes
+// at most one window of its own events (3-4 on BASELINE's PHOLD).
+#pragma once
+#include "pdes_core.cuh"
+#include "tile_types.cuh"
+
+namespace deva_b200 {
+namespace tl {
+
+// ---- block-phase emulation ----------------------------------------------------------------------
+// TL_THREADS(tid) { ... }  runs its body once per thread of the block: on the device that is the
+// calling thread, on the host a loop.  `continue` leaves the body for that thread.  Values that must
+// survive a TL_SYNC live in the block's shared workspace, never in locals.
+#if defined(__CUDA_ARCH__)
+#define TL_THREADS(tid) for (int tid = (int)threadIdx.x, tl_once_ = 1; tl_once_; tl_once_ = 0)
+#define TL_SYNC() __syncthreads()
+#else
+#define TL_THREADS(tid) for (int tid = 0; tid < TILE; tid++)
+#define TL_SYNC() ((void)0)
+#endif
+
+#if defined(__CUDA_ARCH__)
+DEVA_HD unsigned long long atom_add_u64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
+DEVA_HD void atom_min_ull(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
+DEVA_HD EvRec ld_ev_cg(const EvRec *p) {   // bypasses L1: the record may have been written by a peer GPU during this launch
+  const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(p));
+  const uint4 b = __ldcg(reinterpret_cast<const uint4 *>(p) + 1);
+  EvRec e;
+  e.time = ((uint64_t)a.y << 32) | a.x; e.sub = ((uint64_t)a.w << 32) | a.z;
+  e.p0 = b.x; e.p1 = b.y; e.dst = b.z; e.flags = b.w;
+  return e;
+}
+#else
+DEVA_HD unsigned long long atom_add_u64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+DEVA_HD void atom_min_ull(unsigned long long *p, unsigned long long v) { if (v < *p) *p = v; }
+DEVA_HD EvRec ld_ev_cg(const EvRec *p) { return *p; }
+#endif
+
+#if defined(__CUDACC__)
+// ---- TMA bulk copies (cp.async.bulk) + mbarrier: one elected thread moves a whole list -----------
+// (device only; the bodies are empty in nvcc's host pass)
+#if defined(__CUDA_ARCH__)
+#define TL_ASM(...) asm volatile(__VA_ARGS__)
+#else
+#define TL_ASM(...) ((void)0)
+#endif
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__cvta_generic_to_shared(p);
+#else
+  return 0;
+#endif
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  TL_ASM("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  TL_ASM("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  TL_ASM("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  TL_ASM(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra W_%=;\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared; bytes a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  TL_ASM("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  TL_ASM("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { TL_ASM("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { TL_ASM("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources may be reused
+__device__ __forceinline__ void bulk_wait_all() { TL_ASM("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes are done
+__device__ __forceinline__ void fence_async_smem() { TL_ASM("fence.proxy.async.shared::cta;" ::: "memory"); }   // generic writes -> async reads
+#endif
+
+// the open epoch, as every block sees it for the whole launch
+struct Epoch {
+  uint64_t cur_abs, ub, gvt;
+  uint32_t shift, par, in_epoch, epoch, stop, launch;
+  uint32_t sp_w_n, sp_r_n, sp_r_fresh;   // spill lists: readable part of the one this launch appends to; the other one; its fresh tail
+};
+DEVA_HD Epoch load_epoch(const TCtl *c) {
+  Epoch ep;
+  ep.cur_abs = c->cur_abs; ep.ub = c->ub; ep.gvt = c->gvt; ep.shift = c->shift; ep.par = c->par;
+  ep.in_epoch = c->in_epoch; ep.epoch = c->epoch; ep.stop = c->stop; ep.launch = c->launch;
+  ep.sp_w_n = c->sp_start[ep.par]; ep.sp_r_n = c->sp_n[ep.par ^ 1u]; ep.sp_r_fresh = c->sp_fresh[ep.par ^ 1u];
+  return ep;
+}
+
+// per-block accumulators (shared memory), folded into TCtl once per tile
+struct Hdr {
+  uint32_t n, nb, nl, nlw, nl_old, nf, first, slow, in_buf, slot, lo, hi, skip, used_far;
+  uint32_t executed, rolled, anti, remote, err, fresh_antis;
+  int32_t committed, nondet;
+  uint32_t bh[NB];        // records this block appended per ring slot (-> ctl->btotal)
+  uint32_t work_item;
+};
+
+// one block's shared-memory workspace
+struct Blk {
+  EvRec *R;          // [rcap]  the tile's window events; a slot is reused for the child its event sent
+  LpState *S;        // [TILE]  LP states: loaded from the checkpoint buffer, updated in place
+  uint16_t *ord;     // [rcap]  record indices grouped by LP
+  uint8_t *efl;      // [rcap]  per-record flags (F_*)
+  uint32_t *off;     // [TILE+1] segment bounds per LP
+  uint32_t *cur;     // [TILE]  histogram / scatter cursors
+  Hdr *h;
+  uint64_t *mbar;
+  uint32_t rcap;
+  uint32_t mphase;   // mbarrier phase parity (uniform across the block)
+};
+enum : uint8_t { F_FRESH = 1, F_ANTI = 2, F_INOLD = 4, F_INNEW = 8, F_CN = 16, F_CO = 32, F_OUT = 64, F_DEAD = 128 };
+
+DEVA_HD size_t blk_bytes(uint32_t rcap) {
+  size_t b = (size_t)rcap * sizeof(EvRec) + TILE * sizeof(LpState);
+  b += (size_t)rcap * 2; b = (b + 15) & ~(size_t)15;
+  b += rcap; b = (b + 15) & ~(size_t)15;
+  b += (TILE + 1) * 4; b = (b + 15) & ~(size_t)15;
+  b += TILE * 4;
+  b += sizeof(Hdr); b = (b + 15) & ~(size_t)15;
+  b += 16;
+  return b;
+}
+DEVA_HD void blk_carve(Blk &b, unsigned char *base, uint32_t rcap) {
+  size_t o = 0;
+  b.rcap = rcap;
+  b.R = reinterpret_cast<EvRec *>(base); o += (size_t)rcap * sizeof(EvRec);
+  b.S = reinterpret_cast<LpState *>(base + o); o += TILE * sizeof(LpState);
+  b.ord = reinterpret_cast<uint16_t *>(base + o); o += (size_t)rcap * 2; o = (o + 15) & ~(size_t)15;
+  b.efl = reinterpret_cast<uint8_t *>(base + o); o += rcap; o = (o + 15) & ~(size_t)15;
+  b.off = reinterpret_cast<uint32_t *>(base + o); o += (TILE + 1) * 4; o = (o + 15) & ~(size_t)15;
+  b.cur = reinterpret_cast<uint32_t *>(base + o); o += TILE * 4;
+  b.h = reinterpret_cast<Hdr *>(base + o); o += sizeof(Hdr); o = (o + 15) & ~(size_t)15;
+  b.mbar = reinterpret_cast<uint64_t *>(base + o);
+  b.mphase = 0;
+}
+
+// (time, subtime) is the reference's order (stamped_event::operator<, pdes.hxx:936-941); ties - which the
+// reference leaves to heap order and reports as deterministic=0 - are broken by the payload so that a
+// re-evaluation replays exactly the sequence the previous evaluation ran
+DEVA_HD bool rec_less(const EvRec &a, const EvRec &b) {
+  if (a.time != b.time) return a.time < b.time;
+  if (a.sub != b.sub) return a.sub < b.sub;
+  if (a.p0 != b.p0) return a.p0 < b.p0;
+  return a.p1 < b.p1;
+}
+
+// ---- routing: where a record goes (execute_context::send, pdes.hxx:666-732; arrive_*, pdes.cxx:393-493)
+//   other GPU            -> this GPU's region of that GPU's receive buffer (NVLink store)
+//   time < ub (in epoch) -> the destination tile's LATE list: a straggler / anti-message / in-window child
+//   ring bucket          -> the (tile, bucket) list;  beyond the horizon or list full -> the tile's far list
+// bh: the calling block's per-slot histogram in shared memory (folded into ctl->btotal per tile), or
+// null to count straight into ctl->btotal.
+DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uint32_t *bh, uint32_t *err) {
+  const uint64_t dl64 = (uint64_t)rec.dst - v.lp_begin;
+  if (dl64 >= v.A) { *err |= ERR_NOT_OWNER; return; }
+  const uint32_t tile = (uint32_t)dl64 / TILE;
+  TCtl *c = v.ctl;
+  if (rec.flags & EV_ANTI) atom_add_u64((unsigned long long *)&c->antis_pending, 1ull);
+  if (!ep.in_epoch) atom_min_ull(&c->gvt, rec.time);   // a root: the commit horizon cannot lie above it
+  if (ep.in_epoch && rec.time < ep.ub) {
+    if (rec.time < ep.gvt) { *err |= ERR_BELOW_GVT; return; }
+    const uint32_t p = atom_add_u32(&v.lcnt[ep.par][tile], 1u);
+    if (atom_exch_u32(&v.dmark[tile], ep.launch) != ep.launch)                    // first arrival of this launch:
+      v.dirty[ep.par][atom_add_u32(&c->dirty_n[ep.par], 1u)] = tile;              // the tile joins the next launch
+    if (p < v.CL) st_ev(&v.late[ep.par][(size_t)tile * v.CL + p], rec);
+    else {                                           // the tile's late list is full: job-wide spill list (evaluated by scanning)
+      const uint32_t q = atom_add_u32(&c->sp_n[ep.par], 1u);
+      if (q < v.SP) st_ev(&v.spill[ep.par][q], rec); else *err |= ERR_LATE_OVERFLOW;
+    }
+    return;
+  }
+  const uint64_t b = rec.time >> ep.shift;
+  const uint64_t d = b - ep.cur_abs;                 // (wraps to huge when b < cur_abs: goes to far, flagged)
+  const bool ring = ep.in_epoch ? (d >= 1 && d < NB) : (d < NB);
+  if (ring) {
+    const uint32_t slot = (uint32_t)(b % NB);
+    const uint32_t p = atom_add_u32(&v.ncnt[(size_t)tile * NB + slot], 1u);
+    if (p < v.C) {
+      st_ev(&v.near_[((size_t)tile * NB + slot) * v.C + p], rec);
+      if (bh) atom_add_u32(&bh[slot], 1u); else atom_add_u64(&c->btotal[slot], 1ull);
+      return;
+    }
+    // list full: the record waits in the far list (readers clamp ncnt to C)
+  }
+  const uint32_t p = atom_add_u32(&v.fcnt[tile], 1u);
+  if (p >= v.CF) { *err |= ERR_FAR_OVERFLOW; return; }
+  st_ev(&v.far_[(size_t)tile * v.CF + p], rec);
+  atom_add_u64(&c->far_total, 1ull);
+  if (d < NB) {                                      // belongs to the ring (its list is full, or it is the open bucket's
+    atom_or_u32(&v.tflags[tile], TF_OVF);            // tail beyond t_end): a rebin at the epoch's end puts it in place
+    atom_or_u32(&c->ovf_flag, 1u);
+  } else {
+    atom_min_ull(&c->far_min, rec.time);             // (far_min covers only records beyond the ring)
+    if (b < ep.cur_abs) atom_or_u32(&c->need_rebase, 1u);   // a root below the calendar's base
+  }
+}
+DEVA_HD void route_append(const TView &v, const Epoch &ep, const EvRec &rec, uint32_t *bh, uint32_t *err, uint32_t *remote) {
+  if (v.n_gpus > 1) {
+    const uint32_t g = (uint32_t)(rec.dst / v.lp_per_gpu);
+    if (g != (uint32_t)v.gpu_rank) {
+      if (g >= (uint32_t)v.n_gpus) { *err |= ERR_NOT_OWNER; return; }
+      const uint32_t p = agg_claim(&v.ctl->send_n[g], g);
+      if (p < v.peer_cap) st_ev(&v.peer_buf[g][p], rec); else *err |= ERR_SEND_OVERFLOW;
+      (*remote)++;
+      return;
+    }
+  }
+  append_local(v, ep, rec, bh, err);
+}
+
+// ---- the per-LP walk ------------------------------------------------------------------------------
+// An LP's window events are the live records of its segment plus the children it sends to itself
+// inside the window ("internal": they never leave the thread).  walk() runs them in order.
+//   MODE_FIRST  first evaluation of the epoch: every record is new; a child that leaves takes its
+//               parent's slot in shared memory (flushed by the whole block afterwards)
+//   MODE_SHARED re-evaluation, common prefix of the old and the new sequence: nothing is emitted
+//               (it was, last time); stops at the first record only one of them holds
+//   MODE_NEW    re-evaluation, new sequence from the fork on: children are sent
+//   MODE_OLD    re-evaluation, old sequence from the fork on: children are cancelled (anti-messages)
+enum { MODE_FIRST = 0, MODE_SHARED = 1, MODE_NEW = 2, MODE_OLD = 3 };
+struct Chain {
+  uint64_t st[MAX_STW], seq;
+  uint64_t it[2], is[2]; uint32_t ip0[2], ip1[2]; uint32_t islot[2]; uint32_t nic;   // internal children (bit i of nic: slot i in use)
+  uint64_t lt, ls; uint32_t any, cnt, tie;
+};
+
+template <class M>
+DEVA_HD bool walk(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t s0, uint32_t s1, uint64_t gid, int mode,
+                  Chain &ch, uint32_t *err, uint32_t *remote, uint32_t *anti_sent) {
+  const uint8_t need = mode == MODE_OLD ? F_INOLD : F_INNEW;
+  const uint8_t cons = mode == MODE_OLD ? F_CO : (mode == MODE_NEW || mode == MODE_FIRST ? F_CN : (uint8_t)(F_CN | F_CO));
+  for (;;) {
+    // next list record of this sequence: the smallest unconsumed one
+    int best = -1;
+#pragma unroll 1
+    for (uint32_t j = s0; j < s1; j++) {
+      const uint32_t i = b.ord[j];
+      const uint8_t f = b.efl[i];
+      if (mode == MODE_SHARED) { if (!(f & (F_INOLD | F_INNEW)) || (f & F_CN)) continue; }
+      else if (!(f & need) || (f & cons)) continue;
+      if (best < 0 || rec_less(b.R[i], b.R[best])) best = (int)i;
+    }
+    // ... or an internal child, if earlier (a list record wins a full tie)
+    int ici = -1;
+    if (ch.nic) {
+      if ((ch.nic & 1u) && (ch.nic & 2u)) {
+        const bool l10 = ch.it[1] < ch.it[0] || (ch.it[1] == ch.it[0] && (ch.is[1] < ch.is[0] || (ch.is[1] == ch.is[0] &&
+                         (ch.ip0[1] < ch.ip0[0] || (ch.ip0[1] == ch.ip0[0] && ch.ip1[1] < ch.ip1[0])))));
+        ici = l10 ? 1 : 0;
+      } else ici = (ch.nic & 1u) ? 0 : 1;
+    }
+    EvRec e;
+    uint32_t slot;
+    if (ici >= 0) {
+      e.time = ch.it[ici]; e.sub = ch.is[ici]; e.p0 = ch.ip0[ici]; e.p1 = ch.ip1[ici];
+      if (best >= 0 && !rec_less(e, b.R[best])) ici = -1;
+    }
+    if (ici >= 0) {
+      slot = ch.islot[ici];
+      ch.nic &= ~(1u << ici);
+    } else {
+      if (best < 0) return false;
+      const uint8_t f = b.efl[best];
+      if (mode == MODE_SHARED && (f & (F_INOLD | F_INNEW)) != (F_INOLD | F_INNEW)) return true;   // the sequences part here
+      e = b.R[best];
+      b.efl[best] = f | cons;
+      slot = (uint32_t)best;
+    }
+    e.dst = (uint32_t)gid; e.flags = 0;
+    if (ch.any && !key_less(ch.lt, ch.ls, e.time, e.sub)) ch.tie = 1;   // equal (time, subtime): pdes.cxx:828-831
+    ch.lt = e.time; ch.ls = e.sub; ch.any = 1;
+    ch.cnt++;
+    EvRec c;
+    const bool sent = M::execute(mp, ch.st, e, gid, c, false);
+    if (!sent) continue;
+    if (!mp.user_subtime) c.sub = ch.seq;        // event_subtime / next_seq_id, pdes.hxx:513-526,676
+    ch.seq += v.lp_n;
+    if ((uint64_t)c.dst == gid && c.time < ep.ub && ch.nic != 3u) {   // stays inside this thread
+      const int k = (ch.nic & 1u) ? 1 : 0;
+      ch.it[k] = c.time; ch.is[k] = c.sub; ch.ip0[k] = c.p0; ch.ip1[k] = c.p1; ch.islot[k] = slot;
+      ch.nic |= 1u << k;
+      continue;
+    }
+    if (mode == MODE_SHARED) continue;           // already sent by the previous evaluation
+    if (mode == MODE_FIRST) {                    // the child takes the slot; the block flushes all slots together
+      b.R[slot] = c;
+      b.efl[slot] = F_OUT;
+    } else {
+      if (mode == MODE_OLD) { c.flags = EV_ANTI; (*anti_sent)++; }
+      route_append(v, ep, c, b.h->bh, err, remote);
+    }
+  }
+}
+
+// anti-messages of one LP's segment against identical positives (arrive_near<-1>, pdes.cxx:480-487;
+// from_far matching, pdes.cxx:400-457).  Sets F_INOLD / F_INNEW on every positive.
+DEVA_HD void net_segment(Blk &b, uint32_t s0, uint32_t s1, uint32_t *err, uint32_t *fresh_antis) {
+  bool any_anti = false;
+#pragma unroll 1
+  for (uint32_t j = s0; j < s1; j++) {
+    const uint32_t i = b.ord[j];
+    uint8_t f = b.efl[i];
+    if (f & F_DEAD) continue;
+    if (f & F_ANTI) { any_anti = true; continue; }
+    f |= (f & F_FRESH) ? F_INNEW : (uint8_t)(F_INOLD | F_INNEW);
+    b.efl[i] = f;
+  }
+  if (!any_anti) return;
+  // old anti-messages first: the old set is closed (every anti in it has its positive in it)
+  for (int pass = 0; pass < 2; pass++) {
+#pragma unroll 1
+    for (uint32_t j = s0; j < s1; j++) {
+      const uint32_t ia = b.ord[j];
+      const uint8_t fa = b.efl[ia];
+      if ((fa & F_DEAD) || !(fa & F_ANTI) || ((fa & F_FRESH) ? 1 : 0) != pass) continue;
+      if (pass) (*fresh_antis)++;
+      const EvRec a = b.R[ia];
+      int hit = -1;
+#pragma unroll 1
+      for (uint32_t k = s0; k < s1; k++) {
+        const uint32_t ip = b.ord[k];
+        const uint8_t fp = b.efl[ip];
+        if ((fp & (F_ANTI | F_DEAD)) || !(fp & F_INNEW)) continue;
+        if (!pass && (fp & F_FRESH)) continue;
+        if (!same_event(a, b.R[ip])) continue;
+        if (pass && !(fp & F_FRESH) && hit >= 0) continue;   // a fresh anti prefers a fresh positive
+        hit = (int)ip;
+        if (!pass || (fp & F_FRESH)) break;
+      }
+      if (hit < 0) { *err |= ERR_ANTI_UNMATCHED; continue; }
+      b.efl[hit] &= pass ? (uint8_t)~F_INNEW : (uint8_t)~(F_INOLD | F_INNEW);
+    }
+  }
+}
+
+DEVA_HD void chain_start(Chain &ch, const LpState &s) {
+#pragma unroll
+  for (int w = 0; w < MAX_STW; w++) ch.st[w] = s.w[w];
+  ch.seq = s.seq; ch.nic = 0; ch.lt = ch.ls = 0; ch.any = ch.cnt = ch.tie = 0;
+}
+
+// exclusive prefix sum over b.cur[0..TILE) -> b.off[0..TILE]; leaves b.cur[i] = b.off[i]
+DEVA_HD void block_scan(Blk &b) {
+#if defined(__CUDA_ARCH__)
+  __shared__ uint32_t wsum[TILE / 32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t x = b.cur[tid];
+  uint32_t inc = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  uint32_t base = 0;
+#pragma unroll
+  for (int k = 0; k < TILE / 32; k++) if (k < w) base += wsum[k];
+  b.off[tid] = base + inc - x;
+  b.cur[tid] = base + inc - x;
+  if (tid == TILE - 1) b.off[TILE] = base + inc;
+  __syncthreads();
+#else
+  uint32_t run = 0;
+  for (int i = 0; i < TILE; i++) { const uint32_t x = b.cur[i]; b.off[i] = run; b.cur[i] = run; run += x; }
+  b.off[TILE] = run;
+#endif
+}
+
+// Sort the block's records b.R[0..n) by LP (counting sort on the LP's index in the tile), net the
+// anti-messages, run every LP's walk, flush the children.  lo/hi: LP sub-range handled (whole tile
+// unless the window did not fit in shared memory).
+template <class M>
+DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf) {
+  Hdr &h = *b.h;
+  const uint64_t tile_gid = v.lp_begin + (uint64_t)tile * TILE;
+  TL_THREADS(tid) { b.cur[tid] = 0; }
+  TL_SYNC();
+  TL_THREADS(tid) {
+    for (uint32_t i = tid; i < h.n; i += TILE) {
+      const uint32_t lp = (uint32_t)((uint64_t)b.R[i].dst - tile_gid);
+      atom_add_u32(&b.cur[lp], 1u);
+    }
+  }
+  TL_SYNC();
+  block_scan(b);
+  TL_SYNC();
+  TL_THREADS(tid) {
+    for (uint32_t i = tid; i < h.n; i += TILE) {
+      const uint32_t lp = (uint32_t)((uint64_t)b.R[i].dst - tile_gid);
+      b.ord[atom_add_u32(&b.cur[lp], 1u)] = (uint16_t)i;
+    }
+  }
+  TL_SYNC();
+  // ---- every LP's thread runs its window
+  TL_THREADS(tid) {
+    const uint32_t s0 = b.off[tid], s1 = b.off[tid + 1];
+    if (s0 == s1) continue;
+    const uint64_t gid = tile_gid + (uint64_t)tid;
+    uint32_t err = 0, remote = 0, anti_sent = 0, fresh_antis = 0;
+    bool fresh = false;
+#pragma unroll 1
+    for (uint32_t j = s0; j < s1; j++) { const uint8_t f = b.efl[b.ord[j]]; fresh |= (f & (F_FRESH | F_DEAD)) == F_FRESH; }
+    if (!fresh) continue;                       // nothing new for this LP since its last evaluation
+    net_segment(b, s0, s1, &err, &fresh_antis);
+    Chain ch;
+    chain_start(ch, b.S[tid]);
+    if (h.first) {
+      walk<M>(v, mp, ep, b, s0, s1, gid, MODE_FIRST, ch, &err, &remote, &anti_sent);
+#pragma unroll
+      for (int w = 0; w < MAX_STW; w++) b.S[tid].w[w] = ch.st[w];
+      b.S[tid].seq = ch.seq;
+      atom_add_u32(&h.executed, ch.cnt);
+      atom_add_u32((uint32_t *)&h.committed, ch.cnt);
+      if (ch.tie) atom_add_u32((uint32_t *)&h.nondet, 1u);
+    } else {
+      const bool forked = walk<M>(v, mp, ep, b, s0, s1, gid, MODE_SHARED, ch, &err, &remote, &anti_sent);
+      if (forked) {
+        Chain old = ch;
+        const uint32_t shared_n = ch.cnt;
+        walk<M>(v, mp, ep, b, s0, s1, gid, MODE_NEW, ch, &err, &remote, &anti_sent);
+        LpState *so = &v.st[out_buf][(size_t)tile * TILE + tid];
+#pragma unroll
+        for (int w = 0; w < MAX_STW; w++) so->w[w] = ch.st[w];
+        so->seq = ch.seq;
+        walk<M>(v, mp, ep, b, s0, s1, gid, MODE_OLD, old, &err, &remote, &anti_sent);
+        atom_add_u32(&h.executed, ch.cnt);                                     // the prefix ran again, too
+        atom_add_u32(&h.rolled, old.cnt - shared_n);
+        atom_add_u32((uint32_t *)&h.committed, ch.cnt - old.cnt);              // (two's complement delta)
+        atom_add_u32((uint32_t *)&h.nondet, ch.tie - old.tie);
+      }
+    }
+    if (err) atom_or_u32(&h.err, err);
+    if (remote) atom_add_u32(&h.remote, remote);
+    if (anti_sent) atom_add_u32(&h.anti, anti_sent);
+    if (fresh_antis) atom_add_u32(&h.fresh_antis, fresh_antis);
+  }
+  TL_SYNC();
+  // ---- flush: every slot that now holds a child goes to its list (all lanes busy, atomics in bulk)
+  if (h.first) {
+    TL_THREADS(tid) {
+      uint32_t err = 0, remote = 0;
+      for (uint32_t i = tid; i < h.n; i += TILE)
+        if (b.efl[i] & F_OUT) route_append(v, ep, b.R[i], h.bh, &err, &remote);
+      if (err) atom_or_u32(&h.err, err);
+      if (remote) atom_add_u32(&h.remote, remote);
+    }
+    TL_SYNC();
+  }
+}
+
+// One tile, one launch of an epoch.  Its window events are the open bucket's list (+ what waits for
+// that bucket in the far list) and the in-window arrivals of this epoch: the late list the previous
+// launch wrote (complete) and the part of the other one an earlier evaluation has seen.
+template <class M>
+DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, Blk &b, uint32_t tile) {
+  Hdr &h = *b.h;
+  ModelParams mp = mp0;
+  mp.stop = (int32_t)ep.stop;
+  const uint32_t rd = ep.par ^ 1u;                 // late list written by the previous launch
+  TL_THREADS(tid) {
+    if (tid != 0) continue;
+    h.slot = (uint32_t)(ep.cur_abs % NB);
+    const uint32_t nc = v.ncnt[(size_t)tile * NB + h.slot];
+    h.nb = nc < v.C ? nc : v.C;
+    const uint32_t lc = v.lcnt[rd][tile];
+    h.nl = lc < v.CL ? lc : v.CL;                  // all of it is complete: this launch appends to the other list
+    h.first = v.tev[tile] != ep.epoch;
+    h.nlw = h.first ? 0u : v.lseen[ep.par][tile];  // the other list: what this tile has evaluated before (complete, too)
+    h.nl_old = h.first ? 0u : v.lseen[rd][tile];
+    h.nf = (v.tflags[tile] & TF_OVF) ? v.fpub[tile] : 0u;   // (count as of the last rebin: those records are complete)
+    h.in_buf = v.tcur[tile];
+    h.skip = (h.nb + h.nl + h.nlw + h.nf) == 0;
+    h.slow = h.nf > 0 || h.nb + h.nl + h.nlw > b.rcap || ep.sp_w_n > 0 || ep.sp_r_n > 0;
+    if (ep.sp_w_n > 0 || ep.sp_r_n > 0) h.skip = 0;
+    h.executed = h.rolled = h.anti = h.remote = h.err = h.fresh_antis = 0; h.committed = h.nondet = 0; h.used_far = 0;
+    for (int i = 0; i < NB; i++) h.bh[i] = 0;
+  }
+  TL_SYNC();
+  if (h.skip) return;
+  const uint32_t out_buf = h.in_buf ^ 1u;
+  const EvRec *list = v.near_ + ((size_t)tile * NB + h.slot) * v.C;
+  const EvRec *late_w = v.late[ep.par] + (size_t)tile * v.CL;
+  const EvRec *late_r = v.late[rd] + (size_t)tile * v.CL;
+  const LpState *s_in = v.st[h.in_buf] + (size_t)tile * TILE;
+  const uint32_t n_src = h.nb + h.nlw + h.nl;                  // R order: bucket | other late list | late list just written
+  const uint32_t n_oldsrc = h.nb + h.nlw + h.nl_old;           // ... of which a re-evaluation has seen all but the last list's tail
+
+  if (!h.slow) {
+    // ---- fast path: lists and states come in as bulk copies (TMA), completion on one mbarrier
+#if defined(__CUDA_ARCH__)
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(b.mbar, n_src * (uint32_t)sizeof(EvRec) + TILE * (uint32_t)sizeof(LpState));
+      if (h.nb) bulk_g2s(b.R, list, h.nb * (uint32_t)sizeof(EvRec), b.mbar);
+      if (h.nlw) bulk_g2s(b.R + h.nb, late_w, h.nlw * (uint32_t)sizeof(EvRec), b.mbar);
+      if (h.nl) bulk_g2s(b.R + h.nb + h.nlw, late_r, h.nl * (uint32_t)sizeof(EvRec), b.mbar);
+      bulk_g2s(b.S, s_in, TILE * (uint32_t)sizeof(LpState), b.mbar);
+    }
+    mbar_wait(b.mbar, b.mphase);
+    b.mphase ^= 1u;
+#else
+    for (uint32_t i = 0; i < h.nb; i++) b.R[i] = list[i];
+    for (uint32_t i = 0; i < h.nlw; i++) b.R[h.nb + i] = late_w[i];
+    for (uint32_t i = 0; i < h.nl; i++) b.R[h.nb + h.nlw + i] = late_r[i];
+    for (int i = 0; i < TILE; i++) b.S[i] = s_in[i];
+#endif
+    // flags; records outside [gvt, ub) are not part of this epoch (a bucket cut by t_end keeps its tail,
+    // after a pause its head is already committed): inert, parked on the tile's first LP
+    TL_THREADS(tid) {
+      if (tid == 0) h.n = n_src;
+      for (uint32_t i = tid; i < n_src; i += TILE) {
+        const EvRec &r = b.R[i];
+        uint8_t f = (h.first || i >= n_oldsrc) ? F_FRESH : 0;
+        if (r.flags & EV_ANTI) f |= F_ANTI;
+        if (r.time >= ep.ub || r.time < ep.gvt || (r.flags & EV_DEAD)) { b.R[i].dst = (uint32_t)(v.lp_begin + (uint64_t)tile * TILE); f = F_DEAD; }
+        b.efl[i] = f;
+      }
+    }
+    TL_SYNC();
+    run_records<M>(v, mp, ep, b, tile, out_buf);
+  } else {
+    // ---- slow path: the window does not fit in shared memory (a start-up bucket holding every root,
+    // many same-time events) or part of it waits in the far list: LP sub-ranges, one sweep each
+    TL_THREADS(tid) {
+      b.S[tid] = s_in[tid];
+      if (tid == 0) h.lo = 0;
+    }
+    TL_SYNC();
+    const EvRec *farl = v.far_ + (size_t)tile * v.CF;
+    const uint64_t tile_gid = v.lp_begin + (uint64_t)tile * TILE;
+    const uint32_t sp_w = ep.sp_w_n < v.SP ? ep.sp_w_n : v.SP, sp_r = ep.sp_r_n < v.SP ? ep.sp_r_n : v.SP;
+    const uint32_t n_far_end = n_src + h.nf, n_all = n_far_end + sp_w + sp_r;
+    // record i of the tile's sources; returns false for records that are not this tile's / not this epoch's
+    auto fetch = [&](uint32_t i, EvRec &r, bool &fresh) -> bool {
+      fresh = h.first != 0;
+      if (i < h.nb) r = list[i];
+      else if (i < h.nb + h.nlw) r = late_w[i - h.nb];
+      else if (i < n_src) { r = late_r[i - h.nb - h.nlw]; fresh |= i >= n_oldsrc; }
+      else if (i < n_far_end) r = farl[i - n_src];
+      else if (i < n_far_end + sp_w) r = ld_ev(&v.spill[ep.par][i - n_far_end]);
+      else { r = ld_ev(&v.spill[rd][i - n_far_end - sp_w]); fresh |= (i - n_far_end - sp_w) >= ep.sp_r_fresh; }
+      if (i >= n_far_end && (uint64_t)r.dst - tile_gid >= (uint64_t)TILE) return false;
+      return !(r.time >= ep.ub || r.time < ep.gvt || (r.flags & EV_DEAD));
+    };
+    while (h.lo < TILE) {
+      // per-LP record counts of the remaining LPs -> the widest sub-range that fits
+      TL_THREADS(tid) { b.cur[tid] = 0; }
+      TL_SYNC();
+      TL_THREADS(tid) {
+        for (uint32_t i = tid; i < n_all; i += TILE) {
+          EvRec r; bool fresh;
+          if (!fetch(i, r, fresh)) continue;
+          const uint32_t lp = (uint32_t)((uint64_t)r.dst - tile_gid);
+          if (lp >= h.lo && lp < TILE) atom_add_u32(&b.cur[lp], 1u);
+        }
+      }
+      TL_SYNC();
+      TL_THREADS(tid) {
+        if (tid != 0) continue;
+        uint32_t sum = 0, hi = h.lo;
+        while (hi < TILE && sum + b.cur[hi] <= b.rcap) { sum += b.cur[hi]; hi++; }
+        if (hi == h.lo) { h.err |= ERR_LP_OVERFLOW; hi = h.lo + 1; }   // one LP alone exceeds the workspace
+        h.hi = hi;
+        h.n = 0;
+      }
+      TL_SYNC();
+      TL_THREADS(tid) {
+        for (uint32_t i = tid; i < n_all; i += TILE) {
+          EvRec r; bool fresh;
+          if (!fetch(i, r, fresh)) continue;
+          const uint32_t lp = (uint32_t)((uint64_t)r.dst - tile_gid);
+          if (lp < h.lo || lp >= h.hi) continue;
+          const uint32_t p = atom_add_u32(&h.n, 1u);
+          if (p >= b.rcap) continue;     // (only after ERR_LP_OVERFLOW)
+          b.R[p] = r;
+          uint8_t f = fresh ? F_FRESH : 0;
+          if (r.flags & EV_ANTI) f |= F_ANTI;
+          b.efl[p] = f;
+          if (i >= n_src && i < n_far_end) h.used_far = 1;
+        }
+      }
+      TL_SYNC();
+      TL_THREADS(tid) { if (tid == 0 && h.n > b.rcap) h.n = b.rcap; }
+      TL_SYNC();
+      run_records<M>(v, mp, ep, b, tile, out_buf);
+      TL_THREADS(tid) { if (tid == 0) h.lo = h.hi; }
+      TL_SYNC();
+    }
+  }
+
+  // ---- write back: first evaluation stores the whole tile's states (one bulk copy) into the
+  // result buffer; a re-evaluation has stored the LPs it changed itself
+  if (h.first) {
+#if defined(__CUDA_ARCH__)
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_s2g(v.st[out_buf] + (size_t)tile * TILE, b.S, TILE * (uint32_t)sizeof(LpState));
+      bulk_commit();
+      bulk_wait_all();
+    }
+#else
+    for (int i = 0; i < TILE; i++) v.st[out_buf][(size_t)tile * TILE + i] = b.S[i];
+#endif
+  }
+  TL_THREADS(tid) {
+    if (tid != 0) continue;
+    TCtl *c = v.ctl;
+    v.tev[tile] = ep.epoch;
+    v.lseen[rd][tile] = h.nl;
+    v.lseen[ep.par][tile] = h.nlw;
+    if (h.executed) atom_add_u64(&c->executed, h.executed);
+    if (h.committed) atom_add_u64(&c->committed, (unsigned long long)(long long)h.committed);
+    if (h.rolled) atom_add_u64(&c->rolled, h.rolled);
+    if (h.anti) atom_add_u64(&c->anti_sent, h.anti);
+    if (h.remote) atom_add_u64(&c->remote_sent, h.remote);
+    if (h.nondet) atom_add_u64((unsigned long long *)&c->nondet, (unsigned long long)(long long)h.nondet);
+    if (h.fresh_antis) atom_add_u64((unsigned long long *)&c->antis_pending, (unsigned long long)(-(long long)h.fresh_antis));
+    if (h.err) atom_or_u32(&c->err, h.err);
+    if (h.used_far) atom_or_u32(&c->ovf_flag, 1u);   // consumed far records must be dropped before the next epoch
+    for (int i = 0; i < NB; i++) if (h.bh[i]) atom_add_u64(&c->btotal[i], h.bh[i]);
+    atom_add_u64(&c->evals, 1ull);
+  }
+  TL_SYNC();
+}
+
+// ---- calendar maintenance (PH_REBIN): one tile's far list - or every list of the tile when the
+// bucket width or the base changes - is re-bucketed against the current base.  No evaluation runs
+// concurrently and a tile's records never leave the tile, so the block owns everything it touches.
+DEVA_HD void rebin_tile(const TView &v, const Epoch &ep, Blk &b, uint32_t tile, EvRec *scratch, uint32_t all) {
+  Hdr &h = *b.h;
+  TL_THREADS(tid) {
+    if (tid != 0) continue;
+    h.n = 0; h.err = 0;
+    for (int i = 0; i < NB; i++) h.bh[i] = 0;
+  }
+  TL_SYNC();
+  // gather: far list (+ every near list) -> scratch, dropping what is committed or annihilated
+  const uint32_t nf = v.fcnt[tile] < v.CF ? v.fcnt[tile] : v.CF;
+  TL_THREADS(tid) {
+    for (uint32_t i = tid; i < nf; i += TILE) {
+      const EvRec r = ld_ev(&v.far_[(size_t)tile * v.CF + i]);
+      if (r.time < ep.gvt || (r.flags & EV_DEAD)) continue;
+      const uint32_t p = atom_add_u32(&h.n, 1u);
+      if (p < v.scratch_cap) st_ev(&scratch[p], r);
+    }
+  }
+  TL_SYNC();
+  if (all) {
+    for (uint32_t s = 0; s < NB; s++) {
+      const uint32_t nc0 = v.ncnt[(size_t)tile * NB + s];
+      const uint32_t nc = nc0 < v.C ? nc0 : v.C;
+      TL_THREADS(tid) {
+        for (uint32_t i = tid; i < nc; i += TILE) {
+          const EvRec r = ld_ev(&v.near_[((size_t)tile * NB + s) * v.C + i]);
+          if (r.time < ep.gvt || (r.flags & EV_DEAD)) continue;
+          const uint32_t p = atom_add_u32(&h.n, 1u);
+          if (p < v.scratch_cap) st_ev(&scratch[p], r);
+        }
+      }
+      TL_SYNC();
+    }
+  }
+  TL_THREADS(tid) {
+    if (tid != 0) continue;
+    if (h.n > v.scratch_cap) { h.err |= ERR_TILE_OVERFLOW; h.n = v.scratch_cap; }
+    v.fcnt[tile] = 0;
+    v.tflags[tile] = 0;
+    if (all) for (uint32_t s = 0; s < NB; s++) v.ncnt[(size_t)tile * NB + s] = 0;
+  }
+  TL_SYNC();
+  // scatter back (ctl->far_total / far_min, and btotal when `all`, were zeroed when the rebin was scheduled)
+  TL_THREADS(tid) {
+    uint32_t err = 0;
+    for (uint32_t i = tid; i < h.n; i += TILE) {
+      const EvRec r = ld_ev(&scratch[i]);
+      const uint64_t bb = r.time >> ep.shift;
+      const uint64_t d = bb - ep.cur_abs;
+      if (d < NB) {
+        const uint32_t slot = (uint32_t)(bb % NB);
+        const uint32_t p = atom_add_u32(&v.ncnt[(size_t)tile * NB + slot], 1u);
+        if (p < v.C) { st_ev(&v.near_[((size_t)tile * NB + slot) * v.C + p], r); atom_add_u32(&h.bh[slot], 1u); continue; }
+      }
+      const uint32_t p = atom_add_u32(&v.fcnt[tile], 1u);
+      if (p >= v.CF) { err |= ERR_FAR_OVERFLOW; continue; }
+      st_ev(&v.far_[(size_t)tile * v.CF + p], r);
+      atom_add_u64(&v.ctl->far_total, 1ull);
+      if (d < NB) atom_or_u32(&v.tflags[tile], TF_OVF);   // its bucket's list is full: evaluated from here (slow path)
+      else atom_min_ull(&v.ctl->far_min, r.time);
+    }
+    if (err) atom_or_u32(&h.err, err);
+  }
+  TL_SYNC();
+  TL_THREADS(tid) {
+    if (tid != 0) continue;
+    const uint32_t fc = v.fcnt[tile];
+    v.fpub[tile] = fc < v.CF ? fc : v.CF;
+    if (h.err) atom_or_u32(&v.ctl->err, h.err);
+    for (int i = 0; i < NB; i++) if (h.bh[i]) atom_add_u64(&v.ctl->btotal[i], h.bh[i]);
+  }
+  TL_SYNC();
+}
+
+// ---- the epoch state machine ------------------------------------------------------------------------
+// Job-wide figures a decision rests on.  One GPU: read from the local control block.  Several GPUs:
+// the sums / minima of every GPU's figures (exchanged device-side), so that all GPUs decide alike.
+struct Glob {
+  unsigned long long btotal[NB], far_total, far_min, executed, committed, dirty_n, err;
+  uint32_t ovf_flag, need_rebase;
+};
+DEVA_HD void glob_from_ctl(Glob &g, const TCtl *c, uint32_t dirty_n) {
+  for (int i = 0; i < NB; i++) g.btotal[i] = c->btotal[i];
+  g.far_total = c->far_total; g.far_min = c->far_min; g.executed = c->executed; g.committed = c->committed;
+  g.dirty_n = dirty_n; g.err = c->err; g.ovf_flag = c->ovf_flag; g.need_rebase = c->need_rebase;
+}
+
+DEVA_HD uint64_t bucket_end(uint64_t b_abs, uint32_t shift) {
+  const uint64_t e = (b_abs + 1) << shift;
+  return ((e >> shift) == b_abs + 1) ? e : ~0ull;    // (overflow of the shift: no upper bound)
+}
+
+// Picks what the next launch does (single thread).  `inclusive`: the bucket at cur_abs may be the next one
+// (drain start, after a rebin); otherwise it has just been consumed.
+DEVA_HD void choose_next(TCtl *c, const TParams &tp, const Glob &g, bool inclusive) {
+  c->in_epoch = 0;
+  // a change of the bucket width re-buckets everything (window policy; pdes.cxx:233-280 only changes a scalar)
+  if (c->want_shift != c->shift) {
+    c->shift = c->want_shift;
+    c->cur_abs = c->gvt >> c->shift;
+    c->phase = PH_REBIN; c->rebin_all = 1;
+    for (int i = 0; i < NB; i++) c->btotal[i] = 0;
+    c->far_total = 0; c->far_min = ~0ull; c->ovf_flag = 0; c->need_rebase = 0;
+    return;
+  }
+  uint64_t nb_abs = ~0ull;
+  for (uint32_t d = inclusive ? 0u : 1u; d < (uint32_t)NB; d++) {
+    const uint64_t bb = c->cur_abs + d;
+    if (g.btotal[bb % NB] > 0) { nb_abs = bb; break; }
+  }
+  const uint64_t far_b = g.far_total > 0 && g.far_min != ~0ull ? g.far_min >> c->shift : ~0ull;
+  if (g.need_rebase || g.ovf_flag || (far_b != ~0ull && far_b <= nb_abs)) {
+    // far records are due (or misplaced): re-bucket them against the base the next epoch will have
+    uint64_t base = nb_abs < far_b ? nb_abs : far_b;
+    if (base == ~0ull) base = c->cur_abs;
+    const bool back = base < c->cur_abs;             // a root below the base: every ring position changes
+    c->cur_abs = base;
+    c->phase = PH_REBIN; c->rebin_all = back ? 1u : 0u;
+    if (back) for (int i = 0; i < NB; i++) c->btotal[i] = 0;
+    c->far_total = 0; c->far_min = ~0ull; c->ovf_flag = 0; c->need_rebase = 0;
+    return;
+  }
+  if (nb_abs == ~0ull) {                             // nothing is pending anywhere
+    c->gvt = ~0ull; c->phase = PH_DONE;
+    return;
+  }
+  // the bucket about to open holds more than the lists are built for (a start-up where every root falls
+  // into one bucket, a model denser than the current width suits): halve the width first
+  if (!c->fixed_shift && c->shift > 0 && g.btotal[nb_abs % NB] * 16ull > (unsigned long long)tp.pol_occ_x16 * c->lp_total) {
+    c->want_shift = c->shift - 1; c->hold = 2;
+    choose_next(c, tp, g, inclusive);
+    return;
+  }
+  const uint64_t start = nb_abs << c->shift;
+  c->cur_abs = nb_abs;
+  if (start > c->gvt) c->gvt = start;
+  if (c->gvt >= c->t_end) { c->phase = PH_DONE; return; }
+  const uint64_t be = bucket_end(nb_abs, c->shift);
+  c->ub = be < c->t_end ? be : c->t_end;
+  c->phase = PH_EVAL; c->full = 1; c->in_epoch = 1; c->epoch++;
+}
+
+// Window policy (global_status_state::update, pdes.cxx:233-280): the bucket width is the optimism
+// window.  Efficiency = committed / executed over the last epochs; too much wasted work halves the
+// width, nearly none doubles it while the epochs are thin (few commits per LP).  Never changes results.
+DEVA_HD void policy_update(TCtl *c, const TParams &tp, const Glob &g) {
+  if (c->fixed_shift) return;
+  if (++c->pol_epochs < 2) return;
+  const unsigned long long ex = g.executed - c->e_exec0;
+  const long long cm = (long long)(g.committed - c->e_commit0);
+  const uint32_t n_ep = c->pol_epochs;
+  c->pol_epochs = 0; c->e_exec0 = g.executed; c->e_commit0 = g.committed;
+  if (c->hold) { c->hold--; return; }
+  if (ex == 0 || cm <= 0) return;
+  const unsigned long long eff_pm = (unsigned long long)cm * 1000ull / ex;
+  const unsigned long long dens_x16 = (unsigned long long)cm * 16ull / (c->lp_total * n_ep);
+  if (eff_pm < tp.pol_lo_pm && c->shift > 0) { c->want_shift = c->shift - 1; c->hold = 2; }
+  else if (eff_pm > tp.pol_hi_pm && dens_x16 < tp.pol_density_x16 && c->shift < 40) { c->want_shift = c->shift + 1; c->hold = 2; }
+}
+
+// Runs once per launch, by the last block to finish (one GPU) or by the exchange kernel after the
+// peers' figures are in (several GPUs): follow-up launch, epoch commit, or calendar maintenance next.
+DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
+  TCtl *c = v.ctl;
+  const uint32_t phase = c->phase;
+  if (phase == PH_EVAL && g.dirty_n == 0) {
+    // ---- epoch commit (fossil collection, pdes.cxx:816-871): everything below ub is final.  The
+    // tiles that ran swap their state buffers; a bucket consumed to its end gives its lists back.
+    const bool whole = c->ub == bucket_end(c->cur_abs, c->shift);
+    const uint32_t slot = (uint32_t)(c->cur_abs % NB), epoch = c->epoch;
+    TL_THREADS(tid) {
+      for (uint32_t t = tid; t < v.NT; t += TILE) {
+        if (v.tev[t] == epoch) v.tcur[t] ^= 1u;
+        if (whole) v.ncnt[(size_t)t * NB + slot] = 0;
+        v.lcnt[0][t] = 0; v.lcnt[1][t] = 0;
+      }
+    }
+    TL_SYNC();
+  }
+  TL_THREADS(tid) {
+    if (tid != 0) continue;
+    c->work = 0; c->ticket = 0; c->launch++;
+    c->dirty_n[c->par ^ 1u] = 0;                   // the list this launch consumed
+    c->sp_fresh[c->par] = c->sp_start[c->par];     // spill list this launch appended to: its new records start here
+    c->sp_start[c->par] = c->sp_n[c->par] < v.SP ? c->sp_n[c->par] : v.SP;
+    for (int i = 0; i < MAX_GPUS; i++) c->send_n[i] = 0;
+    if (g.err) { c->err |= (uint32_t)g.err; c->phase = PH_DONE; continue; }
+    if (phase == PH_EVAL) {
+      if (g.dirty_n > 0) {                         // stragglers / anti-messages arrived: follow-up launch over their tiles
+        c->full = 0; c->par ^= 1u;
+        continue;
+      }
+      const bool whole = c->ub == bucket_end(c->cur_abs, c->shift);
+      if (whole) c->btotal[c->cur_abs % NB] = 0;
+      c->gvt = c->ub;
+      c->epochs++;
+      for (int i = 0; i < 2; i++) c->sp_n[i] = c->sp_start[i] = c->sp_fresh[i] = 0;
+      c->par ^= 1u;
+      c->stop = c->stop_req;
+      policy_update(c, tp, g);
+      if (c->gvt >= c->t_end) { c->phase = PH_DONE; c->in_epoch = 0; continue; }
+      Glob g2 = g;
+      if (whole) g2.btotal[c->cur_abs % NB] = 0;
+      choose_next(c, tp, g2, !whole);
+    } else if (phase == PH_REBIN) {
+      Glob g2;
+      glob_from_ctl(g2, c, 0);                     // (several GPUs: the exchange kernel passes the sums)
+      if (v.n_gpus > 1) g2 = g;
+      choose_next(c, tp, g2, true);
+    }
+  }
+  TL_SYNC();
+}
+
+// drain entry: latch t_end, pick the first epoch
+DEVA_HD void begin_drain(const TView &v, const TParams &tp, uint64_t t_end, const Glob &g) {
+  TCtl *c = v.ctl;
+  c->t_end = t_end;
+  c->work = 0; c->ticket = 0;
+  c->stop = c->stop_req;
+  c->pol_epochs = 0; c->e_exec0 = g.executed; c->e_commit0 = g.committed;
+  if (c->gvt >= t_end) { c->phase = PH_DONE; return; }
+  choose_next(c, tp, g, true);
+}
+
+// ---- setup -------------------------------------------------------------------------------------------
+template <class M>
+DEVA_HD void tile_init_lp(const TView &v, const ModelParams &mp, uint32_t lp, int init_state) {
+  const uint64_t gid = v.lp_begin + lp;
+  LpState s;
+  for (int w = 0; w < MAX_STW; w++) s.w[w] = 0;
+  if (init_state) M::init_state(mp, gid, s.w);
+  s.seq = gid;                                        // pdes.cxx:332: seq_id_bumper = global_cd_begin + i
+  v.st[0][lp] = s;
+  v.st[1][lp] = s;
+}
+
+// K roots of one LP (test/phold.cxx:172-178 with PHOLD-T's root time; bench/phold.cxx:152-158)
+template <class M>
+DEVA_HD void tile_seed_lp(const TView &v, const ModelParams &mp, const Epoch &ep, uint32_t lp, uint32_t k, int rootdiv, uint64_t per_rank, uint32_t *err) {
+  const uint64_t gid = v.lp_begin + lp;
+  if (gid >= mp.lp_n_model) return;                   // padding LPs of the rank decomposition get no roots
+  for (uint32_t j = 0; j < k; j++) {
+    EvRec e;
+    uint64_t ray;
+    if (M::MODEL_ID == 2) { ray = gid * k + j; e.time = ray; }
+    else { ray = gid + (uint64_t)j * mp.lp_n_model; e.time = rootdiv ? j : ray; }
+    e.sub = mp.user_subtime ? ray : gid % per_rank;  // pdes.hxx:907: root subtime = LOCAL cd index
+    e.p0 = (uint32_t)ray; e.p1 = 0; e.dst = (uint32_t)gid; e.flags = 0;
+    append_local(v, ep, e, nullptr, err);
+  }
+}
+
+// ---- drain exit: anti-messages still waiting for their positive in a future bucket are matched now,
+// so that no positive / anti pair is left pending at a pause (it would lower the GVT drain returns and
+// the pending count; the reference annihilates on arrival, pdes.cxx:400-457,480-487).  One thread per
+// record position; a positive is claimed with a CAS on its flags word.
+DEVA_HD bool claim_positive(EvRec *list, uint32_t n, const EvRec &a) {
+  for (uint32_t i = 0; i < n; i++) {
+    EvRec *q = &list[i];
+    if (q->time != a.time || q->sub != a.sub || q->p0 != a.p0 || q->p1 != a.p1 || q->dst != a.dst) continue;
+#if defined(__CUDA_ARCH__)
+    if (atomicCAS(&q->flags, 0u, (uint32_t)EV_DEAD) == 0u) return true;
+#else
+    if (q->flags == 0u) { q->flags = EV_DEAD; return true; }
+#endif
+  }
+  return false;
+}
+DEVA_HD void net_pending_record(const TView &v, const Epoch &ep, uint32_t tile, EvRec *a, uint32_t *err, uint32_t *matched) {
+  if (!(a->flags & EV_ANTI) || (a->flags & EV_DEAD) || a->time < ep.gvt) return;
+  const uint64_t bb = a->time >> ep.shift;
+  bool ok = false;
+  if (bb - ep.cur_abs < NB) {
+    const uint32_t slot = (uint32_t)(bb % NB);
+    const uint32_t nc0 = v.ncnt[(size_t)tile * NB + slot];
+    ok = claim_positive(&v.near_[((size_t)tile * NB + slot) * v.C], nc0 < v.C ? nc0 : v.C, *a);
+  }
+  if (!ok) { const uint32_t fc = v.fcnt[tile]; ok = claim_positive(&v.far_[(size_t)tile * v.CF], fc < v.CF ? fc : v.CF, *a); }
+  if (ok) { a->flags |= EV_DEAD; (*matched)++; } else *err |= ERR_ANTI_UNMATCHED;
+}
+
+DEVA_HD bool rec_live(const EvRec &r, uint64_t gvt) { return r.time >= gvt && !(r.flags & EV_DEAD); }
+
+// out[0] ^= last state word, out[1] += hash(state words), out[2] += pending count, out[3] += hash(pending)
+// (same figures as the first engine's digest_lp, pdes_core.cuh)
+DEVA_HD void tile_digest_lp(const TView &v, int stw, uint32_t lp, uint64_t out[4]) {
+  const uint64_t gid = v.lp_begin + lp;
+  const LpState &s = v.st[v.tcur[lp / TILE]][lp];
+  out[0] ^= s.w[stw - 1];
+  for (int w = 0; w < stw; w++) out[1] += mix64(s.w[w] ^ mix64(gid * 4 + w + 1));
+}
+DEVA_HD void tile_digest_rec(const EvRec &e, uint64_t gvt, uint64_t out[4]) {
+  if (!rec_live(e, gvt)) return;
+  out[2] += 1;
+  out[3] += mix64(e.time ^ mix64(e.sub ^ mix64(((uint64_t)e.p0 << 32 | e.dst) + (e.flags & EV_ANTI))));
+}
+
+// every record position of one tile, strided over `nthr` callers: f(EvRec *)
+template <class F>
+DEVA_HD void for_tile_records(const TView &v, uint32_t tile, uint32_t tid, uint32_t nthr, F &f) {
+  for (uint32_t s = 0; s < (uint32_t)NB; s++) {
+    const uint32_t nc0 = v.ncnt[(size_t)tile * NB + s];
+    const uint32_t nc = nc0 < v.C ? nc0 : v.C;
+    EvRec *l = &v.near_[((size_t)tile * NB + s) * v.C];
+    for (uint32_t i = tid; i < nc; i += nthr) f(&l[i]);
+  }
+  const uint32_t fc0 = v.fcnt[tile];
+  const uint32_t fc = fc0 < v.CF ? fc0 : v.CF;
+  EvRec *l = &v.far_[(size_t)tile * v.CF];
+  for (uint32_t i = tid; i < fc; i += nthr) f(&l[i]);
+}
+struct NetFn {
+  const TView &v; Epoch ep; uint32_t tile; uint32_t err, matched;
+  DEVA_HD void operator()(EvRec *r) { net_pending_record(v, ep, tile, r, &err, &matched); }
+};
+struct MinFn {
+  uint64_t gvt, tmin;
+  DEVA_HD void operator()(EvRec *r) { if (rec_live(*r, gvt) && r->time < tmin) tmin = r->time; }
+};
+struct DigestFn {
+  uint64_t gvt; uint64_t *out;
+  DEVA_HD void operator()(EvRec *r) { tile_digest_rec(*r, gvt, out); }
+};
+
+}  // namespace tl
+}  // namespace deva_b200

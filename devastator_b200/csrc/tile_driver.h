@@ -1,0 +1,296 @@
+// tile_driver.h - host side of the TILE engine: allocation, seeding, the drain loop, rewind, statistics.
+//
+// Written against a Backend (the CUDA one in tile_engine.cuh launches kernels on a stream; the
+// emulation one in tests/emu runs the same device functions as host loops), so that the `-m "not gpu"`
+// suite exercises the very code that drives the GPU.
+//
+// The drain loop replaces pdes::drain's main loop (pdes.cxx:695-1058).  The host does NOT take part
+// in the epoch protocol: it enqueues launches of the step kernel blindly, in batches, and reads the
+// device's control block once per batch; the device decides by itself whether the next launch is a
+// follow-up over the tiles that received stragglers, the first pass of the next epoch, or calendar
+// maintenance (close_launch, tile_core.cuh).
+#pragma once
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/deva_b200.h"
+#include "tile_core.cuh"
+
+namespace deva_b200 {
+namespace tl {
+
+int tile_fail(int code, const char *fmt, ...);   // sets deva_b200_last_error (defined by the library that includes this)
+
+inline const char *tile_err_text(uint32_t err) {
+  static thread_local char buf[512];
+  buf[0] = 0;
+  if (err & ERR_ANTI_UNMATCHED) strcat(buf, "anti-message without matching event; ");
+  if (err & ERR_SEND_OVERFLOW) strcat(buf, "peer receive region overflowed (DEVA_B200_SEND_CAP_PER_LP); ");
+  if (err & ERR_NOT_OWNER) strcat(buf, "event addressed to an LP this engine does not own; ");
+  if (err & ERR_BELOW_GVT) strcat(buf, "record below GVT; ");
+  if (err & ERR_LATE_OVERFLOW) strcat(buf, "more in-window arrivals in one epoch than the late lists and the spill list hold: the window is far too wide for this model (DEVA_B200_TILE_CL / DEVA_B200_TILE_SPILL); ");
+  if (err & ERR_FAR_OVERFLOW) strcat(buf, "a tile's far list overflowed (DEVA_B200_TILE_CF / pq_cap); ");
+  if (err & ERR_TILE_OVERFLOW) strcat(buf, "a tile's bucket cannot hold its arrivals / a tile exceeds the rebin scratch (DEVA_B200_TILE_C); ");
+  if (err & ERR_LP_OVERFLOW) strcat(buf, "one LP holds more events in one window than a block's workspace (DEVA_B200_TILE_RCAP); ");
+  if (err & ERR_PEER_TIMEOUT) strcat(buf, "a peer GPU did not answer within the time-out; ");
+  return buf;
+}
+
+template <class M> struct ModelTag { using type = M; };
+template <class F>
+static auto tile_dispatch_model(int model, F &&f) {
+  if (model == DEVA_B200_MODEL_PHOLD_BENCH) return f(ModelTag<PholdBench>{});
+  return f(ModelTag<PholdTest>{});
+}
+
+static inline uint32_t env_u32(const char *name, uint32_t dflt) {
+  const char *s = getenv(name);
+  return s && *s ? (uint32_t)strtoul(s, nullptr, 10) : dflt;
+}
+
+template <class BE>
+struct TileEngine {
+  deva_b200_config cfg;
+  ModelParams mp;
+  TView v;
+  TParams tp;
+  int stw = 0;
+  BE be;
+  TCtl hc;                     // host copy of the control block (last read)
+  uint32_t batch = 16;         // launches enqueued between two reads of the control block
+  uint64_t launches = 0, passes0 = 0;
+  double drain_ms = 0, exec_ms = 0;
+  std::atomic<int32_t> stop_req{0};
+  bool has_rewind = false;
+  struct Snap { void *live, *copy; size_t bytes; };
+  std::vector<Snap> snaps;
+  TCtl snap_ctl;
+  // drain timer (counterpart of the reference's DrainTimer, pdes.hxx:139-308): one CSV row per batch
+  std::string timer_path;
+
+  int create(const deva_b200_config *c) {
+    cfg = *c;
+    stw = c->model == DEVA_B200_MODEL_PHOLD_BENCH ? PholdBench::STW : PholdTest::STW;
+    mp.lp_n_model = c->mp.lp_n_model; mp.p_remote_thresh = c->mp.p_remote_thresh; mp.neg_lambda = -c->mp.lambda;
+    mp.end_time = c->mp.end_time; mp.user_subtime = c->mp.user_subtime; mp.bench_lp_per_rank = c->mp.bench_lp_per_rank;
+    mp.bench_peer_stddev = c->mp.bench_peer_stddev; mp.stop = 0;
+    memset(&v, 0, sizeof v);
+    v.A = (uint32_t)c->lp_count;
+    v.NT = (v.A + TILE - 1) / TILE;
+    // capacities, in records per tile.  Defaults: a bucket list holds 6 events per LP (the policy aims at
+    // 2-4 per LP per epoch), the far list 32 per LP.  pq_cap (pending events per LP) scales the far list.
+    v.C = env_u32("DEVA_B200_TILE_C", 6 * TILE);
+    v.CL = env_u32("DEVA_B200_TILE_CL", 4 * TILE);
+    v.CF = env_u32("DEVA_B200_TILE_CF", (uint32_t)(c->pq_cap > 0 ? std::max(c->pq_cap, 8) : 32) * TILE);
+    v.lp_begin = c->lp_begin; v.lp_n = c->lp_n; v.n_gpus = c->n_gpus; v.gpu_rank = c->gpu_rank;
+    v.lp_per_gpu = (c->lp_n + c->n_gpus - 1) / c->n_gpus;
+    tp.rcap = env_u32("DEVA_B200_TILE_RCAP", 1280);
+    if (tp.rcap > 65535) tp.rcap = 65535;   // (record indices are 16 bits)
+    tp.pol_lo_pm = env_u32("DEVA_B200_POL_LO", 800);
+    tp.pol_hi_pm = env_u32("DEVA_B200_POL_HI", 960);
+    tp.pol_density_x16 = env_u32("DEVA_B200_POL_DENSITY_X16", 40);
+    tp.pol_occ_x16 = env_u32("DEVA_B200_POL_OCC_X16", 72);
+    batch = std::max<uint32_t>(1, env_u32("DEVA_B200_TILE_BATCH", 16));
+    int rc;
+    if ((rc = be.open(c->device, tp.rcap))) return rc;
+    if (const char *tpth = getenv("DEVA_B200_DRAIN_TIMER")) timer_path = tpth;
+    const size_t NT = v.NT, LP = NT * TILE;
+#define TA(p, n) if ((rc = be.alloc((void **)&(p), (size_t)(n) * sizeof(*(p))))) return rc;
+    TA(v.st[0], LP) TA(v.st[1], LP) TA(v.tcur, NT) TA(v.tev, NT) TA(v.tflags, NT)
+    TA(v.near_, NT * NB * v.C) TA(v.ncnt, NT * NB)
+    TA(v.late[0], NT * v.CL) TA(v.late[1], NT * v.CL) TA(v.lcnt[0], NT) TA(v.lcnt[1], NT) TA(v.lseen[0], NT) TA(v.lseen[1], NT) TA(v.dmark, NT)
+    TA(v.far_, NT * v.CF) TA(v.fcnt, NT) TA(v.fpub, NT)
+    TA(v.dirty[0], NT) TA(v.dirty[1], NT) TA(v.ctl, 1)
+    v.SP = env_u32("DEVA_B200_TILE_SPILL", (uint32_t)std::max<size_t>(65536, 4 * (size_t)v.A));
+    TA(v.spill[0], v.SP) TA(v.spill[1], v.SP)
+    v.scratch_cap = env_u32("DEVA_B200_TILE_SCRATCH", 24576);
+    TA(v.scratch, (size_t)be.grid_blocks() * v.scratch_cap)
+#undef TA
+    if ((rc = be.zero(v.ctl, sizeof(TCtl)))) return rc;
+    memset(&hc, 0, sizeof hc);
+    // window: a fixed width is rounded down to a power of two (the bucket width); 0 = adaptive, starting at 16
+    uint32_t shift = 4;
+    if (c->window) { shift = 0; while ((2ull << shift) <= c->window && shift < 40) shift++; hc.fixed_shift = 1; }
+    else shift = env_u32("DEVA_B200_TILE_SHIFT0", 4);
+    hc.shift = hc.want_shift = shift;
+    hc.lp_total = c->lp_n;
+    hc.far_min = ~0ull;
+    if ((rc = clear_calendar(false))) return rc;
+    return init_states(0);
+  }
+
+  // empties every list and restarts the calendar at time 0 (statistics and the learned width stay)
+  int clear_calendar(bool keep_ctl_from_device) {
+    int rc;
+    if (keep_ctl_from_device && (rc = be.read_ctl(v, &hc))) return rc;
+    const size_t NT = v.NT;
+    if ((rc = be.zero(v.ncnt, NT * NB * 4)) || (rc = be.zero(v.fcnt, NT * 4)) || (rc = be.zero(v.fpub, NT * 4)) ||
+        (rc = be.zero(v.lcnt[0], NT * 4)) || (rc = be.zero(v.lcnt[1], NT * 4)) || (rc = be.zero(v.tflags, NT * 4)) ||
+        (rc = be.zero(v.tcur, NT * 4)) || (rc = be.fill_ff(v.tev, NT * 4)) || (rc = be.fill_ff(v.dmark, NT * 4)))
+      return rc;
+    hc.cur_abs = 0; hc.ub = 0; hc.gvt = 0; hc.t_end = 0; hc.far_min = ~0ull; hc.phase = PH_IDLE; hc.full = 0; hc.par = 0;
+    hc.in_epoch = 0; hc.work = hc.ticket = 0; hc.dirty_n[0] = hc.dirty_n[1] = 0; for (int i = 0; i < 2; i++) hc.sp_n[i] = hc.sp_start[i] = hc.sp_fresh[i] = 0; hc.ovf_flag = hc.need_rebase = 0;
+    for (int i = 0; i < NB; i++) hc.btotal[i] = 0;
+    hc.far_total = 0; hc.antis_pending = 0; hc.err = 0; hc.nondet = 0;
+    hc.want_shift = hc.shift;
+    for (int i = 0; i < MAX_GPUS; i++) hc.send_n[i] = 0;
+    return be.write_ctl(v, &hc);
+  }
+
+  int init_states(int init_state) {
+    int rc = tile_dispatch_model(cfg.model, [&](auto m) { return be.template k_init<typename decltype(m)::type>(v, mp, init_state); });
+    launches++;
+    return rc;
+  }
+
+  int reset() {   // pdes::finalize + pdes::init on the same allocation
+    int rc;
+    if ((rc = clear_calendar(true))) return rc;
+    has_rewind = false;
+    return init_states(0);
+  }
+
+  int seed(uint32_t k, int rootdiv, int ranks) {
+    int rc;
+    if ((rc = clear_calendar(true)) || (rc = init_states(1))) return rc;
+    const int R = ranks > 0 ? ranks : 1;
+    const uint64_t per = (v.lp_n + R - 1) / R;
+    rc = tile_dispatch_model(cfg.model, [&](auto m) { return be.template k_seed<typename decltype(m)::type>(v, mp, k, rootdiv, per); });
+    launches++;
+    has_rewind = false;
+    return rc;
+  }
+
+  int roots(uint64_t n, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload) {
+    int rc = be.k_roots(v, n, time, sub, lp, payload);
+    launches++;
+    if (rc) return rc;
+    if ((rc = be.read_ctl(v, &hc))) return rc;
+    return check_err();
+  }
+
+  int check_err() {
+    const uint32_t err = hc.err;
+    if (!err) return 0;
+    const bool cap = err & (ERR_SEND_OVERFLOW | ERR_LATE_OVERFLOW | ERR_FAR_OVERFLOW | ERR_TILE_OVERFLOW | ERR_LP_OVERFLOW);
+    return tile_fail(cap ? DEVA_B200_ERR_CAPACITY : DEVA_B200_ERR_INVARIANT, "tile engine error 0x%x: %s", err, tile_err_text(err));
+  }
+
+  int drain(uint64_t t_end, int rewindable, uint64_t *gvt_out) {
+    if (has_rewind) return tile_fail(DEVA_B200_ERR_STATE, "lingering rewind state: call deva_b200_rewind first (pdes.cxx:705-708)");
+    int rc;
+    be.timer_start(0);
+    if (rewindable && (rc = snapshot())) return rc;
+    if ((rc = be.read_ctl(v, &hc))) return rc;
+    hc.stop_req = (uint32_t)stop_req.load();
+    const unsigned long long launch0 = hc.launch;
+    if ((rc = be.write_ctl(v, &hc))) return rc;
+    if ((rc = be.k_begin(v, tp, t_end))) return rc;
+    launches++;
+    FILE *tf = nullptr;
+    if (!timer_path.empty()) {
+      const std::string path = timer_path + "." + std::to_string(cfg.gpu_rank) + ".csv";
+      tf = fopen(path.c_str(), "a");
+      if (tf) { fseek(tf, 0, SEEK_END); if (ftell(tf) == 0) fprintf(tf, "sim_time,window,epochs,launches,executed,rolled_back,committed,batch_ms\n"); }
+    }
+    uint64_t guard = 0;
+    for (;;) {
+      TCtl before = hc;
+      be.timer_start(1);
+      for (uint32_t i = 0; i < batch; i++) {
+        rc = tile_dispatch_model(cfg.model, [&](auto m) { return be.template k_step<typename decltype(m)::type>(v, mp, tp); });
+        if (rc) { if (tf) fclose(tf); return rc; }
+      }
+      launches += batch;
+      const double bms = be.timer_stop(1);
+      exec_ms += bms;
+      hc.stop_req = (uint32_t)stop_req.load();
+      if ((rc = be.read_ctl_set_stop(v, &hc, hc.stop_req))) { if (tf) fclose(tf); return rc; }
+      if (tf) fprintf(tf, "%llu,%llu,%llu,%u,%llu,%llu,%llu,%.4f\n", (unsigned long long)before.gvt, 1ull << hc.shift,
+                      (unsigned long long)(hc.epochs - before.epochs), hc.launch - before.launch, (unsigned long long)(hc.executed - before.executed),
+                      (unsigned long long)(hc.rolled - before.rolled), (unsigned long long)(hc.committed - before.committed), bms);
+      if (hc.err) { if (tf) fclose(tf); return check_err(); }
+      if (hc.phase == PH_DONE) break;
+      if (hc.launch == before.launch && ++guard > 4) { if (tf) fclose(tf); return tile_fail(DEVA_B200_ERR_INVARIANT, "tile engine: the step kernel makes no progress (phase %u)", hc.phase); }
+      if (hc.launch != before.launch) guard = 0;
+    }
+    if (tf) fclose(tf);
+    passes0 += hc.launch - launch0;
+    // exit: no positive / anti pair may stay pending (it would lower the GVT returned, pdes.cxx:878-886)
+    if (hc.antis_pending > 0) {
+      if ((rc = be.k_net_pending(v))) return rc;
+      launches++;
+    }
+    uint64_t gvt = ~0ull;
+    if (hc.gvt != ~0ull) {
+      if ((rc = be.k_min_pending(v, &gvt))) return rc;
+      launches++;
+      if ((rc = be.read_ctl(v, &hc))) return rc;
+      if (hc.err) return check_err();
+    }
+    drain_ms += be.timer_stop(0);
+    if (gvt_out) *gvt_out = gvt;
+    return 0;
+  }
+
+  int snapshot() {
+    int rc;
+    if (snaps.empty()) {
+      const size_t NT = v.NT, LP = NT * TILE;
+      Snap l[] = {{v.st[0], nullptr, LP * sizeof(LpState)}, {v.st[1], nullptr, LP * sizeof(LpState)}, {v.tcur, nullptr, NT * 4},
+                  {v.tflags, nullptr, NT * 4}, {v.fpub, nullptr, NT * 4}, {v.ncnt, nullptr, NT * NB * 4}, {v.fcnt, nullptr, NT * 4},
+                  {v.near_, nullptr, NT * NB * v.C * sizeof(EvRec)}, {v.far_, nullptr, NT * v.CF * sizeof(EvRec)}};
+      for (auto &s : l) {
+        if ((rc = be.alloc(&s.copy, s.bytes))) return rc;
+        snaps.push_back(s);
+      }
+    }
+    for (auto &s : snaps) if ((rc = be.d2d(s.copy, s.live, s.bytes))) return rc;
+    if ((rc = be.read_ctl(v, &snap_ctl))) return rc;
+    has_rewind = true;
+    return 0;
+  }
+
+  int rewind(int do_rewind) {
+    if (!has_rewind) return tile_fail(DEVA_B200_ERR_STATE, "rewind without a rewindable drain (pdes.cxx:1138)");
+    has_rewind = false;
+    if (!do_rewind) return 0;
+    int rc;
+    for (auto &s : snaps) if ((rc = be.d2d(s.live, s.copy, s.bytes))) return rc;
+    if ((rc = be.fill_ff(v.tev, (size_t)v.NT * 4))) return rc;
+    if ((rc = be.read_ctl(v, &hc))) return rc;
+    // the pending set, the calendar and the commit horizon come back; statistics are NOT rewound
+    // (SURVEY Appendix A.7), and the epoch serial keeps counting
+    TCtl n = snap_ctl;
+    n.epoch = hc.epoch; n.launch = hc.launch; n.executed = hc.executed; n.committed = hc.committed; n.rolled = hc.rolled;
+    n.anti_sent = hc.anti_sent; n.remote_sent = hc.remote_sent; n.epochs = hc.epochs; n.evals = hc.evals; n.nondet = hc.nondet;
+    n.round = hc.round; n.work = 0; n.ticket = 0; n.phase = PH_IDLE; n.in_epoch = 0;
+    hc = n;
+    return be.write_ctl(v, &hc);
+  }
+
+  int get_stats(deva_b200_stats *out) {
+    int rc;
+    if ((rc = be.read_ctl(v, &hc))) return rc;
+    memset(out, 0, sizeof *out);
+    out->executed_n = hc.executed; out->committed_n = hc.committed; out->deterministic = hc.nondet > 0 ? 0 : 1;
+    out->rolled_back_n = hc.rolled; out->anti_sent_n = hc.anti_sent; out->remote_sent_n = hc.remote_sent;
+    out->passes = passes0; out->window_last = 1ull << hc.shift; out->drain_ms = drain_ms; out->exec_kernel_ms = exec_ms;
+    out->kernel_launches = launches;
+    return 0;
+  }
+
+  int digest(uint64_t out[4]) { launches++; return be.k_digest(v, stw, out); }
+  int set_state(uint64_t first, uint64_t count, const uint64_t *words) { launches++; return be.k_state(v, (uint32_t)(first - v.lp_begin), (uint32_t)count, stw, const_cast<uint64_t *>(words), 1); }
+  int get_state(uint64_t first, uint64_t count, uint64_t *words) { launches++; return be.k_state(v, (uint32_t)(first - v.lp_begin), (uint32_t)count, stw, words, 0); }
+  void destroy() { be.free_all(); }
+};
+
+}  // namespace tl
+}  // namespace deva_b200

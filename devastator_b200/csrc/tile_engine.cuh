@@ -1,0 +1,324 @@
+// tile_engine.cuh - CUDA backend of the TILE engine: the kernels and the stream plumbing.
+//
+// k_tile_step is THE kernel: a persistent grid (a few blocks per SM) whose blocks pull tiles from a
+// work counter; each tile's open bucket, its in-window arrivals and its 256 LP states enter shared
+// memory as bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier -> SYNCS), are
+// counting-sorted by LP, executed one LP per thread, and the children leave through atomically
+// claimed list slots; the tile's states go back as one bulk store.  The last block to finish runs
+// the epoch state machine (close_launch), so the next launch knows what to do without the host.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "tile_driver.h"
+
+namespace deva_b200 {
+namespace tl {
+
+#ifndef DEVA_TILE_MINB
+#define DEVA_TILE_MINB 3   // resident blocks per SM the register allocator must allow
+#endif
+
+template <class M>
+__global__ void __launch_bounds__(TILE, DEVA_TILE_MINB)
+k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams mp, const __grid_constant__ TParams tp) {
+  extern __shared__ __align__(128) unsigned char tl_smem[];
+  TCtl *c = v.ctl;
+  const uint32_t phase = c->phase;
+  if (phase != PH_EVAL && phase != PH_REBIN) return;   // done / idle: the launch is a no-op
+  Blk b;
+  blk_carve(b, tl_smem, tp.rcap);
+  if (threadIdx.x == 0) mbar_init(b.mbar, 1);
+  __syncthreads();
+  const Epoch ep = load_epoch(c);
+  const bool all_tiles = phase == PH_REBIN || c->full;
+  const uint32_t n_work = all_tiles ? v.NT : c->dirty_n[ep.par ^ 1u];
+  const uint32_t rebin_all = c->rebin_all;
+  for (;;) {
+    if (threadIdx.x == 0) b.h->work_item = atomicAdd(&c->work, 1u);
+    __syncthreads();
+    const uint32_t w = b.h->work_item;
+    __syncthreads();
+    if (w >= n_work) break;
+    const uint32_t tile = all_tiles ? w : v.dirty[ep.par ^ 1u][w];
+    if (phase == PH_EVAL) eval_tile<M>(v, mp, ep, b, tile);
+    else rebin_tile(v, ep, b, tile, v.scratch + (size_t)blockIdx.x * v.scratch_cap, rebin_all);
+  }
+  // the last block to finish closes the launch: follow-up, epoch commit, or calendar maintenance next
+  __shared__ uint32_t is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&c->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last || v.n_gpus > 1) return;   // (several GPUs: the exchange kernel closes, once the peers' figures are in)
+  __threadfence();
+  __shared__ Glob g;
+  if (threadIdx.x == 0) glob_from_ctl(g, c, c->dirty_n[c->par]);
+  __syncthreads();
+  close_launch(v, tp, g);
+}
+
+__global__ void k_tile_begin(TView v, TParams tp, uint64_t t_end) {
+  if (threadIdx.x || blockIdx.x) return;
+  Glob g;
+  glob_from_ctl(g, v.ctl, 0);
+  begin_drain(v, tp, t_end, g);
+}
+
+template <class M>
+__global__ void k_tile_init(TView v, ModelParams mp, int init_state) {
+  const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp < v.NT * TILE) tile_init_lp<M>(v, mp, lp, init_state && lp < v.A);
+}
+
+template <class M>
+__global__ void k_tile_seed(TView v, ModelParams mp, uint32_t k, int rootdiv, uint64_t per) {
+  const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+  Epoch ep = load_epoch(v.ctl);
+  ep.in_epoch = 0;
+  uint32_t err = 0;
+  if (lp < v.A) tile_seed_lp<M>(v, mp, ep, lp, k, rootdiv, per, &err);
+  if (err) atomicOr(&v.ctl->err, err);
+}
+
+__global__ void k_tile_roots(TView v, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload, uint32_t n) {
+  Epoch ep = load_epoch(v.ctl);
+  ep.in_epoch = 0;
+  uint32_t err = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    EvRec r;
+    r.time = time[i]; r.sub = sub[i]; r.p0 = payload[i]; r.p1 = 0; r.dst = lp[i]; r.flags = 0;
+    append_local(v, ep, r, nullptr, &err);
+  }
+  if (err) atomicOr(&v.ctl->err, err);
+}
+
+// AoS host layout [count][stw]  <->  the model words of LpState (current buffer of the LP's tile)
+__global__ void k_tile_state(TView v, uint64_t *aos, uint32_t first, uint32_t count, int stw, int to_device) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t lp = first + i;
+  LpState *s = &v.st[v.tcur[lp / TILE]][lp];
+  for (int w = 0; w < stw; w++) {
+    if (to_device) s->w[w] = aos[(size_t)i * stw + w]; else aos[(size_t)i * stw + w] = s->w[w];
+  }
+}
+
+__global__ void k_tile_net_pending(TView v) {
+  const Epoch ep = load_epoch(v.ctl);
+  for (uint32_t t = blockIdx.x; t < v.NT; t += gridDim.x) {
+    NetFn f{v, ep, t, 0, 0};
+    for_tile_records(v, t, threadIdx.x, blockDim.x, f);
+    if (f.err) atomicOr(&v.ctl->err, f.err);
+    if (f.matched) atomicAdd((unsigned long long *)&v.ctl->antis_pending, (unsigned long long)(-(long long)f.matched));
+  }
+}
+
+__global__ void k_tile_min_pending(TView v, unsigned long long *out) {
+  MinFn f{v.ctl->gvt, ~0ull};
+  for (uint32_t t = blockIdx.x; t < v.NT; t += gridDim.x) for_tile_records(v, t, threadIdx.x, blockDim.x, f);
+  unsigned long long tmin = f.tmin;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, tmin, o); tmin = t2 < tmin ? t2 : tmin; }
+  if ((threadIdx.x & 31) == 0 && tmin != ~0ull) atomicMin(out, tmin);
+}
+
+__global__ void k_tile_digest(TView v, int stw, unsigned long long *out) {
+  uint64_t acc[4] = {0, 0, 0, 0};
+  for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < v.A; lp += gridDim.x * blockDim.x) tile_digest_lp(v, stw, lp, acc);
+  DigestFn f{v.ctl->gvt, acc};
+  for (uint32_t t = blockIdx.x; t < v.NT; t += gridDim.x) for_tile_records(v, t, threadIdx.x, blockDim.x, f);
+  atomicXor(&out[0], (unsigned long long)acc[0]);
+  atomicAdd(&out[1], (unsigned long long)acc[1]);
+  atomicAdd(&out[2], (unsigned long long)acc[2]);
+  atomicAdd(&out[3], (unsigned long long)acc[3]);
+}
+
+#define TCU(call)                                                                                                      \
+  do {                                                                                                                 \
+    cudaError_t _e = (call);                                                                                           \
+    if (_e != cudaSuccess) return tile_fail(DEVA_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct CudaBE {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<void *> allocs;
+  cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  TCtl *h_ctl = nullptr;              // pinned
+  unsigned long long *d_tmp = nullptr;
+  unsigned long long *h_tmp = nullptr;
+  char *stage = nullptr;
+  size_t stage_bytes = 0;
+  int grid = 0;
+  size_t smem = 0;
+  bool smem_set[2] = {false, false};
+
+  int open(int dev, uint32_t rcap) {
+    device = dev;
+    TCU(cudaSetDevice(dev));
+    TCU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto &p : ev) for (auto &e : p) TCU(cudaEventCreate(&e));
+    TCU(cudaHostAlloc((void **)&h_ctl, sizeof(TCtl), cudaHostAllocDefault));
+    TCU(cudaHostAlloc((void **)&h_tmp, 64, cudaHostAllocDefault));
+    TCU(cudaMalloc((void **)&d_tmp, 64));
+    cudaDeviceProp prop;
+    TCU(cudaGetDeviceProperties(&prop, dev));
+    smem = blk_bytes(rcap);
+    if (smem > (size_t)prop.sharedMemPerBlockOptin) return tile_fail(DEVA_B200_ERR_ARG, "DEVA_B200_TILE_RCAP=%u needs %zu bytes of shared memory per block", rcap, smem);
+    int per_sm = (int)((size_t)prop.sharedMemPerMultiprocessor / (smem + 1024));
+    per_sm = std::max(1, std::min(per_sm, (int)env_u32("DEVA_B200_TILE_BLOCKS_PER_SM", 8)));
+    per_sm = std::min(per_sm, prop.maxThreadsPerMultiProcessor / TILE);
+    grid = prop.multiProcessorCount * per_sm;
+    return 0;
+  }
+  int grid_blocks() const { return grid; }
+  int alloc(void **p, size_t bytes) {
+    cudaError_t r = cudaMalloc(p, bytes ? bytes : 16);
+    if (r != cudaSuccess) return tile_fail(DEVA_B200_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(r));
+    allocs.push_back(*p);
+    return 0;
+  }
+  void free_all() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (void *p : allocs) cudaFree(p);
+    allocs.clear();
+    if (stage) cudaFree(stage);
+    if (d_tmp) cudaFree(d_tmp);
+    if (h_ctl) cudaFreeHost(h_ctl);
+    if (h_tmp) cudaFreeHost(h_tmp);
+    for (auto &p : ev) for (auto &e : p) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr; stage = nullptr; d_tmp = nullptr; h_ctl = nullptr; h_tmp = nullptr;
+  }
+  int zero(void *p, size_t n) { TCU(cudaMemsetAsync(p, 0, n, stream)); return 0; }
+  int fill_ff(void *p, size_t n) { TCU(cudaMemsetAsync(p, 0xff, n, stream)); return 0; }
+  int d2d(void *d, const void *s, size_t n) { TCU(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream)); return 0; }
+  int read_ctl(const TView &v, TCtl *out) {
+    TCU(cudaMemcpyAsync(h_ctl, v.ctl, sizeof(TCtl), cudaMemcpyDeviceToHost, stream));
+    TCU(cudaStreamSynchronize(stream));
+    *out = *h_ctl;
+    return 0;
+  }
+  int write_ctl(const TView &v, const TCtl *in) {
+    *h_ctl = *in;
+    TCU(cudaMemcpyAsync(v.ctl, h_ctl, sizeof(TCtl), cudaMemcpyHostToDevice, stream));
+    TCU(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int read_ctl_set_stop(const TView &v, TCtl *out, uint32_t stop) {
+    int rc = read_ctl(v, out);
+    if (rc) return rc;
+    if (out->stop_req != stop) {   // (the stream is idle: no kernel reads the block now)
+      h_tmp[4] = stop;
+      TCU(cudaMemcpyAsync(&v.ctl->stop_req, &h_tmp[4], sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    }
+    return 0;
+  }
+  void timer_start(int i) { cudaEventRecord(ev[i][0], stream); }
+  double timer_stop(int i) {
+    cudaEventRecord(ev[i][1], stream);
+    cudaEventSynchronize(ev[i][1]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev[i][0], ev[i][1]);
+    return ms;
+  }
+  int stage_reserve(size_t bytes) {
+    if (bytes <= stage_bytes) return 0;
+    if (stage) cudaFree(stage);
+    stage = nullptr; stage_bytes = 0;
+    cudaError_t r = cudaMalloc((void **)&stage, bytes);
+    if (r != cudaSuccess) return tile_fail(DEVA_B200_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(r));
+    stage_bytes = bytes;
+    return 0;
+  }
+
+  template <class M>
+  int k_init(const TView &v, const ModelParams &mp, int init_state) {
+    TCU(cudaSetDevice(device));
+    const uint32_t n = v.NT * TILE;
+    k_tile_init<M><<<(n + 255) / 256, 256, 0, stream>>>(v, mp, init_state);
+    TCU(cudaGetLastError());
+    return 0;
+  }
+  template <class M>
+  int k_seed(const TView &v, const ModelParams &mp, uint32_t k, int rootdiv, uint64_t per) {
+    k_tile_seed<M><<<(v.A + 255) / 256, 256, 0, stream>>>(v, mp, k, rootdiv, per);
+    TCU(cudaGetLastError());
+    return 0;
+  }
+  int k_roots(const TView &v, uint64_t n, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload) {
+    TCU(cudaSetDevice(device));
+    if (n == 0) return 0;
+    if (n > 0xffffffffull) return tile_fail(DEVA_B200_ERR_ARG, "too many roots in one call");
+    int rc = stage_reserve(n * 24);
+    if (rc) return rc;
+    uint64_t *d_t = (uint64_t *)stage, *d_s = d_t + n;
+    uint32_t *d_l = (uint32_t *)(d_s + n), *d_p = d_l + n;
+    TCU(cudaMemcpyAsync(d_t, time, n * 8, cudaMemcpyHostToDevice, stream));
+    TCU(cudaMemcpyAsync(d_s, sub, n * 8, cudaMemcpyHostToDevice, stream));
+    TCU(cudaMemcpyAsync(d_l, lp, n * 4, cudaMemcpyHostToDevice, stream));
+    TCU(cudaMemcpyAsync(d_p, payload, n * 4, cudaMemcpyHostToDevice, stream));
+    const unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    k_tile_roots<<<g, 256, 0, stream>>>(v, d_t, d_s, d_l, d_p, (uint32_t)n);
+    TCU(cudaGetLastError());
+    return 0;
+  }
+  int k_begin(const TView &v, const TParams &tp, uint64_t t_end) {
+    TCU(cudaSetDevice(device));
+    k_tile_begin<<<1, 32, 0, stream>>>(v, tp, t_end);
+    TCU(cudaGetLastError());
+    return 0;
+  }
+  template <class M>
+  int k_step(const TView &v, const ModelParams &mp, const TParams &tp) {
+    const int mi = M::MODEL_ID == 2 ? 1 : 0;
+    if (!smem_set[mi]) {
+      TCU(cudaFuncSetAttribute(k_tile_step<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[mi] = true;
+    }
+    k_tile_step<M><<<grid, TILE, smem, stream>>>(v, mp, tp);
+    TCU(cudaGetLastError());
+    return 0;
+  }
+  int k_net_pending(const TView &v) {
+    k_tile_net_pending<<<std::min<uint32_t>(v.NT, 148 * 8), 256, 0, stream>>>(v);
+    TCU(cudaGetLastError());
+    return 0;
+  }
+  int k_min_pending(const TView &v, uint64_t *out) {
+    TCU(cudaMemsetAsync(d_tmp, 0xff, 8, stream));
+    k_tile_min_pending<<<std::min<uint32_t>(v.NT, 148 * 8), 256, 0, stream>>>(v, d_tmp);
+    TCU(cudaGetLastError());
+    TCU(cudaMemcpyAsync(h_tmp, d_tmp, 8, cudaMemcpyDeviceToHost, stream));
+    TCU(cudaStreamSynchronize(stream));
+    *out = h_tmp[0];
+    return 0;
+  }
+  int k_digest(const TView &v, int stw, uint64_t out[4]) {
+    TCU(cudaSetDevice(device));
+    TCU(cudaMemsetAsync(d_tmp, 0, 32, stream));
+    k_tile_digest<<<std::min<uint32_t>(v.NT, 148 * 8), 256, 0, stream>>>(v, stw, d_tmp);
+    TCU(cudaGetLastError());
+    TCU(cudaMemcpyAsync(h_tmp, d_tmp, 32, cudaMemcpyDeviceToHost, stream));
+    TCU(cudaStreamSynchronize(stream));
+    for (int i = 0; i < 4; i++) out[i] = h_tmp[i];
+    return 0;
+  }
+  int k_state(const TView &v, uint32_t first, uint32_t count, int stw, uint64_t *words, int to_device) {
+    TCU(cudaSetDevice(device));
+    if (count == 0) return 0;
+    int rc = stage_reserve((size_t)count * stw * 8);
+    if (rc) return rc;
+    uint64_t *tmp = (uint64_t *)stage;
+    if (to_device) TCU(cudaMemcpyAsync(tmp, words, (size_t)count * stw * 8, cudaMemcpyHostToDevice, stream));
+    k_tile_state<<<(count + 255) / 256, 256, 0, stream>>>(v, tmp, first, count, stw, to_device);
+    TCU(cudaGetLastError());
+    if (!to_device) TCU(cudaMemcpyAsync(words, tmp, (size_t)count * stw * 8, cudaMemcpyDeviceToHost, stream));
+    TCU(cudaStreamSynchronize(stream));
+    return 0;
+  }
+};
+
+}  // namespace tl
+}  // namespace deva_b200

@@ -19,6 +19,7 @@
 #include "../../include/deva_b200.h"
 #include "../../devastator_b200/csrc/pdes_core.cuh"
 #include "../../devastator_b200/csrc/window_policy.h"
+#include "emu_tile.hpp"
 
 using namespace deva_b200;
 
@@ -31,7 +32,21 @@ static int fail(int code, const char *fmt, ...) {
   return code;
 }
 
+namespace deva_b200 { namespace tl {
+int tile_fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+} }
+typedef deva_b200::tl::TileEngine<deva_b200::tl::HostBE> EmuTile;
+// DEVA_B200_ENGINE=lp selects the first engine (one thread per LP, per-LP pools); default: the tile engine
+static bool want_tile() { const char *k = getenv("DEVA_B200_ENGINE"); return !(k && !strcmp(k, "lp")); }
+
 struct deva_b200_engine {
+  EmuTile *tile = nullptr;
   deva_b200_config cfg;
   ModelParams mp;
   View v;
@@ -85,6 +100,13 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   deva_b200_engine *e = new deva_b200_engine;
   e->cfg = *cfg;
   e->stw = cfg->model == DEVA_B200_MODEL_PHOLD_BENCH ? PholdBench::STW : PholdTest::STW;
+  if (want_tile()) {
+    e->tile = new EmuTile;
+    const int rc = e->tile->create(cfg);
+    if (rc) { e->tile->destroy(); delete e->tile; delete e; return rc; }
+    *out = e;
+    return 0;
+  }
   e->mp.lp_n_model = cfg->mp.lp_n_model;
   e->mp.p_remote_thresh = cfg->mp.p_remote_thresh;
   e->mp.neg_lambda = -cfg->mp.lambda;
@@ -130,16 +152,19 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
 
 void deva_b200_destroy(deva_b200_engine *e) {
   if (!e) return;
+  if (e->tile) { e->tile->destroy(); delete e->tile; }
   for (void *p : e->allocs) free(p);
   delete e;
 }
 
 int deva_b200_set_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t count, const uint64_t *words) {
+  if (e->tile) return e->tile->set_state(lp_first, count, words);
   for (uint64_t i = 0; i < count; i++)
     for (int w = 0; w < e->stw; w++) e->v.st[(size_t)w * e->v.A + (lp_first - e->v.lp_begin) + i] = words[i * e->stw + w];
   return 0;
 }
 int deva_b200_get_lp_state(deva_b200_engine *e, uint64_t lp_first, uint64_t count, uint64_t *words) {
+  if (e->tile) return e->tile->get_state(lp_first, count, words);
   for (uint64_t i = 0; i < count; i++)
     for (int w = 0; w < e->stw; w++) words[i * e->stw + w] = e->v.st[(size_t)w * e->v.A + (lp_first - e->v.lp_begin) + i];
   return 0;
@@ -153,6 +178,7 @@ static int check_err(deva_b200_engine *e) {
 
 int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time, const uint64_t *subtime,
                           const uint32_t *lp, const uint32_t *payload) {
+  if (e->tile) return e->tile->roots(n, time, subtime, lp, payload);
   for (uint64_t i = 0; i < n; i++) {
     EvRec r; r.time = time[i]; r.sub = subtime[i]; r.p0 = payload[i]; r.p1 = 0; r.dst = lp[i]; r.flags = 0;
     deliver_to_pending(e->v, r, &e->ctl.err);
@@ -161,6 +187,7 @@ int deva_b200_root_events(deva_b200_engine *e, uint64_t n, const uint64_t *time,
 }
 
 int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k, int32_t rootdiv, int32_t ranks) {
+  if (e->tile) return e->tile->seed(k, rootdiv, ranks);
   View &v = e->v;
   if (k > v.pq_cap) return fail(DEVA_B200_ERR_CAPACITY, "k_per_lp exceeds pq_cap");
   const int R = ranks > 0 ? ranks : 1;
@@ -175,8 +202,8 @@ int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k, int32_t rootdiv, int32
   return 0;
 }
 
-int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) { e->mp.stop = stop; return 0; }
-int deva_b200_reset(deva_b200_engine *e) { init_lps(e, 0); e->par = 0; e->has_rewind = false; return 0; }
+int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) { if (e->tile) { e->tile->stop_req = stop; return 0; } e->mp.stop = stop; return 0; }
+int deva_b200_reset(deva_b200_engine *e) { if (e->tile) return e->tile->reset(); init_lps(e, 0); e->par = 0; e->has_rewind = false; return 0; }
 
 // ---- lockstep multi-engine driver (stands in for one process per GPU + NCCL) ---------------------
 static void pass_one(deva_b200_engine *e, const PassArgs &pa, bool full, uint64_t *wx, uint64_t *wr) {
@@ -303,11 +330,13 @@ int emu_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewind
 }
 
 int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out) {
+  if (e->tile) return e->tile->drain(t_end, rewindable, gvt_out);
   if (e->cfg.n_gpus != 1) return fail(DEVA_B200_ERR_STATE, "emu: use emu_drain_multi for n_gpus > 1");
   return emu_drain_multi(&e, 1, t_end, rewindable, gvt_out);
 }
 
 int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind) {
+  if (e->tile) return e->tile->rewind(do_rewind);
   if (!e->has_rewind) return fail(DEVA_B200_ERR_STATE, "rewind without a rewindable drain");
   e->has_rewind = false;
   if (do_rewind) {
@@ -321,6 +350,7 @@ int deva_b200_rewind(deva_b200_engine *e, int32_t do_rewind) {
 }
 
 int deva_b200_get_stats(deva_b200_engine *e, deva_b200_stats *out) {
+  if (e->tile) return e->tile->get_stats(out);
   memset(out, 0, sizeof *out);
   out->executed_n = e->ctl.cnt[0][CNT_EXEC]; out->committed_n = e->ctl.cnt[0][CNT_COMMIT];
   out->deterministic = (e->ctl.cnt[0][CNT_FLAGS] >> 31) ? 0 : 1;
@@ -330,6 +360,7 @@ int deva_b200_get_stats(deva_b200_engine *e, deva_b200_stats *out) {
 }
 
 int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]) {
+  if (e->tile) return e->tile->digest(out);
   out[0] = out[1] = out[2] = out[3] = 0;
   for (uint32_t lp = 0; lp < e->v.A; lp++) digest_lp(e->v, e->stw, lp, out);
   return 0;
@@ -337,7 +368,7 @@ int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]) {
 
 int deva_b200_comm_unique_id(void *uid128) { memset(uid128, 0, 128); return 0; }
 int deva_b200_comm_init(deva_b200_engine *, const void *) { return 0; }
-void emu_set_shuffle(deva_b200_engine *e, uint64_t seed) { e->shuffle = seed; }
+void emu_set_shuffle(deva_b200_engine *e, uint64_t seed) { if (e->tile) e->tile->be.shuffle = seed; e->shuffle = seed; }
 // what deva_b200_comm_init does with CUDA IPC: every engine gets a pointer to ITS region of every
 // peer's receive buffer, and lp_pass stores cross-GPU records there directly
 void emu_enable_peer_delivery(deva_b200_engine **es, int G) {
