@@ -480,7 +480,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
 
 void deva_b200_destroy(deva_b200_engine *e) {
   if (!e) return;
-  if (e->tile) { e->tile->destroy(); delete e->tile; delete e; return; }
+  if (e->tile) { cudaSetDevice(e->cfg.device); for (void *p : e->tile->ipc_open) cudaIpcCloseMemHandle(p); e->tile->destroy(); delete e->tile; delete e; return; }
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void *p : e->ipc_open) cudaIpcCloseMemHandle(p);
@@ -968,6 +968,49 @@ int deva_b200_comm_unique_id(void *uid128) {
   return 0;
 }
 
+// TILE engine: NCCL is plumbing only - one all-gather of the CUDA IPC handles of the engines' comm
+// blocks at start-up.  Every round of a drain is then closed on the device (k_tile_xchg): records are
+// stored straight into the peer's receive region by the step kernel, counts / figures / tags by plain
+// and release stores into the peer's mailboxes.
+static int tile_comm_init(deva_b200_engine *e, const NcclUid &uid) {
+  CudaTile *t = e->tile;
+  const int G = e->cfg.n_gpus, me = e->cfg.gpu_rank;
+  cudaStream_t st = t->be.stream;
+  void *comm = nullptr;
+  NC(g_nccl.CommInitRank(&comm, G, uid, me));
+  cudaIpcMemHandle_t mine;
+  unsigned long long ok = 1;
+  if (cudaIpcGetMemHandle(&mine, t->comm_block) != cudaSuccess) { ok = 0; memset(&mine, 0, sizeof mine); cudaGetLastError(); }
+  cudaIpcMemHandle_t *d_all = nullptr;
+  unsigned long long *d_ok = nullptr;
+  CU(cudaMalloc((void **)&d_all, sizeof(mine) * (G + 1)));
+  CU(cudaMalloc((void **)&d_ok, 16));
+  CU(cudaMemcpyAsync(d_all + G, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
+  int nrc = g_nccl.AllGather(d_all + G, d_all, sizeof(mine), NC_U8, comm, st);
+  std::vector<cudaIpcMemHandle_t> all(G);
+  if (!nrc) {
+    CU(cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * G, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int g = 0; g < G && ok; g++) {
+      if (g == me) continue;
+      void *pb = nullptr;
+      if (cudaIpcOpenMemHandle(&pb, all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      t->ipc_open.push_back(pb);
+      t->map_peer(g, pb);
+    }
+    CU(cudaMemcpyAsync(d_ok, &ok, 8, cudaMemcpyHostToDevice, st));
+    nrc = g_nccl.AllReduce(d_ok, d_ok + 1, 1, NC_U64, NC_MIN, comm, st);
+    CU(cudaMemcpyAsync(&ok, d_ok + 1, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  cudaFree(d_all); cudaFree(d_ok);
+  g_nccl.CommDestroy(comm);
+  if (nrc) return fail(DEVA_B200_ERR_COMM, "NCCL failed while exchanging IPC handles: %s", g_nccl.GetErrorString(nrc));
+  if (!ok) return fail(DEVA_B200_ERR_COMM, "CUDA IPC peer mapping unavailable: the tile engine needs it (DEVA_B200_ENGINE=lp has a staged NCCL transport)");
+  t->peers_ready();
+  return 0;
+}
+
 int deva_b200_comm_init(deva_b200_engine *e, const void *uid128) {
   if (!e || !uid128) return fail(DEVA_B200_ERR_ARG, "null argument");
   if (e->cfg.n_gpus == 1) return 0;
@@ -976,6 +1019,7 @@ int deva_b200_comm_init(deva_b200_engine *e, const void *uid128) {
   CU(cudaSetDevice(e->cfg.device));
   NcclUid uid;
   memcpy(uid.b, uid128, 128);
+  if (e->tile) return tile_comm_init(e, uid);
   NC(g_nccl.CommInitRank(&e->comm, e->cfg.n_gpus, uid, e->cfg.gpu_rank));
   // Peer delivery: map every peer's receive buffer with CUDA IPC (one process per GPU).
   // DEVA_B200_XCHG=nccl keeps the staged exchange (sendbuf + NCCL send/recv); so does a box where

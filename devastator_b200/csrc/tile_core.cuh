@@ -207,8 +207,7 @@ DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uin
   }
   const uint64_t b = rec.time >> ep.shift;
   const uint64_t d = b - ep.cur_abs;                 // (wraps to huge when b < cur_abs: goes to far, flagged)
-  const bool ring = ep.in_epoch ? (d >= 1 && d < NB) : (d < NB);
-  if (ring) {
+  if (d < NB) {   // (the open bucket itself only when t_end cuts it: evaluations read its count as of the epoch's start)
     const uint32_t slot = (uint32_t)(b % NB);
     const uint32_t p = atom_add_u32(&v.ncnt[(size_t)tile * NB + slot], 1u);
     if (p < v.C) {
@@ -219,7 +218,13 @@ DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uin
     // list full: the record waits in the far list (readers clamp ncnt to C)
   }
   const uint32_t p = atom_add_u32(&v.fcnt[tile], 1u);
-  if (p >= v.CF) { *err |= ERR_FAR_OVERFLOW; return; }
+  if (p >= v.CF) {
+#if !defined(__CUDA_ARCH__) && defined(DEVA_TILE_DEBUG)
+    fprintf(stderr, "far overflow: t=%llu flags=%u cur=%llu ub=%llu gvt=%llu shift=%u in_epoch=%u d=%llu ncnt=%u\n", (unsigned long long)rec.time, rec.flags, (unsigned long long)ep.cur_abs,
+            (unsigned long long)ep.ub, (unsigned long long)ep.gvt, ep.shift, ep.in_epoch, (unsigned long long)d, d < NB ? v.ncnt[(size_t)tile * NB + (b % NB)] : 0u);
+#endif
+    *err |= ERR_FAR_OVERFLOW; return;
+  }
   st_ev(&v.far_[(size_t)tile * v.CF + p], rec);
   atom_add_u64(&c->far_total, 1ull);
   if (d < NB) {                                      // belongs to the ring (its list is full, or it is the open bucket's
@@ -494,8 +499,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
   TL_THREADS(tid) {
     if (tid != 0) continue;
     h.slot = (uint32_t)(ep.cur_abs % NB);
-    const uint32_t nc = v.ncnt[(size_t)tile * NB + h.slot];
-    h.nb = nc < v.C ? nc : v.C;
+    h.nb = v.npub[tile];                           // (records appended to the open bucket since lie beyond ub)
     const uint32_t lc = v.lcnt[rd][tile];
     h.nl = lc < v.CL ? lc : v.CL;                  // all of it is complete: this launch appends to the other list
     h.first = v.tev[tile] != ep.epoch;
@@ -820,16 +824,33 @@ DEVA_HD void policy_update(TCtl *c, const TParams &tp, const Glob &g) {
   else if (eff_pm > tp.pol_hi_pm && dens_x16 < tp.pol_density_x16 && c->shift < 40) { c->want_shift = c->shift + 1; c->hold = 2; }
 }
 
+// An epoch opens: every tile's count of the open bucket is frozen (all threads of the closing block).
+DEVA_HD void open_epoch_snapshot(const TView &v) {
+  const TCtl *c = v.ctl;
+  if (c->phase != PH_EVAL || !c->full) return;
+  const uint32_t slot = (uint32_t)(c->cur_abs % NB);
+  TL_THREADS(tid) {
+    for (uint32_t t = tid; t < v.NT; t += TILE) {
+      const uint32_t nc = v.ncnt[(size_t)t * NB + slot];
+      v.npub[t] = nc < v.C ? nc : v.C;
+    }
+  }
+  TL_SYNC();
+}
+
 // Runs once per launch, by the last block to finish (one GPU) or by the exchange kernel after the
 // peers' figures are in (several GPUs): follow-up launch, epoch commit, or calendar maintenance next.
 DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
   TCtl *c = v.ctl;
-  const uint32_t phase = c->phase;
-  if (phase == PH_EVAL && g.dirty_n == 0) {
+  // (read by every thread before thread 0 moves the state machine on)
+  const uint32_t phase = c->phase, epoch = c->epoch;
+  const uint32_t slot = (uint32_t)(c->cur_abs % NB);
+  const bool whole = c->ub == bucket_end(c->cur_abs, c->shift);
+  const bool commit = phase == PH_EVAL && g.dirty_n == 0 && !g.err;
+  TL_SYNC();
+  if (commit) {
     // ---- epoch commit (fossil collection, pdes.cxx:816-871): everything below ub is final.  The
     // tiles that ran swap their state buffers; a bucket consumed to its end gives its lists back.
-    const bool whole = c->ub == bucket_end(c->cur_abs, c->shift);
-    const uint32_t slot = (uint32_t)(c->cur_abs % NB), epoch = c->epoch;
     TL_THREADS(tid) {
       for (uint32_t t = tid; t < v.NT; t += TILE) {
         if (v.tev[t] == epoch) v.tcur[t] ^= 1u;
@@ -852,8 +873,7 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
         c->full = 0; c->par ^= 1u;
         continue;
       }
-      const bool whole = c->ub == bucket_end(c->cur_abs, c->shift);
-      if (whole) c->btotal[c->cur_abs % NB] = 0;
+      if (whole) c->btotal[slot] = 0;
       c->gvt = c->ub;
       c->epochs++;
       for (int i = 0; i < 2; i++) c->sp_n[i] = c->sp_start[i] = c->sp_fresh[i] = 0;
@@ -862,7 +882,7 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
       policy_update(c, tp, g);
       if (c->gvt >= c->t_end) { c->phase = PH_DONE; c->in_epoch = 0; continue; }
       Glob g2 = g;
-      if (whole) g2.btotal[c->cur_abs % NB] = 0;
+      if (whole) g2.btotal[slot] = 0;
       choose_next(c, tp, g2, !whole);
     } else if (phase == PH_REBIN) {
       Glob g2;
@@ -872,17 +892,23 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
     }
   }
   TL_SYNC();
+  open_epoch_snapshot(v);
 }
 
-// drain entry: latch t_end, pick the first epoch
+// drain entry: latch t_end, pick the first epoch (thread 0), freeze the open bucket's counts (all threads)
 DEVA_HD void begin_drain(const TView &v, const TParams &tp, uint64_t t_end, const Glob &g) {
   TCtl *c = v.ctl;
-  c->t_end = t_end;
-  c->work = 0; c->ticket = 0;
-  c->stop = c->stop_req;
-  c->pol_epochs = 0; c->e_exec0 = g.executed; c->e_commit0 = g.committed;
-  if (c->gvt >= t_end) { c->phase = PH_DONE; return; }
-  choose_next(c, tp, g, true);
+  TL_THREADS(tid) {
+    if (tid != 0) continue;
+    c->t_end = t_end;
+    c->work = 0; c->ticket = 0;
+    c->stop = c->stop_req;
+    c->pol_epochs = 0; c->e_exec0 = g.executed; c->e_commit0 = g.committed;
+    if (c->gvt >= t_end) { c->phase = PH_DONE; continue; }
+    choose_next(c, tp, g, true);
+  }
+  TL_SYNC();
+  open_epoch_snapshot(v);
 }
 
 // ---- setup -------------------------------------------------------------------------------------------
@@ -956,6 +982,28 @@ DEVA_HD void tile_digest_rec(const EvRec &e, uint64_t gvt, uint64_t out[4]) {
   if (!rec_live(e, gvt)) return;
   out[2] += 1;
   out[3] += mix64(e.time ^ mix64(e.sub ^ mix64(((uint64_t)e.p0 << 32 | e.dst) + (e.flags & EV_ANTI))));
+}
+
+// ---- several GPUs: what one GPU tells the others once per round, and how the answers fold ----------
+// (replaces gvt.cxx's tree reduction rdxn_up/rdxn_down, gvt.cxx:78-149, and the credit counters of
+// gvt.hxx:50-57: a round is closed by every GPU, so nothing is in flight when the figures are taken)
+DEVA_HD void make_peer_msg(const TView &v, PeerMsg &m) {
+  const TCtl *c = v.ctl;
+  m.dirty_n = c->dirty_n[c->par]; m.err = c->err; m.far_min = c->far_min; m.min_b = 0;
+  m.executed = c->executed; m.committed = c->committed; m.rolled = c->rolled; m.far_total = c->far_total;
+  for (int i = 0; i < NB; i++) m.btotal[i] = c->btotal[i];
+  m.antis_pending = (unsigned long long)c->antis_pending; m.ovf_flag = c->ovf_flag | (c->need_rebase << 1); m.pad0 = m.pad1 = 0;
+}
+DEVA_HD void fold_peer_msgs(const PeerMsg *msgs, int G, Glob &g) {
+  for (int i = 0; i < NB; i++) g.btotal[i] = 0;
+  g.far_total = 0; g.far_min = ~0ull; g.executed = 0; g.committed = 0; g.dirty_n = 0; g.err = 0; g.ovf_flag = 0; g.need_rebase = 0;
+  for (int k = 0; k < G; k++) {
+    const PeerMsg &m = msgs[k];
+    for (int i = 0; i < NB; i++) g.btotal[i] += m.btotal[i];
+    g.far_total += m.far_total; if (m.far_min < g.far_min) g.far_min = m.far_min;
+    g.executed += m.executed; g.committed += m.committed; g.dirty_n += m.dirty_n; g.err |= m.err;
+    g.ovf_flag |= (uint32_t)(m.ovf_flag & 1ull); g.need_rebase |= (uint32_t)((m.ovf_flag >> 1) & 1ull);
+  }
 }
 
 // every record position of one tile, strided over `nthr` callers: f(EvRec *)

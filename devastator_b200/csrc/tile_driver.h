@@ -71,6 +71,10 @@ struct TileEngine {
   struct Snap { void *live, *copy; size_t bytes; };
   std::vector<Snap> snaps;
   TCtl snap_ctl;
+  void *comm_block = nullptr;
+  size_t comm_bytes = 0, off_mbox = 0, off_tag1 = 0, off_tag2 = 0, off_count = 0;
+  uint32_t send_cap = 0;
+  std::vector<void *> ipc_open;   // peer mappings to close
   // drain timer (counterpart of the reference's DrainTimer, pdes.hxx:139-308): one CSV row per batch
   std::string timer_path;
 
@@ -103,7 +107,7 @@ struct TileEngine {
     const size_t NT = v.NT, LP = NT * TILE;
 #define TA(p, n) if ((rc = be.alloc((void **)&(p), (size_t)(n) * sizeof(*(p))))) return rc;
     TA(v.st[0], LP) TA(v.st[1], LP) TA(v.tcur, NT) TA(v.tev, NT) TA(v.tflags, NT)
-    TA(v.near_, NT * NB * v.C) TA(v.ncnt, NT * NB)
+    TA(v.near_, NT * NB * v.C) TA(v.ncnt, NT * NB) TA(v.npub, NT)
     TA(v.late[0], NT * v.CL) TA(v.late[1], NT * v.CL) TA(v.lcnt[0], NT) TA(v.lcnt[1], NT) TA(v.lseen[0], NT) TA(v.lseen[1], NT) TA(v.dmark, NT)
     TA(v.far_, NT * v.CF) TA(v.fcnt, NT) TA(v.fpub, NT)
     TA(v.dirty[0], NT) TA(v.dirty[1], NT) TA(v.ctl, 1)
@@ -112,6 +116,19 @@ struct TileEngine {
     v.scratch_cap = env_u32("DEVA_B200_TILE_SCRATCH", 24576);
     TA(v.scratch, (size_t)be.grid_blocks() * v.scratch_cap)
 #undef TA
+    if (c->n_gpus > 1) {
+      // comm block (one allocation, mapped by every peer with CUDA IPC): the receive regions - region g is
+      // written by GPU g's step kernel over NVLink - and the mailboxes of the device-side exchange
+      const size_t per_lp = std::max<uint32_t>(1, env_u32("DEVA_B200_SEND_CAP_PER_LP", 4));
+      send_cap = (uint32_t)std::min<size_t>(std::max<size_t>((size_t)v.A * per_lp, 1u << 16), 1u << 27);
+      off_mbox = (size_t)send_cap * c->n_gpus * sizeof(EvRec);
+      off_tag1 = off_mbox + 2 * MAX_GPUS * sizeof(PeerMsg);
+      off_tag2 = off_tag1 + MAX_GPUS * 8;
+      off_count = off_tag2 + MAX_GPUS * 8;
+      comm_bytes = off_count + 2 * MAX_GPUS * 4;
+      if ((rc = be.alloc(&comm_block, comm_bytes)) || (rc = be.zero(comm_block, comm_bytes))) return rc;
+      set_comm_ptrs((char *)comm_block, &v.recvbuf, &v.mbox, &v.mtag1, &v.mtag2, &v.mcount);
+    }
     if ((rc = be.zero(v.ctl, sizeof(TCtl)))) return rc;
     memset(&hc, 0, sizeof hc);
     // window: a fixed width is rounded down to a power of two (the bucket width); 0 = adaptive, starting at 16
@@ -142,6 +159,18 @@ struct TileEngine {
     for (int i = 0; i < MAX_GPUS; i++) hc.send_n[i] = 0;
     return be.write_ctl(v, &hc);
   }
+
+  void set_comm_ptrs(char *base, EvRec **recv, PeerMsg **mbox, unsigned long long **t1, unsigned long long **t2, uint32_t **cnt) const {
+    *recv = (EvRec *)base; *mbox = (PeerMsg *)(base + off_mbox); *t1 = (unsigned long long *)(base + off_tag1);
+    *t2 = (unsigned long long *)(base + off_tag2); *cnt = (uint32_t *)(base + off_count);
+  }
+  // peer g's comm block is mapped at `base` (CUDA IPC / peer access; the emulation passes the peer's host block)
+  void map_peer(int g, void *base) {
+    EvRec *recv;
+    set_comm_ptrs((char *)base, &recv, &v.peer_mbox[g], &v.peer_tag1[g], &v.peer_tag2[g], &v.peer_count[g]);
+    v.peer_buf[g] = recv + (size_t)v.gpu_rank * send_cap;   // this GPU's region in g's receive buffer
+  }
+  void peers_ready() { v.peer_cap = send_cap; }
 
   int init_states(int init_state) {
     int rc = tile_dispatch_model(cfg.model, [&](auto m) { return be.template k_init<typename decltype(m)::type>(v, mp, init_state); });
@@ -184,6 +213,7 @@ struct TileEngine {
 
   int drain(uint64_t t_end, int rewindable, uint64_t *gvt_out) {
     if (has_rewind) return tile_fail(DEVA_B200_ERR_STATE, "lingering rewind state: call deva_b200_rewind first (pdes.cxx:705-708)");
+    if (cfg.n_gpus > 1 && !v.peer_cap) return tile_fail(DEVA_B200_ERR_STATE, "n_gpus > 1 but deva_b200_comm_init was not called");
     int rc;
     be.timer_start(0);
     if (rewindable && (rc = snapshot())) return rc;

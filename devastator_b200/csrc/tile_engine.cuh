@@ -18,6 +18,42 @@ namespace tl {
 #define DEVA_TILE_MINB 3   // resident blocks per SM the register allocator must allow
 #endif
 
+// ---- several GPUs: device-side exchange over the peers' IPC-mapped comm blocks (NVLink) ---------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long x;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(x) : "l"(p) : "memory");
+  return x;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long x) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory");
+}
+// waits until *p >= tag; gives up after ~20 s (a peer died): never hangs the GPU
+__device__ __forceinline__ bool wait_tag(const unsigned long long *p, unsigned long long tag) {
+  unsigned long long t0 = 0;
+  for (uint32_t it = 0;; it++) {
+    if (ld_acquire_sys(p) >= tag) return true;
+    __nanosleep(64);
+    if ((it & 1023u) == 1023u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (!t0) t0 = now;
+      else if (now - t0 > 20000000000ull) return false;
+    }
+  }
+}
+// end of a step launch: tell every peer how many records this GPU stored into its receive region
+// (the records themselves were written by all blocks before their tickets; __threadfence_system there)
+__device__ __forceinline__ void publish_counts(const TView &v) {
+  TCtl *c = v.ctl;
+  const unsigned long long tag = (unsigned long long)c->round + 1ull;
+  const uint32_t g = threadIdx.x;
+  if (g < (uint32_t)v.n_gpus && g != (uint32_t)v.gpu_rank) {
+    v.peer_count[g][(c->round & 1u) * MAX_GPUS + v.gpu_rank] = c->send_n[g];
+    __threadfence_system();
+    st_release_sys(&v.peer_tag1[g][v.gpu_rank], tag);
+  }
+}
+
 template <class M>
 __global__ void __launch_bounds__(TILE, DEVA_TILE_MINB)
 k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams mp, const __grid_constant__ TParams tp) {
@@ -45,22 +81,135 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
   }
   // the last block to finish closes the launch: follow-up, epoch commit, or calendar maintenance next
   __shared__ uint32_t is_last;
-  __threadfence();
+  if (v.n_gpus > 1) __threadfence_system(); else __threadfence();   // (records stored into peer GPUs' memory, too)
   __syncthreads();
   if (threadIdx.x == 0) is_last = atomicAdd(&c->ticket, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (!is_last || v.n_gpus > 1) return;   // (several GPUs: the exchange kernel closes, once the peers' figures are in)
+  if (!is_last) return;
   __threadfence();
+  if (v.n_gpus > 1) {   // several GPUs: the exchange kernel closes the launch, once the peers' figures are in
+    publish_counts(v);
+    return;
+  }
   __shared__ Glob g;
   if (threadIdx.x == 0) glob_from_ctl(g, c, c->dirty_n[c->par]);
   __syncthreads();
   close_launch(v, tp, g);
 }
 
-__global__ void k_tile_begin(TView v, TParams tp, uint64_t t_end) {
-  if (threadIdx.x || blockIdx.x) return;
-  Glob g;
-  glob_from_ctl(g, v.ctl, 0);
+// One round's closing: receive what the peers stored here, exchange the job-wide figures, run the
+// epoch state machine - identically on every GPU, without the host and without NCCL.
+__global__ void __launch_bounds__(256) k_tile_xchg(const __grid_constant__ TView v, const __grid_constant__ TParams tp, const int begin_mode) {
+  TCtl *c = v.ctl;
+  const uint32_t phase = c->phase;
+  if (!begin_mode && phase != PH_EVAL && phase != PH_REBIN) return;
+  const int G = v.n_gpus, me = v.gpu_rank;
+  const uint32_t r = c->round;
+  const unsigned long long tag = (unsigned long long)r + 1ull;
+  __shared__ uint32_t counts[MAX_GPUS];
+  __shared__ uint32_t timeout, is_last;
+  __shared__ PeerMsg msgs[MAX_GPUS];
+  __shared__ Glob g;
+  if (threadIdx.x == 0) timeout = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < G) {
+    counts[threadIdx.x] = 0;
+    if ((int)threadIdx.x != me) {
+      if (!wait_tag(&v.mtag1[threadIdx.x], tag)) atomicOr(&timeout, 1u);
+      else { const uint32_t n = __ldcg(&v.mcount[(r & 1u) * MAX_GPUS + threadIdx.x]); counts[threadIdx.x] = n < v.peer_cap ? n : v.peer_cap; }
+    }
+  }
+  __syncthreads();
+  const Epoch ep = load_epoch(c);
+  uint32_t err = timeout ? (uint32_t)ERR_PEER_TIMEOUT : 0u;
+  for (int src = 0; src < G; src++) {
+    const uint32_t n = counts[src];
+    const EvRec *recs = v.recvbuf + (size_t)src * v.peer_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      append_local(v, ep, ld_ev_cg(&recs[i]), nullptr, &err);
+  }
+  if (err) atomicOr(&c->err, err);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&c->xticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // ---- last block: this GPU's figures to every peer, theirs back, one decision
+  if (threadIdx.x == 0) make_peer_msg(v, msgs[me]);
+  __syncthreads();
+  {
+    const uint32_t words = sizeof(PeerMsg) / 8;
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&msgs[me]);
+    for (int p = 0; p < G; p++) {
+      if (p == me) continue;
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(&v.peer_mbox[p][(r & 1u) * MAX_GPUS + me]);
+      for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < G && (int)threadIdx.x != me) {
+    st_release_sys(&v.peer_tag2[threadIdx.x][me], tag);
+    if (!wait_tag(&v.mtag2[threadIdx.x], tag)) atomicOr(&timeout, 1u);
+  }
+  __syncthreads();
+  {
+    const uint32_t words = sizeof(PeerMsg) / 8;
+    for (int p = 0; p < G; p++) {
+      if (p == me) continue;
+      const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&v.mbox[(r & 1u) * MAX_GPUS + p]);
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(&msgs[p]);
+      for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = __ldcg(&src[w]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    fold_peer_msgs(msgs, G, g);
+    if (timeout) g.err |= ERR_PEER_TIMEOUT;
+    c->round = r + 1u;
+    c->xticket = 0;
+  }
+  __syncthreads();
+  if (begin_mode) begin_drain(v, tp, c->t_end, g);
+  else close_launch(v, tp, g);
+}
+
+// drain entry with several GPUs: latch t_end, publish "no records", then k_tile_xchg(begin_mode) decides
+__global__ void k_tile_begin_multi(TView v, uint64_t t_end) {
+  if (blockIdx.x) return;
+  if (threadIdx.x == 0) { v.ctl->t_end = t_end; for (int i = 0; i < MAX_GPUS; i++) v.ctl->send_n[i] = 0; }
+  __syncthreads();
+  publish_counts(v);
+}
+
+// drain exit with several GPUs: min over the GPUs of their exact local minimum
+__global__ void k_tile_xmin(TView v, unsigned long long *io) {
+  TCtl *c = v.ctl;
+  const int G = v.n_gpus, me = v.gpu_rank;
+  const uint32_t r = c->round;
+  const unsigned long long tag = (unsigned long long)r + 1ull;
+  __shared__ uint32_t timeout;
+  __shared__ unsigned long long mn;
+  if (threadIdx.x == 0) { timeout = 0; mn = io[0]; }
+  __syncthreads();
+  if ((int)threadIdx.x < G && (int)threadIdx.x != me) {
+    const int p = threadIdx.x;
+    v.peer_mbox[p][(r & 1u) * MAX_GPUS + me].far_min = io[0];
+    __threadfence_system();
+    st_release_sys(&v.peer_tag2[p][me], tag);
+    st_release_sys(&v.peer_tag1[p][me], tag);
+    if (!wait_tag(&v.mtag2[p], tag)) atomicOr(&timeout, 1u);
+    else atomicMin(&mn, __ldcg(&v.mbox[(r & 1u) * MAX_GPUS + p].far_min));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { io[0] = mn; c->round = r + 1u; if (timeout) atomicOr(&c->err, (uint32_t)ERR_PEER_TIMEOUT); }
+}
+
+__global__ void __launch_bounds__(TILE) k_tile_begin(TView v, TParams tp, uint64_t t_end) {
+  __shared__ Glob g;
+  if (threadIdx.x == 0) glob_from_ctl(g, v.ctl, 0);
+  __syncthreads();
   begin_drain(v, tp, t_end, g);
 }
 
@@ -149,7 +298,7 @@ struct CudaBE {
   unsigned long long *h_tmp = nullptr;
   char *stage = nullptr;
   size_t stage_bytes = 0;
-  int grid = 0;
+  int grid = 0, xchg_grid = 148;
   size_t smem = 0;
   bool smem_set[2] = {false, false};
 
@@ -169,6 +318,7 @@ struct CudaBE {
     per_sm = std::max(1, std::min(per_sm, (int)env_u32("DEVA_B200_TILE_BLOCKS_PER_SM", 8)));
     per_sm = std::min(per_sm, prop.maxThreadsPerMultiProcessor / TILE);
     grid = prop.multiProcessorCount * per_sm;
+    xchg_grid = prop.multiProcessorCount;
     return 0;
   }
   int grid_blocks() const { return grid; }
@@ -266,7 +416,10 @@ struct CudaBE {
   }
   int k_begin(const TView &v, const TParams &tp, uint64_t t_end) {
     TCU(cudaSetDevice(device));
-    k_tile_begin<<<1, 32, 0, stream>>>(v, tp, t_end);
+    if (v.n_gpus > 1) {
+      k_tile_begin_multi<<<1, 32, 0, stream>>>(v, t_end);
+      k_tile_xchg<<<1, 256, 0, stream>>>(v, tp, 1);
+    } else k_tile_begin<<<1, TILE, 0, stream>>>(v, tp, t_end);
     TCU(cudaGetLastError());
     return 0;
   }
@@ -278,6 +431,7 @@ struct CudaBE {
       smem_set[mi] = true;
     }
     k_tile_step<M><<<grid, TILE, smem, stream>>>(v, mp, tp);
+    if (v.n_gpus > 1) k_tile_xchg<<<xchg_grid, 256, 0, stream>>>(v, tp, 0);
     TCU(cudaGetLastError());
     return 0;
   }
@@ -289,6 +443,7 @@ struct CudaBE {
   int k_min_pending(const TView &v, uint64_t *out) {
     TCU(cudaMemsetAsync(d_tmp, 0xff, 8, stream));
     k_tile_min_pending<<<std::min<uint32_t>(v.NT, 148 * 8), 256, 0, stream>>>(v, d_tmp);
+    if (v.n_gpus > 1) k_tile_xmin<<<1, 32, 0, stream>>>(v, d_tmp);
     TCU(cudaGetLastError());
     TCU(cudaMemcpyAsync(h_tmp, d_tmp, 8, cudaMemcpyDeviceToHost, stream));
     TCU(cudaStreamSynchronize(stream));

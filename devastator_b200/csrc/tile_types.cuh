@@ -100,7 +100,7 @@ struct TView {
   int32_t n_gpus, gpu_rank;
   LpState *st[2];
   uint32_t *tcur, *tev, *tflags;   // per tile: checkpoint buffer index; epoch of last evaluation; TF_*
-  EvRec *near_; uint32_t *ncnt;
+  EvRec *near_; uint32_t *ncnt, *npub;   // npub: the open bucket's record count when its epoch began (what evaluations read)
   EvRec *late[2]; uint32_t *lcnt[2], *lseen[2];   // lseen: how many of a late list's records the tile's last evaluation saw
   uint32_t *dmark;                 // per tile: serial of the launch that last queued it for re-evaluation
   EvRec *far_; uint32_t *fcnt, *fpub;   // fpub: a tile's far count as of the last rebin (those records are complete)

@@ -48,3 +48,14 @@ def cuda_api():
     """The product library.  Fails loudly when it is missing or no GPU is visible - no fallback."""
     from devastator_b200 import engine as E
     return E.load()
+
+
+ENGINE_KINDS = ["tile", "lp"]
+
+
+@pytest.fixture(params=ENGINE_KINDS)
+def engine_kind(request, monkeypatch):
+    """Both engines behind the C ABI: "tile" (default: calendar of per-tile event lists, epochs closed on
+    the device) and "lp" (the first engine: one thread per LP over per-LP pools)."""
+    monkeypatch.setenv("DEVA_B200_ENGINE", request.param)
+    return request.param

@@ -279,7 +279,80 @@ static uint64_t exact_gvt_all(deva_b200_engine **es, int G) {
   return gvt;
 }
 
+}  // extern "C"
+// ---- TILE engine, several engines in lockstep (stands in for one process per GPU): the step kernel
+// on every engine, then what k_tile_xchg does on the GPU box - receive the peers' records, exchange
+// the figures, run the epoch state machine on every engine with the same sums.
+using namespace deva_b200::tl;
+template <class F>
+static auto tile_model(deva_b200_engine *e, F &&f) { return tile_dispatch_model(e->cfg.model, f); }
+static void tile_deliver_all(deva_b200_engine **es, int G) {
+  for (int d = 0; d < G; d++) {
+    EmuTile *r = es[d]->tile;
+    const Epoch ep = load_epoch(r->v.ctl);
+    uint32_t err = 0;
+    for (int g = 0; g < G; g++) {
+      if (g == d) continue;
+      EmuTile *s = es[g]->tile;
+      uint32_t n = s->v.ctl->send_n[d];
+      if (n > s->v.peer_cap) n = s->v.peer_cap;
+      const EvRec *recs = r->v.recvbuf + (size_t)g * r->send_cap;
+      for (uint32_t i = 0; i < n; i++) append_local(r->v, ep, recs[i], nullptr, &err);
+    }
+    r->v.ctl->err |= err;
+  }
+}
+static void tile_fold_all(deva_b200_engine **es, int G, Glob &g) {
+  std::vector<PeerMsg> msgs(G);
+  for (int k = 0; k < G; k++) make_peer_msg(es[k]->tile->v, msgs[k]);
+  fold_peer_msgs(msgs.data(), G, g);
+}
+static int emu_tile_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out) {
+  for (int k = 0; k < G; k++) {
+    EmuTile *t = es[k]->tile;
+    if (t->has_rewind) return fail(DEVA_B200_ERR_STATE, "lingering rewind state");
+    if (G > 1 && !t->v.peer_cap) return fail(DEVA_B200_ERR_STATE, "emu_enable_peer_delivery was not called");
+    if (rewindable) { int rc = t->snapshot(); if (rc) return rc; }
+    t->v.ctl->stop_req = (uint32_t)t->stop_req.load();
+    t->v.ctl->t_end = t_end;
+    for (int i = 0; i < MAX_GPUS; i++) t->v.ctl->send_n[i] = 0;
+  }
+  Glob g;
+  tile_fold_all(es, G, g);
+  for (int k = 0; k < G; k++) { begin_drain(es[k]->tile->v, es[k]->tile->tp, t_end, g); es[k]->tile->v.ctl->round++; }
+  for (uint64_t guard = 0;; guard++) {
+    const uint32_t phase = es[0]->tile->v.ctl->phase;
+    for (int k = 1; k < G; k++) if (es[k]->tile->v.ctl->phase != phase) return fail(DEVA_B200_ERR_INVARIANT, "engines disagree on the phase");
+    if (phase == PH_DONE) break;
+    if (guard > 10000000) return fail(DEVA_B200_ERR_INVARIANT, "tile engines do not converge");
+    for (int k = 0; k < G; k++) {
+      EmuTile *t = es[k]->tile;
+      tile_model(es[k], [&](auto m) { t->be.template step_noclose<typename decltype(m)::type>(t->v, t->mp, t->tp); return 0; });
+    }
+    tile_deliver_all(es, G);
+    tile_fold_all(es, G, g);
+    for (int k = 0; k < G; k++) { close_launch(es[k]->tile->v, es[k]->tile->tp, g); es[k]->tile->v.ctl->round++; }
+    if (g.err) break;
+  }
+  uint64_t gvt = ~0ull;
+  for (int k = 0; k < G; k++) {
+    EmuTile *t = es[k]->tile;
+    t->hc = *t->v.ctl;
+    if (t->hc.err) return t->check_err();
+    if (t->hc.antis_pending > 0) t->be.k_net_pending(t->v);
+    uint64_t m = ~0ull;
+    if (t->hc.gvt != ~0ull) t->be.k_min_pending(t->v, &m);
+    gvt = std::min(gvt, m);
+    t->hc = *t->v.ctl;
+    if (t->hc.err) return t->check_err();
+  }
+  if (gvt_out) *gvt_out = gvt;
+  return 0;
+}
+extern "C" {
+
 int emu_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out) {
+  if (es[0]->tile) return emu_tile_drain_multi(es, G, t_end, rewindable, gvt_out);
   for (int g = 0; g < G; g++) if (es[g]->has_rewind) return fail(DEVA_B200_ERR_STATE, "lingering rewind state");
   for (int g = 0; g < G; g++) {
     deva_b200_engine *e = es[g];
@@ -330,7 +403,7 @@ int emu_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewind
 }
 
 int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out) {
-  if (e->tile) return e->tile->drain(t_end, rewindable, gvt_out);
+  if (e->tile) return e->cfg.n_gpus == 1 ? e->tile->drain(t_end, rewindable, gvt_out) : emu_tile_drain_multi(&e, 1, t_end, rewindable, gvt_out);
   if (e->cfg.n_gpus != 1) return fail(DEVA_B200_ERR_STATE, "emu: use emu_drain_multi for n_gpus > 1");
   return emu_drain_multi(&e, 1, t_end, rewindable, gvt_out);
 }
@@ -372,6 +445,13 @@ void emu_set_shuffle(deva_b200_engine *e, uint64_t seed) { if (e->tile) e->tile-
 // what deva_b200_comm_init does with CUDA IPC: every engine gets a pointer to ITS region of every
 // peer's receive buffer, and lp_pass stores cross-GPU records there directly
 void emu_enable_peer_delivery(deva_b200_engine **es, int G) {
+  if (es[0]->tile) {
+    for (int g = 0; g < G; g++) {
+      for (int d = 0; d < G; d++) if (d != g) es[g]->tile->map_peer(d, es[d]->tile->comm_block);
+      es[g]->tile->peers_ready();
+    }
+    return;
+  }
   for (int g = 0; g < G; g++) {
     for (int d = 0; d < G; d++) es[g]->v.peer_buf[d] = d == g ? nullptr : es[d]->recvbuf + (size_t)g * es[d]->v.send_cap;
     es[g]->v.peer_cap = es[g]->v.send_cap;

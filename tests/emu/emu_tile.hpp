@@ -82,9 +82,19 @@ struct HostBE {
   }
   template <class M>
   int k_step(const TView &v, const ModelParams &mp, const TParams &tp) {
+    if (!step_noclose<M>(v, mp, tp)) return 0;
+    TCtl *c = v.ctl;
+    Glob g;
+    glob_from_ctl(g, c, c->dirty_n[c->par]);
+    close_launch(v, tp, g);
+    return 0;
+  }
+  // the step kernel without its closing (several engines: the lockstep / gloo drivers close after the exchange)
+  template <class M>
+  bool step_noclose(const TView &v, const ModelParams &mp, const TParams &tp) {
     TCtl *c = v.ctl;
     const uint32_t phase = c->phase;
-    if (phase != PH_EVAL && phase != PH_REBIN) return 0;
+    if (phase != PH_EVAL && phase != PH_REBIN) return false;
     const Epoch ep = load_epoch(c);
     const bool all_tiles = phase == PH_REBIN || c->full;
     std::vector<uint32_t> work;
@@ -100,10 +110,7 @@ struct HostBE {
       if (phase == PH_EVAL) eval_tile<M>(v, mp, ep, b, tile);
       else rebin_tile(v, ep, b, tile, v.scratch, rebin_all);
     }
-    Glob g;
-    glob_from_ctl(g, c, c->dirty_n[c->par]);
-    close_launch(v, tp, g);
-    return 0;
+    return true;
   }
   int k_net_pending(const TView &v) {
     const Epoch ep = load_epoch(v.ctl);

@@ -21,7 +21,7 @@ BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks
 
 
 @pytest.fixture(params=BACKENDS)
-def api(request):
+def api(request, engine_kind):
     return request.getfixturevalue("emu_api" if request.param == "emu" else "cuda_api")
 
 
@@ -151,16 +151,48 @@ def test_events_beyond_t_end_stay_pending(api):
     assert gvt == 0 and eng.stats()["committed_n"] == 0 and eng.digest()["pending"] == A * K
 
 
-def test_capacity_overflow_fails_loudly(api):
+def test_capacity_overflow_fails_loudly(api, engine_kind, monkeypatch):
+    if engine_kind == "tile":   # its capacities are per tile: a far list too small for the roots it must park
+        monkeypatch.setenv("DEVA_B200_TILE_C", "16")
+        monkeypatch.setenv("DEVA_B200_TILE_CF", "64")
     eng = S.make(api, 64, P=0.5, LAM=10.0, END=400, pq_cap=4, inbox_cap=2, log_cap=8)
-    eng.seed_phold(4, 1, 1)
-    with pytest.raises(E.EngineError):
+    with pytest.raises(E.EngineError) as ei:
+        eng.seed_phold(4, 1, 1)
         eng.drain()
+    assert ei.value.code == -3   # DEVA_B200_ERR_CAPACITY: never a silent drop
 
 
 def test_small_capacities_still_exact(api):
     """Inbox spill, working-set eviction and a full undo log are slow paths, not wrong paths."""
     S.run_phold_t(api, 64, 4, 0.5, 10.0, 400, window=40, pq_cap=64, inbox_cap=1, log_cap=6)
+
+
+@pytest.mark.parametrize("knobs", [
+    dict(DEVA_B200_TILE_C="32", DEVA_B200_TILE_CF="65536"),                                   # bucket lists overflow into the far list (rebin + slow path)
+    dict(DEVA_B200_TILE_CL="4"),                                   # late lists overflow into the job-wide spill list
+    dict(DEVA_B200_TILE_RCAP="160"),                               # a tile's window does not fit the workspace: LP sub-range sweeps
+    dict(DEVA_B200_TILE_C="24", DEVA_B200_TILE_CL="3", DEVA_B200_TILE_RCAP="160", DEVA_B200_TILE_CF="65536"),
+], ids=["near", "late", "rcap", "all"])
+@pytest.mark.parametrize("window", [1, 16, 40, 0])
+def test_tile_engine_capacity_fallbacks_are_exact(api, engine_kind, monkeypatch, knobs, window):
+    """The tile engine's fall-backs - far list for a full bucket list, spill list for a full late list, LP
+    sub-ranges for a window larger than shared memory - are slow paths, not wrong paths."""
+    if engine_kind != "tile":
+        pytest.skip("tile engine knobs")
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    S.run_phold_t(api, 300, 8, 0.5, 20.0, 300, window=window)
+    S.run_phold_t(api, 64, 4, 0.5, 10.0, 400, window=window, drain_end=150)
+
+
+def test_tile_engine_runs_dense_models_with_default_settings(api, engine_kind):
+    """lambda ~ 1 with every child leaving its LP (the reference runs these; the first engine refuses them
+    with its default start-up window): no knob needed."""
+    if engine_kind != "tile":
+        pytest.skip("the first engine needs DEVA_B200_WINDOW_START=1 here (next tests)")
+    S.run_phold_t(api, 47, 7, 1.0, 1.0, 15, window=0)
+    S.run_phold_t(api, 181, 8, 1.0, 5.0, 40, window=0)
+    S.run_phold_t(api, 600, 16, 1.0, 1.0, 30, window=0)
 
 
 # ---- bench/phold.cxx model (rng + Box-Muller destination), made reproducible by an end_time -----
@@ -227,6 +259,7 @@ def test_window_start_knob_keeps_dense_models_within_capacity(api, monkeypatch):
 
 
 def test_default_start_window_refuses_loudly_when_far_too_optimistic(emu_api, monkeypatch):
+    monkeypatch.setenv("DEVA_B200_ENGINE", "lp")   # (the tile engine runs this model with default settings, see above)
     monkeypatch.setenv("DEVA_B200_WAKE_MIN", "0")
     with pytest.raises(E.EngineError) as ei:
         S.run_phold_t(emu_api, 47, 7, 1.0, 1.0, 15, window=0)

@@ -32,7 +32,9 @@ def make_group(api, G, A, peer=False, **kw):
 @pytest.mark.parametrize("G", [2, 4, 8])
 @pytest.mark.parametrize("window", [1, 20, 0])
 @pytest.mark.parametrize("P", [0.1, 0.5])
-def test_partitioned_equals_oracle(emu_api, G, window, P, peer):
+def test_partitioned_equals_oracle(emu_api, engine_kind, G, window, P, peer):
+    if engine_kind == "tile" and not peer:
+        pytest.skip("the tile engine has one transport: peer delivery + device-side exchange")
     A, K, LAM, END = 1000, 16, 100.0, 300
     o, ost = O.run(A, K, P, LAM, END)
     engs = make_group(emu_api, G, A, peer=peer, window=window, p_remote=P, lam=LAM, end_time=END)
@@ -51,7 +53,7 @@ def test_partitioned_equals_oracle(emu_api, G, window, P, peer):
     assert chk == o["checksum"]
 
 
-def test_partitioned_default_subtime_and_rewind(emu_api):
+def test_partitioned_default_subtime_and_rewind(emu_api, engine_kind):
     """test/phold.cxx on 2 GPUs x (virtual ranks = 4): sequence-id tiebreak, drain/rewind thirds."""
     A, K, P, LAM, END, ranks, G = 1000, 2, 0.5, 100.0, 10000, 4, 2
     engs = make_group(emu_api, G, A, peer=True, window=0, p_remote=P, lam=LAM, end_time=END, user_subtime=0)
