@@ -40,9 +40,11 @@ namespace tl {
 #if defined(__CUDA_ARCH__)
 #define TL_THREADS(tid) for (int tid = (int)threadIdx.x, tl_once_ = 1; tl_once_; tl_once_ = 0)
 #define TL_SYNC() __syncthreads()
+#define TL_NTHR ((uint32_t)blockDim.x)
 #else
-#define TL_THREADS(tid) for (int tid = 0; tid < TILE; tid++)
+#define TL_THREADS(tid) for (int tid = 0; tid < NTHR; tid++)
 #define TL_SYNC() ((void)0)
+#define TL_NTHR ((uint32_t)NTHR)
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -125,10 +127,12 @@ DEVA_HD Epoch load_epoch(const TCtl *c) {
 // per-block accumulators (shared memory), folded into TCtl once per tile
 struct Hdr {
   uint32_t n, nb, nl, nlw, nl_old, nf, first, slow, in_buf, slot, lo, hi, skip, used_far;
-  uint32_t executed, rolled, anti, remote, err, fresh_antis;
+  uint32_t bins[NBIN], n_active, chunk;   // LPs per record count; LPs that run; next chunk of 32 LPs to hand to a warp
+  uint32_t work_item, next_item;
+  // accumulated over all the tiles the block handles in a launch, folded into TCtl once (blk_flush)
+  uint32_t executed, rolled, anti, remote, err, fresh_antis, evals, ovf;
   int32_t committed, nondet;
   uint32_t bh[NB];        // records this block appended per ring slot (-> ctl->btotal)
-  uint32_t work_item;
 };
 
 // one block's shared-memory workspace
@@ -139,6 +143,7 @@ struct Blk {
   uint8_t *efl;      // [rcap]  per-record flags (F_*)
   uint32_t *off;     // [TILE+1] segment bounds per LP
   uint32_t *cur;     // [TILE]  histogram / scatter cursors
+  uint16_t *perm;    // [TILE]  LPs in the order they run (most records first)
   Hdr *h;
   uint64_t *mbar;
   uint32_t rcap;
@@ -152,6 +157,7 @@ DEVA_HD size_t blk_bytes(uint32_t rcap) {
   b += rcap; b = (b + 15) & ~(size_t)15;
   b += (TILE + 1) * 4; b = (b + 15) & ~(size_t)15;
   b += TILE * 4;
+  b += TILE * 2;
   b += sizeof(Hdr); b = (b + 15) & ~(size_t)15;
   b += 16;
   return b;
@@ -165,6 +171,7 @@ DEVA_HD void blk_carve(Blk &b, unsigned char *base, uint32_t rcap) {
   b.efl = reinterpret_cast<uint8_t *>(base + o); o += rcap; o = (o + 15) & ~(size_t)15;
   b.off = reinterpret_cast<uint32_t *>(base + o); o += (TILE + 1) * 4; o = (o + 15) & ~(size_t)15;
   b.cur = reinterpret_cast<uint32_t *>(base + o); o += TILE * 4;
+  b.perm = reinterpret_cast<uint16_t *>(base + o); o += TILE * 2;
   b.h = reinterpret_cast<Hdr *>(base + o); o += sizeof(Hdr); o = (o + 15) & ~(size_t)15;
   b.mbar = reinterpret_cast<uint64_t *>(base + o);
   b.mphase = 0;
@@ -259,53 +266,55 @@ DEVA_HD void route_append(const TView &v, const Epoch &ep, const EvRec &rec, uin
 //   MODE_NEW    re-evaluation, new sequence from the fork on: children are sent
 //   MODE_OLD    re-evaluation, old sequence from the fork on: children are cancelled (anti-messages)
 enum { MODE_FIRST = 0, MODE_SHARED = 1, MODE_NEW = 2, MODE_OLD = 3 };
+struct IChild { uint64_t t, s; uint32_t p0, p1, slot; };
 struct Chain {
   uint64_t st[MAX_STW], seq;
-  uint64_t it[2], is[2]; uint32_t ip0[2], ip1[2]; uint32_t islot[2]; uint32_t nic;   // internal children (bit i of nic: slot i in use)
+  IChild c0, c1; uint32_t nic;     // internal children (bit i of nic: slot i in use)
   uint64_t lt, ls; uint32_t any, cnt, tie;
+  uint32_t cur;                    // next position in the LP's (sorted) segment
 };
+DEVA_HD bool ichild_less(const IChild &a, const IChild &b) {
+  if (a.t != b.t) return a.t < b.t;
+  if (a.s != b.s) return a.s < b.s;
+  if (a.p0 != b.p0) return a.p0 < b.p0;
+  return a.p1 < b.p1;
+}
 
 template <class M>
-DEVA_HD bool walk(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t s0, uint32_t s1, uint64_t gid, int mode,
+DEVA_HD bool walk(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t s1, uint64_t gid, int mode,
                   Chain &ch, uint32_t *err, uint32_t *remote, uint32_t *anti_sent) {
   const uint8_t need = mode == MODE_OLD ? F_INOLD : F_INNEW;
-  const uint8_t cons = mode == MODE_OLD ? F_CO : (mode == MODE_NEW || mode == MODE_FIRST ? F_CN : (uint8_t)(F_CN | F_CO));
   for (;;) {
-    // next list record of this sequence: the smallest unconsumed one
+    // next list record of this sequence: the segment is sorted, skip what the sequence does not hold
     int best = -1;
+    uint8_t f = 0;
+    uint32_t j = ch.cur;
 #pragma unroll 1
-    for (uint32_t j = s0; j < s1; j++) {
+    for (; j < s1; j++) {
       const uint32_t i = b.ord[j];
-      const uint8_t f = b.efl[i];
-      if (mode == MODE_SHARED) { if (!(f & (F_INOLD | F_INNEW)) || (f & F_CN)) continue; }
-      else if (!(f & need) || (f & cons)) continue;
-      if (best < 0 || rec_less(b.R[i], b.R[best])) best = (int)i;
+      f = b.efl[i];
+      if (mode == MODE_SHARED ? (f & (F_INOLD | F_INNEW)) != 0 : (f & need) != 0) { best = (int)i; break; }
     }
+    ch.cur = j;
     // ... or an internal child, if earlier (a list record wins a full tie)
     int ici = -1;
-    if (ch.nic) {
-      if ((ch.nic & 1u) && (ch.nic & 2u)) {
-        const bool l10 = ch.it[1] < ch.it[0] || (ch.it[1] == ch.it[0] && (ch.is[1] < ch.is[0] || (ch.is[1] == ch.is[0] &&
-                         (ch.ip0[1] < ch.ip0[0] || (ch.ip0[1] == ch.ip0[0] && ch.ip1[1] < ch.ip1[0])))));
-        ici = l10 ? 1 : 0;
-      } else ici = (ch.nic & 1u) ? 0 : 1;
-    }
     EvRec e;
-    uint32_t slot;
-    if (ici >= 0) {
-      e.time = ch.it[ici]; e.sub = ch.is[ici]; e.p0 = ch.ip0[ici]; e.p1 = ch.ip1[ici];
+    if (ch.nic) {
+      ici = ch.nic == 3u ? (ichild_less(ch.c1, ch.c0) ? 1 : 0) : ((ch.nic & 1u) ? 0 : 1);
+      const IChild q = ici ? ch.c1 : ch.c0;
+      e.time = q.t; e.sub = q.s; e.p0 = q.p0; e.p1 = q.p1;
       if (best >= 0 && !rec_less(e, b.R[best])) ici = -1;
     }
+    uint32_t slot;
     if (ici >= 0) {
-      slot = ch.islot[ici];
+      slot = ici ? ch.c1.slot : ch.c0.slot;
       ch.nic &= ~(1u << ici);
     } else {
       if (best < 0) return false;
-      const uint8_t f = b.efl[best];
       if (mode == MODE_SHARED && (f & (F_INOLD | F_INNEW)) != (F_INOLD | F_INNEW)) return true;   // the sequences part here
       e = b.R[best];
-      b.efl[best] = f | cons;
       slot = (uint32_t)best;
+      ch.cur = j + 1;
     }
     e.dst = (uint32_t)gid; e.flags = 0;
     if (ch.any && !key_less(ch.lt, ch.ls, e.time, e.sub)) ch.tie = 1;   // equal (time, subtime): pdes.cxx:828-831
@@ -317,9 +326,8 @@ DEVA_HD bool walk(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b
     if (!mp.user_subtime) c.sub = ch.seq;        // event_subtime / next_seq_id, pdes.hxx:513-526,676
     ch.seq += v.lp_n;
     if ((uint64_t)c.dst == gid && c.time < ep.ub && ch.nic != 3u) {   // stays inside this thread
-      const int k = (ch.nic & 1u) ? 1 : 0;
-      ch.it[k] = c.time; ch.is[k] = c.sub; ch.ip0[k] = c.p0; ch.ip1[k] = c.p1; ch.islot[k] = slot;
-      ch.nic |= 1u << k;
+      IChild q; q.t = c.time; q.s = c.sub; q.p0 = c.p0; q.p1 = c.p1; q.slot = slot;
+      if (ch.nic & 1u) { ch.c1 = q; ch.nic |= 2u; } else { ch.c0 = q; ch.nic |= 1u; }
       continue;
     }
     if (mode == MODE_SHARED) continue;           // already sent by the previous evaluation
@@ -377,26 +385,30 @@ DEVA_HD void net_segment(Blk &b, uint32_t s0, uint32_t s1, uint32_t *err, uint32
 DEVA_HD void chain_start(Chain &ch, const LpState &s) {
 #pragma unroll
   for (int w = 0; w < MAX_STW; w++) ch.st[w] = s.w[w];
-  ch.seq = s.seq; ch.nic = 0; ch.lt = ch.ls = 0; ch.any = ch.cnt = ch.tie = 0;
+  ch.seq = s.seq; ch.nic = 0; ch.lt = ch.ls = 0; ch.any = ch.cnt = ch.tie = 0; ch.cur = 0;
 }
 
-// exclusive prefix sum over b.cur[0..TILE) -> b.off[0..TILE]; leaves b.cur[i] = b.off[i]
+// exclusive prefix sum over b.cur[0..TILE) -> b.off[0..TILE]; leaves b.cur[i] = b.off[i].
+// (block of NTHR threads, TILE / NTHR consecutive entries each)
 DEVA_HD void block_scan(Blk &b) {
 #if defined(__CUDA_ARCH__)
-  __shared__ uint32_t wsum[TILE / 32];
+  constexpr int PER = TILE / NTHR;
+  __shared__ uint32_t wsum[NTHR / 32];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const uint32_t x = b.cur[tid];
-  uint32_t inc = x;
+  uint32_t x[PER], sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; k++) { x[k] = b.cur[tid * PER + k]; sum += x[k]; }
+  uint32_t inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
   if (lane == 31) wsum[w] = inc;
   __syncthreads();
-  uint32_t base = 0;
+  uint32_t run = inc - sum;
 #pragma unroll
-  for (int k = 0; k < TILE / 32; k++) if (k < w) base += wsum[k];
-  b.off[tid] = base + inc - x;
-  b.cur[tid] = base + inc - x;
-  if (tid == TILE - 1) b.off[TILE] = base + inc;
+  for (int k = 0; k < NTHR / 32; k++) if (k < w) run += wsum[k];
+#pragma unroll
+  for (int k = 0; k < PER; k++) { b.off[tid * PER + k] = run; b.cur[tid * PER + k] = run; run += x[k]; }
+  if (tid == NTHR - 1) b.off[TILE] = run;
   __syncthreads();
 #else
   uint32_t run = 0;
@@ -405,17 +417,72 @@ DEVA_HD void block_scan(Blk &b) {
 #endif
 }
 
-// Sort the block's records b.R[0..n) by LP (counting sort on the LP's index in the tile), net the
-// anti-messages, run every LP's walk, flush the children.  lo/hi: LP sub-range handled (whole tile
-// unless the window did not fit in shared memory).
+// One LP's window: net its anti-messages, sort its records, walk them.
+template <class M>
+DEVA_HD void run_lp(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf, uint32_t lp) {
+  Hdr &h = *b.h;
+  const uint32_t s0 = b.off[lp], s1 = b.off[lp + 1];
+  const uint64_t gid = v.lp_begin + (uint64_t)tile * TILE + lp;
+  uint32_t err = 0, remote = 0, anti_sent = 0, fresh_antis = 0;
+  net_segment(b, s0, s1, &err, &fresh_antis);
+  // insertion sort of the segment's indices by (time, subtime, payload): 2-4 records as a rule
+#pragma unroll 1
+  for (uint32_t a = s0 + 1; a < s1; a++) {
+    const uint16_t ia = b.ord[a];
+    uint32_t k = a;
+    while (k > s0 && rec_less(b.R[ia], b.R[b.ord[k - 1]])) { b.ord[k] = b.ord[k - 1]; k--; }
+    b.ord[k] = ia;
+  }
+  Chain ch;
+  chain_start(ch, b.S[lp]);
+  ch.cur = s0;
+  if (h.first) {
+    walk<M>(v, mp, ep, b, s1, gid, MODE_FIRST, ch, &err, &remote, &anti_sent);
+#pragma unroll
+    for (int w = 0; w < MAX_STW; w++) b.S[lp].w[w] = ch.st[w];
+    b.S[lp].seq = ch.seq;
+    atom_add_u32(&h.executed, ch.cnt);
+    atom_add_u32((uint32_t *)&h.committed, ch.cnt);
+    if (ch.tie) atom_add_u32((uint32_t *)&h.nondet, 1u);
+  } else {
+    const bool forked = walk<M>(v, mp, ep, b, s1, gid, MODE_SHARED, ch, &err, &remote, &anti_sent);
+    if (forked) {
+      Chain old = ch;
+      const uint32_t shared_n = ch.cnt;
+      walk<M>(v, mp, ep, b, s1, gid, MODE_NEW, ch, &err, &remote, &anti_sent);
+      LpState *so = &v.st[out_buf][(size_t)tile * TILE + lp];
+#pragma unroll
+      for (int w = 0; w < MAX_STW; w++) so->w[w] = ch.st[w];
+      so->seq = ch.seq;
+      walk<M>(v, mp, ep, b, s1, gid, MODE_OLD, old, &err, &remote, &anti_sent);
+      atom_add_u32(&h.executed, ch.cnt);                                     // the prefix ran again, too
+      atom_add_u32(&h.rolled, old.cnt - shared_n);
+      atom_add_u32((uint32_t *)&h.committed, ch.cnt - old.cnt);              // (two's complement delta)
+      atom_add_u32((uint32_t *)&h.nondet, ch.tie - old.tie);
+    }
+  }
+  if (err) atom_or_u32(&h.err, err);
+  if (remote) atom_add_u32(&h.remote, remote);
+  if (anti_sent) atom_add_u32(&h.anti, anti_sent);
+  if (fresh_antis) atom_add_u32(&h.fresh_antis, fresh_antis);
+}
+
+// Sort the block's records b.R[0..n) by LP (counting sort on the LP's index in the tile), order the
+// LPs by how many records they hold, run them - warps pull chunks of 32 LPs, heaviest first, so that a
+// warp's lanes run equally long - and flush the children.
 template <class M>
 DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf) {
   Hdr &h = *b.h;
   const uint64_t tile_gid = v.lp_begin + (uint64_t)tile * TILE;
-  TL_THREADS(tid) { b.cur[tid] = 0; }
+  TL_THREADS(tid) {
+    for (uint32_t lp = tid; lp < (uint32_t)TILE; lp += TL_NTHR) b.cur[lp] = 0;
+    if (tid < NBIN) h.bins[tid] = 0;
+    if (tid == 0) h.chunk = 0;
+  }
   TL_SYNC();
   TL_THREADS(tid) {
-    for (uint32_t i = tid; i < h.n; i += TILE) {
+    for (uint32_t i = tid; i < h.n; i += TL_NTHR) {
+      if (b.efl[i] & F_DEAD) continue;             // (not this epoch's: in no LP's segment)
       const uint32_t lp = (uint32_t)((uint64_t)b.R[i].dst - tile_gid);
       atom_add_u32(&b.cur[lp], 1u);
     }
@@ -424,67 +491,109 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
   block_scan(b);
   TL_SYNC();
   TL_THREADS(tid) {
-    for (uint32_t i = tid; i < h.n; i += TILE) {
+    for (uint32_t i = tid; i < h.n; i += TL_NTHR) {
+      if (b.efl[i] & F_DEAD) continue;
       const uint32_t lp = (uint32_t)((uint64_t)b.R[i].dst - tile_gid);
       b.ord[atom_add_u32(&b.cur[lp], 1u)] = (uint16_t)i;
     }
   }
   TL_SYNC();
-  // ---- every LP's thread runs its window
+  // ---- LPs by record count, descending (counting sort on min(count, NBIN-1)); an LP without a fresh
+  // record has nothing to do since its last evaluation and counts 0
   TL_THREADS(tid) {
-    const uint32_t s0 = b.off[tid], s1 = b.off[tid + 1];
-    if (s0 == s1) continue;
-    const uint64_t gid = tile_gid + (uint64_t)tid;
-    uint32_t err = 0, remote = 0, anti_sent = 0, fresh_antis = 0;
-    bool fresh = false;
+    for (uint32_t lp = tid; lp < (uint32_t)TILE; lp += TL_NTHR) {
+      const uint32_t s0 = b.off[lp], s1 = b.off[lp + 1];
+      uint32_t n = 0;
+      if (h.first) n = s1 - s0;
+      else {
+        bool fresh = false;
 #pragma unroll 1
-    for (uint32_t j = s0; j < s1; j++) { const uint8_t f = b.efl[b.ord[j]]; fresh |= (f & (F_FRESH | F_DEAD)) == F_FRESH; }
-    if (!fresh) continue;                       // nothing new for this LP since its last evaluation
-    net_segment(b, s0, s1, &err, &fresh_antis);
-    Chain ch;
-    chain_start(ch, b.S[tid]);
-    if (h.first) {
-      walk<M>(v, mp, ep, b, s0, s1, gid, MODE_FIRST, ch, &err, &remote, &anti_sent);
-#pragma unroll
-      for (int w = 0; w < MAX_STW; w++) b.S[tid].w[w] = ch.st[w];
-      b.S[tid].seq = ch.seq;
-      atom_add_u32(&h.executed, ch.cnt);
-      atom_add_u32((uint32_t *)&h.committed, ch.cnt);
-      if (ch.tie) atom_add_u32((uint32_t *)&h.nondet, 1u);
-    } else {
-      const bool forked = walk<M>(v, mp, ep, b, s0, s1, gid, MODE_SHARED, ch, &err, &remote, &anti_sent);
-      if (forked) {
-        Chain old = ch;
-        const uint32_t shared_n = ch.cnt;
-        walk<M>(v, mp, ep, b, s0, s1, gid, MODE_NEW, ch, &err, &remote, &anti_sent);
-        LpState *so = &v.st[out_buf][(size_t)tile * TILE + tid];
-#pragma unroll
-        for (int w = 0; w < MAX_STW; w++) so->w[w] = ch.st[w];
-        so->seq = ch.seq;
-        walk<M>(v, mp, ep, b, s0, s1, gid, MODE_OLD, old, &err, &remote, &anti_sent);
-        atom_add_u32(&h.executed, ch.cnt);                                     // the prefix ran again, too
-        atom_add_u32(&h.rolled, old.cnt - shared_n);
-        atom_add_u32((uint32_t *)&h.committed, ch.cnt - old.cnt);              // (two's complement delta)
-        atom_add_u32((uint32_t *)&h.nondet, ch.tie - old.tie);
+        for (uint32_t j = s0; j < s1; j++) { const uint8_t f = b.efl[b.ord[j]]; fresh |= (f & (F_FRESH | F_DEAD)) == F_FRESH; }
+        n = fresh ? s1 - s0 : 0u;
       }
+      const uint32_t key = n < (uint32_t)NBIN - 1u ? n : (uint32_t)NBIN - 1u;
+      uint32_t pos;
+#if defined(__CUDA_ARCH__)
+      {   // one atomic per distinct key per warp
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs((int)m) - 1, lane = (int)(threadIdx.x & 31);
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&h.bins[key], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        pos = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+      }
+#else
+      pos = h.bins[key]++;
+#endif
+      b.cur[lp] = key | (pos << 8);
     }
-    if (err) atom_or_u32(&h.err, err);
-    if (remote) atom_add_u32(&h.remote, remote);
-    if (anti_sent) atom_add_u32(&h.anti, anti_sent);
-    if (fresh_antis) atom_add_u32(&h.fresh_antis, fresh_antis);
   }
+  TL_SYNC();
+  TL_THREADS(tid) {
+    if (tid != 0) continue;
+    uint32_t run = 0;
+    for (int k = NBIN - 1; k >= 1; k--) { const uint32_t c = h.bins[k]; h.bins[k] = run; run += c; }
+    h.n_active = run;
+  }
+  TL_SYNC();
+  TL_THREADS(tid) {
+    for (uint32_t lp = tid; lp < (uint32_t)TILE; lp += TL_NTHR) {
+      const uint32_t key = b.cur[lp] & 0xffu, pos = b.cur[lp] >> 8;
+      if (key) b.perm[h.bins[key] + pos] = (uint16_t)lp;
+    }
+  }
+  TL_SYNC();
+  // ---- run
+#if defined(__CUDA_ARCH__)
+  {
+    const int lane = (int)(threadIdx.x & 31);
+    for (;;) {
+      uint32_t c = 0;
+      if (lane == 0) c = atomicAdd(&h.chunk, 1u);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c * 32u >= h.n_active) break;
+      const uint32_t idx = c * 32u + (uint32_t)lane;
+      if (idx < h.n_active) run_lp<M>(v, mp, ep, b, tile, out_buf, b.perm[idx]);
+      __syncwarp();
+    }
+  }
+#else
+  for (uint32_t idx = 0; idx < h.n_active; idx++) run_lp<M>(v, mp, ep, b, tile, out_buf, b.perm[idx]);
+#endif
   TL_SYNC();
   // ---- flush: every slot that now holds a child goes to its list (all lanes busy, atomics in bulk)
   if (h.first) {
     TL_THREADS(tid) {
       uint32_t err = 0, remote = 0;
-      for (uint32_t i = tid; i < h.n; i += TILE)
+      for (uint32_t i = tid; i < h.n; i += TL_NTHR)
         if (b.efl[i] & F_OUT) route_append(v, ep, b.R[i], h.bh, &err, &remote);
       if (err) atom_or_u32(&h.err, err);
       if (remote) atom_add_u32(&h.remote, remote);
     }
     TL_SYNC();
   }
+}
+
+// per-launch accumulators of a block: zero at kernel start, folded into TCtl at kernel end
+DEVA_HD void blk_begin(Blk &b) {
+  Hdr &h = *b.h;
+  h.executed = h.rolled = h.anti = h.remote = h.err = h.fresh_antis = h.evals = h.ovf = 0; h.committed = h.nondet = 0;
+  for (int i = 0; i < NB; i++) h.bh[i] = 0;
+}
+DEVA_HD void blk_flush(const TView &v, Blk &b) {
+  Hdr &h = *b.h;
+  TCtl *c = v.ctl;
+  if (h.executed) atom_add_u64(&c->executed, h.executed);
+  if (h.committed) atom_add_u64(&c->committed, (unsigned long long)(long long)h.committed);
+  if (h.rolled) atom_add_u64(&c->rolled, h.rolled);
+  if (h.anti) atom_add_u64(&c->anti_sent, h.anti);
+  if (h.remote) atom_add_u64(&c->remote_sent, h.remote);
+  if (h.nondet) atom_add_u64((unsigned long long *)&c->nondet, (unsigned long long)(long long)h.nondet);
+  if (h.fresh_antis) atom_add_u64((unsigned long long *)&c->antis_pending, (unsigned long long)(-(long long)h.fresh_antis));
+  if (h.err) atom_or_u32(&c->err, h.err);
+  if (h.ovf) atom_or_u32(&c->ovf_flag, 1u);          // consumed far records must be dropped before the next epoch
+  if (h.evals) atom_add_u64(&c->evals, h.evals);
+  for (int i = 0; i < NB; i++) if (h.bh[i]) atom_add_u64(&c->btotal[i], h.bh[i]);
 }
 
 // One tile, one launch of an epoch.  Its window events are the open bucket's list (+ what waits for
@@ -510,8 +619,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     h.skip = (h.nb + h.nl + h.nlw + h.nf) == 0;
     h.slow = h.nf > 0 || h.nb + h.nl + h.nlw > b.rcap || ep.sp_w_n > 0 || ep.sp_r_n > 0;
     if (ep.sp_w_n > 0 || ep.sp_r_n > 0) h.skip = 0;
-    h.executed = h.rolled = h.anti = h.remote = h.err = h.fresh_antis = 0; h.committed = h.nondet = 0; h.used_far = 0;
-    for (int i = 0; i < NB; i++) h.bh[i] = 0;
+    h.used_far = 0;
   }
   TL_SYNC();
   if (h.skip) return;
@@ -542,14 +650,14 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     for (int i = 0; i < TILE; i++) b.S[i] = s_in[i];
 #endif
     // flags; records outside [gvt, ub) are not part of this epoch (a bucket cut by t_end keeps its tail,
-    // after a pause its head is already committed): inert, parked on the tile's first LP
+    // after a pause its head is already committed): inert
     TL_THREADS(tid) {
       if (tid == 0) h.n = n_src;
-      for (uint32_t i = tid; i < n_src; i += TILE) {
+      for (uint32_t i = tid; i < n_src; i += TL_NTHR) {
         const EvRec &r = b.R[i];
         uint8_t f = (h.first || i >= n_oldsrc) ? F_FRESH : 0;
         if (r.flags & EV_ANTI) f |= F_ANTI;
-        if (r.time >= ep.ub || r.time < ep.gvt || (r.flags & EV_DEAD)) { b.R[i].dst = (uint32_t)(v.lp_begin + (uint64_t)tile * TILE); f = F_DEAD; }
+        if (r.time >= ep.ub || r.time < ep.gvt || (r.flags & EV_DEAD)) f = F_DEAD;
         b.efl[i] = f;
       }
     }
@@ -559,7 +667,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     // ---- slow path: the window does not fit in shared memory (a start-up bucket holding every root,
     // many same-time events) or part of it waits in the far list: LP sub-ranges, one sweep each
     TL_THREADS(tid) {
-      b.S[tid] = s_in[tid];
+      for (uint32_t lp = tid; lp < (uint32_t)TILE; lp += TL_NTHR) b.S[lp] = s_in[lp];
       if (tid == 0) h.lo = 0;
     }
     TL_SYNC();
@@ -581,10 +689,10 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     };
     while (h.lo < TILE) {
       // per-LP record counts of the remaining LPs -> the widest sub-range that fits
-      TL_THREADS(tid) { b.cur[tid] = 0; }
+      TL_THREADS(tid) { for (uint32_t lp = tid; lp < (uint32_t)TILE; lp += TL_NTHR) b.cur[lp] = 0; }
       TL_SYNC();
       TL_THREADS(tid) {
-        for (uint32_t i = tid; i < n_all; i += TILE) {
+        for (uint32_t i = tid; i < n_all; i += TL_NTHR) {
           EvRec r; bool fresh;
           if (!fetch(i, r, fresh)) continue;
           const uint32_t lp = (uint32_t)((uint64_t)r.dst - tile_gid);
@@ -602,7 +710,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
       }
       TL_SYNC();
       TL_THREADS(tid) {
-        for (uint32_t i = tid; i < n_all; i += TILE) {
+        for (uint32_t i = tid; i < n_all; i += TL_NTHR) {
           EvRec r; bool fresh;
           if (!fetch(i, r, fresh)) continue;
           const uint32_t lp = (uint32_t)((uint64_t)r.dst - tile_gid);
@@ -634,7 +742,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     if (threadIdx.x == 0) {
       bulk_s2g(v.st[out_buf] + (size_t)tile * TILE, b.S, TILE * (uint32_t)sizeof(LpState));
       bulk_commit();
-      bulk_wait_all();
+      bulk_wait_read();   // (the workspace is reused by the next tile; the kernel's end waits for the write itself)
     }
 #else
     for (int i = 0; i < TILE; i++) v.st[out_buf][(size_t)tile * TILE + i] = b.S[i];
@@ -642,21 +750,11 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
   }
   TL_THREADS(tid) {
     if (tid != 0) continue;
-    TCtl *c = v.ctl;
     v.tev[tile] = ep.epoch;
     v.lseen[rd][tile] = h.nl;
     v.lseen[ep.par][tile] = h.nlw;
-    if (h.executed) atom_add_u64(&c->executed, h.executed);
-    if (h.committed) atom_add_u64(&c->committed, (unsigned long long)(long long)h.committed);
-    if (h.rolled) atom_add_u64(&c->rolled, h.rolled);
-    if (h.anti) atom_add_u64(&c->anti_sent, h.anti);
-    if (h.remote) atom_add_u64(&c->remote_sent, h.remote);
-    if (h.nondet) atom_add_u64((unsigned long long *)&c->nondet, (unsigned long long)(long long)h.nondet);
-    if (h.fresh_antis) atom_add_u64((unsigned long long *)&c->antis_pending, (unsigned long long)(-(long long)h.fresh_antis));
-    if (h.err) atom_or_u32(&c->err, h.err);
-    if (h.used_far) atom_or_u32(&c->ovf_flag, 1u);   // consumed far records must be dropped before the next epoch
-    for (int i = 0; i < NB; i++) if (h.bh[i]) atom_add_u64(&c->btotal[i], h.bh[i]);
-    atom_add_u64(&c->evals, 1ull);
+    if (h.used_far) h.ovf = 1;
+    h.evals++;
   }
   TL_SYNC();
 }
@@ -675,7 +773,7 @@ DEVA_HD void rebin_tile(const TView &v, const Epoch &ep, Blk &b, uint32_t tile, 
   // gather: far list (+ every near list) -> scratch, dropping what is committed or annihilated
   const uint32_t nf = v.fcnt[tile] < v.CF ? v.fcnt[tile] : v.CF;
   TL_THREADS(tid) {
-    for (uint32_t i = tid; i < nf; i += TILE) {
+    for (uint32_t i = tid; i < nf; i += TL_NTHR) {
       const EvRec r = ld_ev(&v.far_[(size_t)tile * v.CF + i]);
       if (r.time < ep.gvt || (r.flags & EV_DEAD)) continue;
       const uint32_t p = atom_add_u32(&h.n, 1u);
@@ -688,7 +786,7 @@ DEVA_HD void rebin_tile(const TView &v, const Epoch &ep, Blk &b, uint32_t tile, 
       const uint32_t nc0 = v.ncnt[(size_t)tile * NB + s];
       const uint32_t nc = nc0 < v.C ? nc0 : v.C;
       TL_THREADS(tid) {
-        for (uint32_t i = tid; i < nc; i += TILE) {
+        for (uint32_t i = tid; i < nc; i += TL_NTHR) {
           const EvRec r = ld_ev(&v.near_[((size_t)tile * NB + s) * v.C + i]);
           if (r.time < ep.gvt || (r.flags & EV_DEAD)) continue;
           const uint32_t p = atom_add_u32(&h.n, 1u);
@@ -709,7 +807,7 @@ DEVA_HD void rebin_tile(const TView &v, const Epoch &ep, Blk &b, uint32_t tile, 
   // scatter back (ctl->far_total / far_min, and btotal when `all`, were zeroed when the rebin was scheduled)
   TL_THREADS(tid) {
     uint32_t err = 0;
-    for (uint32_t i = tid; i < h.n; i += TILE) {
+    for (uint32_t i = tid; i < h.n; i += TL_NTHR) {
       const EvRec r = ld_ev(&scratch[i]);
       const uint64_t bb = r.time >> ep.shift;
       const uint64_t d = bb - ep.cur_abs;
@@ -830,7 +928,7 @@ DEVA_HD void open_epoch_snapshot(const TView &v) {
   if (c->phase != PH_EVAL || !c->full) return;
   const uint32_t slot = (uint32_t)(c->cur_abs % NB);
   TL_THREADS(tid) {
-    for (uint32_t t = tid; t < v.NT; t += TILE) {
+    for (uint32_t t = tid; t < v.NT; t += TL_NTHR) {
       const uint32_t nc = v.ncnt[(size_t)t * NB + slot];
       v.npub[t] = nc < v.C ? nc : v.C;
     }
@@ -852,7 +950,7 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
     // ---- epoch commit (fossil collection, pdes.cxx:816-871): everything below ub is final.  The
     // tiles that ran swap their state buffers; a bucket consumed to its end gives its lists back.
     TL_THREADS(tid) {
-      for (uint32_t t = tid; t < v.NT; t += TILE) {
+      for (uint32_t t = tid; t < v.NT; t += TL_NTHR) {
         if (v.tev[t] == epoch) v.tcur[t] ^= 1u;
         if (whole) v.ncnt[(size_t)t * NB + slot] = 0;
         v.lcnt[0][t] = 0; v.lcnt[1][t] = 0;

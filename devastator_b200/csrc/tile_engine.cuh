@@ -15,7 +15,7 @@ namespace deva_b200 {
 namespace tl {
 
 #ifndef DEVA_TILE_MINB
-#define DEVA_TILE_MINB 3   // resident blocks per SM the register allocator must allow
+#define DEVA_TILE_MINB 4   // resident blocks per SM the register allocator must allow
 #endif
 
 // ---- several GPUs: device-side exchange over the peers' IPC-mapped comm blocks (NVLink) ---------------
@@ -55,7 +55,7 @@ __device__ __forceinline__ void publish_counts(const TView &v) {
 }
 
 template <class M>
-__global__ void __launch_bounds__(TILE, DEVA_TILE_MINB)
+__global__ void __launch_bounds__(NTHR, DEVA_TILE_MINB)
 k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams mp, const __grid_constant__ TParams tp) {
   extern __shared__ __align__(128) unsigned char tl_smem[];
   TCtl *c = v.ctl;
@@ -63,21 +63,29 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
   if (phase != PH_EVAL && phase != PH_REBIN) return;   // done / idle: the launch is a no-op
   Blk b;
   blk_carve(b, tl_smem, tp.rcap);
-  if (threadIdx.x == 0) mbar_init(b.mbar, 1);
+  if (threadIdx.x == 0) {
+    mbar_init(b.mbar, 1);
+    blk_begin(b);
+    b.h->next_item = atomicAdd(&c->work, 1u);
+  }
   __syncthreads();
   const Epoch ep = load_epoch(c);
   const bool all_tiles = phase == PH_REBIN || c->full;
   const uint32_t n_work = all_tiles ? v.NT : c->dirty_n[ep.par ^ 1u];
   const uint32_t rebin_all = c->rebin_all;
   for (;;) {
-    if (threadIdx.x == 0) b.h->work_item = atomicAdd(&c->work, 1u);
-    __syncthreads();
-    const uint32_t w = b.h->work_item;
+    const uint32_t w = b.h->next_item;
     __syncthreads();
     if (w >= n_work) break;
+    if (threadIdx.x == 0) b.h->next_item = atomicAdd(&c->work, 1u);   // (its round trip hides behind this tile's work)
     const uint32_t tile = all_tiles ? w : v.dirty[ep.par ^ 1u][w];
     if (phase == PH_EVAL) eval_tile<M>(v, mp, ep, b, tile);
     else rebin_tile(v, ep, b, tile, v.scratch + (size_t)blockIdx.x * v.scratch_cap, rebin_all);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    blk_flush(v, b);
+    bulk_wait_all();   // the bulk stores of the tiles' states are complete
   }
   // the last block to finish closes the launch: follow-up, epoch commit, or calendar maintenance next
   __shared__ uint32_t is_last;
@@ -316,7 +324,7 @@ struct CudaBE {
     if (smem > (size_t)prop.sharedMemPerBlockOptin) return tile_fail(DEVA_B200_ERR_ARG, "DEVA_B200_TILE_RCAP=%u needs %zu bytes of shared memory per block", rcap, smem);
     int per_sm = (int)((size_t)prop.sharedMemPerMultiprocessor / (smem + 1024));
     per_sm = std::max(1, std::min(per_sm, (int)env_u32("DEVA_B200_TILE_BLOCKS_PER_SM", 8)));
-    per_sm = std::min(per_sm, prop.maxThreadsPerMultiProcessor / TILE);
+    per_sm = std::min(per_sm, prop.maxThreadsPerMultiProcessor / NTHR);
     grid = prop.multiProcessorCount * per_sm;
     xchg_grid = prop.multiProcessorCount;
     return 0;
@@ -430,7 +438,7 @@ struct CudaBE {
       TCU(cudaFuncSetAttribute(k_tile_step<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set[mi] = true;
     }
-    k_tile_step<M><<<grid, TILE, smem, stream>>>(v, mp, tp);
+    k_tile_step<M><<<grid, NTHR, smem, stream>>>(v, mp, tp);
     if (v.n_gpus > 1) k_tile_xchg<<<xchg_grid, 256, 0, stream>>>(v, tp, 0);
     TCU(cudaGetLastError());
     return 0;

@@ -25,7 +25,9 @@
 namespace deva_b200 {
 namespace tl {
 
-constexpr int TILE = 256;   // LPs per tile == threads per block
+constexpr int TILE = 256;   // LPs per tile (one block works on one tile at a time)
+constexpr int NTHR = 128;   // threads per block of the step kernel: warps pull chunks of 32 LPs, heaviest first
+constexpr int NBIN = 32;    // LPs are ordered by min(records held, NBIN - 1) before they run
 constexpr int NB = 32;      // ring slots of the calendar
 constexpr uint32_t NEVER = 0xffffffffu;
 

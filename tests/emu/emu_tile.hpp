@@ -106,10 +106,14 @@ struct HostBE {
     }
     Blk b = workspace(tp.rcap);
     const uint32_t rebin_all = c->rebin_all;
+    blk_begin(b);
+    size_t done = 0;
     for (uint32_t tile : work) {
       if (phase == PH_EVAL) eval_tile<M>(v, mp, ep, b, tile);
       else rebin_tile(v, ep, b, tile, v.scratch, rebin_all);
+      if (++done % 3 == 0) { blk_flush(v, b); blk_begin(b); }   // (several "blocks" share the launch)
     }
+    blk_flush(v, b);
     return true;
   }
   int k_net_pending(const TView &v) {
