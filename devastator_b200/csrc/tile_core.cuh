@@ -113,26 +113,27 @@ __device__ __forceinline__ void fence_async_smem() { TL_ASM("fence.proxy.async.s
 // the open epoch, as every block sees it for the whole launch
 struct Epoch {
   uint64_t cur_abs, ub, gvt;
-  uint32_t shift, par, in_epoch, epoch, stop, launch;
+  uint32_t shift, par, in_epoch, epoch, stop, launch, m;
   uint32_t sp_w_n, sp_r_n, sp_r_fresh;   // spill lists: readable part of the one this launch appends to; the other one; its fresh tail
 };
 DEVA_HD Epoch load_epoch(const TCtl *c) {
   Epoch ep;
   ep.cur_abs = c->cur_abs; ep.ub = c->ub; ep.gvt = c->gvt; ep.shift = c->shift; ep.par = c->par;
-  ep.in_epoch = c->in_epoch; ep.epoch = c->epoch; ep.stop = c->stop; ep.launch = c->launch;
+  ep.in_epoch = c->in_epoch; ep.epoch = c->epoch; ep.stop = c->stop; ep.launch = c->launch; ep.m = c->win_m;
   ep.sp_w_n = c->sp_start[ep.par]; ep.sp_r_n = c->sp_n[ep.par ^ 1u]; ep.sp_r_fresh = c->sp_fresh[ep.par ^ 1u];
   return ep;
 }
 
 // per-block accumulators (shared memory), folded into TCtl once per tile
 struct Hdr {
-  uint32_t n, nb, nl, nlw, nl_old, nf, first, slow, in_buf, slot, lo, hi, skip, used_far;
+  uint32_t n, nb, nl, nlw, nl_old, nf, first, slow, in_buf, lo, hi, skip, used_far;
+  uint32_t nbk[MAXM];                     // records of each of the window's buckets (nb = their sum)
   uint32_t bins[NBIN], n_active, chunk;   // LPs per record count; LPs that run; next chunk of 32 LPs to hand to a warp
   uint32_t work_item, next_item;
   // accumulated over all the tiles the block handles in a launch, folded into TCtl once (blk_flush)
   uint32_t executed, rolled, anti, remote, err, fresh_antis, evals, ovf;
   int32_t committed, nondet;
-  uint32_t bh[NB];        // records this block appended per ring slot (-> ctl->btotal)
+  alignas(8) uint32_t bh[NB + 4];    // records this block appended per ring slot (-> ctl->btotal); [NB] far count, [NB+2..3] far min time (u64)
 };
 
 // one block's shared-memory workspace
@@ -233,11 +234,16 @@ DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uin
     *err |= ERR_FAR_OVERFLOW; return;
   }
   st_ev(&v.far_[(size_t)tile * v.CF + p], rec);
-  atom_add_u64(&c->far_total, 1ull);
   if (d < NB) {                                      // belongs to the ring (its list is full, or it is the open bucket's
-    atom_or_u32(&v.tflags[tile], TF_OVF);            // tail beyond t_end): a rebin at the epoch's end puts it in place
+    atom_add_u64(&c->far_total, 1ull);               // tail beyond t_end): a rebin at the epoch's end puts it in place
+    atom_or_u32(&v.tflags[tile], TF_OVF);
     atom_or_u32(&c->ovf_flag, 1u);
+  } else if (bh) {                                   // beyond the ring: counted per block (bh[NB], bh[NB+1..2] = count, min time)
+    atom_add_u32(&bh[NB], 1u);
+    atom_min_u64(reinterpret_cast<uint64_t *>(&bh[NB + 2]), rec.time);
+    if (b < ep.cur_abs) atom_or_u32(&c->need_rebase, 1u);
   } else {
+    atom_add_u64(&c->far_total, 1ull);
     atom_min_ull(&c->far_min, rec.time);             // (far_min covers only records beyond the ring)
     if (b < ep.cur_abs) atom_or_u32(&c->need_rebase, 1u);   // a root below the calendar's base
   }
@@ -578,7 +584,8 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
 DEVA_HD void blk_begin(Blk &b) {
   Hdr &h = *b.h;
   h.executed = h.rolled = h.anti = h.remote = h.err = h.fresh_antis = h.evals = h.ovf = 0; h.committed = h.nondet = 0;
-  for (int i = 0; i < NB; i++) h.bh[i] = 0;
+  for (int i = 0; i < NB + 2; i++) h.bh[i] = 0;
+  h.bh[NB + 2] = h.bh[NB + 3] = 0xffffffffu;
 }
 DEVA_HD void blk_flush(const TView &v, Blk &b) {
   Hdr &h = *b.h;
@@ -594,6 +601,10 @@ DEVA_HD void blk_flush(const TView &v, Blk &b) {
   if (h.ovf) atom_or_u32(&c->ovf_flag, 1u);          // consumed far records must be dropped before the next epoch
   if (h.evals) atom_add_u64(&c->evals, h.evals);
   for (int i = 0; i < NB; i++) if (h.bh[i]) atom_add_u64(&c->btotal[i], h.bh[i]);
+  if (h.bh[NB]) {
+    atom_add_u64(&c->far_total, h.bh[NB]);
+    atom_min_ull(&c->far_min, *reinterpret_cast<unsigned long long *>(&h.bh[NB + 2]));
+  }
 }
 
 // One tile, one launch of an epoch.  Its window events are the open bucket's list (+ what waits for
@@ -607,8 +618,8 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
   const uint32_t rd = ep.par ^ 1u;                 // late list written by the previous launch
   TL_THREADS(tid) {
     if (tid != 0) continue;
-    h.slot = (uint32_t)(ep.cur_abs % NB);
-    h.nb = v.npub[tile];                           // (records appended to the open bucket since lie beyond ub)
+    h.nb = 0;                                      // (records appended to the open buckets since the epoch began lie beyond ub)
+    for (uint32_t k = 0; k < ep.m; k++) { h.nbk[k] = v.npub[(size_t)tile * MAXM + k]; h.nb += h.nbk[k]; }
     const uint32_t lc = v.lcnt[rd][tile];
     h.nl = lc < v.CL ? lc : v.CL;                  // all of it is complete: this launch appends to the other list
     h.first = v.tev[tile] != ep.epoch;
@@ -624,7 +635,8 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
   TL_SYNC();
   if (h.skip) return;
   const uint32_t out_buf = h.in_buf ^ 1u;
-  const EvRec *list = v.near_ + ((size_t)tile * NB + h.slot) * v.C;
+  // bucket k of the window lives in ring slot (cur_abs + k) % NB
+  auto blist = [&](uint32_t k) -> const EvRec * { return v.near_ + ((size_t)tile * NB + (uint32_t)((ep.cur_abs + k) % NB)) * v.C; };
   const EvRec *late_w = v.late[ep.par] + (size_t)tile * v.CL;
   const EvRec *late_r = v.late[rd] + (size_t)tile * v.CL;
   const LpState *s_in = v.st[h.in_buf] + (size_t)tile * TILE;
@@ -636,7 +648,10 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
 #if defined(__CUDA_ARCH__)
     if (threadIdx.x == 0) {
       mbar_expect_tx(b.mbar, n_src * (uint32_t)sizeof(EvRec) + TILE * (uint32_t)sizeof(LpState));
-      if (h.nb) bulk_g2s(b.R, list, h.nb * (uint32_t)sizeof(EvRec), b.mbar);
+      for (uint32_t k = 0, o = 0; k < ep.m; k++) {
+        if (h.nbk[k]) bulk_g2s(b.R + o, blist(k), h.nbk[k] * (uint32_t)sizeof(EvRec), b.mbar);
+        o += h.nbk[k];
+      }
       if (h.nlw) bulk_g2s(b.R + h.nb, late_w, h.nlw * (uint32_t)sizeof(EvRec), b.mbar);
       if (h.nl) bulk_g2s(b.R + h.nb + h.nlw, late_r, h.nl * (uint32_t)sizeof(EvRec), b.mbar);
       bulk_g2s(b.S, s_in, TILE * (uint32_t)sizeof(LpState), b.mbar);
@@ -644,7 +659,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     mbar_wait(b.mbar, b.mphase);
     b.mphase ^= 1u;
 #else
-    for (uint32_t i = 0; i < h.nb; i++) b.R[i] = list[i];
+    for (uint32_t k = 0, o = 0; k < ep.m; k++) { for (uint32_t i = 0; i < h.nbk[k]; i++) b.R[o + i] = blist(k)[i]; o += h.nbk[k]; }
     for (uint32_t i = 0; i < h.nlw; i++) b.R[h.nb + i] = late_w[i];
     for (uint32_t i = 0; i < h.nl; i++) b.R[h.nb + h.nlw + i] = late_r[i];
     for (int i = 0; i < TILE; i++) b.S[i] = s_in[i];
@@ -678,7 +693,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     // record i of the tile's sources; returns false for records that are not this tile's / not this epoch's
     auto fetch = [&](uint32_t i, EvRec &r, bool &fresh) -> bool {
       fresh = h.first != 0;
-      if (i < h.nb) r = list[i];
+      if (i < h.nb) { uint32_t k = 0, o = i; while (o >= h.nbk[k]) { o -= h.nbk[k]; k++; } r = blist(k)[o]; }
       else if (i < h.nb + h.nlw) r = late_w[i - h.nb];
       else if (i < n_src) { r = late_r[i - h.nb - h.nlw]; fresh |= i >= n_oldsrc; }
       else if (i < n_far_end) r = farl[i - n_src];
@@ -766,8 +781,7 @@ DEVA_HD void rebin_tile(const TView &v, const Epoch &ep, Blk &b, uint32_t tile, 
   Hdr &h = *b.h;
   TL_THREADS(tid) {
     if (tid != 0) continue;
-    h.n = 0; h.err = 0;
-    for (int i = 0; i < NB; i++) h.bh[i] = 0;
+    h.n = 0;
   }
   TL_SYNC();
   // gather: far list (+ every near list) -> scratch, dropping what is committed or annihilated
@@ -819,9 +833,9 @@ DEVA_HD void rebin_tile(const TView &v, const Epoch &ep, Blk &b, uint32_t tile, 
       const uint32_t p = atom_add_u32(&v.fcnt[tile], 1u);
       if (p >= v.CF) { err |= ERR_FAR_OVERFLOW; continue; }
       st_ev(&v.far_[(size_t)tile * v.CF + p], r);
-      atom_add_u64(&v.ctl->far_total, 1ull);
+      atom_add_u32(&h.bh[NB], 1u);
       if (d < NB) atom_or_u32(&v.tflags[tile], TF_OVF);   // its bucket's list is full: evaluated from here (slow path)
-      else atom_min_ull(&v.ctl->far_min, r.time);
+      else atom_min_u64(reinterpret_cast<uint64_t *>(&h.bh[NB + 2]), r.time);
     }
     if (err) atom_or_u32(&h.err, err);
   }
@@ -829,9 +843,7 @@ DEVA_HD void rebin_tile(const TView &v, const Epoch &ep, Blk &b, uint32_t tile, 
   TL_THREADS(tid) {
     if (tid != 0) continue;
     const uint32_t fc = v.fcnt[tile];
-    v.fpub[tile] = fc < v.CF ? fc : v.CF;
-    if (h.err) atom_or_u32(&v.ctl->err, h.err);
-    for (int i = 0; i < NB; i++) if (h.bh[i]) atom_add_u64(&v.ctl->btotal[i], h.bh[i]);
+    v.fpub[tile] = fc < v.CF ? fc : v.CF;   // (the block's counters reach TCtl at the kernel's end, blk_flush)
   }
   TL_SYNC();
 }
@@ -855,7 +867,7 @@ DEVA_HD uint64_t bucket_end(uint64_t b_abs, uint32_t shift) {
 }
 
 // Picks what the next launch does (single thread).  `inclusive`: the bucket at cur_abs may be the next one
-// (drain start, after a rebin); otherwise it has just been consumed.
+// (always, now: the caller moves cur_abs past what has been consumed).
 DEVA_HD void choose_next(TCtl *c, const TParams &tp, const Glob &g, bool inclusive) {
   c->in_epoch = 0;
   // a change of the bucket width re-buckets everything (window policy; pdes.cxx:233-280 only changes a scalar)
@@ -872,8 +884,10 @@ DEVA_HD void choose_next(TCtl *c, const TParams &tp, const Glob &g, bool inclusi
     const uint64_t bb = c->cur_abs + d;
     if (g.btotal[bb % NB] > 0) { nb_abs = bb; break; }
   }
+  uint32_t m = c->want_m < 1 ? 1u : (c->want_m > (uint32_t)MAXM ? (uint32_t)MAXM : c->want_m);
+  if (c->fixed_shift) m = 1;
   const uint64_t far_b = g.far_total > 0 && g.far_min != ~0ull ? g.far_min >> c->shift : ~0ull;
-  if (g.need_rebase || g.ovf_flag || (far_b != ~0ull && far_b <= nb_abs)) {
+  if (g.need_rebase || g.ovf_flag || (far_b != ~0ull && (nb_abs == ~0ull || far_b <= nb_abs + (m - 1)))) {
     // far records are due (or misplaced): re-bucket them against the base the next epoch will have
     uint64_t base = nb_abs < far_b ? nb_abs : far_b;
     if (base == ~0ull) base = c->cur_abs;
@@ -888,25 +902,42 @@ DEVA_HD void choose_next(TCtl *c, const TParams &tp, const Glob &g, bool inclusi
     c->gvt = ~0ull; c->phase = PH_DONE;
     return;
   }
-  // the bucket about to open holds more than the lists are built for (a start-up where every root falls
-  // into one bucket, a model denser than the current width suits): halve the width first
-  if (!c->fixed_shift && c->shift > 0 && g.btotal[nb_abs % NB] * 16ull > (unsigned long long)tp.pol_occ_x16 * c->lp_total) {
-    c->want_shift = c->shift - 1; c->hold = 2;
-    choose_next(c, tp, g, inclusive);
-    return;
+  // the buckets about to open hold more than the lists and the workspace are built for (a start-up where
+  // every root falls into a few ticks, a model denser than the current width suits): fewer buckets per
+  // epoch first, then narrower buckets
+  if (!c->fixed_shift) {
+    const unsigned long long limit = (unsigned long long)tp.pol_occ_x16 * c->lp_total;
+    for (;;) {
+      unsigned long long sum = 0;
+      for (uint32_t k = 0; k < m; k++) sum += g.btotal[(nb_abs + k) % NB];
+      if (sum * 16ull <= limit) break;
+      if (m > 1) { m = m / 2; c->want_m = m; c->hold = 1; continue; }
+      if (c->shift > 0) {
+        // narrow by as many halvings as the excess calls for, in one re-bucketing
+        uint32_t down = 1;
+        while (down < c->shift && ((sum * 16ull) >> down) > limit) down++;
+        c->want_shift = c->shift - down; c->hold = 2;
+        choose_next(c, tp, g, inclusive);
+        return;
+      }
+      break;
+    }
   }
   const uint64_t start = nb_abs << c->shift;
   c->cur_abs = nb_abs;
   if (start > c->gvt) c->gvt = start;
   if (c->gvt >= c->t_end) { c->phase = PH_DONE; return; }
-  const uint64_t be = bucket_end(nb_abs, c->shift);
+  const uint64_t be = bucket_end(nb_abs + (m - 1), c->shift);
+  c->win_m = m;
   c->ub = be < c->t_end ? be : c->t_end;
   c->phase = PH_EVAL; c->full = 1; c->in_epoch = 1; c->epoch++;
 }
 
-// Window policy (global_status_state::update, pdes.cxx:233-280): the bucket width is the optimism
-// window.  Efficiency = committed / executed over the last epochs; too much wasted work halves the
-// width, nearly none doubles it while the epochs are thin (few commits per LP).  Never changes results.
+// Window policy (global_status_state::update, pdes.cxx:233-280).  The optimism window is win_m buckets
+// of 1 << shift ticks.  Efficiency = committed / executed over the last epochs: too much wasted work
+// shrinks the window, nearly none grows it while the epochs are thin (few commits per LP).  The bucket
+// count moves first (free); the bucket width only when the count is at its limit (a re-bucketing).
+// Never changes results.
 DEVA_HD void policy_update(TCtl *c, const TParams &tp, const Glob &g) {
   if (c->fixed_shift) return;
   if (++c->pol_epochs < 2) return;
@@ -918,20 +949,32 @@ DEVA_HD void policy_update(TCtl *c, const TParams &tp, const Glob &g) {
   if (ex == 0 || cm <= 0) return;
   const unsigned long long eff_pm = (unsigned long long)cm * 1000ull / ex;
   const unsigned long long dens_x16 = (unsigned long long)cm * 16ull / (c->lp_total * n_ep);
-  if (eff_pm < tp.pol_lo_pm && c->shift > 0) { c->want_shift = c->shift - 1; c->hold = 2; }
-  else if (eff_pm > tp.pol_hi_pm && dens_x16 < tp.pol_density_x16 && c->shift < 40) { c->want_shift = c->shift + 1; c->hold = 2; }
+  const uint32_t m = c->win_m;
+  if (eff_pm < tp.pol_lo_pm) {
+    if (m > 1) c->want_m = m - (m + 2) / 3;
+    else if (c->shift > 0) { c->want_shift = c->shift - 1; c->want_m = 1; c->hold = 2; }
+  } else if (eff_pm > tp.pol_hi_pm && dens_x16 < tp.pol_density_x16) {
+    if (m < tp.pol_m_max) c->want_m = m + 1;
+    else if (c->shift < 40) {
+      // wider buckets; by two steps at once when the epochs are very thin (after a dense start-up)
+      const uint32_t up = dens_x16 * 4 < tp.pol_density_x16 ? 2u : 1u;
+      c->want_shift = c->shift + up; c->want_m = up == 2 ? 1u : (m + 1) / 2; c->hold = 2;
+    }
+  }
 }
 
 // An epoch opens: every tile's count of the open bucket is frozen (all threads of the closing block).
 DEVA_HD void open_epoch_snapshot(const TView &v) {
   const TCtl *c = v.ctl;
   if (c->phase != PH_EVAL || !c->full) return;
-  const uint32_t slot = (uint32_t)(c->cur_abs % NB);
+  const uint32_t m = c->win_m;
+  const uint64_t cur = c->cur_abs;
   TL_THREADS(tid) {
-    for (uint32_t t = tid; t < v.NT; t += TL_NTHR) {
-      const uint32_t nc = v.ncnt[(size_t)t * NB + slot];
-      v.npub[t] = nc < v.C ? nc : v.C;
-    }
+    for (uint32_t t = tid; t < v.NT; t += TL_NTHR)
+      for (uint32_t k = 0; k < m; k++) {
+        const uint32_t nc = v.ncnt[(size_t)t * NB + (uint32_t)((cur + k) % NB)];
+        v.npub[(size_t)t * MAXM + k] = nc < v.C ? nc : v.C;
+      }
   }
   TL_SYNC();
 }
@@ -941,9 +984,11 @@ DEVA_HD void open_epoch_snapshot(const TView &v) {
 DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
   TCtl *c = v.ctl;
   // (read by every thread before thread 0 moves the state machine on)
-  const uint32_t phase = c->phase, epoch = c->epoch;
-  const uint32_t slot = (uint32_t)(c->cur_abs % NB);
-  const bool whole = c->ub == bucket_end(c->cur_abs, c->shift);
+  const uint32_t phase = c->phase, epoch = c->epoch, m = c->win_m, shift = c->shift;
+  const uint64_t cur = c->cur_abs, ub = c->ub;
+  // buckets of the window consumed to their end (all of them unless t_end cut the window)
+  uint32_t n_whole = 0;
+  while (n_whole < m && bucket_end(cur + n_whole, shift) <= ub) n_whole++;
   const bool commit = phase == PH_EVAL && g.dirty_n == 0 && !g.err;
   TL_SYNC();
   if (commit) {
@@ -952,7 +997,7 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
     TL_THREADS(tid) {
       for (uint32_t t = tid; t < v.NT; t += TL_NTHR) {
         if (v.tev[t] == epoch) v.tcur[t] ^= 1u;
-        if (whole) v.ncnt[(size_t)t * NB + slot] = 0;
+        for (uint32_t k = 0; k < n_whole; k++) v.ncnt[(size_t)t * NB + (uint32_t)((cur + k) % NB)] = 0;
         v.lcnt[0][t] = 0; v.lcnt[1][t] = 0;
       }
     }
@@ -971,7 +1016,7 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
         c->full = 0; c->par ^= 1u;
         continue;
       }
-      if (whole) c->btotal[slot] = 0;
+      for (uint32_t k = 0; k < n_whole; k++) c->btotal[(cur + k) % NB] = 0;
       c->gvt = c->ub;
       c->epochs++;
       for (int i = 0; i < 2; i++) c->sp_n[i] = c->sp_start[i] = c->sp_fresh[i] = 0;
@@ -980,8 +1025,9 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
       policy_update(c, tp, g);
       if (c->gvt >= c->t_end) { c->phase = PH_DONE; c->in_epoch = 0; continue; }
       Glob g2 = g;
-      if (whole) g2.btotal[slot] = 0;
-      choose_next(c, tp, g2, !whole);
+      for (uint32_t k = 0; k < n_whole; k++) g2.btotal[(cur + k) % NB] = 0;
+      c->cur_abs = cur + n_whole;                  // first bucket not consumed to its end
+      choose_next(c, tp, g2, true);
     } else if (phase == PH_REBIN) {
       Glob g2;
       glob_from_ctl(g2, c, 0);                     // (several GPUs: the exchange kernel passes the sums)

@@ -100,6 +100,7 @@ struct TileEngine {
     tp.pol_hi_pm = env_u32("DEVA_B200_POL_HI", 960);
     tp.pol_density_x16 = env_u32("DEVA_B200_POL_DENSITY_X16", 40);
     tp.pol_occ_x16 = env_u32("DEVA_B200_POL_OCC_X16", 72);
+    tp.pol_m_max = std::min<uint32_t>(MAXM, std::max<uint32_t>(1, env_u32("DEVA_B200_POL_M_MAX", 2)));
     batch = std::max<uint32_t>(1, env_u32("DEVA_B200_TILE_BATCH", 16));
     int rc;
     if ((rc = be.open(c->device, tp.rcap))) return rc;
@@ -107,7 +108,7 @@ struct TileEngine {
     const size_t NT = v.NT, LP = NT * TILE;
 #define TA(p, n) if ((rc = be.alloc((void **)&(p), (size_t)(n) * sizeof(*(p))))) return rc;
     TA(v.st[0], LP) TA(v.st[1], LP) TA(v.tcur, NT) TA(v.tev, NT) TA(v.tflags, NT)
-    TA(v.near_, NT * NB * v.C) TA(v.ncnt, NT * NB) TA(v.npub, NT)
+    TA(v.near_, NT * NB * v.C) TA(v.ncnt, NT * NB) TA(v.npub, NT * MAXM)
     TA(v.late[0], NT * v.CL) TA(v.late[1], NT * v.CL) TA(v.lcnt[0], NT) TA(v.lcnt[1], NT) TA(v.lseen[0], NT) TA(v.lseen[1], NT) TA(v.dmark, NT)
     TA(v.far_, NT * v.CF) TA(v.fcnt, NT) TA(v.fpub, NT)
     TA(v.dirty[0], NT) TA(v.dirty[1], NT) TA(v.ctl, 1)
@@ -136,6 +137,7 @@ struct TileEngine {
     if (c->window) { shift = 0; while ((2ull << shift) <= c->window && shift < 40) shift++; hc.fixed_shift = 1; }
     else shift = env_u32("DEVA_B200_TILE_SHIFT0", 4);
     hc.shift = hc.want_shift = shift;
+    hc.win_m = hc.want_m = 1;
     hc.lp_total = c->lp_n;
     hc.far_min = ~0ull;
     if ((rc = clear_calendar(false))) return rc;
@@ -242,7 +244,7 @@ struct TileEngine {
       exec_ms += bms;
       hc.stop_req = (uint32_t)stop_req.load();
       if ((rc = be.read_ctl_set_stop(v, &hc, hc.stop_req))) { if (tf) fclose(tf); return rc; }
-      if (tf) fprintf(tf, "%llu,%llu,%llu,%u,%llu,%llu,%llu,%.4f\n", (unsigned long long)before.gvt, 1ull << hc.shift,
+      if (tf) fprintf(tf, "%llu,%llu,%llu,%u,%llu,%llu,%llu,%.4f\n", (unsigned long long)before.gvt, (unsigned long long)hc.win_m << hc.shift,
                       (unsigned long long)(hc.epochs - before.epochs), hc.launch - before.launch, (unsigned long long)(hc.executed - before.executed),
                       (unsigned long long)(hc.rolled - before.rolled), (unsigned long long)(hc.committed - before.committed), bms);
       if (hc.err) { if (tf) fclose(tf); return check_err(); }
@@ -311,7 +313,7 @@ struct TileEngine {
     memset(out, 0, sizeof *out);
     out->executed_n = hc.executed; out->committed_n = hc.committed; out->deterministic = hc.nondet > 0 ? 0 : 1;
     out->rolled_back_n = hc.rolled; out->anti_sent_n = hc.anti_sent; out->remote_sent_n = hc.remote_sent;
-    out->passes = passes0; out->window_last = 1ull << hc.shift; out->drain_ms = drain_ms; out->exec_kernel_ms = exec_ms;
+    out->passes = passes0; out->window_last = (uint64_t)hc.win_m << hc.shift; out->drain_ms = drain_ms; out->exec_kernel_ms = exec_ms;
     out->kernel_launches = launches;
     return 0;
   }

@@ -27,6 +27,7 @@ namespace tl {
 
 constexpr int TILE = 256;   // LPs per tile (one block works on one tile at a time)
 constexpr int NTHR = 128;   // threads per block of the step kernel: warps pull chunks of 32 LPs, heaviest first
+constexpr int MAXM = 8;     // an epoch's window spans 1..MAXM consecutive buckets (the policy's cheap knob)
 constexpr int NBIN = 32;    // LPs are ordered by min(records held, NBIN - 1) before they run
 constexpr int NB = 32;      // ring slots of the calendar
 constexpr uint32_t NEVER = 0xffffffffu;
@@ -66,6 +67,7 @@ struct TCtl {
   unsigned long long far_min;      // min time over the far lists (atomicMin on append; exact after a rebin)
   unsigned long long last_far_abs; // cur_abs at the last far rebin
   uint32_t shift, want_shift;      // bucket width = 1 << shift; the width the policy wants next
+  uint32_t win_m, want_m;          // buckets per epoch (window = win_m << shift); what the policy wants for the next epoch
   uint32_t phase, full, par, epoch, launch, hold;
   uint32_t rebin_all;              // PH_REBIN: 1 = re-bucket every list (width change), 0 = far lists only
   uint32_t fixed_shift;            // 1: window pinned by the caller (deva_static_look_dt, pdes.cxx:36)
@@ -102,7 +104,7 @@ struct TView {
   int32_t n_gpus, gpu_rank;
   LpState *st[2];
   uint32_t *tcur, *tev, *tflags;   // per tile: checkpoint buffer index; epoch of last evaluation; TF_*
-  EvRec *near_; uint32_t *ncnt, *npub;   // npub: the open bucket's record count when its epoch began (what evaluations read)
+  EvRec *near_; uint32_t *ncnt, *npub;   // npub[NT][MAXM]: the open buckets' record counts when their epoch began (what evaluations read)
   EvRec *late[2]; uint32_t *lcnt[2], *lseen[2];   // lseen: how many of a late list's records the tile's last evaluation saw
   uint32_t *dmark;                 // per tile: serial of the launch that last queued it for re-evaluation
   EvRec *far_; uint32_t *fcnt, *fpub;   // fpub: a tile's far count as of the last rebin (those records are complete)
@@ -124,6 +126,8 @@ struct TParams {          // launch-time constants
   uint32_t pol_lo_pm, pol_hi_pm;   // efficiency band (per mille) of the window policy
   uint32_t pol_density_x16;        // grow the window while commits per LP per epoch stay below this / 16
   uint32_t pol_occ_x16;            // halve it before opening a bucket that holds more than this / 16 records per LP
+  uint32_t pol_m_max;              // most buckets per epoch the policy uses (wider windows widen the buckets instead:
+                                   // the ring's horizon is NB buckets, and what lands beyond it costs a second pass)
 };
 
 }  // namespace tl
