@@ -113,13 +113,16 @@ __device__ __forceinline__ void fence_async_smem() { TL_ASM("fence.proxy.async.s
 // the open epoch, as every block sees it for the whole launch
 struct Epoch {
   uint64_t cur_abs, ub, gvt;
-  uint32_t shift, par, in_epoch, epoch, stop, launch, m;
+  uint32_t shift, par, in_epoch, epoch, stop, launch, m, partial, rc_n, tag;
+  uint64_t ring_hi, rc_lo;
   uint32_t sp_w_n, sp_r_n, sp_r_fresh;   // spill lists: readable part of the one this launch appends to; the other one; its fresh tail
 };
 DEVA_HD Epoch load_epoch(const TCtl *c) {
   Epoch ep;
   ep.cur_abs = c->cur_abs; ep.ub = c->ub; ep.gvt = c->gvt; ep.shift = c->shift; ep.par = c->par;
   ep.in_epoch = c->in_epoch; ep.epoch = c->epoch; ep.stop = c->stop; ep.launch = c->launch; ep.m = c->win_m;
+  ep.partial = c->partial; ep.rc_n = (c->full || c->phase == PH_REBIN) ? c->rc_n : 0u; ep.rc_lo = c->rc_lo; ep.tag = 0;
+  ep.ring_hi = c->in_epoch && c->full ? c->ring_hi : c->cur_abs + NB;
   ep.sp_w_n = c->sp_start[ep.par]; ep.sp_r_n = c->sp_n[ep.par ^ 1u]; ep.sp_r_fresh = c->sp_fresh[ep.par ^ 1u];
   return ep;
 }
@@ -188,6 +191,26 @@ DEVA_HD bool rec_less(const EvRec &a, const EvRec &b) {
   return a.p1 < b.p1;
 }
 
+// A late list's counter carries the epoch it counts for above the count (epoch << 32 | count), so that
+// an epoch's commit need not touch every tile: the first arrival of a new epoch restarts the count.
+DEVA_HD uint32_t late_count(unsigned long long raw, uint32_t epoch) { return (uint32_t)(raw >> 32) == epoch ? (uint32_t)raw : 0u; }
+DEVA_HD uint32_t late_claim(unsigned long long *p, uint32_t epoch) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(p);
+  for (;;) {
+    const unsigned long long nw = (uint32_t)(old >> 32) == epoch ? old + 1ull : (((unsigned long long)epoch << 32) | 1ull);
+    const unsigned long long seen = atomicCAS(p, old, nw);
+    if (seen == old) return (uint32_t)nw - 1u;
+    old = seen;
+  }
+#else
+  const unsigned long long old = *p;
+  const unsigned long long nw = (uint32_t)(old >> 32) == epoch ? old + 1ull : (((unsigned long long)epoch << 32) | 1ull);
+  *p = nw;
+  return (uint32_t)nw - 1u;
+#endif
+}
+
 // ---- routing: where a record goes (execute_context::send, pdes.hxx:666-732; arrive_*, pdes.cxx:393-493)
 //   other GPU            -> this GPU's region of that GPU's receive buffer (NVLink store)
 //   time < ub (in epoch) -> the destination tile's LATE list: a straggler / anti-message / in-window child
@@ -203,7 +226,7 @@ DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uin
   if (!ep.in_epoch) atom_min_ull(&c->gvt, rec.time);   // a root: the commit horizon cannot lie above it
   if (ep.in_epoch && rec.time < ep.ub) {
     if (rec.time < ep.gvt) { *err |= ERR_BELOW_GVT; return; }
-    const uint32_t p = atom_add_u32(&v.lcnt[ep.par][tile], 1u);
+    const uint32_t p = late_claim(&v.lcnt[ep.par][tile], ep.epoch);
     if (atom_exch_u32(&v.dmark[tile], ep.launch) != ep.launch)                    // first arrival of this launch:
       v.dirty[ep.par][atom_add_u32(&c->dirty_n[ep.par], 1u)] = tile;              // the tile joins the next launch
     if (p < v.CL) st_ev(&v.late[ep.par][(size_t)tile * v.CL + p], rec);
@@ -215,7 +238,7 @@ DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uin
   }
   const uint64_t b = rec.time >> ep.shift;
   const uint64_t d = b - ep.cur_abs;                 // (wraps to huge when b < cur_abs: goes to far, flagged)
-  if (d < NB) {   // (the open bucket itself only when t_end cuts it: evaluations read its count as of the epoch's start)
+  if (d < NB && b < ep.ring_hi) {   // (the open buckets themselves only when t_end cuts them: evaluations then read frozen counts)
     const uint32_t slot = (uint32_t)(b % NB);
     const uint32_t p = atom_add_u32(&v.ncnt[(size_t)tile * NB + slot], 1u);
     if (p < v.C) {
@@ -618,11 +641,20 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
   const uint32_t rd = ep.par ^ 1u;                 // late list written by the previous launch
   TL_THREADS(tid) {
     if (tid != 0) continue;
-    h.nb = 0;                                      // (records appended to the open buckets since the epoch began lie beyond ub)
-    for (uint32_t k = 0; k < ep.m; k++) { h.nbk[k] = v.npub[(size_t)tile * MAXM + k]; h.nb += h.nbk[k]; }
-    const uint32_t lc = v.lcnt[rd][tile];
+    // the lists of the window committed last are empty from here on (nobody appends to them in this launch)
+    for (uint32_t k = 0; k < ep.rc_n; k++) v.ncnt[(size_t)tile * NB + (uint32_t)((ep.rc_lo + k) % NB)] = 0;
+    h.nb = 0;
+    for (uint32_t k = 0; k < ep.m; k++) {
+      // (t_end cuts the window: records beyond ub are appended to its buckets meanwhile, the counts were frozen)
+      const uint32_t nc = ep.partial ? v.npub[(size_t)tile * MAXM + k] : v.ncnt[(size_t)tile * NB + (uint32_t)((ep.cur_abs + k) % NB)];
+      h.nbk[k] = nc < v.C ? nc : v.C;
+      h.nb += h.nbk[k];
+    }
+    const uint32_t lc = late_count(v.lcnt[rd][tile], ep.epoch);
     h.nl = lc < v.CL ? lc : v.CL;                  // all of it is complete: this launch appends to the other list
-    h.first = v.tev[tile] != ep.epoch;
+    const uint32_t tev = v.tev[tile];
+    h.first = tev != ep.epoch;
+
     h.nlw = h.first ? 0u : v.lseen[ep.par][tile];  // the other list: what this tile has evaluated before (complete, too)
     h.nl_old = h.first ? 0u : v.lseen[rd][tile];
     h.nf = (v.tflags[tile] & TF_OVF) ? v.fpub[tile] : 0u;   // (count as of the last rebin: those records are complete)
@@ -630,6 +662,9 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     h.skip = (h.nb + h.nl + h.nlw + h.nf) == 0;
     h.slow = h.nf > 0 || h.nb + h.nl + h.nlw > b.rcap || ep.sp_w_n > 0 || ep.sp_r_n > 0;
     if (ep.sp_w_n > 0 || ep.sp_r_n > 0) h.skip = 0;
+    // its last evaluation's epoch is committed: that result is the state now (a tile that is skipped
+    // keeps the swap for the evaluation that will update tev)
+    if (!h.skip && h.first && tev != NEVER) { v.tcur[tile] ^= 1u; h.in_buf ^= 1u; }
     h.used_far = 0;
   }
   TL_SYNC();
@@ -782,6 +817,7 @@ DEVA_HD void rebin_tile(const TView &v, const Epoch &ep, Blk &b, uint32_t tile, 
   TL_THREADS(tid) {
     if (tid != 0) continue;
     h.n = 0;
+    for (uint32_t k = 0; k < ep.rc_n; k++) v.ncnt[(size_t)tile * NB + (uint32_t)((ep.rc_lo + k) % NB)] = 0;   // (see eval_tile)
   }
   TL_SYNC();
   // gather: far list (+ every near list) -> scratch, dropping what is committed or annihilated
@@ -930,6 +966,8 @@ DEVA_HD void choose_next(TCtl *c, const TParams &tp, const Glob &g, bool inclusi
   const uint64_t be = bucket_end(nb_abs + (m - 1), c->shift);
   c->win_m = m;
   c->ub = be < c->t_end ? be : c->t_end;
+  c->partial = c->ub < be ? 1u : 0u;
+  if (c->ring_hi < nb_abs + 1) c->ring_hi = nb_abs + 1;   // (at least the window's own first bucket)
   c->phase = PH_EVAL; c->full = 1; c->in_epoch = 1; c->epoch++;
 }
 
@@ -966,7 +1004,7 @@ DEVA_HD void policy_update(TCtl *c, const TParams &tp, const Glob &g) {
 // An epoch opens: every tile's count of the open bucket is frozen (all threads of the closing block).
 DEVA_HD void open_epoch_snapshot(const TView &v) {
   const TCtl *c = v.ctl;
-  if (c->phase != PH_EVAL || !c->full) return;
+  if (c->phase != PH_EVAL || !c->full || !c->partial) return;
   const uint32_t m = c->win_m;
   const uint64_t cur = c->cur_abs;
   TL_THREADS(tid) {
@@ -991,21 +1029,15 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
   while (n_whole < m && bucket_end(cur + n_whole, shift) <= ub) n_whole++;
   const bool commit = phase == PH_EVAL && g.dirty_n == 0 && !g.err;
   TL_SYNC();
-  if (commit) {
-    // ---- epoch commit (fossil collection, pdes.cxx:816-871): everything below ub is final.  The
-    // tiles that ran swap their state buffers; a bucket consumed to its end gives its lists back.
-    TL_THREADS(tid) {
-      for (uint32_t t = tid; t < v.NT; t += TL_NTHR) {
-        if (v.tev[t] == epoch) v.tcur[t] ^= 1u;
-        for (uint32_t k = 0; k < n_whole; k++) v.ncnt[(size_t)t * NB + (uint32_t)((cur + k) % NB)] = 0;
-        v.lcnt[0][t] = 0; v.lcnt[1][t] = 0;
-      }
-    }
-    TL_SYNC();
-  }
+  // ---- epoch commit (fossil collection, pdes.cxx:816-871): everything below ub is final.  Nothing is
+  // touched per tile here: a tile that ran swaps its state buffers when it is next evaluated (or at
+  // the drain's exit), the consumed buckets' lists are emptied by their tiles in the next launch, and
+  // the late lists' counters restart by their epoch tag.
+  (void)commit; (void)epoch;
   TL_THREADS(tid) {
     if (tid != 0) continue;
     c->work = 0; c->ticket = 0; c->launch++;
+    if (c->full || phase == PH_REBIN) c->rc_n = 0;   // every tile has emptied the lists of the window committed before
     c->dirty_n[c->par ^ 1u] = 0;                   // the list this launch consumed
     c->sp_fresh[c->par] = c->sp_start[c->par];     // spill list this launch appended to: its new records start here
     c->sp_start[c->par] = c->sp_n[c->par] < v.SP ? c->sp_n[c->par] : v.SP;
@@ -1017,6 +1049,7 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
         continue;
       }
       for (uint32_t k = 0; k < n_whole; k++) c->btotal[(cur + k) % NB] = 0;
+      c->rc_lo = cur; c->rc_n = n_whole; c->ring_hi = cur + NB;
       c->gvt = c->ub;
       c->epochs++;
       for (int i = 0; i < 2; i++) c->sp_n[i] = c->sp_start[i] = c->sp_fresh[i] = 0;
@@ -1053,6 +1086,11 @@ DEVA_HD void begin_drain(const TView &v, const TParams &tp, uint64_t t_end, cons
   }
   TL_SYNC();
   open_epoch_snapshot(v);
+}
+
+// drain exit: a tile evaluated in the (committed) last epochs takes its result as its state
+DEVA_HD void settle_tile(const TView &v, uint32_t t) {
+  if (v.tev[t] != NEVER) { v.tcur[t] ^= 1u; v.tev[t] = NEVER; }
 }
 
 // ---- setup -------------------------------------------------------------------------------------------

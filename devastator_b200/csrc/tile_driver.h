@@ -150,11 +150,11 @@ struct TileEngine {
     if (keep_ctl_from_device && (rc = be.read_ctl(v, &hc))) return rc;
     const size_t NT = v.NT;
     if ((rc = be.zero(v.ncnt, NT * NB * 4)) || (rc = be.zero(v.fcnt, NT * 4)) || (rc = be.zero(v.fpub, NT * 4)) ||
-        (rc = be.zero(v.lcnt[0], NT * 4)) || (rc = be.zero(v.lcnt[1], NT * 4)) || (rc = be.zero(v.tflags, NT * 4)) ||
+        (rc = be.zero(v.lcnt[0], NT * 8)) || (rc = be.zero(v.lcnt[1], NT * 8)) || (rc = be.zero(v.tflags, NT * 4)) ||
         (rc = be.zero(v.tcur, NT * 4)) || (rc = be.fill_ff(v.tev, NT * 4)) || (rc = be.fill_ff(v.dmark, NT * 4)))
       return rc;
     hc.cur_abs = 0; hc.ub = 0; hc.gvt = 0; hc.t_end = 0; hc.far_min = ~0ull; hc.phase = PH_IDLE; hc.full = 0; hc.par = 0;
-    hc.in_epoch = 0; hc.work = hc.ticket = 0; hc.dirty_n[0] = hc.dirty_n[1] = 0; for (int i = 0; i < 2; i++) hc.sp_n[i] = hc.sp_start[i] = hc.sp_fresh[i] = 0; hc.ovf_flag = hc.need_rebase = 0;
+    hc.in_epoch = 0; hc.partial = 0; hc.rc_n = 0; hc.rc_lo = 0; hc.ring_hi = NB; hc.work = hc.ticket = 0; hc.dirty_n[0] = hc.dirty_n[1] = 0; for (int i = 0; i < 2; i++) hc.sp_n[i] = hc.sp_start[i] = hc.sp_fresh[i] = 0; hc.ovf_flag = hc.need_rebase = 0;
     for (int i = 0; i < NB; i++) hc.btotal[i] = 0;
     hc.far_total = 0; hc.antis_pending = 0; hc.err = 0; hc.nondet = 0;
     hc.want_shift = hc.shift;
@@ -254,6 +254,8 @@ struct TileEngine {
     }
     if (tf) fclose(tf);
     passes0 += hc.launch - launch0;
+    if ((rc = be.k_settle(v))) return rc;
+    launches++;
     // exit: no positive / anti pair may stay pending (it would lower the GVT returned, pdes.cxx:878-886)
     if (hc.antis_pending > 0) {
       if ((rc = be.k_net_pending(v))) return rc;

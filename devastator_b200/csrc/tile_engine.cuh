@@ -260,6 +260,11 @@ __global__ void k_tile_state(TView v, uint64_t *aos, uint32_t first, uint32_t co
   }
 }
 
+__global__ void k_tile_settle(TView v) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < v.NT) settle_tile(v, t);
+}
+
 __global__ void k_tile_net_pending(TView v) {
   const Epoch ep = load_epoch(v.ctl);
   for (uint32_t t = blockIdx.x; t < v.NT; t += gridDim.x) {
@@ -440,6 +445,11 @@ struct CudaBE {
     }
     k_tile_step<M><<<grid, NTHR, smem, stream>>>(v, mp, tp);
     if (v.n_gpus > 1) k_tile_xchg<<<xchg_grid, 256, 0, stream>>>(v, tp, 0);
+    TCU(cudaGetLastError());
+    return 0;
+  }
+  int k_settle(const TView &v) {
+    k_tile_settle<<<(v.NT + 255) / 256, 256, 0, stream>>>(v);
     TCU(cudaGetLastError());
     return 0;
   }

@@ -73,6 +73,11 @@ struct TCtl {
   uint32_t fixed_shift;            // 1: window pinned by the caller (deva_static_look_dt, pdes.cxx:36)
   uint32_t stop, stop_req;         // bench PHOLD cut-off flag, latched at epoch boundaries
   uint32_t in_epoch;               // appends below ub are stragglers of the open epoch
+  uint32_t partial;                // t_end cuts the window's last bucket: evaluations read the counts frozen in npub
+  unsigned long long ring_hi;      // ring appends go to buckets below this (the slots of the window committed last are recycled
+                                   // by their tiles during the epoch's first launch, so that launch's horizon stops short of them)
+  unsigned long long rc_lo;        // first bucket of the window committed last ...
+  uint32_t rc_n, rc_pad;           // ... and how many of its buckets were consumed to their end (their lists are to be emptied)
   // ---- work distribution within a launch
   uint32_t work, ticket;
   uint32_t dirty_n[2];
@@ -105,7 +110,7 @@ struct TView {
   LpState *st[2];
   uint32_t *tcur, *tev, *tflags;   // per tile: checkpoint buffer index; epoch of last evaluation; TF_*
   EvRec *near_; uint32_t *ncnt, *npub;   // npub[NT][MAXM]: the open buckets' record counts when their epoch began (what evaluations read)
-  EvRec *late[2]; uint32_t *lcnt[2], *lseen[2];   // lseen: how many of a late list's records the tile's last evaluation saw
+  EvRec *late[2]; unsigned long long *lcnt[2]; uint32_t *lseen[2];   // lcnt: epoch << 32 | records (restarts with every epoch);   // lseen: how many of a late list's records the tile's last evaluation saw
   uint32_t *dmark;                 // per tile: serial of the launch that last queued it for re-evaluation
   EvRec *far_; uint32_t *fcnt, *fpub;   // fpub: a tile's far count as of the last rebin (those records are complete)
   uint32_t *dirty[2];              // tiles that received in-window arrivals during a launch

@@ -339,6 +339,7 @@ static int emu_tile_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, in
     EmuTile *t = es[k]->tile;
     t->hc = *t->v.ctl;
     if (t->hc.err) return t->check_err();
+    t->be.k_settle(t->v);
     if (t->hc.antis_pending > 0) t->be.k_net_pending(t->v);
     uint64_t m = ~0ull;
     if (t->hc.gvt != ~0ull) t->be.k_min_pending(t->v, &m);

@@ -116,6 +116,7 @@ struct HostBE {
     blk_flush(v, b);
     return true;
   }
+  int k_settle(const TView &v) { for (uint32_t t = 0; t < v.NT; t++) settle_tile(v, t); return 0; }
   int k_net_pending(const TView &v) {
     const Epoch ep = load_epoch(v.ctl);
     uint32_t err = 0, matched = 0;
