@@ -238,7 +238,8 @@ DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uin
   }
   const uint64_t b = rec.time >> ep.shift;
   const uint64_t d = b - ep.cur_abs;                 // (wraps to huge when b < cur_abs: goes to far, flagged)
-  if (d < NB && b < ep.ring_hi) {   // (the open buckets themselves only when t_end cuts them: evaluations then read frozen counts)
+  const bool in_ring = d < NB && b < ep.ring_hi;   // (the open buckets themselves only when t_end cuts them: evaluations then read frozen counts)
+  if (in_ring) {
     const uint32_t slot = (uint32_t)(b % NB);
     const uint32_t p = atom_add_u32(&v.ncnt[(size_t)tile * NB + slot], 1u);
     if (p < v.C) {
@@ -257,7 +258,7 @@ DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uin
     *err |= ERR_FAR_OVERFLOW; return;
   }
   st_ev(&v.far_[(size_t)tile * v.CF + p], rec);
-  if (d < NB) {                                      // belongs to the ring (its list is full, or it is the open bucket's
+  if (in_ring) {                                     // belongs to the ring (its list is full, or it is the open bucket's
     atom_add_u64(&c->far_total, 1ull);               // tail beyond t_end): a rebin at the epoch's end puts it in place
     atom_or_u32(&v.tflags[tile], TF_OVF);
     atom_or_u32(&c->ovf_flag, 1u);
