@@ -41,10 +41,14 @@ namespace tl {
 #define TL_THREADS(tid) for (int tid = (int)threadIdx.x, tl_once_ = 1; tl_once_; tl_once_ = 0)
 #define TL_SYNC() __syncthreads()
 #define TL_NTHR ((uint32_t)blockDim.x)
+#define TL_LANES(lane) for (int lane = (int)(threadIdx.x & 31), tl_lo_ = 1; tl_lo_; tl_lo_ = 0)
+#define TL_WSYNC() __syncwarp()
 #else
 #define TL_THREADS(tid) for (int tid = 0; tid < NTHR; tid++)
 #define TL_SYNC() ((void)0)
 #define TL_NTHR ((uint32_t)NTHR)
+#define TL_LANES(lane) for (int lane = 0; lane < 32; lane++)
+#define TL_WSYNC() ((void)0)
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -129,7 +133,7 @@ DEVA_HD Epoch load_epoch(const TCtl *c) {
 
 // per-block accumulators (shared memory), folded into TCtl once per tile
 struct Hdr {
-  uint32_t n, nb, nl, nlw, nl_old, nf, first, slow, in_buf, lo, hi, skip, used_far;
+  uint32_t n, nb, nl, nlw, nl_old, nf, first, slow, in_buf, lo, hi, skip, used_far, seg_big;
   uint32_t nbk[MAXM];                     // records of each of the window's buckets (nb = their sum)
   uint32_t bins[NBIN], n_active, chunk;   // LPs per record count; LPs that run; next chunk of 32 LPs to hand to a warp
   uint32_t work_item, next_item;
@@ -145,13 +149,14 @@ struct Blk {
   LpState *S;        // [TILE]  LP states: loaded from the checkpoint buffer, updated in place
   uint16_t *ord;     // [rcap]  record indices grouped by LP
   uint8_t *efl;      // [rcap]  per-record flags (F_*)
-  uint32_t *off;     // [TILE+1] segment bounds per LP
+  uint32_t *off;     // [GOFF]  segment bounds per LP (TILE + 1 used)
   uint32_t *cur;     // [TILE]  histogram / scatter cursors
   uint16_t *perm;    // [TILE]  LPs in the order they run (most records first)
   Hdr *h;
   uint64_t *mbar;
   uint32_t rcap;
   uint32_t mphase;   // mbarrier phase parity (uniform across the block)
+  unsigned char *pool; uint32_t pool_bytes;   // R | S | ord | efl as one region: the warps' workspaces in a follow-up launch
 };
 enum : uint8_t { F_FRESH = 1, F_ANTI = 2, F_INOLD = 4, F_INNEW = 8, F_CN = 16, F_CO = 32, F_OUT = 64, F_DEAD = 128 };
 
@@ -159,7 +164,7 @@ DEVA_HD size_t blk_bytes(uint32_t rcap) {
   size_t b = (size_t)rcap * sizeof(EvRec) + TILE * sizeof(LpState);
   b += (size_t)rcap * 2; b = (b + 15) & ~(size_t)15;
   b += rcap; b = (b + 15) & ~(size_t)15;
-  b += (TILE + 1) * 4; b = (b + 15) & ~(size_t)15;
+  b += GOFF * 4;
   b += TILE * 4;
   b += TILE * 2;
   b += sizeof(Hdr); b = (b + 15) & ~(size_t)15;
@@ -169,11 +174,13 @@ DEVA_HD size_t blk_bytes(uint32_t rcap) {
 DEVA_HD void blk_carve(Blk &b, unsigned char *base, uint32_t rcap) {
   size_t o = 0;
   b.rcap = rcap;
+  b.pool = base;
   b.R = reinterpret_cast<EvRec *>(base); o += (size_t)rcap * sizeof(EvRec);
   b.S = reinterpret_cast<LpState *>(base + o); o += TILE * sizeof(LpState);
   b.ord = reinterpret_cast<uint16_t *>(base + o); o += (size_t)rcap * 2; o = (o + 15) & ~(size_t)15;
   b.efl = reinterpret_cast<uint8_t *>(base + o); o += rcap; o = (o + 15) & ~(size_t)15;
-  b.off = reinterpret_cast<uint32_t *>(base + o); o += (TILE + 1) * 4; o = (o + 15) & ~(size_t)15;
+  b.pool_bytes = (uint32_t)o;
+  b.off = reinterpret_cast<uint32_t *>(base + o); o += GOFF * 4;
   b.cur = reinterpret_cast<uint32_t *>(base + o); o += TILE * 4;
   b.perm = reinterpret_cast<uint16_t *>(base + o); o += TILE * 2;
   b.h = reinterpret_cast<Hdr *>(base + o); o += sizeof(Hdr); o = (o + 15) & ~(size_t)15;
@@ -447,11 +454,13 @@ DEVA_HD void block_scan(Blk &b) {
 #endif
 }
 
-// One LP's window: net its anti-messages, sort its records, walk them.
+// One LP's window: net its anti-messages, sort its records, walk them.  `first`: the epoch's first
+// evaluation of a tile by a block (state in b.S, children take their parents' slots); otherwise the LP
+// is re-evaluated from the checkpoint `sin` and differences are sent / cancelled at once.
 template <class M>
-DEVA_HD void run_lp(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf, uint32_t lp) {
+DEVA_HD void run_lp_core(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf, uint32_t lp,
+                         uint32_t s0, uint32_t s1, const LpState &sin, bool first) {
   Hdr &h = *b.h;
-  const uint32_t s0 = b.off[lp], s1 = b.off[lp + 1];
   const uint64_t gid = v.lp_begin + (uint64_t)tile * TILE + lp;
   uint32_t err = 0, remote = 0, anti_sent = 0, fresh_antis = 0;
   net_segment(b, s0, s1, &err, &fresh_antis);
@@ -464,9 +473,9 @@ DEVA_HD void run_lp(const TView &v, const ModelParams &mp, const Epoch &ep, Blk 
     b.ord[k] = ia;
   }
   Chain ch;
-  chain_start(ch, b.S[lp]);
+  chain_start(ch, sin);
   ch.cur = s0;
-  if (h.first) {
+  if (first) {
     walk<M>(v, mp, ep, b, s1, gid, MODE_FIRST, ch, &err, &remote, &anti_sent);
 #pragma unroll
     for (int w = 0; w < MAX_STW; w++) b.S[lp].w[w] = ch.st[w];
@@ -495,6 +504,11 @@ DEVA_HD void run_lp(const TView &v, const ModelParams &mp, const Epoch &ep, Blk 
   if (remote) atom_add_u32(&h.remote, remote);
   if (anti_sent) atom_add_u32(&h.anti, anti_sent);
   if (fresh_antis) atom_add_u32(&h.fresh_antis, fresh_antis);
+}
+template <class M>
+DEVA_HD void run_lp(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf, uint32_t lp) {
+  const LpState sin = b.S[lp];
+  run_lp_core<M>(v, mp, ep, b, tile, out_buf, lp, b.off[lp], b.off[lp + 1], sin, b.h->first != 0);
 }
 
 // Sort the block's records b.R[0..n) by LP (counting sort on the LP's index in the tile), order the
@@ -541,6 +555,7 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
         for (uint32_t j = s0; j < s1; j++) { const uint8_t f = b.efl[b.ord[j]]; fresh |= (f & (F_FRESH | F_DEAD)) == F_FRESH; }
         n = fresh ? s1 - s0 : 0u;
       }
+      if (s1 - s0 > SEG_WARP_MAX) h.seg_big = 1;   // (benign race: any writer stores 1)
       const uint32_t key = n < (uint32_t)NBIN - 1u ? n : (uint32_t)NBIN - 1u;
       uint32_t pos;
 #if defined(__CUDA_ARCH__)
@@ -666,7 +681,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     // its last evaluation's epoch is committed: that result is the state now (a tile that is skipped
     // keeps the swap for the evaluation that will update tev)
     if (!h.skip && h.first && tev != NEVER) { v.tcur[tile] ^= 1u; h.in_buf ^= 1u; }
-    h.used_far = 0;
+    h.used_far = 0; h.seg_big = 0;
   }
   TL_SYNC();
   if (h.skip) return;
@@ -786,17 +801,28 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
 
   // ---- write back: first evaluation stores the whole tile's states (one bulk copy) into the
   // result buffer; a re-evaluation has stored the LPs it changed itself
+  // The fast path also leaves the per-LP index of the window's records (positions in the bucket lists,
+  // grouped by LP): a warp that re-evaluates single LPs of this tile later in the epoch fetches just theirs.
+  const bool idx = h.first && !h.slow && !h.seg_big && h.nl + h.nlw == 0;
   if (h.first) {
 #if defined(__CUDA_ARCH__)
     fence_async_smem();
     __syncthreads();
     if (threadIdx.x == 0) {
       bulk_s2g(v.st[out_buf] + (size_t)tile * TILE, b.S, TILE * (uint32_t)sizeof(LpState));
+      if (idx) {
+        bulk_s2g(v.goff + (size_t)tile * GOFF, b.off, GOFF * 4u);
+        if (h.n) bulk_s2g(v.gord + (size_t)tile * v.gr, b.ord, ((h.n * 2u) + 15u) & ~15u);
+      }
       bulk_commit();
-      bulk_wait_read();   // (the workspace is reused by the next tile; the kernel's end waits for the write itself)
+      bulk_wait_read();   // (the workspace is reused by the next tile; the kernel's end waits for the writes themselves)
     }
 #else
     for (int i = 0; i < TILE; i++) v.st[out_buf][(size_t)tile * TILE + i] = b.S[i];
+    if (idx) {
+      for (int i = 0; i <= TILE; i++) v.goff[(size_t)tile * GOFF + i] = b.off[i];
+      for (uint32_t i = 0; i < h.n; i++) v.gord[(size_t)tile * v.gr + i] = b.ord[i];
+    }
 #endif
   }
   TL_THREADS(tid) {
@@ -804,10 +830,175 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     v.tev[tile] = ep.epoch;
     v.lseen[rd][tile] = h.nl;
     v.lseen[ep.par][tile] = h.nlw;
+    if (h.first) {   // this epoch's flags (TF_OVF is the appenders')
+      const uint32_t keep = v.tflags[tile] & TF_OVF;
+      const uint32_t want = keep | (idx ? (uint32_t)TF_IDX : 0u) | ((h.slow || h.seg_big) ? (uint32_t)TF_HEAVY : 0u);
+#if defined(__CUDA_ARCH__)
+      atomicAnd(&v.tflags[tile], (uint32_t)TF_OVF);
+      atomicOr(&v.tflags[tile], want);
+#else
+      v.tflags[tile] = want;
+#endif
+    }
     if (h.used_far) h.ovf = 1;
     h.evals++;
   }
   TL_SYNC();
+}
+
+// ---- follow-up launches: ONE WARP re-evaluates a tile --------------------------------------------------
+// A tile that received stragglers / anti-messages has a handful of affected LPs (17 of 256 on
+// BASELINE's PHOLD).  Instead of loading and sorting the whole window again, a warp finds the affected
+// LPs from the fresh arrivals, fetches just their records - the bucket records through the index the
+// first evaluation left (gord / goff), the arrivals by scanning the two short late lists - into its
+// share of the block's shared memory, and each lane re-runs one LP from the checkpoint.
+struct WHdr {
+  uint32_t first, in_buf, nl, nlw, nl_old, nb, n_aff, idx_ok, round_n, nbk[MAXM];
+  uint32_t bitmap[TILE / 32];
+  uint32_t need[32], offs[32];
+};
+struct WBlk {
+  WHdr *h; uint8_t *alist; EvRec *R; uint16_t *ord; uint8_t *efl; uint32_t cap;
+};
+DEVA_HD void warp_carve(WBlk &w, const Blk &b, int warp, int n_warps) {
+  const uint32_t region = (b.pool_bytes / (uint32_t)n_warps) & ~15u;
+  unsigned char *base = b.pool + (size_t)warp * region;
+  size_t o = 0;
+  w.h = reinterpret_cast<WHdr *>(base); o += (sizeof(WHdr) + 15) & ~(size_t)15;
+  w.alist = base + o; o += TILE;
+  const uint32_t cap = ((region - (uint32_t)o) / 35u) & ~7u;   // 32 (record) + 2 (index) + 1 (flags) bytes each
+  w.cap = cap;
+  w.R = reinterpret_cast<EvRec *>(base + o); o += (size_t)cap * sizeof(EvRec);
+  w.ord = reinterpret_cast<uint16_t *>(base + o); o += (size_t)cap * 2;
+  w.efl = base + o;
+}
+
+template <class M>
+DEVA_HD void follow_tile_warp(const TView &v, const ModelParams &mp0, const Epoch &ep, Blk &b, WBlk &w, uint32_t tile) {
+  WHdr &h = *w.h;
+#if !defined(__CUDA_ARCH__) && defined(DEVA_TILE_DEBUG)
+  { static unsigned long n_warp_tiles = 0; if ((++n_warp_tiles & 1023) == 1) fprintf(stderr, "warp path tiles: %lu\n", n_warp_tiles); }
+#endif
+  ModelParams mp = mp0;
+  mp.stop = (int32_t)ep.stop;
+  const uint32_t rd = ep.par ^ 1u;
+  const uint64_t tile_gid = v.lp_begin + (uint64_t)tile * TILE;
+  TL_LANES(lane) {
+    if (lane != 0) continue;
+    const uint32_t tev = v.tev[tile];
+    h.first = tev != ep.epoch;
+    h.in_buf = v.tcur[tile];
+    if (h.first && tev != NEVER) { v.tcur[tile] ^= 1u; h.in_buf ^= 1u; }   // (see eval_tile)
+    const uint32_t lc = late_count(v.lcnt[rd][tile], ep.epoch);
+    h.nl = lc < v.CL ? lc : v.CL;
+    h.nlw = h.first ? 0u : v.lseen[ep.par][tile];
+    h.nl_old = h.first ? 0u : v.lseen[rd][tile];
+    h.idx_ok = !h.first && (v.tflags[tile] & TF_IDX);
+    h.nb = 0;
+    for (uint32_t k = 0; k < ep.m; k++) {
+      const uint32_t nc = ep.partial ? v.npub[(size_t)tile * MAXM + k] : v.ncnt[(size_t)tile * NB + (uint32_t)((ep.cur_abs + k) % NB)];
+      h.nbk[k] = nc < v.C ? nc : v.C;
+      h.nb += h.nbk[k];
+    }
+    for (int i = 0; i < TILE / 32; i++) h.bitmap[i] = 0;
+  }
+  TL_WSYNC();
+  const uint32_t out_buf = h.in_buf ^ 1u;
+  const LpState *s_in = v.st[h.in_buf] + (size_t)tile * TILE;
+  const EvRec *late_w = v.late[ep.par] + (size_t)tile * v.CL;
+  const EvRec *late_r = v.late[rd] + (size_t)tile * v.CL;
+  auto live = [&](const EvRec &r) { return !(r.time >= ep.ub || r.time < ep.gvt || (r.flags & EV_DEAD)); };
+  if (h.first) {   // the tile's first evaluation in this epoch: every LP's result starts as its checkpoint
+    TL_LANES(lane) { for (uint32_t i = lane; i < (uint32_t)TILE; i += 32) v.st[out_buf][(size_t)tile * TILE + i] = s_in[i]; }
+    TL_WSYNC();
+  }
+  // ---- affected LPs: destinations of the fresh arrivals
+  TL_LANES(lane) {
+    for (uint32_t i = h.nl_old + lane; i < h.nl; i += 32) {
+      const EvRec r = ld_ev(&late_r[i]);
+      if (!live(r)) continue;
+      const uint32_t lp = (uint32_t)((uint64_t)r.dst - tile_gid);
+      atom_or_u32(&h.bitmap[lp >> 5], 1u << (lp & 31u));
+    }
+  }
+  TL_WSYNC();
+  TL_LANES(lane) {
+    if (lane != 0) continue;
+    uint32_t n = 0;
+    for (uint32_t wd = 0; wd < (uint32_t)TILE / 32; wd++)
+      for (uint32_t m = h.bitmap[wd]; m; m &= m - 1) w.alist[n++] = (uint8_t)(wd * 32u + (uint32_t)ffs32(m) - 1u);
+    h.n_aff = n;
+  }
+  TL_WSYNC();
+  Blk wb = b;   // the walk's view: this warp's records; the block's accumulators
+  wb.R = w.R; wb.ord = w.ord; wb.efl = w.efl;
+  const uint32_t *goff = v.goff + (size_t)tile * GOFF;
+  const uint16_t *gord = v.gord + (size_t)tile * v.gr;
+  for (uint32_t base = 0; base < h.n_aff;) {
+    // how many records each of the next 32 LPs holds
+    TL_LANES(lane) {
+      uint32_t need = 0;
+      if (base + lane < h.n_aff) {
+        const uint32_t lp = w.alist[base + lane];
+        if (h.idx_ok) need = goff[lp + 1] - goff[lp];
+        const uint32_t gd = (uint32_t)(tile_gid + lp);
+        for (uint32_t i = 0; i < h.nlw; i++) need += late_w[i].dst == gd;
+        for (uint32_t i = 0; i < h.nl; i++) need += late_r[i].dst == gd;
+      }
+      h.need[lane] = need;
+    }
+    TL_WSYNC();
+    TL_LANES(lane) {
+      if (lane != 0) continue;
+      uint32_t cum = 0, k = 0;
+      while (k < 32 && base + k < h.n_aff && cum + h.need[k] <= w.cap) { h.offs[k] = cum; cum += h.need[k]; k++; }
+      if (k == 0) { atom_or_u32(&b.h->err, ERR_LP_OVERFLOW); h.offs[0] = 0; h.need[0] = 0; k = 1; }   // (guarded by SEG_WARP_MAX / LATE_WARP_MAX)
+      h.round_n = k;
+    }
+    TL_WSYNC();
+    TL_LANES(lane) {
+      if ((uint32_t)lane >= h.round_n) continue;
+      const uint32_t lp = w.alist[base + lane];
+      const uint32_t gd = (uint32_t)(tile_gid + lp);
+      const uint32_t s0 = h.offs[lane];
+      uint32_t n = s0;
+      auto put = [&](const EvRec &r, bool fresh) {
+        if (!live(r)) return;
+        w.R[n] = r;
+        w.efl[n] = (uint8_t)((fresh ? F_FRESH : 0) | ((r.flags & EV_ANTI) ? F_ANTI : 0));
+        w.ord[n] = (uint16_t)n;
+        n++;
+      };
+      if (h.idx_ok && h.need[lane]) {
+        for (uint32_t j = goff[lp]; j < goff[lp + 1]; j++) {
+          uint32_t pos = gord[j], k = 0;
+          while (k + 1 < ep.m && pos >= h.nbk[k]) { pos -= h.nbk[k]; k++; }
+          put(ld_ev(v.near_ + ((size_t)tile * NB + (uint32_t)((ep.cur_abs + k) % NB)) * v.C + pos), false);
+        }
+      }
+      for (uint32_t i = 0; i < h.nlw; i++) if (late_w[i].dst == gd) put(ld_ev(&late_w[i]), false);
+      for (uint32_t i = 0; i < h.nl; i++) if (late_r[i].dst == gd) put(ld_ev(&late_r[i]), h.first || i >= h.nl_old);
+      const LpState sin = s_in[lp];
+      run_lp_core<M>(v, mp, ep, wb, tile, out_buf, lp, s0, n, sin, false);
+    }
+    TL_WSYNC();
+    base += h.round_n;
+  }
+  TL_LANES(lane) {
+    if (lane != 0) continue;
+    v.tev[tile] = ep.epoch;
+    v.lseen[rd][tile] = h.nl;
+    v.lseen[ep.par][tile] = h.nlw;
+    if (h.first) {
+#if defined(__CUDA_ARCH__)
+      atomicAnd(&v.tflags[tile], (uint32_t)TF_OVF);
+#else
+      v.tflags[tile] &= TF_OVF;
+#endif
+    }
+    atom_add_u32(&b.h->evals, 1u);
+  }
+  TL_WSYNC();
 }
 
 // ---- calendar maintenance (PH_REBIN): one tile's far list - or every list of the tile when the
@@ -1034,7 +1225,31 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
   // touched per tile here: a tile that ran swaps its state buffers when it is next evaluated (or at
   // the drain's exit), the consumed buckets' lists are emptied by their tiles in the next launch, and
   // the late lists' counters restart by their epoch tag.
-  (void)commit; (void)epoch;
+  (void)commit;
+  // ---- a follow-up launch comes next: its tiles are split between warps (a few LPs to re-run from
+  // the index the first evaluation left) and whole blocks (tiles that went the slow way, or hold a lot)
+  if (phase == PH_EVAL && g.dirty_n > 0 && !g.err) {
+    const uint32_t par = c->par, nd = c->dirty_n[par];
+    const bool spill = c->sp_n[0] != 0 || c->sp_n[1] != 0;
+    TL_THREADS(tid) { if (tid == 0) { c->nw_work = 0; c->nb_work = 0; } }
+    TL_SYNC();
+    TL_THREADS(tid) {
+      for (uint32_t i = tid; i < nd; i += TL_NTHR) {
+        const uint32_t t = v.dirty[par][i];
+        const bool first = v.tev[t] != epoch;
+        const uint32_t fl = v.tflags[t];
+        const uint32_t nlate = late_count(v.lcnt[0][t], epoch) + late_count(v.lcnt[1][t], epoch);
+        bool heavy = spill || nlate > LATE_WARP_MAX || (fl & TF_OVF);
+        if (!first) heavy |= !(fl & TF_IDX) || (fl & TF_HEAVY);
+        else {   // not evaluated yet in this epoch: the warp path assumes its buckets are empty
+          for (uint32_t k = 0; k < m; k++) heavy |= v.ncnt[(size_t)t * NB + (uint32_t)((cur + k) % NB)] != 0;
+        }
+        if (heavy) v.blist[atom_add_u32(&c->nb_work, 1u)] = t;
+        else v.wlist[atom_add_u32(&c->nw_work, 1u)] = t;
+      }
+    }
+    TL_SYNC();
+  }
   TL_THREADS(tid) {
     if (tid != 0) continue;
     c->work = 0; c->ticket = 0; c->launch++;
@@ -1047,6 +1262,7 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
     if (phase == PH_EVAL) {
       if (g.dirty_n > 0) {                         // stragglers / anti-messages arrived: follow-up launch over their tiles
         c->full = 0; c->par ^= 1u;
+        c->workw = 0;
         continue;
       }
       for (uint32_t k = 0; k < n_whole; k++) c->btotal[(cur + k) % NB] = 0;

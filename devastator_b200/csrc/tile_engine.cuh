@@ -71,16 +71,32 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
   __syncthreads();
   const Epoch ep = load_epoch(c);
   const bool all_tiles = phase == PH_REBIN || c->full;
-  const uint32_t n_work = all_tiles ? v.NT : c->dirty_n[ep.par ^ 1u];
+  const uint32_t n_work = all_tiles ? v.NT : c->nb_work;   // follow-up launch: the tiles re-evaluated by whole blocks
   const uint32_t rebin_all = c->rebin_all;
   for (;;) {
     const uint32_t w = b.h->next_item;
     __syncthreads();
     if (w >= n_work) break;
     if (threadIdx.x == 0) b.h->next_item = atomicAdd(&c->work, 1u);   // (its round trip hides behind this tile's work)
-    const uint32_t tile = all_tiles ? w : v.dirty[ep.par ^ 1u][w];
+    const uint32_t tile = all_tiles ? w : v.blist[w];
     if (phase == PH_EVAL) eval_tile<M>(v, mp, ep, b, tile);
     else rebin_tile(v, ep, b, tile, v.scratch + (size_t)blockIdx.x * v.scratch_cap, rebin_all);
+    __syncthreads();
+  }
+  if (phase == PH_EVAL && !all_tiles) {
+    // follow-up launch: the other tiles, one warp each, re-running only the LPs that received something
+    __syncthreads();
+    WBlk wk;
+    warp_carve(wk, b, (int)(threadIdx.x >> 5), NTHR / 32);
+    const uint32_t nw = c->nw_work;
+    const int lane = (int)(threadIdx.x & 31);
+    for (;;) {
+      uint32_t wi = 0;
+      if (lane == 0) wi = atomicAdd(&c->workw, 1u);
+      wi = __shfl_sync(0xffffffffu, wi, 0);
+      if (wi >= nw) break;
+      follow_tile_warp<M>(v, mp, ep, b, wk, v.wlist[wi]);
+    }
     __syncthreads();
   }
   if (threadIdx.x == 0) {

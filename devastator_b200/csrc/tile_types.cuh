@@ -45,7 +45,14 @@ enum : uint32_t {   // engine errors beyond pdes_types.cuh's (same word)
   ERR_LATE_OVERFLOW = 256u, ERR_FAR_OVERFLOW = 512u, ERR_TILE_OVERFLOW = 1024u, ERR_LP_OVERFLOW = 2048u,
   ERR_PEER_TIMEOUT = 4096u
 };
-enum : uint32_t { TF_OVF = 1u };   // tile flag: its far list holds records that belong to a near bucket
+enum : uint32_t {
+  TF_OVF = 1u,     // tile flag: its far list holds records that belong to a near bucket
+  TF_HEAVY = 2u,   // this epoch's first evaluation went the slow way (or one LP holds very many records): re-evaluate by block
+  TF_IDX = 4u      // this epoch's first evaluation left the per-LP index of the window's records (gord / goff)
+};
+constexpr int GOFF = TILE + 4;        // row length of goff (u32; TILE + 1 used, padded to 16 bytes)
+constexpr uint32_t SEG_WARP_MAX = 64; // an LP with more window records than this is re-evaluated by a whole block
+constexpr uint32_t LATE_WARP_MAX = 160;
 
 // what every GPU tells every other GPU once per round (device-side exchange, no host, no NCCL)
 struct DEVA_ALIGN(16) PeerMsg {
@@ -80,6 +87,7 @@ struct TCtl {
   uint32_t rc_n, rc_pad;           // ... and how many of its buckets were consumed to their end (their lists are to be emptied)
   // ---- work distribution within a launch
   uint32_t work, ticket;
+  uint32_t workw, nw_work, nb_work, wpad;   // follow-up launch: next warp item; tiles for warps; tiles for blocks
   uint32_t dirty_n[2];
   uint32_t sp_n[2], sp_start[2], sp_fresh[2];   // spill lists: records; count when the list's last launch began; first record of that launch
   uint32_t ovf_flag, need_rebase;
@@ -114,6 +122,9 @@ struct TView {
   uint32_t *dmark;                 // per tile: serial of the launch that last queued it for re-evaluation
   EvRec *far_; uint32_t *fcnt, *fpub;   // fpub: a tile's far count as of the last rebin (those records are complete)
   uint32_t *dirty[2];              // tiles that received in-window arrivals during a launch
+  uint32_t *wlist, *blist;         // ... split for the next launch: re-evaluated by one warp each / by a whole block (heavy)
+  uint16_t *gord; uint32_t *goff;  // [NT][rcap], [NT][GOFF]: the window's records grouped by LP (positions in the bucket lists), left by
+  uint32_t gr;                     //   a tile's first evaluation for the warps that re-evaluate single LPs; gr = row length of gord
   EvRec *spill[2]; uint32_t SP;    // in-window arrivals beyond a late list's capacity (any tile), kept for the epoch like the late lists
   TCtl *ctl;
   EvRec *scratch; uint32_t scratch_cap;   // rebin: one tile's worth of records per resident block

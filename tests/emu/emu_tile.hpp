@@ -97,13 +97,15 @@ struct HostBE {
     if (phase != PH_EVAL && phase != PH_REBIN) return false;
     const Epoch ep = load_epoch(c);
     const bool all_tiles = phase == PH_REBIN || c->full;
-    std::vector<uint32_t> work;
+    std::vector<uint32_t> work, wwork;
     if (all_tiles) { work.resize(v.NT); for (uint32_t i = 0; i < v.NT; i++) work[i] = i; }
-    else work.assign(v.dirty[ep.par ^ 1u], v.dirty[ep.par ^ 1u] + c->dirty_n[ep.par ^ 1u]);
-    if (shuffle && work.size() > 1) {   // the order blocks pick up tiles in is not defined on the GPU either
+    else { work.assign(v.blist, v.blist + c->nb_work); wwork.assign(v.wlist, v.wlist + c->nw_work); }
+    auto shuf = [&](std::vector<uint32_t> &x) {   // the order blocks / warps pick up tiles in is not defined on the GPU either
+      if (!shuffle || x.size() < 2) return;
       uint64_t s = shuffle * 0x9E3779B97F4A7C15ull + (++launch_no);
-      for (size_t i = work.size(); i > 1; i--) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; std::swap(work[i - 1], work[s % i]); }
-    }
+      for (size_t i = x.size(); i > 1; i--) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; std::swap(x[i - 1], x[s % i]); }
+    };
+    shuf(work); shuf(wwork);
     Blk b = workspace(tp.rcap);
     const uint32_t rebin_all = c->rebin_all;
     blk_begin(b);
@@ -112,6 +114,11 @@ struct HostBE {
       if (phase == PH_EVAL) eval_tile<M>(v, mp, ep, b, tile);
       else rebin_tile(v, ep, b, tile, v.scratch, rebin_all);
       if (++done % 3 == 0) { blk_flush(v, b); blk_begin(b); }   // (several "blocks" share the launch)
+    }
+    if (!wwork.empty()) {   // follow-up launch: tiles re-evaluated by one warp each (a warp's share of the block's workspace)
+      WBlk wk;
+      warp_carve(wk, b, (int)(launch_no % (NTHR / 32)), NTHR / 32);
+      for (uint32_t tile : wwork) follow_tile_warp<M>(v, mp, ep, b, wk, tile);
     }
     blk_flush(v, b);
     return true;
