@@ -457,9 +457,12 @@ DEVA_HD void block_scan(Blk &b) {
 // One LP's window: net its anti-messages, sort its records, walk them.  `first`: the epoch's first
 // evaluation of a tile by a block (state in b.S, children take their parents' slots); otherwise the LP
 // is re-evaluated from the checkpoint `sin` and differences are sent / cancelled at once.
-template <class M>
+template <class M, bool FULLK>
 DEVA_HD void run_lp_core(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf, uint32_t lp,
-                         uint32_t s0, uint32_t s1, const LpState &sin, bool first) {
+                         uint32_t s0, uint32_t s1, const LpState &sin, bool first_rt) {
+  // FULLK: compiled for the kernel of an epoch's first launch, where every evaluation is a first one -
+  // the re-evaluation code (two chains alive at once) is not even instantiated there
+  const bool first = FULLK ? true : first_rt;
   Hdr &h = *b.h;
   const uint64_t gid = v.lp_begin + (uint64_t)tile * TILE + lp;
   uint32_t err = 0, remote = 0, anti_sent = 0, fresh_antis = 0;
@@ -483,7 +486,7 @@ DEVA_HD void run_lp_core(const TView &v, const ModelParams &mp, const Epoch &ep,
     atom_add_u32(&h.executed, ch.cnt);
     atom_add_u32((uint32_t *)&h.committed, ch.cnt);
     if (ch.tie) atom_add_u32((uint32_t *)&h.nondet, 1u);
-  } else {
+  } else if (!FULLK) {
     const bool forked = walk<M>(v, mp, ep, b, s1, gid, MODE_SHARED, ch, &err, &remote, &anti_sent);
     if (forked) {
       Chain old = ch;
@@ -505,16 +508,16 @@ DEVA_HD void run_lp_core(const TView &v, const ModelParams &mp, const Epoch &ep,
   if (anti_sent) atom_add_u32(&h.anti, anti_sent);
   if (fresh_antis) atom_add_u32(&h.fresh_antis, fresh_antis);
 }
-template <class M>
+template <class M, bool FULLK>
 DEVA_HD void run_lp(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf, uint32_t lp) {
   const LpState sin = b.S[lp];
-  run_lp_core<M>(v, mp, ep, b, tile, out_buf, lp, b.off[lp], b.off[lp + 1], sin, b.h->first != 0);
+  run_lp_core<M, FULLK>(v, mp, ep, b, tile, out_buf, lp, b.off[lp], b.off[lp + 1], sin, b.h->first != 0);
 }
 
 // Sort the block's records b.R[0..n) by LP (counting sort on the LP's index in the tile), order the
 // LPs by how many records they hold, run them - warps pull chunks of 32 LPs, heaviest first, so that a
 // warp's lanes run equally long - and flush the children.
-template <class M>
+template <class M, bool FULLK>
 DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf) {
   Hdr &h = *b.h;
   const uint64_t tile_gid = v.lp_begin + (uint64_t)tile * TILE;
@@ -598,12 +601,12 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
       c = __shfl_sync(0xffffffffu, c, 0);
       if (c * 32u >= h.n_active) break;
       const uint32_t idx = c * 32u + (uint32_t)lane;
-      if (idx < h.n_active) run_lp<M>(v, mp, ep, b, tile, out_buf, b.perm[idx]);
+      if (idx < h.n_active) run_lp<M, FULLK>(v, mp, ep, b, tile, out_buf, b.perm[idx]);
       __syncwarp();
     }
   }
 #else
-  for (uint32_t idx = 0; idx < h.n_active; idx++) run_lp<M>(v, mp, ep, b, tile, out_buf, b.perm[idx]);
+  for (uint32_t idx = 0; idx < h.n_active; idx++) run_lp<M, FULLK>(v, mp, ep, b, tile, out_buf, b.perm[idx]);
 #endif
   TL_SYNC();
   // ---- flush: every slot that now holds a child goes to its list (all lanes busy, atomics in bulk)
@@ -649,7 +652,7 @@ DEVA_HD void blk_flush(const TView &v, Blk &b) {
 // One tile, one launch of an epoch.  Its window events are the open bucket's list (+ what waits for
 // that bucket in the far list) and the in-window arrivals of this epoch: the late list the previous
 // launch wrote (complete) and the part of the other one an earlier evaluation has seen.
-template <class M>
+template <class M, bool FULLK>
 DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, Blk &b, uint32_t tile) {
   Hdr &h = *b.h;
   ModelParams mp = mp0;
@@ -728,7 +731,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
       }
     }
     TL_SYNC();
-    run_records<M>(v, mp, ep, b, tile, out_buf);
+    run_records<M, FULLK>(v, mp, ep, b, tile, out_buf);
   } else {
     // ---- slow path: the window does not fit in shared memory (a start-up bucket holding every root,
     // many same-time events) or part of it waits in the far list: LP sub-ranges, one sweep each
@@ -793,7 +796,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
       TL_SYNC();
       TL_THREADS(tid) { if (tid == 0 && h.n > b.rcap) h.n = b.rcap; }
       TL_SYNC();
-      run_records<M>(v, mp, ep, b, tile, out_buf);
+      run_records<M, FULLK>(v, mp, ep, b, tile, out_buf);
       TL_THREADS(tid) { if (tid == 0) h.lo = h.hi; }
       TL_SYNC();
     }
@@ -979,7 +982,7 @@ DEVA_HD void follow_tile_warp(const TView &v, const ModelParams &mp0, const Epoc
       for (uint32_t i = 0; i < h.nlw; i++) if (late_w[i].dst == gd) put(ld_ev(&late_w[i]), false);
       for (uint32_t i = 0; i < h.nl; i++) if (late_r[i].dst == gd) put(ld_ev(&late_r[i]), h.first || i >= h.nl_old);
       const LpState sin = s_in[lp];
-      run_lp_core<M>(v, mp, ep, wb, tile, out_buf, lp, s0, n, sin, false);
+      run_lp_core<M, false>(v, mp, ep, wb, tile, out_buf, lp, s0, n, sin, false);
     }
     TL_WSYNC();
     base += h.round_n;

@@ -54,13 +54,18 @@ __device__ __forceinline__ void publish_counts(const TView &v) {
   }
 }
 
-template <class M>
-__global__ void __launch_bounds__(NTHR, DEVA_TILE_MINB)
+// FULLK = true: the kernel of an epoch's first launch (every tile, first evaluations only) and of the
+// calendar maintenance; FULLK = false: the kernel of the follow-up launches (re-evaluations).  The host
+// enqueues them in a fixed pattern (one full, three follow-ups, ...); a launch whose turn it is not
+// returns at once - what the next launch has to do is decided on the device (close_launch).
+template <class M, bool FULLK>
+__global__ void __launch_bounds__(NTHR, FULLK ? DEVA_TILE_MINB : 3)
 k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams mp, const __grid_constant__ TParams tp) {
   extern __shared__ __align__(128) unsigned char tl_smem[];
   TCtl *c = v.ctl;
   const uint32_t phase = c->phase;
   if (phase != PH_EVAL && phase != PH_REBIN) return;   // done / idle: the launch is a no-op
+  if (FULLK != (phase == PH_REBIN || c->full != 0)) return;   // not this kernel's turn
   Blk b;
   blk_carve(b, tl_smem, tp.rcap);
   if (threadIdx.x == 0) {
@@ -79,11 +84,11 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
     if (w >= n_work) break;
     if (threadIdx.x == 0) b.h->next_item = atomicAdd(&c->work, 1u);   // (its round trip hides behind this tile's work)
     const uint32_t tile = all_tiles ? w : v.blist[w];
-    if (phase == PH_EVAL) eval_tile<M>(v, mp, ep, b, tile);
+    if (phase == PH_EVAL) eval_tile<M, FULLK>(v, mp, ep, b, tile);
     else rebin_tile(v, ep, b, tile, v.scratch + (size_t)blockIdx.x * v.scratch_cap, rebin_all);
     __syncthreads();
   }
-  if (phase == PH_EVAL && !all_tiles) {
+  if (!FULLK && phase == PH_EVAL && !all_tiles) {
     // follow-up launch: the other tiles, one warp each, re-running only the LPs that received something
     __syncthreads();
     WBlk wk;
@@ -112,6 +117,7 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
   if (!is_last) return;
   __threadfence();
   if (v.n_gpus > 1) {   // several GPUs: the exchange kernel closes the launch, once the peers' figures are in
+    if (threadIdx.x == 0) c->stepped = 1;
     publish_counts(v);
     return;
   }
@@ -127,6 +133,7 @@ __global__ void __launch_bounds__(256) k_tile_xchg(const __grid_constant__ TView
   TCtl *c = v.ctl;
   const uint32_t phase = c->phase;
   if (!begin_mode && phase != PH_EVAL && phase != PH_REBIN) return;
+  if (!begin_mode && !c->stepped) return;   // the step kernel before was not its turn (decided alike on every GPU)
   const int G = v.n_gpus, me = v.gpu_rank;
   const uint32_t r = c->round;
   const unsigned long long tag = (unsigned long long)r + 1ull;
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(256) k_tile_xchg(const __grid_constant__ TView
     if (timeout) g.err |= ERR_PEER_TIMEOUT;
     c->round = r + 1u;
     c->xticket = 0;
+    c->stepped = 0;
   }
   __syncthreads();
   if (begin_mode) begin_drain(v, tp, c->t_end, g);
@@ -327,7 +335,8 @@ struct CudaBE {
   unsigned long long *h_tmp = nullptr;
   char *stage = nullptr;
   size_t stage_bytes = 0;
-  int grid = 0, xchg_grid = 148;
+  int grid = 0, grid_follow = 0, xchg_grid = 148;
+  uint32_t step_no = 0, pattern = 4;   // one full-launch slot in every `pattern` launches
   size_t smem = 0;
   bool smem_set[2] = {false, false};
 
@@ -343,14 +352,21 @@ struct CudaBE {
     TCU(cudaGetDeviceProperties(&prop, dev));
     smem = blk_bytes(rcap);
     if (smem > (size_t)prop.sharedMemPerBlockOptin) return tile_fail(DEVA_B200_ERR_ARG, "DEVA_B200_TILE_RCAP=%u needs %zu bytes of shared memory per block", rcap, smem);
-    int per_sm = (int)((size_t)prop.sharedMemPerMultiprocessor / (smem + 1024));
-    per_sm = std::max(1, std::min(per_sm, (int)env_u32("DEVA_B200_TILE_BLOCKS_PER_SM", 8)));
-    per_sm = std::min(per_sm, prop.maxThreadsPerMultiProcessor / NTHR);
-    grid = prop.multiProcessorCount * per_sm;
+    // persistent grids: exactly as many blocks as are resident at once (registers and shared memory decide)
+    TCU(cudaFuncSetAttribute(k_tile_step<PholdTest, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCU(cudaFuncSetAttribute(k_tile_step<PholdTest, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ_full = 1, occ_follow = 1;
+    TCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_full, k_tile_step<PholdTest, true>, NTHR, smem));
+    TCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_follow, k_tile_step<PholdTest, false>, NTHR, smem));
+    const int cap = (int)env_u32("DEVA_B200_TILE_BLOCKS_PER_SM", 16);
+    grid = prop.multiProcessorCount * std::max(1, std::min(occ_full, cap));
+    grid_follow = prop.multiProcessorCount * std::max(1, std::min(occ_follow, cap));
     xchg_grid = prop.multiProcessorCount;
+    pattern = std::max<uint32_t>(2, env_u32("DEVA_B200_TILE_PATTERN", 4));
+    if (getenv("DEVA_B200_TILE_VERBOSE")) fprintf(stderr, "deva_b200 tile engine: TILE %d, %d threads, rcap %u, smem %zu B, blocks/SM full %d follow %d\n", TILE, NTHR, rcap, smem, occ_full, occ_follow);
     return 0;
   }
-  int grid_blocks() const { return grid; }
+  int grid_blocks() const { return std::max(grid, grid_follow); }
   int alloc(void **p, size_t bytes) {
     cudaError_t r = cudaMalloc(p, bytes ? bytes : 16);
     if (r != cudaSuccess) return tile_fail(DEVA_B200_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(r));
@@ -456,10 +472,13 @@ struct CudaBE {
   int k_step(const TView &v, const ModelParams &mp, const TParams &tp) {
     const int mi = M::MODEL_ID == 2 ? 1 : 0;
     if (!smem_set[mi]) {
-      TCU(cudaFuncSetAttribute(k_tile_step<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TCU(cudaFuncSetAttribute(k_tile_step<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TCU(cudaFuncSetAttribute(k_tile_step<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set[mi] = true;
     }
-    k_tile_step<M><<<grid, NTHR, smem, stream>>>(v, mp, tp);
+    // pattern: full, follow, follow, follow (an epoch is one full launch and, on BASELINE's PHOLD, 2-3 follow-ups)
+    if ((step_no++ % pattern) == 0) k_tile_step<M, true><<<grid, NTHR, smem, stream>>>(v, mp, tp);
+    else k_tile_step<M, false><<<grid_follow, NTHR, smem, stream>>>(v, mp, tp);
     if (v.n_gpus > 1) k_tile_xchg<<<xchg_grid, 256, 0, stream>>>(v, tp, 0);
     TCU(cudaGetLastError());
     return 0;

@@ -25,8 +25,14 @@
 namespace deva_b200 {
 namespace tl {
 
-constexpr int TILE = 256;   // LPs per tile (one block works on one tile at a time)
-constexpr int NTHR = 128;   // threads per block of the step kernel: warps pull chunks of 32 LPs, heaviest first
+#ifndef DEVA_TILE_LPS
+#define DEVA_TILE_LPS 256
+#endif
+#ifndef DEVA_TILE_NTHR
+#define DEVA_TILE_NTHR 128
+#endif
+constexpr int TILE = DEVA_TILE_LPS;   // LPs per tile (one block works on one tile at a time)
+constexpr int NTHR = DEVA_TILE_NTHR;   // threads per block of the step kernel: warps pull chunks of 32 LPs, heaviest first
 constexpr int MAXM = 8;     // an epoch's window spans 1..MAXM consecutive buckets (the policy's cheap knob)
 constexpr int NBIN = 32;    // LPs are ordered by min(records held, NBIN - 1) before they run
 constexpr int NB = 32;      // ring slots of the calendar
@@ -106,6 +112,7 @@ struct TCtl {
   // ---- multi-GPU
   uint32_t send_n[MAX_GPUS];       // records stored into each peer's receive region in this launch
   uint32_t round, xticket;
+  uint32_t stepped, spad;          // the step kernel of this round did work (else the exchange kernel is a no-op, too)
   PeerMsg agg;                     // job-wide sums of the last round
   unsigned long long g_exec0, g_commit0;
 };

@@ -111,7 +111,7 @@ struct HostBE {
     blk_begin(b);
     size_t done = 0;
     for (uint32_t tile : work) {
-      if (phase == PH_EVAL) eval_tile<M>(v, mp, ep, b, tile);
+      if (phase == PH_EVAL) { if (c->full) eval_tile<M, true>(v, mp, ep, b, tile); else eval_tile<M, false>(v, mp, ep, b, tile); }
       else rebin_tile(v, ep, b, tile, v.scratch, rebin_all);
       if (++done % 3 == 0) { blk_flush(v, b); blk_begin(b); }   // (several "blocks" share the launch)
     }

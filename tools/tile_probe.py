@@ -5,6 +5,8 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from devastator_b200 import engine as E
+if os.environ.get("QB_LIB"):   # A/B against another build of the same ABI
+    E.LIB_PATH = os.path.join(ROOT, os.environ["QB_LIB"])
 
 A = int(os.environ.get("QB_A", 1 << 20)); K = 16; P = float(os.environ.get("QB_P", 0.1)); LAM = 100.0
 END = int(os.environ.get("QB_END", 1000)); REPS = int(os.environ.get("QB_REPS", 3))
