@@ -42,11 +42,19 @@ REF = os.environ.get("DEVA_REFERENCE_ROOT", "/root/reference")
 DEFINES = [
     "-DDEBUG=0", "-DNDEBUG=1", "-DDEVA_OPNEW_DEVA=1", "-DDEVA_DUMMY_EXEC=0", "-DDRAIN_TIMER=0",
     "-DTIMELINE=0", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1", "-DDEVA_THREADS_SPSC=1",
-    "-DDEVA_THREADS_ALLOC_OPNEW_ASYM=1", "-DDEVA_THREADS_SPSC_BITS=32",
+    "-DDEVA_THREADS_ALLOC_OPNEW_ASYM=1",
     "-DDEVA_THREADS_SPSC_PREFETCH=0", "-DDEVA_THREADS_SPSC_ORDER_DFS=1",
     "-DDEVA_THREADS_SIGNAL_REAP_MEMCPY=1", '-DDEVA_GIT_VERSION="ref"',
 ]
-CXXFLAGS = ["-std=c++14", "-O3", "-pthread", "-Wno-aligned-new", "-w"]
+# -O3 builds of the reference use LTO (brutal.py:62,82)
+CXXFLAGS = ["-std=c++14", "-O3", "-flto", "-pthread", "-Wno-aligned-new", "-w"]
+
+
+def spsc_bits(R):
+    """tsigbits as the reference's build tool derives it from the thread count (brutal.py:118-121):
+    64*8/threads, rounded down to one of 8 / 16 / 32."""
+    t = 64 * 8 / R
+    return (8, 16, 32)[sum(x < t for x in (8, 16))]
 RUNTIME_TUS = [
     "src/devastator/pdes.cxx", "src/devastator/gvt.cxx", "src/devastator/threads.cxx",
     "src/devastator/diagnostic.cxx", "src/devastator/datarow.cxx", "src/devastator/opnew.cxx",
@@ -73,7 +81,10 @@ PHOLD_T_CONFIGS = {
     "mid":    dict(A=100000,  K=16, P=0.10, LAMBDA=100, END=300,  sub=1, rootdiv=1),
     # BASELINE config 2 (1M LPs, 16 ev/LP, 10% remote); END is a run-time env knob (PHOLD_T_END)
     "cfg2":   dict(A=1048576, K=16, P=0.10, LAMBDA=100, END=1000, sub=1, rootdiv=1),
+    # BASELINE config 3 (8M LPs, 50% remote): the CPU baseline of the multi-GPU bench lines
+    "cfg3":   dict(A=8388608, K=16, P=0.50, LAMBDA=100, END=1000, sub=1, rootdiv=1),
 }
+BASELINE_TAGS = ("cfg2", "cfg3")   # built for the host core counts a GPU box may have, not for the small rank counts
 
 PHOLD_T_MAIN = r'''
 // ---- driver appended by oracle/build_ref.py (not reference text) --------------------------------
@@ -205,8 +216,8 @@ def build_runtime(R, force):
         obj = os.path.join(objdir, os.path.basename(tu).replace(".cxx", ".o"))
         objs.append(obj)
         if force or newer(obj, [src]):
-            jobs.append(["g++", *CXXFLAGS, *DEFINES, f"-DDEVA_THREAD_N={R}", f"-I{REF}/src",
-                         "-c", src, "-o", obj])
+            jobs.append(["g++", *CXXFLAGS, *DEFINES, f"-DDEVA_THREAD_N={R}", f"-DDEVA_THREADS_SPSC_BITS={spsc_bits(R)}",
+                         f"-I{REF}/src", "-c", src, "-o", obj])
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         list(ex.map(sh, jobs))
     return objs
@@ -215,8 +226,8 @@ def build_runtime(R, force):
 def link_app(R, objs, src, exe, extra=(), force=False):
     if not (force or newer(exe, [src] + objs)):
         return exe
-    sh(["g++", *CXXFLAGS, *DEFINES, f"-DDEVA_THREAD_N={R}", f"-I{REF}/src", f"-I{REF}/bench",
-        *extra, src, *objs, "-o", exe])
+    sh(["g++", *CXXFLAGS, *DEFINES, f"-DDEVA_THREAD_N={R}", f"-DDEVA_THREADS_SPSC_BITS={spsc_bits(R)}", f"-I{REF}/src",
+        f"-I{REF}/bench", *extra, src, *objs, "-o", exe])
     return exe
 
 
@@ -376,18 +387,20 @@ def main():
         if "phold_t" in only:
             gen = gen_phold_t()
             for tag in tags:
+                if tag == "cfg3" and R != 8:
+                    continue
                 jobs.append((gen, exe_name("phold_t", R, tag), tuple(phold_t_flags(PHOLD_T_CONFIGS[tag]))))
         with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
             built += list(ex.map(lambda j: link_app(R, objs, j[0], j[1], j[2], a.force), jobs))
     # the CPU-baseline binary (BASELINE config 2) for the host core counts a GPU box may have
-    if "phold_t" in only and "cfg2" in tags:
+    if "phold_t" in only:
         gen = gen_phold_t()
         for R in a.baseline_ranks:
-            if R in a.ranks:
-                continue
             objs = build_runtime(R, a.force)
-            built.append(link_app(R, objs, gen, exe_name("phold_t", R, "cfg2"),
-                                  tuple(phold_t_flags(PHOLD_T_CONFIGS["cfg2"])), a.force))
+            for tag in BASELINE_TAGS:
+                if tag in tags and not (R in a.ranks and tag == "cfg2"):
+                    built.append(link_app(R, objs, gen, exe_name("phold_t", R, tag),
+                                          tuple(phold_t_flags(PHOLD_T_CONFIGS[tag])), a.force))
     for b in built:
         print("built", os.path.relpath(b, os.path.dirname(HERE)))
     return 0

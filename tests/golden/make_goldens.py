@@ -88,7 +88,7 @@ def main():
         if per * R <= 1000 and de is None:
             np.save(os.path.join(HERE, f"phold_b_{tag}_state.npy"), st)
     for tag, cfg in PHOLD_T_CONFIGS.items():
-        if tag == "cfg2":
+        if tag in ("cfg2", "cfg3"):   # full size: see make_big_goldens.py
             continue
         for R in (2, 8):
             out, st = run_phold_t(tag, R)
