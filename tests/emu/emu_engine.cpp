@@ -499,4 +499,73 @@ uint32_t emu_pass_end(deva_b200_engine *e) {   // LPs woken for the next follow-
 uint64_t emu_upper_bound(deva_b200_engine *e, uint64_t gvt, uint64_t t_end) { return e->wp.upper_bound(gvt, t_end); }
 void emu_policy_update(deva_b200_engine *e, uint64_t wx, uint64_t wr) { e->wp.update(wx, wr); }
 
+// ---- tile engine, one engine per PROCESS (gloo test): the pieces of k_tile_step / k_tile_xchg with the
+// caller's transport between them.  Peer g's comm block is stood in for by a local block of the same
+// layout, so the step code stores cross-GPU records exactly as it does over NVLink; the caller ships
+// region [0, send_n[g]) to process g, which appends the records as k_tile_xchg does.
+uint32_t emu_tile_msg_bytes(void) { return (uint32_t)sizeof(PeerMsg); }
+int emu_tile_mp_setup(deva_b200_engine *e) {
+  if (!e->tile) return fail(DEVA_B200_ERR_STATE, "not a tile engine");
+  EmuTile *t = e->tile;
+  for (int g = 0; g < t->cfg.n_gpus; g++) {
+    if (g == t->cfg.gpu_rank) continue;
+    void *blk = nullptr;
+    if (t->be.alloc(&blk, t->comm_bytes)) return fail(DEVA_B200_ERR_CUDA, "out of memory");
+    t->map_peer(g, blk);
+  }
+  t->peers_ready();
+  return 0;
+}
+int emu_tile_mp_begin(deva_b200_engine *e, uint64_t t_end) {
+  EmuTile *t = e->tile;
+  if (t->has_rewind) return fail(DEVA_B200_ERR_STATE, "lingering rewind state");
+  if (!t->v.peer_cap) return fail(DEVA_B200_ERR_STATE, "emu_tile_mp_setup was not called");
+  t->v.ctl->stop_req = (uint32_t)t->stop_req.load();
+  t->v.ctl->t_end = t_end;
+  for (int i = 0; i < MAX_GPUS; i++) t->v.ctl->send_n[i] = 0;
+  return 0;
+}
+void emu_tile_mp_msg(deva_b200_engine *e, void *out) { make_peer_msg(e->tile->v, *(PeerMsg *)out); }
+// begin = 1: what k_tile_xchg(begin_mode) does; else the closing of a round.  Returns the phase.
+int emu_tile_mp_close(deva_b200_engine *e, const void *msgs, int G, int begin) {
+  EmuTile *t = e->tile;
+  Glob g;
+  fold_peer_msgs((const PeerMsg *)msgs, G, g);
+  if (begin) begin_drain(t->v, t->tp, t->v.ctl->t_end, g); else close_launch(t->v, t->tp, g);
+  t->v.ctl->round++;
+  return (int)t->v.ctl->phase;
+}
+int emu_tile_mp_step(deva_b200_engine *e) {
+  EmuTile *t = e->tile;
+  tile_model(e, [&](auto m) { t->be.template step_noclose<typename decltype(m)::type>(t->v, t->mp, t->tp); return 0; });
+  return 0;
+}
+uint32_t emu_tile_mp_send(deva_b200_engine *e, int g, void *out) {   // records this engine stored for engine g in this round
+  EmuTile *t = e->tile;
+  uint32_t n = t->v.ctl->send_n[g];
+  if (n > t->v.peer_cap) n = t->v.peer_cap;
+  if (out) memcpy(out, t->v.peer_buf[g], (size_t)n * sizeof(EvRec));
+  return n;
+}
+int emu_tile_mp_deliver(deva_b200_engine *e, const void *recs, uint32_t n) {
+  EmuTile *t = e->tile;
+  const Epoch ep = load_epoch(t->v.ctl);
+  uint32_t err = 0;
+  for (uint32_t i = 0; i < n; i++) append_local(t->v, ep, ((const EvRec *)recs)[i], nullptr, &err);
+  t->v.ctl->err |= err;
+  return 0;
+}
+int emu_tile_mp_finish(deva_b200_engine *e, uint64_t *local_min) {
+  EmuTile *t = e->tile;
+  t->hc = *t->v.ctl;
+  if (t->hc.err) return t->check_err();
+  t->be.k_settle(t->v);
+  if (t->hc.antis_pending > 0) t->be.k_net_pending(t->v);
+  uint64_t m = ~0ull;
+  if (t->hc.gvt != ~0ull) t->be.k_min_pending(t->v, &m);
+  *local_min = m;
+  t->hc = *t->v.ctl;
+  return t->hc.err ? t->check_err() : 0;
+}
+
 }  // extern "C"

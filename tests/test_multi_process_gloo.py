@@ -1,8 +1,14 @@
-"""World-size-2 test of the multi-GPU protocol with REAL processes and a real transport (gloo):
-each process owns one block of LPs in an emulated engine (tests/emu), and the per-window sequence of
-engine.cu's run_window() - execute pass, exchange the per-peer counts, exchange the staged records,
-deliver them, min-allreduce the GVT candidate, sum-allreduce the window statistics, lockstep window
-policy - is driven from Python with torch.distributed in place of NCCL.  Result must equal the oracle."""
+"""World-size-2 tests of the multi-GPU protocols with REAL processes and a real transport (gloo):
+each process owns one block of LPs in an emulated engine (tests/emu).
+
+tile engine (default): the round sequence of k_tile_step + k_tile_xchg - step, ship the records stored
+for the peer, append them, exchange the PeerMsg figures, run the epoch state machine on every process
+with the same sums - with gloo in place of the NVLink stores and the device-side mailboxes.
+
+lp engine: the per-window sequence of engine.cu's run_window() - execute pass, exchange the per-peer
+counts, exchange the staged records, deliver them, min-allreduce the GVT candidate, sum-allreduce the
+window statistics, lockstep window policy - with torch.distributed in place of NCCL.
+Results must equal the oracle."""
 import ctypes as C
 import os
 import socket
@@ -83,6 +89,7 @@ def _worker(rank, world, port, cfg, ret):
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    os.environ["DEVA_B200_ENGINE"] = "lp"
     from devastator_b200 import engine as E
     api = E.Api(C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libdeva_b200_emu.so")))
     _bind(api)
@@ -124,8 +131,112 @@ def _worker(rank, world, port, cfg, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cfg", [dict(A=1000, K=16, P=0.5, LAM=100.0, END=300, window=20),
-                                 dict(A=1000, K=16, P=0.1, LAM=100.0, END=300, window=0)], ids=["p50-w20", "p10-adaptive"])
+def _exchange_records(api, eng, rank, world, count_fn, copy_fn, deliver_fn):
+    """counts all-gather, then pairwise send/recv of the 32-byte records, then deliver"""
+    counts = torch.tensor([0 if g == rank else count_fn(g) for g in range(world)], dtype=torch.int64)
+    allc = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allc, counts)
+    for peer in range(world):
+        if peer == rank:
+            continue
+        ns, nr = int(counts[peer]), int(allc[peer][rank])
+        sbuf = torch.zeros(max(ns, 1) * 32, dtype=torch.uint8)
+        if ns:
+            copy_fn(peer, sbuf.data_ptr())
+        rbuf = torch.zeros(max(nr, 1) * 32, dtype=torch.uint8)
+        if rank < peer:
+            if ns: dist.send(sbuf[:ns * 32], peer)
+            if nr: dist.recv(rbuf[:nr * 32], peer)
+        else:
+            if nr: dist.recv(rbuf[:nr * 32], peer)
+            if ns: dist.send(sbuf[:ns * 32], peer)
+        if nr:
+            deliver_fn(rbuf.data_ptr(), nr)
+
+
+def _tile_worker(rank, world, port, cfg, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["DEVA_B200_ENGINE"] = "tile"
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from devastator_b200 import engine as E
+    api = E.Api(C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libdeva_b200_emu.so")))
+    L, P = api.lib, C.c_void_p
+    L.emu_tile_msg_bytes.restype = C.c_uint32
+    L.emu_tile_mp_setup.argtypes = [P]
+    L.emu_tile_mp_begin.argtypes = [P, C.c_uint64]
+    L.emu_tile_mp_msg.argtypes = [P, P]; L.emu_tile_mp_msg.restype = None
+    L.emu_tile_mp_close.argtypes = [P, P, C.c_int, C.c_int]
+    L.emu_tile_mp_step.argtypes = [P]
+    L.emu_tile_mp_send.argtypes = [P, C.c_int, P]; L.emu_tile_mp_send.restype = C.c_uint32
+    L.emu_tile_mp_deliver.argtypes = [P, P, C.c_uint32]
+    L.emu_tile_mp_finish.argtypes = [P, C.POINTER(C.c_uint64)]
+    A = cfg["A"]
+    per = (A + world - 1) // world
+    cnt = min(per, A - rank * per)
+    eng = E.Engine(E.MODEL_PHOLD_TEST, A, lp_begin=rank * per, lp_count=cnt, n_gpus=world, gpu_rank=rank, window=cfg["window"],
+                   p_remote=cfg["P"], lam=cfg["LAM"], end_time=cfg["END"], api=api)
+    api.check(L.emu_tile_mp_setup(eng.h))
+    eng.seed_phold(cfg["K"], 1, 1)
+    nmsg = L.emu_tile_msg_bytes()
+
+    def figures():   # every process's PeerMsg, as k_tile_xchg's mailboxes carry them
+        mine = torch.zeros(nmsg, dtype=torch.uint8)
+        L.emu_tile_mp_msg(eng.h, mine.data_ptr())
+        allm = [torch.zeros(nmsg, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        return torch.cat(allm).contiguous()
+
+    PH_DONE = 3
+    for t_end in cfg.get("ends", [T_INF]):
+        api.check(L.emu_tile_mp_begin(eng.h, t_end))
+        f = figures()   # (keep the tensor alive across the call)
+        phase = L.emu_tile_mp_close(eng.h, f.data_ptr(), world, 1)
+        rounds = 0
+        while phase != PH_DONE:
+            L.emu_tile_mp_step(eng.h)
+            _exchange_records(api, eng, rank, world, lambda g: L.emu_tile_mp_send(eng.h, g, None),
+                              lambda g, ptr: L.emu_tile_mp_send(eng.h, g, ptr), lambda ptr, n: L.emu_tile_mp_deliver(eng.h, ptr, n))
+            f = figures()
+            phase = L.emu_tile_mp_close(eng.h, f.data_ptr(), world, 0)
+            rounds += 1
+            assert rounds < 1000000
+        m = C.c_uint64()
+        api.check(L.emu_tile_mp_finish(eng.h, C.byref(m)))
+        gvt = _u64_min(m.value)
+    st = torch.from_numpy(eng.get_state().astype(np.int64))
+    pad = torch.zeros((per, 3), dtype=torch.int64); pad[:cnt] = st
+    gathered = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(gathered, pad)
+    s = eng.stats()
+    tot = _sum(s["committed_n"], s["remote_sent_n"])
+    if rank == 0:
+        ret["state"] = torch.cat(gathered)[:A].numpy().astype(np.uint64)
+        ret["commits"], ret["crossed"], ret["gvt"], ret["windows"] = tot[0], tot[1], gvt, rounds
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+CFGS = [dict(A=1000, K=16, P=0.5, LAM=100.0, END=300, window=20), dict(A=1000, K=16, P=0.1, LAM=100.0, END=300, window=0)]
+
+
+@pytest.mark.parametrize("cfg", CFGS + [dict(A=777, K=8, P=1.0, LAM=20.0, END=200, window=0, ends=[60, 130, T_INF])],
+                         ids=["p50-w20", "p10-adaptive", "allremote-segments"])
+def test_two_processes_gloo_tile_engine_equal_oracle(emu_api, cfg):
+    import oracle_lib as O
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_tile_worker, args=(2, port, cfg, ret), nprocs=2, join=True)
+    o, ost = O.run(cfg["A"], cfg["K"], cfg["P"], cfg["LAM"], cfg["END"])
+    np.testing.assert_array_equal(ret["state"], ost)
+    assert ret["commits"] == o["commits"] and ret["gvt"] == o["gvt"]
+    assert ret["crossed"] > 0
+
+
+@pytest.mark.parametrize("cfg", CFGS, ids=["p50-w20", "p10-adaptive"])
 def test_two_processes_gloo_equal_oracle(emu_api, cfg):
     import oracle_lib as O
     with socket.socket() as s:
