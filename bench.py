@@ -1,25 +1,34 @@
 #!/usr/bin/env python3
-"""bench.py - committed events/sec of the PDES hot path on PHOLD-T (BASELINE.json configs[1]).
+"""bench.py - committed events/sec of the PDES hot path on PHOLD-T (BASELINE.json configs[1] and configs[2]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]                 # our arm
-    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the reference on host cores
-    torchrun ... bench.py --gpus N ...                                   # N > 1: one rank per GPU
+    python bench.py [--gpus N] [--steps K] [--warmup W]                    # our arm
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # the reference on host cores
+    torchrun ... bench.py --gpus N ...                                     # N > 1: one rank per GPU
 
-Workload (config.workload): PHOLD-T = the reference's test/phold.cxx model (xorshift128+ state,
-check hash, exponential delay with glibc log, uniform remote destination) with its documented
-`subtime() = ray` tiebreak (test/phold.cxx:74-76), 1 048 576 LPs per GPU, 16 root events per LP,
-10 % remote fraction, lambda = 100, end_time = 1000 (about 1.7e8 committed events per GPU).
-Weak scaling: LPs are block-partitioned, 1M per GPU; destinations are uniform over ALL LPs, so a
-fraction p*(N-1)/N of the events crosses GPUs through the per-window NCCL exchange.
+Workloads (config.workload names the one a line is quoted on).  PHOLD-T = the reference's
+test/phold.cxx model (xorshift128+ state, check hash, exponential delay through glibc's log, uniform
+remote destination) with its documented `subtime() = ray` tiebreak (test/phold.cxx:74-76), 16 root
+events per LP, lambda = 100, end_time = 1000:
+  N = 1 : BASELINE config 2 - 1 048 576 LPs, 10 % remote                      (1.82e8 commits per step)
+  N > 1 : BASELINE config 3 - 8 388 608 LPs block-partitioned over the N GPUs, 50 % remote
+          (1.46e9 commits per step; a fraction 0.5 (N-1)/N of all events crosses GPUs over NVLink)
+Both are also run at the other GPU counts and reported inside the same JSON line under "also":
+config 3 on one GPU (the strong-scaling base of the N > 1 lines) and config 2's geometry weak-scaled
+(1 M LPs per GPU, 10 % remote: the series round 1 reported).
 
 One "step" = one complete optimistic drain of a freshly seeded instance: every event with
-time < end_time executed, rolled back where needed, committed.
-  value : whole-job committed events/sec, instance seeded on the device (inputs resident in HBM),
-          timed with CUDA events on the engine's stream over exactly K steps, max over ranks.
-  e2e   : same metric through the host-buffer API (pinned host state words + root columns copied
-          H2D, drain, state words copied D2H) with the copies inside the timed region.
-  roofline : k_pass (the execute kernel): 120 algorithmic bytes per committed event
-          x commits / summed k_pass CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+time < end_time executed, rolled back where needed, committed.  Seeding (building the root events,
+the counterpart of the reference's root_event() calls before drain()) is outside the timed region of
+`value` - the reference arm times its drain() calls the same way - and inside the one of `e2e`.
+  value : whole-job committed events/sec, inputs resident in HBM (instance seeded on the device), CUDA
+          events on the engine's stream around each of the K drains, summed, max over ranks.
+  e2e   : same metric through the host-buffer API (pinned host state words + root columns copied H2D and
+          inserted, drain, state words copied D2H), everything inside the timed region, all K steps.
+  roofline : the step kernel k_tile_step (all its launches): B_alg algorithmic bytes per committed event
+          (120 + 48 f, f = cross-GPU fraction) x commits / summed CUDA-event time of the
+          launches, against MEASURED_PEAKS.json hbm_gbs; `traffic` from the committed ncu capture.
+  parity : commits, XOR checksum, additive state hash and final GVT gathered over the ranks and ASSERTED
+          against tests/golden/bench_goldens.json (reference binary / pinned oracle) - a mismatch exits 1.
   cpu_baseline : the reference itself (oracle/_ref, built from /root/reference) on the host cores.
 """
 import argparse
@@ -34,20 +43,56 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LP_PER_GPU = int(os.environ.get("DEVA_BENCH_LP_PER_GPU", 1 << 20))
 K_ROOTS = 16
-P_REMOTE = float(os.environ.get("DEVA_BENCH_P_REMOTE", 0.10))
 LAMBDA = 100.0
 END_TIME = int(os.environ.get("DEVA_BENCH_END", 1000))
 WINDOW = int(os.environ.get("DEVA_BENCH_WINDOW", 0))      # 0 = engine's adaptive policy
-B_ALG = 120.0   # algorithmic bytes per committed event: 2*E + 2*S + V, E = S = V = 24 B
+CFG3_LPS = int(os.environ.get("DEVA_BENCH_CFG3_LPS", 1 << 23))
+CFG2_LPS = int(os.environ.get("DEVA_BENCH_CFG2_LPS", 1 << 20))
+
+
+def b_alg(p_remote, n):
+    """algorithmic bytes per committed event: 2*E + 2*S + V = 120 B (E = S = V = 24 B), plus 48 B for
+    an event that crosses GPUs (written into the peer's receive region, read back, appended): SURVEY 8d"""
+    return 120.0 + 48.0 * p_remote * (n - 1) / n
+
+
+def workloads(n):
+    """(tag, total LPs, remote fraction, scaling) - the first one is the line's headline"""
+    cfg2 = ("cfg2", CFG2_LPS * n, 0.10, "weak")
+    cfg3 = ("cfg3", CFG3_LPS, 0.50, "strong")
+    forced = os.environ.get("DEVA_BENCH_WORKLOAD")
+    if forced:
+        return [w for w in (cfg2, cfg3) if w[0] == forced]
+    return [cfg2, cfg3] if n == 1 else [cfg3, cfg2]
+
+
+def workload_config(tag, lp_total, p, n):
+    name = {"cfg2": "BASELINE config 2 geometry", "cfg3": "BASELINE config 3"}[tag]
+    return {"workload": "%s: PHOLD-T (test/phold.cxx model, subtime()=ray), %d LPs block-partitioned over %d GPU(s) (%d per GPU), "
+                        "%d roots/LP, p_remote=%.2f, lambda=%g, end_time=%d" % (name, lp_total, n, lp_total // n, K_ROOTS, p, LAMBDA, END_TIME),
+            "tag": tag, "lps_total": lp_total, "events_live": lp_total * K_ROOTS, "partition": "block, %d LPs per GPU" % (lp_total // n),
+            "p_remote": p, "cross_gpu_fraction": p * (n - 1) / n, "window": "adaptive" if WINDOW == 0 else WINDOW,
+            "l2": "inputs larger than L2: the calendar lists and LP states touched per epoch (>= 250 MB per GPU) exceed the 126 MB L2; no flush"}
 
 
 def hbm_peak():
     try:
-        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def goldens():
+    try:
+        vs = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_goldens.json")))["vectors"]
+    except Exception:
+        return {}
+    out = {}
+    for v in vs:
+        if v["end_time"] == END_TIME and v["k"] == K_ROOTS:
+            out.setdefault((v["lp_n"], v["p_remote"]), v)   # (the reference-binary vector comes first)
+    return out
 
 
 class ClockSampler:
@@ -98,28 +143,34 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------------
-def ref_binary(threads=None):
-    """oracle/_ref PHOLD-T binary (BASELINE config 2 geometry) for the largest power-of-two rank
-    count <= host cores (world size is a compile-time constant in the reference)."""
+# ---- the reference on the host cores -------------------------------------------------------------
+def ref_binary(tag):
+    """oracle/_ref PHOLD-T binary of the workload for the largest power-of-two rank count <= host cores
+    (world size is a compile-time constant in the reference)."""
     ncpu = os.cpu_count() or 1
-    want = threads or int(os.environ.get("DEVA_BENCH_REF_RANKS", 0)) or ncpu
+    want = int(os.environ.get("DEVA_BENCH_REF_RANKS", 0)) or ncpu
     for R in (64, 32, 16, 8, 4, 2):
-        p = os.path.join(ROOT, "oracle", "_ref", f"ref_phold_t_cfg2_R{R}")
+        p = os.path.join(ROOT, "oracle", "_ref", f"ref_phold_t_{tag}_R{R}")
         if R <= want and os.path.exists(p):
             return p, R
     return None, 0
 
 
-REF_LEAD_IN = 200   # untimed lead-in [0, 200): the start-up transient (16 roots/LP inside [0,16)) is not steady state
+# untimed lead-in [0, lead_in): the start-up transient (16 roots per LP inside [0, 16)) is not steady state
+REF_LEAD_IN = {"cfg2": 200, "cfg3": 100}
+REF_LPS = {"cfg2": 1 << 20, "cfg3": 1 << 23}      # what the binaries were compiled for (oracle/build_ref.py)
+REF_P = {"cfg2": 0.10, "cfg3": 0.50}
 
 
-def run_reference_segments(n_seg, dt, timeout=900):
-    exe, R = ref_binary()
+def run_reference_segments(tag, n_seg, dt, timeout=1500):
+    exe, R = ref_binary(tag)
     if not exe:
         return None
-    env = dict(os.environ, pdes_heartbeat="0", PHOLD_T_SEGMENTS=f"{n_seg}:{dt}:{REF_LEAD_IN}", PHOLD_T_END=str(10**9))
-    out = subprocess.run([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    env = dict(os.environ, pdes_heartbeat="0", PHOLD_T_SEGMENTS=f"{n_seg}:{dt}:{REF_LEAD_IN[tag]}", PHOLD_T_END=str(10**9))
+    try:
+        out = subprocess.run([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return None
     segs = []
     for line in out.stdout.splitlines():
         try:
@@ -128,50 +179,82 @@ def run_reference_segments(n_seg, dt, timeout=900):
             continue
         if "segment" in j:
             segs.append(j)
-    return dict(ranks=R, segments=segs, rc=out.returncode)
+    return dict(ranks=R, segments=segs, rc=out.returncode, tag=tag)
+
+
+def reference_sample(tag, n_timed, n_warm, events_per_seg):
+    """n_warm + n_timed drain(t_end) slices of the reference binary of workload `tag`; falls back to the
+    config-2 binary when the config-3 one cannot run on this host (memory), and says so."""
+    for t in ([tag] if tag == "cfg2" else [tag, "cfg2"]):
+        dt = max(2, int(round(events_per_seg / (REF_LPS[t] * K_ROOTS / LAMBDA))))
+        res = run_reference_segments(t, n_warm + n_timed, dt)
+        if res and len(res["segments"]) >= n_warm + n_timed:
+            timed = res["segments"][n_warm:]
+            commits = sum(s["commits"] for s in timed)
+            secs = sum(s["drain_secs"] for s in timed)
+            res.update(dt=dt, commits=commits, secs=secs, value=commits / secs)
+            return res
+    return None
+
+
+def sample_text(res, n_timed, n_warm):
+    t = res["tag"]
+    return (f"reference binary oracle/_ref/ref_phold_t_{t}_R{res['ranks']} ({res['ranks']} rank threads of {os.cpu_count()} host CPUs; "
+            f"{REF_LPS[t]} LPs, p_remote={REF_P[t]}): {n_timed} timed drain(t_end) slices of {res['dt']} sim-time units "
+            f"({res['commits']} commits in {res['secs']:.1f} s) after an untimed lead-in [0,{REF_LEAD_IN[t]}) and {n_warm} warm-up slice(s)")
 
 
 def reference_arm(args):
     """The reference's own CPU implementation of the path (oracle/_ref, UNMODIFIED runtime built from
-    /root/reference), all host threads, steps = successive drain(t_end) slices of one simulation."""
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
+    /root/reference), all host threads, steps = successive drain(t_end) slices of one simulation of the
+    workload our arm's headline is quoted on (config 2 at N = 1, config 3 at N > 1)."""
+    if int(os.environ.get("RANK", 0)) != 0:
         return 0
     K, W = args.steps, args.warmup
-    per_step_s = min(15.0, max(1.0, 120.0 / (K + W)))
-    dt = max(2, int(round(per_step_s * 1.0e6 / (LP_PER_GPU * K_ROOTS / LAMBDA))))
-    res = run_reference_segments(K + W, dt)
-    if not res or len(res["segments"]) < K + W:
+    tag, lp_total, p, scaling = workloads(args.gpus)[0]
+    # about 1e7 committed events per slice (1-3 s of host time): the whole run ends within minutes
+    res = reference_sample(tag, K, W, float(os.environ.get("DEVA_BENCH_REF_EVENTS_PER_STEP", 1.0e7)))
+    if not res:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binary missing or failed (run __graft_entry__.build() where /root/reference exists)"}))
         return 0
-    timed = res["segments"][W:]
-    commits = sum(s["commits"] for s in timed)
-    secs = sum(s["drain_secs"] for s in timed)
-    val = commits / secs
-    sample = (f"{K} timed drain(t_end) slices of {dt} sim-time units after an untimed lead-in [0,{REF_LEAD_IN}) and {W} warm-up slices, 1M-LP PHOLD-T "
-              f"(single-GPU geometry; also used for N>1, where the larger LP count would only slow the CPU run)")
+    t = res["tag"]
+    cfg = workload_config(t, REF_LPS[t], REF_P[t], args.gpus)
+    cfg["workload"] = (f"{'BASELINE config 3' if t == 'cfg3' else 'BASELINE config 2 geometry'}: PHOLD-T, {REF_LPS[t]} LPs on the host cores "
+                       f"({res['ranks']} rank threads), {K_ROOTS} roots/LP, p_remote={REF_P[t]:.2f}, lambda={LAMBDA:g}, drain(t_end) slices")
+    cfg["partition"] = "block over %d host rank threads" % res["ranks"]
+    cfg["cross_gpu_fraction"] = 0.0
+    if t != tag:
+        cfg["note"] = f"the {tag} binary could not run on this host (memory / time-out): the config-2 binary was timed instead"
     line = {
-        "impl": "reference", "metric": "committed events/sec (PHOLD-T)", "value": val, "unit": "events/s",
-        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * secs / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": val, "unit": "events/s", "cores": res["ranks"], "kind": "reference", "sample": sample},
-        "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "committed events/sec (PHOLD-T)", "value": res["value"], "unit": "events/s",
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * res["secs"] / K, "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": res["value"], "unit": "events/s", "cores": res["ranks"], "kind": "reference", "sample": sample_text(res, K, W)},
+        "e2e": {"value": res["value"], "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
 
 
-def workload_config(n):
-    return {"workload": "PHOLD-T (test/phold.cxx model, subtime()=ray): %d LPs/GPU x %d GPU, %d roots/LP, p_remote=%.2f, "
-                        "lambda=%g, end_time=%d" % (LP_PER_GPU, n, K_ROOTS, P_REMOTE, LAMBDA, END_TIME),
-            "lps_total": LP_PER_GPU * n, "events_live": LP_PER_GPU * n * K_ROOTS, "partition": "block, %d LPs per GPU" % LP_PER_GPU,
-            "cross_gpu_fraction": P_REMOTE * (n - 1) / n, "window": "adaptive" if WINDOW == 0 else WINDOW,
-            "l2": "working set per window (pending 2 GiB + undo log 3 GiB per GPU) exceeds the 126 MB L2; no flush needed"}
+def cpu_baseline(tag):
+    """Bounded sample (about 10-30 s of drain time) of the same workload on the reference itself, host cores."""
+    res = reference_sample(tag, 2, 1, float(os.environ.get("DEVA_BENCH_CPU_EVENTS_PER_STEP", 3.0e7)))
+    if not res:
+        return {"value": None, "unit": "events/s", "cores": 0, "kind": "reference", "sample": "unavailable: oracle/_ref binary missing"}
+    return {"value": res["value"], "unit": "events/s", "cores": res["ranks"], "kind": "reference", "sample": sample_text(res, 2, 1)}
 
 
-# ------------------------------------------------------------------------------------------------
+def measured_traffic():
+    """dram bytes per launch of the step kernel from the committed ncu --set full capture of this very
+    configuration (profiles/k_tile_step_traffic.json, written by tools/ncu_traffic.py), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "k_tile_step_traffic.json")))
+    except Exception:
+        return None
+
+
+# ---- our arm -------------------------------------------------------------------------------------
 def ours(args):
     import numpy as np
     import torch
@@ -185,23 +268,25 @@ def ours(args):
     if world != N:
         raise SystemExit(f"--gpus {N} but WORLD_SIZE={world}: launch N>1 with torchrun, one rank per GPU")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if N > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lp_n = LP_PER_GPU * N
-    eng = E.Engine(E.MODEL_PHOLD_TEST, lp_n, lp_begin=rank * LP_PER_GPU, lp_count=LP_PER_GPU, device=local, n_gpus=N,
-                   gpu_rank=rank, window=WINDOW, p_remote=P_REMOTE, lam=LAMBDA, end_time=END_TIME, user_subtime=1)
-    if N > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(E.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        eng.comm_init(bytes(uid.cpu().numpy().tobytes()))
-    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
+    gold = goldens()
+    MASK = (1 << 64) - 1
 
     def sync_all():
         torch.cuda.synchronize()
         if N > 1:
             dist.barrier()
+
+    def gather_u64(xs):
+        """every rank's list of u64 values -> [rank][i] on every rank"""
+        if N == 1:
+            return [list(xs)]
+        t = torch.tensor([np.uint64(x).astype(np.int64) for x in xs], dtype=torch.int64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(N)]
+        dist.all_gather(out, t)
+        return [[int(v) & MASK for v in o.tolist()] for o in out]
 
     def allmax(x):
         if N == 1:
@@ -210,136 +295,165 @@ def ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def allsum(x):
-        if N == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.int64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return int(t.item())
+    def run(tag, lp_total, p, scaling, headline):
+        per = (lp_total + N - 1) // N
+        cnt = min(per, lp_total - rank * per)
+        eng = E.Engine(E.MODEL_PHOLD_TEST, lp_total, lp_begin=rank * per, lp_count=cnt, device=local, n_gpus=N,
+                       gpu_rank=rank, window=WINDOW, p_remote=p, lam=LAMBDA, end_time=END_TIME, user_subtime=1)
+        if N > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(E.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            eng.comm_init(bytes(uid.cpu().numpy().tobytes()))
+        stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+        K, W = args.steps, args.warmup
 
-    def step_device():
-        eng.seed_phold(K_ROOTS, 1, 1)
-        return eng.drain()
+        # ---- value: inputs resident in HBM, drains timed with CUDA events on the engine's stream
+        for _ in range(W):
+            eng.seed_phold(K_ROOTS, 1, 1)
+            eng.drain()
+        sync_all()
+        sampler = ClockSampler(local) if (headline and rank == 0) else None
+        if sampler:
+            sampler.start()
+        s0 = eng.stats()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        seed_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        t_wall0 = time.perf_counter()
+        gvt = None
+        for k in range(K):
+            seed_evs[k][0].record(stream)
+            eng.seed_phold(K_ROOTS, 1, 1)
+            seed_evs[k][1].record(stream)
+            if N > 1:
+                sync_all()          # every rank's step starts together (the drain itself synchronises the ranks on the device)
+            evs[k][0].record(stream)
+            gvt = eng.drain()
+            evs[k][1].record(stream)
+        sync_all()
+        t_wall = time.perf_counter() - t_wall0
+        s1 = eng.stats()
+        clocks = sampler.stop() if sampler else None
+        ms = allmax(sum(a.elapsed_time(b) for a, b in evs))
+        seed_ms = allmax(sum(a.elapsed_time(b) for a, b in seed_evs))
+        d = eng.digest()
+        commits_local = s1["committed_n"] - s0["committed_n"]
+        executed_local = s1["executed_n"] - s0["executed_n"]
+        kernel_ms = s1["exec_kernel_ms"] - s0["exec_kernel_ms"]
+        passes = s1["passes"] - s0["passes"]
+        launches = s1["kernel_launches"] - s0["kernel_launches"]
+        g = gather_u64([commits_local, executed_local, d["checksum"], d["state_hash"], gvt, d["pending"], s1["rolled_back_n"] - s0["rolled_back_n"],
+                        s1["remote_sent_n"] - s0["remote_sent_n"]])
+        commits = sum(r[0] for r in g)
+        executed = sum(r[1] for r in g)
+        checksum = 0
+        for r in g:
+            checksum ^= r[2]
+        state_hash = sum(r[3] for r in g) & MASK
+        value = commits / (ms * 1e-3)
+        # ---- parity against the goldens of the benchmarked configuration
+        gv = gold.get((lp_total, p))
+        if gv is None:
+            verdict = "none (no golden for this size)"
+        else:
+            ok = (commits == K * gv["commits"] and checksum == gv["checksum"] and state_hash == gv["state_hash"] and
+                  all(r[4] == gv["gvt"] for r in g) and all(r[5] == 0 for r in g) and s1["deterministic"] == gv["deterministic"])
+            verdict = "match" if ok else "MISMATCH"
+        parity = {"golden": verdict, "golden_source": gv["source"] if gv else None, "commits_per_step": commits // K,
+                  "checksum": checksum, "state_hash": state_hash, "final_gvt": gvt, "executed_per_step": executed // K,
+                  "efficiency": commits / executed if executed else None, "rolled_back_per_step": sum(r[6] for r in g) // K,
+                  "crossed_gpus_per_step": sum(r[7] for r in g) // K}
 
-    # ---- value: inputs resident in HBM ----------------------------------------------------------
-    for _ in range(args.warmup):
-        step_device()
-    sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    s0 = eng.stats()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        gvt = step_device()
-    ev1.record(stream)
-    sync_all()
-    t_wall = time.perf_counter() - t_wall0
-    s1 = eng.stats()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = allmax(ev0.elapsed_time(ev1))
-    commits_local = s1["committed_n"] - s0["committed_n"]
-    commits = allsum(commits_local)
-    value = commits / (ms * 1e-3)
-    kernel_ms = s1["exec_kernel_ms"] - s0["exec_kernel_ms"]
-    passes = s1["passes"] - s0["passes"]
-    launches = s1["kernel_launches"] - s0["kernel_launches"]
-    executed = s1["executed_n"] - s0["executed_n"]
-    digest = eng.digest()
+        out = {"tag": tag, "value": value, "ms_per_step": ms / K, "seed_ms_per_step": seed_ms / K, "scaling": scaling,
+               "config": workload_config(tag, lp_total, p, N), "parity": parity, "gpu_launches": int(launches),
+               "wall_ms_per_step": 1e3 * t_wall / K, "launches_per_step": passes / K, "window_last": s1["window_last"]}
+        peak, peak_kind = hbm_peak()
+        B = b_alg(p, N)
+        achieved = B * commits_local / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                           "traffic": None, "kernel": "k_tile_step<PholdTest> (an epoch's full launch + its follow-up launches)",
+                           "bytes_per_event": B, "launches": int(passes), "avg_launch_ms": kernel_ms / passes if passes else None,
+                           "kernel_share_of_step": kernel_ms / ms if ms else None, "peak_kind": peak_kind}
+        if clocks is not None:
+            out["clocks"] = clocks
 
-    # ---- e2e: host buffers, copies inside the timed region --------------------------------------
-    st_host = torch.from_numpy(E.phold_initial_state_np(E.MODEL_PHOLD_TEST, rank * LP_PER_GPU, LP_PER_GPU)).pin_memory()
-    cols = [torch.from_numpy(np.ascontiguousarray(c)).pin_memory()
-            for c in E.phold_roots(E.MODEL_PHOLD_TEST, lp_n, K_ROOTS, rank * LP_PER_GPU, LP_PER_GPU)]
-    st_out = torch.empty_like(st_host).pin_memory()
-    h2d = st_host.numel() * 8 + sum(c.numel() * c.element_size() for c in cols)
-    d2h = st_out.numel() * 8
+        # ---- e2e: host buffers, copies inside the timed region, all K steps
+        if headline or args.e2e_all:
+            first = rank * per
+            st_host = torch.from_numpy(E.phold_initial_state_np(E.MODEL_PHOLD_TEST, first, cnt)).pin_memory()
+            cols = [torch.from_numpy(np.ascontiguousarray(c)).pin_memory() for c in E.phold_roots(E.MODEL_PHOLD_TEST, lp_total, K_ROOTS, first, cnt)]
+            st_out = torch.empty_like(st_host).pin_memory()
+            h2d = st_host.numel() * 8 + sum(c.numel() * c.element_size() for c in cols)
+            d2h = st_out.numel() * 8
+            st_np, st_out_np, cols_np = st_host.numpy(), st_out.numpy(), [c.numpy() for c in cols]
 
-    st_np, st_out_np, cols_np = st_host.numpy(), st_out.numpy(), [c.numpy() for c in cols]
-    dbg = os.environ.get("DEVA_BENCH_DEBUG")
+            def step_host():
+                eng.reset()
+                eng.set_state(st_np)
+                eng.root_events(*cols_np)
+                eng.drain()
+                eng.get_state(out=st_out_np)
 
-    def step_host():
-        t = [time.perf_counter()]
-        eng.reset(); t.append(time.perf_counter())
-        eng.set_state(st_np); t.append(time.perf_counter())
-        eng.root_events(*cols_np); t.append(time.perf_counter())
-        g = eng.drain(); t.append(time.perf_counter())
-        eng.get_state(out=st_out_np); t.append(time.perf_counter())
-        if dbg and rank == 0:
-            sys.stderr.write("e2e step ms reset/set_state/roots/drain/get_state: %s\n" % [round((b - a) * 1e3, 2) for a, b in zip(t, t[1:])])
-        return g, eng.stats()
+            step_host()
+            sync_all()
+            se0 = eng.stats()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                step_host()
+            sync_all()
+            e2e_s = allmax(time.perf_counter() - t0)
+            se1 = eng.stats()
+            ge = gather_u64([se1["committed_n"] - se0["committed_n"], int(np.bitwise_xor.reduce(st_out_np[:, 2]))])
+            e2e_commits = sum(r[0] for r in ge)
+            chk = 0
+            for r in ge:
+                chk ^= r[1]
+            # the host path and the device-seeded path must end in the same state (and in the golden's)
+            if chk != checksum or e2e_commits != commits:
+                parity["golden"] = "MISMATCH"
+                parity["e2e_path"] = "host-buffer path and device-seeded path disagree"
+            out["e2e"] = {"value": e2e_commits / e2e_s, "unit": "events/s", "h2d_bytes_per_step": h2d * N if N > 1 else h2d,
+                          "d2h_bytes_per_step": d2h * N if N > 1 else d2h, "steps": K, "bytes_are": "summed over the ranks"}
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        if N > 1:
+            dist.barrier()
+        return out
 
-    e2e_steps = max(1, min(args.steps, 3))
-    step_host()
-    sync_all()
-    se0 = eng.stats()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
-    sync_all()
-    e2e_s = allmax(time.perf_counter() - t0)
-    se1 = eng.stats()
-    e2e_commits = allsum(se1["committed_n"] - se0["committed_n"])
-    e2e_val = e2e_commits / e2e_s
-    # the host path and the device-seeded path must end in the same state
-    chk_host = int(np.bitwise_xor.reduce(st_out.numpy()[:, 2]))
-    assert chk_host == digest["checksum"], "host-buffer path and device-seeded path disagree"
-
-    peak, peak_kind = hbm_peak()
-    achieved = B_ALG * commits_local / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    results = []
+    wl = workloads(N)
+    for i, (tag, lp_total, p, scaling) in enumerate(wl):
+        results.append(run(tag, lp_total, p, scaling, headline=(i == 0)))
+    head = results[0]
     line = {
-        "metric": "committed events/sec (PHOLD-T)", "value": value, "unit": "events/s", "n_gpus": N,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
-        "config": workload_config(N),
-        "e2e": {"value": e2e_val, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": measured_traffic(),
-                     "kernel": "k_pass<PholdTest>", "bytes_per_event": B_ALG, "launches": int(passes),
-                     "avg_launch_ms": kernel_ms / passes if passes else None, "kernel_share_of_step": kernel_ms / ms,
-                     "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback"},
-        "clocks": clocks,
-        "parity": {"commits_per_step": commits // args.steps, "executed_per_step": executed // args.steps,
-                   "efficiency": commits_local / executed if executed else None, "final_gvt": gvt,
-                   "checksum_rank0": digest["checksum"], "wall_ms_per_step": 1e3 * t_wall / args.steps,
-                   "windows_per_step": passes / args.steps, "window_last": s1["window_last"]},
+        "metric": "committed events/sec (PHOLD-T)", "value": head["value"], "unit": "events/s", "n_gpus": N,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": head["scaling"], "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
+        "config": head["config"], "e2e": head.get("e2e"), "gpu_launches": head["gpu_launches"],
+        "roofline": head["roofline"], "clocks": head.get("clocks"), "parity": head["parity"],
+        "seed_ms_per_step": head["seed_ms_per_step"], "wall_ms_per_step": head["wall_ms_per_step"],
+        "launches_per_step": head["launches_per_step"], "window_last": head["window_last"],
+        "also": {r["tag"]: {k: r[k] for k in ("value", "ms_per_step", "seed_ms_per_step", "scaling", "config", "parity", "roofline", "gpu_launches") if k in r}
+                 | ({"e2e": r["e2e"]} if "e2e" in r else {}) for r in results[1:]},
     }
-    if rank == 0 and N == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline()
+    tr = measured_traffic()
+    if tr and N == 1:
+        line["roofline"]["traffic"] = tr.get("dram_bytes_per_full_launch")
+        line["roofline"]["traffic_detail"] = tr
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(head["tag"])
+    bad = [r["tag"] for r in results if r["parity"]["golden"] == "MISMATCH"]
     if rank == 0:
-        print(json.dumps(line))
-    eng.close()
+        print(json.dumps(line), flush=True)
     if N > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if bad:
+        sys.stderr.write("PARITY MISMATCH against tests/golden/bench_goldens.json: %s\n" % bad)
+        return 1
     return 0
-
-
-def measured_traffic():
-    """dram bytes per k_pass launch from the committed ncu capture (profiles/*.json), or None."""
-    p = os.path.join(ROOT, "profiles", "k_pass_traffic.json")
-    try:
-        return json.load(open(p))["dram_bytes_per_launch"]
-    except Exception:
-        return None
-
-
-def cpu_baseline():
-    """Bounded sample (about 10-30 s) of the same workload on the reference itself, host cores."""
-    dt = 40
-    res = run_reference_segments(3, dt, timeout=600)
-    if not res or len(res["segments"]) < 3:
-        return {"value": None, "unit": "events/s", "cores": 0, "kind": "reference", "sample": "unavailable: oracle/_ref binary missing"}
-    timed = res["segments"][1:]
-    commits = sum(s["commits"] for s in timed)
-    secs = sum(s["drain_secs"] for s in timed)
-    return {"value": commits / secs, "unit": "events/s", "cores": res["ranks"], "kind": "reference",
-            "sample": f"reference binary (oracle/_ref, {res['ranks']} rank threads of {os.cpu_count()} host CPUs): 2 timed drain(t_end) "
-                      f"slices of {dt} sim-time units ({commits} commits in {secs:.1f} s) after an untimed lead-in [0,{REF_LEAD_IN}) and "
-                      f"1 warm-up slice, 1M-LP PHOLD-T"}
 
 
 def main():
@@ -349,6 +463,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-all", action="store_true", help="measure e2e for the secondary workloads, too")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

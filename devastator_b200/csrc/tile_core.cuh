@@ -131,16 +131,32 @@ DEVA_HD Epoch load_epoch(const TCtl *c) {
   return ep;
 }
 
+// A block's tally of what it appended (shared memory; append_local counts here instead of hammering a
+// handful of addresses in TCtl with one global atomic per record): [0, NB) records per ring slot, then
+enum : int {
+  BH_FAR = NB,        // records beyond the ring's horizon (-> far_total)
+  BH_OVF = NB + 1,    // records of a ring bucket whose list was full (-> far_total, ovf_flag)
+  BH_FMIN = NB + 2,   // u64: earliest record beyond the horizon (-> far_min)
+  BH_ANTI = NB + 4,   // anti-messages appended (-> antis_pending)
+  BH_REBASE = NB + 5, // a record below the calendar's base (-> need_rebase)
+  BH_RMIN = NB + 6,   // u64: earliest record appended outside an epoch, i.e. a root (-> gvt)
+  BH_N = NB + 8
+};
+DEVA_HD void bh_init(uint32_t *bh) {
+  for (int i = 0; i < BH_N; i++) bh[i] = 0;
+  bh[BH_FMIN] = bh[BH_FMIN + 1] = bh[BH_RMIN] = bh[BH_RMIN + 1] = 0xffffffffu;
+}
+
 // per-block accumulators (shared memory), folded into TCtl once per tile
 struct Hdr {
   uint32_t n, nb, nl, nlw, nl_old, nf, first, slow, in_buf, lo, hi, skip, used_far, seg_big;
   uint32_t nbk[MAXM];                     // records of each of the window's buckets (nb = their sum)
   uint32_t bins[NBIN], n_active, chunk;   // LPs per record count; LPs that run; next chunk of 32 LPs to hand to a warp
-  uint32_t work_item, next_item;
+  uint32_t work_item, next_item, n_gen;
   // accumulated over all the tiles the block handles in a launch, folded into TCtl once (blk_flush)
   uint32_t executed, rolled, anti, remote, err, fresh_antis, evals, ovf;
   int32_t committed, nondet;
-  alignas(8) uint32_t bh[NB + 4];    // records this block appended per ring slot (-> ctl->btotal); [NB] far count, [NB+2..3] far min time (u64)
+  alignas(8) uint32_t bh[BH_N];      // what this block appended, per ring slot and otherwise (see BH_*): folded into TCtl by bh_flush
 };
 
 // one block's shared-memory workspace
@@ -158,7 +174,7 @@ struct Blk {
   uint32_t mphase;   // mbarrier phase parity (uniform across the block)
   unsigned char *pool; uint32_t pool_bytes;   // R | S | ord | efl as one region: the warps' workspaces in a follow-up launch
 };
-enum : uint8_t { F_FRESH = 1, F_ANTI = 2, F_INOLD = 4, F_INNEW = 8, F_CN = 16, F_CO = 32, F_OUT = 64, F_DEAD = 128 };
+enum : uint8_t { F_OWN = 1 /* flush only: a child that stays in its tile */, F_FRESH = 1, F_ANTI = 2, F_INOLD = 4, F_INNEW = 8, F_CN = 16, F_CO = 32, F_OUT = 64, F_DEAD = 128 };
 
 DEVA_HD size_t blk_bytes(uint32_t rcap) {
   size_t b = (size_t)rcap * sizeof(EvRec) + TILE * sizeof(LpState);
@@ -222,15 +238,45 @@ DEVA_HD uint32_t late_claim(unsigned long long *p, uint32_t epoch) {
 //   other GPU            -> this GPU's region of that GPU's receive buffer (NVLink store)
 //   time < ub (in epoch) -> the destination tile's LATE list: a straggler / anti-message / in-window child
 //   ring bucket          -> the (tile, bucket) list;  beyond the horizon or list full -> the tile's far list
-// bh: the calling block's per-slot histogram in shared memory (folded into ctl->btotal per tile), or
-// null to count straight into ctl->btotal.
+// bh: the calling block's tally in shared memory (BH_*; folded into TCtl by bh_flush), or null to count
+// straight into TCtl.
+// the tile's far list: records beyond the ring's horizon, and (in_ring) records whose bucket list is full
+DEVA_HD void append_far(const TView &v, const Epoch &ep, const EvRec &rec, uint32_t tile, bool in_ring, uint32_t *bh, uint32_t *err) {
+  TCtl *c = v.ctl;
+  const uint64_t b = rec.time >> ep.shift;
+  const uint32_t p = atom_add_u32(&v.fcnt[tile], 1u);
+  if (p >= v.CF) {
+#if !defined(__CUDA_ARCH__) && defined(DEVA_TILE_DEBUG)
+    fprintf(stderr, "far overflow: t=%llu flags=%u cur=%llu ub=%llu gvt=%llu shift=%u in_epoch=%u\n", (unsigned long long)rec.time, rec.flags, (unsigned long long)ep.cur_abs,
+            (unsigned long long)ep.ub, (unsigned long long)ep.gvt, ep.shift, ep.in_epoch);
+#endif
+    *err |= ERR_FAR_OVERFLOW; return;
+  }
+  st_ev(&v.far_[(size_t)tile * v.CF + p], rec);
+  if (in_ring) {                                     // belongs to the ring (its list is full, or it is the open bucket's
+    atom_or_u32(&v.tflags[tile], TF_OVF);            // tail beyond t_end): a rebin at the epoch's end puts it in place
+    if (bh) atom_add_u32(&bh[BH_OVF], 1u);
+    else { atom_add_u64(&c->far_total, 1ull); atom_or_u32(&c->ovf_flag, 1u); }
+  } else if (bh) {                                   // beyond the ring: counted per block
+    atom_add_u32(&bh[BH_FAR], 1u);
+    if (rec.time < *reinterpret_cast<volatile uint64_t *>(&bh[BH_FMIN])) atom_min_u64(reinterpret_cast<uint64_t *>(&bh[BH_FMIN]), rec.time);
+    if (b < ep.cur_abs) bh[BH_REBASE] = 1u;          // (benign race: any writer stores 1)
+  } else {
+    atom_add_u64(&c->far_total, 1ull);
+    atom_min_ull(&c->far_min, rec.time);             // (far_min covers only records beyond the ring)
+    if (b < ep.cur_abs) atom_or_u32(&c->need_rebase, 1u);   // a root below the calendar's base
+  }
+}
 DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uint32_t *bh, uint32_t *err) {
   const uint64_t dl64 = (uint64_t)rec.dst - v.lp_begin;
   if (dl64 >= v.A) { *err |= ERR_NOT_OWNER; return; }
   const uint32_t tile = (uint32_t)dl64 / TILE;
   TCtl *c = v.ctl;
-  if (rec.flags & EV_ANTI) atom_add_u64((unsigned long long *)&c->antis_pending, 1ull);
-  if (!ep.in_epoch) atom_min_ull(&c->gvt, rec.time);   // a root: the commit horizon cannot lie above it
+  if (rec.flags & EV_ANTI) { if (bh) atom_add_u32(&bh[BH_ANTI], 1u); else atom_add_u64((unsigned long long *)&c->antis_pending, 1ull); }
+  if (!ep.in_epoch) {                                  // a root: the commit horizon cannot lie above it
+    if (!bh) atom_min_ull(&c->gvt, rec.time);
+    else if (rec.time < *reinterpret_cast<volatile uint64_t *>(&bh[BH_RMIN])) atom_min_u64(reinterpret_cast<uint64_t *>(&bh[BH_RMIN]), rec.time);
+  }
   if (ep.in_epoch && rec.time < ep.ub) {
     if (rec.time < ep.gvt) { *err |= ERR_BELOW_GVT; return; }
     const uint32_t p = late_claim(&v.lcnt[ep.par][tile], ep.epoch);
@@ -256,28 +302,7 @@ DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uin
     }
     // list full: the record waits in the far list (readers clamp ncnt to C)
   }
-  const uint32_t p = atom_add_u32(&v.fcnt[tile], 1u);
-  if (p >= v.CF) {
-#if !defined(__CUDA_ARCH__) && defined(DEVA_TILE_DEBUG)
-    fprintf(stderr, "far overflow: t=%llu flags=%u cur=%llu ub=%llu gvt=%llu shift=%u in_epoch=%u d=%llu ncnt=%u\n", (unsigned long long)rec.time, rec.flags, (unsigned long long)ep.cur_abs,
-            (unsigned long long)ep.ub, (unsigned long long)ep.gvt, ep.shift, ep.in_epoch, (unsigned long long)d, d < NB ? v.ncnt[(size_t)tile * NB + (b % NB)] : 0u);
-#endif
-    *err |= ERR_FAR_OVERFLOW; return;
-  }
-  st_ev(&v.far_[(size_t)tile * v.CF + p], rec);
-  if (in_ring) {                                     // belongs to the ring (its list is full, or it is the open bucket's
-    atom_add_u64(&c->far_total, 1ull);               // tail beyond t_end): a rebin at the epoch's end puts it in place
-    atom_or_u32(&v.tflags[tile], TF_OVF);
-    atom_or_u32(&c->ovf_flag, 1u);
-  } else if (bh) {                                   // beyond the ring: counted per block (bh[NB], bh[NB+1..2] = count, min time)
-    atom_add_u32(&bh[NB], 1u);
-    atom_min_u64(reinterpret_cast<uint64_t *>(&bh[NB + 2]), rec.time);
-    if (b < ep.cur_abs) atom_or_u32(&c->need_rebase, 1u);
-  } else {
-    atom_add_u64(&c->far_total, 1ull);
-    atom_min_ull(&c->far_min, rec.time);             // (far_min covers only records beyond the ring)
-    if (b < ep.cur_abs) atom_or_u32(&c->need_rebase, 1u);   // a root below the calendar's base
-  }
+  append_far(v, ep, rec, tile, in_ring, bh, err);
 }
 DEVA_HD void route_append(const TView &v, const Epoch &ep, const EvRec &rec, uint32_t *bh, uint32_t *err, uint32_t *remote) {
   if (v.n_gpus > 1) {
@@ -609,14 +634,65 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
   for (uint32_t idx = 0; idx < h.n_active; idx++) run_lp<M, FULLK>(v, mp, ep, b, tile, out_buf, b.perm[idx]);
 #endif
   TL_SYNC();
-  // ---- flush: every slot that now holds a child goes to its list (all lanes busy, atomics in bulk)
+  // ---- flush: every slot that now holds a child goes to its list.  Nine children in ten stay in this
+  // tile (self-sends): they are counted per ring slot in shared memory, ONE global atomic per slot claims
+  // their places in the tile's lists, and their stores wait for nothing.  The others (another tile, the
+  // open window, beyond the horizon, another GPU) are gathered into a dense list first, so that their
+  // atomics leave in one go with every lane busy instead of one round trip per loop iteration.
   if (h.first) {
+    uint32_t *own = b.cur;                                            // [0, NB) records per slot | [NB, 2 NB) list position claimed | [2 NB, 3 NB) cursor
+    uint16_t *gen = reinterpret_cast<uint16_t *>(b.cur + 3 * NB);     // the other records' indices (b.cur and b.perm are contiguous, both free now)
+    constexpr uint32_t GEN_CAP = (uint32_t)((TILE - 3 * NB) * 2 + TILE);
+    static_assert(TILE >= 3 * NB, "flush workspace");
+    TL_THREADS(tid) {
+      for (uint32_t k = tid; k < 3u * NB; k += TL_NTHR) own[k] = 0;
+      if (tid == 0) h.n_gen = 0;
+    }
+    TL_SYNC();
     TL_THREADS(tid) {
       uint32_t err = 0, remote = 0;
-      for (uint32_t i = tid; i < h.n; i += TL_NTHR)
-        if (b.efl[i] & F_OUT) route_append(v, ep, b.R[i], h.bh, &err, &remote);
+      for (uint32_t i = tid; i < h.n; i += TL_NTHR) {
+        if (!(b.efl[i] & F_OUT)) continue;
+        const EvRec &r = b.R[i];
+        const uint64_t bk = r.time >> ep.shift;
+        if ((uint64_t)r.dst - tile_gid < (uint64_t)TILE && (uint64_t)r.dst - v.lp_begin < (uint64_t)v.A &&   // (a GPU's last tile may be partial)
+            r.time >= ep.ub && bk - ep.cur_abs < (uint64_t)NB && bk < ep.ring_hi) {
+          atom_add_u32(&own[(uint32_t)(bk % NB)], 1u);
+          b.efl[i] = F_OUT | F_OWN;
+        } else {
+          const uint32_t q = atom_add_u32(&h.n_gen, 1u);
+          if (q < GEN_CAP) gen[q] = (uint16_t)i; else route_append(v, ep, r, h.bh, &err, &remote);
+        }
+      }
       if (err) atom_or_u32(&h.err, err);
       if (remote) atom_add_u32(&h.remote, remote);
+    }
+    TL_SYNC();
+    TL_THREADS(tid) {
+      uint32_t err = 0, remote = 0, mine = 0, base = 0;
+      if (tid < NB && (mine = own[tid]) != 0) base = atom_add_u32(&v.ncnt[(size_t)tile * NB + tid], mine);   // (in flight while the loop below runs)
+      const uint32_t ng = h.n_gen < GEN_CAP ? h.n_gen : GEN_CAP;
+      for (uint32_t q = tid; q < ng; q += TL_NTHR) route_append(v, ep, b.R[gen[q]], h.bh, &err, &remote);
+      if (mine) {
+        own[NB + tid] = base;
+        const uint32_t room = base < v.C ? v.C - base : 0u;
+        atom_add_u32(&h.bh[tid], mine < room ? mine : room);
+      }
+      if (err) atom_or_u32(&h.err, err);
+      if (remote) atom_add_u32(&h.remote, remote);
+    }
+    TL_SYNC();
+    TL_THREADS(tid) {
+      uint32_t err = 0;
+      for (uint32_t i = tid; i < h.n; i += TL_NTHR) {
+        if ((b.efl[i] & (F_OUT | F_OWN)) != (F_OUT | F_OWN)) continue;
+        const EvRec &r = b.R[i];
+        const uint32_t slot = (uint32_t)((r.time >> ep.shift) % NB);
+        const uint32_t p = own[NB + slot] + atom_add_u32(&own[2 * NB + slot], 1u);
+        if (p < v.C) st_ev(&v.near_[((size_t)tile * NB + slot) * v.C + p], r);
+        else append_far(v, ep, r, tile, true, h.bh, &err);   // list full: the record waits in the far list
+      }
+      if (err) atom_or_u32(&h.err, err);
     }
     TL_SYNC();
   }
@@ -626,8 +702,21 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
 DEVA_HD void blk_begin(Blk &b) {
   Hdr &h = *b.h;
   h.executed = h.rolled = h.anti = h.remote = h.err = h.fresh_antis = h.evals = h.ovf = 0; h.committed = h.nondet = 0;
-  for (int i = 0; i < NB + 2; i++) h.bh[i] = 0;
-  h.bh[NB + 2] = h.bh[NB + 3] = 0xffffffffu;
+  bh_init(h.bh);
+}
+// a block's tally -> TCtl (one thread)
+DEVA_HD void bh_flush(const TView &v, const uint32_t *bh) {
+  TCtl *c = v.ctl;
+  for (int i = 0; i < NB; i++) if (bh[i]) atom_add_u64(&c->btotal[i], bh[i]);
+  if (bh[BH_FAR]) {
+    atom_add_u64(&c->far_total, bh[BH_FAR]);
+    atom_min_ull(&c->far_min, *reinterpret_cast<const unsigned long long *>(&bh[BH_FMIN]));
+  }
+  if (bh[BH_OVF]) { atom_add_u64(&c->far_total, bh[BH_OVF]); atom_or_u32(&c->ovf_flag, 1u); }
+  if (bh[BH_ANTI]) atom_add_u64((unsigned long long *)&c->antis_pending, bh[BH_ANTI]);
+  if (bh[BH_REBASE]) atom_or_u32(&c->need_rebase, 1u);
+  const unsigned long long rmin = *reinterpret_cast<const unsigned long long *>(&bh[BH_RMIN]);
+  if (rmin != ~0ull) atom_min_ull(&c->gvt, rmin);
 }
 DEVA_HD void blk_flush(const TView &v, Blk &b) {
   Hdr &h = *b.h;
@@ -642,11 +731,7 @@ DEVA_HD void blk_flush(const TView &v, Blk &b) {
   if (h.err) atom_or_u32(&c->err, h.err);
   if (h.ovf) atom_or_u32(&c->ovf_flag, 1u);          // consumed far records must be dropped before the next epoch
   if (h.evals) atom_add_u64(&c->evals, h.evals);
-  for (int i = 0; i < NB; i++) if (h.bh[i]) atom_add_u64(&c->btotal[i], h.bh[i]);
-  if (h.bh[NB]) {
-    atom_add_u64(&c->far_total, h.bh[NB]);
-    atom_min_ull(&c->far_min, *reinterpret_cast<unsigned long long *>(&h.bh[NB + 2]));
-  }
+  bh_flush(v, h.bh);
 }
 
 // One tile, one launch of an epoch.  Its window events are the open bucket's list (+ what waits for
@@ -1064,9 +1149,9 @@ DEVA_HD void rebin_tile(const TView &v, const Epoch &ep, Blk &b, uint32_t tile, 
       const uint32_t p = atom_add_u32(&v.fcnt[tile], 1u);
       if (p >= v.CF) { err |= ERR_FAR_OVERFLOW; continue; }
       st_ev(&v.far_[(size_t)tile * v.CF + p], r);
-      atom_add_u32(&h.bh[NB], 1u);
-      if (d < NB) atom_or_u32(&v.tflags[tile], TF_OVF);   // its bucket's list is full: evaluated from here (slow path)
-      else atom_min_u64(reinterpret_cast<uint64_t *>(&h.bh[NB + 2]), r.time);
+      atom_add_u32(&h.bh[BH_FAR], 1u);
+      if (d < NB) atom_or_u32(&v.tflags[tile], TF_OVF);   // its bucket's list is full: evaluated from here (slow path; no new rebin is asked for)
+      else atom_min_u64(reinterpret_cast<uint64_t *>(&h.bh[BH_FMIN]), r.time);
     }
     if (err) atom_or_u32(&h.err, err);
   }
@@ -1136,7 +1221,8 @@ DEVA_HD void choose_next(TCtl *c, const TParams &tp, const Glob &g, bool inclusi
   // the buckets about to open hold more than the lists and the workspace are built for (a start-up where
   // every root falls into a few ticks, a model denser than the current width suits): fewer buckets per
   // epoch first, then narrower buckets
-  if (!c->fixed_shift) {
+  // (a window pinned by the caller is an upper bound: it narrows the same way, and never widens again)
+  {
     const unsigned long long limit = (unsigned long long)tp.pol_occ_x16 * c->lp_total;
     for (;;) {
       unsigned long long sum = 0;
@@ -1327,7 +1413,7 @@ DEVA_HD void tile_init_lp(const TView &v, const ModelParams &mp, uint32_t lp, in
 
 // K roots of one LP (test/phold.cxx:172-178 with PHOLD-T's root time; bench/phold.cxx:152-158)
 template <class M>
-DEVA_HD void tile_seed_lp(const TView &v, const ModelParams &mp, const Epoch &ep, uint32_t lp, uint32_t k, int rootdiv, uint64_t per_rank, uint32_t *err) {
+DEVA_HD void tile_seed_lp(const TView &v, const ModelParams &mp, const Epoch &ep, uint32_t lp, uint32_t k, int rootdiv, uint64_t per_rank, uint32_t *bh, uint32_t *err) {
   const uint64_t gid = v.lp_begin + lp;
   if (gid >= mp.lp_n_model) return;                   // padding LPs of the rank decomposition get no roots
   for (uint32_t j = 0; j < k; j++) {
@@ -1337,7 +1423,7 @@ DEVA_HD void tile_seed_lp(const TView &v, const ModelParams &mp, const Epoch &ep
     else { ray = gid + (uint64_t)j * mp.lp_n_model; e.time = rootdiv ? j : ray; }
     e.sub = mp.user_subtime ? ray : gid % per_rank;  // pdes.hxx:907: root subtime = LOCAL cd index
     e.p0 = (uint32_t)ray; e.p1 = 0; e.dst = (uint32_t)gid; e.flags = 0;
-    append_local(v, ep, e, nullptr, err);
+    append_local(v, ep, e, bh, err);
   }
 }
 

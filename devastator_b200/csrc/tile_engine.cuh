@@ -153,13 +153,18 @@ __global__ void __launch_bounds__(256) k_tile_xchg(const __grid_constant__ TView
   __syncthreads();
   const Epoch ep = load_epoch(c);
   uint32_t err = timeout ? (uint32_t)ERR_PEER_TIMEOUT : 0u;
+  __shared__ __align__(8) uint32_t bh[BH_N];
+  if (threadIdx.x == 0) bh_init(bh);
+  __syncthreads();
   for (int src = 0; src < G; src++) {
     const uint32_t n = counts[src];
     const EvRec *recs = v.recvbuf + (size_t)src * v.peer_cap;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-      append_local(v, ep, ld_ev_cg(&recs[i]), nullptr, &err);
+      append_local(v, ep, ld_ev_cg(&recs[i]), bh, &err);
   }
   if (err) atomicOr(&c->err, err);
+  __syncthreads();
+  if (threadIdx.x == 0) bh_flush(v, bh);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) is_last = atomicAdd(&c->xticket, 1u) == gridDim.x - 1;
@@ -257,20 +262,30 @@ __global__ void k_tile_seed(TView v, ModelParams mp, uint32_t k, int rootdiv, ui
   Epoch ep = load_epoch(v.ctl);
   ep.in_epoch = 0;
   uint32_t err = 0;
-  if (lp < v.A) tile_seed_lp<M>(v, mp, ep, lp, k, rootdiv, per, &err);
+  __shared__ __align__(8) uint32_t bh[BH_N];
+  if (threadIdx.x == 0) bh_init(bh);
+  __syncthreads();
+  if (lp < v.A) tile_seed_lp<M>(v, mp, ep, lp, k, rootdiv, per, bh, &err);
   if (err) atomicOr(&v.ctl->err, err);
+  __syncthreads();
+  if (threadIdx.x == 0) bh_flush(v, bh);
 }
 
 __global__ void k_tile_roots(TView v, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload, uint32_t n) {
   Epoch ep = load_epoch(v.ctl);
   ep.in_epoch = 0;
   uint32_t err = 0;
+  __shared__ __align__(8) uint32_t bh[BH_N];
+  if (threadIdx.x == 0) bh_init(bh);
+  __syncthreads();
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     EvRec r;
     r.time = time[i]; r.sub = sub[i]; r.p0 = payload[i]; r.p1 = 0; r.dst = lp[i]; r.flags = 0;
-    append_local(v, ep, r, nullptr, &err);
+    append_local(v, ep, r, bh, &err);
   }
   if (err) atomicOr(&v.ctl->err, err);
+  __syncthreads();
+  if (threadIdx.x == 0) bh_flush(v, bh);
 }
 
 // AoS host layout [count][stw]  <->  the model words of LpState (current buffer of the LP's tile)

@@ -59,7 +59,13 @@ struct HostBE {
     Epoch ep = load_epoch(v.ctl);
     ep.in_epoch = 0;
     uint32_t err = 0;
-    for (uint32_t lp = 0; lp < v.A; lp++) tile_seed_lp<M>(v, mp, ep, lp, k, rootdiv, per, &err);
+    alignas(8) uint32_t bh[BH_N];   // (as the kernel does: a block's tally, folded into TCtl at its end)
+    bh_init(bh);
+    for (uint32_t lp = 0; lp < v.A; lp++) {
+      tile_seed_lp<M>(v, mp, ep, lp, k, rootdiv, per, bh, &err);
+      if (lp % 256 == 255) { bh_flush(v, bh); bh_init(bh); }
+    }
+    bh_flush(v, bh);
     v.ctl->err |= err;
     return 0;
   }
@@ -67,10 +73,13 @@ struct HostBE {
     Epoch ep = load_epoch(v.ctl);
     ep.in_epoch = 0;
     uint32_t err = 0;
+    alignas(8) uint32_t bh[BH_N];
+    bh_init(bh);
     for (uint64_t i = 0; i < n; i++) {
       EvRec r; r.time = time[i]; r.sub = sub[i]; r.p0 = payload[i]; r.p1 = 0; r.dst = lp[i]; r.flags = 0;
-      append_local(v, ep, r, nullptr, &err);
+      append_local(v, ep, r, (i & 1) ? bh : nullptr, &err);   // (both ways of counting)
     }
+    bh_flush(v, bh);
     v.ctl->err |= err;
     return 0;
   }
