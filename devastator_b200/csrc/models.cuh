@@ -28,6 +28,7 @@ DEVA_HD void rng_seed(int seed, uint64_t &a, uint64_t &b) {
 
 struct ModelParams {       // device copy of deva_b200_model_params (+ derived)
   uint64_t lp_n_model;
+  uint64_t lp_n_magic;     // floor((2^64 - 1) / lp_n_model): x % lp_n_model without a 64-bit division (model_params_derive)
   uint64_t p_remote_thresh;
   double neg_lambda;
   uint64_t end_time;
@@ -36,6 +37,20 @@ struct ModelParams {       // device copy of deva_b200_model_params (+ derived)
   double bench_peer_stddev;
   int32_t stop;            // bench PHOLD wall-clock cut-off flag (bench/phold.cxx:95-104)
 };
+
+DEVA_HD void model_params_derive(ModelParams &p) { p.lp_n_magic = p.lp_n_model ? ~0ull / p.lp_n_model : 0; }
+// x % lp_n_model, exactly: q = hi64(x * magic) is the quotient or at most 2 short of it (Barrett), so the
+// remainder needs at most two corrections - against ~60 instructions of the software 64-bit division
+DEVA_HD uint64_t mod_lp_n(const ModelParams &p, uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  const uint64_t q = __umul64hi(x, p.lp_n_magic);
+#else
+  const uint64_t q = (uint64_t)(((unsigned __int128)x * p.lp_n_magic) >> 64);
+#endif
+  uint64_t r = x - q * p.lp_n_model;
+  while (r >= p.lp_n_model) r -= p.lp_n_model;
+  return r;
+}
 
 // ---- test/phold.cxx model -----------------------------------------------------------------------
 struct PholdTest {
@@ -57,7 +72,7 @@ struct PholdTest {
     s[2] = chk;
     const uint64_t dt = phold_dt(rng_next(s[0], s[1]), p.neg_lambda);
     uint64_t to = lp;
-    if (rng_next(s[0], s[1]) < p.p_remote_thresh) to = (uint64_t)(int)(rng_next(s[0], s[1]) % p.lp_n_model);
+    if (rng_next(s[0], s[1]) < p.p_remote_thresh) to = (uint64_t)(int)mod_lp_n(p, rng_next(s[0], s[1]));
     if (e.time + dt < p.end_time) {
       c.time = e.time + dt;
       c.sub = ray;   // used only when user_subtime (test/phold.cxx:75); else the engine assigns seq ids

@@ -51,6 +51,15 @@ namespace tl {
 #define TL_WSYNC() ((void)0)
 #endif
 
+// phase clocks (compiled in with -DDEVA_TILE_PROF only; tools/tile_prof.py)
+#if defined(DEVA_TILE_PROF) && defined(__CUDA_ARCH__)
+#define TL_PROF(h, k) do { if (threadIdx.x == 0) { const unsigned long long t_ = clock64(); (h).prof[k] += t_ - (h).pt; (h).pt = t_; } } while (0)
+#define TL_PROF_START(h) do { if (threadIdx.x == 0) (h).pt = clock64(); } while (0)
+#else
+#define TL_PROF(h, k) ((void)0)
+#define TL_PROF_START(h) ((void)0)
+#endif
+
 #if defined(__CUDA_ARCH__)
 DEVA_HD unsigned long long atom_add_u64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 DEVA_HD void atom_min_ull(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
@@ -147,15 +156,23 @@ DEVA_HD void bh_init(uint32_t *bh) {
   bh[BH_FMIN] = bh[BH_FMIN + 1] = bh[BH_RMIN] = bh[BH_RMIN + 1] = 0xffffffffu;
 }
 
+// destination codes of a first evaluation's children that are placed in bulk by the flush:
+// [0, NB) ring slot of the tile's own lists, [NB, NB + MAX_GPUS) the receive region of a peer GPU
+constexpr int OWN_N = NB + MAX_GPUS;
+
 // per-block accumulators (shared memory), folded into TCtl once per tile
 struct Hdr {
   uint32_t n, nb, nl, nlw, nl_old, nf, first, slow, in_buf, lo, hi, skip, used_far, seg_big;
   uint32_t nbk[MAXM];                     // records of each of the window's buckets (nb = their sum)
   uint32_t bins[NBIN], n_active, chunk;   // LPs per record count; LPs that run; next chunk of 32 LPs to hand to a warp
   uint32_t work_item, next_item, n_gen;
+  uint32_t own[2 * OWN_N];                // flush: children counted per destination code (ring slot of this tile / peer GPU) | the places claimed for them
   // accumulated over all the tiles the block handles in a launch, folded into TCtl once (blk_flush)
   uint32_t executed, rolled, anti, remote, err, fresh_antis, evals, ovf;
   int32_t committed, nondet;
+#ifdef DEVA_TILE_PROF
+  unsigned long long prof[12], pt;
+#endif
   alignas(8) uint32_t bh[BH_N];      // what this block appended, per ring slot and otherwise (see BH_*): folded into TCtl by bh_flush
 };
 
@@ -172,6 +189,7 @@ struct Blk {
   uint64_t *mbar;
   uint32_t rcap;
   uint32_t mphase;   // mbarrier phase parity (uniform across the block)
+  uint64_t tile_gid; // first LP of the tile being evaluated (run_records)
   unsigned char *pool; uint32_t pool_bytes;   // R | S | ord | efl as one region: the warps' workspaces in a follow-up launch
 };
 enum : uint8_t { F_OWN = 1 /* flush only: a child that stays in its tile */, F_FRESH = 1, F_ANTI = 2, F_INOLD = 4, F_INNEW = 8, F_CN = 16, F_CO = 32, F_OUT = 64, F_DEAD = 128 };
@@ -217,20 +235,22 @@ DEVA_HD bool rec_less(const EvRec &a, const EvRec &b) {
 // A late list's counter carries the epoch it counts for above the count (epoch << 32 | count), so that
 // an epoch's commit need not touch every tile: the first arrival of a new epoch restarts the count.
 DEVA_HD uint32_t late_count(unsigned long long raw, uint32_t epoch) { return (uint32_t)(raw >> 32) == epoch ? (uint32_t)raw : 0u; }
-DEVA_HD uint32_t late_claim(unsigned long long *p, uint32_t epoch) {
+// `old` = what atomicAdd(p, 1) returned.  Its tag is the open epoch's for all but a tile's first arrival: one
+// round trip.  A stale tag: the first arrival restarts the count (the increment of the stale value is wiped
+// by whoever restarts it; if somebody else did, a place in the restarted count is claimed).
+DEVA_HD uint32_t late_claim_finish(unsigned long long *p, unsigned long long old, uint32_t epoch) {
+  if ((uint32_t)(old >> 32) == epoch) return (uint32_t)old;
 #if defined(__CUDA_ARCH__)
-  unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(p);
+  old += 1ull;
   for (;;) {
-    const unsigned long long nw = (uint32_t)(old >> 32) == epoch ? old + 1ull : (((unsigned long long)epoch << 32) | 1ull);
-    const unsigned long long seen = atomicCAS(p, old, nw);
-    if (seen == old) return (uint32_t)nw - 1u;
+    if ((uint32_t)(old >> 32) == epoch) return (uint32_t)atomicAdd(p, 1ull);
+    const unsigned long long seen = atomicCAS(p, old, ((unsigned long long)epoch << 32) | 1ull);
+    if (seen == old) return 0u;
     old = seen;
   }
 #else
-  const unsigned long long old = *p;
-  const unsigned long long nw = (uint32_t)(old >> 32) == epoch ? old + 1ull : (((unsigned long long)epoch << 32) | 1ull);
-  *p = nw;
-  return (uint32_t)nw - 1u;
+  *p = ((unsigned long long)epoch << 32) | 1ull;
+  return 0u;
 #endif
 }
 
@@ -267,6 +287,10 @@ DEVA_HD void append_far(const TView &v, const Epoch &ep, const EvRec &rec, uint3
     if (b < ep.cur_abs) atom_or_u32(&c->need_rebase, 1u);   // a root below the calendar's base
   }
 }
+// One record into this GPU's lists.  Whatever the destination - a late list, a bucket's list, the far list -
+// the place is claimed by ONE atomic that every lane of the warp issues together (the counters are 32-bit
+// words, the late lists' a tagged 64-bit one: a 64-bit add on the aligned pair serves all of them), so a warp
+// whose lanes go different ways pays one round trip, not one per way.
 DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uint32_t *bh, uint32_t *err) {
   const uint64_t dl64 = (uint64_t)rec.dst - v.lp_begin;
   if (dl64 >= v.A) { *err |= ERR_NOT_OWNER; return; }
@@ -277,36 +301,53 @@ DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uin
     if (!bh) atom_min_ull(&c->gvt, rec.time);
     else if (rec.time < *reinterpret_cast<volatile uint64_t *>(&bh[BH_RMIN])) atom_min_u64(reinterpret_cast<uint64_t *>(&bh[BH_RMIN]), rec.time);
   }
-  if (ep.in_epoch && rec.time < ep.ub) {
-    if (rec.time < ep.gvt) { *err |= ERR_BELOW_GVT; return; }
-    const uint32_t p = late_claim(&v.lcnt[ep.par][tile], ep.epoch);
-    if (atom_exch_u32(&v.dmark[tile], ep.launch) != ep.launch)                    // first arrival of this launch:
+  const bool late = ep.in_epoch && rec.time < ep.ub;   // a straggler / anti-message / in-window child of the open epoch
+  if (late && rec.time < ep.gvt) { *err |= ERR_BELOW_GVT; return; }
+  const uint64_t b = rec.time >> ep.shift;
+  const uint64_t d = b - ep.cur_abs;                 // (wraps to huge when b < cur_abs: goes to far, flagged)
+  const bool in_ring = !late && d < NB && b < ep.ring_hi;   // (the open buckets themselves only when t_end cuts them: evaluations then read frozen counts)
+  const uint32_t slot = (uint32_t)(b % NB);
+  // ---- where, and which counter
+  uint32_t *ctr = late ? reinterpret_cast<uint32_t *>(&v.lcnt[ep.par][tile]) : in_ring ? &v.ncnt[(size_t)tile * NB + slot] : &v.fcnt[tile];
+  EvRec *list = late ? v.late[ep.par] + (size_t)tile * v.CL : in_ring ? v.near_ + ((size_t)tile * NB + slot) * v.C : v.far_ + (size_t)tile * v.CF;
+  const uint32_t cap = late ? v.CL : in_ring ? v.C : v.CF;
+  const bool hi = (reinterpret_cast<uintptr_t>(ctr) & 4u) != 0;
+  unsigned long long *ctr64 = reinterpret_cast<unsigned long long *>(reinterpret_cast<uintptr_t>(ctr) & ~(uintptr_t)7);
+  uint32_t mark = ep.launch;
+  if (late) mark = atom_exch_u32(&v.dmark[tile], ep.launch);   // (in flight together with the claim)
+  const unsigned long long old = atom_add_u64(ctr64, hi ? (1ull << 32) : 1ull);
+  uint32_t p = hi ? (uint32_t)(old >> 32) : (uint32_t)old;
+  if (late) p = late_claim_finish(ctr64, old, ep.epoch);
+  if (p < cap) st_ev(&list[p], rec);
+  if (late) {
+    if (mark != ep.launch)                                                        // first arrival of this launch:
       v.dirty[ep.par][atom_add_u32(&c->dirty_n[ep.par], 1u)] = tile;              // the tile joins the next launch
-    if (p < v.CL) st_ev(&v.late[ep.par][(size_t)tile * v.CL + p], rec);
-    else {                                           // the tile's late list is full: job-wide spill list (evaluated by scanning)
+    if (p >= cap) {                                  // the tile's late list is full: job-wide spill list (evaluated by scanning)
       const uint32_t q = atom_add_u32(&c->sp_n[ep.par], 1u);
       if (q < v.SP) st_ev(&v.spill[ep.par][q], rec); else *err |= ERR_LATE_OVERFLOW;
     }
     return;
   }
-  const uint64_t b = rec.time >> ep.shift;
-  const uint64_t d = b - ep.cur_abs;                 // (wraps to huge when b < cur_abs: goes to far, flagged)
-  const bool in_ring = d < NB && b < ep.ring_hi;   // (the open buckets themselves only when t_end cuts them: evaluations then read frozen counts)
   if (in_ring) {
-    const uint32_t slot = (uint32_t)(b % NB);
-    const uint32_t p = atom_add_u32(&v.ncnt[(size_t)tile * NB + slot], 1u);
-    if (p < v.C) {
-      st_ev(&v.near_[((size_t)tile * NB + slot) * v.C + p], rec);
-      if (bh) atom_add_u32(&bh[slot], 1u); else atom_add_u64(&c->btotal[slot], 1ull);
-      return;
-    }
-    // list full: the record waits in the far list (readers clamp ncnt to C)
+    if (p < cap) { if (bh) atom_add_u32(&bh[slot], 1u); else atom_add_u64(&c->btotal[slot], 1ull); }
+    else append_far(v, ep, rec, tile, true, bh, err);   // list full: the record waits in the far list (readers clamp ncnt to C)
+    return;
   }
-  append_far(v, ep, rec, tile, in_ring, bh, err);
+  // far list (the place was claimed above)
+  if (p >= cap) { *err |= ERR_FAR_OVERFLOW; return; }
+  if (bh) {                                          // beyond the ring: counted per block
+    atom_add_u32(&bh[BH_FAR], 1u);
+    if (rec.time < *reinterpret_cast<volatile uint64_t *>(&bh[BH_FMIN])) atom_min_u64(reinterpret_cast<uint64_t *>(&bh[BH_FMIN]), rec.time);
+    if (b < ep.cur_abs) bh[BH_REBASE] = 1u;          // (benign race: any writer stores 1)
+  } else {
+    atom_add_u64(&c->far_total, 1ull);
+    atom_min_ull(&c->far_min, rec.time);             // (far_min covers only records beyond the ring)
+    if (b < ep.cur_abs) atom_or_u32(&c->need_rebase, 1u);   // a root below the calendar's base
+  }
 }
 DEVA_HD void route_append(const TView &v, const Epoch &ep, const EvRec &rec, uint32_t *bh, uint32_t *err, uint32_t *remote) {
   if (v.n_gpus > 1) {
-    const uint32_t g = (uint32_t)(rec.dst / v.lp_per_gpu);
+    const uint32_t g = (v.lp_per_gpu >> 32) ? 0u : rec.dst / (uint32_t)v.lp_per_gpu;   // (a 32-bit division: LP ids are 32 bits)
     if (g != (uint32_t)v.gpu_rank) {
       if (g >= (uint32_t)v.n_gpus) { *err |= ERR_NOT_OWNER; return; }
       const uint32_t p = agg_claim(&v.ctl->send_n[g], g);
@@ -328,6 +369,7 @@ DEVA_HD void route_append(const TView &v, const Epoch &ep, const EvRec &rec, uin
 //   MODE_NEW    re-evaluation, new sequence from the fork on: children are sent
 //   MODE_OLD    re-evaluation, old sequence from the fork on: children are cancelled (anti-messages)
 enum { MODE_FIRST = 0, MODE_SHARED = 1, MODE_NEW = 2, MODE_OLD = 3 };
+constexpr uint32_t GEN_CAP = TILE * 2;   // a first evaluation's children that leave the tile: indices listed in b.cur (u16 entries)
 struct IChild { uint64_t t, s; uint32_t p0, p1, slot; };
 struct Chain {
   uint64_t st[MAX_STW], seq;
@@ -394,8 +436,34 @@ DEVA_HD bool walk(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b
     }
     if (mode == MODE_SHARED) continue;           // already sent by the previous evaluation
     if (mode == MODE_FIRST) {                    // the child takes the slot; the block flushes all slots together
+      // Most children stay in this tile (self-sends) or go to another GPU: such a child takes its place among
+      // the block's additions to that list here (shared-memory counter per ring slot / per peer; parked in the
+      // flags word, which is 0 on every positive record), and the flush claims the places of all of them with
+      // ONE global atomic per list.  The others are listed, so that the flush sends them with every lane busy.
+      Hdr &h = *b.h;
+      const uint64_t bk = c.time >> ep.shift;
+      uint8_t fl = F_OUT;
+      uint32_t code = 0xffu;
+      if (v.n_gpus > 1) {
+        const uint32_t g = (v.lp_per_gpu >> 32) ? 0u : c.dst / (uint32_t)v.lp_per_gpu;   // (a 32-bit division: LP ids are 32 bits)
+        if (g != (uint32_t)v.gpu_rank) {
+          if (g >= (uint32_t)v.n_gpus) { *err |= ERR_NOT_OWNER; continue; }
+          code = (uint32_t)NB + g;
+        }
+      }
+      if (code == 0xffu && (uint64_t)c.dst - b.tile_gid < (uint64_t)TILE && (uint64_t)c.dst - v.lp_begin < (uint64_t)v.A &&   // (a GPU's last tile may be partial)
+          c.time >= ep.ub && bk - ep.cur_abs < (uint64_t)NB && bk < ep.ring_hi)
+        code = (uint32_t)(bk % NB);
+      if (code != 0xffu) {
+        c.flags = (atom_add_u32(&h.own[code], 1u) << 8) | code;
+        fl |= F_OWN;
+      } else {
+        const uint32_t q = atom_add_u32(&h.n_gen, 1u);
+        if (q < GEN_CAP) reinterpret_cast<uint16_t *>(b.cur)[q] = (uint16_t)slot;   // (b.cur is free once the LPs' run order is built)
+        else { route_append(v, ep, c, h.bh, err, remote); fl = 0; }
+      }
       b.R[slot] = c;
-      b.efl[slot] = F_OUT;
+      b.efl[slot] = fl;
     } else {
       if (mode == MODE_OLD) { c.flags = EV_ANTI; (*anti_sent)++; }
       route_append(v, ep, c, b.h->bh, err, remote);
@@ -546,10 +614,12 @@ template <class M, bool FULLK>
 DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf) {
   Hdr &h = *b.h;
   const uint64_t tile_gid = v.lp_begin + (uint64_t)tile * TILE;
+  b.tile_gid = tile_gid;
   TL_THREADS(tid) {
     for (uint32_t lp = tid; lp < (uint32_t)TILE; lp += TL_NTHR) b.cur[lp] = 0;
     if (tid < NBIN) h.bins[tid] = 0;
-    if (tid == 0) h.chunk = 0;
+    if (tid < OWN_N) h.own[tid] = 0;
+    if (tid == 0) { h.chunk = 0; h.n_gen = 0; }
   }
   TL_SYNC();
   TL_THREADS(tid) {
@@ -617,6 +687,7 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
   }
   TL_SYNC();
   // ---- run
+  TL_PROF(h, 3);
 #if defined(__CUDA_ARCH__)
   {
     const int lane = (int)(threadIdx.x & 31);
@@ -634,68 +705,53 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
   for (uint32_t idx = 0; idx < h.n_active; idx++) run_lp<M, FULLK>(v, mp, ep, b, tile, out_buf, b.perm[idx]);
 #endif
   TL_SYNC();
-  // ---- flush: every slot that now holds a child goes to its list.  Nine children in ten stay in this
-  // tile (self-sends): they are counted per ring slot in shared memory, ONE global atomic per slot claims
-  // their places in the tile's lists, and their stores wait for nothing.  The others (another tile, the
-  // open window, beyond the horizon, another GPU) are gathered into a dense list first, so that their
-  // atomics leave in one go with every lane busy instead of one round trip per loop iteration.
+  TL_PROF(h, 4);
+  // ---- flush: every slot that now holds a child goes to its list.  The children that stay in the tile or
+  // leave for another GPU were counted per list as they were produced (walk): one atomic per list claims
+  // their places - in the tile's bucket lists, in this GPU's region of the peer's receive buffer - and their
+  // stores wait for nothing.  The others (another tile, the open window, beyond the horizon) were listed:
+  // their atomics leave in one go, every lane busy.
   if (h.first) {
-    uint32_t *own = b.cur;                                            // [0, NB) records per slot | [NB, 2 NB) list position claimed | [2 NB, 3 NB) cursor
-    uint16_t *gen = reinterpret_cast<uint16_t *>(b.cur + 3 * NB);     // the other records' indices (b.cur and b.perm are contiguous, both free now)
-    constexpr uint32_t GEN_CAP = (uint32_t)((TILE - 3 * NB) * 2 + TILE);
-    static_assert(TILE >= 3 * NB, "flush workspace");
-    TL_THREADS(tid) {
-      for (uint32_t k = tid; k < 3u * NB; k += TL_NTHR) own[k] = 0;
-      if (tid == 0) h.n_gen = 0;
-    }
-    TL_SYNC();
-    TL_THREADS(tid) {
-      uint32_t err = 0, remote = 0;
-      for (uint32_t i = tid; i < h.n; i += TL_NTHR) {
-        if (!(b.efl[i] & F_OUT)) continue;
-        const EvRec &r = b.R[i];
-        const uint64_t bk = r.time >> ep.shift;
-        if ((uint64_t)r.dst - tile_gid < (uint64_t)TILE && (uint64_t)r.dst - v.lp_begin < (uint64_t)v.A &&   // (a GPU's last tile may be partial)
-            r.time >= ep.ub && bk - ep.cur_abs < (uint64_t)NB && bk < ep.ring_hi) {
-          atom_add_u32(&own[(uint32_t)(bk % NB)], 1u);
-          b.efl[i] = F_OUT | F_OWN;
-        } else {
-          const uint32_t q = atom_add_u32(&h.n_gen, 1u);
-          if (q < GEN_CAP) gen[q] = (uint16_t)i; else route_append(v, ep, r, h.bh, &err, &remote);
-        }
-      }
-      if (err) atom_or_u32(&h.err, err);
-      if (remote) atom_add_u32(&h.remote, remote);
-    }
-    TL_SYNC();
+    const uint16_t *gen = reinterpret_cast<const uint16_t *>(b.cur);
     TL_THREADS(tid) {
       uint32_t err = 0, remote = 0, mine = 0, base = 0;
-      if (tid < NB && (mine = own[tid]) != 0) base = atom_add_u32(&v.ncnt[(size_t)tile * NB + tid], mine);   // (in flight while the loop below runs)
+      if (tid < OWN_N && (mine = h.own[tid]) != 0)   // (in flight while the loop below runs)
+        base = atom_add_u32(tid < NB ? &v.ncnt[(size_t)tile * NB + tid] : &v.ctl->send_n[tid - NB], mine);
       const uint32_t ng = h.n_gen < GEN_CAP ? h.n_gen : GEN_CAP;
       for (uint32_t q = tid; q < ng; q += TL_NTHR) route_append(v, ep, b.R[gen[q]], h.bh, &err, &remote);
+      TL_PROF(h, 10);
       if (mine) {
-        own[NB + tid] = base;
-        const uint32_t room = base < v.C ? v.C - base : 0u;
-        atom_add_u32(&h.bh[tid], mine < room ? mine : room);
+        h.own[OWN_N + tid] = base;
+        if (tid < NB) {
+          const uint32_t room = base < v.C ? v.C - base : 0u;
+          atom_add_u32(&h.bh[tid], mine < room ? mine : room);
+        } else {
+          remote += mine;
+          if (base + mine > v.peer_cap) err |= ERR_SEND_OVERFLOW;
+        }
       }
+      TL_PROF(h, 11);
       if (err) atom_or_u32(&h.err, err);
       if (remote) atom_add_u32(&h.remote, remote);
     }
     TL_SYNC();
+    TL_PROF(h, 9);
     TL_THREADS(tid) {
       uint32_t err = 0;
       for (uint32_t i = tid; i < h.n; i += TL_NTHR) {
         if ((b.efl[i] & (F_OUT | F_OWN)) != (F_OUT | F_OWN)) continue;
-        const EvRec &r = b.R[i];
-        const uint32_t slot = (uint32_t)((r.time >> ep.shift) % NB);
-        const uint32_t p = own[NB + slot] + atom_add_u32(&own[2 * NB + slot], 1u);
-        if (p < v.C) st_ev(&v.near_[((size_t)tile * NB + slot) * v.C + p], r);
+        EvRec r = b.R[i];
+        const uint32_t code = r.flags & 0xffu, p = h.own[OWN_N + code] + (r.flags >> 8);
+        r.flags = 0;
+        if (code >= (uint32_t)NB) { if (p < v.peer_cap) st_ev(&v.peer_buf[code - NB][p], r); }   // NVLink store into the peer's receive region
+        else if (p < v.C) st_ev(&v.near_[((size_t)tile * NB + code) * v.C + p], r);
         else append_far(v, ep, r, tile, true, h.bh, &err);   // list full: the record waits in the far list
       }
       if (err) atom_or_u32(&h.err, err);
     }
     TL_SYNC();
   }
+  TL_PROF(h, 5);
 }
 
 // per-launch accumulators of a block: zero at kernel start, folded into TCtl at kernel end
@@ -703,6 +759,9 @@ DEVA_HD void blk_begin(Blk &b) {
   Hdr &h = *b.h;
   h.executed = h.rolled = h.anti = h.remote = h.err = h.fresh_antis = h.evals = h.ovf = 0; h.committed = h.nondet = 0;
   bh_init(h.bh);
+#ifdef DEVA_TILE_PROF
+  for (int i = 0; i < 12; i++) h.prof[i] = 0;
+#endif
 }
 // a block's tally -> TCtl (one thread)
 DEVA_HD void bh_flush(const TView &v, const uint32_t *bh) {
@@ -732,6 +791,9 @@ DEVA_HD void blk_flush(const TView &v, Blk &b) {
   if (h.ovf) atom_or_u32(&c->ovf_flag, 1u);          // consumed far records must be dropped before the next epoch
   if (h.evals) atom_add_u64(&c->evals, h.evals);
   bh_flush(v, h.bh);
+#ifdef DEVA_TILE_PROF
+  for (int i = 0; i < 12; i++) if (h.prof[i]) atom_add_u64(&c->prof[i], h.prof[i]);
+#endif
 }
 
 // One tile, one launch of an epoch.  Its window events are the open bucket's list (+ what waits for
@@ -743,6 +805,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
   ModelParams mp = mp0;
   mp.stop = (int32_t)ep.stop;
   const uint32_t rd = ep.par ^ 1u;                 // late list written by the previous launch
+  TL_PROF_START(h);
   TL_THREADS(tid) {
     if (tid != 0) continue;
     // the lists of the window committed last are empty from here on (nobody appends to them in this launch)
@@ -773,6 +836,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
   }
   TL_SYNC();
   if (h.skip) return;
+  TL_PROF(h, 0);
   const uint32_t out_buf = h.in_buf ^ 1u;
   // bucket k of the window lives in ring slot (cur_abs + k) % NB
   auto blist = [&](uint32_t k) -> const EvRec * { return v.near_ + ((size_t)tile * NB + (uint32_t)((ep.cur_abs + k) % NB)) * v.C; };
@@ -797,6 +861,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     }
     mbar_wait(b.mbar, b.mphase);
     b.mphase ^= 1u;
+    TL_PROF(h, 1);
 #else
     for (uint32_t k = 0, o = 0; k < ep.m; k++) { for (uint32_t i = 0; i < h.nbk[k]; i++) b.R[o + i] = blist(k)[i]; o += h.nbk[k]; }
     for (uint32_t i = 0; i < h.nlw; i++) b.R[h.nb + i] = late_w[i];
@@ -816,6 +881,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
       }
     }
     TL_SYNC();
+    TL_PROF(h, 2);
     run_records<M, FULLK>(v, mp, ep, b, tile, out_buf);
   } else {
     // ---- slow path: the window does not fit in shared memory (a start-up bucket holding every root,
@@ -932,6 +998,10 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     h.evals++;
   }
   TL_SYNC();
+  TL_PROF(h, 6);
+#ifdef DEVA_TILE_PROF
+  TL_THREADS(tid) { if (tid == 0) h.prof[7]++; }
+#endif
 }
 
 // ---- follow-up launches: ONE WARP re-evaluates a tile --------------------------------------------------
@@ -946,14 +1016,14 @@ struct WHdr {
   uint32_t need[32], offs[32];
 };
 struct WBlk {
-  WHdr *h; uint8_t *alist; EvRec *R; uint16_t *ord; uint8_t *efl; uint32_t cap;
+  WHdr *h; uint16_t *alist; EvRec *R; uint16_t *ord; uint8_t *efl; uint32_t cap;
 };
 DEVA_HD void warp_carve(WBlk &w, const Blk &b, int warp, int n_warps) {
   const uint32_t region = (b.pool_bytes / (uint32_t)n_warps) & ~15u;
   unsigned char *base = b.pool + (size_t)warp * region;
   size_t o = 0;
   w.h = reinterpret_cast<WHdr *>(base); o += (sizeof(WHdr) + 15) & ~(size_t)15;
-  w.alist = base + o; o += TILE;
+  w.alist = reinterpret_cast<uint16_t *>(base + o); o += TILE * 2;
   const uint32_t cap = ((region - (uint32_t)o) / 35u) & ~7u;   // 32 (record) + 2 (index) + 1 (flags) bytes each
   w.cap = cap;
   w.R = reinterpret_cast<EvRec *>(base + o); o += (size_t)cap * sizeof(EvRec);
@@ -1014,7 +1084,7 @@ DEVA_HD void follow_tile_warp(const TView &v, const ModelParams &mp0, const Epoc
     if (lane != 0) continue;
     uint32_t n = 0;
     for (uint32_t wd = 0; wd < (uint32_t)TILE / 32; wd++)
-      for (uint32_t m = h.bitmap[wd]; m; m &= m - 1) w.alist[n++] = (uint8_t)(wd * 32u + (uint32_t)ffs32(m) - 1u);
+      for (uint32_t m = h.bitmap[wd]; m; m &= m - 1) w.alist[n++] = (uint16_t)(wd * 32u + (uint32_t)ffs32(m) - 1u);
     h.n_aff = n;
   }
   TL_WSYNC();
@@ -1203,6 +1273,21 @@ DEVA_HD void choose_next(TCtl *c, const TParams &tp, const Glob &g, bool inclusi
   uint32_t m = c->want_m < 1 ? 1u : (c->want_m > (uint32_t)MAXM ? (uint32_t)MAXM : c->want_m);
   if (c->fixed_shift) m = 1;
   const uint64_t far_b = g.far_total > 0 && g.far_min != ~0ull ? g.far_min >> c->shift : ~0ull;
+  // Bucket lists overflowed into the far lists (a start-up where every root falls into a few ticks): if the
+  // buckets about to open are too full for the lists anyway, go to the width that suits in ONE re-bucketing
+  // instead of re-bucketing the overflow first and narrowing step by step afterwards.
+  if (g.ovf_flag && !g.need_rebase && nb_abs != ~0ull && c->shift > 0) {
+    const unsigned long long limit = (unsigned long long)tp.pol_occ_x16 * c->lp_total;
+    unsigned long long sum = g.far_total;            // (upper bound: all of the overflow counted into the next window)
+    for (uint32_t k = 0; k < m; k++) sum += g.btotal[(nb_abs + k) % NB];
+    if (sum * 16ull > limit) {
+      uint32_t down = 1;
+      while (down < c->shift && ((sum * 16ull) >> down) > limit) down++;
+      c->want_shift = c->shift - down; c->want_m = 1; c->hold = 2;
+      choose_next(c, tp, g, inclusive);
+      return;
+    }
+  }
   if (g.need_rebase || g.ovf_flag || (far_b != ~0ull && (nb_abs == ~0ull || far_b <= nb_abs + (m - 1)))) {
     // far records are due (or misplaced): re-bucket them against the base the next epoch will have
     uint64_t base = nb_abs < far_b ? nb_abs : far_b;

@@ -84,6 +84,7 @@ struct TileEngine {
     mp.lp_n_model = c->mp.lp_n_model; mp.p_remote_thresh = c->mp.p_remote_thresh; mp.neg_lambda = -c->mp.lambda;
     mp.end_time = c->mp.end_time; mp.user_subtime = c->mp.user_subtime; mp.bench_lp_per_rank = c->mp.bench_lp_per_rank;
     mp.bench_peer_stddev = c->mp.bench_peer_stddev; mp.stop = 0;
+    model_params_derive(mp);
     memset(&v, 0, sizeof v);
     v.A = (uint32_t)c->lp_count;
     v.NT = (v.A + TILE - 1) / TILE;
@@ -143,6 +144,9 @@ struct TileEngine {
     hc.win_m = hc.want_m = 1;
     hc.lp_total = c->lp_n;
     hc.far_min = ~0ull;
+#ifdef DEVA_TILE_PROF
+    hc.prof[14] = ~0ull;
+#endif
     if ((rc = clear_calendar(false))) return rc;
     return init_states(0);
   }
@@ -195,6 +199,18 @@ struct TileEngine {
     if ((rc = clear_calendar(true)) || (rc = init_states(1))) return rc;
     const int R = ranks > 0 ? ranks : 1;
     const uint64_t per = (v.lp_n + R - 1) / R;
+    if (!hc.fixed_shift && rootdiv && cfg.model != DEVA_B200_MODEL_PHOLD_BENCH) {
+      // k roots per LP at times 0 .. k-1: one per LP per tick.  Start with buckets that hold what the lists are
+      // built for (the policy widens them once the events have spread out) instead of overflowing the first
+      // bucket's lists and re-bucketing everything before the first epoch.
+      uint32_t s0 = 0;
+      while ((2ull << s0) * 16ull <= tp.pol_occ_x16 && s0 < hc.shift) s0++;
+      if (s0 < hc.shift) {
+        if ((rc = be.read_ctl(v, &hc))) return rc;
+        hc.shift = hc.want_shift = s0; hc.win_m = hc.want_m = 1;
+        if ((rc = be.write_ctl(v, &hc))) return rc;
+      }
+    }
     rc = tile_dispatch_model(cfg.model, [&](auto m) { return be.template k_seed<typename decltype(m)::type>(v, mp, k, rootdiv, per); });
     launches++;
     has_rewind = false;
@@ -234,26 +250,46 @@ struct TileEngine {
       tf = fopen(path.c_str(), "a");
       if (tf) { fseek(tf, 0, SEEK_END); if (ftell(tf) == 0) fprintf(tf, "sim_time,window,epochs,launches,executed,rolled_back,committed,batch_ms\n"); }
     }
-    uint64_t guard = 0;
-    for (;;) {
-      TCtl before = hc;
-      be.timer_start(1);
+    // Batches of launches are enqueued one AHEAD of the batch whose control block the host is looking at, so the
+    // device never waits for the host between batches (a launch after the drain's end is a no-op of a few us).
+    auto enqueue = [&](int slot) -> int {
+      be.batch_begin(slot);
       for (uint32_t i = 0; i < batch; i++) {
-        rc = tile_dispatch_model(cfg.model, [&](auto m) { return be.template k_step<typename decltype(m)::type>(v, mp, tp); });
-        if (rc) { if (tf) fclose(tf); return rc; }
+        int r = tile_dispatch_model(cfg.model, [&](auto m) { return be.template k_step<typename decltype(m)::type>(v, mp, tp); });
+        if (r) return r;
       }
       launches += batch;
-      const double bms = be.timer_stop(1);
+      return be.batch_end(v, slot);
+    };
+    uint64_t guard = 0;
+    int slot = 0;
+    uint32_t stop_sent = hc.stop_req;
+    if ((rc = enqueue(slot))) { if (tf) fclose(tf); return rc; }
+    for (;;) {
+      TCtl before = hc;
+      const uint32_t want_stop = (uint32_t)stop_req.load();
+      if (want_stop != stop_sent) {
+        if ((rc = be.set_stop(v, want_stop))) { if (tf) fclose(tf); return rc; }
+        stop_sent = want_stop;
+      }
+      if ((rc = enqueue(slot ^ 1))) { if (tf) fclose(tf); return rc; }
+      double bms = 0;
+      if ((rc = be.batch_wait(v, slot, &hc, &bms))) { if (tf) fclose(tf); return rc; }
+      slot ^= 1;
       exec_ms += bms;
-      hc.stop_req = (uint32_t)stop_req.load();
-      if ((rc = be.read_ctl_set_stop(v, &hc, hc.stop_req))) { if (tf) fclose(tf); return rc; }
       if (tf) fprintf(tf, "%llu,%llu,%llu,%u,%llu,%llu,%llu,%.4f\n", (unsigned long long)before.gvt, (unsigned long long)hc.win_m << hc.shift,
                       (unsigned long long)(hc.epochs - before.epochs), hc.launch - before.launch, (unsigned long long)(hc.executed - before.executed),
                       (unsigned long long)(hc.rolled - before.rolled), (unsigned long long)(hc.committed - before.committed), bms);
-      if (hc.err) { if (tf) fclose(tf); return check_err(); }
+      if (hc.err) { be.batch_wait(v, slot, nullptr, nullptr); if (tf) fclose(tf); return check_err(); }
       if (hc.phase == PH_DONE) break;
-      if (hc.launch == before.launch && ++guard > 4) { if (tf) fclose(tf); return tile_fail(DEVA_B200_ERR_INVARIANT, "tile engine: the step kernel makes no progress (phase %u)", hc.phase); }
+      if (hc.launch == before.launch && ++guard > 4) { be.batch_wait(v, slot, nullptr, nullptr); if (tf) fclose(tf); return tile_fail(DEVA_B200_ERR_INVARIANT, "tile engine: the step kernel makes no progress (phase %u)", hc.phase); }
       if (hc.launch != before.launch) guard = 0;
+    }
+    {   // the batch enqueued ahead ran as no-ops (or found nothing left to do)
+      double bms = 0;
+      if ((rc = be.batch_wait(v, slot, &hc, &bms))) { if (tf) fclose(tf); return rc; }
+      exec_ms += bms;
+      if (hc.err) { if (tf) fclose(tf); return check_err(); }
     }
     if (tf) fclose(tf);
     passes0 += hc.launch - launch0;
@@ -273,6 +309,20 @@ struct TileEngine {
     }
     drain_ms += be.timer_stop(0);
     if (gvt_out) *gvt_out = gvt;
+#ifdef DEVA_TILE_PROF
+    {   // cumulative phase clocks of the full launches (see TCtl::prof)
+      static const char *nm[12] = {"header", "load", "flags", "sort", "run", "flush:stores", "writeback", "", "flush:classify", "flush:sync", "flush:t0 others", "flush:t0 claim"};
+      double tot = 0;
+      for (int i = 0; i < 12; i++) if (i != 7) tot += (double)hc.prof[i];
+      fprintf(stderr, "tile prof:");
+      for (int i = 0; i < 12; i++) if (i != 7) fprintf(stderr, " %s %.1f%%", nm[i], 100.0 * hc.prof[i] / (tot > 0 ? tot : 1));
+      const double per_launch = (double)hc.prof[13] / (double)(hc.prof[7] ? (double)hc.prof[7] / v.NT : 1);
+      fprintf(stderr, " | ticks/tile %.0f tiles %llu | block lifetime / (blocks x launch span) = %.3f, span total %.3f ms\n", tot / (hc.prof[7] ? hc.prof[7] : 1),
+              (unsigned long long)hc.prof[7], hc.prof[15] ? (double)hc.prof[12] / ((double)hc.prof[15] * per_launch) : 0.0, hc.prof[15] * 1e-6);
+      fprintf(stderr, "tile prof: launch spans (cumulative): full %.3f ms / %llu, follow-up %.3f ms / %llu, rebin %.3f ms / %llu\n", hc.prof[15] * 1e-6, (unsigned long long)hc.prof[20],
+              hc.prof[16] * 1e-6, (unsigned long long)hc.prof[17], hc.prof[18] * 1e-6, (unsigned long long)hc.prof[19]);
+    }
+#endif
     return 0;
   }
 

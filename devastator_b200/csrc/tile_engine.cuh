@@ -15,7 +15,10 @@ namespace deva_b200 {
 namespace tl {
 
 #ifndef DEVA_TILE_MINB
-#define DEVA_TILE_MINB 4   // resident blocks per SM the register allocator must allow
+#define DEVA_TILE_MINB 4   // resident blocks per SM the register allocator must allow (kernel of an epoch's first launch)
+#endif
+#ifndef DEVA_TILE_MINB_FOLLOW
+#define DEVA_TILE_MINB_FOLLOW 3   // ... kernel of the follow-up launches (two chains alive at once: more registers)
 #endif
 
 // ---- several GPUs: device-side exchange over the peers' IPC-mapped comm blocks (NVLink) ---------------
@@ -59,13 +62,17 @@ __device__ __forceinline__ void publish_counts(const TView &v) {
 // enqueues them in a fixed pattern (one full, three follow-ups, ...); a launch whose turn it is not
 // returns at once - what the next launch has to do is decided on the device (close_launch).
 template <class M, bool FULLK>
-__global__ void __launch_bounds__(NTHR, FULLK ? DEVA_TILE_MINB : 3)
+__global__ void __launch_bounds__(NTHR, FULLK ? DEVA_TILE_MINB : DEVA_TILE_MINB_FOLLOW)
 k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams mp, const __grid_constant__ TParams tp) {
   extern __shared__ __align__(128) unsigned char tl_smem[];
   TCtl *c = v.ctl;
   const uint32_t phase = c->phase;
   if (phase != PH_EVAL && phase != PH_REBIN) return;   // done / idle: the launch is a no-op
   if (FULLK != (phase == PH_REBIN || c->full != 0)) return;   // not this kernel's turn
+#ifdef DEVA_TILE_PROF
+  unsigned long long prof_t0 = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(prof_t0));
+#endif
   Blk b;
   blk_carve(b, tl_smem, tp.rcap);
   if (threadIdx.x == 0) {
@@ -107,6 +114,14 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
   if (threadIdx.x == 0) {
     blk_flush(v, b);
     bulk_wait_all();   // the bulk stores of the tiles' states are complete
+#ifdef DEVA_TILE_PROF
+    {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (FULLK && phase == PH_EVAL) { atomicAdd(&c->prof[12], t1 - prof_t0); atomicAdd(&c->prof[13], 1ull); }
+      atomicMin(&c->prof[14], prof_t0);
+    }
+#endif
   }
   // the last block to finish closes the launch: follow-up, epoch commit, or calendar maintenance next
   __shared__ uint32_t is_last;
@@ -116,6 +131,15 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+#ifdef DEVA_TILE_PROF
+  if (threadIdx.x == 0) {   // the launch's span: earliest block start .. now
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    const int k = phase == PH_REBIN ? 18 : FULLK ? 15 : 16;
+    c->prof[k] += t1 - c->prof[14]; c->prof[14] = ~0ull;
+    c->prof[k == 15 ? 20 : k + 1]++;
+  }
+#endif
   if (v.n_gpus > 1) {   // several GPUs: the exchange kernel closes the launch, once the peers' figures are in
     if (threadIdx.x == 0) c->stepped = 1;
     publish_counts(v);
@@ -345,7 +369,10 @@ struct CudaBE {
   cudaStream_t stream = nullptr;
   std::vector<void *> allocs;
   cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  cudaEvent_t bev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // per batch slot: begin, end, control block copied
   TCtl *h_ctl = nullptr;              // pinned
+  TCtl *h_ctl2 = nullptr;             // pinned, one per batch slot
+  int stop_slot = 0;
   unsigned long long *d_tmp = nullptr;
   unsigned long long *h_tmp = nullptr;
   char *stage = nullptr;
@@ -360,7 +387,9 @@ struct CudaBE {
     TCU(cudaSetDevice(dev));
     TCU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto &p : ev) for (auto &e : p) TCU(cudaEventCreate(&e));
+    for (auto &p : bev) for (auto &e : p) TCU(cudaEventCreate(&e));
     TCU(cudaHostAlloc((void **)&h_ctl, sizeof(TCtl), cudaHostAllocDefault));
+    TCU(cudaHostAlloc((void **)&h_ctl2, 2 * sizeof(TCtl), cudaHostAllocDefault));
     TCU(cudaHostAlloc((void **)&h_tmp, 64, cudaHostAllocDefault));
     TCU(cudaMalloc((void **)&d_tmp, 64));
     cudaDeviceProp prop;
@@ -396,10 +425,12 @@ struct CudaBE {
     if (stage) cudaFree(stage);
     if (d_tmp) cudaFree(d_tmp);
     if (h_ctl) cudaFreeHost(h_ctl);
+    if (h_ctl2) cudaFreeHost(h_ctl2);
+    for (auto &p : bev) for (auto &e : p) if (e) cudaEventDestroy(e);
     if (h_tmp) cudaFreeHost(h_tmp);
     for (auto &p : ev) for (auto &e : p) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
-    stream = nullptr; stage = nullptr; d_tmp = nullptr; h_ctl = nullptr; h_tmp = nullptr;
+    stream = nullptr; stage = nullptr; d_tmp = nullptr; h_ctl = nullptr; h_ctl2 = nullptr; h_tmp = nullptr;
   }
   int zero(void *p, size_t n) { TCU(cudaMemsetAsync(p, 0, n, stream)); return 0; }
   int fill_ff(void *p, size_t n) { TCU(cudaMemsetAsync(p, 0xff, n, stream)); return 0; }
@@ -416,13 +447,23 @@ struct CudaBE {
     TCU(cudaStreamSynchronize(stream));
     return 0;
   }
-  int read_ctl_set_stop(const TView &v, TCtl *out, uint32_t stop) {
-    int rc = read_ctl(v, out);
-    if (rc) return rc;
-    if (out->stop_req != stop) {   // (the stream is idle: no kernel reads the block now)
-      h_tmp[4] = stop;
-      TCU(cudaMemcpyAsync(&v.ctl->stop_req, &h_tmp[4], sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-    }
+  // ---- batches of launches, two in flight: events around each, the control block copied out behind it
+  void batch_begin(int slot) { cudaEventRecord(bev[slot][0], stream); }
+  int batch_end(const TView &v, int slot) {
+    TCU(cudaEventRecord(bev[slot][1], stream));
+    TCU(cudaMemcpyAsync(&h_ctl2[slot], v.ctl, sizeof(TCtl), cudaMemcpyDeviceToHost, stream));
+    TCU(cudaEventRecord(bev[slot][2], stream));
+    return 0;
+  }
+  int batch_wait(const TView &, int slot, TCtl *out, double *ms) {
+    TCU(cudaEventSynchronize(bev[slot][2]));
+    if (out) *out = h_ctl2[slot];
+    if (ms) { float f = 0; cudaEventElapsedTime(&f, bev[slot][0], bev[slot][1]); *ms = f; }
+    return 0;
+  }
+  int set_stop(const TView &v, uint32_t stop) {   // (in stream order: takes effect between two launches; latched at an epoch boundary)
+    h_tmp[4 + (stop_slot ^= 1)] = stop;
+    TCU(cudaMemcpyAsync(&v.ctl->stop_req, &h_tmp[4 + stop_slot], sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     return 0;
   }
   void timer_start(int i) { cudaEventRecord(ev[i][0], stream); }

@@ -115,6 +115,12 @@ struct TCtl {
   uint32_t stepped, spad;          // the step kernel of this round did work (else the exchange kernel is a no-op, too)
   PeerMsg agg;                     // job-wide sums of the last round
   unsigned long long g_exec0, g_commit0;
+#ifdef DEVA_TILE_PROF
+  // phase clocks of the step kernel (thread 0 of every block, clock64 ticks summed over blocks; tools/tile_prof.py):
+  // [0] header [1] load wait [2] flags [3] sort [4] run [5] flush [6] write back [7] tiles, [8] flush: classify, [9] flush: claims + others; [12] block lifetime (globaltimer ns),
+  // [13] blocks, [14] earliest block start of the launch, [15] summed launch spans (globaltimer ns; full launches only)
+  unsigned long long prof[24];      // ... [16] follow-up launches: summed spans, [17] count; [18] rebin launches: summed spans, [19] count; [20] full launches
+#endif
 };
 
 struct TView {

@@ -115,6 +115,7 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   e->mp.bench_lp_per_rank = cfg->mp.bench_lp_per_rank;
   e->mp.bench_peer_stddev = cfg->mp.bench_peer_stddev;
   e->mp.stop = 0;
+  model_params_derive(e->mp);
   View &v = e->v;
   memset(&v, 0, sizeof v);
   memset(&e->ctl, 0, sizeof e->ctl);

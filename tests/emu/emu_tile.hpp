@@ -36,7 +36,11 @@ struct HostBE {
   int d2d(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
   int read_ctl(const TView &v, TCtl *out) { *out = *v.ctl; return 0; }
   int write_ctl(const TView &v, const TCtl *in) { *v.ctl = *in; return 0; }
-  int read_ctl_set_stop(const TView &v, TCtl *out, uint32_t stop) { v.ctl->stop_req = stop; *out = *v.ctl; return 0; }
+  TCtl slot_ctl[2];
+  void batch_begin(int) {}
+  int batch_end(const TView &v, int slot) { slot_ctl[slot] = *v.ctl; return 0; }
+  int batch_wait(const TView &, int slot, TCtl *out, double *ms) { if (out) *out = slot_ctl[slot]; if (ms) *ms = 0; return 0; }
+  int set_stop(const TView &v, uint32_t stop) { v.ctl->stop_req = stop; return 0; }
   void timer_start(int) {}
   double timer_stop(int) { return 0; }
 
