@@ -1004,15 +1004,20 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
 #endif
 }
 
-// ---- follow-up launches: ONE WARP re-evaluates a tile --------------------------------------------------
-// A tile that received stragglers / anti-messages has a handful of affected LPs (17 of 256 on
-// BASELINE's PHOLD).  Instead of loading and sorting the whole window again, a warp finds the affected
-// LPs from the fresh arrivals, fetches just their records - the bucket records through the index the
-// first evaluation left (gord / goff), the arrivals by scanning the two short late lists - into its
-// share of the block's shared memory, and each lane re-runs one LP from the checkpoint.
-struct WHdr {
-  uint32_t first, in_buf, nl, nlw, nl_old, nb, n_aff, idx_ok, round_n, nbk[MAXM];
+// ---- follow-up launches: ONE WARP re-evaluates a few tiles ----------------------------------------------
+// A tile that received stragglers / anti-messages has a handful of affected LPs (5 of 256 on BASELINE's
+// PHOLD).  Instead of loading and sorting the whole window again, a warp takes up to TMAX such tiles at
+// once, finds the affected LPs from the fresh arrivals, fetches just their records - the bucket records
+// through the index the first evaluation left (gord / goff), the arrivals by scanning the two short late
+// lists - into its share of the block's shared memory, and each lane re-runs one LP from the checkpoint.
+constexpr int TMAX = 4;
+struct WTile {
+  uint32_t tile, first, in_buf, nl, nlw, nl_old, nb, idx_ok, nbk[MAXM];
   uint32_t bitmap[TILE / 32];
+};
+struct WHdr {
+  WTile t[TMAX];
+  uint32_t nt, n_aff, round_n;
   uint32_t need[32], offs[32];
 };
 struct WBlk {
@@ -1023,7 +1028,7 @@ DEVA_HD void warp_carve(WBlk &w, const Blk &b, int warp, int n_warps) {
   unsigned char *base = b.pool + (size_t)warp * region;
   size_t o = 0;
   w.h = reinterpret_cast<WHdr *>(base); o += (sizeof(WHdr) + 15) & ~(size_t)15;
-  w.alist = reinterpret_cast<uint16_t *>(base + o); o += TILE * 2;
+  w.alist = reinterpret_cast<uint16_t *>(base + o); o += (size_t)TMAX * TILE * 2;   // entries: slot in t[] * TILE + LP
   const uint32_t cap = ((region - (uint32_t)o) / 35u) & ~7u;   // 32 (record) + 2 (index) + 1 (flags) bytes each
   w.cap = cap;
   w.R = reinterpret_cast<EvRec *>(base + o); o += (size_t)cap * sizeof(EvRec);
@@ -1031,77 +1036,94 @@ DEVA_HD void warp_carve(WBlk &w, const Blk &b, int warp, int n_warps) {
   w.efl = base + o;
 }
 
+// May a warp re-evaluate single LPs of this tile (or does a whole block have to evaluate it again)?
+// Evaluated by the launch that consumes the dirty list, for every tile on it.
+DEVA_HD bool tile_needs_block(const TView &v, const Epoch &ep, uint32_t t) {
+  const bool first = v.tev[t] != ep.epoch;
+  const uint32_t fl = v.tflags[t];
+  const uint32_t nlate = late_count(v.lcnt[0][t], ep.epoch) + late_count(v.lcnt[1][t], ep.epoch);
+  bool heavy = ep.sp_w_n > 0 || ep.sp_r_n > 0 || nlate > LATE_WARP_MAX || (fl & TF_OVF);
+  if (!first) heavy |= !(fl & TF_IDX) || (fl & TF_HEAVY);
+  else {   // not evaluated yet in this epoch: the warp path assumes its buckets are empty
+    for (uint32_t k = 0; k < ep.m; k++) heavy |= v.ncnt[(size_t)t * NB + (uint32_t)((ep.cur_abs + k) % NB)] != 0;
+  }
+  return heavy;
+}
+
 template <class M>
-DEVA_HD void follow_tile_warp(const TView &v, const ModelParams &mp0, const Epoch &ep, Blk &b, WBlk &w, uint32_t tile) {
+DEVA_HD void follow_tiles_warp(const TView &v, const ModelParams &mp0, const Epoch &ep, Blk &b, WBlk &w, const uint32_t *tiles, uint32_t nt) {
   WHdr &h = *w.h;
-#if !defined(__CUDA_ARCH__) && defined(DEVA_TILE_DEBUG)
-  { static unsigned long n_warp_tiles = 0; if ((++n_warp_tiles & 1023) == 1) fprintf(stderr, "warp path tiles: %lu\n", n_warp_tiles); }
-#endif
   ModelParams mp = mp0;
   mp.stop = (int32_t)ep.stop;
   const uint32_t rd = ep.par ^ 1u;
-  const uint64_t tile_gid = v.lp_begin + (uint64_t)tile * TILE;
+  auto live = [&](const EvRec &r) { return !(r.time >= ep.ub || r.time < ep.gvt || (r.flags & EV_DEAD)); };
+  // ---- the tiles' headers (one lane each)
   TL_LANES(lane) {
-    if (lane != 0) continue;
+    if (lane == 0) h.nt = nt;
+    if ((uint32_t)lane >= nt) continue;
+    WTile &t = h.t[lane];
+    const uint32_t tile = tiles[lane];
+    t.tile = tile;
     const uint32_t tev = v.tev[tile];
-    h.first = tev != ep.epoch;
-    h.in_buf = v.tcur[tile];
-    if (h.first && tev != NEVER) { v.tcur[tile] ^= 1u; h.in_buf ^= 1u; }   // (see eval_tile)
+    t.first = tev != ep.epoch;
+    t.in_buf = v.tcur[tile];
+    if (t.first && tev != NEVER) { v.tcur[tile] ^= 1u; t.in_buf ^= 1u; }   // (see eval_tile)
     const uint32_t lc = late_count(v.lcnt[rd][tile], ep.epoch);
-    h.nl = lc < v.CL ? lc : v.CL;
-    h.nlw = h.first ? 0u : v.lseen[ep.par][tile];
-    h.nl_old = h.first ? 0u : v.lseen[rd][tile];
-    h.idx_ok = !h.first && (v.tflags[tile] & TF_IDX);
-    h.nb = 0;
+    t.nl = lc < v.CL ? lc : v.CL;
+    t.nlw = t.first ? 0u : v.lseen[ep.par][tile];
+    t.nl_old = t.first ? 0u : v.lseen[rd][tile];
+    t.idx_ok = !t.first && (v.tflags[tile] & TF_IDX);
+    t.nb = 0;
     for (uint32_t k = 0; k < ep.m; k++) {
       const uint32_t nc = ep.partial ? v.npub[(size_t)tile * MAXM + k] : v.ncnt[(size_t)tile * NB + (uint32_t)((ep.cur_abs + k) % NB)];
-      h.nbk[k] = nc < v.C ? nc : v.C;
-      h.nb += h.nbk[k];
+      t.nbk[k] = nc < v.C ? nc : v.C;
+      t.nb += t.nbk[k];
     }
-    for (int i = 0; i < TILE / 32; i++) h.bitmap[i] = 0;
+    for (int i = 0; i < TILE / 32; i++) t.bitmap[i] = 0;
   }
   TL_WSYNC();
-  const uint32_t out_buf = h.in_buf ^ 1u;
-  const LpState *s_in = v.st[h.in_buf] + (size_t)tile * TILE;
-  const EvRec *late_w = v.late[ep.par] + (size_t)tile * v.CL;
-  const EvRec *late_r = v.late[rd] + (size_t)tile * v.CL;
-  auto live = [&](const EvRec &r) { return !(r.time >= ep.ub || r.time < ep.gvt || (r.flags & EV_DEAD)); };
-  if (h.first) {   // the tile's first evaluation in this epoch: every LP's result starts as its checkpoint
-    TL_LANES(lane) { for (uint32_t i = lane; i < (uint32_t)TILE; i += 32) v.st[out_buf][(size_t)tile * TILE + i] = s_in[i]; }
-    TL_WSYNC();
-  }
-  // ---- affected LPs: destinations of the fresh arrivals
-  TL_LANES(lane) {
-    for (uint32_t i = h.nl_old + lane; i < h.nl; i += 32) {
-      const EvRec r = ld_ev(&late_r[i]);
-      if (!live(r)) continue;
-      const uint32_t lp = (uint32_t)((uint64_t)r.dst - tile_gid);
-      atom_or_u32(&h.bitmap[lp >> 5], 1u << (lp & 31u));
+  for (uint32_t k = 0; k < nt; k++) {
+    const WTile &t = h.t[k];
+    const uint64_t tile_gid = v.lp_begin + (uint64_t)t.tile * TILE;
+    const LpState *s_in = v.st[t.in_buf] + (size_t)t.tile * TILE;
+    if (t.first) {   // the tile's first evaluation in this epoch: every LP's result starts as its checkpoint
+      TL_LANES(lane) { for (uint32_t i = lane; i < (uint32_t)TILE; i += 32) v.st[t.in_buf ^ 1u][(size_t)t.tile * TILE + i] = s_in[i]; }
+    }
+    // affected LPs: destinations of the fresh arrivals
+    const EvRec *late_r = v.late[rd] + (size_t)t.tile * v.CL;
+    TL_LANES(lane) {
+      for (uint32_t i = t.nl_old + lane; i < t.nl; i += 32) {
+        const EvRec r = ld_ev(&late_r[i]);
+        if (!live(r)) continue;
+        const uint32_t lp = (uint32_t)((uint64_t)r.dst - tile_gid);
+        atom_or_u32(&h.t[k].bitmap[lp >> 5], 1u << (lp & 31u));
+      }
     }
   }
   TL_WSYNC();
   TL_LANES(lane) {
     if (lane != 0) continue;
     uint32_t n = 0;
-    for (uint32_t wd = 0; wd < (uint32_t)TILE / 32; wd++)
-      for (uint32_t m = h.bitmap[wd]; m; m &= m - 1) w.alist[n++] = (uint16_t)(wd * 32u + (uint32_t)ffs32(m) - 1u);
+    for (uint32_t k = 0; k < nt; k++)
+      for (uint32_t wd = 0; wd < (uint32_t)TILE / 32; wd++)
+        for (uint32_t m = h.t[k].bitmap[wd]; m; m &= m - 1) w.alist[n++] = (uint16_t)(k * TILE + wd * 32u + (uint32_t)ffs32(m) - 1u);
     h.n_aff = n;
   }
   TL_WSYNC();
   Blk wb = b;   // the walk's view: this warp's records; the block's accumulators
   wb.R = w.R; wb.ord = w.ord; wb.efl = w.efl;
-  const uint32_t *goff = v.goff + (size_t)tile * GOFF;
-  const uint16_t *gord = v.gord + (size_t)tile * v.gr;
   for (uint32_t base = 0; base < h.n_aff;) {
     // how many records each of the next 32 LPs holds
     TL_LANES(lane) {
       uint32_t need = 0;
       if (base + lane < h.n_aff) {
-        const uint32_t lp = w.alist[base + lane];
-        if (h.idx_ok) need = goff[lp + 1] - goff[lp];
-        const uint32_t gd = (uint32_t)(tile_gid + lp);
-        for (uint32_t i = 0; i < h.nlw; i++) need += late_w[i].dst == gd;
-        for (uint32_t i = 0; i < h.nl; i++) need += late_r[i].dst == gd;
+        const WTile &t = h.t[w.alist[base + lane] / TILE];
+        const uint32_t lp = w.alist[base + lane] % TILE;
+        if (t.idx_ok) { const uint32_t *goff = v.goff + (size_t)t.tile * GOFF; need = goff[lp + 1] - goff[lp]; }
+        const uint32_t gd = (uint32_t)(v.lp_begin + (uint64_t)t.tile * TILE + lp);
+        const EvRec *late_w = v.late[ep.par] + (size_t)t.tile * v.CL, *late_r = v.late[rd] + (size_t)t.tile * v.CL;
+        for (uint32_t i = 0; i < t.nlw; i++) need += late_w[i].dst == gd;
+        for (uint32_t i = 0; i < t.nl; i++) need += late_r[i].dst == gd;
       }
       h.need[lane] = need;
     }
@@ -1116,8 +1138,10 @@ DEVA_HD void follow_tile_warp(const TView &v, const ModelParams &mp0, const Epoc
     TL_WSYNC();
     TL_LANES(lane) {
       if ((uint32_t)lane >= h.round_n) continue;
-      const uint32_t lp = w.alist[base + lane];
-      const uint32_t gd = (uint32_t)(tile_gid + lp);
+      const WTile &t = h.t[w.alist[base + lane] / TILE];
+      const uint32_t lp = w.alist[base + lane] % TILE;
+      const uint32_t gd = (uint32_t)(v.lp_begin + (uint64_t)t.tile * TILE + lp);
+      const EvRec *late_w = v.late[ep.par] + (size_t)t.tile * v.CL, *late_r = v.late[rd] + (size_t)t.tile * v.CL;
       const uint32_t s0 = h.offs[lane];
       uint32_t n = s0;
       auto put = [&](const EvRec &r, bool fresh) {
@@ -1127,34 +1151,37 @@ DEVA_HD void follow_tile_warp(const TView &v, const ModelParams &mp0, const Epoc
         w.ord[n] = (uint16_t)n;
         n++;
       };
-      if (h.idx_ok && h.need[lane]) {
+      if (t.idx_ok && h.need[lane]) {
+        const uint32_t *goff = v.goff + (size_t)t.tile * GOFF;
+        const uint16_t *gord = v.gord + (size_t)t.tile * v.gr;
         for (uint32_t j = goff[lp]; j < goff[lp + 1]; j++) {
           uint32_t pos = gord[j], k = 0;
-          while (k + 1 < ep.m && pos >= h.nbk[k]) { pos -= h.nbk[k]; k++; }
-          put(ld_ev(v.near_ + ((size_t)tile * NB + (uint32_t)((ep.cur_abs + k) % NB)) * v.C + pos), false);
+          while (k + 1 < ep.m && pos >= t.nbk[k]) { pos -= t.nbk[k]; k++; }
+          put(ld_ev(v.near_ + ((size_t)t.tile * NB + (uint32_t)((ep.cur_abs + k) % NB)) * v.C + pos), false);
         }
       }
-      for (uint32_t i = 0; i < h.nlw; i++) if (late_w[i].dst == gd) put(ld_ev(&late_w[i]), false);
-      for (uint32_t i = 0; i < h.nl; i++) if (late_r[i].dst == gd) put(ld_ev(&late_r[i]), h.first || i >= h.nl_old);
-      const LpState sin = s_in[lp];
-      run_lp_core<M, false>(v, mp, ep, wb, tile, out_buf, lp, s0, n, sin, false);
+      for (uint32_t i = 0; i < t.nlw; i++) if (late_w[i].dst == gd) put(ld_ev(&late_w[i]), false);
+      for (uint32_t i = 0; i < t.nl; i++) if (late_r[i].dst == gd) put(ld_ev(&late_r[i]), t.first || i >= t.nl_old);
+      const LpState sin = v.st[t.in_buf][(size_t)t.tile * TILE + lp];
+      run_lp_core<M, false>(v, mp, ep, wb, t.tile, t.in_buf ^ 1u, lp, s0, n, sin, false);
     }
     TL_WSYNC();
     base += h.round_n;
   }
   TL_LANES(lane) {
-    if (lane != 0) continue;
-    v.tev[tile] = ep.epoch;
-    v.lseen[rd][tile] = h.nl;
-    v.lseen[ep.par][tile] = h.nlw;
-    if (h.first) {
+    if ((uint32_t)lane >= nt) continue;
+    const WTile &t = h.t[lane];
+    v.tev[t.tile] = ep.epoch;
+    v.lseen[rd][t.tile] = t.nl;
+    v.lseen[ep.par][t.tile] = t.nlw;
+    if (t.first) {
 #if defined(__CUDA_ARCH__)
-      atomicAnd(&v.tflags[tile], (uint32_t)TF_OVF);
+      atomicAnd(&v.tflags[t.tile], (uint32_t)TF_OVF);
 #else
-      v.tflags[tile] &= TF_OVF;
+      v.tflags[t.tile] &= TF_OVF;
 #endif
     }
-    atom_add_u32(&b.h->evals, 1u);
+    if (lane == 0) atom_add_u32(&b.h->evals, nt);
   }
   TL_WSYNC();
 }
@@ -1400,33 +1427,9 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
   // the drain's exit), the consumed buckets' lists are emptied by their tiles in the next launch, and
   // the late lists' counters restart by their epoch tag.
   (void)commit;
-  // ---- a follow-up launch comes next: its tiles are split between warps (a few LPs to re-run from
-  // the index the first evaluation left) and whole blocks (tiles that went the slow way, or hold a lot)
-  if (phase == PH_EVAL && g.dirty_n > 0 && !g.err) {
-    const uint32_t par = c->par, nd = c->dirty_n[par];
-    const bool spill = c->sp_n[0] != 0 || c->sp_n[1] != 0;
-    TL_THREADS(tid) { if (tid == 0) { c->nw_work = 0; c->nb_work = 0; } }
-    TL_SYNC();
-    TL_THREADS(tid) {
-      for (uint32_t i = tid; i < nd; i += TL_NTHR) {
-        const uint32_t t = v.dirty[par][i];
-        const bool first = v.tev[t] != epoch;
-        const uint32_t fl = v.tflags[t];
-        const uint32_t nlate = late_count(v.lcnt[0][t], epoch) + late_count(v.lcnt[1][t], epoch);
-        bool heavy = spill || nlate > LATE_WARP_MAX || (fl & TF_OVF);
-        if (!first) heavy |= !(fl & TF_IDX) || (fl & TF_HEAVY);
-        else {   // not evaluated yet in this epoch: the warp path assumes its buckets are empty
-          for (uint32_t k = 0; k < m; k++) heavy |= v.ncnt[(size_t)t * NB + (uint32_t)((cur + k) % NB)] != 0;
-        }
-        if (heavy) v.blist[atom_add_u32(&c->nb_work, 1u)] = t;
-        else v.wlist[atom_add_u32(&c->nw_work, 1u)] = t;
-      }
-    }
-    TL_SYNC();
-  }
   TL_THREADS(tid) {
     if (tid != 0) continue;
-    c->work = 0; c->ticket = 0; c->launch++;
+    c->work = 0; c->workw = 0; c->workh = 0; c->n_heavy = 0; c->ticket = 0; c->launch++;
     if (c->full || phase == PH_REBIN) c->rc_n = 0;   // every tile has emptied the lists of the window committed before
     c->dirty_n[c->par ^ 1u] = 0;                   // the list this launch consumed
     c->sp_fresh[c->par] = c->sp_start[c->par];     // spill list this launch appended to: its new records start here
@@ -1436,7 +1439,6 @@ DEVA_HD void close_launch(const TView &v, const TParams &tp, const Glob &g) {
     if (phase == PH_EVAL) {
       if (g.dirty_n > 0) {                         // stragglers / anti-messages arrived: follow-up launch over their tiles
         c->full = 0; c->par ^= 1u;
-        c->workw = 0;
         continue;
       }
       for (uint32_t k = 0; k < n_whole; k++) c->btotal[(cur + k) % NB] = 0;
@@ -1469,7 +1471,7 @@ DEVA_HD void begin_drain(const TView &v, const TParams &tp, uint64_t t_end, cons
   TL_THREADS(tid) {
     if (tid != 0) continue;
     c->t_end = t_end;
-    c->work = 0; c->ticket = 0;
+    c->work = 0; c->workw = 0; c->workh = 0; c->n_heavy = 0; c->ticket = 0;
     c->stop = c->stop_req;
     c->pol_epochs = 0; c->e_exec0 = g.executed; c->e_commit0 = g.committed;
     if (c->gvt >= t_end) { c->phase = PH_DONE; continue; }

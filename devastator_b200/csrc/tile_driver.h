@@ -110,10 +110,9 @@ struct TileEngine {
 #define TA(p, n) if ((rc = be.alloc((void **)&(p), (size_t)(n) * sizeof(*(p))))) return rc;
     TA(v.st[0], LP) TA(v.st[1], LP) TA(v.tcur, NT) TA(v.tev, NT) TA(v.tflags, NT)
     TA(v.near_, NT * NB * v.C) TA(v.ncnt, NT * NB) TA(v.npub, NT * MAXM)
-    TA(v.late[0], NT * v.CL) TA(v.late[1], NT * v.CL) TA(v.lcnt[0], NT) TA(v.lcnt[1], NT) TA(v.lseen[0], NT) TA(v.lseen[1], NT) TA(v.dmark, NT)
+    TA(v.late[0], NT * v.CL) TA(v.late[1], NT * v.CL) TA(v.lcnt[0], NT) TA(v.lcnt[1], NT) TA(v.lseen[0], NT) TA(v.lseen[1], NT) TA(v.dmark, NT) TA(v.tdone, NT)
     TA(v.far_, NT * v.CF) TA(v.fcnt, NT) TA(v.fpub, NT)
     TA(v.dirty[0], NT) TA(v.dirty[1], NT) TA(v.ctl, 1)
-    TA(v.wlist, NT) TA(v.blist, NT)
     v.gr = (tp.rcap + 7u) & ~7u;
     TA(v.gord, NT * v.gr) TA(v.goff, NT * GOFF)
     v.SP = env_u32("DEVA_B200_TILE_SPILL", (uint32_t)std::max<size_t>(65536, 4 * (size_t)v.A));
@@ -158,10 +157,10 @@ struct TileEngine {
     const size_t NT = v.NT;
     if ((rc = be.zero(v.ncnt, NT * NB * 4)) || (rc = be.zero(v.fcnt, NT * 4)) || (rc = be.zero(v.fpub, NT * 4)) ||
         (rc = be.zero(v.lcnt[0], NT * 8)) || (rc = be.zero(v.lcnt[1], NT * 8)) || (rc = be.zero(v.tflags, NT * 4)) ||
-        (rc = be.zero(v.tcur, NT * 4)) || (rc = be.fill_ff(v.tev, NT * 4)) || (rc = be.fill_ff(v.dmark, NT * 4)))
+        (rc = be.zero(v.tcur, NT * 4)) || (rc = be.fill_ff(v.tev, NT * 4)) || (rc = be.fill_ff(v.dmark, NT * 4)) || (rc = be.fill_ff(v.tdone, NT * 4)))
       return rc;
     hc.cur_abs = 0; hc.ub = 0; hc.gvt = 0; hc.t_end = 0; hc.far_min = ~0ull; hc.phase = PH_IDLE; hc.full = 0; hc.par = 0;
-    hc.workw = hc.nw_work = hc.nb_work = 0; hc.in_epoch = 0; hc.partial = 0; hc.rc_n = 0; hc.rc_lo = 0; hc.ring_hi = NB; hc.work = hc.ticket = 0; hc.dirty_n[0] = hc.dirty_n[1] = 0; for (int i = 0; i < 2; i++) hc.sp_n[i] = hc.sp_start[i] = hc.sp_fresh[i] = 0; hc.ovf_flag = hc.need_rebase = 0;
+    hc.workw = hc.workh = hc.n_heavy = 0; hc.in_epoch = 0; hc.partial = 0; hc.rc_n = 0; hc.rc_lo = 0; hc.ring_hi = NB; hc.work = hc.ticket = 0; hc.dirty_n[0] = hc.dirty_n[1] = 0; for (int i = 0; i < 2; i++) hc.sp_n[i] = hc.sp_start[i] = hc.sp_fresh[i] = 0; hc.ovf_flag = hc.need_rebase = 0;
     for (int i = 0; i < NB; i++) hc.btotal[i] = 0;
     hc.far_total = 0; hc.antis_pending = 0; hc.err = 0; hc.nondet = 0;
     hc.want_shift = hc.shift;

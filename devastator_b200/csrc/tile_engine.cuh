@@ -83,33 +83,82 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
   __syncthreads();
   const Epoch ep = load_epoch(c);
   const bool all_tiles = phase == PH_REBIN || c->full;
-  const uint32_t n_work = all_tiles ? v.NT : c->nb_work;   // follow-up launch: the tiles re-evaluated by whole blocks
-  const uint32_t rebin_all = c->rebin_all;
-  for (;;) {
-    const uint32_t w = b.h->next_item;
-    __syncthreads();
-    if (w >= n_work) break;
-    if (threadIdx.x == 0) b.h->next_item = atomicAdd(&c->work, 1u);   // (its round trip hides behind this tile's work)
-    const uint32_t tile = all_tiles ? w : v.blist[w];
-    if (phase == PH_EVAL) eval_tile<M, FULLK>(v, mp, ep, b, tile);
-    else rebin_tile(v, ep, b, tile, v.scratch + (size_t)blockIdx.x * v.scratch_cap, rebin_all);
-    __syncthreads();
-  }
-  if (!FULLK && phase == PH_EVAL && !all_tiles) {
-    // follow-up launch: the other tiles, one warp each, re-running only the LPs that received something
-    __syncthreads();
-    WBlk wk;
-    warp_carve(wk, b, (int)(threadIdx.x >> 5), NTHR / 32);
-    const uint32_t nw = c->nw_work;
-    const int lane = (int)(threadIdx.x & 31);
+  if (all_tiles) {
+    const uint32_t rebin_all = c->rebin_all;
     for (;;) {
-      uint32_t wi = 0;
-      if (lane == 0) wi = atomicAdd(&c->workw, 1u);
-      wi = __shfl_sync(0xffffffffu, wi, 0);
-      if (wi >= nw) break;
-      follow_tile_warp<M>(v, mp, ep, b, wk, v.wlist[wi]);
+      const uint32_t w = b.h->next_item;
+      __syncthreads();
+      if (w >= v.NT) break;
+      if (threadIdx.x == 0) b.h->next_item = atomicAdd(&c->work, 1u);   // (its round trip hides behind this tile's work)
+      if (phase == PH_EVAL) eval_tile<M, FULLK>(v, mp, ep, b, w);
+      else rebin_tile(v, ep, b, w, v.scratch + (size_t)blockIdx.x * v.scratch_cap, rebin_all);
+      __syncthreads();
+    }
+  } else if (!FULLK) {
+    // ---- follow-up launch: the tiles that received in-window arrivals during the previous launch.
+    // Pass 1, warps on their own (no block barrier): a warp pulls a few tiles off the list, one lane classifies
+    // each (tile_needs_block), and the warp re-runs only the LPs of the light ones that received something -
+    // as many tiles at a time as fill its lanes.  Pass 2, blocks: the tiles nobody has claimed - the ones that must
+    // be evaluated again as a whole - are evaluated by whole blocks.  A tile is claimed through tdone (the
+    // launch's serial), so the two passes of different blocks may overlap in time.
+    constexpr uint32_t NW = NTHR / 32;
+    const uint32_t rdl = ep.par ^ 1u, nd = c->dirty_n[rdl];
+    const uint32_t *dl = v.dirty[rdl];
+    uint32_t per_warp = nd / (gridDim.x * NW);   // tiles pulled at a time: as many as keep every warp of the grid busy
+    per_warp = per_warp < 1u ? 1u : (per_warp > (uint32_t)TMAX ? (uint32_t)TMAX : per_warp);
+    __shared__ uint32_t w_tile[NW][TMAX], w_fresh[NW][TMAX];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    WBlk wk;
+    warp_carve(wk, b, (int)wid, (int)NW);
+    __syncthreads();
+    for (;;) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&c->workw, per_warp);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= nd) break;
+      const uint32_t n = nd - base < per_warp ? nd - base : per_warp;
+      if (lane < n) {
+        const uint32_t t = dl[base + lane];
+        uint32_t fresh = 0xffffffffu;              // (= not this warp's: heavy, or claimed by a block already)
+        if (!tile_needs_block(v, ep, t)) {
+          if (atomicExch(&v.tdone[t], ep.launch) != ep.launch) {
+            const uint32_t lc = late_count(v.lcnt[rdl][t], ep.epoch), seen = v.tev[t] != ep.epoch ? 0u : v.lseen[rdl][t];
+            fresh = (lc < v.CL ? lc : v.CL) - seen;
+          }
+        } else atomicAdd(&c->n_heavy, 1u);
+        w_tile[wid][lane] = t; w_fresh[wid][lane] = fresh;
+      }
+      __syncwarp();
+      // sub-batches: as many consecutive light tiles as fill the lanes (one lane per affected LP, at most one per fresh arrival)
+      for (uint32_t i = 0; i < n;) {
+        if (w_fresh[wid][i] == 0xffffffffu) { i++; continue; }
+        uint32_t j = i, sum = 0;
+        while (j < n && w_fresh[wid][j] != 0xffffffffu && (j == i || sum + w_fresh[wid][j] <= 32u)) { sum += w_fresh[wid][j]; j++; }
+        follow_tiles_warp<M>(v, mp, ep, b, wk, &w_tile[wid][i], j - i);
+        i = j;
+      }
+      __syncwarp();
     }
     __syncthreads();
+    if (c->n_heavy) {   // (some warp of the grid met a tile for a whole block - the block that did will come by here)
+      for (;;) {
+        if (threadIdx.x == 0) b.h->work_item = atomicAdd(&c->workh, (uint32_t)NTHR);
+        __syncthreads();
+        const uint32_t base = b.h->work_item;
+        if (base >= nd) break;
+        const uint32_t n = nd - base < (uint32_t)NTHR ? nd - base : (uint32_t)NTHR;
+        __shared__ uint32_t todo[NTHR], n_todo;
+        if (threadIdx.x == 0) n_todo = 0;
+        __syncthreads();
+        if (threadIdx.x < n) {
+          const uint32_t t = dl[base + threadIdx.x];
+          if (atomicExch(&v.tdone[t], ep.launch) != ep.launch) todo[atomicAdd(&n_todo, 1u)] = t;
+        }
+        __syncthreads();
+        for (uint32_t i = 0; i < n_todo; i++) { eval_tile<M, false>(v, mp, ep, b, todo[i]); __syncthreads(); }
+        __syncthreads();
+      }
+    }
   }
   if (threadIdx.x == 0) {
     blk_flush(v, b);

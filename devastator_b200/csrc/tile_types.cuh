@@ -93,7 +93,7 @@ struct TCtl {
   uint32_t rc_n, rc_pad;           // ... and how many of its buckets were consumed to their end (their lists are to be emptied)
   // ---- work distribution within a launch
   uint32_t work, ticket;
-  uint32_t workw, nw_work, nb_work, wpad;   // follow-up launch: next warp item; tiles for warps; tiles for blocks
+  uint32_t workw, workh, n_heavy, wpad;     // follow-up launch: next list position for the warps / for the blocks; tiles met that need a whole block
   uint32_t dirty_n[2];
   uint32_t sp_n[2], sp_start[2], sp_fresh[2];   // spill lists: records; count when the list's last launch began; first record of that launch
   uint32_t ovf_flag, need_rebase;
@@ -133,9 +133,9 @@ struct TView {
   EvRec *near_; uint32_t *ncnt, *npub;   // npub[NT][MAXM]: the open buckets' record counts when their epoch began (what evaluations read)
   EvRec *late[2]; unsigned long long *lcnt[2]; uint32_t *lseen[2];   // lcnt: epoch << 32 | records (restarts with every epoch);   // lseen: how many of a late list's records the tile's last evaluation saw
   uint32_t *dmark;                 // per tile: serial of the launch that last queued it for re-evaluation
+  uint32_t *tdone;                 // per tile: serial of the follow-up launch in which a warp or a block claimed it
   EvRec *far_; uint32_t *fcnt, *fpub;   // fpub: a tile's far count as of the last rebin (those records are complete)
   uint32_t *dirty[2];              // tiles that received in-window arrivals during a launch
-  uint32_t *wlist, *blist;         // ... split for the next launch: re-evaluated by one warp each / by a whole block (heavy)
   uint16_t *gord; uint32_t *goff;  // [NT][rcap], [NT][GOFF]: the window's records grouped by LP (positions in the bucket lists), left by
   uint32_t gr;                     //   a tile's first evaluation for the warps that re-evaluate single LPs; gr = row length of gord
   EvRec *spill[2]; uint32_t SP;    // in-window arrivals beyond a late list's capacity (any tile), kept for the epoch like the late lists

@@ -110,28 +110,54 @@ struct HostBE {
     if (phase != PH_EVAL && phase != PH_REBIN) return false;
     const Epoch ep = load_epoch(c);
     const bool all_tiles = phase == PH_REBIN || c->full;
-    std::vector<uint32_t> work, wwork;
+    std::vector<uint32_t> work;
+    const uint32_t rdl = ep.par ^ 1u;
     if (all_tiles) { work.resize(v.NT); for (uint32_t i = 0; i < v.NT; i++) work[i] = i; }
-    else { work.assign(v.blist, v.blist + c->nb_work); wwork.assign(v.wlist, v.wlist + c->nw_work); }
-    auto shuf = [&](std::vector<uint32_t> &x) {   // the order blocks / warps pick up tiles in is not defined on the GPU either
-      if (!shuffle || x.size() < 2) return;
-      uint64_t s = shuffle * 0x9E3779B97F4A7C15ull + (++launch_no);
-      for (size_t i = x.size(); i > 1; i--) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; std::swap(x[i - 1], x[s % i]); }
-    };
-    shuf(work); shuf(wwork);
+    else work.assign(v.dirty[rdl], v.dirty[rdl] + c->dirty_n[rdl]);
+    // the order blocks / warps pick up tiles in is not defined on the GPU either
+    uint64_t sd = shuffle * 0x9E3779B97F4A7C15ull + (++launch_no);
+    auto rnd = [&]() { sd ^= sd << 13; sd ^= sd >> 7; sd ^= sd << 17; return sd; };
+    if (shuffle && work.size() > 1) for (size_t i = work.size(); i > 1; i--) std::swap(work[i - 1], work[rnd() % i]);
     Blk b = workspace(tp.rcap);
     const uint32_t rebin_all = c->rebin_all;
     blk_begin(b);
     size_t done = 0;
-    for (uint32_t tile : work) {
-      if (phase == PH_EVAL) { if (c->full) eval_tile<M, true>(v, mp, ep, b, tile); else eval_tile<M, false>(v, mp, ep, b, tile); }
-      else rebin_tile(v, ep, b, tile, v.scratch, rebin_all);
-      if (++done % 3 == 0) { blk_flush(v, b); blk_begin(b); }   // (several "blocks" share the launch)
-    }
-    if (!wwork.empty()) {   // follow-up launch: tiles re-evaluated by one warp each (a warp's share of the block's workspace)
-      WBlk wk;
-      warp_carve(wk, b, (int)(launch_no % (NTHR / 32)), NTHR / 32);
-      for (uint32_t tile : wwork) follow_tile_warp<M>(v, mp, ep, b, wk, tile);
+    if (all_tiles) {
+      for (uint32_t tile : work) {
+        if (phase == PH_EVAL) eval_tile<M, true>(v, mp, ep, b, tile);
+        else rebin_tile(v, ep, b, tile, v.scratch, rebin_all);
+        if (++done % 3 == 0) { blk_flush(v, b); blk_begin(b); }   // (several "blocks" share the launch)
+      }
+    } else {
+      // follow-up launch, as the kernel does it: pass 1 - "warps" pull a few tiles at a time, claim the light
+      // ones and re-run their affected LPs (a warp's share of the block's workspace); pass 2 - the tiles nobody
+      // claimed are evaluated by the "block"
+      constexpr uint32_t NW = NTHR / 32;
+      for (size_t base = 0; base < work.size();) {
+        const uint32_t per_warp = shuffle ? 1u + (uint32_t)(rnd() % TMAX) : 1u;
+        const size_t n = std::min<size_t>(per_warp, work.size() - base);
+        std::vector<uint32_t> light;
+        for (size_t i = 0; i < n; i++) {
+          const uint32_t t = work[base + i];
+          if (tile_needs_block(v, ep, t)) { c->n_heavy++; continue; }
+          if (v.tdone[t] != ep.launch) { v.tdone[t] = ep.launch; light.push_back(t); }
+        }
+        if (!light.empty()) {
+          WBlk wk;
+          warp_carve(wk, b, (int)(rnd() % NW), (int)NW);
+          follow_tiles_warp<M>(v, mp, ep, b, wk, light.data(), (uint32_t)light.size());
+        }
+        base += n;
+        if (++done % 3 == 0) { blk_flush(v, b); blk_begin(b); }
+      }
+      if (c->n_heavy) {
+        for (uint32_t t : work) {
+          if (v.tdone[t] == ep.launch) continue;
+          v.tdone[t] = ep.launch;
+          eval_tile<M, false>(v, mp, ep, b, t);
+          if (++done % 3 == 0) { blk_flush(v, b); blk_begin(b); }
+        }
+      }
     }
     blk_flush(v, b);
     return true;
