@@ -42,6 +42,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries ONE JSON line: NCCL's banner ("NCCL version ...", printed at NCCL_DEBUG=VERSION) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 K_ROOTS = 16
 LAMBDA = 100.0
@@ -116,9 +118,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line)
+            self.lines.append((time.perf_counter(), line))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """median SM clock / reasons over the samples that arrived inside [t0, t1] (the timed region; the
+        sampler is started before the warm-up so that nvidia-smi is already streaming by then)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         self.proc.terminate()
@@ -126,21 +130,29 @@ class ClockSampler:
             self.proc.wait(timeout=3)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+
+        def digest(lines):
+            sm, mx, reasons = [], [], set()
+            for _, line in lines:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sm, mx, reasons
+        inside = [x for x in self.lines if t0 is None or (t0 <= x[0] <= t1 + 0.12)]
+        window = "timed region"
+        if not digest(inside)[0]:       # a timed region shorter than the sampling period: the samples around it (warm-up = same load)
+            inside, window = self.lines, "warm-up + timed region (the timed region was shorter than the 100 ms sampling period)"
+        sm, mx, reasons = digest(inside)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 # ---- the reference on the host cores -------------------------------------------------------------
@@ -310,13 +322,13 @@ def ours(args):
         K, W = args.steps, args.warmup
 
         # ---- value: inputs resident in HBM, drains timed with CUDA events on the engine's stream
+        sampler = ClockSampler(local) if (headline and rank == 0) else None
+        if sampler:
+            sampler.start()
         for _ in range(W):
             eng.seed_phold(K_ROOTS, 1, 1)
             eng.drain()
         sync_all()
-        sampler = ClockSampler(local) if (headline and rank == 0) else None
-        if sampler:
-            sampler.start()
         s0 = eng.stats()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         seed_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -334,7 +346,7 @@ def ours(args):
         sync_all()
         t_wall = time.perf_counter() - t_wall0
         s1 = eng.stats()
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t_wall0, t_wall0 + t_wall) if sampler else None
         ms = allmax(sum(a.elapsed_time(b) for a, b in evs))
         seed_ms = allmax(sum(a.elapsed_time(b) for a, b in seed_evs))
         d = eng.digest()

@@ -7,6 +7,8 @@
 // (replaces gvt.cxx:53-149 - with a synchronous window there are no messages in flight at the
 // reduction point, so the epoch/credit machinery collapses to a min).
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -59,6 +61,10 @@ static bool want_tile() { const char *k = getenv("DEVA_B200_ENGINE"); return !(k
 
 // ------------------------------------------------------------------------------------------------
 // kernels
+__global__ void k_clear_sticky(Ctl *c) {
+  c->cnt[threadIdx.x][CNT_FLAGS] = 0;
+  if (threadIdx.x == 0) { c->err = 0; c->spill_n = 0; c->wake_n[0] = c->wake_n[1] = 0; for (int i = 0; i < MAX_GPUS; i++) c->send_n[i] = 0; }
+}
 constexpr int PASS_THREADS = 128;
 
 // MINB = minimum resident blocks per SM the register allocator must allow (occupancy knob)
@@ -262,6 +268,7 @@ struct CtlSum { uint64_t gvt_next, executed, committed, rolled_back, anti_sent, 
 
 // ------------------------------------------------------------------------------------------------
 struct deva_b200_engine {
+  std::atomic<int32_t> stop_flag{0};   // bench PHOLD cut-off (set by another thread: the drop-in's watchdog); copied into mp per launch
   CudaTile *tile = nullptr;
   deva_b200_config cfg;
   ModelParams mp;
@@ -388,6 +395,19 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
     return fail(DEVA_B200_ERR_ARG, "bad LP partition");
   if (cfg->n_gpus < 1 || cfg->n_gpus > MAX_GPUS || cfg->gpu_rank < 0 || cfg->gpu_rank >= cfg->n_gpus)
     return fail(DEVA_B200_ERR_ARG, "bad n_gpus/gpu_rank");
+  if (cfg->n_gpus > 1) {
+    // cross-GPU routing is owner(lp) = lp / ceil(lp_n / n_gpus): the caller's partition must be that one
+    const uint64_t per = (cfg->lp_n + cfg->n_gpus - 1) / cfg->n_gpus, first = per * (uint64_t)cfg->gpu_rank;
+    if (first >= cfg->lp_n)
+      return fail(DEVA_B200_ERR_ARG, "lp_n = %llu leaves GPU %d of %d without LPs (block partition of ceil(lp_n / n_gpus) = %llu LPs per GPU): use fewer GPUs",
+                  (unsigned long long)cfg->lp_n, cfg->gpu_rank, cfg->n_gpus, (unsigned long long)per);
+    const uint64_t cnt = cfg->lp_n - first < per ? cfg->lp_n - first : per;
+    if (cfg->lp_begin != first || cfg->lp_count != cnt)
+      return fail(DEVA_B200_ERR_ARG, "LP partition [%llu, +%llu) of GPU %d is not the block partition the routing assumes: [%llu, +%llu)",
+                  (unsigned long long)cfg->lp_begin, (unsigned long long)cfg->lp_count, cfg->gpu_rank, (unsigned long long)first, (unsigned long long)cnt);
+  }
+  if (cfg->log_cap > 65535) return fail(DEVA_B200_ERR_ARG, "log_cap must be < 65536");
+  if (!want_tile() && cfg->pq_cap > MAX_PQ_CAP) return fail(DEVA_B200_ERR_ARG, "pq_cap must be <= %d", MAX_PQ_CAP);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(DEVA_B200_ERR_CUDA, "no CUDA device: this engine has no CPU path");
@@ -417,8 +437,6 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   v.pq_cap = cfg->pq_cap > 0 ? cfg->pq_cap : 64;
   v.ib_cap = cfg->inbox_cap > 0 ? cfg->inbox_cap : 16;
   v.log_cap = cfg->log_cap > 0 ? cfg->log_cap : 48;
-  if (v.log_cap > 65535) return fail(DEVA_B200_ERR_ARG, "log_cap must be < 65536");
-  if (v.pq_cap > MAX_PQ_CAP) return fail(DEVA_B200_ERR_ARG, "pq_cap must be <= %d", MAX_PQ_CAP);
   v.lp_begin = cfg->lp_begin;
   v.lp_n = cfg->lp_n;
   v.n_gpus = cfg->n_gpus;
@@ -427,6 +445,15 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
   const size_t A = v.A;
   int rc = 0;
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n)))) { deva_b200_destroy(e); return rc; }
+  // (a CUDA failure after the engine exists: free what was allocated so far)
+#define CUD(call)                                                                                                      \
+  do {                                                                                                                 \
+    cudaError_t _e = (call);                                                                                           \
+    if (_e != cudaSuccess) {                                                                                           \
+      deva_b200_destroy(e);                                                                                            \
+      return fail(DEVA_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__);   \
+    }                                                                                                                  \
+  } while (0)
   DA(v.head, A) DA(v.pcnt, A) DA(v.icnt[0], A) DA(v.icnt[1], A) DA(v.lmeta, A)
   DA(v.st, A * e->stw) DA(v.seq, A) DA(v.lct, A) DA(v.lcs, A)
   DA(v.pq_t, A * v.pq_cap) DA(v.pq_r, A * v.pq_cap) DA(v.ib[0], A * v.ib_cap) DA(v.ib[1], A * v.ib_cap) DA(v.lg, A * v.log_cap)
@@ -447,26 +474,27 @@ int deva_b200_create(const deva_b200_config *cfg, deva_b200_engine **out) {
     DA(e->recvbuf, (size_t)v.send_cap * cfg->n_gpus)
     DA(e->d_counts, MAX_GPUS * MAX_GPUS)
     DA(e->d_red, 32 + 8 * MAX_GPUS)
-    CU(cudaHostAlloc((void **)&e->h_counts, MAX_GPUS * MAX_GPUS * sizeof(uint32_t), cudaHostAllocDefault));
-    CU(cudaHostAlloc((void **)&e->h_red, 8 * MAX_GPUS * sizeof(unsigned long long), cudaHostAllocDefault));
+    CUD(cudaHostAlloc((void **)&e->h_counts, MAX_GPUS * MAX_GPUS * sizeof(uint32_t), cudaHostAllocDefault));
+    CUD(cudaHostAlloc((void **)&e->h_red, 8 * MAX_GPUS * sizeof(unsigned long long), cudaHostAllocDefault));
   }
 #undef DA
-  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  CU(cudaEventCreate(&e->ev_a));
-  CU(cudaEventCreate(&e->ev_b));
-  CU(cudaEventCreate(&e->ev_d0));
-  CU(cudaEventCreate(&e->ev_d1));
-  CU(cudaHostAlloc((void **)&e->h_ctl, sizeof(Ctl), cudaHostAllocDefault));
-  CU(cudaMemsetAsync(v.ctl, 0, sizeof(Ctl), e->stream));
-  CU(cudaMemsetAsync(v.wmark, 0, A * sizeof(uint32_t), e->stream));
+  CUD(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUD(cudaEventCreate(&e->ev_a));
+  CUD(cudaEventCreate(&e->ev_b));
+  CUD(cudaEventCreate(&e->ev_d0));
+  CUD(cudaEventCreate(&e->ev_d1));
+  CUD(cudaHostAlloc((void **)&e->h_ctl, sizeof(Ctl), cudaHostAllocDefault));
+  CUD(cudaMemsetAsync(v.ctl, 0, sizeof(Ctl), e->stream));
+  CUD(cudaMemsetAsync(v.wmark, 0, A * sizeof(uint32_t), e->stream));
   const int grid = (int)((A + 255) / 256);
   dispatch_model(cfg->model, [&](auto m) {
     using M = decltype(m);
     k_init<M><<<grid, 256, 0, e->stream>>>(v, e->mp, 0);
     return 0;
   });
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(e->stream));
+  CUD(cudaGetLastError());
+  CUD(cudaStreamSynchronize(e->stream));
+#undef CUD
   e->wp.init(cfg->window);
   const char *prof = getenv("DEVA_B200_PROFILE");
   if (prof) e->profile = atoi(prof) != 0;
@@ -623,6 +651,10 @@ int deva_b200_reset(deva_b200_engine *e) {
   });
   e->launches++;
   CU(cudaGetLastError());
+  // finalize + init: errors, the non-determinism flag and the transient lists do not survive (cumulative
+  // statistics do: pdes::local_stats keeps counting across init / finalize in the reference, too)
+  k_clear_sticky<<<1, CTL_SLOTS, 0, e->stream>>>(e->v.ctl);
+  CU(cudaGetLastError());
   e->par = 0;
   e->has_rewind = false;
   return 0;
@@ -631,7 +663,7 @@ int deva_b200_reset(deva_b200_engine *e) {
 int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) {
   if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
   if (e->tile) { e->tile->stop_req.store(stop); return 0; }
-  e->mp.stop = stop;
+  e->stop_flag.store(stop, std::memory_order_relaxed);
   return 0;
 }
 
@@ -701,6 +733,7 @@ static int allreduce_pass(deva_b200_engine *e, bool pack_on_device, uint32_t par
 
 static int launch_pass(deva_b200_engine *e, const PassArgs &pa, uint32_t list_n) {
   const int grid = (int)(((list_n ? list_n : e->v.A) + PASS_THREADS - 1) / PASS_THREADS);
+  e->mp.stop = e->stop_flag.load(std::memory_order_relaxed);
   if (e->profile) CU(cudaEventRecord(e->ev_a, e->stream));
   dispatch_model(e->cfg.model, [&](auto m) {
     using M = decltype(m);
