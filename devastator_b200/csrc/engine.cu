@@ -1045,6 +1045,31 @@ static int tile_comm_init(deva_b200_engine *e, const NcclUid &uid) {
   return 0;
 }
 
+int deva_b200_comm_init_group(deva_b200_engine **es, int32_t n) {
+  if (!es || n < 1) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (n == 1) return 0;
+  for (int g = 0; g < n; g++) {
+    if (!es[g] || !es[g]->tile) return fail(DEVA_B200_ERR_STATE, "engines that share a process need the tile engine (DEVA_B200_ENGINE unset)");
+    if (es[g]->cfg.n_gpus != n || es[g]->cfg.gpu_rank != g) return fail(DEVA_B200_ERR_ARG, "engine %d was created with n_gpus = %d, gpu_rank = %d", g, es[g]->cfg.n_gpus, es[g]->cfg.gpu_rank);
+  }
+  for (int g = 0; g < n; g++) {
+    CU(cudaSetDevice(es[g]->cfg.device));
+    for (int d = 0; d < n; d++) {
+      if (d == g) continue;
+      if (es[d]->cfg.device == es[g]->cfg.device) return fail(DEVA_B200_ERR_ARG, "engines %d and %d share device %d", g, d, es[g]->cfg.device);
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, es[g]->cfg.device, es[d]->cfg.device));
+      if (!can) return fail(DEVA_B200_ERR_COMM, "GPU %d cannot access GPU %d's memory (no peer access)", es[g]->cfg.device, es[d]->cfg.device);
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(es[d]->cfg.device, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(DEVA_B200_ERR_COMM, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(pe));
+      cudaGetLastError();
+      es[g]->tile->map_peer(d, es[d]->tile->comm_block);
+    }
+    es[g]->tile->peers_ready();
+  }
+  return 0;
+}
+
 int deva_b200_comm_init(deva_b200_engine *e, const void *uid128) {
   if (!e || !uid128) return fail(DEVA_B200_ERR_ARG, "null argument");
   if (e->cfg.n_gpus == 1) return 0;

@@ -250,7 +250,9 @@ namespace {
     std::uint64_t lp_n = 0;
     const pdes::model_binding *model = nullptr;
     bool user_subtime = false;
-    deva_b200_engine *eng = nullptr;
+    deva_b200_engine *eng = nullptr;           // engine 0 (the only one unless DEVA_B200_GPUS > 1)
+    std::vector<deva_b200_engine*> engs;       // one engine per GPU, LPs block-partitioned (ceil(lp_n / GPUs) each)
+    std::uint64_t lp_per_gpu = 0;
     bool has_rewind = false;
     pdes::statistics stats;      // cumulative since init; read after finalize (test/phold.cxx:201-204)
     std::uint64_t gvt = 0;
@@ -289,10 +291,19 @@ namespace {
       }
     }
   }
+  // LPs [first, first + count) of engine g
+  void gpu_range(std::size_t g, std::uint64_t &first, std::uint64_t &count) {
+    first = g_sim.lp_per_gpu*g;
+    count = std::min<std::uint64_t>(g_sim.lp_per_gpu, g_sim.lp_n - first);
+  }
   void download_state() {
     const int stw = deva_b200_state_words(g_sim.eng);
     std::vector<std::uint64_t> words(std::size_t(g_sim.lp_n)*stw);
-    ck(deva_b200_get_lp_state(g_sim.eng, 0, g_sim.lp_n, words.data()), "deva_b200_get_lp_state");
+    for(std::size_t g = 0; g < g_sim.engs.size(); g++) {
+      std::uint64_t first, count;
+      gpu_range(g, first, count);
+      ck(deva_b200_get_lp_state(g_sim.engs[g], first, count, words.data() + first*stw), "deva_b200_get_lp_state");
+    }
     scatter_state(words, stw);
   }
 }
@@ -355,61 +366,97 @@ std::uint64_t pdes::drain(std::uint64_t t_end, bool rewindable) {   // pdes.cxx:
     DEVA_ASSERT_ALWAYS(!g_sim.has_rewind, "Lingering rewind state must be rewound via pdes::rewind(true|false) before calling pdes::drain().");
     if(!g_sim.eng) {
       if(!g_sim.model) pdes::detail::no_device_model("pdes::drain (no root event was ever inserted through a device model)");
-      deva_b200_config cfg;
-      std::memset(&cfg, 0, sizeof cfg);
-      cfg.abi_version = DEVA_B200_ABI_VERSION;
-      cfg.model = g_sim.model->model_id;
-      cfg.device = deva::os_env<int>("DEVA_B200_DEVICE", 0);
-      cfg.n_gpus = 1; cfg.gpu_rank = 0;
-      cfg.pq_cap = deva::os_env<int>("DEVA_B200_PQ_CAP", 0);
-      cfg.inbox_cap = deva::os_env<int>("DEVA_B200_INBOX_CAP", 0);
-      cfg.log_cap = deva::os_env<int>("DEVA_B200_LOG_CAP", 0);
-      cfg.lp_n = g_sim.lp_n; cfg.lp_begin = 0; cfg.lp_count = g_sim.lp_n;
-      const long long look = deva::os_env<long long>("deva_static_look_dt", -1);   // pdes.cxx:36
-      cfg.window = look > 0 ? std::uint64_t(look) : 0;
-      g_sim.model->fill(&cfg.mp, deva::rank_n, g_sim.lp_n);
-      cfg.mp.user_subtime = g_sim.user_subtime ? 1 : 0;
-      ck(deva_b200_create(&cfg, &g_sim.eng), "deva_b200_create");
+      // DEVA_B200_GPUS = N: LPs block-partitioned over N GPUs of this process (one engine and, during a drain,
+      // one host thread per GPU; the GPUs exchange events and close every round among themselves over NVLink) -
+      // the counterpart of the reference's rank threads / processes (world_gasnet.hxx:46-55)
+      int n_gpus = deva::os_env<int>("DEVA_B200_GPUS", 1);
+      if(n_gpus < 1) n_gpus = 1;
+      while(n_gpus > 1 && (g_sim.lp_n + n_gpus - 1)/n_gpus*std::uint64_t(n_gpus - 1) >= g_sim.lp_n) n_gpus--;   // (every GPU owns at least one LP)
+      g_sim.lp_per_gpu = (g_sim.lp_n + n_gpus - 1)/n_gpus;
+      const int dev0 = deva::os_env<int>("DEVA_B200_DEVICE", 0);
+      g_sim.engs.assign(std::size_t(n_gpus), nullptr);
+      for(int g = 0; g < n_gpus; g++) {
+        deva_b200_config cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.abi_version = DEVA_B200_ABI_VERSION;
+        cfg.model = g_sim.model->model_id;
+        cfg.device = dev0 + g;
+        cfg.n_gpus = n_gpus; cfg.gpu_rank = g;
+        cfg.pq_cap = deva::os_env<int>("DEVA_B200_PQ_CAP", 0);
+        cfg.inbox_cap = deva::os_env<int>("DEVA_B200_INBOX_CAP", 0);
+        cfg.log_cap = deva::os_env<int>("DEVA_B200_LOG_CAP", 0);
+        cfg.lp_n = g_sim.lp_n;
+        gpu_range(std::size_t(g), cfg.lp_begin, cfg.lp_count);
+        const long long look = deva::os_env<long long>("deva_static_look_dt", -1);   // pdes.cxx:36
+        cfg.window = look > 0 ? std::uint64_t(look) : 0;
+        g_sim.model->fill(&cfg.mp, deva::rank_n, g_sim.lp_n);
+        cfg.mp.user_subtime = g_sim.user_subtime ? 1 : 0;
+        ck(deva_b200_create(&cfg, &g_sim.engs[std::size_t(g)]), "deva_b200_create");
+      }
+      g_sim.eng = g_sim.engs[0];
+      ck(deva_b200_comm_init_group(g_sim.engs.data(), n_gpus), "deva_b200_comm_init_group");
     }
     const int stw = deva_b200_state_words(g_sim.eng);
     DEVA_ASSERT_ALWAYS(stw == g_sim.model->state_words);
     std::vector<std::uint64_t> words;
     gather_state(words, stw);
-    ck(deva_b200_set_lp_state(g_sim.eng, 0, g_sim.lp_n, words.data()), "deva_b200_set_lp_state");
-    std::vector<std::uint64_t> t, s; std::vector<std::uint32_t> lp, pay;
+    const std::size_t G = g_sim.engs.size();
+    std::vector<std::vector<std::uint64_t>> t(G), sb(G); std::vector<std::vector<std::uint32_t>> lp(G), pay(G);
     for(auto &rs: g_sim.ranks) {
-      for(auto &r: rs.roots) { t.push_back(r.time); s.push_back(r.sub); lp.push_back(r.lp); pay.push_back(r.payload); }
+      for(auto &r: rs.roots) {
+        const std::size_t g = std::size_t(r.lp/g_sim.lp_per_gpu);
+        t[g].push_back(r.time); sb[g].push_back(r.sub); lp[g].push_back(r.lp); pay[g].push_back(r.payload);
+      }
       rs.roots.clear();
     }
-    if(!t.empty()) ck(deva_b200_root_events(g_sim.eng, t.size(), t.data(), s.data(), lp.data(), pay.data()), "deva_b200_root_events");
+    for(std::size_t g = 0; g < G; g++) {
+      std::uint64_t first, count;
+      gpu_range(g, first, count);
+      ck(deva_b200_set_lp_state(g_sim.engs[g], first, count, words.data() + first*stw), "deva_b200_set_lp_state");
+      if(!t[g].empty()) ck(deva_b200_root_events(g_sim.engs[g], t[g].size(), t[g].data(), sb[g].data(), lp[g].data(), pay[g].data()), "deva_b200_root_events");
+    }
 
     // bench PHOLD's wall-clock cut-off (bench/phold.cxx:95-104): a watchdog flips the stop flag
     std::atomic<bool> finished{false};
     std::thread watchdog;
     const double cutoff = g_sim.model->stop_after_secs();
     if(cutoff >= 0) {
-      deva_b200_set_stop(g_sim.eng, 0);
+      for(auto *e: g_sim.engs) deva_b200_set_stop(e, 0);
       watchdog = std::thread([&finished, cutoff] {
         const auto t0 = std::chrono::steady_clock::now();
         while(!finished.load()) {
-          if(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= cutoff) { deva_b200_set_stop(g_sim.eng, 1); break; }
+          if(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= cutoff) { for(auto *e: g_sim.engs) deva_b200_set_stop(e, 1); break; }
           std::this_thread::sleep_for(std::chrono::milliseconds(1));
         }
       });
     }
-    std::uint64_t gvt = 0;
-    const int rc = deva_b200_drain(g_sim.eng, t_end, rewindable ? 1 : 0, &gvt);
+    // one host thread per GPU: the drains run concurrently (their rounds are closed by the GPUs among themselves)
+    std::vector<std::uint64_t> gvts(G, 0);
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> drains;
+    for(std::size_t g = 1; g < G; g++)
+      drains.emplace_back([&, g] { rcs[g] = deva_b200_drain(g_sim.engs[g], t_end, rewindable ? 1 : 0, &gvts[g]); if(rcs[g]) errs[g] = deva_b200_last_error(); });
+    rcs[0] = deva_b200_drain(g_sim.engs[0], t_end, rewindable ? 1 : 0, &gvts[0]);
+    for(auto &th: drains) th.join();
     finished.store(true);
     if(watchdog.joinable()) watchdog.join();
-    ck(rc, "deva_b200_drain");
+    ck(rcs[0], "deva_b200_drain");
+    for(std::size_t g = 1; g < G; g++) if(rcs[g]) deva::assert_failed(__FILE__, __LINE__, ("deva_b200_drain (GPU " + std::to_string(g) + "): " + errs[g]).c_str());
+    std::uint64_t gvt = gvts[0];
+    for(std::size_t g = 1; g < G; g++) DEVA_ASSERT_ALWAYS(gvts[g] == gvt, "the GPUs disagree on the GVT");
     g_sim.gvt = gvt;
     g_sim.has_rewind = rewindable;
     download_state();
-    deva_b200_stats st;
-    ck(deva_b200_get_stats(g_sim.eng, &st), "deva_b200_get_stats");
-    g_sim.stats.executed_n = st.executed_n;
-    g_sim.stats.committed_n = st.committed_n;
-    g_sim.stats.deterministic = st.deterministic != 0;
+    g_sim.stats = pdes::statistics();
+    g_sim.stats.deterministic = true;
+    for(auto *e: g_sim.engs) {
+      deva_b200_stats st;
+      ck(deva_b200_get_stats(e, &st), "deva_b200_get_stats");
+      g_sim.stats.executed_n += st.executed_n;
+      g_sim.stats.committed_n += st.committed_n;
+      g_sim.stats.deterministic = g_sim.stats.deterministic && st.deterministic != 0;
+    }
   }
   deva::barrier();
   return g_sim.gvt;
@@ -420,7 +467,7 @@ void pdes::rewind(bool do_rewind) {                   // pdes.cxx:1137-1229
   if(deva::rank_me() == 0) {
     DEVA_ASSERT_ALWAYS(g_sim.has_rewind, "pdes::rewind without a rewindable drain");
     g_sim.has_rewind = false;
-    ck(deva_b200_rewind(g_sim.eng, do_rewind ? 1 : 0), "deva_b200_rewind");
+    for(auto *e: g_sim.engs) ck(deva_b200_rewind(e, do_rewind ? 1 : 0), "deva_b200_rewind");
     if(do_rewind) download_state();       // fridge::restore: the host copies go back too
   }
   deva::barrier();
@@ -429,7 +476,8 @@ void pdes::rewind(bool do_rewind) {                   // pdes.cxx:1137-1229
 void pdes::finalize() {                               // pdes.cxx:1060-1135
   deva::barrier();
   if(deva::rank_me() == 0) {
-    if(g_sim.eng) { deva_b200_destroy(g_sim.eng); g_sim.eng = nullptr; }
+    for(auto *e: g_sim.engs) deva_b200_destroy(e);
+    g_sim.engs.clear(); g_sim.eng = nullptr;
     g_sim.has_rewind = false;
     for(auto &rs: g_sim.ranks) { rs.regs.clear(); rs.roots.clear(); }
   }

@@ -54,7 +54,7 @@ ABI_SYMBOLS = [
     "deva_b200_state_words", "deva_b200_set_lp_state", "deva_b200_get_lp_state", "deva_b200_root_events",
     "deva_b200_seed_phold", "deva_b200_drain", "deva_b200_rewind", "deva_b200_get_stats", "deva_b200_set_stop",
     "deva_b200_digest", "deva_b200_comm_unique_id", "deva_b200_comm_init", "deva_b200_stream",
-    "deva_b200_reset",
+    "deva_b200_reset", "deva_b200_comm_init_group",
 ]
 
 
@@ -90,6 +90,7 @@ class Api:
         L.deva_b200_stream.argtypes = [P]
         L.deva_b200_reset.argtypes = [P]
         L.deva_b200_stream.restype = P
+        L.deva_b200_comm_init_group.argtypes = [C.POINTER(P), C.c_int32]
 
     def check(self, rc):
         if rc != 0:
@@ -224,6 +225,13 @@ class Engine:
     def comm_init(self, uid_bytes):
         buf = C.create_string_buffer(bytes(uid_bytes), 128)
         self.api.check(self.api.lib.deva_b200_comm_init(self.h, buf))
+
+
+def comm_init_group(engines):
+    """engines that share this process (one per GPU, gpu_rank = index): peer access instead of IPC + NCCL"""
+    api = engines[0].api
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    api.check(api.lib.deva_b200_comm_init_group(arr, len(engines)))
 
 
 def comm_unique_id(api=None):

@@ -148,6 +148,12 @@ void *deva_b200_stream(deva_b200_engine *e);
  * a process, select the staged transport instead (per-peer buffers + grouped ncclSend/ncclRecv). */
 int deva_b200_comm_unique_id(void *uid128);
 int deva_b200_comm_init(deva_b200_engine *e, const void *uid128);
+/* The same for n engines that live in ONE process (one per GPU, created with n_gpus = n and gpu_rank =
+ * their index here): the GPUs map each other's comm blocks through peer access instead of CUDA IPC, no
+ * NCCL involved.  The n drains must then run concurrently, one host thread per engine - every round of
+ * a drain is closed by the GPUs among themselves (replaces the reference's rank threads sharing one
+ * process, threads.cxx:119-142 / world_gasnet.hxx:46-55). */
+int deva_b200_comm_init_group(deva_b200_engine **engines, int32_t n);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <vector>
 
 #include "../../include/deva_b200.h"
@@ -45,7 +48,19 @@ typedef deva_b200::tl::TileEngine<deva_b200::tl::HostBE> EmuTile;
 // DEVA_B200_ENGINE=lp selects the first engine (one thread per LP, per-LP pools); default: the tile engine
 static bool want_tile() { const char *k = getenv("DEVA_B200_ENGINE"); return !(k && !strcmp(k, "lp")); }
 
+// engines of one process that drain together (deva_b200_comm_init_group): their concurrent deva_b200_drain
+// calls - one host thread per engine, as on the GPU box - meet here and the last one in runs the lockstep drain
+struct EmuGroup {
+  std::vector<deva_b200_engine *> es;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0, gen = 0, rc = 0;
+  uint64_t gvt = 0;
+  char err[512] = "";
+};
+
 struct deva_b200_engine {
+  std::shared_ptr<EmuGroup> group;
   EmuTile *tile = nullptr;
   deva_b200_config cfg;
   ModelParams mp;
@@ -405,6 +420,20 @@ int emu_drain_multi(deva_b200_engine **es, int G, uint64_t t_end, int32_t rewind
 }
 
 int deva_b200_drain(deva_b200_engine *e, uint64_t t_end, int32_t rewindable, uint64_t *gvt_out) {
+  if (e->group) {
+    EmuGroup &g = *e->group;
+    std::unique_lock<std::mutex> l(g.mu);
+    const int my_gen = g.gen;
+    if (++g.arrived == (int)g.es.size()) {
+      g.rc = emu_drain_multi(g.es.data(), (int)g.es.size(), t_end, rewindable, &g.gvt);
+      snprintf(g.err, sizeof g.err, "%s", g_err);
+      g.arrived = 0; g.gen++;
+      g.cv.notify_all();
+    } else g.cv.wait(l, [&] { return g.gen != my_gen; });
+    if (g.rc) snprintf(g_err, sizeof g_err, "%s", g.err);
+    if (gvt_out) *gvt_out = g.gvt;
+    return g.rc;
+  }
   if (e->tile) return e->cfg.n_gpus == 1 ? e->tile->drain(t_end, rewindable, gvt_out) : emu_tile_drain_multi(&e, 1, t_end, rewindable, gvt_out);
   if (e->cfg.n_gpus != 1) return fail(DEVA_B200_ERR_STATE, "emu: use emu_drain_multi for n_gpus > 1");
   return emu_drain_multi(&e, 1, t_end, rewindable, gvt_out);
@@ -443,6 +472,15 @@ int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]) {
 
 int deva_b200_comm_unique_id(void *uid128) { memset(uid128, 0, 128); return 0; }
 int deva_b200_comm_init(deva_b200_engine *, const void *) { return 0; }
+void emu_enable_peer_delivery(deva_b200_engine **es, int G);
+int deva_b200_comm_init_group(deva_b200_engine **es, int32_t n) {
+  if (n <= 1) return 0;
+  emu_enable_peer_delivery(es, n);
+  auto g = std::make_shared<EmuGroup>();
+  g->es.assign(es, es + n);
+  for (int i = 0; i < n; i++) es[i]->group = g;
+  return 0;
+}
 void emu_set_shuffle(deva_b200_engine *e, uint64_t seed) { if (e->tile) e->tile->be.shuffle = seed; e->shuffle = seed; }
 // what deva_b200_comm_init does with CUDA IPC: every engine gets a pointer to ITS region of every
 // peer's receive buffer, and lp_pass stores cross-GPU records there directly

@@ -58,6 +58,44 @@ def test_reference_phold_test_source_on_gpu(R):
     check_phold_test_output(out.stdout)
 
 
+def _gpu_count():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=60).stdout
+        return sum(1 for l in out.splitlines() if l.startswith("GPU "))
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+@pytest.mark.parametrize("gpus", [2, 3])
+def test_reference_phold_test_source_multi_gpu_cpp_mirror_emu(emu_api, tmp_path, gpus):
+    """DEVA_B200_GPUS = N: the C++ mirror partitions the LPs over N engines of one process and drains them
+    concurrently, one host thread each (emulation: the concurrent drains meet in a lockstep drain)."""
+    exe = str(tmp_path / "phold_test_R8")
+    emu_dir = os.path.join(ROOT, "tests", "emu", "_build")
+    subprocess.check_call([
+        "g++", "-std=c++14", "-O2", "-pthread", "-w", "-DDEVA_THREAD_N=8", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1",
+        "-DDEBUG=0", f"-I{ROOT}/include", "-include", f"{ROOT}/include/devastator_b200/models/phold_test_model.hxx",
+        f"{REF}/test/phold.cxx", f"{ROOT}/devastator_b200/csrc/host_runtime.cpp", f"-L{emu_dir}", "-ldeva_b200_emu",
+        f"-Wl,-rpath,{emu_dir}", "-o", exe])
+    out = subprocess.run([exe], env=dict(os.environ, DEVA_B200_GPUS=str(gpus)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout
+    check_phold_test_output(out.stdout)
+
+
+@pytest.mark.gpu
+def test_reference_phold_test_source_on_several_gpus_of_one_process():
+    """The reference's unchanged test/phold.cxx on 2 GPUs (and on all of the box's GPUs) behind the C++ drop-in."""
+    n = _gpu_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    exe = os.path.join(BIN, "phold_test_R8")
+    for gpus in sorted({2, min(n, 8)}):
+        out = subprocess.run([exe], env=dict(os.environ, DEVA_B200_GPUS=str(gpus)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout
+        check_phold_test_output(out.stdout)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("R", [1, 4])
 def test_reference_phold_bench_source_on_gpu(R):
