@@ -169,7 +169,7 @@ def ref_binary(tag):
 
 
 # untimed lead-in [0, lead_in): the start-up transient (16 roots per LP inside [0, 16)) is not steady state
-REF_LEAD_IN = {"cfg2": 200, "cfg3": 100}
+REF_LEAD_IN = {"cfg2": 200, "cfg3": 40}    # (config 3 holds 8x the events: a shorter lead-in keeps the run within minutes)
 REF_LPS = {"cfg2": 1 << 20, "cfg3": 1 << 23}      # what the binaries were compiled for (oracle/build_ref.py)
 REF_P = {"cfg2": 0.10, "cfg3": 0.50}
 
@@ -224,8 +224,8 @@ def reference_arm(args):
         return 0
     K, W = args.steps, args.warmup
     tag, lp_total, p, scaling = workloads(args.gpus)[0]
-    # about 1e7 committed events per slice (1-3 s of host time): the whole run ends within minutes
-    res = reference_sample(tag, K, W, float(os.environ.get("DEVA_BENCH_REF_EVENTS_PER_STEP", 1.0e7)))
+    # about 1e7 (config 2) / 3e6 (config 3) committed events per slice, 1-3 s of host time each: the whole run ends within minutes
+    res = reference_sample(tag, K, W, float(os.environ.get("DEVA_BENCH_REF_EVENTS_PER_STEP", 1.0e7 if tag == "cfg2" else 3.0e6)))
     if not res:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binary missing or failed (run __graft_entry__.build() where /root/reference exists)"}))
         return 0
@@ -251,7 +251,7 @@ def reference_arm(args):
 
 def cpu_baseline(tag):
     """Bounded sample (about 10-30 s of drain time) of the same workload on the reference itself, host cores."""
-    res = reference_sample(tag, 2, 1, float(os.environ.get("DEVA_BENCH_CPU_EVENTS_PER_STEP", 3.0e7)))
+    res = reference_sample(tag, 2, 1, float(os.environ.get("DEVA_BENCH_CPU_EVENTS_PER_STEP", 3.0e7 if tag == "cfg2" else 1.0e7)))
     if not res:
         return {"value": None, "unit": "events/s", "cores": 0, "kind": "reference", "sample": "unavailable: oracle/_ref binary missing"}
     return {"value": res["value"], "unit": "events/s", "cores": res["ranks"], "kind": "reference", "sample": sample_text(res, 2, 1)}
@@ -282,6 +282,9 @@ def ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if N > 1:
+        stale = os.path.join("/tmp", "deva_bench_cpu_done_%s" % os.environ.get("MASTER_PORT", "0"))
+        if rank == 0 and os.path.exists(stale):
+            os.remove(stale)
         dist.init_process_group("nccl", device_id=dev)
     gold = goldens()
     MASK = (1 << 64) - 1
@@ -454,18 +457,55 @@ def ours(args):
     if tr and N == 1:
         line["roofline"]["traffic"] = tr.get("dram_bytes_per_full_launch")
         line["roofline"]["traffic_detail"] = tr
-    if rank == 0 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(head["tag"])
+    # the reference on the host cores, rank 0; the other ranks sleep meanwhile (a rank spinning in an NCCL
+    # barrier would take a core away from the reference's pinned rank threads)
+    flag = os.path.join("/tmp", "deva_bench_cpu_done_%s" % os.environ.get("MASTER_PORT", "0"))
+    if not args.no_cpu_baseline:
+        if rank == 0:
+            line["cpu_baseline"] = cpu_baseline(head["tag"])
+            if N > 1:
+                open(flag, "w").close()
+        else:
+            t_wait = time.time()
+            while not os.path.exists(flag) and time.time() - t_wait < 1800:
+                time.sleep(0.25)
     bad = [r["tag"] for r in results if r["parity"]["golden"] == "MISMATCH"]
     if rank == 0:
+        emit_report_rows(results, N)
         print(json.dumps(line), flush=True)
     if N > 1:
         dist.barrier()
         dist.destroy_process_group()
+        if rank == 0 and os.path.exists(flag):
+            os.remove(flag)
     if bad:
         sys.stderr.write("PARITY MISMATCH against tests/golden/bench_goldens.json: %s\n" % bad)
         return 1
     return 0
+
+
+def emit_report_rows(results, n_gpus):
+    """With `report_file` set (the reference's own variable, bench/util/report.cxx:25), every workload of the
+    run is appended as one `row(xs=dict(...), ys=dict(...))` in the format the reference's bench/util/show.py
+    and table.py read, with the y names of bench/phold.cxx:176-179 (a "rank" is a GPU here)."""
+    path = os.environ.get("report_file")
+    if not path:
+        return
+    out = sys.stderr if path == "-" else open(path, "a")
+    if out is not sys.stderr:
+        out.write("# Opened for append at %s\n" % time.strftime("%Y-%m-%d %X"))
+    for r in results:
+        c, p = r["config"], r["parity"]
+        xs = dict(app="phold", engine="deva_b200", gpus=n_gpus, ranks=n_gpus, workload=c["tag"], lp_per_rank=c["lps_total"] // n_gpus,
+                  ray_per_lp=K_ROOTS, p_remote=c["p_remote"], end_time=END_TIME)
+        secs = r["ms_per_step"] * 1e-3
+        ys = dict(execute_per_rank_per_sec=p["executed_per_step"] / secs / n_gpus, commit_per_rank_per_sec=p["commits_per_step"] / secs / n_gpus,
+                  deterministic=1 if p["golden"] != "MISMATCH" else 0)
+        kw = lambda d: ", ".join("%s=%r" % kv for kv in d.items())
+        out.write("row(xs=dict(%s),\n    ys=dict(%s))\n" % (kw(xs), kw(ys)))
+    if out is not sys.stderr:
+        out.close()
+        sys.stderr.write("Report written to '%s'.\n" % path)
 
 
 def main():

@@ -320,6 +320,8 @@ struct TileEngine {
               (unsigned long long)hc.prof[7], hc.prof[15] ? (double)hc.prof[12] / ((double)hc.prof[15] * per_launch) : 0.0, hc.prof[15] * 1e-6);
       fprintf(stderr, "tile prof: launch spans (cumulative): full %.3f ms / %llu, follow-up %.3f ms / %llu, rebin %.3f ms / %llu\n", hc.prof[15] * 1e-6, (unsigned long long)hc.prof[20],
               hc.prof[16] * 1e-6, (unsigned long long)hc.prof[17], hc.prof[18] * 1e-6, (unsigned long long)hc.prof[19]);
+      if (cfg.n_gpus > 1) fprintf(stderr, "tile prof: exchange kernel (last block, cumulative): wait for peers' step kernels %.3f ms, deliver %.3f ms, figures round trip %.3f ms\n",
+                                  hc.prof[21] * 1e-6, hc.prof[22] * 1e-6, hc.prof[23] * 1e-6);
     }
 #endif
     return 0;

@@ -207,6 +207,10 @@ __global__ void __launch_bounds__(256) k_tile_xchg(const __grid_constant__ TView
   const uint32_t phase = c->phase;
   if (!begin_mode && phase != PH_EVAL && phase != PH_REBIN) return;
   if (!begin_mode && !c->stepped) return;   // the step kernel before was not its turn (decided alike on every GPU)
+#ifdef DEVA_TILE_PROF
+  unsigned long long xt0 = 0, xt1 = 0, xt2 = 0, xt3 = 0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt0));
+#endif
   const int G = v.n_gpus, me = v.gpu_rank;
   const uint32_t r = c->round;
   const unsigned long long tag = (unsigned long long)r + 1ull;
@@ -224,6 +228,9 @@ __global__ void __launch_bounds__(256) k_tile_xchg(const __grid_constant__ TView
     }
   }
   __syncthreads();
+#ifdef DEVA_TILE_PROF
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt1));
+#endif
   const Epoch ep = load_epoch(c);
   uint32_t err = timeout ? (uint32_t)ERR_PEER_TIMEOUT : 0u;
   __shared__ __align__(8) uint32_t bh[BH_N];
@@ -244,6 +251,9 @@ __global__ void __launch_bounds__(256) k_tile_xchg(const __grid_constant__ TView
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+#ifdef DEVA_TILE_PROF
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt2));
+#endif
   // ---- last block: this GPU's figures to every peer, theirs back, one decision
   if (threadIdx.x == 0) make_peer_msg(v, msgs[me]);
   __syncthreads();
@@ -273,6 +283,12 @@ __global__ void __launch_bounds__(256) k_tile_xchg(const __grid_constant__ TView
     }
   }
   __syncthreads();
+#ifdef DEVA_TILE_PROF
+  if (threadIdx.x == 0 && !begin_mode) {
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt3));
+    c->prof[21] += xt1 - xt0; c->prof[22] += xt2 - xt1; c->prof[23] += xt3 - xt2;   // wait for the peers' step kernels | deliver | figures round trip
+  }
+#endif
   if (threadIdx.x == 0) {
     fold_peer_msgs(msgs, G, g);
     if (timeout) g.err |= ERR_PEER_TIMEOUT;

@@ -264,3 +264,27 @@ def test_default_start_window_refuses_loudly_when_far_too_optimistic(emu_api, mo
     with pytest.raises(E.EngineError) as ei:
         S.run_phold_t(emu_api, 47, 7, 1.0, 1.0, 15, window=0)
     assert ei.value.code == -3   # DEVA_B200_ERR_CAPACITY: never a silent drop
+
+
+def test_drain_timer_csv_rows_add_up(api, engine_kind, tmp_path, monkeypatch):
+    """DEVA_B200_DRAIN_TIMER=<prefix> (the counterpart of the reference's DrainTimer, pdes.hxx:139-308): one CSV
+    row per batch of launches / per epoch; the rows' executed / committed columns add up to the statistics."""
+    if engine_kind != "tile":
+        pytest.skip("the first engine's per-epoch CSV has other columns (profiles/r1_k_drain_timer.0.csv)")
+    prefix = str(tmp_path / "timer")
+    monkeypatch.setenv("DEVA_B200_DRAIN_TIMER", prefix)
+    monkeypatch.setenv("DEVA_B200_TILE_BATCH", "3")
+    eng = S.make(api, 1000, P=0.5, LAM=100.0, END=300, sub=1)
+    eng.seed_phold(16, 1, 1)
+    eng.drain()
+    st = eng.stats()
+    eng.close()
+    import csv
+    with open(prefix + ".0.csv") as f:
+        rows = list(csv.DictReader(f))
+    assert len(rows) >= 2
+    assert sum(int(r["executed"]) for r in rows) == st["executed_n"]
+    if "committed" in rows[0]:
+        assert sum(int(r["committed"]) for r in rows) == st["committed_n"]
+    times = [int(r["sim_time"]) for r in rows]
+    assert times == sorted(times)
