@@ -120,6 +120,14 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
 __device__ __forceinline__ void bulk_commit() { TL_ASM("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { TL_ASM("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources may be reused
 __device__ __forceinline__ void bulk_wait_all() { TL_ASM("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes are done
+// 4 / 8-byte asynchronous copies global -> shared (LDGSTS): issued and forgotten, waited for where the data is used
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem) {
+  TL_ASM("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src_gmem) {
+  TL_ASM("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { TL_ASM("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { TL_ASM("fence.proxy.async.shared::cta;" ::: "memory"); }   // generic writes -> async reads
 #endif
 
@@ -165,7 +173,11 @@ struct Hdr {
   uint32_t n, nb, nl, nlw, nl_old, nf, first, slow, in_buf, lo, hi, skip, used_far, seg_big;
   uint32_t nbk[MAXM];                     // records of each of the window's buckets (nb = their sum)
   uint32_t bins[NBIN], n_active, chunk;   // LPs per record count; LPs that run; next chunk of 32 LPs to hand to a warp
-  uint32_t work_item, next_item, n_gen;
+  uint32_t work_item, next_item, n_gen, any_anti;
+  // the NEXT tile's header words, fetched with cp.async while this tile is flushed (prefetch_header): [0, MAXM) bucket
+  // counts, then tev, lseen[par], lseen[rd], tflags, fpub, tcur; pf_lcnt = the late list's tagged counter
+  uint32_t pf_tile, pf_w[MAXM + 6];
+  alignas(8) unsigned long long pf_lcnt;
   uint32_t own[2 * OWN_N];                // flush: children counted per destination code (ring slot of this tile / peer GPU) | the places claimed for them
   // accumulated over all the tiles the block handles in a launch, folded into TCtl once (blk_flush)
   uint32_t executed, rolled, anti, remote, err, fresh_antis, evals, ovf;
@@ -552,14 +564,14 @@ DEVA_HD void block_scan(Blk &b) {
 // is re-evaluated from the checkpoint `sin` and differences are sent / cancelled at once.
 template <class M, bool FULLK>
 DEVA_HD void run_lp_core(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf, uint32_t lp,
-                         uint32_t s0, uint32_t s1, const LpState &sin, bool first_rt) {
+                         uint32_t s0, uint32_t s1, const LpState &sin, bool first_rt, bool flags_set = false) {
   // FULLK: compiled for the kernel of an epoch's first launch, where every evaluation is a first one -
   // the re-evaluation code (two chains alive at once) is not even instantiated there
   const bool first = FULLK ? true : first_rt;
   Hdr &h = *b.h;
   const uint64_t gid = v.lp_begin + (uint64_t)tile * TILE + lp;
   uint32_t err = 0, remote = 0, anti_sent = 0, fresh_antis = 0;
-  net_segment(b, s0, s1, &err, &fresh_antis);
+  if (!flags_set) net_segment(b, s0, s1, &err, &fresh_antis);   // (the block path sets the flags itself when the window holds no anti-message)
   // insertion sort of the segment's indices by (time, subtime, payload): 2-4 records as a rule
 #pragma unroll 1
   for (uint32_t a = s0 + 1; a < s1; a++) {
@@ -604,7 +616,27 @@ DEVA_HD void run_lp_core(const TView &v, const ModelParams &mp, const Epoch &ep,
 template <class M, bool FULLK>
 DEVA_HD void run_lp(const TView &v, const ModelParams &mp, const Epoch &ep, Blk &b, uint32_t tile, uint32_t out_buf, uint32_t lp) {
   const LpState sin = b.S[lp];
-  run_lp_core<M, FULLK>(v, mp, ep, b, tile, out_buf, lp, b.off[lp], b.off[lp + 1], sin, b.h->first != 0);
+  run_lp_core<M, FULLK>(v, mp, ep, b, tile, out_buf, lp, b.off[lp], b.off[lp + 1], sin, b.h->first != 0, b.h->any_anti == 0);
+}
+
+// The header words of the tile this block evaluates next (full launch): asynchronous copies into the block's
+// header, issued by one thread while the current tile's children are flushed.  Safe to read early: the open
+// buckets' counts are frozen for the launch, the late list read was completed by the previous launch, the
+// rest is only ever written by the tile's own evaluator (TF_OVF may be set meanwhile: its far records are
+// beyond what fpub counts).
+DEVA_HD void prefetch_header(const TView &v, const Epoch &ep, Hdr &h, uint32_t tile) {
+#if defined(__CUDA_ARCH__)
+  if (tile >= v.NT) return;
+  const uint32_t rd = ep.par ^ 1u;
+  for (uint32_t k = 0; k < ep.m; k++)
+    cp_async4(&h.pf_w[k], ep.partial ? &v.npub[(size_t)tile * MAXM + k] : &v.ncnt[(size_t)tile * NB + (uint32_t)((ep.cur_abs + k) % NB)]);
+  cp_async4(&h.pf_w[MAXM], &v.tev[tile]); cp_async4(&h.pf_w[MAXM + 1], &v.lseen[ep.par][tile]); cp_async4(&h.pf_w[MAXM + 2], &v.lseen[rd][tile]);
+  cp_async4(&h.pf_w[MAXM + 3], &v.tflags[tile]); cp_async4(&h.pf_w[MAXM + 4], &v.fpub[tile]); cp_async4(&h.pf_w[MAXM + 5], &v.tcur[tile]);
+  cp_async8(&h.pf_lcnt, &v.lcnt[rd][tile]);
+  h.pf_tile = tile;
+#else
+  (void)v; (void)ep; (void)h; (void)tile;
+#endif
 }
 
 // Sort the block's records b.R[0..n) by LP (counting sort on the LP's index in the tile), order the
@@ -711,6 +743,7 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
   // their places - in the tile's bucket lists, in this GPU's region of the peer's receive buffer - and their
   // stores wait for nothing.  The others (another tile, the open window, beyond the horizon) were listed:
   // their atomics leave in one go, every lane busy.
+  if (FULLK) { TL_THREADS(tid) { if (tid == (int)TL_NTHR - 1) prefetch_header(v, ep, h, h.next_item); } }
   if (h.first) {
     const uint16_t *gen = reinterpret_cast<const uint16_t *>(b.cur);
     TL_THREADS(tid) {
@@ -759,6 +792,7 @@ DEVA_HD void blk_begin(Blk &b) {
   Hdr &h = *b.h;
   h.executed = h.rolled = h.anti = h.remote = h.err = h.fresh_antis = h.evals = h.ovf = 0; h.committed = h.nondet = 0;
   bh_init(h.bh);
+  h.pf_tile = NEVER;
 #ifdef DEVA_TILE_PROF
   for (int i = 0; i < 12; i++) h.prof[i] = 0;
 #endif
@@ -810,29 +844,45 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     if (tid != 0) continue;
     // the lists of the window committed last are empty from here on (nobody appends to them in this launch)
     for (uint32_t k = 0; k < ep.rc_n; k++) v.ncnt[(size_t)tile * NB + (uint32_t)((ep.rc_lo + k) % NB)] = 0;
+    // the header words: prefetched while the previous tile was flushed (full launch), or loaded now
+    uint32_t w_nc[MAXM], w_tev, w_lsw, w_lsr, w_tfl, w_fpub, w_tcur;
+    unsigned long long w_lcnt;
+#if defined(__CUDA_ARCH__)
+    if (FULLK && h.pf_tile == tile) {
+      cp_async_wait_all();
+      for (uint32_t k = 0; k < ep.m; k++) w_nc[k] = h.pf_w[k];
+      w_tev = h.pf_w[MAXM]; w_lsw = h.pf_w[MAXM + 1]; w_lsr = h.pf_w[MAXM + 2]; w_tfl = h.pf_w[MAXM + 3]; w_fpub = h.pf_w[MAXM + 4]; w_tcur = h.pf_w[MAXM + 5];
+      w_lcnt = h.pf_lcnt;
+    } else
+#endif
+    {
+      // (t_end cuts the window: records beyond ub are appended to its buckets meanwhile, the counts were frozen)
+      for (uint32_t k = 0; k < ep.m; k++) w_nc[k] = ep.partial ? v.npub[(size_t)tile * MAXM + k] : v.ncnt[(size_t)tile * NB + (uint32_t)((ep.cur_abs + k) % NB)];
+      w_lcnt = v.lcnt[rd][tile]; w_tev = v.tev[tile]; w_lsw = v.lseen[ep.par][tile]; w_lsr = v.lseen[rd][tile];
+      w_tfl = v.tflags[tile]; w_fpub = v.fpub[tile]; w_tcur = v.tcur[tile];
+    }
+    h.pf_tile = NEVER;
     h.nb = 0;
     for (uint32_t k = 0; k < ep.m; k++) {
-      // (t_end cuts the window: records beyond ub are appended to its buckets meanwhile, the counts were frozen)
-      const uint32_t nc = ep.partial ? v.npub[(size_t)tile * MAXM + k] : v.ncnt[(size_t)tile * NB + (uint32_t)((ep.cur_abs + k) % NB)];
-      h.nbk[k] = nc < v.C ? nc : v.C;
+      h.nbk[k] = w_nc[k] < v.C ? w_nc[k] : v.C;
       h.nb += h.nbk[k];
     }
-    const uint32_t lc = late_count(v.lcnt[rd][tile], ep.epoch);
+    const uint32_t lc = late_count(w_lcnt, ep.epoch);
     h.nl = lc < v.CL ? lc : v.CL;                  // all of it is complete: this launch appends to the other list
-    const uint32_t tev = v.tev[tile];
+    const uint32_t tev = w_tev;
     h.first = tev != ep.epoch;
 
-    h.nlw = h.first ? 0u : v.lseen[ep.par][tile];  // the other list: what this tile has evaluated before (complete, too)
-    h.nl_old = h.first ? 0u : v.lseen[rd][tile];
-    h.nf = (v.tflags[tile] & TF_OVF) ? v.fpub[tile] : 0u;   // (count as of the last rebin: those records are complete)
-    h.in_buf = v.tcur[tile];
+    h.nlw = h.first ? 0u : w_lsw;                  // the other list: what this tile has evaluated before (complete, too)
+    h.nl_old = h.first ? 0u : w_lsr;
+    h.nf = (w_tfl & TF_OVF) ? w_fpub : 0u;         // (count as of the last rebin: those records are complete)
+    h.in_buf = w_tcur;
     h.skip = (h.nb + h.nl + h.nlw + h.nf) == 0;
     h.slow = h.nf > 0 || h.nb + h.nl + h.nlw > b.rcap || ep.sp_w_n > 0 || ep.sp_r_n > 0;
     if (ep.sp_w_n > 0 || ep.sp_r_n > 0) h.skip = 0;
     // its last evaluation's epoch is committed: that result is the state now (a tile that is skipped
     // keeps the swap for the evaluation that will update tev)
     if (!h.skip && h.first && tev != NEVER) { v.tcur[tile] ^= 1u; h.in_buf ^= 1u; }
-    h.used_far = 0; h.seg_big = 0;
+    h.used_far = 0; h.seg_big = 0; h.any_anti = 0;
   }
   TL_SYNC();
   if (h.skip) return;
@@ -876,7 +926,9 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
         const EvRec &r = b.R[i];
         uint8_t f = (h.first || i >= n_oldsrc) ? F_FRESH : 0;
         if (r.flags & EV_ANTI) f |= F_ANTI;
+        else f |= (f & F_FRESH) ? F_INNEW : (uint8_t)(F_INOLD | F_INNEW);   // (what net_segment sets; it only runs when the window holds an anti-message)
         if (r.time >= ep.ub || r.time < ep.gvt || (r.flags & EV_DEAD)) f = F_DEAD;
+        if (f & F_ANTI) h.any_anti = 1;              // (benign race: any writer stores 1)
         b.efl[i] = f;
       }
     }
@@ -939,7 +991,8 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
           if (p >= b.rcap) continue;     // (only after ERR_LP_OVERFLOW)
           b.R[p] = r;
           uint8_t f = fresh ? F_FRESH : 0;
-          if (r.flags & EV_ANTI) f |= F_ANTI;
+          if (r.flags & EV_ANTI) { f |= F_ANTI; h.any_anti = 1; }
+          else f |= fresh ? F_INNEW : (uint8_t)(F_INOLD | F_INNEW);
           b.efl[p] = f;
           if (i >= n_src && i < n_far_end) h.used_far = 1;
         }

@@ -57,6 +57,104 @@ __device__ __forceinline__ void publish_counts(const TView &v) {
   }
 }
 
+// One round's closing with several GPUs: receive what the peers stored here, exchange the job-wide figures,
+// run the epoch state machine - identically on every GPU, without the host and without NCCL.  Called by EVERY
+// block of the launch once its own part of the step is done (the step kernel runs straight on into it: a
+// block that finishes early waits here for the peers' records instead of leaving), `ws` = a block's
+// scratch in shared memory (xchg_ws_bytes).
+struct XWs {
+  PeerMsg msgs[MAX_GPUS];
+  Glob g;
+  uint32_t counts[MAX_GPUS], timeout, is_last;
+  alignas(8) uint32_t bh[BH_N];
+};
+__device__ __forceinline__ void exchange_round(const TView &v, const TParams &tp, const Epoch &ep, XWs &ws, const int begin_mode) {
+  TCtl *c = v.ctl;
+#ifdef DEVA_TILE_PROF
+  unsigned long long xt0 = 0, xt1 = 0, xt2 = 0, xt3 = 0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt0));
+#endif
+  const int G = v.n_gpus, me = v.gpu_rank;
+  const uint32_t r = c->round;
+  const unsigned long long tag = (unsigned long long)r + 1ull;
+  if (threadIdx.x == 0) { ws.timeout = 0; bh_init(ws.bh); }
+  __syncthreads();
+  if ((int)threadIdx.x < G) {
+    ws.counts[threadIdx.x] = 0;
+    if ((int)threadIdx.x != me) {
+      if (!wait_tag(&v.mtag1[threadIdx.x], tag)) atomicOr(&ws.timeout, 1u);
+      else { const uint32_t n = __ldcg(&v.mcount[(r & 1u) * MAX_GPUS + threadIdx.x]); ws.counts[threadIdx.x] = n < v.peer_cap ? n : v.peer_cap; }
+    }
+  }
+  __syncthreads();
+#ifdef DEVA_TILE_PROF
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt1));
+#endif
+  uint32_t err = ws.timeout ? (uint32_t)ERR_PEER_TIMEOUT : 0u;
+  for (int src = 0; src < G; src++) {
+    const uint32_t n = ws.counts[src];
+    const EvRec *recs = v.recvbuf + (size_t)src * v.peer_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      append_local(v, ep, ld_ev_cg(&recs[i]), ws.bh, &err);
+  }
+  if (err) atomicOr(&c->err, err);
+  __syncthreads();
+  if (threadIdx.x == 0) bh_flush(v, ws.bh);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ws.is_last = atomicAdd(&c->xticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!ws.is_last) return;
+  __threadfence();
+#ifdef DEVA_TILE_PROF
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt2));
+#endif
+  // ---- last block: this GPU's figures to every peer, theirs back, one decision
+  if (threadIdx.x == 0) make_peer_msg(v, ws.msgs[me]);
+  __syncthreads();
+  {
+    const uint32_t words = sizeof(PeerMsg) / 8;
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&ws.msgs[me]);
+    for (int p = 0; p < G; p++) {
+      if (p == me) continue;
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(&v.peer_mbox[p][(r & 1u) * MAX_GPUS + me]);
+      for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < G && (int)threadIdx.x != me) {
+    st_release_sys(&v.peer_tag2[threadIdx.x][me], tag);
+    if (!wait_tag(&v.mtag2[threadIdx.x], tag)) atomicOr(&ws.timeout, 1u);
+  }
+  __syncthreads();
+  {
+    const uint32_t words = sizeof(PeerMsg) / 8;
+    for (int p = 0; p < G; p++) {
+      if (p == me) continue;
+      const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&v.mbox[(r & 1u) * MAX_GPUS + p]);
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(&ws.msgs[p]);
+      for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = __ldcg(&src[w]);
+    }
+  }
+  __syncthreads();
+#ifdef DEVA_TILE_PROF
+  if (threadIdx.x == 0 && !begin_mode) {
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt3));
+    c->prof[21] += xt1 - xt0; c->prof[22] += xt2 - xt1; c->prof[23] += xt3 - xt2;   // wait for the peers' step kernels | deliver | figures round trip
+  }
+#endif
+  if (threadIdx.x == 0) {
+    fold_peer_msgs(ws.msgs, G, ws.g);
+    if (ws.timeout) ws.g.err |= ERR_PEER_TIMEOUT;
+    c->round = r + 1u;
+    c->xticket = 0;
+  }
+  __syncthreads();
+  if (begin_mode) begin_drain(v, tp, c->t_end, ws.g);
+  else close_launch(v, tp, ws.g);
+}
+
 // FULLK = true: the kernel of an epoch's first launch (every tile, first evaluations only) and of the
 // calendar maintenance; FULLK = false: the kernel of the follow-up launches (re-evaluations).  The host
 // enqueues them in a fixed pattern (one full, three follow-ups, ...); a launch whose turn it is not
@@ -66,6 +164,10 @@ __global__ void __launch_bounds__(NTHR, FULLK ? DEVA_TILE_MINB : DEVA_TILE_MINB_
 k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams mp, const __grid_constant__ TParams tp) {
   extern __shared__ __align__(128) unsigned char tl_smem[];
   TCtl *c = v.ctl;
+  // Programmatic dependent launch: this grid's blocks may become resident while the previous launch drains
+  // (its blocks leave one by one at its tail); nothing of the previous launch is read before this point.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t phase = c->phase;
   if (phase != PH_EVAL && phase != PH_REBIN) return;   // done / idle: the launch is a no-op
   if (FULLK != (phase == PH_REBIN || c->full != 0)) return;   // not this kernel's turn
@@ -178,127 +280,37 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
   __syncthreads();
   if (threadIdx.x == 0) is_last = atomicAdd(&c->ticket, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+  if (is_last) {
+    __threadfence();
 #ifdef DEVA_TILE_PROF
-  if (threadIdx.x == 0) {   // the launch's span: earliest block start .. now
-    unsigned long long t1;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-    const int k = phase == PH_REBIN ? 18 : FULLK ? 15 : 16;
-    c->prof[k] += t1 - c->prof[14]; c->prof[14] = ~0ull;
-    c->prof[k == 15 ? 20 : k + 1]++;
-  }
+    if (threadIdx.x == 0) {   // the launch's span: earliest block start .. now
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      const int k = phase == PH_REBIN ? 18 : FULLK ? 15 : 16;
+      c->prof[k] += t1 - c->prof[14]; c->prof[14] = ~0ull;
+      c->prof[k == 15 ? 20 : k + 1]++;
+    }
 #endif
-  if (v.n_gpus > 1) {   // several GPUs: the exchange kernel closes the launch, once the peers' figures are in
-    if (threadIdx.x == 0) c->stepped = 1;
-    publish_counts(v);
+  }
+  if (v.n_gpus > 1) {
+    // several GPUs: the last block tells the peers how many records this GPU left them; every block then goes
+    // on into the round's closing (the workspace is free now: the exchange's scratch lives in it)
+    if (is_last) publish_counts(v);
+    exchange_round(v, tp, ep, *reinterpret_cast<XWs *>(tl_smem), 0);
     return;
   }
+  if (!is_last) return;
   __shared__ Glob g;
   if (threadIdx.x == 0) glob_from_ctl(g, c, c->dirty_n[c->par]);
   __syncthreads();
   close_launch(v, tp, g);
 }
 
-// One round's closing: receive what the peers stored here, exchange the job-wide figures, run the
-// epoch state machine - identically on every GPU, without the host and without NCCL.
-__global__ void __launch_bounds__(256) k_tile_xchg(const __grid_constant__ TView v, const __grid_constant__ TParams tp, const int begin_mode) {
-  TCtl *c = v.ctl;
-  const uint32_t phase = c->phase;
-  if (!begin_mode && phase != PH_EVAL && phase != PH_REBIN) return;
-  if (!begin_mode && !c->stepped) return;   // the step kernel before was not its turn (decided alike on every GPU)
-#ifdef DEVA_TILE_PROF
-  unsigned long long xt0 = 0, xt1 = 0, xt2 = 0, xt3 = 0;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt0));
-#endif
-  const int G = v.n_gpus, me = v.gpu_rank;
-  const uint32_t r = c->round;
-  const unsigned long long tag = (unsigned long long)r + 1ull;
-  __shared__ uint32_t counts[MAX_GPUS];
-  __shared__ uint32_t timeout, is_last;
-  __shared__ PeerMsg msgs[MAX_GPUS];
-  __shared__ Glob g;
-  if (threadIdx.x == 0) timeout = 0;
-  __syncthreads();
-  if ((int)threadIdx.x < G) {
-    counts[threadIdx.x] = 0;
-    if ((int)threadIdx.x != me) {
-      if (!wait_tag(&v.mtag1[threadIdx.x], tag)) atomicOr(&timeout, 1u);
-      else { const uint32_t n = __ldcg(&v.mcount[(r & 1u) * MAX_GPUS + threadIdx.x]); counts[threadIdx.x] = n < v.peer_cap ? n : v.peer_cap; }
-    }
-  }
-  __syncthreads();
-#ifdef DEVA_TILE_PROF
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt1));
-#endif
-  const Epoch ep = load_epoch(c);
-  uint32_t err = timeout ? (uint32_t)ERR_PEER_TIMEOUT : 0u;
-  __shared__ __align__(8) uint32_t bh[BH_N];
-  if (threadIdx.x == 0) bh_init(bh);
-  __syncthreads();
-  for (int src = 0; src < G; src++) {
-    const uint32_t n = counts[src];
-    const EvRec *recs = v.recvbuf + (size_t)src * v.peer_cap;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-      append_local(v, ep, ld_ev_cg(&recs[i]), bh, &err);
-  }
-  if (err) atomicOr(&c->err, err);
-  __syncthreads();
-  if (threadIdx.x == 0) bh_flush(v, bh);
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&c->xticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-#ifdef DEVA_TILE_PROF
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt2));
-#endif
-  // ---- last block: this GPU's figures to every peer, theirs back, one decision
-  if (threadIdx.x == 0) make_peer_msg(v, msgs[me]);
-  __syncthreads();
-  {
-    const uint32_t words = sizeof(PeerMsg) / 8;
-    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&msgs[me]);
-    for (int p = 0; p < G; p++) {
-      if (p == me) continue;
-      unsigned long long *dst = reinterpret_cast<unsigned long long *>(&v.peer_mbox[p][(r & 1u) * MAX_GPUS + me]);
-      for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < G && (int)threadIdx.x != me) {
-    st_release_sys(&v.peer_tag2[threadIdx.x][me], tag);
-    if (!wait_tag(&v.mtag2[threadIdx.x], tag)) atomicOr(&timeout, 1u);
-  }
-  __syncthreads();
-  {
-    const uint32_t words = sizeof(PeerMsg) / 8;
-    for (int p = 0; p < G; p++) {
-      if (p == me) continue;
-      const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&v.mbox[(r & 1u) * MAX_GPUS + p]);
-      unsigned long long *dst = reinterpret_cast<unsigned long long *>(&msgs[p]);
-      for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = __ldcg(&src[w]);
-    }
-  }
-  __syncthreads();
-#ifdef DEVA_TILE_PROF
-  if (threadIdx.x == 0 && !begin_mode) {
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(xt3));
-    c->prof[21] += xt1 - xt0; c->prof[22] += xt2 - xt1; c->prof[23] += xt3 - xt2;   // wait for the peers' step kernels | deliver | figures round trip
-  }
-#endif
-  if (threadIdx.x == 0) {
-    fold_peer_msgs(msgs, G, g);
-    if (timeout) g.err |= ERR_PEER_TIMEOUT;
-    c->round = r + 1u;
-    c->xticket = 0;
-    c->stepped = 0;
-  }
-  __syncthreads();
-  if (begin_mode) begin_drain(v, tp, c->t_end, g);
-  else close_launch(v, tp, g);
+// drain entry with several GPUs (after k_tile_begin_multi): the exchange alone, which picks the first epoch
+__global__ void __launch_bounds__(256) k_tile_xchg_begin(const __grid_constant__ TView v, const __grid_constant__ TParams tp) {
+  __shared__ XWs ws;
+  const Epoch ep = load_epoch(v.ctl);
+  exchange_round(v, tp, ep, ws, 1);
 }
 
 // drain entry with several GPUs: latch t_end, publish "no records", then k_tile_xchg(begin_mode) decides
@@ -444,6 +456,7 @@ struct CudaBE {
   size_t stage_bytes = 0;
   int grid = 0, grid_follow = 0, xchg_grid = 148;
   uint32_t step_no = 0, pattern = 4;   // one full-launch slot in every `pattern` launches
+  bool pdl = true;                    // programmatic dependent launch of the step kernels (DEVA_B200_TILE_PDL=0: off)
   size_t smem = 0;
   bool smem_set[2] = {false, false};
 
@@ -472,6 +485,7 @@ struct CudaBE {
     grid_follow = prop.multiProcessorCount * std::max(1, std::min(occ_follow, cap));
     xchg_grid = prop.multiProcessorCount;
     pattern = std::max<uint32_t>(2, env_u32("DEVA_B200_TILE_PATTERN", 4));
+    pdl = env_u32("DEVA_B200_TILE_PDL", 1) != 0;
     if (getenv("DEVA_B200_TILE_VERBOSE")) fprintf(stderr, "deva_b200 tile engine: TILE %d, %d threads, rcap %u, smem %zu B, blocks/SM full %d follow %d\n", TILE, NTHR, rcap, smem, occ_full, occ_follow);
     return 0;
   }
@@ -584,7 +598,7 @@ struct CudaBE {
     TCU(cudaSetDevice(device));
     if (v.n_gpus > 1) {
       k_tile_begin_multi<<<1, 32, 0, stream>>>(v, t_end);
-      k_tile_xchg<<<1, 256, 0, stream>>>(v, tp, 1);
+      k_tile_xchg_begin<<<1, 256, 0, stream>>>(v, tp);
     } else k_tile_begin<<<1, TILE, 0, stream>>>(v, tp, t_end);
     TCU(cudaGetLastError());
     return 0;
@@ -598,9 +612,15 @@ struct CudaBE {
       smem_set[mi] = true;
     }
     // pattern: full, follow, follow, follow (an epoch is one full launch and, on BASELINE's PHOLD, 2-3 follow-ups)
-    if ((step_no++ % pattern) == 0) k_tile_step<M, true><<<grid, NTHR, smem, stream>>>(v, mp, tp);
-    else k_tile_step<M, false><<<grid_follow, NTHR, smem, stream>>>(v, mp, tp);
-    if (v.n_gpus > 1) k_tile_xchg<<<xchg_grid, 256, 0, stream>>>(v, tp, 0);
+    const bool full = (step_no++ % pattern) == 0;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(full ? grid : grid_follow)); lc.blockDim = dim3(NTHR); lc.dynamicSmemBytes = smem; lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    lc.attrs = at; lc.numAttrs = 1;
+    if (full) TCU(cudaLaunchKernelEx(&lc, k_tile_step<M, true>, v, mp, tp));
+    else TCU(cudaLaunchKernelEx(&lc, k_tile_step<M, false>, v, mp, tp));
     TCU(cudaGetLastError());
     return 0;
   }
