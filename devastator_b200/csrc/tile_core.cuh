@@ -71,7 +71,9 @@ DEVA_HD EvRec ld_ev_cg(const EvRec *p) {   // bypasses L1: the record may have b
   e.p0 = b.x; e.p1 = b.y; e.dst = b.z; e.flags = b.w;
   return e;
 }
+DEVA_HD uint32_t ld_u32_cg(const uint32_t *p) { return __ldcg(p); }
 #else
+DEVA_HD uint32_t ld_u32_cg(const uint32_t *p) { return *p; }
 DEVA_HD unsigned long long atom_add_u64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 DEVA_HD void atom_min_ull(unsigned long long *p, unsigned long long v) { if (v < *p) *p = v; }
 DEVA_HD EvRec ld_ev_cg(const EvRec *p) { return *p; }
@@ -299,10 +301,9 @@ DEVA_HD void append_far(const TView &v, const Epoch &ep, const EvRec &rec, uint3
     if (b < ep.cur_abs) atom_or_u32(&c->need_rebase, 1u);   // a root below the calendar's base
   }
 }
-// One record into this GPU's lists.  Whatever the destination - a late list, a bucket's list, the far list -
-// the place is claimed by ONE atomic that every lane of the warp issues together (the counters are 32-bit
-// words, the late lists' a tagged 64-bit one: a 64-bit add on the aligned pair serves all of them), so a warp
-// whose lanes go different ways pays one round trip, not one per way.
+// One record into this GPU's lists.  A bucket's list and the far list are claimed by the same atomic
+// instruction, issued by the warp's lanes together whichever of the two they go to; the late lists (tagged
+// 64-bit counters) by a second one.
 DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uint32_t *bh, uint32_t *err) {
   const uint64_t dl64 = (uint64_t)rec.dst - v.lp_begin;
   if (dl64 >= v.A) { *err |= ERR_NOT_OWNER; return; }
@@ -319,17 +320,17 @@ DEVA_HD void append_local(const TView &v, const Epoch &ep, const EvRec &rec, uin
   const uint64_t d = b - ep.cur_abs;                 // (wraps to huge when b < cur_abs: goes to far, flagged)
   const bool in_ring = !late && d < NB && b < ep.ring_hi;   // (the open buckets themselves only when t_end cuts them: evaluations then read frozen counts)
   const uint32_t slot = (uint32_t)(b % NB);
-  // ---- where, and which counter
-  uint32_t *ctr = late ? reinterpret_cast<uint32_t *>(&v.lcnt[ep.par][tile]) : in_ring ? &v.ncnt[(size_t)tile * NB + slot] : &v.fcnt[tile];
+  // ---- where, and which counter.  (Two atomic widths - the late lists' tagged 64-bit counters, 32-bit ones
+  // elsewhere - and never both on one word: atomicity between overlapping accesses of different sizes is not
+  // something the memory model promises.)
   EvRec *list = late ? v.late[ep.par] + (size_t)tile * v.CL : in_ring ? v.near_ + ((size_t)tile * NB + slot) * v.C : v.far_ + (size_t)tile * v.CF;
   const uint32_t cap = late ? v.CL : in_ring ? v.C : v.CF;
-  const bool hi = (reinterpret_cast<uintptr_t>(ctr) & 4u) != 0;
-  unsigned long long *ctr64 = reinterpret_cast<unsigned long long *>(reinterpret_cast<uintptr_t>(ctr) & ~(uintptr_t)7);
-  uint32_t mark = ep.launch;
-  if (late) mark = atom_exch_u32(&v.dmark[tile], ep.launch);   // (in flight together with the claim)
-  const unsigned long long old = atom_add_u64(ctr64, hi ? (1ull << 32) : 1ull);
-  uint32_t p = hi ? (uint32_t)(old >> 32) : (uint32_t)old;
-  if (late) p = late_claim_finish(ctr64, old, ep.epoch);
+  uint32_t mark = ep.launch, p;
+  if (late) {
+    mark = atom_exch_u32(&v.dmark[tile], ep.launch);   // (in flight together with the claim)
+    unsigned long long *lc = &v.lcnt[ep.par][tile];
+    p = late_claim_finish(lc, atom_add_u64(lc, 1ull), ep.epoch);
+  } else p = atom_add_u32(in_ring ? &v.ncnt[(size_t)tile * NB + slot] : &v.fcnt[tile], 1u);
   if (p < cap) st_ev(&list[p], rec);
   if (late) {
     if (mark != ep.launch)                                                        // first arrival of this launch:
@@ -743,7 +744,7 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
   // their places - in the tile's bucket lists, in this GPU's region of the peer's receive buffer - and their
   // stores wait for nothing.  The others (another tile, the open window, beyond the horizon) were listed:
   // their atomics leave in one go, every lane busy.
-  if (FULLK) { TL_THREADS(tid) { if (tid == (int)TL_NTHR - 1) prefetch_header(v, ep, h, h.next_item); } }
+  if (FULLK) { TL_THREADS(tid) { if (tid == 0) prefetch_header(v, ep, h, h.next_item); } }   // (thread 0: cp.async completion is tracked per thread, and thread 0 is the one that waits for it)
   if (h.first) {
     const uint16_t *gen = reinterpret_cast<const uint16_t *>(b.cur);
     TL_THREADS(tid) {
@@ -1456,7 +1457,8 @@ DEVA_HD void open_epoch_snapshot(const TView &v) {
   TL_THREADS(tid) {
     for (uint32_t t = tid; t < v.NT; t += TL_NTHR)
       for (uint32_t k = 0; k < m; k++) {
-        const uint32_t nc = v.ncnt[(size_t)t * NB + (uint32_t)((cur + k) % NB)];
+        // (read at L2: this SM's L1 may hold the counter line as it was when a header of this launch read it)
+        const uint32_t nc = ld_u32_cg(&v.ncnt[(size_t)t * NB + (uint32_t)((cur + k) % NB)]);
         v.npub[(size_t)t * MAXM + k] = nc < v.C ? nc : v.C;
       }
   }

@@ -58,10 +58,11 @@ __device__ __forceinline__ void publish_counts(const TView &v) {
 }
 
 // One round's closing with several GPUs: receive what the peers stored here, exchange the job-wide figures,
-// run the epoch state machine - identically on every GPU, without the host and without NCCL.  Called by EVERY
-// block of the launch once its own part of the step is done (the step kernel runs straight on into it: a
-// block that finishes early waits here for the peers' records instead of leaving), `ws` = a block's
-// scratch in shared memory (xchg_ws_bytes).
+// run the epoch state machine - identically on every GPU, without the host and without NCCL.  Runs as a kernel
+// of its own behind every step kernel (k_tile_xchg).  -DDEVA_TILE_XCHG_FUSED instead lets every block of the
+// step kernel run straight on into it (a block that finishes early waits for the peers' records instead of
+// leaving): measured 3 % SLOWER on 2 GPUs (33.65 vs 34.56 ms per 2 M-LP drain, same box) and not the default.
+// `ws` = a block's scratch in shared memory.
 struct XWs {
   PeerMsg msgs[MAX_GPUS];
   Glob g;
@@ -293,10 +294,14 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
 #endif
   }
   if (v.n_gpus > 1) {
-    // several GPUs: the last block tells the peers how many records this GPU left them; every block then goes
-    // on into the round's closing (the workspace is free now: the exchange's scratch lives in it)
+    // several GPUs: the last block tells the peers how many records this GPU left them; the round's closing
+    // follows as a kernel of its own
+#ifndef DEVA_TILE_XCHG_FUSED
+    if (is_last) { if (threadIdx.x == 0) c->stepped = 1; publish_counts(v); }
+#else
     if (is_last) publish_counts(v);
     exchange_round(v, tp, ep, *reinterpret_cast<XWs *>(tl_smem), 0);
+#endif
     return;
   }
   if (!is_last) return;
@@ -306,6 +311,18 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
   close_launch(v, tp, g);
 }
 
+#ifndef DEVA_TILE_XCHG_FUSED
+// the round's closing, launched after every step kernel (a no-op when that launch was one)
+__global__ void __launch_bounds__(256) k_tile_xchg(const __grid_constant__ TView v, const __grid_constant__ TParams tp) {
+  __shared__ XWs ws;
+  TCtl *c = v.ctl;
+  if (c->phase != PH_EVAL && c->phase != PH_REBIN) return;
+  if (!c->stepped) return;
+  const Epoch ep = load_epoch(c);
+  exchange_round(v, tp, ep, ws, 0);
+  if (threadIdx.x == 0 && ws.is_last) c->stepped = 0;
+}
+#endif
 // drain entry with several GPUs (after k_tile_begin_multi): the exchange alone, which picks the first epoch
 __global__ void __launch_bounds__(256) k_tile_xchg_begin(const __grid_constant__ TView v, const __grid_constant__ TParams tp) {
   __shared__ XWs ws;
@@ -621,6 +638,9 @@ struct CudaBE {
     lc.attrs = at; lc.numAttrs = 1;
     if (full) TCU(cudaLaunchKernelEx(&lc, k_tile_step<M, true>, v, mp, tp));
     else TCU(cudaLaunchKernelEx(&lc, k_tile_step<M, false>, v, mp, tp));
+#ifndef DEVA_TILE_XCHG_FUSED
+    if (v.n_gpus > 1) k_tile_xchg<<<xchg_grid, 256, 0, stream>>>(v, tp);
+#endif
     TCU(cudaGetLastError());
     return 0;
   }

@@ -112,6 +112,7 @@ struct TCtl {
   // ---- multi-GPU
   uint32_t send_n[MAX_GPUS];       // records stored into each peer's receive region in this launch
   uint32_t round, xticket;
+  uint32_t stepped, spad;          // the step kernel of this round did work (else the exchange kernel behind it is a no-op, too)
   PeerMsg agg;                     // job-wide sums of the last round
   unsigned long long g_exec0, g_commit0;
 #ifdef DEVA_TILE_PROF
