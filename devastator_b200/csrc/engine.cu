@@ -660,6 +660,12 @@ int deva_b200_reset(deva_b200_engine *e) {
   return 0;
 }
 
+int deva_b200_set_heartbeat(deva_b200_engine *e, double secs, deva_b200_heartbeat_fn cb, void *user) {
+  if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (e->tile) { e->tile->hb_secs = secs; e->tile->hb_fn = cb; e->tile->hb_user = user; }   // (the LP engine has no heartbeat)
+  return 0;
+}
+
 int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) {
   if (!e) return fail(DEVA_B200_ERR_ARG, "null argument");
   if (e->tile) { e->tile->stop_req.store(stop); return 0; }

@@ -394,6 +394,13 @@ std::uint64_t pdes::drain(std::uint64_t t_end, bool rewindable) {   // pdes.cxx:
         ck(deva_b200_create(&cfg, &g_sim.engs[std::size_t(g)]), "deva_b200_create");
       }
       g_sim.eng = g_sim.engs[0];
+      // pdes::drain()'s status block (pdes.cxx:282-301), printed by the thread that drains engine 0
+      if(pdes::chitter_secs > 0 && pdes::chitter_io != nullptr && deva::os_env<bool>("pdes_heartbeat", true))
+        deva_b200_set_heartbeat(g_sim.eng, double(pdes::chitter_secs), [](void*, std::uint64_t gvt, std::uint64_t window, double cps, double eff) {
+          (*pdes::chitter_io) << "pdes::drain() status:\n" << "  gvt = " << double(gvt) << '\n' << "  lookahead = " << float(window) << '\n'
+                              << "  commits/sec = " << cps << '\n' << "  efficiency = " << eff << '\n' << '\n';
+          pdes::chitter_io->flush();
+        }, nullptr);
       ck(deva_b200_comm_init_group(g_sim.engs.data(), n_gpus), "deva_b200_comm_init_group");
     }
     const int stw = deva_b200_state_words(g_sim.eng);

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -77,6 +78,10 @@ struct TileEngine {
   std::vector<void *> ipc_open;   // peer mappings to close
   // drain timer (counterpart of the reference's DrainTimer, pdes.hxx:139-308): one CSV row per batch
   std::string timer_path;
+  // heartbeat (pdes.cxx:282-301)
+  double hb_secs = 0;
+  deva_b200_heartbeat_fn hb_fn = nullptr;
+  void *hb_user = nullptr;
 
   int create(const deva_b200_config *c) {
     cfg = *c;
@@ -263,6 +268,8 @@ struct TileEngine {
     uint64_t guard = 0;
     int slot = 0;
     uint32_t stop_sent = hc.stop_req;
+    auto hb_t0 = std::chrono::steady_clock::now();
+    unsigned long long hb_c0 = hc.committed, hb_x0 = hc.executed;
     if ((rc = enqueue(slot))) { if (tf) fclose(tf); return rc; }
     for (;;) {
       TCtl before = hc;
@@ -279,6 +286,15 @@ struct TileEngine {
       if (tf) fprintf(tf, "%llu,%llu,%llu,%u,%llu,%llu,%llu,%.4f\n", (unsigned long long)before.gvt, (unsigned long long)hc.win_m << hc.shift,
                       (unsigned long long)(hc.epochs - before.epochs), hc.launch - before.launch, (unsigned long long)(hc.executed - before.executed),
                       (unsigned long long)(hc.rolled - before.rolled), (unsigned long long)(hc.committed - before.committed), bms);
+      if (hb_fn && hb_secs > 0) {
+        const auto now = std::chrono::steady_clock::now();
+        const double dt = std::chrono::duration<double>(now - hb_t0).count();
+        if (dt >= hb_secs) {
+          const unsigned long long dc = hc.committed - hb_c0, dx = hc.executed - hb_x0;
+          hb_fn(hb_user, hc.gvt, (uint64_t)hc.win_m << hc.shift, (double)dc / dt, dx ? (double)dc / (double)dx : 1.0);
+          hb_t0 = now; hb_c0 = hc.committed; hb_x0 = hc.executed;
+        }
+      }
       if (hc.err) { be.batch_wait(v, slot, nullptr, nullptr); if (tf) fclose(tf); return check_err(); }
       if (hc.phase == PH_DONE) break;
       if (hc.launch == before.launch && ++guard > 4) { be.batch_wait(v, slot, nullptr, nullptr); if (tf) fclose(tf); return tile_fail(DEVA_B200_ERR_INVARIANT, "tile engine: the step kernel makes no progress (phase %u)", hc.phase); }

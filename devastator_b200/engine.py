@@ -54,7 +54,7 @@ ABI_SYMBOLS = [
     "deva_b200_state_words", "deva_b200_set_lp_state", "deva_b200_get_lp_state", "deva_b200_root_events",
     "deva_b200_seed_phold", "deva_b200_drain", "deva_b200_rewind", "deva_b200_get_stats", "deva_b200_set_stop",
     "deva_b200_digest", "deva_b200_comm_unique_id", "deva_b200_comm_init", "deva_b200_stream",
-    "deva_b200_reset", "deva_b200_comm_init_group",
+    "deva_b200_reset", "deva_b200_comm_init_group", "deva_b200_set_heartbeat",
 ]
 
 
@@ -62,6 +62,9 @@ class EngineError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"deva_b200 error {code}: {msg}")
         self.code = code
+
+
+HEARTBEAT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double)
 
 
 class Api:
@@ -91,6 +94,7 @@ class Api:
         L.deva_b200_reset.argtypes = [P]
         L.deva_b200_stream.restype = P
         L.deva_b200_comm_init_group.argtypes = [C.POINTER(P), C.c_int32]
+        L.deva_b200_set_heartbeat.argtypes = [P, C.c_double, HEARTBEAT_FN, P]
 
     def check(self, rc):
         if rc != 0:
@@ -209,6 +213,11 @@ class Engine:
         s = Stats()
         self.api.check(self.api.lib.deva_b200_get_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def set_heartbeat(self, secs, fn):
+        """fn(gvt, window, commits_per_sec, efficiency) about every `secs` seconds of a drain (pdes::chitter_secs)"""
+        self._hb = HEARTBEAT_FN(lambda user, gvt, window, cps, eff: fn(gvt, window, cps, eff)) if fn else C.cast(None, HEARTBEAT_FN)
+        self.api.check(self.api.lib.deva_b200_set_heartbeat(self.h, float(secs), self._hb, None))
 
     def set_stop(self, stop):
         self.api.check(self.api.lib.deva_b200_set_stop(self.h, int(stop)))

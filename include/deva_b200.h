@@ -140,6 +140,13 @@ int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]);
  * caller: events must be recorded on the launching stream). */
 void *deva_b200_stream(deva_b200_engine *e);
 
+/* Heartbeat (replaces the status block pdes::drain prints every pdes::chitter_secs seconds,
+ * pdes.cxx:282-301): while a drain runs, `cb` is called from the draining thread about every `secs`
+ * seconds with the commit horizon, the optimism window, committed events per second and the efficiency
+ * (committed / executed) since the last call.  secs <= 0 or cb == NULL switches it off. */
+typedef void (*deva_b200_heartbeat_fn)(void *user, uint64_t gvt, uint64_t window, double commits_per_sec, double efficiency);
+int deva_b200_set_heartbeat(deva_b200_engine *e, double secs, deva_b200_heartbeat_fn cb, void *user);
+
 /* Multi-GPU (replaces world_gasnet / threads transports and gvt.cxx's credit-counted reduction).
  * uid = 128-byte ncclUniqueId made by rank 0.  With one process per GPU the engines map each other's
  * receive buffers (CUDA IPC) and the execute kernel stores cross-GPU records straight into the

@@ -218,6 +218,10 @@ int deva_b200_seed_phold(deva_b200_engine *e, uint32_t k, int32_t rootdiv, int32
   return 0;
 }
 
+int deva_b200_set_heartbeat(deva_b200_engine *e, double secs, deva_b200_heartbeat_fn cb, void *user) {
+  if (e->tile) { e->tile->hb_secs = secs; e->tile->hb_fn = cb; e->tile->hb_user = user; }
+  return 0;
+}
 int deva_b200_set_stop(deva_b200_engine *e, int32_t stop) { if (e->tile) { e->tile->stop_req = stop; return 0; } e->mp.stop = stop; return 0; }
 int deva_b200_reset(deva_b200_engine *e) { if (e->tile) return e->tile->reset(); init_lps(e, 0); e->par = 0; e->has_rewind = false; return 0; }
 

@@ -288,3 +288,23 @@ def test_drain_timer_csv_rows_add_up(api, engine_kind, tmp_path, monkeypatch):
         assert sum(int(r["committed"]) for r in rows) == st["committed_n"]
     times = [int(r["sim_time"]) for r in rows]
     assert times == sorted(times)
+
+
+def test_heartbeat_callback(api, engine_kind):
+    """deva_b200_set_heartbeat: the counterpart of pdes::drain()'s status block (pdes.cxx:282-301)"""
+    if engine_kind != "tile":
+        pytest.skip("the first engine has no heartbeat")
+    beats = []
+    eng = S.make(api, 4096, P=0.5, LAM=100.0, END=400, sub=1)
+    eng.set_heartbeat(1e-9, lambda gvt, window, cps, eff: beats.append((gvt, window, cps, eff)))   # (every batch)
+    eng.seed_phold(16, 1, 1)
+    eng.drain()
+    assert len(beats) >= 2
+    assert all(0 < b[3] <= 1.0 for b in beats) and all(b[1] >= 1 for b in beats)
+    assert [b[0] for b in beats] == sorted(b[0] for b in beats)
+    n = len(beats)
+    eng.set_heartbeat(0, None)
+    eng.seed_phold(16, 1, 1)
+    eng.drain()
+    assert len(beats) == n
+    eng.close()
