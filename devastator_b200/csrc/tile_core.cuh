@@ -204,6 +204,7 @@ struct Blk {
   uint32_t rcap;
   uint32_t mphase;   // mbarrier phase parity (uniform across the block)
   uint64_t tile_gid; // first LP of the tile being evaluated (run_records)
+  const uint32_t *next_reg;   // thread 0: the register that holds the next work item (its atomic's result is first needed at the flush), or null
   unsigned char *pool; uint32_t pool_bytes;   // R | S | ord | efl as one region: the warps' workspaces in a follow-up launch
 };
 enum : uint8_t { F_OWN = 1 /* flush only: a child that stays in its tile */, F_FRESH = 1, F_ANTI = 2, F_INOLD = 4, F_INNEW = 8, F_CN = 16, F_CO = 32, F_OUT = 64, F_DEAD = 128 };
@@ -234,6 +235,7 @@ DEVA_HD void blk_carve(Blk &b, unsigned char *base, uint32_t rcap) {
   b.h = reinterpret_cast<Hdr *>(base + o); o += sizeof(Hdr); o = (o + 15) & ~(size_t)15;
   b.mbar = reinterpret_cast<uint64_t *>(base + o);
   b.mphase = 0;
+  b.next_reg = nullptr;
 }
 
 // (time, subtime) is the reference's order (stamped_event::operator<, pdes.hxx:936-941); ties - which the
@@ -744,7 +746,7 @@ DEVA_HD void run_records(const TView &v, const ModelParams &mp, const Epoch &ep,
   // their places - in the tile's bucket lists, in this GPU's region of the peer's receive buffer - and their
   // stores wait for nothing.  The others (another tile, the open window, beyond the horizon) were listed:
   // their atomics leave in one go, every lane busy.
-  if (FULLK) { TL_THREADS(tid) { if (tid == 0) prefetch_header(v, ep, h, h.next_item); } }   // (thread 0: cp.async completion is tracked per thread, and thread 0 is the one that waits for it)
+  if (FULLK) { TL_THREADS(tid) { if (tid == 0) { if (b.next_reg) h.next_item = *b.next_reg; prefetch_header(v, ep, h, h.next_item); } } }   // (thread 0: cp.async completion is tracked per thread, and thread 0 is the one that waits for it)
   if (h.first) {
     const uint16_t *gen = reinterpret_cast<const uint16_t *>(b.cur);
     TL_THREADS(tid) {
@@ -882,7 +884,7 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     if (ep.sp_w_n > 0 || ep.sp_r_n > 0) h.skip = 0;
     // its last evaluation's epoch is committed: that result is the state now (a tile that is skipped
     // keeps the swap for the evaluation that will update tev)
-    if (!h.skip && h.first && tev != NEVER) { v.tcur[tile] ^= 1u; h.in_buf ^= 1u; }
+    if (!h.skip && h.first && tev != NEVER) { h.in_buf ^= 1u; v.tcur[tile] = h.in_buf; }   // (a store: the old value is in hand)
     h.used_far = 0; h.seg_big = 0; h.any_anti = 0;
   }
   TL_SYNC();
@@ -1039,13 +1041,12 @@ DEVA_HD void eval_tile(const TView &v, const ModelParams &mp0, const Epoch &ep, 
     v.lseen[rd][tile] = h.nl;
     v.lseen[ep.par][tile] = h.nlw;
     if (h.first) {   // this epoch's flags (TF_OVF is the appenders')
-      const uint32_t keep = v.tflags[tile] & TF_OVF;
-      const uint32_t want = keep | (idx ? (uint32_t)TF_IDX : 0u) | ((h.slow || h.seg_big) ? (uint32_t)TF_HEAVY : 0u);
+      const uint32_t want = (idx ? (uint32_t)TF_IDX : 0u) | ((h.slow || h.seg_big) ? (uint32_t)TF_HEAVY : 0u);
 #if defined(__CUDA_ARCH__)
-      atomicAnd(&v.tflags[tile], (uint32_t)TF_OVF);
-      atomicOr(&v.tflags[tile], want);
+      atomicAnd(&v.tflags[tile], (uint32_t)TF_OVF);   // (two fire-and-forget atomics: nothing is read back)
+      if (want) atomicOr(&v.tflags[tile], want);
 #else
-      v.tflags[tile] = want;
+      v.tflags[tile] = (v.tflags[tile] & TF_OVF) | want;
 #endif
     }
     if (h.used_far) h.ovf = 1;
@@ -1121,7 +1122,7 @@ DEVA_HD void follow_tiles_warp(const TView &v, const ModelParams &mp0, const Epo
     const uint32_t tev = v.tev[tile];
     t.first = tev != ep.epoch;
     t.in_buf = v.tcur[tile];
-    if (t.first && tev != NEVER) { v.tcur[tile] ^= 1u; t.in_buf ^= 1u; }   // (see eval_tile)
+    if (t.first && tev != NEVER) { t.in_buf ^= 1u; v.tcur[tile] = t.in_buf; }   // (see eval_tile)
     const uint32_t lc = late_count(v.lcnt[rd][tile], ep.epoch);
     t.nl = lc < v.CL ? lc : v.CL;
     t.nlw = t.first ? 0u : v.lseen[ep.par][tile];

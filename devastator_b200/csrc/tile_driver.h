@@ -64,7 +64,7 @@ struct TileEngine {
   int stw = 0;
   BE be;
   TCtl hc;                     // host copy of the control block (last read)
-  uint32_t batch = 16;         // launches enqueued between two reads of the control block
+  uint32_t batch = 32;         // launches enqueued between two reads of the control block
   uint64_t launches = 0, passes0 = 0;
   double drain_ms = 0, exec_ms = 0;
   std::atomic<int32_t> stop_req{0};
@@ -107,7 +107,7 @@ struct TileEngine {
     tp.pol_density_x16 = env_u32("DEVA_B200_POL_DENSITY_X16", 40);
     tp.pol_occ_x16 = env_u32("DEVA_B200_POL_OCC_X16", 72);
     tp.pol_m_max = std::min<uint32_t>(MAXM, std::max<uint32_t>(1, env_u32("DEVA_B200_POL_M_MAX", 2)));
-    batch = std::max<uint32_t>(1, env_u32("DEVA_B200_TILE_BATCH", 16));
+    batch = std::max<uint32_t>(1, env_u32("DEVA_B200_TILE_BATCH", 32));
     int rc;
     if ((rc = be.open(c->device, tp.rcap))) return rc;
     if (const char *tpth = getenv("DEVA_B200_DRAIN_TIMER")) timer_path = tpth;

@@ -188,15 +188,19 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
   const bool all_tiles = phase == PH_REBIN || c->full;
   if (all_tiles) {
     const uint32_t rebin_all = c->rebin_all;
+    uint32_t nx = 0;                // thread 0: the next work item, kept in a register until the tile's flush (or its end):
+    b.next_reg = &nx;               // storing it to shared memory at once would stall on the atomic's round trip
     for (;;) {
       const uint32_t w = b.h->next_item;
       __syncthreads();
       if (w >= v.NT) break;
-      if (threadIdx.x == 0) b.h->next_item = atomicAdd(&c->work, 1u);   // (its round trip hides behind this tile's work)
+      if (threadIdx.x == 0) nx = atomicAdd(&c->work, 1u);
       if (phase == PH_EVAL) eval_tile<M, FULLK>(v, mp, ep, b, w);
       else rebin_tile(v, ep, b, w, v.scratch + (size_t)blockIdx.x * v.scratch_cap, rebin_all);
+      if (threadIdx.x == 0) b.h->next_item = nx;
       __syncthreads();
     }
+    b.next_reg = nullptr;
   } else if (!FULLK) {
     // ---- follow-up launch: the tiles that received in-window arrivals during the previous launch.
     // Pass 1, warps on their own (no block barrier): a warp pulls a few tiles off the list, one lane classifies
@@ -500,7 +504,7 @@ struct CudaBE {
     const int cap = (int)env_u32("DEVA_B200_TILE_BLOCKS_PER_SM", 16);
     grid = prop.multiProcessorCount * std::max(1, std::min(occ_full, cap));
     grid_follow = prop.multiProcessorCount * std::max(1, std::min(occ_follow, cap));
-    xchg_grid = prop.multiProcessorCount;
+    xchg_grid = prop.multiProcessorCount * (int)std::max<uint32_t>(1, env_u32("DEVA_B200_XCHG_BLOCKS_PER_SM", 1));
     pattern = std::max<uint32_t>(2, env_u32("DEVA_B200_TILE_PATTERN", 4));
     pdl = env_u32("DEVA_B200_TILE_PDL", 1) != 0;
     if (getenv("DEVA_B200_TILE_VERBOSE")) fprintf(stderr, "deva_b200 tile engine: TILE %d, %d threads, rcap %u, smem %zu B, blocks/SM full %d follow %d\n", TILE, NTHR, rcap, smem, occ_full, occ_follow);
