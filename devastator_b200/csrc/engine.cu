@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) k_pass(const __grid_consta
   // wake list written by the previous pass (follow-up pass: only LPs that received records).
   const uint32_t i = blockIdx.x * PASS_THREADS + threadIdx.x;
   Acc acc;
-  acc.tmin = ~0ull; acc.stall = ~0ull;
+  acc.tmin = ~0ull;
   acc.executed = acc.committed = acc.rolled = acc.anti = acc.remote = acc.err = acc.nondet = 0;
   uint32_t lp = 0xffffffffu;
   if (list_n == 0) { if (i < v.A) lp = i; }
@@ -296,13 +296,13 @@ struct deva_b200_engine {
   void *comm = nullptr;
   EvRec *recvbuf = nullptr;
   std::vector<void *> ipc_open;    // peer mappings to close
-  uint32_t *d_counts = nullptr;    // [2][MAX_GPUS]: send counts row, recv counts row
+  uint32_t *d_counts = nullptr;    // [MAX_GPUS][MAX_GPUS]: every rank's send_n row (all-gathered count matrix)
   uint32_t *h_counts = nullptr;    // pinned
   unsigned long long *h_red = nullptr;  // pinned: allreduce results
   uint64_t g_exec = 0, g_rolled = 0;    // job-wide cumulative counters at the previous pass (multi-GPU)
   unsigned long long *d_red = nullptr;  // allreduce scratch
   bool profile = true;
-  int pass_variant = 6;   // k_pass<M, MINB> instantiation (DEVA_B200_PASS_MINB = 4 | 6 | 8)
+  int pass_variant = 6;   // k_pass<M, MINB> instantiation (DEVA_B200_PASS_MINB = 4 | 5 | 6 | 8)
   uint32_t pass_tag = 0;  // serial number of the last pass (wake-list dedup tag)
   char *stage = nullptr;  // grow-only device staging for host-buffer calls (no cudaMalloc/cudaFree per call)
   size_t stage_bytes = 0;
@@ -362,7 +362,6 @@ static const char *err_text(uint32_t err) {
   static thread_local char buf[256];
   buf[0] = 0;
   if (err & ERR_PQ_OVERFLOW) strcat(buf, "pending slots of an LP overflowed (raise pq_cap); ");
-  if (err & ERR_LOG_STALL) strcat(buf, "undo log stalled; ");
   if (err & ERR_ANTI_UNMATCHED) strcat(buf, "anti-message without matching event; ");
   if (err & ERR_SELF_CHILD_LOST) strcat(buf, "self-sent child not found on rollback; ");
   if (err & ERR_SPILL_OVERFLOW) strcat(buf, "inbox spill buffer overflowed (raise inbox_cap); ");

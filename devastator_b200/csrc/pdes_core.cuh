@@ -141,7 +141,6 @@ constexpr uint32_t FL_SENT = 0x80000000u;   // LogRec::fl "sent a child" bit
 // per-thread accumulators, block-reduced by the kernel wrapper
 struct Acc {
   uint64_t tmin;     // min time over everything this thread leaves pending or emits (-> next GVT)
-  uint64_t stall;    // min time of an in-window event this thread could not run (working set / undo log full)
   uint32_t executed, committed, rolled, anti, remote, err, nondet;
 };
 
@@ -640,7 +639,8 @@ DEVA_HD void lp_pass(const View &v, const ModelParams &mp, const PassArgs &pa, u
   v.head[lp] = khead;
   v.lmeta[lp] = ln | (lt << 16);
   if (khead < acc.tmin) acc.tmin = khead;
-  if (khead < pa.ub && khead < acc.stall) acc.stall = khead;   // an in-window record could not run (capacity)
+  // (an in-window record that could not run for lack of room in the working set or the undo log stays in the pool:
+  //  it bounds the GVT through khead and runs in the next epoch's full pass)
 }
 
 // Between windows: put records (roots, inbox spill, records received from peer GPUs) into the

@@ -66,7 +66,7 @@ struct DEVA_ALIGN(16) LogRec {
 static_assert(sizeof(LogRec) == 64, "LogRec must be 64 bytes");
 
 enum : uint32_t {
-  ERR_PQ_OVERFLOW = 1u, ERR_LOG_STALL = 2u, ERR_ANTI_UNMATCHED = 4u, ERR_SELF_CHILD_LOST = 8u,
+  ERR_PQ_OVERFLOW = 1u, /* 2u: unused */ ERR_ANTI_UNMATCHED = 4u, ERR_SELF_CHILD_LOST = 8u,
   ERR_SPILL_OVERFLOW = 16u, ERR_SEND_OVERFLOW = 32u, ERR_NOT_OWNER = 64u, ERR_BELOW_GVT = 128u
 };
 
@@ -84,7 +84,6 @@ struct Ctl {
   uint32_t spill_n;               // records in the spill buffer (inbox overflow)
   uint32_t send_n[MAX_GPUS];      // records staged for each peer GPU
   uint32_t wake_n[2];             // LPs woken for the next / current follow-up pass (double-buffered)
-  unsigned long long stall_min;   // min time of an in-window event that could not run (capacity): bounds the next epoch
 };
 
 struct View {

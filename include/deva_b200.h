@@ -133,7 +133,7 @@ int deva_b200_set_stop(deva_b200_engine *e, int32_t stop);
 
 /* Digest of this engine's LPs, computed on the device: out[0] = XOR of state word (state_words-1)
  * (== test/phold.cxx:138-148 checksum()), out[1] = order-sensitive 64-bit hash of all state words,
- * out[2] = pending-event count, out[3] = XOR-hash of the pending-event records. */
+ * out[2] = pending-event count, out[3] = additive hash (sum mod 2^64) of the pending-event records. */
 int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]);
 
 /* The cudaStream_t every kernel and copy of this engine is issued on (for CUDA-event timing by the

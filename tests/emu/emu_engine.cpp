@@ -237,7 +237,7 @@ static void pass_one(deva_b200_engine *e, const PassArgs &pa, bool full, uint64_
     for (size_t i = order.size(); i > 1; i--) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; std::swap(order[i - 1], order[s % i]); }
   }
   e->ctl.wake_n[pa.par ^ 1u] = 0;
-  Acc acc; memset(&acc, 0, sizeof acc); acc.tmin = ~0ull; acc.stall = ~0ull;
+  Acc acc; memset(&acc, 0, sizeof acc); acc.tmin = ~0ull;
   dispatch_model(e->cfg.model, [&](auto m) {
     using M = decltype(m);
     for (uint32_t lp : order) lp_pass<M>(v, e->mp, pa, lp, acc);
