@@ -24,6 +24,7 @@
 #include "pdes_core.cuh"
 #include "window_policy.h"
 #include "tile_engine.cuh"
+#include "hostq.cuh"
 
 using namespace deva_b200;
 
@@ -1047,6 +1048,119 @@ static int tile_comm_init(deva_b200_engine *e, const NcclUid &uid) {
   if (nrc) return fail(DEVA_B200_ERR_COMM, "NCCL failed while exchanging IPC handles: %s", g_nccl.GetErrorString(nrc));
   if (!ok) return fail(DEVA_B200_ERR_COMM, "CUDA IPC peer mapping unavailable: the tile engine needs it (DEVA_B200_ENGINE=lp has a staged NCCL transport)");
   t->peers_ready();
+  return 0;
+}
+
+// ---- host-executed handlers: the device-resident pending-event pool (hostq.cuh) -----------------------------
+struct deva_b200_hostq {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t cap = 0, n = 0;            // records the pool holds (host copy of the count)
+  hq::Cols pool[2], sel, out;         // the pool (two halves: compaction goes from one to the other), the horizon's records, sorted
+  int cur = 0;
+  uint32_t *idx = nullptr;
+  hq::Ctl *ctl = nullptr, *h_ctl = nullptr;
+  void *tmp = nullptr; size_t tmp_bytes = 0;
+  unsigned long long *h_t = nullptr, *h_s = nullptr, *h_h = nullptr; uint32_t *h_lp = nullptr; uint64_t h_cap = 0;   // pinned staging
+};
+static int hq_cols_alloc(hq::Cols &c, uint64_t n) {
+  CU(cudaMalloc((void **)&c.t, n * 8)); CU(cudaMalloc((void **)&c.s, n * 8)); CU(cudaMalloc((void **)&c.h, n * 8)); CU(cudaMalloc((void **)&c.lp, n * 4));
+  return 0;
+}
+static void hq_cols_free(hq::Cols &c) { cudaFree(c.t); cudaFree(c.s); cudaFree(c.h); cudaFree(c.lp); }
+static int hq_stage(deva_b200_hostq *q, uint64_t n) {
+  if (n <= q->h_cap) return 0;
+  if (q->h_t) { cudaFreeHost(q->h_t); cudaFreeHost(q->h_s); cudaFreeHost(q->h_h); cudaFreeHost(q->h_lp); }
+  const uint64_t m = std::max<uint64_t>(n, 1u << 16);
+  CU(cudaHostAlloc((void **)&q->h_t, m * 8, cudaHostAllocDefault)); CU(cudaHostAlloc((void **)&q->h_s, m * 8, cudaHostAllocDefault));
+  CU(cudaHostAlloc((void **)&q->h_h, m * 8, cudaHostAllocDefault)); CU(cudaHostAlloc((void **)&q->h_lp, m * 4, cudaHostAllocDefault));
+  q->h_cap = m;
+  return 0;
+}
+int deva_b200_hostq_create(int32_t device, uint64_t capacity, deva_b200_hostq **out) {
+  if (!out) return fail(DEVA_B200_ERR_ARG, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(DEVA_B200_ERR_CUDA, "no CUDA device: this engine has no CPU path");
+  CU(cudaSetDevice(device));
+  deva_b200_hostq *q = new deva_b200_hostq;
+  q->device = device;
+  q->cap = capacity ? capacity : (1ull << 22);
+  if (q->cap > 0x7fffffffull) { delete q; return fail(DEVA_B200_ERR_ARG, "hostq capacity too large"); }
+  int rc = 0;
+  if ((rc = hq_cols_alloc(q->pool[0], q->cap)) || (rc = hq_cols_alloc(q->pool[1], q->cap)) || (rc = hq_cols_alloc(q->sel, q->cap)) || (rc = hq_cols_alloc(q->out, q->cap))) { deva_b200_hostq_destroy(q); return rc; }
+  if (cudaMalloc((void **)&q->idx, q->cap * 4) != cudaSuccess || cudaMalloc((void **)&q->ctl, sizeof(hq::Ctl)) != cudaSuccess ||
+      cudaHostAlloc((void **)&q->h_ctl, sizeof(hq::Ctl), cudaHostAllocDefault) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) != cudaSuccess) { deva_b200_hostq_destroy(q); return fail(DEVA_B200_ERR_CUDA, "hostq allocation failed"); }
+  cub::DeviceMergeSort::SortKeys(nullptr, q->tmp_bytes, q->idx, (int)q->cap, hq::ByLpSub{q->sel}, q->stream);
+  if (cudaMalloc(&q->tmp, q->tmp_bytes ? q->tmp_bytes : 16) != cudaSuccess) { deva_b200_hostq_destroy(q); return fail(DEVA_B200_ERR_CUDA, "hostq allocation failed"); }
+  *out = q;
+  return 0;
+}
+void deva_b200_hostq_destroy(deva_b200_hostq *q) {
+  if (!q) return;
+  cudaSetDevice(q->device);
+  if (q->stream) cudaStreamSynchronize(q->stream);
+  hq_cols_free(q->pool[0]); hq_cols_free(q->pool[1]); hq_cols_free(q->sel); hq_cols_free(q->out);
+  cudaFree(q->idx); cudaFree(q->ctl); cudaFree(q->tmp);
+  if (q->h_ctl) cudaFreeHost(q->h_ctl);
+  if (q->h_t) { cudaFreeHost(q->h_t); cudaFreeHost(q->h_s); cudaFreeHost(q->h_h); cudaFreeHost(q->h_lp); }
+  if (q->stream) cudaStreamDestroy(q->stream);
+  delete q;
+}
+int deva_b200_hostq_push(deva_b200_hostq *q, uint64_t n, const uint64_t *time, const uint64_t *subtime, const uint32_t *lp, const uint64_t *handle) {
+  if (!q || (n && (!time || !subtime || !lp || !handle))) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (n == 0) return 0;
+  if (q->n + n > q->cap) return fail(DEVA_B200_ERR_CAPACITY, "host-handler event pool is full (%llu pending + %llu new > capacity %llu: DEVA_B200_HOSTQ_CAP)",
+                                     (unsigned long long)q->n, (unsigned long long)n, (unsigned long long)q->cap);
+  CU(cudaSetDevice(q->device));
+  int rc = hq_stage(q, n);
+  if (rc) return rc;
+  memcpy(q->h_t, time, n * 8); memcpy(q->h_s, subtime, n * 8); memcpy(q->h_h, handle, n * 8); memcpy(q->h_lp, lp, n * 4);
+  hq::Cols &p = q->pool[q->cur];
+  CU(cudaMemcpyAsync(p.t + q->n, q->h_t, n * 8, cudaMemcpyHostToDevice, q->stream)); CU(cudaMemcpyAsync(p.s + q->n, q->h_s, n * 8, cudaMemcpyHostToDevice, q->stream));
+  CU(cudaMemcpyAsync(p.h + q->n, q->h_h, n * 8, cudaMemcpyHostToDevice, q->stream)); CU(cudaMemcpyAsync(p.lp + q->n, q->h_lp, n * 4, cudaMemcpyHostToDevice, q->stream));
+  CU(cudaStreamSynchronize(q->stream));   // (the staging buffers are reused by the next call)
+  q->n += n;
+  return 0;
+}
+int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
+                            uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
+  if (!q || !n_out || !gvt_out) return fail(DEVA_B200_ERR_ARG, "null argument");
+  *n_out = 0; *gvt_out = ~0ull;
+  if (pending_out) *pending_out = q->n;
+  if (q->n == 0) return 0;
+  CU(cudaSetDevice(q->device));
+  const uint32_t n = (uint32_t)q->n;
+  const unsigned grid = (unsigned)std::min<uint32_t>((n + 255) / 256, 148 * 8);
+  hq::Cols &src = q->pool[q->cur], &keep = q->pool[q->cur ^ 1];
+  q->h_ctl->tmin = ~0ull; q->h_ctl->n_sel = 0; q->h_ctl->n_keep = 0;
+  CU(cudaMemcpyAsync(q->ctl, q->h_ctl, sizeof(hq::Ctl), cudaMemcpyHostToDevice, q->stream));
+  hq::k_hq_min<<<grid, 256, 0, q->stream>>>(src.t, n, q->ctl);                    // GVT: block + grid min-reduction
+  CU(cudaMemcpyAsync(q->h_ctl, q->ctl, sizeof(hq::Ctl), cudaMemcpyDeviceToHost, q->stream));
+  CU(cudaStreamSynchronize(q->stream));
+  *gvt_out = q->h_ctl->tmin;
+  if (q->h_ctl->tmin >= t_end) return 0;
+  hq::k_hq_split<<<grid, 256, 0, q->stream>>>(src, n, q->ctl, q->sel, keep);      // the horizon's events out, the rest compacted
+  CU(cudaMemcpyAsync(q->h_ctl, q->ctl, sizeof(hq::Ctl), cudaMemcpyDeviceToHost, q->stream));
+  CU(cudaStreamSynchronize(q->stream));
+  const uint32_t ns = q->h_ctl->n_sel, nk = q->h_ctl->n_keep;
+  if (ns + nk != n) return fail(DEVA_B200_ERR_INVARIANT, "hostq: compaction lost records");
+  if (ns > max_n) return fail(DEVA_B200_ERR_CAPACITY, "hostq: %u events at one time stamp, room for %llu", ns, (unsigned long long)max_n);
+  const unsigned g2 = (unsigned)std::min<uint32_t>((ns + 255) / 256, 148 * 8);
+  hq::k_hq_iota<<<g2, 256, 0, q->stream>>>(q->idx, ns);
+  size_t tb = q->tmp_bytes;
+  if (cub::DeviceMergeSort::SortKeys(q->tmp, tb, q->idx, (int)ns, hq::ByLpSub{q->sel}, q->stream) != cudaSuccess) return fail(DEVA_B200_ERR_CUDA, "hostq: sort failed");
+  hq::k_hq_gather<<<g2, 256, 0, q->stream>>>(q->sel, q->idx, ns, q->out);
+  CU(cudaGetLastError());
+  int rc = hq_stage(q, ns);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(q->h_t, q->out.t, (size_t)ns * 8, cudaMemcpyDeviceToHost, q->stream)); CU(cudaMemcpyAsync(q->h_s, q->out.s, (size_t)ns * 8, cudaMemcpyDeviceToHost, q->stream));
+  CU(cudaMemcpyAsync(q->h_h, q->out.h, (size_t)ns * 8, cudaMemcpyDeviceToHost, q->stream)); CU(cudaMemcpyAsync(q->h_lp, q->out.lp, (size_t)ns * 4, cudaMemcpyDeviceToHost, q->stream));
+  CU(cudaStreamSynchronize(q->stream));
+  memcpy(time, q->h_t, (size_t)ns * 8); memcpy(subtime, q->h_s, (size_t)ns * 8); memcpy(handle, q->h_h, (size_t)ns * 8); memcpy(lp, q->h_lp, (size_t)ns * 4);
+  q->cur ^= 1; q->n = nk;
+  *n_out = ns;
+  if (pending_out) *pending_out = nk;
   return 0;
 }
 

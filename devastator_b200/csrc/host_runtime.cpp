@@ -16,6 +16,7 @@
 #include <csignal>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -244,6 +245,14 @@ namespace {
     std::uint64_t lp_begin = 0;
     std::vector<Reg> regs;
     std::vector<Root> roots;
+    // ---- host-executed handlers (Tier G)
+    std::vector<pdes::detail::host_event*> outbox;        // events this rank's thread created since the last push
+    std::vector<std::function<void()>> task_outbox;       // bcast_procs functors created by this rank's handlers
+    std::vector<std::uint64_t> seq;                        // per cd: next default subtime (pdes.cxx:221-225,332)
+    std::vector<std::uint64_t> last_t, last_s;             // per cd: key of the event committed last (determinism flag, pdes.cxx:828-831)
+    std::vector<char> any_commit;
+    pdes::statistics hstats;
+    std::size_t slice_lo = 0, slice_hi = 0;                // this rank's part of the batch at the horizon
   };
   struct Sim {
     std::vector<RankSide> ranks;
@@ -257,6 +266,14 @@ namespace {
     pdes::statistics stats;      // cumulative since init; read after finalize (test/phold.cxx:201-204)
     std::uint64_t gvt = 0;
     std::mutex mu;
+    // ---- host-executed handlers (Tier G): the device-resident pending pool and the batch at the horizon
+    bool host_mode = false;
+    deva_b200_hostq *hq = nullptr;
+    std::vector<std::uint64_t> b_time, b_sub, b_handle;
+    std::vector<std::uint32_t> b_lp;
+    std::uint64_t b_n = 0;
+    bool host_done = false;
+    std::vector<std::function<void()>> tasks;              // bcast_procs functors every rank runs before the next batch
   };
   Sim g_sim;
 
@@ -333,8 +350,141 @@ void pdes::init(std::int32_t cds_this_rank) {       // pdes.cxx:313-343
   RankSide &rs = g_sim.ranks[me];
   rs.cds = cds_this_rank;
   rs.lp_begin = begin;
-  if(me == 0) g_sim.lp_n = total;
+  rs.seq.resize(std::size_t(cds_this_rank));
+  for(std::int32_t cd = 0; cd < cds_this_rank; cd++) rs.seq[std::size_t(cd)] = begin + std::uint64_t(cd);   // pdes.cxx:332
+  rs.last_t.assign(std::size_t(cds_this_rank), 0); rs.last_s.assign(std::size_t(cds_this_rank), 0); rs.any_commit.assign(std::size_t(cds_this_rank), 0);
+  rs.hstats = pdes::statistics();
+  if(me == 0) { g_sim.lp_n = total; g_sim.host_mode = false; g_sim.host_done = false; }
   deva::barrier();
+}
+
+// ---- host-executed handlers (Tier G) ---------------------------------------------------------------------
+// Event types without a device model: their handlers run here, on the rank thread that owns the cd, while the
+// pending set, the commit horizon and the order of execution come from the GPU (deva_b200_hostq_*).
+namespace {
+  thread_local pdes::execute_context *t_cxt = nullptr;   // the handler running on this thread
+  void host_mode_on() {
+    std::lock_guard<std::mutex> l(g_sim.mu);
+    DEVA_ASSERT_ALWAYS(!g_sim.model, "one simulation uses one tier: device-resident models and host-executed event types cannot be mixed");
+    g_sim.host_mode = true;
+  }
+}
+void pdes::detail::host_root_event(std::int32_t cd, host_event *e) {
+  RankSide &rs = g_sim.ranks[deva::rank_me()];
+  DEVA_ASSERT_ALWAYS(0 <= cd && cd < rs.cds);
+  if(!g_sim.host_mode) host_mode_on();
+  e->target_rank = deva::rank_me(); e->target_cd = cd;
+  rs.outbox.push_back(e);
+}
+void pdes::detail::host_send(std::int32_t rank, std::int32_t cd, host_event *e) {
+  DEVA_ASSERT_ALWAYS(0 <= rank && rank < deva::rank_n && 0 <= cd && cd < g_sim.ranks[std::size_t(rank)].cds, "send to a cd that does not exist");
+  e->target_rank = rank; e->target_cd = cd;
+  g_sim.ranks[deva::rank_me()].outbox.push_back(e);
+}
+std::uint64_t pdes::detail::next_seq_id(std::int32_t cd, std::int32_t n) {     // pdes.cxx:221-225
+  RankSide &rs = g_sim.ranks[deva::rank_me()];
+  const std::uint64_t id = rs.seq[std::size_t(cd)];
+  rs.seq[std::size_t(cd)] += std::uint64_t(n)*g_sim.lp_n;
+  return id;
+}
+std::uint64_t pdes::detail::seq_id_delta() { return g_sim.lp_n; }
+void pdes::detail::host_bcast(std::function<void()> &&fn) { g_sim.ranks[deva::rank_me()].task_outbox.push_back(std::move(fn)); }
+
+namespace {
+  // pdes::drain for host-executed event types.  Every iteration: (1) every rank thread runs the bcast_procs functors
+  // of the previous batch (they insert events on their own rank); (2) rank 0 pushes what the ranks created into the
+  // device pool and pops the events at the commit horizon (GVT = smallest pending time), ordered by (cd, subtime);
+  // (3) every rank thread executes its cds' events in that order - nothing at the horizon can be rolled back, so each
+  // is committed (the reverser's commit hook runs) and destroyed at once.
+  std::uint64_t host_drain(std::uint64_t t_end, bool rewindable) {
+    const int me = deva::rank_me();
+    RankSide &rs = g_sim.ranks[std::size_t(me)];
+    DEVA_ASSERT_ALWAYS(!rewindable, "rewindable drains of host-executed event types are not built (device-resident models support them)");
+    if(me == 0 && !g_sim.hq)
+      ck(deva_b200_hostq_create(deva::os_env<int>("DEVA_B200_DEVICE", 0), deva::os_env<std::uint64_t>("DEVA_B200_HOSTQ_CAP", 0), &g_sim.hq), "deva_b200_hostq_create");
+    for(;;) {
+      deva::barrier();
+      for(auto &task: g_sim.tasks) task();                              // (1)
+      deva::barrier();
+      if(me == 0) {                                                     // (2)
+        g_sim.tasks.clear();
+        std::vector<std::uint64_t> t, sb, h; std::vector<std::uint32_t> lp;
+        for(auto &r: g_sim.ranks) {
+          for(auto *e: r.outbox) {
+            t.push_back(e->time); sb.push_back(e->subtime); h.push_back(std::uint64_t(reinterpret_cast<std::uintptr_t>(e)));
+            lp.push_back(std::uint32_t(g_sim.ranks[std::size_t(e->target_rank)].lp_begin + std::uint64_t(e->target_cd)));
+          }
+          r.outbox.clear();
+        }
+        if(!t.empty()) ck(deva_b200_hostq_push(g_sim.hq, t.size(), t.data(), sb.data(), lp.data(), h.data()), "deva_b200_hostq_push");
+        std::uint64_t pending = 0, gvt = 0;
+        const std::size_t room = std::max<std::size_t>(g_sim.b_time.size(), std::size_t(1) << 16);
+        g_sim.b_time.resize(room); g_sim.b_sub.resize(room); g_sim.b_handle.resize(room); g_sim.b_lp.resize(room);
+        int rc = deva_b200_hostq_pop_min(g_sim.hq, t_end, room, g_sim.b_time.data(), g_sim.b_sub.data(), g_sim.b_lp.data(), g_sim.b_handle.data(), &g_sim.b_n, &gvt, &pending);
+        if(rc == DEVA_B200_ERR_CAPACITY) {   // more events at one time stamp than the arrays hold: they are all still pending - grow and retry
+          const std::size_t more = std::size_t(pending) + 1;
+          g_sim.b_time.resize(more); g_sim.b_sub.resize(more); g_sim.b_handle.resize(more); g_sim.b_lp.resize(more);
+          rc = deva_b200_hostq_pop_min(g_sim.hq, t_end, more, g_sim.b_time.data(), g_sim.b_sub.data(), g_sim.b_lp.data(), g_sim.b_handle.data(), &g_sim.b_n, &gvt, &pending);
+        }
+        ck(rc, "deva_b200_hostq_pop_min");
+        g_sim.gvt = gvt;
+        g_sim.host_done = g_sim.b_n == 0;
+        // the batch is sorted by global cd: every rank's share is one contiguous range
+        std::size_t i = 0;
+        for(auto &r: g_sim.ranks) {
+          r.slice_lo = i;
+          while(i < g_sim.b_n && g_sim.b_lp[i] < r.lp_begin + std::uint64_t(r.cds)) i++;
+          r.slice_hi = i;
+        }
+      }
+      deva::barrier();
+      if(g_sim.host_done) break;
+      for(std::size_t i = rs.slice_lo; i < rs.slice_hi; i++) {          // (3)
+        auto *e = reinterpret_cast<pdes::detail::host_event*>(std::uintptr_t(g_sim.b_handle[i]));
+        const std::size_t cd = std::size_t(g_sim.b_lp[i] - rs.lp_begin);
+        pdes::execute_context cxt;
+        cxt.cd = std::int32_t(cd); cxt.time = g_sim.b_time[i]; cxt.subtime = g_sim.b_sub[i];
+        if(rs.any_commit[cd]) {
+          const bool older = cxt.time < rs.last_t[cd] || (cxt.time == rs.last_t[cd] && cxt.subtime < rs.last_s[cd]);
+          DEVA_ASSERT_ALWAYS(!older, "an event arrived behind one its cd has already executed (a send that did not move time forward): "
+                                     "that needs a rollback, which the conservative host executor does not do");
+          if(cxt.time == rs.last_t[cd] && cxt.subtime == rs.last_s[cd]) rs.hstats.deterministic = false;   // pdes.cxx:828-831
+        }
+        rs.any_commit[cd] = 1; rs.last_t[cd] = cxt.time; rs.last_s[cd] = cxt.subtime;
+        t_cxt = &cxt;
+        e->execute(cxt);
+        t_cxt = nullptr;
+        rs.hstats.executed_n += 1;
+        pdes::event_context ec = cxt;
+        e->commit(ec);                                                  // final at once: pdes.cxx:842-856
+        rs.hstats.committed_n += 1;
+        delete e;
+      }
+      deva::barrier();
+      if(me == 0) for(auto &r: g_sim.ranks) { for(auto &f: r.task_outbox) g_sim.tasks.push_back(std::move(f)); r.task_outbox.clear(); }
+    }
+    deva::barrier();
+    return g_sim.gvt;
+  }
+  void host_finalize() {       // destroy what is still pending (pdes.cxx:1060-1135)
+    if(deva::rank_me() != 0) return;
+    for(auto &r: g_sim.ranks) { for(auto *e: r.outbox) delete e; r.outbox.clear(); r.task_outbox.clear(); }
+    g_sim.tasks.clear();
+    if(g_sim.hq) {
+      std::vector<std::uint64_t> t(1 << 16), sb(1 << 16), h(1 << 16); std::vector<std::uint32_t> lp(1 << 16);
+      for(;;) {
+        std::uint64_t n = 0, gvt = 0, pending = 0;
+        int rc = deva_b200_hostq_pop_min(g_sim.hq, ~std::uint64_t(0), t.size(), t.data(), sb.data(), lp.data(), h.data(), &n, &gvt, &pending);
+        if(rc == DEVA_B200_ERR_CAPACITY) { t.resize(pending + 1); sb.resize(pending + 1); h.resize(pending + 1); lp.resize(pending + 1); continue; }
+        ck(rc, "deva_b200_hostq_pop_min");
+        if(n == 0) break;
+        for(std::uint64_t i = 0; i < n; i++) delete reinterpret_cast<pdes::detail::host_event*>(std::uintptr_t(h[i]));
+      }
+      deva_b200_hostq_destroy(g_sim.hq);
+      g_sim.hq = nullptr;
+    }
+    g_sim.host_mode = false;
+  }
 }
 
 void pdes::detail::register_state_raw(std::int32_t cd, void *addr, std::size_t bytes) {
@@ -354,6 +504,7 @@ void pdes::detail::root_event_raw(std::int32_t cd, std::uint64_t time, std::uint
   DEVA_ASSERT_ALWAYS(0 <= cd && cd < rs.cds);
   {
     std::lock_guard<std::mutex> l(g_sim.mu);
+    DEVA_ASSERT_ALWAYS(!g_sim.host_mode, "one simulation uses one tier: device-resident models and host-executed event types cannot be mixed");
     if(!g_sim.model) { g_sim.model = model; g_sim.user_subtime = user_subtime; }
     DEVA_ASSERT_ALWAYS(g_sim.model->model_id == model->model_id, "one device model per simulation");
   }
@@ -362,6 +513,7 @@ void pdes::detail::root_event_raw(std::int32_t cd, std::uint64_t time, std::uint
 
 std::uint64_t pdes::drain(std::uint64_t t_end, bool rewindable) {   // pdes.cxx:695-1058
   deva::barrier();
+  if(g_sim.host_mode) return host_drain(t_end, rewindable);
   if(deva::rank_me() == 0) {
     DEVA_ASSERT_ALWAYS(!g_sim.has_rewind, "Lingering rewind state must be rewound via pdes::rewind(true|false) before calling pdes::drain().");
     if(!g_sim.eng) {
@@ -482,6 +634,7 @@ void pdes::rewind(bool do_rewind) {                   // pdes.cxx:1137-1229
 
 void pdes::finalize() {                               // pdes.cxx:1060-1135
   deva::barrier();
+  if(g_sim.host_mode) { host_finalize(); deva::barrier(); return; }
   if(deva::rank_me() == 0) {
     for(auto *e: g_sim.engs) deva_b200_destroy(e);
     g_sim.engs.clear(); g_sim.eng = nullptr;
@@ -492,6 +645,7 @@ void pdes::finalize() {                               // pdes.cxx:1060-1135
 }
 
 pdes::statistics pdes::local_stats() {
+  if(g_sim.ranks[std::size_t(deva::rank_me())].hstats.executed_n) return g_sim.ranks[std::size_t(deva::rank_me())].hstats;   // host-executed: per rank
   // the engine keeps one set of counters; rank 0 reports them so that reduce_sum(local_stats())
   // (bench/phold.cxx:169, test/phold.cxx:147) yields the totals
   return deva::rank_me() == 0 ? g_sim.stats : pdes::statistics();

@@ -55,6 +55,7 @@ ABI_SYMBOLS = [
     "deva_b200_seed_phold", "deva_b200_drain", "deva_b200_rewind", "deva_b200_get_stats", "deva_b200_set_stop",
     "deva_b200_digest", "deva_b200_comm_unique_id", "deva_b200_comm_init", "deva_b200_stream",
     "deva_b200_reset", "deva_b200_comm_init_group", "deva_b200_set_heartbeat",
+    "deva_b200_hostq_create", "deva_b200_hostq_destroy", "deva_b200_hostq_push", "deva_b200_hostq_pop_min",
 ]
 
 
@@ -95,6 +96,11 @@ class Api:
         L.deva_b200_stream.restype = P
         L.deva_b200_comm_init_group.argtypes = [C.POINTER(P), C.c_int32]
         L.deva_b200_set_heartbeat.argtypes = [P, C.c_double, HEARTBEAT_FN, P]
+        L.deva_b200_hostq_create.argtypes = [C.c_int32, C.c_uint64, C.POINTER(P)]
+        L.deva_b200_hostq_destroy.argtypes = [P]
+        L.deva_b200_hostq_destroy.restype = None
+        L.deva_b200_hostq_push.argtypes = [P, C.c_uint64, P, P, P, P]
+        L.deva_b200_hostq_pop_min.argtypes = [P, C.c_uint64, C.c_uint64, P, P, P, P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
 
     def check(self, rc):
         if rc != 0:
@@ -234,6 +240,34 @@ class Engine:
     def comm_init(self, uid_bytes):
         buf = C.create_string_buffer(bytes(uid_bytes), 128)
         self.api.check(self.api.lib.deva_b200_comm_init(self.h, buf))
+
+
+class HostQueue:
+    """The device-resident pending-event pool behind host-executed handlers (deva_b200_hostq_*): push events, pop all
+    events at the commit horizon (smallest pending time) ordered by (lp, subtime, handle)."""
+
+    def __init__(self, capacity=0, device=0, api=None):
+        self.api = api or load()
+        self.h = C.c_void_p()
+        self.api.check(self.api.lib.deva_b200_hostq_create(device, capacity, C.byref(self.h)))
+
+    def push(self, time, subtime, lp, handle):
+        t = np.ascontiguousarray(time, dtype=np.uint64); s = np.ascontiguousarray(subtime, dtype=np.uint64)
+        l = np.ascontiguousarray(lp, dtype=np.uint32); h = np.ascontiguousarray(handle, dtype=np.uint64)
+        self.api.check(self.api.lib.deva_b200_hostq_push(self.h, t.size, t.ctypes.data, s.ctypes.data, l.ctypes.data, h.ctypes.data))
+
+    def pop_min(self, t_end=T_INF, room=1 << 16):
+        t = np.empty(room, np.uint64); s = np.empty(room, np.uint64); l = np.empty(room, np.uint32); h = np.empty(room, np.uint64)
+        n, gvt, pending = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.api.check(self.api.lib.deva_b200_hostq_pop_min(self.h, t_end, room, t.ctypes.data, s.ctypes.data, l.ctypes.data, h.ctypes.data,
+                                                            C.byref(n), C.byref(gvt), C.byref(pending)))
+        k = n.value
+        return dict(time=t[:k], subtime=s[:k], lp=l[:k], handle=h[:k], gvt=gvt.value, pending=pending.value)
+
+    def close(self):
+        if self.h:
+            self.api.lib.deva_b200_hostq_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 def comm_init_group(engines):

@@ -30,6 +30,10 @@ APPS = [
     # no device model: drives deva::gvt (include/devastator/gvt.hxx) directly; built with the asserts of the
     # test enabled (DEBUG=1), they are what checks that the GVT never overtakes a message
     ("gvt_test", "test/gvt-test.cxx", None, [], [2, 3, 8]),
+    # no device model either: HOST-EXECUTED handlers (Tier G) - E::execute, commit hooks and bcast_procs run on the
+    # rank threads, the pending set / GVT / order of execution come from the GPU pool (deva_b200_hostq_*)
+    ("stencil", "test/stencil.cxx", "", [], [1, 2, 4]),
+    ("phold_bcast", "test/phold-bcast.cxx", "", [], [1, 2]),
 ]
 
 
@@ -54,7 +58,7 @@ def main():
             if not (force or newer(exe, srcs + hdrs + [RUNTIME, os.path.join(LIBDIR, "libdeva_b200.so"), __file__])):
                 continue
             dbg = ["-DDEBUG=1"] if model is None else ["-DDEBUG=0", "-DNDEBUG=1"]
-            inc_model = [] if model is None else ["-include", os.path.join(INC, model)]
+            inc_model = [] if not model else ["-include", os.path.join(INC, model)]
             cmd = ["g++", "-std=c++14", "-O2", "-pthread", "-w", f"-DDEVA_THREAD_N={R}", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1",
                    *dbg, f"-I{INC}", f"-I{os.path.join(REF, 'bench')}", *inc_model,
                    *srcs, RUNTIME, f"-L{LIBDIR}", "-ldeva_b200", "-Wl,-rpath,$ORIGIN/../../devastator_b200", "-o", exe]

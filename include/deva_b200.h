@@ -147,6 +147,24 @@ void *deva_b200_stream(deva_b200_engine *e);
 typedef void (*deva_b200_heartbeat_fn)(void *user, uint64_t gvt, uint64_t window, double commits_per_sec, double efficiency);
 int deva_b200_set_heartbeat(deva_b200_engine *e, double secs, deva_b200_heartbeat_fn cb, void *user);
 
+/* ---- Host-executed handlers (Tier G): the pending-event pool of event types that have no device model.
+ * Their handlers are host C++ and run on the host's rank threads (include/devastator/pdes.hxx); the GPU keeps the
+ * pending set (replaces cd_state::future_events / sim_state::cds_by_now, pdes.cxx:82-154), finds the commit
+ * horizon (GVT = smallest pending time: block + grid min-reduction, replaces gvt.cxx:53-149), extracts the events
+ * at the horizon by stream compaction and orders them by (LP, subtime, handle).  `handle` is opaque to the engine
+ * (the host's event object; the counterpart of the reference's event_vtable*, pdes.hxx:350-357). */
+typedef struct deva_b200_hostq deva_b200_hostq;
+int deva_b200_hostq_create(int32_t device, uint64_t capacity, deva_b200_hostq **out);
+void deva_b200_hostq_destroy(deva_b200_hostq *q);
+/* appends n pending events (execute_context::send / root_event, pdes.hxx:666-732,901-909) */
+int deva_b200_hostq_push(deva_b200_hostq *q, uint64_t n, const uint64_t *time, const uint64_t *subtime,
+                         const uint32_t *lp, const uint64_t *handle);
+/* Removes and returns ALL pending events with the smallest time stamp, provided it is < t_end, sorted by
+ * (lp, subtime, handle).  *n_out = 0 when nothing is pending below t_end; *gvt_out = the smallest pending time
+ * before the call (~0 when the pool is empty); *pending_out = events left in the pool.  max_n = room in the arrays. */
+int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime,
+                            uint32_t *lp, uint64_t *handle, uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out);
+
 /* Multi-GPU (replaces world_gasnet / threads transports and gvt.cxx's credit-counted reduction).
  * uid = 128-byte ncclUniqueId made by rank 0.  With one process per GPU the engines map each other's
  * receive buffers (CUDA IPC) and the execute kernel stores cross-GPU records straight into the

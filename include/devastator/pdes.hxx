@@ -15,8 +15,13 @@
 // are instantiated after the app has defined E.  For such an E the handler (E::execute and its
 // reverse object) runs inside the execute kernel; the host copies of the state objects given to
 // register_state are uploaded at drain() entry and written back at drain() exit, so the app reads
-// its results where it always did.  An event type with no device model aborts loudly at its first
-// root_event: host-handler execution (Tier G of SURVEY.md 7.1) is not built - there is no CPU path.
+// its results where it always did.
+// An event type with NO device model (test/stencil.cxx, test/phold-bcast.cxx) keeps its handlers on the host
+// (Tier G of SURVEY.md 7.1): E::execute, the reverser's commit and bcast_procs run on the owning rank's thread,
+// as in the reference; the pending set, the commit horizon (GVT) and the order of execution come from the GPU
+// (deva_b200_hostq_*, devastator_b200/csrc/hostq.cuh).  Execution is conservative - only events at the horizon
+// run, so nothing is ever unexecuted - which needs sends to move time forward (time > current time), the case
+// the reference documents for events without a user subtime (pdes.hxx:683-689).  One simulation uses one tier.
 #ifndef DEVA_B200_PDES_HXX
 #define DEVA_B200_PDES_HXX
 
@@ -72,6 +77,27 @@ namespace pdes {
 
   namespace detail {   // implemented in devastator_b200/csrc/host_runtime.cpp
     constexpr std::uint64_t end_of_time = std::uint64_t(-1);
+
+    // ---- host-executed events (Tier G): the type-erased event object, pdes.hxx:350-357,588-647
+    struct host_event {
+      std::uint64_t time = 0, subtime = 0;
+      std::int32_t target_rank = 0, target_cd = 0;
+      virtual ~host_event() {}
+      virtual void execute(execute_context &cxt) = 0;
+      virtual void commit(event_context &cxt) = 0;      // the reverser's commit hook (if any); destroys the reverser
+    };
+    void host_root_event(std::int32_t cd, host_event *e);                     // into a cd of this rank
+    void host_send(std::int32_t rank, std::int32_t cd, host_event *e);        // from a handler running on this rank
+    std::uint64_t next_seq_id(std::int32_t cd, std::int32_t n);               // cd_state::next_seq_id, pdes.cxx:221-225
+    std::uint64_t seq_id_delta();                                             // = number of cds in the job (pdes.cxx:321)
+    void host_bcast(std::function<void()> &&run_on_every_rank);               // runs on every rank thread before the next events
+
+    template<typename E, typename ExecRet, typename HasCommit = void>
+    struct event_commit_dispatch { void operator()(event_context&, E&, ExecRet&) const {} };
+    template<typename E, typename ExecRet>
+    struct event_commit_dispatch<E, ExecRet, decltype(std::declval<ExecRet>().commit(std::declval<event_context&>(), std::declval<E&>()), void())> {
+      void operator()(event_context &cxt, E &user, ExecRet &r) const { r.commit(cxt, user); }
+    };
     void register_state_raw(std::int32_t cd, void *addr, std::size_t bytes);
     void root_event_raw(std::int32_t cd, std::uint64_t time, std::uint64_t subtime, bool user_subtime,
                         std::uint32_t payload, const model_binding *model);
@@ -90,6 +116,19 @@ namespace pdes {
     };
   }
 
+  namespace detail {
+    template<typename E>
+    struct host_event_impl final: host_event {
+      using ExecRet = typename std::remove_const<decltype(std::declval<E>().execute(std::declval<execute_context&>()))>::type;
+      E user;
+      union { ExecRet exec_ret; };
+      explicit host_event_impl(E u): user(std::move(u)) {}
+      ~host_event_impl() {}
+      void execute(execute_context &cxt) override { ::new(&exec_ret) ExecRet{user.execute(cxt)}; }
+      void commit(event_context &cxt) override { event_commit_dispatch<E, ExecRet>()(cxt, user, exec_ret); exec_ret.~ExecRet(); }
+    };
+  }
+
   template<typename T>
   void register_state(std::int32_t cd, T *address) {
     static_assert(std::is_trivially_copyable<T>::value,
@@ -100,21 +139,55 @@ namespace pdes {
   template<typename Event>
   void root_event(std::int32_t cd, std::uint64_t time, Event user) {   // pdes.hxx:901-909
     using DM = device_model<Event>;
-    if(DM::model_id == 0) detail::no_device_model("pdes::root_event");
     // root subtime = E::subtime() or the LOCAL cd index (pdes.hxx:907)
     const std::uint64_t sub = detail::event_subtime<Event>()(std::uint64_t(cd), user);
+    if(DM::model_id == 0) {            // no device model: the handlers of this event type run on the host
+      auto *e = new detail::host_event_impl<Event>(std::move(user));
+      e->time = time; e->subtime = sub;
+      detail::host_root_event(cd, e);
+      return;
+    }
     detail::root_event_raw(cd, time, sub, detail::event_subtime<Event>::user,
                            DM::template payload<Event>(user), DM::template binding<Event>());
   }
 
+  // Only reachable from a host-side E::execute (device-resident models send from the kernel).
   template<typename Event1>
-  void execute_context::send(std::int32_t, std::int32_t, std::uint64_t, Event1&&) {
-    // Only reachable from a host-side E::execute; device-resident models send from the kernel.
-    detail::no_device_model("execute_context::send on the host");
+  void execute_context::send(std::int32_t rank, std::int32_t cd, std::uint64_t time, Event1 &&user) {   // pdes.hxx:666-732
+    if(dummy) return;
+    using Event = typename std::decay<Event1>::type;
+    const std::uint64_t subtime = detail::event_subtime<Event>()(detail::next_seq_id(this->cd, +1), user);
+    DEVA_ASSERT_ALWAYS(std::make_pair(this->time, this->subtime) <= std::make_pair(time, subtime),
+                       "Sent events must have a greater-or-equal (time,subtime) combo.");
+    auto *e = new detail::host_event_impl<Event>(static_cast<Event1&&>(user));
+    e->time = time; e->subtime = subtime;
+    detail::host_send(rank, cd, e);
   }
+
   template<typename ProcFn>
-  void execute_context::bcast_procs(std::uint64_t, std::int32_t, ProcFn) {
-    detail::no_device_model("execute_context::bcast_procs on the host");
+  void execute_context::bcast_procs(std::uint64_t time_lb, std::int32_t total_event_n, ProcFn proc_fn) {   // pdes.hxx:736-813
+    if(dummy) return;
+    // every rank numbers the events it inserts from the same base (pdes.hxx:746,761)
+    const std::uint64_t seq_id_base = detail::next_seq_id(this->cd, total_event_n);
+    detail::host_bcast([=]() {
+      proc_fn([&](int rank, int local_event_n, auto fn) {
+        if(rank != deva::rank_me() || local_event_n == 0) return;     // (this copy of the functor acts for its own rank)
+        std::uint64_t seq_id_bumper = seq_id_base;
+        int actual = 0;
+        fn([&](std::int32_t cd, std::uint64_t time, auto e_user) {
+          DEVA_ASSERT_ALWAYS(time_lb <= time, "Invalid time lower-bound supplied to execute_context::bcast_procs.");
+          using Event = decltype(e_user);
+          const std::uint64_t seq_id = seq_id_bumper;
+          seq_id_bumper += detail::seq_id_delta();
+          actual += 1;
+          const std::uint64_t sub = detail::event_subtime<Event>()(seq_id, e_user);
+          auto *e = new detail::host_event_impl<Event>(std::move(e_user));
+          e->time = time; e->subtime = sub;
+          detail::host_send(rank, cd, e);
+        });
+        DEVA_ASSERT_ALWAYS(local_event_n == actual, "Event count given to `run_at_rank` within bcast process function does not match actual number of events inserted.");
+      });
+    });
   }
 }
 }

@@ -474,6 +474,36 @@ int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]) {
   return 0;
 }
 
+// ---- host-executed handlers: a host stand-in for the device pool of hostq.cuh (same contract) ----------------
+struct HqRec { uint64_t t, s, h; uint32_t lp; };
+struct deva_b200_hostq { std::vector<HqRec> recs; uint64_t cap; };
+int deva_b200_hostq_create(int32_t, uint64_t capacity, deva_b200_hostq **out) { *out = new deva_b200_hostq; (*out)->cap = capacity ? capacity : (1ull << 22); return 0; }
+void deva_b200_hostq_destroy(deva_b200_hostq *q) { delete q; }
+int deva_b200_hostq_push(deva_b200_hostq *q, uint64_t n, const uint64_t *time, const uint64_t *subtime, const uint32_t *lp, const uint64_t *handle) {
+  if (q->recs.size() + n > q->cap) return fail(DEVA_B200_ERR_CAPACITY, "host-handler event pool is full");
+  for (uint64_t i = 0; i < n; i++) q->recs.push_back({time[i], subtime[i], handle[i], lp[i]});
+  return 0;
+}
+int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
+                            uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
+  *n_out = 0; *gvt_out = ~0ull;
+  if (pending_out) *pending_out = q->recs.size();
+  if (q->recs.empty()) return 0;
+  uint64_t tmin = ~0ull;
+  for (auto &r : q->recs) tmin = std::min(tmin, r.t);
+  *gvt_out = tmin;
+  if (tmin >= t_end) return 0;
+  std::vector<HqRec> sel, keep;
+  for (auto &r : q->recs) (r.t == tmin ? sel : keep).push_back(r);
+  if (sel.size() > max_n) return fail(DEVA_B200_ERR_CAPACITY, "hostq: too many events at one time stamp");
+  std::sort(sel.begin(), sel.end(), [](const HqRec &a, const HqRec &b) { return a.lp != b.lp ? a.lp < b.lp : a.s != b.s ? a.s < b.s : a.h < b.h; });
+  for (size_t i = 0; i < sel.size(); i++) { time[i] = sel[i].t; subtime[i] = sel[i].s; lp[i] = sel[i].lp; handle[i] = sel[i].h; }
+  q->recs.swap(keep);
+  *n_out = sel.size();
+  if (pending_out) *pending_out = q->recs.size();
+  return 0;
+}
+
 int deva_b200_comm_unique_id(void *uid128) { memset(uid128, 0, 128); return 0; }
 int deva_b200_comm_init(deva_b200_engine *, const void *) { return 0; }
 void emu_enable_peer_delivery(deva_b200_engine **es, int G);

@@ -142,3 +142,62 @@ def test_reference_world_tests_through_world_mirror(tmp_path, app, expect):
         f"-L{ROOT}/devastator_b200", "-ldeva_b200", f"-Wl,-rpath,{ROOT}/devastator_b200", "-o", exe])
     out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert out.returncode == 0 and expect in out.stdout, out.stdout[-2000:]
+
+
+# ---- host-executed handlers (Tier G): event types without a device model ------------------------------------
+def _build_host_app(tmp_path, src, R):
+    exe = str(tmp_path / (os.path.basename(src).replace(".cxx", "") + f"_R{R}"))
+    emu_dir = os.path.join(ROOT, "tests", "emu", "_build")
+    subprocess.check_call([
+        "g++", "-std=c++14", "-O2", "-pthread", "-w", f"-DDEVA_THREAD_N={R}", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1",
+        "-DDEBUG=0", "-DNDEBUG=1", f"-I{ROOT}/include", f"{REF}/{src}", f"{ROOT}/devastator_b200/csrc/host_runtime.cpp",
+        f"-L{emu_dir}", "-ldeva_b200_emu", f"-Wl,-rpath,{emu_dir}", "-o", exe])
+    return exe
+
+
+PHOLD_BCAST_GOLDEN = {1: (99420, 840663732868261650), 2: (196980, 10848649704370676656)}
+
+
+def check_phold_bcast_output(text, R):
+    commits = [int(x) for x in re.findall(r"commits = (\d+)", text)]
+    sums = [int(x) for x in re.findall(r"checksum = (\d+)", text)]
+    assert len(commits) == 4 and len(sums) == 4, text
+    assert set(commits) == {PHOLD_BCAST_GOLDEN[R][0]} and set(sums) == {PHOLD_BCAST_GOLDEN[R][1]}, text
+    assert "deterministic = 0" not in text
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+@pytest.mark.parametrize("R", [1, 2])
+def test_reference_phold_bcast_source_host_handlers_emu(emu_api, tmp_path, R):
+    """test/phold-bcast.cxx, unchanged: bcast_procs + default (sequence-id) subtimes through the host executor; the
+    pending pool is the emulation's stand-in for the device pool.  Goldens: the reference's own binaries."""
+    out = subprocess.run([_build_host_app(tmp_path, "test/phold-bcast.cxx", R)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout
+    check_phold_bcast_output(out.stdout, R)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+def test_reference_stencil_source_host_handlers_emu(emu_api, tmp_path):
+    """test/stencil.cxx, unchanged (64 M events; 80 same-time events per cell; commit hooks): checks itself against a
+    serial recomputation and prints `Looks good!`"""
+    out = subprocess.run([_build_host_app(tmp_path, "test/stencil.cxx", 2)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0 and "Looks good!" in out.stdout, out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R", [1, 2])
+def test_reference_phold_bcast_source_on_gpu(R):
+    exe = os.path.join(BIN, f"phold_bcast_R{R}")
+    assert os.path.exists(exe), "dropin/_bin missing: run __graft_entry__.build() where /root/reference exists"
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout
+    check_phold_bcast_output(out.stdout, R)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R", [1, 4])
+def test_reference_stencil_source_on_gpu(R):
+    exe = os.path.join(BIN, f"stencil_R{R}")
+    assert os.path.exists(exe)
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert out.returncode == 0 and "Looks good!" in out.stdout, out.stdout
