@@ -265,7 +265,7 @@ struct TileEngine {
       launches += batch;
       return be.batch_end(v, slot);
     };
-    uint64_t guard = 0;
+    uint64_t guard = 0, stalled = 0;
     int slot = 0;
     uint32_t stop_sent = hc.stop_req;
     auto hb_t0 = std::chrono::steady_clock::now();
@@ -297,6 +297,17 @@ struct TileEngine {
       }
       if (hc.err) { be.batch_wait(v, slot, nullptr, nullptr); if (tf) fclose(tf); return check_err(); }
       if (hc.phase == PH_DONE) break;
+      // launches run but no epoch commits and the horizon does not move: a livelock must end loudly, with what the
+      // device says about itself, not as a hang (an epoch needs 2-4 launches; 64 batches without one is not work)
+      if (hc.epochs == before.epochs && hc.gvt == before.gvt && hc.launch != before.launch) {
+        if (++stalled > 64) {
+          be.batch_wait(v, slot, nullptr, nullptr);
+          if (tf) fclose(tf);
+          return tile_fail(DEVA_B200_ERR_INVARIANT, "tile engine: %llu launches without an epoch commit (phase %u, epoch %u, full %u, gvt %llu, ub %llu, window %u x 2^%u, "
+                           "dirty %u/%u, spill %u/%u, far %llu, antis pending %lld)", (unsigned long long)stalled * batch, hc.phase, hc.epoch, hc.full, (unsigned long long)hc.gvt,
+                           (unsigned long long)hc.ub, hc.win_m, hc.shift, hc.dirty_n[0], hc.dirty_n[1], hc.sp_n[0], hc.sp_n[1], (unsigned long long)hc.far_total, (long long)hc.antis_pending);
+        }
+      } else stalled = 0;
       if (hc.launch == before.launch && ++guard > 4) { be.batch_wait(v, slot, nullptr, nullptr); if (tf) fclose(tf); return tile_fail(DEVA_B200_ERR_INVARIANT, "tile engine: the step kernel makes no progress (phase %u)", hc.phase); }
       if (hc.launch != before.launch) guard = 0;
     }

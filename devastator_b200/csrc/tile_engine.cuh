@@ -247,7 +247,7 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
       __syncwarp();
     }
     __syncthreads();
-    if (c->n_heavy) {   // (some warp of the grid met a tile for a whole block - the block that did will come by here)
+    if (ld_u32_cg(&c->n_heavy)) {   // (read at L2; some warp of the grid met a tile for a whole block - the block that did will come by here)
       for (;;) {
         if (threadIdx.x == 0) b.h->work_item = atomicAdd(&c->workh, (uint32_t)NTHR);
         __syncthreads();
