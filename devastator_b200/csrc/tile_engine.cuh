@@ -246,8 +246,13 @@ k_tile_step(const __grid_constant__ TView v, const __grid_constant__ ModelParams
       }
       __syncwarp();
     }
+    // (ONE thread reads the counter and the block branches on what it saw: every thread reading it for itself could
+    //  split the block around the barriers below when another block's warp bumps it in between - a rare hang once)
+    __shared__ uint32_t any_heavy;
     __syncthreads();
-    if (ld_u32_cg(&c->n_heavy)) {   // (read at L2; some warp of the grid met a tile for a whole block - the block that did will come by here)
+    if (threadIdx.x == 0) any_heavy = ld_u32_cg(&c->n_heavy);
+    __syncthreads();
+    if (any_heavy) {   // some warp of the grid met a tile for a whole block - the block that did will come by here
       for (;;) {
         if (threadIdx.x == 0) b.h->work_item = atomicAdd(&c->workh, (uint32_t)NTHR);
         __syncthreads();
