@@ -5,6 +5,8 @@
     /root/reference/test/phold.cxx   -> dropin/_bin/phold_test_R<R>     (self-checking: "Looks good!")
     /root/reference/bench/phold.cxx  -> dropin/_bin/phold_bench_R<R>    (prints a report row)
     /root/reference/test/gvt-test.cxx -> dropin/_bin/gvt_test_R<R>      (host-rank GVT service, asserts on: "SUCCESS")
+    /root/reference/test/stencil.cxx, test/phold-bcast.cxx, example/heat/heat.cxx -> stencil_R<R>, phold_bcast_R<R>,
+                                        heat_R<R>, heat_q0_R<R>         (host-executed handlers over the device pool)
 
 The sources are compiled where they lie under /root/reference (never copied).  The only additions
 on the build line are -I include and the force-included model binding header.  Outputs are
@@ -34,6 +36,10 @@ APPS = [
     # rank threads, the pending set / GVT / order of execution come from the GPU pool (deva_b200_hostq_*)
     ("stencil", "test/stencil.cxx", "", [], [1, 2, 4]),
     ("phold_bcast", "test/phold-bcast.cxx", "", [], [1, 2]),
+    # example/heat (1-D heat diffusion, quantized-state-system actors), unchanged, Tier G:
+    # Advance / ShareState handlers (qss.hxx:92-144) run on the rank threads in the order the device pool decides
+    ("heat", "example/heat/heat.cxx", "", [], [1, 4]),
+    ("heat_q0", "example/heat/heat.cxx", "", [], [2], ["-DQSS_ORDER=0"]),
 ]
 
 
@@ -51,7 +57,8 @@ def main():
         return 0
     os.makedirs(OUT, exist_ok=True)
     hdrs = [os.path.join(dp, f) for dp, _, fs in os.walk(INC) for f in fs]
-    for name, src, model, extra, ranks in APPS:
+    for name, src, model, extra, ranks, *more in APPS:
+        flags = more[0] if more else []
         for R in ranks:
             exe = os.path.join(OUT, f"{name}_R{R}")
             srcs = [os.path.join(REF, src)] + [os.path.join(REF, e) for e in extra]
@@ -60,7 +67,7 @@ def main():
             dbg = ["-DDEBUG=1"] if model is None else ["-DDEBUG=0", "-DNDEBUG=1"]
             inc_model = [] if not model else ["-include", os.path.join(INC, model)]
             cmd = ["g++", "-std=c++14", "-O2", "-pthread", "-w", f"-DDEVA_THREAD_N={R}", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1",
-                   *dbg, f"-I{INC}", f"-I{os.path.join(REF, 'bench')}", *inc_model,
+                   *dbg, *flags, f"-I{INC}", f"-I{os.path.join(REF, 'bench')}", *inc_model,
                    *srcs, RUNTIME, f"-L{LIBDIR}", "-ldeva_b200", "-Wl,-rpath,$ORIGIN/../../devastator_b200", "-o", exe]
             r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             if r.returncode != 0:

@@ -2,6 +2,7 @@
 // (mirrors the names in src/devastator/utility.hxx:12-96 that app code can see).
 #ifndef DEVA_B200_UTILITY_HXX
 #define DEVA_B200_UTILITY_HXX
+#include <array>   // (as the reference's utility header does, src/upcxx/utility.hpp: apps rely on it transitively)
 #include <type_traits>
 #include <utility>
 

@@ -362,7 +362,7 @@ def exe_name(kind, R, tag=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ranks", type=int, nargs="*", default=[2, 8])
-    ap.add_argument("--only", default="phold_test,phold_bench,phold_t,phold_b")
+    ap.add_argument("--only", default="phold_test,phold_bench,phold_t,phold_b,heat")
     ap.add_argument("--tags", default=",".join(PHOLD_T_CONFIGS))
     ap.add_argument("--baseline-ranks", type=int, nargs="*", default=[4, 16, 32, 64])
     ap.add_argument("--force", action="store_true")
@@ -382,6 +382,10 @@ def main():
         if "phold_bench" in only:
             jobs.append((os.path.join(REF, "bench/phold.cxx"), exe_name("phold_bench", R),
                          (os.path.join(REF, "bench/util/report.cxx"),)))
+        if "heat" in only:
+            # example/heat (QSS actors), unchanged: QSS order 1 (its default) and order 0
+            jobs.append((os.path.join(REF, "example/heat/heat.cxx"), exe_name("heat", R), ()))
+            jobs.append((os.path.join(REF, "example/heat/heat.cxx"), exe_name("heat_q0", R), ("-DQSS_ORDER=0",)))
         if "phold_b" in only:
             jobs.append((gen_phold_b(), exe_name("phold_b", R), (os.path.join(REF, "bench/util/report.cxx"),)))
         if "phold_t" in only:

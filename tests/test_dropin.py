@@ -5,6 +5,7 @@ include/devastator/*.hxx (dropin/build_dropin.py).
    the header mirror and linked with the host EMULATION of the engine ABI, which checks the C++
    veneer (rank threads, collectives, state gather/scatter, root staging, rewind) without a GPU.
  - GPU suite: the prebuilt product binaries (linked with libdeva_b200.so) run on the B200."""
+import json
 import os
 import re
 import subprocess
@@ -145,12 +146,12 @@ def test_reference_world_tests_through_world_mirror(tmp_path, app, expect):
 
 
 # ---- host-executed handlers (Tier G): event types without a device model ------------------------------------
-def _build_host_app(tmp_path, src, R):
+def _build_host_app(tmp_path, src, R, flags=()):
     exe = str(tmp_path / (os.path.basename(src).replace(".cxx", "") + f"_R{R}"))
     emu_dir = os.path.join(ROOT, "tests", "emu", "_build")
     subprocess.check_call([
         "g++", "-std=c++14", "-O2", "-pthread", "-w", f"-DDEVA_THREAD_N={R}", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1",
-        "-DDEBUG=0", "-DNDEBUG=1", f"-I{ROOT}/include", f"{REF}/{src}", f"{ROOT}/devastator_b200/csrc/host_runtime.cpp",
+        "-DDEBUG=0", "-DNDEBUG=1", *flags, f"-I{ROOT}/include", f"{REF}/{src}", f"{ROOT}/devastator_b200/csrc/host_runtime.cpp",
         f"-L{emu_dir}", "-ldeva_b200_emu", f"-Wl,-rpath,{emu_dir}", "-o", exe])
     return exe
 
@@ -201,3 +202,39 @@ def test_reference_stencil_source_on_gpu(R):
     assert os.path.exists(exe)
     out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert out.returncode == 0 and "Looks good!" in out.stdout, out.stdout
+
+
+# ---- example/heat (QSS actors), unchanged, through the host executor ------------------
+with open(os.path.join(ROOT, "tests", "golden", "heat_goldens.json")) as _f:
+    HEAT_GOLDEN = json.load(_f)     # the reference's own binaries, tests/golden/make_heat_goldens.py
+
+
+def check_heat_output(exe, tag):
+    g = HEAT_GOLDEN[tag]
+    out = subprocess.run([exe], env=dict(os.environ, **g["env"]), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("Actors : [")]
+    assert len(lines) == 2, out.stdout[-2000:]
+    assert lines[1] == g["final"], (tag, lines[1], g["final"])      # the printed cell values, character for character
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+@pytest.mark.parametrize("kind,R", [("heat", 1), ("heat", 4), ("heat_q0", 2)])
+def test_reference_heat_source_host_handlers_emu(emu_api, tmp_path, kind, R):
+    """example/heat/heat.cxx, unchanged: Advance / ShareState events (qss.hxx:92-144) with double-polynomial
+    neighbour tables, both same-time priorities (time.hxx:7-12), executed in the pool's order; every golden
+    configuration of its QSS order, ragged partitions included."""
+    exe = _build_host_app(tmp_path, "example/heat/heat.cxx", R, ["-DQSS_ORDER=0"] if kind == "heat_q0" else [])
+    for tag, g in HEAT_GOLDEN.items():
+        if g["kind"] == kind:
+            check_heat_output(exe, tag)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,R", [("heat", 1), ("heat", 4), ("heat_q0", 2)])
+def test_reference_heat_source_on_gpu(kind, R):
+    exe = os.path.join(BIN, f"{kind}_R{R}")
+    assert os.path.exists(exe), "dropin/_bin missing: run __graft_entry__.build() where /root/reference exists"
+    for tag, g in HEAT_GOLDEN.items():
+        if g["kind"] == kind:
+            check_heat_output(exe, tag)
