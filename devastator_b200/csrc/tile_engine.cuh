@@ -470,6 +470,9 @@ __global__ void k_tile_digest(TView v, int stw, unsigned long long *out) {
 struct CudaBE {
   int device = 0;
   cudaStream_t stream = nullptr;
+  uint64_t root_chunk = 1u << 21;         // roots per chunk (DEVA_B200_ROOT_CHUNK; 0 = one piece)
+  cudaStream_t copy_stream = nullptr;     // host -> device copies of the root columns, one chunk ahead of the insertion kernel
+  cudaEvent_t cev[2] = {nullptr, nullptr};  // [0] staging buffer free (on `stream`), [1] chunk landed (on `copy_stream`)
   std::vector<void *> allocs;
   cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   cudaEvent_t bev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // per batch slot: begin, end, control block copied
@@ -490,6 +493,9 @@ struct CudaBE {
     device = dev;
     TCU(cudaSetDevice(dev));
     TCU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    TCU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (auto &e : cev) TCU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (const char *rc = getenv("DEVA_B200_ROOT_CHUNK")) root_chunk = strtoull(rc, nullptr, 10);
     for (auto &p : ev) for (auto &e : p) TCU(cudaEventCreate(&e));
     for (auto &p : bev) for (auto &e : p) TCU(cudaEventCreate(&e));
     TCU(cudaHostAlloc((void **)&h_ctl, sizeof(TCtl), cudaHostAllocDefault));
@@ -534,7 +540,10 @@ struct CudaBE {
     for (auto &p : bev) for (auto &e : p) if (e) cudaEventDestroy(e);
     if (h_tmp) cudaFreeHost(h_tmp);
     for (auto &p : ev) for (auto &e : p) if (e) cudaEventDestroy(e);
+    for (auto &e : cev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream) cudaStreamDestroy(stream);
+    copy_stream = nullptr;
     stream = nullptr; stage = nullptr; d_tmp = nullptr; h_ctl = nullptr; h_ctl2 = nullptr; h_tmp = nullptr;
   }
   int zero(void *p, size_t n) { TCU(cudaMemsetAsync(p, 0, n, stream)); return 0; }
@@ -611,13 +620,23 @@ struct CudaBE {
     if (rc) return rc;
     uint64_t *d_t = (uint64_t *)stage, *d_s = d_t + n;
     uint32_t *d_l = (uint32_t *)(d_s + n), *d_p = d_l + n;
-    TCU(cudaMemcpyAsync(d_t, time, n * 8, cudaMemcpyHostToDevice, stream));
-    TCU(cudaMemcpyAsync(d_s, sub, n * 8, cudaMemcpyHostToDevice, stream));
-    TCU(cudaMemcpyAsync(d_l, lp, n * 4, cudaMemcpyHostToDevice, stream));
-    TCU(cudaMemcpyAsync(d_p, payload, n * 4, cudaMemcpyHostToDevice, stream));
-    const unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16);
-    k_tile_roots<<<g, 256, 0, stream>>>(v, d_t, d_s, d_l, d_p, (uint32_t)n);
-    TCU(cudaGetLastError());
+    // The columns cross PCIe in chunks on a stream of their own; the insertion kernel of chunk c runs behind its copy
+    // and beside the copies of chunk c+1 (link-bound: 24 B per root; the scatter into the tiles' lists hides behind it).
+    const uint64_t CH = root_chunk ? root_chunk : n;
+    TCU(cudaEventRecord(cev[0], stream));                 // earlier users of the staging buffer are done
+    TCU(cudaStreamWaitEvent(copy_stream, cev[0], 0));
+    for (uint64_t o = 0; o < n; o += CH) {
+      const uint64_t m = std::min<uint64_t>(CH, n - o);
+      TCU(cudaMemcpyAsync(d_t + o, time + o, m * 8, cudaMemcpyHostToDevice, copy_stream));
+      TCU(cudaMemcpyAsync(d_s + o, sub + o, m * 8, cudaMemcpyHostToDevice, copy_stream));
+      TCU(cudaMemcpyAsync(d_l + o, lp + o, m * 4, cudaMemcpyHostToDevice, copy_stream));
+      TCU(cudaMemcpyAsync(d_p + o, payload + o, m * 4, cudaMemcpyHostToDevice, copy_stream));
+      TCU(cudaEventRecord(cev[1], copy_stream));
+      TCU(cudaStreamWaitEvent(stream, cev[1], 0));
+      const unsigned g = (unsigned)std::min<uint64_t>((m + 255) / 256, 148 * 16);
+      k_tile_roots<<<g, 256, 0, stream>>>(v, d_t + o, d_s + o, d_l + o, d_p + o, (uint32_t)m);
+      TCU(cudaGetLastError());
+    }
     return 0;
   }
   int k_begin(const TView &v, const TParams &tp, uint64_t t_end) {
