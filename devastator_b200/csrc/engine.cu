@@ -1057,6 +1057,7 @@ struct deva_b200_hostq {
   cudaStream_t stream = nullptr;
   uint64_t cap = 0, n = 0;            // records the pool holds (host copy of the count)
   hq::Cols pool[2], sel, out;         // the pool (two halves: compaction goes from one to the other), the horizon's records, sorted
+  hq::Cols snap = {nullptr, nullptr, nullptr, nullptr}; uint64_t snap_n = 0; bool has_snap = false;   // rewindable drain: the pool as it was
   int cur = 0;
   uint32_t *idx = nullptr;
   hq::Ctl *ctl = nullptr, *h_ctl = nullptr;
@@ -1101,6 +1102,7 @@ void deva_b200_hostq_destroy(deva_b200_hostq *q) {
   cudaSetDevice(q->device);
   if (q->stream) cudaStreamSynchronize(q->stream);
   hq_cols_free(q->pool[0]); hq_cols_free(q->pool[1]); hq_cols_free(q->sel); hq_cols_free(q->out);
+  if (q->snap.t) hq_cols_free(q->snap);
   cudaFree(q->idx); cudaFree(q->ctl); cudaFree(q->tmp);
   if (q->h_ctl) cudaFreeHost(q->h_ctl);
   if (q->h_t) { cudaFreeHost(q->h_t); cudaFreeHost(q->h_s); cudaFreeHost(q->h_h); cudaFreeHost(q->h_lp); }
@@ -1123,8 +1125,8 @@ int deva_b200_hostq_push(deva_b200_hostq *q, uint64_t n, const uint64_t *time, c
   q->n += n;
   return 0;
 }
-int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
-                            uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
+static int hq_pop(deva_b200_hostq *q, bool by_key, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
+                  uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
   if (!q || !n_out || !gvt_out) return fail(DEVA_B200_ERR_ARG, "null argument");
   *n_out = 0; *gvt_out = ~0ull;
   if (pending_out) *pending_out = q->n;
@@ -1133,9 +1135,10 @@ int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, 
   const uint32_t n = (uint32_t)q->n;
   const unsigned grid = (unsigned)std::min<uint32_t>((n + 255) / 256, 148 * 8);
   hq::Cols &src = q->pool[q->cur], &keep = q->pool[q->cur ^ 1];
-  q->h_ctl->tmin = ~0ull; q->h_ctl->n_sel = 0; q->h_ctl->n_keep = 0;
+  q->h_ctl->tmin = ~0ull; q->h_ctl->smin = ~0ull; q->h_ctl->n_sel = 0; q->h_ctl->n_keep = 0; q->h_ctl->by_key = by_key ? 1u : 0u; q->h_ctl->pad = 0;
   CU(cudaMemcpyAsync(q->ctl, q->h_ctl, sizeof(hq::Ctl), cudaMemcpyHostToDevice, q->stream));
   hq::k_hq_min<<<grid, 256, 0, q->stream>>>(src.t, n, q->ctl);                    // GVT: block + grid min-reduction
+  if (by_key) hq::k_hq_min_sub<<<grid, 256, 0, q->stream>>>(src.t, src.s, n, q->ctl);   // (in stream order behind it)
   CU(cudaMemcpyAsync(q->h_ctl, q->ctl, sizeof(hq::Ctl), cudaMemcpyDeviceToHost, q->stream));
   CU(cudaStreamSynchronize(q->stream));
   *gvt_out = q->h_ctl->tmin;
@@ -1161,6 +1164,65 @@ int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, 
   q->cur ^= 1; q->n = nk;
   *n_out = ns;
   if (pending_out) *pending_out = nk;
+  return 0;
+}
+
+int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
+                            uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
+  return hq_pop(q, false, t_end, max_n, time, subtime, lp, handle, n_out, gvt_out, pending_out);
+}
+int deva_b200_hostq_pop_min_key(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
+                                uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
+  return hq_pop(q, true, t_end, max_n, time, subtime, lp, handle, n_out, gvt_out, pending_out);
+}
+int deva_b200_hostq_erase(deva_b200_hostq *q, uint64_t n, const uint64_t *handles, uint64_t *n_erased) {
+  if (!q || (n && !handles)) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (n_erased) *n_erased = 0;
+  if (n == 0 || q->n == 0) return 0;
+  if (n > q->cap) return fail(DEVA_B200_ERR_ARG, "hostq: more handles to erase than the pool can hold");
+  CU(cudaSetDevice(q->device));
+  int rc = hq_stage(q, n);
+  if (rc) return rc;
+  memcpy(q->h_h, handles, n * 8);
+  std::sort(q->h_h, q->h_h + n);
+  unsigned long long *gone = q->sel.h;          // (the horizon's staging column is free between two pops)
+  CU(cudaMemcpyAsync(gone, q->h_h, n * 8, cudaMemcpyHostToDevice, q->stream));
+  q->h_ctl->tmin = ~0ull; q->h_ctl->smin = ~0ull; q->h_ctl->n_sel = 0; q->h_ctl->n_keep = 0; q->h_ctl->by_key = 0; q->h_ctl->pad = 0;
+  CU(cudaMemcpyAsync(q->ctl, q->h_ctl, sizeof(hq::Ctl), cudaMemcpyHostToDevice, q->stream));
+  const uint32_t m = (uint32_t)q->n;
+  const unsigned grid = (unsigned)std::min<uint32_t>((m + 255) / 256, 148 * 8);
+  hq::k_hq_erase<<<grid, 256, 0, q->stream>>>(q->pool[q->cur], m, gone, (uint32_t)n, q->ctl, q->pool[q->cur ^ 1]);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(q->h_ctl, q->ctl, sizeof(hq::Ctl), cudaMemcpyDeviceToHost, q->stream));
+  CU(cudaStreamSynchronize(q->stream));
+  const uint32_t nk = q->h_ctl->n_keep;
+  if (nk > m) return fail(DEVA_B200_ERR_INVARIANT, "hostq: erase grew the pool");
+  if (n_erased) *n_erased = m - nk;
+  q->cur ^= 1; q->n = nk;
+  return 0;
+}
+int deva_b200_hostq_snapshot(deva_b200_hostq *q) {
+  if (!q) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (q->has_snap) return fail(DEVA_B200_ERR_STATE, "hostq: lingering snapshot (rewind first, pdes.cxx:705-708)");
+  CU(cudaSetDevice(q->device));
+  int rc = 0;
+  if (!q->snap.t && (rc = hq_cols_alloc(q->snap, q->cap))) return rc;
+  const hq::Cols &p = q->pool[q->cur];
+  CU(cudaMemcpyAsync(q->snap.t, p.t, q->n * 8, cudaMemcpyDeviceToDevice, q->stream)); CU(cudaMemcpyAsync(q->snap.s, p.s, q->n * 8, cudaMemcpyDeviceToDevice, q->stream));
+  CU(cudaMemcpyAsync(q->snap.h, p.h, q->n * 8, cudaMemcpyDeviceToDevice, q->stream)); CU(cudaMemcpyAsync(q->snap.lp, p.lp, q->n * 4, cudaMemcpyDeviceToDevice, q->stream));
+  q->snap_n = q->n; q->has_snap = true;
+  return 0;
+}
+int deva_b200_hostq_rewind(deva_b200_hostq *q, int32_t do_rewind) {
+  if (!q) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (!q->has_snap) return fail(DEVA_B200_ERR_STATE, "hostq: rewind without a snapshot");
+  q->has_snap = false;
+  if (!do_rewind) return 0;
+  CU(cudaSetDevice(q->device));
+  const hq::Cols &p = q->pool[q->cur];
+  CU(cudaMemcpyAsync(p.t, q->snap.t, q->snap_n * 8, cudaMemcpyDeviceToDevice, q->stream)); CU(cudaMemcpyAsync(p.s, q->snap.s, q->snap_n * 8, cudaMemcpyDeviceToDevice, q->stream));
+  CU(cudaMemcpyAsync(p.h, q->snap.h, q->snap_n * 8, cudaMemcpyDeviceToDevice, q->stream)); CU(cudaMemcpyAsync(p.lp, q->snap.lp, q->snap_n * 4, cudaMemcpyDeviceToDevice, q->stream));
+  q->n = q->snap_n;
   return 0;
 }
 

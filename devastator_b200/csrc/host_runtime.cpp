@@ -10,6 +10,7 @@
 #include <devastator/os_env.hxx>
 #include <devastator/pdes.hxx>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -253,6 +254,18 @@ namespace {
     std::vector<char> any_commit;
     pdes::statistics hstats;
     std::size_t slice_lo = 0, slice_hi = 0;                // this rank's part of the batch at the horizon
+    // the open horizon (one time stamp): what this rank's thread executed there, not committed yet, and what it created
+    struct PastRec { pdes::detail::host_event *e; std::int32_t cd; std::uint64_t time, sub, seq_before, prev_t, prev_s; char prev_any; };
+    std::vector<PastRec> past;
+    std::vector<pdes::detail::host_event*> born;
+    std::vector<std::function<std::uint64_t()>> checksummer;   // per cd (register_checksum_if_debug; DEBUG builds)
+    // rewindable drain (pdes.cxx:710-739): the registered objects' bytes, the per-cd counters, the event objects
+    // that may not be deleted before pdes::rewind decides
+    std::vector<std::vector<char>> fridge;
+    std::vector<std::uint64_t> seq_rw, last_t_rw, last_s_rw;
+    std::vector<char> any_rw;
+    std::vector<pdes::detail::host_event*> created;        // made by this rank's thread during the rewindable drain
+    std::vector<pdes::detail::host_event*> kept_roots;     // older events this rank committed during it
   };
   struct Sim {
     std::vector<RankSide> ranks;
@@ -274,6 +287,15 @@ namespace {
     std::uint64_t b_n = 0;
     bool host_done = false;
     std::vector<std::function<void()>> tasks;              // bcast_procs functors every rank runs before the next batch
+    bool in_host_drain = false;
+    bool hor_open = false;                                 // a time stamp has been executed (in part) and not committed
+    std::uint64_t hor_time = 0;
+    bool by_key = false;                                   // the open time stamp is being redone key by key
+    bool close_horizon = false;                            // (rank 0 -> all) commit the open horizon before this batch
+    std::atomic<bool> overtaken{false};                    // some rank met an event behind one its cd had executed
+    std::uint32_t drain_id = 0;
+    bool host_rewindable = false, host_has_rewind = false;
+    std::uint64_t undone_horizons = 0;
   };
   Sim g_sim;
 
@@ -354,7 +376,8 @@ void pdes::init(std::int32_t cds_this_rank) {       // pdes.cxx:313-343
   for(std::int32_t cd = 0; cd < cds_this_rank; cd++) rs.seq[std::size_t(cd)] = begin + std::uint64_t(cd);   // pdes.cxx:332
   rs.last_t.assign(std::size_t(cds_this_rank), 0); rs.last_s.assign(std::size_t(cds_this_rank), 0); rs.any_commit.assign(std::size_t(cds_this_rank), 0);
   rs.hstats = pdes::statistics();
-  if(me == 0) { g_sim.lp_n = total; g_sim.host_mode = false; g_sim.host_done = false; }
+  rs.checksummer.assign(std::size_t(cds_this_rank), std::function<std::uint64_t()>());
+  if(me == 0) { g_sim.lp_n = total; g_sim.host_mode = false; g_sim.host_done = false; g_sim.host_has_rewind = false; g_sim.host_rewindable = false; g_sim.in_host_drain = false; }
   deva::barrier();
 }
 
@@ -369,17 +392,35 @@ namespace {
     g_sim.host_mode = true;
   }
 }
+namespace {
+  // every event object made on this thread: which drain it belongs to, and - inside a drain - that it is a child of
+  // the open horizon (it disappears again if that horizon is undone)
+  void adopt(RankSide &rs, pdes::detail::host_event *e) {
+    e->drain_id = g_sim.drain_id;
+    if(g_sim.in_host_drain) {
+      e->born_here = true;
+      rs.born.push_back(e);
+      if(g_sim.host_rewindable) rs.created.push_back(e);
+    }
+    rs.outbox.push_back(e);
+  }
+}
 void pdes::detail::host_root_event(std::int32_t cd, host_event *e) {
   RankSide &rs = g_sim.ranks[deva::rank_me()];
   DEVA_ASSERT_ALWAYS(0 <= cd && cd < rs.cds);
   if(!g_sim.host_mode) host_mode_on();
   e->target_rank = deva::rank_me(); e->target_cd = cd;
-  rs.outbox.push_back(e);
+  adopt(rs, e);
 }
 void pdes::detail::host_send(std::int32_t rank, std::int32_t cd, host_event *e) {
   DEVA_ASSERT_ALWAYS(0 <= rank && rank < deva::rank_n && 0 <= cd && cd < g_sim.ranks[std::size_t(rank)].cds, "send to a cd that does not exist");
   e->target_rank = rank; e->target_cd = cd;
-  g_sim.ranks[deva::rank_me()].outbox.push_back(e);
+  adopt(g_sim.ranks[deva::rank_me()], e);
+}
+void pdes::detail::no_reverser() {
+  deva::assert_failed(__FILE__, __LINE__, "an execution has to be undone, but what this event type's execute() returned has neither "
+                                          "unexecute(event_context&, Event&) nor a call operator (pdes.hxx:531-563)");
+  std::abort();
 }
 std::uint64_t pdes::detail::next_seq_id(std::int32_t cd, std::int32_t n) {     // pdes.cxx:221-225
   RankSide &rs = g_sim.ranks[deva::rank_me()];
@@ -394,14 +435,95 @@ namespace {
   // pdes::drain for host-executed event types.  Every iteration: (1) every rank thread runs the bcast_procs functors
   // of the previous batch (they insert events on their own rank); (2) rank 0 pushes what the ranks created into the
   // device pool and pops the events at the commit horizon (GVT = smallest pending time), ordered by (cd, subtime);
-  // (3) every rank thread executes its cds' events in that order - nothing at the horizon can be rolled back, so each
-  // is committed (the reverser's commit hook runs) and destroyed at once.
+  // (3) every rank thread executes its cds' events in that order.
+  //
+  // One time stamp (the HORIZON) is open at a time.  What ran there stays uncommitted until the pool's minimum has
+  // moved past it, because a handler may send to the same time stamp (pdes.hxx:683-689 only asks for a
+  // greater-or-equal (time, subtime)), and such a child can sort BEFORE something its cd has already run.  Then the
+  // horizon is undone - the reference's rollback (pdes.cxx:527-693) at the granularity of one time stamp: every rank
+  // unexecutes what it ran there, latest first; every event object created there (the children, and theirs) is erased
+  // from the pool by handle and destroyed; the events the horizon started from go back into the pool - and the time
+  // stamp is redone key by key (deva_b200_hostq_pop_min_key), which cannot be overtaken.  Commit hooks run when the
+  // horizon closes, in the order of execution.
+  void commit_horizon(RankSide &rs) {
+    for(auto *e: rs.born) e->born_here = false;
+    rs.born.clear();
+    for(auto &p: rs.past) {
+      pdes::event_context ec; ec.cd = p.cd; ec.time = p.time; ec.subtime = p.sub;
+      p.e->commit(ec);                                                  // pdes.cxx:842-856
+      rs.hstats.committed_n += 1;
+      if(!g_sim.host_rewindable) delete p.e;
+      else { p.e->done = true; if(p.e->drain_id != g_sim.drain_id) rs.kept_roots.push_back(p.e); }
+    }
+    rs.past.clear();
+  }
+  void undo_horizon(RankSide &rs, int me) {
+    // (a) this rank's executions, latest first; what the horizon started from goes back to the pool
+    for(std::size_t i = rs.past.size(); i-- > 0;) {
+      auto &p = rs.past[i];
+      pdes::event_context ec; ec.cd = p.cd; ec.time = p.time; ec.subtime = p.sub;
+      p.e->unexecute(ec);
+      #if DEBUG
+        if(rs.checksummer[std::size_t(p.cd)])
+          DEVA_ASSERT_ALWAYS(rs.checksummer[std::size_t(p.cd)]() == p.e->entry_checksum, "Checksum mismatch after unexecute.");
+      #endif
+      rs.seq[std::size_t(p.cd)] = p.seq_before;
+      rs.last_t[std::size_t(p.cd)] = p.prev_t; rs.last_s[std::size_t(p.cd)] = p.prev_s; rs.any_commit[std::size_t(p.cd)] = p.prev_any;
+      if(!p.e->born_here) rs.outbox.push_back(p.e);
+    }
+    rs.past.clear();
+    rs.task_outbox.clear();
+    deva::barrier();                 // nobody reads another rank's event objects after this
+    // (b) the horizon's children: out of the outbox here, out of the pool on the device, then destroyed
+    rs.outbox.erase(std::remove_if(rs.outbox.begin(), rs.outbox.end(), [](pdes::detail::host_event *e) { return e->born_here; }), rs.outbox.end());
+    deva::barrier();
+    if(me == 0) {
+      std::vector<std::uint64_t> gone;
+      for(auto &r: g_sim.ranks) for(auto *e: r.born) gone.push_back(std::uint64_t(reinterpret_cast<std::uintptr_t>(e)));
+      std::uint64_t erased = 0;
+      if(!gone.empty()) ck(deva_b200_hostq_erase(g_sim.hq, gone.size(), gone.data(), &erased), "deva_b200_hostq_erase");
+      g_sim.tasks.clear();
+      g_sim.by_key = true;
+      g_sim.overtaken.store(false);
+      g_sim.undone_horizons += 1;
+    }
+    deva::barrier();
+    for(auto *e: rs.born) {
+      e->born_here = false;
+      if(!g_sim.host_rewindable) delete e; else e->done = true;      // (a rewindable drain destroys them at pdes::rewind)
+    }
+    rs.born.clear();
+  }
+
   std::uint64_t host_drain(std::uint64_t t_end, bool rewindable) {
     const int me = deva::rank_me();
     RankSide &rs = g_sim.ranks[std::size_t(me)];
-    DEVA_ASSERT_ALWAYS(!rewindable, "rewindable drains of host-executed event types are not built (device-resident models support them)");
-    if(me == 0 && !g_sim.hq)
-      ck(deva_b200_hostq_create(deva::os_env<int>("DEVA_B200_DEVICE", 0), deva::os_env<std::uint64_t>("DEVA_B200_HOSTQ_CAP", 0), &g_sim.hq), "deva_b200_hostq_create");
+    if(me == 0) {
+      DEVA_ASSERT_ALWAYS(!g_sim.host_has_rewind, "Lingering rewind state must be rewound via pdes::rewind(true|false) before calling pdes::drain().");
+      if(!g_sim.hq)
+        ck(deva_b200_hostq_create(deva::os_env<int>("DEVA_B200_DEVICE", 0), deva::os_env<std::uint64_t>("DEVA_B200_HOSTQ_CAP", 0), &g_sim.hq), "deva_b200_hostq_create");
+      if(rewindable) {   // the pool as it is once the events created since the last drain are in it
+        std::vector<std::uint64_t> t, sb, h; std::vector<std::uint32_t> lp;
+        for(auto &r: g_sim.ranks) {
+          for(auto *e: r.outbox) {
+            t.push_back(e->time); sb.push_back(e->subtime); h.push_back(std::uint64_t(reinterpret_cast<std::uintptr_t>(e)));
+            lp.push_back(std::uint32_t(g_sim.ranks[std::size_t(e->target_rank)].lp_begin + std::uint64_t(e->target_cd)));
+          }
+          r.outbox.clear();
+        }
+        if(!t.empty()) ck(deva_b200_hostq_push(g_sim.hq, t.size(), t.data(), sb.data(), lp.data(), h.data()), "deva_b200_hostq_push");
+        ck(deva_b200_hostq_snapshot(g_sim.hq), "deva_b200_hostq_snapshot");
+      }
+      g_sim.drain_id += 1;
+      g_sim.host_rewindable = rewindable; g_sim.host_has_rewind = rewindable;
+      g_sim.in_host_drain = true;
+      g_sim.hor_open = false; g_sim.by_key = false; g_sim.overtaken.store(false);
+    }
+    if(rewindable) {     // fridge (pdes.cxx:710-739): the registered objects and the per-cd counters as they are now
+      rs.fridge.resize(rs.regs.size());
+      for(std::size_t i = 0; i < rs.regs.size(); i++) rs.fridge[i].assign(static_cast<char*>(rs.regs[i].addr), static_cast<char*>(rs.regs[i].addr) + rs.regs[i].bytes);
+      rs.seq_rw = rs.seq; rs.last_t_rw = rs.last_t; rs.last_s_rw = rs.last_s; rs.any_rw = rs.any_commit;
+    }
     for(;;) {
       deva::barrier();
       for(auto &task: g_sim.tasks) task();                              // (1)
@@ -420,15 +542,20 @@ namespace {
         std::uint64_t pending = 0, gvt = 0;
         const std::size_t room = std::max<std::size_t>(g_sim.b_time.size(), std::size_t(1) << 16);
         g_sim.b_time.resize(room); g_sim.b_sub.resize(room); g_sim.b_handle.resize(room); g_sim.b_lp.resize(room);
-        int rc = deva_b200_hostq_pop_min(g_sim.hq, t_end, room, g_sim.b_time.data(), g_sim.b_sub.data(), g_sim.b_lp.data(), g_sim.b_handle.data(), &g_sim.b_n, &gvt, &pending);
+        auto pop = g_sim.by_key ? deva_b200_hostq_pop_min_key : deva_b200_hostq_pop_min;
+        int rc = pop(g_sim.hq, t_end, room, g_sim.b_time.data(), g_sim.b_sub.data(), g_sim.b_lp.data(), g_sim.b_handle.data(), &g_sim.b_n, &gvt, &pending);
         if(rc == DEVA_B200_ERR_CAPACITY) {   // more events at one time stamp than the arrays hold: they are all still pending - grow and retry
           const std::size_t more = std::size_t(pending) + 1;
           g_sim.b_time.resize(more); g_sim.b_sub.resize(more); g_sim.b_handle.resize(more); g_sim.b_lp.resize(more);
-          rc = deva_b200_hostq_pop_min(g_sim.hq, t_end, more, g_sim.b_time.data(), g_sim.b_sub.data(), g_sim.b_lp.data(), g_sim.b_handle.data(), &g_sim.b_n, &gvt, &pending);
+          rc = pop(g_sim.hq, t_end, more, g_sim.b_time.data(), g_sim.b_sub.data(), g_sim.b_lp.data(), g_sim.b_handle.data(), &g_sim.b_n, &gvt, &pending);
         }
         ck(rc, "deva_b200_hostq_pop_min");
         g_sim.gvt = gvt;
         g_sim.host_done = g_sim.b_n == 0;
+        // the pool's minimum has left the open time stamp (or nothing is left below t_end): that horizon is final
+        g_sim.close_horizon = g_sim.hor_open && (g_sim.host_done || g_sim.b_time[0] != g_sim.hor_time);
+        if(g_sim.close_horizon) { g_sim.hor_open = false; g_sim.by_key = false; }
+        if(!g_sim.host_done) { g_sim.hor_open = true; g_sim.hor_time = g_sim.b_time[0]; }
         // the batch is sorted by global cd: every rank's share is one contiguous range
         std::size_t i = 0;
         for(auto &r: g_sim.ranks) {
@@ -438,36 +565,82 @@ namespace {
         }
       }
       deva::barrier();
+      if(g_sim.close_horizon) commit_horizon(rs);
       if(g_sim.host_done) break;
       for(std::size_t i = rs.slice_lo; i < rs.slice_hi; i++) {          // (3)
         auto *e = reinterpret_cast<pdes::detail::host_event*>(std::uintptr_t(g_sim.b_handle[i]));
         const std::size_t cd = std::size_t(g_sim.b_lp[i] - rs.lp_begin);
         pdes::execute_context cxt;
         cxt.cd = std::int32_t(cd); cxt.time = g_sim.b_time[i]; cxt.subtime = g_sim.b_sub[i];
+        bool older = false;
         if(rs.any_commit[cd]) {
-          const bool older = cxt.time < rs.last_t[cd] || (cxt.time == rs.last_t[cd] && cxt.subtime < rs.last_s[cd]);
-          DEVA_ASSERT_ALWAYS(!older, "an event arrived behind one its cd has already executed (a send that did not move time forward): "
-                                     "that needs a rollback, which the conservative host executor does not do");
-          if(cxt.time == rs.last_t[cd] && cxt.subtime == rs.last_s[cd]) rs.hstats.deterministic = false;   // pdes.cxx:828-831
+          older = cxt.time < rs.last_t[cd] || (cxt.time == rs.last_t[cd] && cxt.subtime < rs.last_s[cd]);
+          if(older) {
+            // behind something this cd has run.  Only a send to the open time stamp can do that, and only while the
+            // time stamp is taken in one piece
+            DEVA_ASSERT_ALWAYS(cxt.time == g_sim.hor_time && cxt.time == rs.last_t[cd] && !g_sim.by_key, "host executor: an event arrived behind the commit horizon");
+            g_sim.overtaken.store(true);
+          }
         }
+        if(older || g_sim.overtaken.load(std::memory_order_relaxed)) {    // the horizon will be undone: hand the rest of the slice back
+          for(std::size_t j = i; j < rs.slice_hi; j++) {
+            auto *r = reinterpret_cast<pdes::detail::host_event*>(std::uintptr_t(g_sim.b_handle[j]));
+            if(!r->born_here) rs.outbox.push_back(r);
+          }
+          break;
+        }
+        if(rs.any_commit[cd] && cxt.time == rs.last_t[cd] && cxt.subtime == rs.last_s[cd]) rs.hstats.deterministic = false;   // pdes.cxx:828-831
+        rs.past.push_back({e, std::int32_t(cd), cxt.time, cxt.subtime, rs.seq[cd], rs.last_t[cd], rs.last_s[cd], rs.any_commit[cd]});
         rs.any_commit[cd] = 1; rs.last_t[cd] = cxt.time; rs.last_s[cd] = cxt.subtime;
+        #if DEBUG
+          e->entry_checksum = rs.checksummer[cd] ? rs.checksummer[cd]() : 0;      // pdes.cxx:929
+        #endif
         t_cxt = &cxt;
         e->execute(cxt);
         t_cxt = nullptr;
         rs.hstats.executed_n += 1;
-        pdes::event_context ec = cxt;
-        e->commit(ec);                                                  // final at once: pdes.cxx:842-856
-        rs.hstats.committed_n += 1;
-        delete e;
       }
       deva::barrier();
+      if(g_sim.overtaken.load()) { undo_horizon(rs, me); continue; }
       if(me == 0) for(auto &r: g_sim.ranks) { for(auto &f: r.task_outbox) g_sim.tasks.push_back(std::move(f)); r.task_outbox.clear(); }
     }
     deva::barrier();
+    if(me == 0) g_sim.in_host_drain = false;
+    deva::barrier();
     return g_sim.gvt;
+  }
+  // pdes::rewind for host-executed event types (pdes.cxx:1137-1229).  true: the registered objects and the per-cd
+  // counters go back to what the fridge holds, the pool to its device-side copy, every event object made during the
+  // drain is destroyed, the older ones it committed are pending again.  false: what the drain committed is destroyed.
+  void host_rewind(bool do_rewind) {
+    const int me = deva::rank_me();
+    RankSide &rs = g_sim.ranks[std::size_t(me)];
+    DEVA_ASSERT_ALWAYS(g_sim.host_has_rewind, "pdes::rewind without a rewindable drain");
+    if(do_rewind) {
+      for(std::size_t i = 0; i < rs.regs.size(); i++) std::memcpy(rs.regs[i].addr, rs.fridge[i].data(), rs.regs[i].bytes);
+      rs.seq = rs.seq_rw; rs.last_t = rs.last_t_rw; rs.last_s = rs.last_s_rw; rs.any_commit = rs.any_rw;
+      for(auto *e: rs.created) delete e;
+      for(auto *e: rs.kept_roots) e->done = false;
+    }
+    else {
+      for(auto *e: rs.created) if(e->done) delete e;
+      for(auto *e: rs.kept_roots) delete e;
+    }
+    rs.created.clear(); rs.kept_roots.clear(); rs.fridge.clear();
+    deva::barrier();
+    if(me == 0) {
+      ck(deva_b200_hostq_rewind(g_sim.hq, do_rewind ? 1 : 0), "deva_b200_hostq_rewind");
+      g_sim.host_has_rewind = false; g_sim.host_rewindable = false;
+    }
   }
   void host_finalize() {       // destroy what is still pending (pdes.cxx:1060-1135)
     if(deva::rank_me() != 0) return;
+    if(deva::os_env<bool>("DEVA_B200_HOSTQ_VERBOSE", false)) {
+      std::uint64_t ex = 0, cm = 0;
+      for(auto &r: g_sim.ranks) { ex += r.hstats.executed_n; cm += r.hstats.committed_n; }
+      std::cerr << "deva_b200 host executor: executed " << ex << ", committed " << cm << ", time stamps undone and redone key by key " << g_sim.undone_horizons << std::endl;
+    }
+    g_sim.undone_horizons = 0;
     for(auto &r: g_sim.ranks) { for(auto *e: r.outbox) delete e; r.outbox.clear(); r.task_outbox.clear(); }
     g_sim.tasks.clear();
     if(g_sim.hq) {
@@ -493,9 +666,16 @@ void pdes::detail::register_state_raw(std::int32_t cd, void *addr, std::size_t b
   rs.regs.push_back({cd, addr, bytes});
 }
 
-void pdes::register_checksum_if_debug(std::int32_t, std::function<std::uint64_t()>&&) {
-  // DEBUG-only hook in the reference (pdes.cxx:369-374); device models are checked against the
-  // oracle instead (tests/)
+void pdes::register_checksum_if_debug(std::int32_t cd, std::function<std::uint64_t()> &&fn) {
+  // DEBUG-only hook in the reference (pdes.cxx:369-374).  Host-executed event types: taken when an execution is
+  // entered and compared after its unexecute (undo_horizon).  Device models are checked against the oracle instead.
+  #if DEBUG
+    RankSide &rs = g_sim.ranks[deva::rank_me()];
+    DEVA_ASSERT_ALWAYS(0 <= cd && cd < rs.cds);
+    rs.checksummer[std::size_t(cd)] = std::move(fn);
+  #else
+    (void)cd; (void)fn;
+  #endif
 }
 
 void pdes::detail::root_event_raw(std::int32_t cd, std::uint64_t time, std::uint64_t subtime, bool user_subtime,
@@ -623,6 +803,7 @@ std::uint64_t pdes::drain(std::uint64_t t_end, bool rewindable) {   // pdes.cxx:
 
 void pdes::rewind(bool do_rewind) {                   // pdes.cxx:1137-1229
   deva::barrier();
+  if(g_sim.host_mode) { host_rewind(do_rewind); deva::barrier(); return; }
   if(deva::rank_me() == 0) {
     DEVA_ASSERT_ALWAYS(g_sim.has_rewind, "pdes::rewind without a rewindable drain");
     g_sim.has_rewind = false;

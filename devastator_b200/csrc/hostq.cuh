@@ -6,8 +6,11 @@
 // what pdes.cxx's heaps and gvt.cxx do in the reference: it holds the pending set in HBM (structure of arrays),
 // finds the commit horizon with a block + grid min-reduction (GVT = the smallest pending time), extracts the
 // events at the horizon by stream compaction and orders them by (LP, subtime) with a device merge sort.  The
-// host runs them conservatively - nothing at the horizon can be rolled back, so they are committed as they run -
-// and pushes what they sent back into the pool (host_runtime.cpp, "Tier G").
+// host runs them conservatively, one time stamp at a time, and pushes what they sent back into the pool
+// (host_runtime.cpp, "Tier G"); when a send that did not move time lands behind an event its cd has already run,
+// the host undoes the open time stamp (E's reverser), the children of the undone executions are erased from the
+// pool by handle (k_hq_erase), and the time stamp is redone key by key (k_hq_min_sub).  Rewindable drains keep a
+// device-side copy of the pool.
 //   cd_state::future_events / cds_by_now   pdes.cxx:82-154     -> the pool + k_hq_min
 //   gvt epochs, fossil collection          gvt.cxx:53-149, pdes.cxx:816-871 -> k_hq_min, k_hq_split (compaction)
 #pragma once
@@ -20,7 +23,7 @@ namespace deva_b200 {
 namespace hq {
 
 struct Cols { unsigned long long *t, *s, *h; uint32_t *lp; };
-struct Ctl { unsigned long long tmin; uint32_t n_sel, n_keep; };
+struct Ctl { unsigned long long tmin, smin; uint32_t n_sel, n_keep, by_key, pad; };
 
 __global__ void k_hq_min(const unsigned long long *t, uint32_t n, Ctl *c) {
   unsigned long long m = ~0ull;
@@ -35,15 +38,25 @@ __global__ void k_hq_min(const unsigned long long *t, uint32_t n, Ctl *c) {
     if (m != ~0ull) atomicMin(&c->tmin, m);
   }
 }
+// the smallest subtime among the records at the smallest time (the horizon narrowed to one (time, subtime) key)
+__global__ void k_hq_min_sub(const unsigned long long *t, const unsigned long long *s, uint32_t n, Ctl *c) {
+  const unsigned long long tmin = c->tmin;
+  unsigned long long m = ~0ull;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) if (t[i] == tmin && s[i] < m) m = s[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, m, o); m = x < m ? x : m; }
+  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&c->smin, m);
+}
 // stream compaction: the records at the horizon go to `sel`, the rest to the other half of the pool (`keep`);
 // places are claimed per warp (one atomic per warp and side)
 __global__ void k_hq_split(Cols src, uint32_t n, Ctl *c, Cols sel, Cols keep) {
-  const unsigned long long tmin = c->tmin;
+  const unsigned long long tmin = c->tmin, smin = c->smin;
+  const bool by_key = c->by_key != 0;
   const uint32_t lane = threadIdx.x & 31;
   for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
     const uint32_t i = base + lane;
     const bool live = i < n;
-    const bool pick = live && src.t[i] == tmin;
+    const bool pick = live && src.t[i] == tmin && (!by_key || src.s[i] == smin);
     const unsigned ms = __ballot_sync(0xffffffffu, pick), mk = __ballot_sync(0xffffffffu, live && !pick);
     uint32_t bs = 0, bk = 0;
     if (lane == 0) { if (ms) bs = atomicAdd(&c->n_sel, (uint32_t)__popc(ms)); if (mk) bk = atomicAdd(&c->n_keep, (uint32_t)__popc(mk)); }
@@ -52,6 +65,27 @@ __global__ void k_hq_split(Cols src, uint32_t n, Ctl *c, Cols sel, Cols keep) {
     const Cols &d = pick ? sel : keep;
     const uint32_t p = pick ? bs + (uint32_t)__popc(ms & ((1u << lane) - 1u)) : bk + (uint32_t)__popc(mk & ((1u << lane) - 1u));
     d.t[p] = src.t[i]; d.s[p] = src.s[i]; d.h[p] = src.h[i]; d.lp[p] = src.lp[i];
+  }
+}
+// erase by handle: `gone` is sorted; a record whose handle is found there is dropped, the rest is compacted into `keep`
+__global__ void k_hq_erase(Cols src, uint32_t n, const unsigned long long *gone, uint32_t n_gone, Ctl *c, Cols keep) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t i = base + lane;
+    bool stay = i < n;
+    if (stay) {
+      const unsigned long long h = src.h[i];
+      uint32_t lo = 0, hi = n_gone;
+      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (gone[mid] < h) lo = mid + 1; else hi = mid; }
+      stay = !(lo < n_gone && gone[lo] == h);
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, stay);
+    uint32_t bk = 0;
+    if (lane == 0 && mk) bk = atomicAdd(&c->n_keep, (uint32_t)__popc(mk));
+    bk = __shfl_sync(0xffffffffu, bk, 0);
+    if (!stay) continue;
+    const uint32_t p = bk + (uint32_t)__popc(mk & ((1u << lane) - 1u));
+    keep.t[p] = src.t[i]; keep.s[p] = src.s[i]; keep.h[p] = src.h[i]; keep.lp[p] = src.lp[i];
   }
 }
 __global__ void k_hq_iota(uint32_t *idx, uint32_t n) {

@@ -56,6 +56,7 @@ ABI_SYMBOLS = [
     "deva_b200_digest", "deva_b200_comm_unique_id", "deva_b200_comm_init", "deva_b200_stream",
     "deva_b200_reset", "deva_b200_comm_init_group", "deva_b200_set_heartbeat",
     "deva_b200_hostq_create", "deva_b200_hostq_destroy", "deva_b200_hostq_push", "deva_b200_hostq_pop_min",
+    "deva_b200_hostq_pop_min_key", "deva_b200_hostq_erase", "deva_b200_hostq_snapshot", "deva_b200_hostq_rewind",
 ]
 
 
@@ -101,6 +102,10 @@ class Api:
         L.deva_b200_hostq_destroy.restype = None
         L.deva_b200_hostq_push.argtypes = [P, C.c_uint64, P, P, P, P]
         L.deva_b200_hostq_pop_min.argtypes = [P, C.c_uint64, C.c_uint64, P, P, P, P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.deva_b200_hostq_pop_min_key.argtypes = L.deva_b200_hostq_pop_min.argtypes
+        L.deva_b200_hostq_erase.argtypes = [P, C.c_uint64, P, C.POINTER(C.c_uint64)]
+        L.deva_b200_hostq_snapshot.argtypes = [P]
+        L.deva_b200_hostq_rewind.argtypes = [P, C.c_int32]
 
     def check(self, rc):
         if rc != 0:
@@ -256,13 +261,27 @@ class HostQueue:
         l = np.ascontiguousarray(lp, dtype=np.uint32); h = np.ascontiguousarray(handle, dtype=np.uint64)
         self.api.check(self.api.lib.deva_b200_hostq_push(self.h, t.size, t.ctypes.data, s.ctypes.data, l.ctypes.data, h.ctypes.data))
 
-    def pop_min(self, t_end=T_INF, room=1 << 16):
+    def pop_min(self, t_end=T_INF, room=1 << 16, by_key=False):
+        """all events at the smallest time stamp; by_key: only those at the smallest (time, subtime) pair"""
         t = np.empty(room, np.uint64); s = np.empty(room, np.uint64); l = np.empty(room, np.uint32); h = np.empty(room, np.uint64)
         n, gvt, pending = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        self.api.check(self.api.lib.deva_b200_hostq_pop_min(self.h, t_end, room, t.ctypes.data, s.ctypes.data, l.ctypes.data, h.ctypes.data,
-                                                            C.byref(n), C.byref(gvt), C.byref(pending)))
+        fn = self.api.lib.deva_b200_hostq_pop_min_key if by_key else self.api.lib.deva_b200_hostq_pop_min
+        self.api.check(fn(self.h, t_end, room, t.ctypes.data, s.ctypes.data, l.ctypes.data, h.ctypes.data, C.byref(n), C.byref(gvt), C.byref(pending)))
         k = n.value
         return dict(time=t[:k], subtime=s[:k], lp=l[:k], handle=h[:k], gvt=gvt.value, pending=pending.value)
+
+    def erase(self, handles):
+        """removes the pending events with these handles; returns how many were found"""
+        h = np.ascontiguousarray(handles, dtype=np.uint64)
+        n = C.c_uint64()
+        self.api.check(self.api.lib.deva_b200_hostq_erase(self.h, h.size, h.ctypes.data, C.byref(n)))
+        return n.value
+
+    def snapshot(self):
+        self.api.check(self.api.lib.deva_b200_hostq_snapshot(self.h))
+
+    def rewind(self, do_rewind):
+        self.api.check(self.api.lib.deva_b200_hostq_rewind(self.h, int(do_rewind)))
 
     def close(self):
         if self.h:

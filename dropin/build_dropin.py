@@ -40,6 +40,12 @@ APPS = [
     # Advance / ShareState handlers (qss.hxx:92-144) run on the rank threads in the order the device pool decides
     ("heat", "example/heat/heat.cxx", "", [], [1, 4]),
     ("heat_q0", "example/heat/heat.cxx", "", [], [2], ["-DQSS_ORDER=0"]),
+    # test/phold.cxx WITHOUT its device model: the same source through the host executor (rewindable drains in thirds,
+    # DEBUG checksums), against the same goldens
+    ("phold_test_host", "test/phold.cxx", "", [], [2], ["-UDEBUG", "-UNDEBUG", "-DDEBUG=1"]),
+    # this repo's own test model whose sends may keep the time stamp (tests/csrc/zero_delay.cxx): time stamps undone and
+    # redone key by key, erase by handle, rewindable drains; goldens from the same source on the reference runtime
+    ("zero_delay", os.path.join(ROOT, "tests", "csrc", "zero_delay.cxx"), "", [], [1, 4], ["-UDEBUG", "-UNDEBUG", "-DDEBUG=1"]),
 ]
 
 

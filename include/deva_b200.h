@@ -164,6 +164,19 @@ int deva_b200_hostq_push(deva_b200_hostq *q, uint64_t n, const uint64_t *time, c
  * before the call (~0 when the pool is empty); *pending_out = events left in the pool.  max_n = room in the arrays. */
 int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime,
                             uint32_t *lp, uint64_t *handle, uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out);
+/* The same with the horizon narrowed to the smallest (time, subtime) PAIR (stamped_event's order, pdes.hxx:916-954):
+ * only the events that share the smallest key leave the pool.  A child never sorts before its parent
+ * (pdes.hxx:683-689), so executing key by key can never be overtaken - the host executor falls back to this for a
+ * time stamp at which an event arrived behind one its cd had already executed (a send that did not move time). */
+int deva_b200_hostq_pop_min_key(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime,
+                                uint32_t *lp, uint64_t *handle, uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out);
+/* Removes the pending events whose handle is one of handles[0..n) (the children of executions that were undone:
+ * the anti-messages of pdes.cxx:393-493,527-693, resolved inside the pool).  *n_erased = how many were found. */
+int deva_b200_hostq_erase(deva_b200_hostq *q, uint64_t n, const uint64_t *handles, uint64_t *n_erased);
+/* Rewindable drains (pdes.cxx:710-739,1137-1229): snapshot keeps a device-side copy of the pending set;
+ * rewind(do_rewind != 0) puts it back, rewind(0) drops it. */
+int deva_b200_hostq_snapshot(deva_b200_hostq *q);
+int deva_b200_hostq_rewind(deva_b200_hostq *q, int32_t do_rewind);
 
 /* Multi-GPU (replaces world_gasnet / threads transports and gvt.cxx's credit-counted reduction).
  * uid = 128-byte ncclUniqueId made by rank 0.  With one process per GPU the engines map each other's

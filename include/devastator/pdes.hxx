@@ -82,8 +82,13 @@ namespace pdes {
     struct host_event {
       std::uint64_t time = 0, subtime = 0;
       std::int32_t target_rank = 0, target_cd = 0;
+      std::uint32_t drain_id = 0;        // the drain (or the root insertions before it) this object was created in
+      bool born_here = false;            // created inside the horizon that is open (not committed yet)
+      bool done = false;                 // executed and committed during a rewindable drain, kept until pdes::rewind
+      std::uint64_t entry_checksum = 0;  // register_checksum_if_debug: the cd's checksum when execute was entered
       virtual ~host_event() {}
       virtual void execute(execute_context &cxt) = 0;
+      virtual void unexecute(event_context &cxt) = 0;   // the reverser's unexecute (or call operator); destroys the reverser
       virtual void commit(event_context &cxt) = 0;      // the reverser's commit hook (if any); destroys the reverser
     };
     void host_root_event(std::int32_t cd, host_event *e);                     // into a cd of this rank
@@ -98,6 +103,16 @@ namespace pdes {
     struct event_commit_dispatch<E, ExecRet, decltype(std::declval<ExecRet>().commit(std::declval<event_context&>(), std::declval<E&>()), void())> {
       void operator()(event_context &cxt, E &user, ExecRet &r) const { r.commit(cxt, user); }
     };
+    // the reverser is undone through `unexecute(cxt, event)` or, failing that, its call operator (pdes.hxx:531-563)
+    template<int N> struct choice: choice<N - 1> {};
+    template<> struct choice<0> {};
+    template<typename E, typename R>
+    auto undo_with(choice<2>, event_context &cxt, E &user, R &r) -> decltype(r.unexecute(cxt, user), void()) { r.unexecute(cxt, user); }
+    template<typename E, typename R>
+    auto undo_with(choice<1>, event_context &cxt, E &user, R &r) -> decltype(r(cxt, user), void()) { r(cxt, user); }
+    [[noreturn]] void no_reverser();
+    template<typename E, typename R>
+    void undo_with(choice<0>, event_context&, E&, R&) { no_reverser(); }
     void register_state_raw(std::int32_t cd, void *addr, std::size_t bytes);
     void root_event_raw(std::int32_t cd, std::uint64_t time, std::uint64_t subtime, bool user_subtime,
                         std::uint32_t payload, const model_binding *model);
@@ -125,6 +140,7 @@ namespace pdes {
       explicit host_event_impl(E u): user(std::move(u)) {}
       ~host_event_impl() {}
       void execute(execute_context &cxt) override { ::new(&exec_ret) ExecRet{user.execute(cxt)}; }
+      void unexecute(event_context &cxt) override { undo_with(choice<2>(), cxt, user, exec_ret); exec_ret.~ExecRet(); }
       void commit(event_context &cxt) override { event_commit_dispatch<E, ExecRet>()(cxt, user, exec_ret); exec_ret.~ExecRet(); }
     };
   }

@@ -362,7 +362,7 @@ def exe_name(kind, R, tag=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ranks", type=int, nargs="*", default=[2, 8])
-    ap.add_argument("--only", default="phold_test,phold_bench,phold_t,phold_b,heat")
+    ap.add_argument("--only", default="phold_test,phold_bench,phold_t,phold_b,heat,zero_delay")
     ap.add_argument("--tags", default=",".join(PHOLD_T_CONFIGS))
     ap.add_argument("--baseline-ranks", type=int, nargs="*", default=[4, 16, 32, 64])
     ap.add_argument("--force", action="store_true")
@@ -386,6 +386,9 @@ def main():
             # example/heat (QSS actors), unchanged: QSS order 1 (its default) and order 0
             jobs.append((os.path.join(REF, "example/heat/heat.cxx"), exe_name("heat", R), ()))
             jobs.append((os.path.join(REF, "example/heat/heat.cxx"), exe_name("heat_q0", R), ("-DQSS_ORDER=0",)))
+        if "zero_delay" in only:
+            # tests/csrc/zero_delay.cxx: this repo's own test model (sends that keep the time stamp) on the reference runtime
+            jobs.append((os.path.join(os.path.dirname(HERE), "tests", "csrc", "zero_delay.cxx"), exe_name("zero_delay", R), ()))
         if "phold_b" in only:
             jobs.append((gen_phold_b(), exe_name("phold_b", R), (os.path.join(REF, "bench/util/report.cxx"),)))
         if "phold_t" in only:

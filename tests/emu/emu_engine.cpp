@@ -476,7 +476,7 @@ int deva_b200_digest(deva_b200_engine *e, uint64_t out[4]) {
 
 // ---- host-executed handlers: a host stand-in for the device pool of hostq.cuh (same contract) ----------------
 struct HqRec { uint64_t t, s, h; uint32_t lp; };
-struct deva_b200_hostq { std::vector<HqRec> recs; uint64_t cap; };
+struct deva_b200_hostq { std::vector<HqRec> recs, snap; uint64_t cap; bool has_snap = false; };
 int deva_b200_hostq_create(int32_t, uint64_t capacity, deva_b200_hostq **out) { *out = new deva_b200_hostq; (*out)->cap = capacity ? capacity : (1ull << 22); return 0; }
 void deva_b200_hostq_destroy(deva_b200_hostq *q) { delete q; }
 int deva_b200_hostq_push(deva_b200_hostq *q, uint64_t n, const uint64_t *time, const uint64_t *subtime, const uint32_t *lp, const uint64_t *handle) {
@@ -484,8 +484,8 @@ int deva_b200_hostq_push(deva_b200_hostq *q, uint64_t n, const uint64_t *time, c
   for (uint64_t i = 0; i < n; i++) q->recs.push_back({time[i], subtime[i], handle[i], lp[i]});
   return 0;
 }
-int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
-                            uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
+static int emu_hq_pop(deva_b200_hostq *q, bool by_key, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
+                      uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
   *n_out = 0; *gvt_out = ~0ull;
   if (pending_out) *pending_out = q->recs.size();
   if (q->recs.empty()) return 0;
@@ -493,14 +493,46 @@ int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, 
   for (auto &r : q->recs) tmin = std::min(tmin, r.t);
   *gvt_out = tmin;
   if (tmin >= t_end) return 0;
+  uint64_t smin = ~0ull;
+  for (auto &r : q->recs) if (r.t == tmin) smin = std::min(smin, r.s);
   std::vector<HqRec> sel, keep;
-  for (auto &r : q->recs) (r.t == tmin ? sel : keep).push_back(r);
+  for (auto &r : q->recs) (r.t == tmin && (!by_key || r.s == smin) ? sel : keep).push_back(r);
   if (sel.size() > max_n) return fail(DEVA_B200_ERR_CAPACITY, "hostq: too many events at one time stamp");
   std::sort(sel.begin(), sel.end(), [](const HqRec &a, const HqRec &b) { return a.lp != b.lp ? a.lp < b.lp : a.s != b.s ? a.s < b.s : a.h < b.h; });
   for (size_t i = 0; i < sel.size(); i++) { time[i] = sel[i].t; subtime[i] = sel[i].s; lp[i] = sel[i].lp; handle[i] = sel[i].h; }
   q->recs.swap(keep);
   *n_out = sel.size();
   if (pending_out) *pending_out = q->recs.size();
+  return 0;
+}
+
+int deva_b200_hostq_pop_min(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
+                            uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
+  return emu_hq_pop(q, false, t_end, max_n, time, subtime, lp, handle, n_out, gvt_out, pending_out);
+}
+int deva_b200_hostq_pop_min_key(deva_b200_hostq *q, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
+                                uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
+  return emu_hq_pop(q, true, t_end, max_n, time, subtime, lp, handle, n_out, gvt_out, pending_out);
+}
+int deva_b200_hostq_erase(deva_b200_hostq *q, uint64_t n, const uint64_t *handles, uint64_t *n_erased) {
+  std::vector<uint64_t> gone(handles, handles + n);
+  std::sort(gone.begin(), gone.end());
+  std::vector<HqRec> keep;
+  for (auto &r : q->recs) if (!std::binary_search(gone.begin(), gone.end(), r.h)) keep.push_back(r);
+  if (n_erased) *n_erased = q->recs.size() - keep.size();
+  q->recs.swap(keep);
+  return 0;
+}
+int deva_b200_hostq_snapshot(deva_b200_hostq *q) {
+  if (q->has_snap) return fail(DEVA_B200_ERR_STATE, "hostq: lingering snapshot");
+  q->snap = q->recs; q->has_snap = true;
+  return 0;
+}
+int deva_b200_hostq_rewind(deva_b200_hostq *q, int32_t do_rewind) {
+  if (!q->has_snap) return fail(DEVA_B200_ERR_STATE, "hostq: rewind without a snapshot");
+  q->has_snap = false;
+  if (do_rewind) q->recs = q->snap;
+  q->snap.clear();
   return 0;
 }
 

@@ -151,7 +151,7 @@ def _build_host_app(tmp_path, src, R, flags=()):
     emu_dir = os.path.join(ROOT, "tests", "emu", "_build")
     subprocess.check_call([
         "g++", "-std=c++14", "-O2", "-pthread", "-w", f"-DDEVA_THREAD_N={R}", "-DDEVA_WORLD=1", "-DDEVA_WORLD_THREADS=1",
-        "-DDEBUG=0", "-DNDEBUG=1", *flags, f"-I{ROOT}/include", f"{REF}/{src}", f"{ROOT}/devastator_b200/csrc/host_runtime.cpp",
+        "-DDEBUG=0", "-DNDEBUG=1", *flags, f"-I{ROOT}/include", os.path.join(REF, src), f"{ROOT}/devastator_b200/csrc/host_runtime.cpp",
         f"-L{emu_dir}", "-ldeva_b200_emu", f"-Wl,-rpath,{emu_dir}", "-o", exe])
     return exe
 
@@ -238,3 +238,56 @@ def test_reference_heat_source_on_gpu(kind, R):
     for tag, g in HEAT_GOLDEN.items():
         if g["kind"] == kind:
             check_heat_output(exe, tag)
+
+
+# ---- the host executor beyond "sends move time forward": rewindable drains, time stamps undone and redone ----------
+DEBUG_ON = ["-UDEBUG", "-UNDEBUG", "-DDEBUG=1"]
+with open(os.path.join(ROOT, "tests", "golden", "zero_delay_goldens.json")) as _f:
+    ZERO_DELAY_GOLDEN = json.load(_f)   # tests/csrc/zero_delay.cxx on the UNMODIFIED reference runtime (make_zero_delay_goldens.py)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+def test_reference_phold_test_source_host_handlers_emu(emu_api, tmp_path):
+    """test/phold.cxx, unchanged, WITHOUT a device model: its handlers run on the host, its rewindable drains in thirds
+    (pdes.cxx:710-739,1137-1229) go through the pool's snapshot; same goldens as the device-resident path."""
+    exe = _build_host_app(tmp_path, "test/phold.cxx", 2, DEBUG_ON)
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:]
+    check_phold_test_output(out.stdout)
+
+
+def check_zero_delay(exe):
+    for tag, g in ZERO_DELAY_GOLDEN.items():
+        out = subprocess.run([exe], env=dict(os.environ, DEVA_B200_HOSTQ_VERBOSE="1", **g["env"]), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert out.returncode == 0, out.stdout[-2000:]
+        lines = out.stdout.splitlines()
+        assert g["line"] in lines, (tag, out.stdout[-1000:])
+        m = re.search(r"executed (\d+), committed (\d+), time stamps undone and redone key by key (\d+)", out.stdout)
+        assert m, out.stdout
+        if tag in ("default", "thirds", "all_zero"):     # these cannot be run without undoing: the path under test was taken
+            assert int(m.group(3)) > 0 and int(m.group(1)) > int(m.group(2)), (tag, m.group(0))
+
+
+@pytest.mark.parametrize("R", [1, 4])
+def test_zero_delay_sends_host_handlers_emu(emu_api, tmp_path, R):
+    """Sends that keep the time stamp land behind events their cd has run: the open time stamp is undone (unexecute,
+    DEBUG checksums compared, children erased from the pool by handle) and redone key by key.  Executions, commit hooks
+    and counts equal the reference runtime's on the same source, rewindable drains included."""
+    check_zero_delay(_build_host_app(tmp_path, os.path.join(ROOT, "tests", "csrc", "zero_delay.cxx"), R, DEBUG_ON))
+
+
+@pytest.mark.gpu
+def test_reference_phold_test_source_host_handlers_on_gpu():
+    exe = os.path.join(BIN, "phold_test_host_R2")
+    assert os.path.exists(exe), "dropin/_bin missing: run __graft_entry__.build() where /root/reference exists"
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:]
+    check_phold_test_output(out.stdout)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R", [1, 4])
+def test_zero_delay_sends_host_handlers_on_gpu(R):
+    exe = os.path.join(BIN, f"zero_delay_R{R}")
+    assert os.path.exists(exe), "dropin/_bin missing: run __graft_entry__.build()"
+    check_zero_delay(exe)

@@ -56,3 +56,76 @@ def test_horizon_respects_t_end_and_capacity_is_loud(qapi):
     b = q.pop_min(room=4)
     assert sorted(b["handle"]) == [16, 24]
     q.close()
+
+
+def _drain_all(q, by_key=False, room=1 << 18):
+    out = []
+    while True:
+        b = q.pop_min(room=room, by_key=by_key)
+        if len(b["time"]) == 0:
+            return out
+        out.append(b)
+
+
+@pytest.mark.parametrize("n", [1, 777, 60000])
+def test_key_by_key_pops_follow_the_stamped_order(qapi, n):
+    """deva_b200_hostq_pop_min_key: one (time, subtime) pair per pop, pairs strictly increasing (pdes.hxx:936-941)"""
+    rng = np.random.default_rng(n + 1)
+    t = rng.integers(3, 9, n).astype(np.uint64); s = rng.integers(0, 40, n).astype(np.uint64)
+    s[rng.integers(0, n)] = np.uint64(2**64 - 1)                       # (the largest subtime is a legal one)
+    lp = rng.integers(0, 500, n).astype(np.uint32); h = np.arange(n, dtype=np.uint64) * 16 + 64
+    q = E.HostQueue(capacity=1 << 17, api=qapi)
+    q.push(t, s, lp, h)
+    last, seen = (-1, -1), []
+    for b in _drain_all(q, by_key=True):
+        key = (int(b["time"][0]), int(b["subtime"][0]))
+        assert key > last and (b["time"] == key[0]).all() and (b["subtime"] == key[1]).all()
+        assert (np.lexsort((b["handle"], b["lp"])) == np.arange(len(b["lp"]))).all()
+        last = key
+        seen.append(b["handle"])
+    assert np.array_equal(np.sort(np.concatenate(seen)), h)
+    q.close()
+
+
+@pytest.mark.parametrize("n,m", [(10, 3), (5000, 1234), (100000, 99999)])
+def test_erase_by_handle(qapi, n, m):
+    """deva_b200_hostq_erase: exactly the named events leave the pool (unknown handles are ignored), the rest still
+    comes back in order"""
+    rng = np.random.default_rng(n)
+    t = rng.integers(0, 50, n).astype(np.uint64); s = rng.integers(0, 9, n).astype(np.uint64)
+    lp = rng.integers(0, 64, n).astype(np.uint32); h = rng.permutation(n).astype(np.uint64) * 8 + 800
+    q = E.HostQueue(capacity=1 << 17, api=qapi)
+    q.push(t, s, lp, h)
+    gone = rng.choice(h, m, replace=False)
+    assert q.erase(np.concatenate([gone, np.array([1, 2, 3], dtype=np.uint64)])) == m
+    assert q.erase(gone) == 0
+    left = np.concatenate([b["handle"] for b in _drain_all(q)]) if m < n else np.zeros(0, np.uint64)
+    assert np.array_equal(np.sort(left), np.sort(np.setdiff1d(h, gone)))
+    q.close()
+
+
+def test_snapshot_and_rewind(qapi):
+    """rewindable drains: the pool as it was at the snapshot comes back on rewind(true); rewind(false) keeps the present"""
+    rng = np.random.default_rng(5)
+    n = 30000
+    t = rng.integers(0, 100, n).astype(np.uint64); s = rng.integers(0, 9, n).astype(np.uint64)
+    lp = rng.integers(0, 64, n).astype(np.uint32); h = np.arange(n, dtype=np.uint64) + 1
+    q = E.HostQueue(capacity=1 << 16, api=qapi)
+    q.push(t, s, lp, h)
+    q.snapshot()
+    with pytest.raises(E.EngineError):
+        q.snapshot()                                  # lingering snapshot
+    first = [q.pop_min(t_end=40, room=n) for _ in range(60)]
+    q.push([1000, 1001], [0, 0], [1, 2], [10**9, 10**9 + 1])
+    q.rewind(True)
+    again = [q.pop_min(t_end=40, room=n) for _ in range(60)]
+    for a, b in zip(first, again):
+        assert np.array_equal(a["handle"], b["handle"]) and a["gvt"] == b["gvt"] and a["pending"] == b["pending"]
+    with pytest.raises(E.EngineError):
+        q.rewind(False)                               # nothing to rewind
+    q.snapshot()
+    q.pop_min(room=n)
+    q.rewind(False)
+    rest = np.concatenate([b["handle"] for b in _drain_all(q)])
+    assert len(rest) == int((t > 40).sum()) and 10**9 not in rest
+    q.close()
