@@ -1537,6 +1537,21 @@ DEVA_HD void begin_drain(const TView &v, const TParams &tp, uint64_t t_end, cons
   open_epoch_snapshot(v);
 }
 
+// Root events are about to be placed into an EMPTY calendar that no drain has touched: pick the bucket width from their
+// density (n roots over `lps` LPs, time stamps root_tmin .. root_tmax of a sample) so that a bucket holds what the
+// lists are built for - the policy widens it once the events have spread out.  Otherwise a dense start (PHOLD: one
+// root per LP and tick) overflows the first bucket's lists and everything is re-bucketed before the first epoch.
+// Never widens; results do not depend on the width.
+DEVA_HD void plan_root_width(TCtl *c, unsigned long long n, unsigned long long lps, uint32_t occ_x16) {
+  if (c->fixed_shift || n == 0 || lps == 0 || c->root_tmin > c->root_tmax) return;
+  const unsigned long long span = c->root_tmax - c->root_tmin + 1;
+  // width w fits while w * (n / (lps * span)) <= occ / 16
+  const double per_tick = (double)n / ((double)lps * (double)span);
+  uint32_t s0 = 0;
+  while (s0 < c->shift && (double)(2ull << s0) * per_tick * 16.0 <= (double)occ_x16) s0++;
+  if (s0 < c->shift) { c->shift = c->want_shift = s0; c->win_m = c->want_m = 1; }
+}
+
 // drain exit: a tile evaluated in the (committed) last epochs takes its result as its state
 DEVA_HD void settle_tile(const TView &v, uint32_t t) {
   if (v.tev[t] != NEVER) { v.tcur[t] ^= 1u; v.tev[t] = NEVER; }

@@ -69,6 +69,8 @@ struct TileEngine {
   double drain_ms = 0, exec_ms = 0;
   std::atomic<int32_t> stop_req{0};
   bool has_rewind = false;
+  bool calendar_untouched = false;   // emptied (create / reset) and neither seeded, given roots nor drained since
+  bool root_plan = true;             // DEVA_B200_ROOT_PLAN=0: keep the learned / initial bucket width when roots arrive
   struct Snap { void *live, *copy; size_t bytes; };
   std::vector<Snap> snaps;
   TCtl snap_ctl;
@@ -101,6 +103,7 @@ struct TileEngine {
     v.lp_begin = c->lp_begin; v.lp_n = c->lp_n; v.n_gpus = c->n_gpus; v.gpu_rank = c->gpu_rank;
     v.lp_per_gpu = (c->lp_n + c->n_gpus - 1) / c->n_gpus;
     tp.rcap = env_u32("DEVA_B200_TILE_RCAP", 1280);
+    root_plan = env_u32("DEVA_B200_ROOT_PLAN", 1) != 0;
     if (tp.rcap > 65535) tp.rcap = 65535;   // (record indices are 16 bits)
     tp.pol_lo_pm = env_u32("DEVA_B200_POL_LO", 800);
     tp.pol_hi_pm = env_u32("DEVA_B200_POL_HI", 960);
@@ -170,6 +173,8 @@ struct TileEngine {
     hc.far_total = 0; hc.antis_pending = 0; hc.err = 0; hc.nondet = 0;
     hc.want_shift = hc.shift;
     for (int i = 0; i < MAX_GPUS; i++) hc.send_n[i] = 0;
+    hc.root_tmin = ~0ull; hc.root_tmax = 0;
+    calendar_untouched = true;
     return be.write_ctl(v, &hc);
   }
 
@@ -201,6 +206,7 @@ struct TileEngine {
   int seed(uint32_t k, int rootdiv, int ranks) {
     int rc;
     if ((rc = clear_calendar(true)) || (rc = init_states(1))) return rc;
+    calendar_untouched = false;
     const int R = ranks > 0 ? ranks : 1;
     const uint64_t per = (v.lp_n + R - 1) / R;
     if (!hc.fixed_shift && rootdiv && cfg.model != DEVA_B200_MODEL_PHOLD_BENCH) {
@@ -222,7 +228,11 @@ struct TileEngine {
   }
 
   int roots(uint64_t n, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload) {
-    int rc = be.k_roots(v, n, time, sub, lp, payload);
+    // the first roots of an empty calendar choose the bucket width from their density (one GPU: with several, every
+    // GPU would have to arrive at the same width from its own share of the roots)
+    const bool plan = calendar_untouched && cfg.n_gpus == 1 && !hc.fixed_shift && root_plan && n > 0;
+    calendar_untouched = false;
+    int rc = be.k_roots(v, n, time, sub, lp, payload, plan ? tp.pol_occ_x16 : 0u);
     launches++;
     if (rc) return rc;
     if ((rc = be.read_ctl(v, &hc))) return rc;
@@ -240,6 +250,7 @@ struct TileEngine {
     if (has_rewind) return tile_fail(DEVA_B200_ERR_STATE, "lingering rewind state: call deva_b200_rewind first (pdes.cxx:705-708)");
     if (cfg.n_gpus > 1 && !v.peer_cap) return tile_fail(DEVA_B200_ERR_STATE, "n_gpus > 1 but deva_b200_comm_init was not called");
     int rc;
+    calendar_untouched = false;
     be.timer_start(0);
     if (rewindable && (rc = snapshot())) return rc;
     if ((rc = be.read_ctl(v, &hc))) return rc;

@@ -398,6 +398,19 @@ __global__ void k_tile_seed(TView v, ModelParams mp, uint32_t k, int rootdiv, ui
   if (threadIdx.x == 0) bh_flush(v, bh);
 }
 
+// earliest / latest time stamp of (a sample of) the root events, and the bucket width they ask for (plan_root_width)
+__global__ void k_tile_roots_span(TView v, const uint64_t *time, uint32_t n) {
+  unsigned long long lo = ~0ull, hi = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { const unsigned long long t = time[i]; lo = t < lo ? t : lo; hi = t > hi ? t : hi; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&v.ctl->root_tmin, lo); atomicMax(&v.ctl->root_tmax, hi); }
+}
+__global__ void k_tile_roots_plan(TView v, unsigned long long n, uint32_t occ_x16) { plan_root_width(v.ctl, n, v.A, occ_x16); }
+
 __global__ void k_tile_roots(TView v, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload, uint32_t n) {
   Epoch ep = load_epoch(v.ctl);
   ep.in_epoch = 0;
@@ -612,7 +625,8 @@ struct CudaBE {
     TCU(cudaGetLastError());
     return 0;
   }
-  int k_roots(const TView &v, uint64_t n, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload) {
+  // plan_occ_x16 != 0: the calendar is empty and untouched - the bucket width is chosen from the first chunk's time stamps
+  int k_roots(const TView &v, uint64_t n, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload, uint32_t plan_occ_x16) {
     TCU(cudaSetDevice(device));
     if (n == 0) return 0;
     if (n > 0xffffffffull) return tile_fail(DEVA_B200_ERR_ARG, "too many roots in one call");
@@ -634,6 +648,10 @@ struct CudaBE {
       TCU(cudaEventRecord(cev[1], copy_stream));
       TCU(cudaStreamWaitEvent(stream, cev[1], 0));
       const unsigned g = (unsigned)std::min<uint64_t>((m + 255) / 256, 148 * 16);
+      if (o == 0 && plan_occ_x16) {
+        k_tile_roots_span<<<std::min(g, 148u * 4u), 256, 0, stream>>>(v, d_t, (uint32_t)m);
+        k_tile_roots_plan<<<1, 1, 0, stream>>>(v, n, plan_occ_x16);
+      }
       k_tile_roots<<<g, 256, 0, stream>>>(v, d_t + o, d_s + o, d_l + o, d_p + o, (uint32_t)m);
       TCU(cudaGetLastError());
     }

@@ -115,6 +115,8 @@ struct TCtl {
   uint32_t stepped, spad;          // the step kernel of this round did work (else the exchange kernel behind it is a no-op, too)
   PeerMsg agg;                     // job-wide sums of the last round
   unsigned long long g_exec0, g_commit0;
+  // ---- root events placed into an empty calendar: earliest / latest time stamp of a sample of them (plan_root_width)
+  unsigned long long root_tmin, root_tmax;
 #ifdef DEVA_TILE_PROF
   // phase clocks of the step kernel (thread 0 of every block, clock64 ticks summed over blocks; tools/tile_prof.py):
   // [0] header [1] load wait [2] flags [3] sort [4] run [5] flush [6] write back [7] tiles, [8] flush: classify, [9] flush: claims + others; [12] block lifetime (globaltimer ns),

@@ -73,7 +73,12 @@ struct HostBE {
     v.ctl->err |= err;
     return 0;
   }
-  int k_roots(const TView &v, uint64_t n, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload) {
+  int k_roots(const TView &v, uint64_t n, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload, uint32_t plan_occ_x16) {
+    if (plan_occ_x16) {      // (the kernel samples the first chunk of the columns)
+      const uint64_t m = std::min<uint64_t>(n, 1u << 21);
+      for (uint64_t i = 0; i < m; i++) { v.ctl->root_tmin = std::min<unsigned long long>(v.ctl->root_tmin, time[i]); v.ctl->root_tmax = std::max<unsigned long long>(v.ctl->root_tmax, time[i]); }
+      plan_root_width(v.ctl, n, v.A, plan_occ_x16);
+    }
     Epoch ep = load_epoch(v.ctl);
     ep.in_epoch = 0;
     uint32_t err = 0;

@@ -256,8 +256,10 @@ def test_reference_phold_test_source_host_handlers_emu(emu_api, tmp_path):
     check_phold_test_output(out.stdout)
 
 
-def check_zero_delay(exe):
+def check_zero_delay(exe, only=None):
     for tag, g in ZERO_DELAY_GOLDEN.items():
+        if only and tag not in only:
+            continue
         out = subprocess.run([exe], env=dict(os.environ, DEVA_B200_HOSTQ_VERBOSE="1", **g["env"]), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
         assert out.returncode == 0, out.stdout[-2000:]
         lines = out.stdout.splitlines()
@@ -290,4 +292,5 @@ def test_reference_phold_test_source_host_handlers_on_gpu():
 def test_zero_delay_sends_host_handlers_on_gpu(R):
     exe = os.path.join(BIN, f"zero_delay_R{R}")
     assert os.path.exists(exe), "dropin/_bin missing: run __graft_entry__.build()"
-    check_zero_delay(exe)
+    # (every key of an undone time stamp is a round trip to the device: the cases are split over the two rank counts)
+    check_zero_delay(exe, ("default", "all_zero_thirds", "one_ray") if R == 1 else ("thirds", "rare_zero", "all_zero"))

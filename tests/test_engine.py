@@ -131,6 +131,33 @@ def test_host_roots_and_state_equal_device_seeding(api):
     np.testing.assert_array_equal(E.phold_initial_state_np(E.MODEL_PHOLD_TEST, 5, 40), E.phold_initial_state(E.MODEL_PHOLD_TEST, 5, 40))
 
 
+def test_roots_into_an_empty_calendar_choose_the_bucket_width(api, engine_kind):
+    """Tile engine, adaptive window: the first roots of an empty calendar pick the bucket width from their density
+    (as device-side seeding does), a reset makes the calendar empty again, later roots keep the width; sparse roots keep
+    the default; the results are the oracle's either way."""
+    if engine_kind != "tile":
+        pytest.skip("the LP engine has no calendar")
+    A, K, P, LAM, END = 2048, 16, 0.1, 100.0, 200
+    o, ost = O.run(A, K, P, LAM, END)
+    eng = S.make(api, A, P=P, LAM=LAM, END=END, window=0)
+    w0 = eng.stats()["window_last"]
+    cols = E.phold_roots(E.MODEL_PHOLD_TEST, A, K, 0, A)
+    for rep in range(2):
+        eng.reset()
+        eng.set_state(E.phold_initial_state_np(E.MODEL_PHOLD_TEST, 0, A))
+        half = len(cols[0]) // 2
+        eng.root_events(*[c[:half] for c in cols])            # K roots per LP at times 0 .. K-1: one per LP and tick
+        w1 = eng.stats()["window_last"]
+        assert w1 < w0 and w1 <= 8, (w0, w1)                  # (half the roots: one per LP and two ticks -> 8; all of them -> 4)
+        eng.root_events(*[c[half:] for c in cols])
+        assert eng.stats()["window_last"] == w1
+        gvt = eng.drain()
+        S.check_against_oracle(eng, o, ost, gvt, rewound_factor=rep + 1)      # (the counters are cumulative since create)
+    eng.reset()
+    eng.root_events(np.array([5, 900], np.uint64), np.array([0, 1], np.uint64), np.array([0, 1], np.uint32), np.array([0, 1], np.uint32))
+    assert eng.stats()["window_last"] >= w1                   # two roots over 2048 LPs: nothing to narrow for
+
+
 # ---- edge cases --------------------------------------------------------------------------------
 def test_empty_simulation(api):
     eng = S.make(api, 16, P=0.5, LAM=10.0, END=100)
