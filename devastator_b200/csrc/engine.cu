@@ -1058,6 +1058,8 @@ struct deva_b200_hostq {
   uint64_t cap = 0, n = 0;            // records the pool holds (host copy of the count)
   hq::Cols pool[2], sel, out;         // the pool (two halves: compaction goes from one to the other), the horizon's records, sorted
   hq::Cols snap = {nullptr, nullptr, nullptr, nullptr}; uint64_t snap_n = 0; bool has_snap = false;   // rewindable drain: the pool as it was
+  unsigned char *small_res = nullptr, *h_small = nullptr; bool small_on = true;   // small pools: one block, one copy back (k_hq_pop_small)
+  bool stage_busy = false;            // a push's copies out of the pinned staging columns may still be in flight
   int cur = 0;
   uint32_t *idx = nullptr;
   hq::Ctl *ctl = nullptr, *h_ctl = nullptr;
@@ -1070,6 +1072,7 @@ static int hq_cols_alloc(hq::Cols &c, uint64_t n) {
 }
 static void hq_cols_free(hq::Cols &c) { cudaFree(c.t); cudaFree(c.s); cudaFree(c.h); cudaFree(c.lp); }
 static int hq_stage(deva_b200_hostq *q, uint64_t n) {
+  if (q->stage_busy) { CU(cudaStreamSynchronize(q->stream)); q->stage_busy = false; }
   if (n <= q->h_cap) return 0;
   if (q->h_t) { cudaFreeHost(q->h_t); cudaFreeHost(q->h_s); cudaFreeHost(q->h_h); cudaFreeHost(q->h_lp); }
   const uint64_t m = std::max<uint64_t>(n, 1u << 16);
@@ -1094,6 +1097,10 @@ int deva_b200_hostq_create(int32_t device, uint64_t capacity, deva_b200_hostq **
       cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) != cudaSuccess) { deva_b200_hostq_destroy(q); return fail(DEVA_B200_ERR_CUDA, "hostq allocation failed"); }
   cub::DeviceMergeSort::SortKeys(nullptr, q->tmp_bytes, q->idx, (int)q->cap, hq::ByLpSub{q->sel}, q->stream);
   if (cudaMalloc(&q->tmp, q->tmp_bytes ? q->tmp_bytes : 16) != cudaSuccess) { deva_b200_hostq_destroy(q); return fail(DEVA_B200_ERR_CUDA, "hostq allocation failed"); }
+  if (cudaMalloc((void **)&q->small_res, hq::SMALL_RESULT_BYTES) != cudaSuccess || cudaHostAlloc((void **)&q->h_small, hq::SMALL_RESULT_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+    deva_b200_hostq_destroy(q); return fail(DEVA_B200_ERR_CUDA, "hostq allocation failed");
+  }
+  if (const char *sm = getenv("DEVA_B200_HOSTQ_SMALL")) q->small_on = atoi(sm) != 0;
   *out = q;
   return 0;
 }
@@ -1103,7 +1110,8 @@ void deva_b200_hostq_destroy(deva_b200_hostq *q) {
   if (q->stream) cudaStreamSynchronize(q->stream);
   hq_cols_free(q->pool[0]); hq_cols_free(q->pool[1]); hq_cols_free(q->sel); hq_cols_free(q->out);
   if (q->snap.t) hq_cols_free(q->snap);
-  cudaFree(q->idx); cudaFree(q->ctl); cudaFree(q->tmp);
+  cudaFree(q->idx); cudaFree(q->ctl); cudaFree(q->tmp); cudaFree(q->small_res);
+  if (q->h_small) cudaFreeHost(q->h_small);
   if (q->h_ctl) cudaFreeHost(q->h_ctl);
   if (q->h_t) { cudaFreeHost(q->h_t); cudaFreeHost(q->h_s); cudaFreeHost(q->h_h); cudaFreeHost(q->h_lp); }
   if (q->stream) cudaStreamDestroy(q->stream);
@@ -1121,7 +1129,7 @@ int deva_b200_hostq_push(deva_b200_hostq *q, uint64_t n, const uint64_t *time, c
   hq::Cols &p = q->pool[q->cur];
   CU(cudaMemcpyAsync(p.t + q->n, q->h_t, n * 8, cudaMemcpyHostToDevice, q->stream)); CU(cudaMemcpyAsync(p.s + q->n, q->h_s, n * 8, cudaMemcpyHostToDevice, q->stream));
   CU(cudaMemcpyAsync(p.h + q->n, q->h_h, n * 8, cudaMemcpyHostToDevice, q->stream)); CU(cudaMemcpyAsync(p.lp + q->n, q->h_lp, n * 4, cudaMemcpyHostToDevice, q->stream));
-  CU(cudaStreamSynchronize(q->stream));   // (the staging buffers are reused by the next call)
+  q->stage_busy = true;   // (the staging columns are reused by the next call: it waits; the pop that normally follows synchronises anyway)
   q->n += n;
   return 0;
 }
@@ -1135,12 +1143,37 @@ static int hq_pop(deva_b200_hostq *q, bool by_key, uint64_t t_end, uint64_t max_
   const uint32_t n = (uint32_t)q->n;
   const unsigned grid = (unsigned)std::min<uint32_t>((n + 255) / 256, 148 * 8);
   hq::Cols &src = q->pool[q->cur], &keep = q->pool[q->cur ^ 1];
+  if (q->small_on && n <= hq::SMALL_POOL) {                 // one block does the whole pop; one copy brings the result back
+    const uint32_t stride = std::min<uint32_t>(n, hq::SMALL_SEL);
+    hq::k_hq_pop_small<<<1, hq::SMALL_THREADS, 0, q->stream>>>(src, n, by_key ? 1u : 0u, t_end, max_n, keep, q->small_res, stride);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(q->h_small, q->small_res, 32 + (size_t)stride * 28, cudaMemcpyDeviceToHost, q->stream));
+    CU(cudaStreamSynchronize(q->stream));
+    q->stage_busy = false;
+    const hq::SmallHdr *hdr = reinterpret_cast<const hq::SmallHdr *>(q->h_small);
+    *gvt_out = hdr->tmin;
+    if (hdr->status == hq::SMALL_NOTHING) return 0;
+    if (hdr->status == hq::SMALL_NO_ROOM) return fail(DEVA_B200_ERR_CAPACITY, "hostq: %u events at one time stamp, room for %llu", hdr->n_sel, (unsigned long long)max_n);
+    if (hdr->status == hq::SMALL_OK) {
+      const uint32_t ns = hdr->n_sel;
+      if (ns + hdr->n_keep != n) return fail(DEVA_B200_ERR_INVARIANT, "hostq: compaction lost records");
+      const unsigned char *p = q->h_small + 32;
+      memcpy(time, p, (size_t)ns * 8); memcpy(subtime, p + (size_t)stride * 8, (size_t)ns * 8); memcpy(handle, p + (size_t)stride * 16, (size_t)ns * 8);
+      memcpy(lp, p + (size_t)stride * 24, (size_t)ns * 4);
+      q->cur ^= 1; q->n = hdr->n_keep;
+      *n_out = ns;
+      if (pending_out) *pending_out = hdr->n_keep;
+      return 0;
+    }
+    // SMALL_TOO_MANY: more records at the horizon than the block sorts - nothing was moved, the general path takes over
+  }
   q->h_ctl->tmin = ~0ull; q->h_ctl->smin = ~0ull; q->h_ctl->n_sel = 0; q->h_ctl->n_keep = 0; q->h_ctl->by_key = by_key ? 1u : 0u; q->h_ctl->pad = 0;
   CU(cudaMemcpyAsync(q->ctl, q->h_ctl, sizeof(hq::Ctl), cudaMemcpyHostToDevice, q->stream));
   hq::k_hq_min<<<grid, 256, 0, q->stream>>>(src.t, n, q->ctl);                    // GVT: block + grid min-reduction
   if (by_key) hq::k_hq_min_sub<<<grid, 256, 0, q->stream>>>(src.t, src.s, n, q->ctl);   // (in stream order behind it)
   CU(cudaMemcpyAsync(q->h_ctl, q->ctl, sizeof(hq::Ctl), cudaMemcpyDeviceToHost, q->stream));
   CU(cudaStreamSynchronize(q->stream));
+  q->stage_busy = false;
   *gvt_out = q->h_ctl->tmin;
   if (q->h_ctl->tmin >= t_end) return 0;
   hq::k_hq_split<<<grid, 256, 0, q->stream>>>(src, n, q->ctl, q->sel, keep);      // the horizon's events out, the rest compacted

@@ -15,7 +15,9 @@ def qapi(request):
     return request.getfixturevalue("emu_api" if request.param == "emu" else "cuda_api")
 
 
-@pytest.mark.parametrize("n,times", [(1, 1), (1000, 7), (50000, 300), (200000, 3)])
+# (the device pool pops small pools - up to 4096 records, up to 1024 of them at the horizon - with one block: the cases
+#  cover that path, the general one, the hand-over between them and a horizon too large for the block)
+@pytest.mark.parametrize("n,times", [(1, 1), (1000, 7), (3000, 2), (4096, 4), (4097, 5), (50000, 300), (200000, 3)])
 def test_everything_comes_back_in_order(qapi, n, times):
     rng = np.random.default_rng(n)
     t = rng.integers(5, 5 + times, n).astype(np.uint64); s = rng.integers(0, 50, n).astype(np.uint64)
