@@ -69,6 +69,7 @@ struct TileEngine {
   double drain_ms = 0, exec_ms = 0;
   std::atomic<int32_t> stop_req{0};
   bool has_rewind = false;
+  uint32_t shift0 = 4;               // the adaptive window's initial bucket width (log2)
   bool calendar_untouched = false;   // emptied (create / reset) and neither seeded, given roots nor drained since
   bool root_plan = true;             // DEVA_B200_ROOT_PLAN=0: keep the learned / initial bucket width when roots arrive
   struct Snap { void *live, *copy; size_t bytes; };
@@ -149,6 +150,7 @@ struct TileEngine {
     else shift = env_u32("DEVA_B200_TILE_SHIFT0", 4);
     hc.shift = hc.want_shift = shift;
     hc.win_m = hc.want_m = 1;
+    shift0 = shift;
     hc.lp_total = c->lp_n;
     hc.far_min = ~0ull;
 #ifdef DEVA_TILE_PROF
@@ -158,7 +160,10 @@ struct TileEngine {
     return init_states(0);
   }
 
-  // empties every list and restarts the calendar at time 0 (statistics and the learned width stay)
+  // empties every list and restarts the calendar at time 0 (statistics stay).  The learned window does NOT: a new
+  // simulation starts from the initial width, as a new engine would - the width the last one ended with belongs to
+  // its last epochs (PHOLD thins out towards end_time and the policy widens 30-fold), and opening the next
+  // simulation's dense start with it piles a hundred generations of events into one window.
   int clear_calendar(bool keep_ctl_from_device) {
     int rc;
     if (keep_ctl_from_device && (rc = be.read_ctl(v, &hc))) return rc;
@@ -171,6 +176,7 @@ struct TileEngine {
     hc.workw = hc.workh = hc.n_heavy = 0; hc.in_epoch = 0; hc.partial = 0; hc.rc_n = 0; hc.rc_lo = 0; hc.ring_hi = NB; hc.work = hc.ticket = 0; hc.dirty_n[0] = hc.dirty_n[1] = 0; for (int i = 0; i < 2; i++) hc.sp_n[i] = hc.sp_start[i] = hc.sp_fresh[i] = 0; hc.ovf_flag = hc.need_rebase = 0;
     for (int i = 0; i < NB; i++) hc.btotal[i] = 0;
     hc.far_total = 0; hc.antis_pending = 0; hc.err = 0; hc.nondet = 0;
+    if (!hc.fixed_shift) { hc.shift = shift0; hc.win_m = hc.want_m = 1; }
     hc.want_shift = hc.shift;
     for (int i = 0; i < MAX_GPUS; i++) hc.send_n[i] = 0;
     hc.root_tmin = ~0ull; hc.root_tmax = 0;

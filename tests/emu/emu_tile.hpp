@@ -75,7 +75,9 @@ struct HostBE {
   }
   int k_roots(const TView &v, uint64_t n, const uint64_t *time, const uint64_t *sub, const uint32_t *lp, const uint32_t *payload, uint32_t plan_occ_x16) {
     if (plan_occ_x16) {      // (the kernel samples the first chunk of the columns)
-      const uint64_t m = std::min<uint64_t>(n, 1u << 21);
+      const char *rc = getenv("DEVA_B200_ROOT_CHUNK");
+      const uint64_t ch = rc ? strtoull(rc, nullptr, 10) : (1u << 21);
+      const uint64_t m = std::min<uint64_t>(n, ch ? ch : n);
       for (uint64_t i = 0; i < m; i++) { v.ctl->root_tmin = std::min<unsigned long long>(v.ctl->root_tmin, time[i]); v.ctl->root_tmax = std::max<unsigned long long>(v.ctl->root_tmax, time[i]); }
       plan_root_width(v.ctl, n, v.A, plan_occ_x16);
     }

@@ -158,6 +158,28 @@ def test_roots_into_an_empty_calendar_choose_the_bucket_width(api, engine_kind):
     assert eng.stats()["window_last"] >= w1                   # two roots over 2048 LPs: nothing to narrow for
 
 
+def test_next_simulation_does_not_inherit_the_last_window(api, engine_kind):
+    """A finished PHOLD run leaves the adaptive window 30 times wider than it started (the events thin out towards
+    end_time).  The next simulation on the same engine (reset = finalize + init) must not open its dense start with
+    that window - a hundred generations of events in one window used to end in a capacity refusal (found by the
+    randomised host-roots test: A=193, K=5, p=0.5, lambda=5, roots at time = ray)."""
+    if engine_kind != "tile":
+        pytest.skip("tile engine's calendar")
+    A, K, P, LAM, END = 193, 5, 0.5, 5.0, 264
+    o, ost = O.run(A, K, P, LAM, END, rootdiv=0)
+    cols = E.phold_roots(E.MODEL_PHOLD_TEST, A, K, 0, A, rootdiv=0)
+    eng = S.make(api, A, P=P, LAM=LAM, END=END, window=0)
+    for rep in range(3):
+        eng.reset()
+        eng.set_state(E.phold_initial_state_np(E.MODEL_PHOLD_TEST, 0, A))
+        eng.root_events(*cols)
+        assert eng.stats()["window_last"] <= 16
+        S.check_against_oracle(eng, o, ost, eng.drain(), rewound_factor=rep + 1)
+    for rep in range(2):                       # the same through device-side seeding
+        eng.seed_phold(K, 0, 1)
+        S.check_against_oracle(eng, o, ost, eng.drain(), rewound_factor=4 + rep)
+
+
 # ---- edge cases --------------------------------------------------------------------------------
 def test_empty_simulation(api):
     eng = S.make(api, 16, P=0.5, LAM=10.0, END=100)

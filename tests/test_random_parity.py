@@ -4,6 +4,7 @@ the fixed scenarios of test_engine.py).  Window width, capacities and the epoch 
 too: none of them may change a committed result."""
 import os
 
+import numpy as np
 import pytest
 from hypothesis import HealthCheck, assume, event, given, settings, strategies as st
 
@@ -208,3 +209,41 @@ def test_random_pause_rewind_resume_matches_oracle(emu_api, kind, A, K, P, LAM, 
     finally:
         eng.close()
         os.environ.pop("DEVA_B200_ENGINE", None)
+
+
+@settings(max_examples=int(os.environ.get("DEVA_TEST_EXAMPLES", 120)), deadline=None,
+          derandomize="DEVA_TEST_EXAMPLES" not in os.environ,
+          suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(A=st.integers(1, 700), K=st.integers(1, 8), P=st.sampled_from([0.0, 0.1, 0.5]), LAM=st.sampled_from([5.0, 40.0, 100.0]),
+       END=st.integers(0, 200), rootdiv=st.sampled_from([0, 1]), order=st.sampled_from(["lp", "time", "shuffled", "reversed"]),
+       chunk=st.sampled_from([0, 1, 7, 64, 1 << 21]), calls=st.sampled_from([1, 2, 5]), seed=st.integers(0, 1 << 30))
+def test_random_host_roots_match_oracle(emu_api, A, K, P, LAM, END, rootdiv, order, chunk, calls, seed):
+    """Host-inserted roots into an empty calendar (tile engine, adaptive window): the bucket width is planned from a
+    SAMPLE of the first call's time stamps (the first chunk the copy pipeline delivers), which may be far from
+    representative - sorted columns, a one-record sample, roots in several calls.  Whatever width comes out, the results
+    are the oracle's; a second simulation after a reset plans again."""
+    os.environ["DEVA_B200_ROOT_CHUNK"] = str(chunk)
+    try:
+        if rootdiv == 0:
+            END = END * 4
+        o, ost = O.run(A, K, P, LAM, END, rootdiv=rootdiv)
+        assume(o["deterministic"])
+        cols = S.E.phold_roots(S.E.MODEL_PHOLD_TEST, A, K, 0, A, rootdiv=rootdiv)
+        n = len(cols[0])
+        rng = np.random.default_rng(seed)
+        perm = {"lp": np.arange(n), "time": np.argsort(cols[0], kind="stable"), "shuffled": rng.permutation(n),
+                "reversed": np.argsort(cols[0], kind="stable")[::-1]}[order]
+        cols = [c[perm] for c in cols]
+        eng = S.make(emu_api, A, P=P, LAM=LAM, END=END, window=0)
+        for rep in range(2):
+            eng.reset()
+            eng.set_state(S.E.phold_initial_state_np(S.E.MODEL_PHOLD_TEST, 0, A))
+            cuts = [n * i // calls for i in range(calls + 1)]
+            for a, b in zip(cuts, cuts[1:]):
+                if b > a:
+                    eng.root_events(*[c[a:b] for c in cols])
+            gvt = eng.drain()
+            S.check_against_oracle(eng, o, ost, gvt, rewound_factor=rep + 1)
+        eng.close()
+    finally:
+        os.environ.pop("DEVA_B200_ROOT_CHUNK", None)
