@@ -71,7 +71,7 @@ struct TileEngine {
   bool has_rewind = false;
   uint32_t shift0 = 4;               // the adaptive window's initial bucket width (log2)
   bool calendar_untouched = false;   // emptied (create / reset) and neither seeded, given roots nor drained since
-  bool root_plan = true;             // DEVA_B200_ROOT_PLAN=0: keep the learned / initial bucket width when roots arrive
+  bool root_plan = true;             // DEVA_B200_ROOT_PLAN=0: keep the initial bucket width when roots arrive
   struct Snap { void *live, *copy; size_t bytes; };
   std::vector<Snap> snaps;
   TCtl snap_ctl;
