@@ -403,16 +403,23 @@ def ours(args):
             d2h = st_out.numel() * 8
             st_np, st_out_np, cols_np = st_host.numpy(), st_out.numpy(), [c.numpy() for c in cols]
 
-            def step_host():
-                eng.reset()
-                eng.set_state(st_np)
-                eng.root_events(*cols_np)
-                eng.drain()
-                eng.get_state(out=st_out_np)
+            parts = {"reset": 0.0, "h2d_state": 0.0, "h2d_roots_and_insert": 0.0, "drain": 0.0, "d2h_state": 0.0}
+
+            def step_host():      # (every call but reset returns synchronised: reset's device time shows under h2d_state)
+                t = [time.perf_counter()]
+                eng.reset(); t.append(time.perf_counter())
+                eng.set_state(st_np); t.append(time.perf_counter())
+                eng.root_events(*cols_np); t.append(time.perf_counter())
+                eng.drain(); t.append(time.perf_counter())
+                eng.get_state(out=st_out_np); t.append(time.perf_counter())
+                for k, a, b in zip(parts, t, t[1:]):
+                    parts[k] += b - a
 
             step_host()
             sync_all()
             se0 = eng.stats()
+            for k in parts:
+                parts[k] = 0.0
             t0 = time.perf_counter()
             for _ in range(K):
                 step_host()
@@ -429,7 +436,8 @@ def ours(args):
                 parity["golden"] = "MISMATCH"
                 parity["e2e_path"] = "host-buffer path and device-seeded path disagree"
             out["e2e"] = {"value": e2e_commits / e2e_s, "unit": "events/s", "h2d_bytes_per_step": h2d * N if N > 1 else h2d,
-                          "d2h_bytes_per_step": d2h * N if N > 1 else d2h, "steps": K, "bytes_are": "summed over the ranks"}
+                          "d2h_bytes_per_step": d2h * N if N > 1 else d2h, "steps": K, "bytes_are": "summed over the ranks",
+                          "ms_per_step_by_call": {k: round(1e3 * v / K, 3) for k, v in parts.items()}, "by_call_is": "rank 0's wall clock"}
         eng.close()
         del eng
         torch.cuda.empty_cache()
