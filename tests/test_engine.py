@@ -36,6 +36,8 @@ def test_phold_t_matches_oracle(api, cfg, window):
     s, o = S.run_phold_t(api, cfg["A"], cfg["K"], cfg["P"], cfg["LAM"], cfg["END"], window=window)
     if window == 1:   # dt >= 1: a 1-tick window is conservative, nothing may roll back
         assert s["rolled_back_n"] == 0 and s["executed_n"] == o["commits"]
+    if window == 100:  # ... and a window of a mean delay (or ten) speculates: the rollback / anti-message path was taken
+        assert s["rolled_back_n"] > 0 and s["anti_sent_n"] > 0 and s["executed_n"] > o["commits"]
 
 
 # ---- how early an epoch's follow-up passes stop never changes results either ----------------------
