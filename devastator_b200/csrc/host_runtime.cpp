@@ -350,8 +350,8 @@ namespace {
 void pdes::detail::no_device_model(const char *what) {
   std::stringstream ss;
   ss << what << ": this event type has no device-resident model (deva::pdes::device_model<E>). "
-        "Host-handler execution is not built; there is no CPU path. Force-include a model header "
-        "(include/devastator_b200/models/*.hxx) on the build line.";
+        "Event types with and without a device model cannot be mixed in one simulation; there is no CPU path. "
+        "Force-include a model header (include/devastator_b200/models/*.hxx) on the build line.";
   deva::assert_failed(__FILE__, __LINE__, ss.str().c_str());
   std::abort();
 }
@@ -694,6 +694,15 @@ void pdes::detail::root_event_raw(std::int32_t cd, std::uint64_t time, std::uint
 std::uint64_t pdes::drain(std::uint64_t t_end, bool rewindable) {   // pdes.cxx:695-1058
   deva::barrier();
   if(g_sim.host_mode) return host_drain(t_end, rewindable);
+  if(!g_sim.eng && !g_sim.model) {     // no root event was ever inserted: an empty simulation, GVT = ~0 (pdes.cxx:878-886)
+    if(deva::rank_me() == 0) {
+      DEVA_ASSERT_ALWAYS(!g_sim.has_rewind, "Lingering rewind state must be rewound via pdes::rewind(true|false) before calling pdes::drain().");
+      g_sim.has_rewind = rewindable;
+      g_sim.gvt = ~std::uint64_t(0);
+    }
+    deva::barrier();
+    return ~std::uint64_t(0);
+  }
   if(deva::rank_me() == 0) {
     DEVA_ASSERT_ALWAYS(!g_sim.has_rewind, "Lingering rewind state must be rewound via pdes::rewind(true|false) before calling pdes::drain().");
     if(!g_sim.eng) {
@@ -808,7 +817,7 @@ void pdes::rewind(bool do_rewind) {                   // pdes.cxx:1137-1229
     DEVA_ASSERT_ALWAYS(g_sim.has_rewind, "pdes::rewind without a rewindable drain");
     g_sim.has_rewind = false;
     for(auto *e: g_sim.engs) ck(deva_b200_rewind(e, do_rewind ? 1 : 0), "deva_b200_rewind");
-    if(do_rewind) download_state();       // fridge::restore: the host copies go back too
+    if(do_rewind && g_sim.eng) download_state();       // fridge::restore: the host copies go back too
   }
   deva::barrier();
 }

@@ -46,6 +46,9 @@ APPS = [
     # this repo's own test model whose sends may keep the time stamp (tests/csrc/zero_delay.cxx): time stamps undone and
     # redone key by key, erase by handle, rewindable drains; goldens from the same source on the reference runtime
     ("zero_delay", os.path.join(ROOT, "tests", "csrc", "zero_delay.cxx"), "", [], [1, 4], ["-UDEBUG", "-UNDEBUG", "-DDEBUG=1"]),
+    # this repo's own 2-D heat stencil with nearest-neighbour events (BASELINE config 5's wording; tests/csrc/heat2d.cxx):
+    # checks itself against a serial recomputation; goldens from the same source on the reference runtime
+    ("heat2d", os.path.join(ROOT, "tests", "csrc", "heat2d.cxx"), "", [], [1, 4]),
 ]
 
 

@@ -362,7 +362,7 @@ def exe_name(kind, R, tag=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ranks", type=int, nargs="*", default=[2, 8])
-    ap.add_argument("--only", default="phold_test,phold_bench,phold_t,phold_b,heat,zero_delay")
+    ap.add_argument("--only", default="phold_test,phold_bench,phold_t,phold_b,heat,zero_delay,heat2d")
     ap.add_argument("--tags", default=",".join(PHOLD_T_CONFIGS))
     ap.add_argument("--baseline-ranks", type=int, nargs="*", default=[4, 16, 32, 64])
     ap.add_argument("--force", action="store_true")
@@ -389,6 +389,9 @@ def main():
         if "zero_delay" in only:
             # tests/csrc/zero_delay.cxx: this repo's own test model (sends that keep the time stamp) on the reference runtime
             jobs.append((os.path.join(os.path.dirname(HERE), "tests", "csrc", "zero_delay.cxx"), exe_name("zero_delay", R), ()))
+        if "heat2d" in only:
+            # tests/csrc/heat2d.cxx: this repo's own 2-D heat stencil (BASELINE config 5's wording) on the reference runtime
+            jobs.append((os.path.join(os.path.dirname(HERE), "tests", "csrc", "heat2d.cxx"), exe_name("heat2d", R), ()))
         if "phold_b" in only:
             jobs.append((gen_phold_b(), exe_name("phold_b", R), (os.path.join(REF, "bench/util/report.cxx"),)))
         if "phold_t" in only:
