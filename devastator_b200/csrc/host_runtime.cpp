@@ -247,7 +247,16 @@ namespace {
     std::vector<Reg> regs;
     std::vector<Root> roots;
     // ---- host-executed handlers (Tier G)
-    std::vector<pdes::detail::host_event*> outbox;        // events this rank's thread created since the last push
+    // events this rank's thread created (or took back) since the last push, as the columns the pool takes: written
+    // where the event is made, so that rank 0 moves arrays and never walks other threads' event objects
+    struct Outbox {
+      std::vector<std::uint64_t> t, s, h; std::vector<std::uint32_t> lp;
+      void add(std::uint64_t time, std::uint64_t sub, std::uint32_t lp_global, pdes::detail::host_event *e) {
+        t.push_back(time); s.push_back(sub); lp.push_back(lp_global); h.push_back(std::uint64_t(reinterpret_cast<std::uintptr_t>(e)));
+      }
+      std::size_t size() const { return h.size(); }
+      void clear() { t.clear(); s.clear(); h.clear(); lp.clear(); }
+    } outbox;
     std::vector<std::function<void()>> task_outbox;       // bcast_procs functors created by this rank's handlers
     std::vector<std::uint64_t> seq;                        // per cd: next default subtime (pdes.cxx:221-225,332)
     std::vector<std::uint64_t> last_t, last_s;             // per cd: key of the event committed last (determinism flag, pdes.cxx:828-831)
@@ -280,19 +289,21 @@ namespace {
     std::uint64_t gvt = 0;
     std::mutex mu;
     // ---- host-executed handlers (Tier G): the device-resident pending pool and the batch at the horizon
-    bool host_mode = false;
+    std::atomic<bool> host_mode{false};
     deva_b200_hostq *hq = nullptr;
     std::vector<std::uint64_t> b_time, b_sub, b_handle;
     std::vector<std::uint32_t> b_lp;
     std::uint64_t b_n = 0;
     bool host_done = false;
     std::vector<std::function<void()>> tasks;              // bcast_procs functors every rank runs before the next batch
+    RankSide::Outbox push_cols;                            // the ranks' outboxes, concatenated for one push
     bool in_host_drain = false;
     bool hor_open = false;                                 // a time stamp has been executed (in part) and not committed
     std::uint64_t hor_time = 0;
     bool by_key = false;                                   // the open time stamp is being redone key by key
     bool close_horizon = false;                            // (rank 0 -> all) commit the open horizon before this batch
     std::atomic<bool> overtaken{false};                    // some rank met an event behind one its cd had executed
+    std::uint64_t horizon_no = 1;                          // bumped whenever a horizon closes (and at every drain's start)
     std::uint32_t drain_id = 0;
     bool host_rewindable = false, host_has_rewind = false;
     std::uint64_t undone_horizons = 0;
@@ -398,11 +409,26 @@ namespace {
   void adopt(RankSide &rs, pdes::detail::host_event *e) {
     e->drain_id = g_sim.drain_id;
     if(g_sim.in_host_drain) {
-      e->born_here = true;
+      e->born_in = g_sim.horizon_no;
       rs.born.push_back(e);
       if(g_sim.host_rewindable) rs.created.push_back(e);
     }
-    rs.outbox.push_back(e);
+    rs.outbox.add(e->time, e->subtime, std::uint32_t(g_sim.ranks[std::size_t(e->target_rank)].lp_begin + std::uint64_t(e->target_cd)), e);
+  }
+  // what every rank's outbox holds goes into the pool in one push
+  void push_outboxes() {
+    std::size_t n = 0;
+    for(auto &r: g_sim.ranks) n += r.outbox.size();
+    if(n == 0) return;
+    auto &p = g_sim.push_cols;
+    p.clear();
+    p.t.reserve(n); p.s.reserve(n); p.h.reserve(n); p.lp.reserve(n);
+    for(auto &r: g_sim.ranks) {
+      p.t.insert(p.t.end(), r.outbox.t.begin(), r.outbox.t.end()); p.s.insert(p.s.end(), r.outbox.s.begin(), r.outbox.s.end());
+      p.h.insert(p.h.end(), r.outbox.h.begin(), r.outbox.h.end()); p.lp.insert(p.lp.end(), r.outbox.lp.begin(), r.outbox.lp.end());
+      r.outbox.clear();
+    }
+    ck(deva_b200_hostq_push(g_sim.hq, n, p.t.data(), p.s.data(), p.lp.data(), p.h.data()), "deva_b200_hostq_push");
   }
 }
 void pdes::detail::host_root_event(std::int32_t cd, host_event *e) {
@@ -445,8 +471,10 @@ namespace {
   // from the pool by handle and destroyed; the events the horizon started from go back into the pool - and the time
   // stamp is redone key by key (deva_b200_hostq_pop_min_key), which cannot be overtaken.  Commit hooks run when the
   // horizon closes, in the order of execution.
+  // (an event made on one rank may be executed - and, here, destroyed - on another within the same horizon: closing a
+  //  horizon touches no event but the ones this rank executed; "born in the open horizon" is a number compare)
+  inline bool born_here(const pdes::detail::host_event *e) { return e->born_in == g_sim.horizon_no; }
   void commit_horizon(RankSide &rs) {
-    for(auto *e: rs.born) e->born_here = false;
     rs.born.clear();
     for(auto &p: rs.past) {
       pdes::event_context ec; ec.cd = p.cd; ec.time = p.time; ec.subtime = p.sub;
@@ -469,13 +497,20 @@ namespace {
       #endif
       rs.seq[std::size_t(p.cd)] = p.seq_before;
       rs.last_t[std::size_t(p.cd)] = p.prev_t; rs.last_s[std::size_t(p.cd)] = p.prev_s; rs.any_commit[std::size_t(p.cd)] = p.prev_any;
-      if(!p.e->born_here) rs.outbox.push_back(p.e);
+      if(!born_here(p.e)) rs.outbox.add(p.time, p.sub, std::uint32_t(rs.lp_begin + std::uint64_t(p.cd)), p.e);
     }
     rs.past.clear();
     rs.task_outbox.clear();
     deva::barrier();                 // nobody reads another rank's event objects after this
     // (b) the horizon's children: out of the outbox here, out of the pool on the device, then destroyed
-    rs.outbox.erase(std::remove_if(rs.outbox.begin(), rs.outbox.end(), [](pdes::detail::host_event *e) { return e->born_here; }), rs.outbox.end());
+    {
+      RankSide::Outbox kept;
+      for(std::size_t i = 0; i < rs.outbox.size(); i++) {
+        auto *e = reinterpret_cast<pdes::detail::host_event*>(std::uintptr_t(rs.outbox.h[i]));
+        if(!born_here(e)) kept.add(rs.outbox.t[i], rs.outbox.s[i], rs.outbox.lp[i], e);
+      }
+      rs.outbox = std::move(kept);
+    }
     deva::barrier();
     if(me == 0) {
       std::vector<std::uint64_t> gone;
@@ -489,7 +524,7 @@ namespace {
     }
     deva::barrier();
     for(auto *e: rs.born) {
-      e->born_here = false;
+      e->born_in = 0;
       if(!g_sim.host_rewindable) delete e; else e->done = true;      // (a rewindable drain destroys them at pdes::rewind)
     }
     rs.born.clear();
@@ -503,21 +538,14 @@ namespace {
       if(!g_sim.hq)
         ck(deva_b200_hostq_create(deva::os_env<int>("DEVA_B200_DEVICE", 0), deva::os_env<std::uint64_t>("DEVA_B200_HOSTQ_CAP", 0), &g_sim.hq), "deva_b200_hostq_create");
       if(rewindable) {   // the pool as it is once the events created since the last drain are in it
-        std::vector<std::uint64_t> t, sb, h; std::vector<std::uint32_t> lp;
-        for(auto &r: g_sim.ranks) {
-          for(auto *e: r.outbox) {
-            t.push_back(e->time); sb.push_back(e->subtime); h.push_back(std::uint64_t(reinterpret_cast<std::uintptr_t>(e)));
-            lp.push_back(std::uint32_t(g_sim.ranks[std::size_t(e->target_rank)].lp_begin + std::uint64_t(e->target_cd)));
-          }
-          r.outbox.clear();
-        }
-        if(!t.empty()) ck(deva_b200_hostq_push(g_sim.hq, t.size(), t.data(), sb.data(), lp.data(), h.data()), "deva_b200_hostq_push");
+        push_outboxes();
         ck(deva_b200_hostq_snapshot(g_sim.hq), "deva_b200_hostq_snapshot");
       }
       g_sim.drain_id += 1;
       g_sim.host_rewindable = rewindable; g_sim.host_has_rewind = rewindable;
       g_sim.in_host_drain = true;
       g_sim.hor_open = false; g_sim.by_key = false; g_sim.overtaken.store(false);
+      g_sim.horizon_no += 1;
     }
     if(rewindable) {     // fridge (pdes.cxx:710-739): the registered objects and the per-cd counters as they are now
       rs.fridge.resize(rs.regs.size());
@@ -530,15 +558,7 @@ namespace {
       deva::barrier();
       if(me == 0) {                                                     // (2)
         g_sim.tasks.clear();
-        std::vector<std::uint64_t> t, sb, h; std::vector<std::uint32_t> lp;
-        for(auto &r: g_sim.ranks) {
-          for(auto *e: r.outbox) {
-            t.push_back(e->time); sb.push_back(e->subtime); h.push_back(std::uint64_t(reinterpret_cast<std::uintptr_t>(e)));
-            lp.push_back(std::uint32_t(g_sim.ranks[std::size_t(e->target_rank)].lp_begin + std::uint64_t(e->target_cd)));
-          }
-          r.outbox.clear();
-        }
-        if(!t.empty()) ck(deva_b200_hostq_push(g_sim.hq, t.size(), t.data(), sb.data(), lp.data(), h.data()), "deva_b200_hostq_push");
+        push_outboxes();
         std::uint64_t pending = 0, gvt = 0;
         const std::size_t room = std::max<std::size_t>(g_sim.b_time.size(), std::size_t(1) << 16);
         g_sim.b_time.resize(room); g_sim.b_sub.resize(room); g_sim.b_handle.resize(room); g_sim.b_lp.resize(room);
@@ -554,7 +574,7 @@ namespace {
         g_sim.host_done = g_sim.b_n == 0;
         // the pool's minimum has left the open time stamp (or nothing is left below t_end): that horizon is final
         g_sim.close_horizon = g_sim.hor_open && (g_sim.host_done || g_sim.b_time[0] != g_sim.hor_time);
-        if(g_sim.close_horizon) { g_sim.hor_open = false; g_sim.by_key = false; }
+        if(g_sim.close_horizon) { g_sim.hor_open = false; g_sim.by_key = false; g_sim.horizon_no += 1; }
         if(!g_sim.host_done) { g_sim.hor_open = true; g_sim.hor_time = g_sim.b_time[0]; }
         // the batch is sorted by global cd: every rank's share is one contiguous range
         std::size_t i = 0;
@@ -585,7 +605,7 @@ namespace {
         if(older || g_sim.overtaken.load(std::memory_order_relaxed)) {    // the horizon will be undone: hand the rest of the slice back
           for(std::size_t j = i; j < rs.slice_hi; j++) {
             auto *r = reinterpret_cast<pdes::detail::host_event*>(std::uintptr_t(g_sim.b_handle[j]));
-            if(!r->born_here) rs.outbox.push_back(r);
+            if(!born_here(r)) rs.outbox.add(g_sim.b_time[j], g_sim.b_sub[j], g_sim.b_lp[j], r);
           }
           break;
         }
@@ -641,7 +661,10 @@ namespace {
       std::cerr << "deva_b200 host executor: executed " << ex << ", committed " << cm << ", time stamps undone and redone key by key " << g_sim.undone_horizons << std::endl;
     }
     g_sim.undone_horizons = 0;
-    for(auto &r: g_sim.ranks) { for(auto *e: r.outbox) delete e; r.outbox.clear(); r.task_outbox.clear(); }
+    for(auto &r: g_sim.ranks) {
+      for(auto h: r.outbox.h) delete reinterpret_cast<pdes::detail::host_event*>(std::uintptr_t(h));
+      r.outbox.clear(); r.task_outbox.clear();
+    }
     g_sim.tasks.clear();
     if(g_sim.hq) {
       std::vector<std::uint64_t> t(1 << 16), sb(1 << 16), h(1 << 16); std::vector<std::uint32_t> lp(1 << 16);

@@ -83,7 +83,8 @@ namespace pdes {
       std::uint64_t time = 0, subtime = 0;
       std::int32_t target_rank = 0, target_cd = 0;
       std::uint32_t drain_id = 0;        // the drain (or the root insertions before it) this object was created in
-      bool born_here = false;            // created inside the horizon that is open (not committed yet)
+      std::uint64_t born_in = 0;         // number of the horizon it was created in (a child of the OPEN horizon while that is
+                                         // the current number: nobody has to touch the object when the horizon closes)
       bool done = false;                 // executed and committed during a rewindable drain, kept until pdes::rewind
       std::uint64_t entry_checksum = 0;  // register_checksum_if_debug: the cd's checksum when execute was entered
       virtual ~host_event() {}
