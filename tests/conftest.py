@@ -17,7 +17,14 @@ def _newer(target, srcs):
     if not os.path.exists(target):
         return True
     t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in srcs)
+    if any(os.path.getmtime(s) > t for s in srcs):
+        return True
+    # a sanitizer build left behind by a debugging session cannot be loaded into python: rebuild it
+    try:
+        deps = subprocess.run(["ldd", target], capture_output=True, text=True).stdout
+    except OSError:
+        deps = ""
+    return any(x in deps for x in ("libasan", "libtsan", "libubsan"))
 
 
 @pytest.fixture(scope="session")
