@@ -30,7 +30,7 @@ using namespace deva_b200;
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
-static thread_local char g_err[512] = "";
+static thread_local char g_err[1280] = "";
 static int fail(int code, const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

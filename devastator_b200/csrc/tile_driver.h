@@ -29,17 +29,23 @@ namespace tl {
 int tile_fail(int code, const char *fmt, ...);   // sets deva_b200_last_error (defined by the library that includes this)
 
 inline const char *tile_err_text(uint32_t err) {
-  static thread_local char buf[512];
+  static thread_local char buf[1024];
+  size_t n = 0;
   buf[0] = 0;
-  if (err & ERR_ANTI_UNMATCHED) strcat(buf, "anti-message without matching event; ");
-  if (err & ERR_SEND_OVERFLOW) strcat(buf, "peer receive region overflowed (DEVA_B200_SEND_CAP_PER_LP); ");
-  if (err & ERR_NOT_OWNER) strcat(buf, "event addressed to an LP this engine does not own; ");
-  if (err & ERR_BELOW_GVT) strcat(buf, "record below GVT; ");
-  if (err & ERR_LATE_OVERFLOW) strcat(buf, "more in-window arrivals in one epoch than the late lists and the spill list hold: the window is far too wide for this model (DEVA_B200_TILE_CL / DEVA_B200_TILE_SPILL); ");
-  if (err & ERR_FAR_OVERFLOW) strcat(buf, "a tile's far list overflowed (DEVA_B200_TILE_CF / pq_cap); ");
-  if (err & ERR_TILE_OVERFLOW) strcat(buf, "a tile's bucket cannot hold its arrivals / a tile exceeds the rebin scratch (DEVA_B200_TILE_C); ");
-  if (err & ERR_LP_OVERFLOW) strcat(buf, "one LP holds more events in one window than a block's workspace (DEVA_B200_TILE_RCAP); ");
-  if (err & ERR_PEER_TIMEOUT) strcat(buf, "a peer GPU did not answer within the time-out; ");
+  auto add = [&](uint32_t bit, const char *text) {   // bounded: several capacity bits can be set by one launch
+    if (!(err & bit) || n + 1 >= sizeof buf) return;
+    const int w = snprintf(buf + n, sizeof buf - n, "%s; ", text);
+    if (w > 0) n = std::min(sizeof buf - 1, n + (size_t)w);
+  };
+  add(ERR_ANTI_UNMATCHED, "anti-message without matching event");
+  add(ERR_SEND_OVERFLOW, "peer receive region overflowed (DEVA_B200_SEND_CAP_PER_LP)");
+  add(ERR_NOT_OWNER, "event addressed to an LP this engine does not own");
+  add(ERR_BELOW_GVT, "record below GVT");
+  add(ERR_LATE_OVERFLOW, "more in-window arrivals in one epoch than the late lists and the spill list hold: the window is far too wide for this model (DEVA_B200_TILE_CL / DEVA_B200_TILE_SPILL)");
+  add(ERR_FAR_OVERFLOW, "a tile's far list overflowed (DEVA_B200_TILE_CF / pq_cap)");
+  add(ERR_TILE_OVERFLOW, "a tile's bucket cannot hold its arrivals / a tile exceeds the rebin scratch (DEVA_B200_TILE_C)");
+  add(ERR_LP_OVERFLOW, "one LP holds more events in one window than a block's workspace (DEVA_B200_TILE_RCAP)");
+  add(ERR_PEER_TIMEOUT, "a peer GPU did not answer within the time-out");
   return buf;
 }
 
