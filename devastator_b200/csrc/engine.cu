@@ -1135,7 +1135,7 @@ int deva_b200_hostq_push(deva_b200_hostq *q, uint64_t n, const uint64_t *time, c
 }
 static int hq_pop(deva_b200_hostq *q, bool by_key, uint64_t t_end, uint64_t max_n, uint64_t *time, uint64_t *subtime, uint32_t *lp, uint64_t *handle,
                   uint64_t *n_out, uint64_t *gvt_out, uint64_t *pending_out) {
-  if (!q || !n_out || !gvt_out) return fail(DEVA_B200_ERR_ARG, "null argument");
+  if (!q || !n_out || !gvt_out || (max_n && (!time || !subtime || !lp || !handle))) return fail(DEVA_B200_ERR_ARG, "null argument");
   *n_out = 0; *gvt_out = ~0ull;
   if (pending_out) *pending_out = q->n;
   if (q->n == 0) return 0;

@@ -36,7 +36,11 @@ def emu_api():
     csrc = os.path.join(ROOT, "devastator_b200", "csrc")
     srcs = [os.path.join(ROOT, "tests", "emu", "emu_engine.cpp"), os.path.join(ROOT, "include", "deva_b200.h")] + \
         [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h", ".inc"))]
-    if _newer(so, srcs):
+    # DEVA_EMU_LIB: a build of the same harness made elsewhere, e.g. with -fsanitize=address,undefined (then run pytest
+    # under LD_PRELOAD=$(gcc -print-file-name=libasan.so)); tools/emu_sanitized.sh does both
+    if os.environ.get("DEVA_EMU_LIB"):
+        so = os.environ["DEVA_EMU_LIB"]
+    elif _newer(so, srcs):
         os.makedirs(os.path.dirname(so), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-w",
                                srcs[0], "-o", so])
