@@ -153,8 +153,8 @@ void deva::assert_failed(const char *file, int line, const char *msg) {
   { std::lock_guard<std::mutex> l(g_io_mu); std::cerr << ss.str(); }
   std::abort();
 }
-deva::say::say() { ss << "[" << deva::rank_me() << "] "; }
-deva::say::~say() { ss << "\n"; std::lock_guard<std::mutex> l(g_io_mu); std::cerr << ss.str(); }
+deva::say::say() { line_ << "[" << deva::rank_me() << "] "; }
+deva::say::~say() { line_ << "\n"; std::lock_guard<std::mutex> l(g_io_mu); std::cerr << line_.str(); }
 
 deva::datarow deva::describe() {
   datarow ans;

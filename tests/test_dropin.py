@@ -294,3 +294,21 @@ def test_zero_delay_sends_host_handlers_on_gpu(R):
     assert os.path.exists(exe), "dropin/_bin missing: run __graft_entry__.build()"
     # (every key of an undone time stamp is a round trip to the device: the cases are split over the two rank counts)
     check_zero_delay(exe, ("default", "all_zero_thirds", "one_ray") if R == 1 else ("thirds", "rare_zero", "all_zero"))
+
+
+# ---- include/devastator/diagnostic.hxx: the assertion macros and deva::say as the applications use them ----------------
+@pytest.mark.parametrize("debug", [0, 1])
+def test_assert_macros_and_say(emu_api, tmp_path, debug):
+    """One- and two-argument DEVA_ASSERT / DEVA_ASSERT_ALWAYS, streamed messages with manipulators, the one-argument form
+    in an expression, DEVA_DEBUG_ONLY; a violated check prints the reference's block (diagnostic.cxx:34-63) and aborts."""
+    flags = DEBUG_ON if debug else []
+    exe = _build_host_app(tmp_path, os.path.join(ROOT, "tests", "csrc", "assert_probe.cxx"), 1, flags)
+    run = lambda case: subprocess.run([exe, str(case)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    ok = run(0)
+    assert ok.returncode == 0 and f"[0] evaluated={104 if debug else 2} y=7 hex=ff" in ok.stdout, ok.stdout
+    one = run(1)
+    assert one.returncode == -6, one.stdout                       # SIGABRT
+    assert re.search(r"ASSERT FAILED rank=0 at=\S*assert_probe\.cxx:\d+\n\nFailed condition: x == 0\n/{50}", one.stdout), one.stdout
+    two = run(2)
+    assert two.returncode == -6, two.stdout
+    assert "\n\nx is 41   7\nsecond line\n" in two.stdout and "Failed condition" not in two.stdout, two.stdout
